@@ -1,0 +1,516 @@
+// glf_api.cu — the C ABI (include/glfusion.h) and the host-side orchestration of one TPAVIModule forward/backward
+// (R/models/ours.py:845-917) as a fixed sequence of kernel launches on the caller's stream.  No allocation, no
+// synchronisation: the whole sequence is CUDA-graph capturable.
+//
+// mode='dot' is executed in its reassociated O(N C'^2) form, token-major throughout:
+//   fwd:  P=[Theta|Phi|G] = X Wcat^T + b         tcgen05 GEMM (x read once, three projections concatenated)
+//         M_b = Phi_b^T G_b / N                   tcgen05 GEMM, MN-major operands, split-K, fp32 red.add
+//         W'_b = W_z M_b^T                        small fp32 SIMT product (C x C' per sequence)
+//         U_b = Theta_b W'_b^T + b_z              tcgen05 GEMM + per-tile BatchNorm column statistics
+//         BN finalise, then  Z = LN(BN(U) + X)    HBM-bound fused epilogue
+//   bwd:  LN/BN backward (two HBM-bound passes), then six tcgen05 GEMMs (dTheta, dW', dPhi, dG, dWcat, dX) and two
+//         small fp32 products (dW_z, dM).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "glf_internal.h"
+
+namespace glf {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  return set_error(GLF_ERR_DEVICE, "%s: %s", what, cudaGetErrorString(e));
+}
+int check_device_sm100() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return check_cuda(e, "cudaGetDevice");
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10) return set_error(GLF_ERR_DEVICE, "libglf_sm100a needs an sm_100 device (Blackwell B200); found sm_%d%d and there is no fallback path", major, minor);
+  return 0;
+}
+
+namespace {
+
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base(reinterpret_cast<uint8_t*>(b)) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+struct Dims {
+  long long B, N, rows;
+  int C, Ci;
+  int tiles_seq;   // m-tiles per sequence (128 tokens)
+  int tiles_all;   // m-tiles over all rows
+  bool pack_x;     // x must be repacked to token-major bf16
+  bool pack_dz;
+  bool dot;
+};
+
+int make_dims(const glf_desc* d, Dims* o) {
+  if (d == nullptr) return set_error(GLF_ERR_INVALID, "null descriptor");
+  if (d->B <= 0 || d->T <= 0 || d->H <= 0 || d->W <= 0) return set_error(GLF_ERR_INVALID, "empty input (B,T,H,W must be > 0)");
+  if (d->C <= 0 || d->Ci <= 0 || d->C % 8 != 0 || d->Ci % 8 != 0)
+    return set_error(GLF_ERR_INVALID, "C and inter_channels must be positive multiples of 8 (got %d, %d)", d->C, d->Ci);
+  if (d->C > 2048) return set_error(GLF_ERR_INVALID, "C <= 2048 supported (got %d)", d->C);
+  if (d->mode != GLF_MODE_DOT && d->mode != GLF_MODE_EMBEDDED)
+    return set_error(GLF_ERR_UNSUPPORTED, "mode must be dot or embedded ('gaussian'/'concatenate' are not built by the reference network)");
+  if (d->mode == GLF_MODE_EMBEDDED && d->Ci != 128 && d->Ci != 64)
+    return set_error(GLF_ERR_UNSUPPORTED, "mode='embedded' supports inter_channels 64 or 128 (got %d)", d->Ci);
+  if (d->precision != GLF_PRECISION_BF16) return set_error(GLF_ERR_UNSUPPORTED, "only GLF_PRECISION_BF16 is implemented");
+  if (d->io_dtype != GLF_DTYPE_BF16 && d->io_dtype != GLF_DTYPE_F32) return set_error(GLF_ERR_INVALID, "bad io_dtype");
+  o->B = d->B;
+  o->N = static_cast<long long>(d->T) * d->H * d->W;
+  o->rows = o->B * o->N;
+  if (o->rows * static_cast<long long>(d->C) >= (1LL << 40)) return set_error(GLF_ERR_INVALID, "problem too large");
+  if (o->N > (1LL << 30)) return set_error(GLF_ERR_INVALID, "sequence too long");
+  o->C = d->C;
+  o->Ci = d->Ci;
+  o->tiles_seq = gemm_tiles_m(static_cast<int>(o->N));
+  o->tiles_all = gemm_tiles_m(static_cast<int>(o->rows > 0x7fffffff ? 0x7fffffff : o->rows));
+  if (o->rows > 0x7fffff00LL) return set_error(GLF_ERR_INVALID, "too many tokens");
+  o->pack_x = !(d->x_layout == GLF_LAYOUT_TOKEN && d->io_dtype == GLF_DTYPE_BF16);
+  if (d->x_layout == GLF_LAYOUT_TOKEN && d->io_dtype == GLF_DTYPE_F32 && o->rows * d->C > 0x7fffffffLL)
+    return set_error(GLF_ERR_INVALID, "token-major fp32 input too large for the cast kernel");
+  o->pack_dz = d->dz_layout != GLF_LAYOUT_TOKEN;
+  o->dot = d->mode == GLF_MODE_DOT;
+  return 0;
+}
+
+struct Saved {
+  bf16 *xtok, *P, *Y, *U, *Wp, *WpT, *wcat, *wcatT, *wz, *wzT;
+  float *lse, *M, *bcat, *bn_mean, *bn_rstd, *bn_a, *bn_b, *ln_mu, *ln_r;
+};
+size_t carve_saved(const Dims& m, void* base, Saved* s) {
+  Carver c(base);
+  const size_t rows = m.rows, C = m.C, Ci = m.Ci, B = m.B;
+  s->xtok = m.pack_x ? c.take<bf16>(rows * C) : nullptr;
+  s->P = c.take<bf16>(rows * 3 * Ci);
+  s->U = c.take<bf16>(rows * C);
+  if (m.dot) {
+    s->Y = nullptr; s->lse = nullptr;
+    s->M = c.take<float>(B * Ci * Ci);
+    s->Wp = c.take<bf16>(B * C * Ci);
+    s->WpT = c.take<bf16>(B * Ci * C);
+  } else {
+    s->Y = c.take<bf16>(rows * Ci);
+    s->lse = c.take<float>(rows);
+    s->M = nullptr; s->Wp = nullptr; s->WpT = nullptr;
+  }
+  s->wcat = c.take<bf16>(3 * Ci * C);
+  s->wcatT = c.take<bf16>(3 * Ci * C);
+  s->bcat = c.take<float>(3 * Ci);
+  s->wz = c.take<bf16>(C * Ci);
+  s->wzT = c.take<bf16>(C * Ci);
+  s->bn_mean = c.take<float>(C);
+  s->bn_rstd = c.take<float>(C);
+  s->bn_a = c.take<float>(C);
+  s->bn_b = c.take<float>(C);
+  s->ln_mu = c.take<float>(rows);
+  s->ln_r = c.take<float>(rows);
+  return (c.off + 255) & ~static_cast<size_t>(255);
+}
+
+struct WsFwd { float* colstats; void* saved_fallback; };
+size_t carve_ws_fwd(const Dims& m, void* base, WsFwd* w, size_t saved_bytes) {
+  Carver c(base);
+  const size_t np = m.dot ? static_cast<size_t>(m.B) * m.tiles_seq : static_cast<size_t>(m.tiles_all);
+  w->colstats = c.take<float>(np * 2 * m.C);
+  w->saved_fallback = c.take<uint8_t>(saved_bytes);  // used when the caller passes saved == NULL (inference)
+  return (c.off + 255) & ~static_cast<size_t>(255);
+}
+
+struct WsBwd {
+  bf16 *dztok, *dV, *dU, *dP, *dY, *dxtok, *dM, *dMT;
+  float *dWp, *part_ln, *k1, *k2, *k3, *cs_t, *cs_p, *cs_g, *dwcat, *delta;
+};
+size_t carve_ws_bwd(const glf_desc* d, const Dims& m, void* base, WsBwd* w) {
+  Carver c(base);
+  const size_t rows = m.rows, C = m.C, Ci = m.Ci, B = m.B;
+  w->dztok = m.pack_dz ? c.take<bf16>(rows * C) : nullptr;
+  w->dV = c.take<bf16>(rows * C);
+  w->dU = d->bn_layer ? c.take<bf16>(rows * C) : nullptr;
+  w->dP = c.take<bf16>(rows * 3 * Ci);
+  w->dxtok = m.pack_x ? c.take<bf16>(rows * C) : nullptr;
+  if (m.dot) {
+    w->dY = nullptr; w->delta = nullptr;
+    w->dWp = c.take<float>(B * C * Ci);
+    w->dM = c.take<bf16>(B * Ci * Ci);
+    w->dMT = c.take<bf16>(B * Ci * Ci);
+  } else {
+    w->dY = c.take<bf16>(rows * Ci);
+    w->delta = c.take<float>(rows);
+    w->dWp = nullptr; w->dM = nullptr; w->dMT = nullptr;
+  }
+  w->part_ln = c.take<float>(static_cast<size_t>(bn_res_ln_bwd_blocks(m.rows, m.C)) * 4 * C);
+  w->k1 = c.take<float>(C);
+  w->k2 = c.take<float>(C);
+  w->k3 = c.take<float>(C);
+  const size_t np = m.dot ? B * m.tiles_seq : static_cast<size_t>(m.tiles_all);
+  w->cs_t = c.take<float>(np * 2 * Ci);
+  w->cs_p = c.take<float>(np * 2 * Ci);
+  w->cs_g = c.take<float>(np * 2 * Ci);
+  w->dwcat = c.take<float>(3 * Ci * C);
+  return (c.off + 255) & ~static_cast<size_t>(255);
+}
+
+int pick_split(long long tiles, int K) {
+  const int kb = (K + 63) / 64;
+  long long s = (2 * 148 + tiles - 1) / tiles;
+  if (s < 1) s = 1;
+  if (s > kb) s = kb;
+  return static_cast<int>(s);
+}
+
+GemmOperand opnd(const void* p, int mn, long long ld, long long bs) {
+  GemmOperand o;
+  o.ptr = p; o.mn_major = mn; o.ld = ld; o.batch_stride = bs;
+  return o;
+}
+
+#define GLF_TRY(expr)        \
+  do {                       \
+    int rc__ = (expr);       \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+int check_ptr(const void* p, const char* name) {
+  if (p == nullptr) return set_error(GLF_ERR_INVALID, "%s is NULL", name);
+  if ((reinterpret_cast<uintptr_t>(p) & 15) != 0) return set_error(GLF_ERR_INVALID, "%s must be 16-byte aligned", name);
+  return 0;
+}
+
+}  // namespace
+}  // namespace glf
+
+using namespace glf;
+
+extern "C" {
+
+GLF_API int glf_version(void) { return GLF_VERSION; }
+GLF_API const char* glf_last_error(void) { return g_err; }
+
+GLF_API int glf_tpavi_sizes(const glf_desc* d, glf_sizes* out) {
+  Dims m;
+  GLF_TRY(make_dims(d, &m));
+  if (out == nullptr) return set_error(GLF_ERR_INVALID, "out is NULL");
+  Saved s; WsFwd wf; WsBwd wb;
+  out->saved_bytes = carve_saved(m, nullptr, &s);
+  out->ws_fwd_bytes = carve_ws_fwd(m, nullptr, &wf, out->saved_bytes);
+  out->ws_bwd_bytes = carve_ws_bwd(d, m, nullptr, &wb);
+  return 0;
+}
+
+GLF_API int glf_tpavi_fwd(const glf_desc* d, const void* x, const glf_weights* w, void* z, void* saved, void* ws,
+                  glf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  Dims m;
+  GLF_TRY(make_dims(d, &m));
+  GLF_TRY(check_device_sm100());
+  GLF_TRY(check_ptr(x, "x"));
+  GLF_TRY(check_ptr(z, "z"));
+  GLF_TRY(check_ptr(ws, "ws"));
+  if (w == nullptr) return set_error(GLF_ERR_INVALID, "weights is NULL");
+  if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0 || (saved && (reinterpret_cast<uintptr_t>(saved) & 255) != 0))
+    return set_error(GLF_ERR_WORKSPACE, "saved/ws blobs must be 256-byte aligned");
+  Saved s; WsFwd wf;
+  const size_t saved_bytes = carve_saved(m, nullptr, &s);
+  carve_ws_fwd(m, ws, &wf, saved_bytes);
+  carve_saved(m, saved ? saved : wf.saved_fallback, &s);
+  const int C = m.C, Ci = m.Ci;
+  const int N = static_cast<int>(m.N), rows = static_cast<int>(m.rows), B = static_cast<int>(m.B);
+
+  GLF_TRY(prep_weights(w, C, Ci, s.wcat, s.wcatT, s.bcat, s.wz, s.wzT, stream));
+  const bf16* X = reinterpret_cast<const bf16*>(x);
+  if (m.pack_x) {
+    if (d->x_layout == GLF_LAYOUT_NCTHW)
+      GLF_TRY(transpose_cast(x, s.xtok, B, C, N, d->io_dtype, GLF_DTYPE_BF16, stream));
+    else
+      GLF_TRY(transpose_cast(x, s.xtok, 1, 1, static_cast<int>(m.rows * C), d->io_dtype, GLF_DTYPE_BF16, stream));  // cast only
+    X = s.xtok;
+  }
+  {  // P = X Wcat^T + bcat
+    GemmArgs g;
+    g.A = opnd(X, 0, C, 0);
+    g.B = opnd(s.wcat, 0, C, 0);
+    g.M = rows; g.N = 3 * Ci; g.K = C;
+    g.bias = s.bcat;
+    g.D = s.P; g.ldd = 3 * Ci;
+    GLF_TRY(gemm(g, stream));
+  }
+  int np = 0;
+  if (m.dot) {
+    GLF_TRY(check_cuda(cudaMemsetAsync(s.M, 0, sizeof(float) * B * Ci * Ci, stream), "memset M"));
+    {  // M_b[i,j] = sum_n Phi[n,i] G[n,j] / N
+      GemmArgs g;
+      g.A = opnd(s.P + Ci, 1, 3 * Ci, static_cast<long long>(N) * 3 * Ci);
+      g.B = opnd(s.P + 2 * Ci, 1, 3 * Ci, static_cast<long long>(N) * 3 * Ci);
+      g.M = Ci; g.N = Ci; g.K = N; g.batch = B;
+      g.alpha = 1.f / static_cast<float>(N);
+      g.out_kind = 2;
+      g.D = s.M; g.ldd = Ci; g.strideD = static_cast<long long>(Ci) * Ci;
+      g.split_k = pick_split(static_cast<long long>(B) * ((Ci + 127) / 128) * ((Ci + 127) / 128), N);
+      GLF_TRY(gemm(g, stream));
+    }
+    // W'_b[c,i] = sum_j Wz[c,j] M_b[i,j]
+    GLF_TRY(small_gemm(w->wz_w, Ci, 1, 0, 0, s.M, 1, Ci, static_cast<long long>(Ci) * Ci, 0, B, 1, C, Ci, Ci, 1.f,
+                       nullptr, s.Wp, s.WpT, stream));
+    {  // U_b = Theta_b W'_b^T + bz   (+ BatchNorm column statistics)
+      GemmArgs g;
+      g.A = opnd(s.P, 0, 3 * Ci, static_cast<long long>(N) * 3 * Ci);
+      g.B = opnd(s.Wp, 0, Ci, static_cast<long long>(C) * Ci);
+      g.M = N; g.N = C; g.K = Ci; g.batch = B;
+      g.bias = w->wz_b;
+      g.D = s.U; g.ldd = C; g.strideD = static_cast<long long>(N) * C;
+      g.colstats = (d->training && d->bn_layer) ? wf.colstats : nullptr;
+      GLF_TRY(gemm(g, stream));
+    }
+    np = B * m.tiles_seq;
+  } else {
+    GLF_TRY(flash_fwd(s.P, s.Y, s.lse, B, N, Ci, stream));
+    {  // U = Y Wz^T + bz
+      GemmArgs g;
+      g.A = opnd(s.Y, 0, Ci, 0);
+      g.B = opnd(s.wz, 0, Ci, 0);
+      g.M = rows; g.N = C; g.K = Ci;
+      g.bias = w->wz_b;
+      g.D = s.U; g.ldd = C;
+      g.colstats = (d->training && d->bn_layer) ? wf.colstats : nullptr;
+      GLF_TRY(gemm(g, stream));
+    }
+    np = m.tiles_all;
+  }
+  GLF_TRY(bn_finalize(wf.colstats, np, C, static_cast<double>(m.rows), d, w, s.bn_mean, s.bn_rstd, s.bn_a, s.bn_b,
+                      stream));
+  GLF_TRY(bn_res_ln_fwd(s.U, X, s.bn_a, s.bn_b, w->ln_w, w->ln_b, z, d->io_dtype, s.ln_mu, s.ln_r, m.rows, C,
+                        d->eps_ln, d->accumulate, stream));
+  return 0;
+}
+
+GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, const glf_weights* w, const void* saved, void* dx,
+                  const glf_grads* g_, void* ws, glf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  Dims m;
+  GLF_TRY(make_dims(d, &m));
+  GLF_TRY(check_device_sm100());
+  GLF_TRY(check_ptr(dz, "dz"));
+  GLF_TRY(check_ptr(x, "x"));
+  GLF_TRY(check_ptr(dx, "dx"));
+  GLF_TRY(check_ptr(saved, "saved"));
+  GLF_TRY(check_ptr(ws, "ws"));
+  if (w == nullptr || g_ == nullptr) return set_error(GLF_ERR_INVALID, "weights/grads is NULL");
+  if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0 || (reinterpret_cast<uintptr_t>(saved) & 255) != 0)
+    return set_error(GLF_ERR_WORKSPACE, "saved/ws blobs must be 256-byte aligned");
+  Saved s; WsBwd wb;
+  carve_saved(m, const_cast<void*>(saved), &s);
+  carve_ws_bwd(d, m, ws, &wb);
+  const int C = m.C, Ci = m.Ci;
+  const int N = static_cast<int>(m.N), rows = static_cast<int>(m.rows), B = static_cast<int>(m.B);
+  const bf16* X = m.pack_x ? s.xtok : reinterpret_cast<const bf16*>(x);
+  const long long seqP = static_cast<long long>(N) * 3 * Ci;
+
+  const void* dZ = dz;
+  int dz_dtype = d->io_dtype;
+  if (m.pack_dz) {
+    GLF_TRY(transpose_cast(dz, wb.dztok, B, C, N, d->io_dtype, GLF_DTYPE_BF16, stream));
+    dZ = wb.dztok;
+    dz_dtype = GLF_DTYPE_BF16;
+  }
+  const int nb = bn_res_ln_bwd_blocks(m.rows, C);
+  GLF_TRY(bn_res_ln_bwd(dZ, dz_dtype, s.U, X, s.bn_a, s.bn_b, s.bn_mean, s.bn_rstd, w->ln_w, s.ln_mu, s.ln_r, wb.dV,
+                        wb.part_ln, m.rows, C, stream));
+  GLF_TRY(bn_bwd_finalize(wb.part_ln, nb, C, static_cast<double>(m.rows), d, w, s.bn_mean, s.bn_rstd, g_, wb.k1, wb.k2,
+                          wb.k3, stream));
+  const bf16* dU = wb.dV;
+  if (d->bn_layer) {
+    GLF_TRY(bn_bwd_apply(wb.dV, s.U, wb.k1, wb.k2, wb.k3, wb.dU, m.rows, C, stream));
+    dU = wb.dU;
+  }
+  int np = 0;
+  if (m.dot) {
+    {  // dTheta_b = dU_b W'_b
+      GemmArgs g;
+      g.A = opnd(dU, 0, C, static_cast<long long>(N) * C);
+      g.B = opnd(s.WpT, 0, C, static_cast<long long>(Ci) * C);
+      g.M = N; g.N = Ci; g.K = C; g.batch = B;
+      g.D = wb.dP; g.ldd = 3 * Ci; g.strideD = seqP;
+      g.colstats = wb.cs_t;
+      GLF_TRY(gemm(g, stream));
+    }
+    GLF_TRY(check_cuda(cudaMemsetAsync(wb.dWp, 0, sizeof(float) * B * C * Ci, stream), "memset dW'"));
+    {  // dW'_b[c,i] = sum_n dU[n,c] Theta[n,i]
+      GemmArgs g;
+      g.A = opnd(dU, 1, C, static_cast<long long>(N) * C);
+      g.B = opnd(s.P, 1, 3 * Ci, seqP);
+      g.M = C; g.N = Ci; g.K = N; g.batch = B;
+      g.out_kind = 2;
+      g.D = wb.dWp; g.ldd = Ci; g.strideD = static_cast<long long>(C) * Ci;
+      g.split_k = pick_split(static_cast<long long>(B) * ((C + 127) / 128) * ((Ci + 127) / 128), N);
+      GLF_TRY(gemm(g, stream));
+    }
+    // dWz[c,j] = sum_b sum_i dW'_b[c,i] M_b[i,j]
+    GLF_TRY(small_gemm(wb.dWp, Ci, 1, 0, static_cast<long long>(C) * Ci, s.M, Ci, 1, 0, static_cast<long long>(Ci) * Ci,
+                       1, B, C, Ci, Ci, 1.f, g_->wz_w, nullptr, nullptr, stream));
+    // dM_b[i,j] = sum_c dW'_b[c,i] Wz[c,j]
+    GLF_TRY(small_gemm(wb.dWp, 1, Ci, static_cast<long long>(C) * Ci, 0, w->wz_w, Ci, 1, 0, 0, B, 1, Ci, Ci, C, 1.f,
+                       nullptr, wb.dM, wb.dMT, stream));
+    {  // dPhi_b = G_b dM_b^T / N
+      GemmArgs g;
+      g.A = opnd(s.P + 2 * Ci, 0, 3 * Ci, seqP);
+      g.B = opnd(wb.dM, 0, Ci, static_cast<long long>(Ci) * Ci);
+      g.M = N; g.N = Ci; g.K = Ci; g.batch = B;
+      g.alpha = 1.f / static_cast<float>(N);
+      g.D = wb.dP + Ci; g.ldd = 3 * Ci; g.strideD = seqP;
+      g.colstats = wb.cs_p;
+      GLF_TRY(gemm(g, stream));
+    }
+    {  // dG_b = Phi_b dM_b / N
+      GemmArgs g;
+      g.A = opnd(s.P + Ci, 0, 3 * Ci, seqP);
+      g.B = opnd(wb.dMT, 0, Ci, static_cast<long long>(Ci) * Ci);
+      g.M = N; g.N = Ci; g.K = Ci; g.batch = B;
+      g.alpha = 1.f / static_cast<float>(N);
+      g.D = wb.dP + 2 * Ci; g.ldd = 3 * Ci; g.strideD = seqP;
+      g.colstats = wb.cs_g;
+      GLF_TRY(gemm(g, stream));
+    }
+    np = B * m.tiles_seq;
+  } else {
+    {  // dY = dU Wz
+      GemmArgs g;
+      g.A = opnd(dU, 0, C, 0);
+      g.B = opnd(s.wzT, 0, C, 0);
+      g.M = rows; g.N = Ci; g.K = C;
+      g.D = wb.dY; g.ldd = Ci;
+      GLF_TRY(gemm(g, stream));
+    }
+    GLF_TRY(check_cuda(cudaMemsetAsync(g_->wz_w, 0, sizeof(float) * C * Ci, stream), "memset dWz"));
+    {  // dWz[c,j] = sum_n dU[n,c] Y[n,j]
+      GemmArgs g;
+      g.A = opnd(dU, 1, C, 0);
+      g.B = opnd(s.Y, 1, Ci, 0);
+      g.M = C; g.N = Ci; g.K = rows;
+      g.out_kind = 2;
+      g.D = g_->wz_w; g.ldd = Ci;
+      g.split_k = pick_split(static_cast<long long>((C + 127) / 128) * ((Ci + 127) / 128), rows);
+      GLF_TRY(gemm(g, stream));
+    }
+    GLF_TRY(flash_bwd(s.P, s.Y, wb.dY, s.lse, wb.dP, wb.delta, B, N, Ci, stream));
+    np = 0;
+  }
+  GLF_TRY(check_cuda(cudaMemsetAsync(wb.dwcat, 0, sizeof(float) * 3 * Ci * C, stream), "memset dWcat"));
+  {  // dWcat[r,c] = sum_n dP[n,r] X[n,c]
+    GemmArgs g;
+    g.A = opnd(wb.dP, 1, 3 * Ci, 0);
+    g.B = opnd(X, 1, C, 0);
+    g.M = 3 * Ci; g.N = C; g.K = rows;
+    g.out_kind = 2;
+    g.D = wb.dwcat; g.ldd = C;
+    g.split_k = pick_split(static_cast<long long>((3 * Ci + 127) / 128) * ((C + 127) / 128), rows);
+    GLF_TRY(gemm(g, stream));
+  }
+  const size_t wbytes = sizeof(float) * Ci * C;
+  GLF_TRY(check_cuda(cudaMemcpyAsync(g_->theta_w, wb.dwcat, wbytes, cudaMemcpyDeviceToDevice, stream), "copy dtheta"));
+  GLF_TRY(check_cuda(cudaMemcpyAsync(g_->phi_w, wb.dwcat + static_cast<size_t>(Ci) * C, wbytes, cudaMemcpyDeviceToDevice, stream), "copy dphi"));
+  GLF_TRY(check_cuda(cudaMemcpyAsync(g_->g_w, wb.dwcat + 2 * static_cast<size_t>(Ci) * C, wbytes, cudaMemcpyDeviceToDevice, stream), "copy dg"));
+  {  // dX = dP Wcat + dV
+    GemmArgs g;
+    g.A = opnd(wb.dP, 0, 3 * Ci, 0);
+    g.B = opnd(s.wcatT, 0, 3 * Ci, 0);
+    g.M = rows; g.N = C; g.K = 3 * Ci;
+    g.addend = wb.dV; g.ld_add = C;
+    g.D = m.pack_x ? static_cast<void*>(wb.dxtok) : dx; g.ldd = C;
+    GLF_TRY(gemm(g, stream));
+  }
+  if (m.dot) {
+    GLF_TRY(reduce_partials(wb.cs_t, np, 2LL * Ci, Ci, 1.f, g_->theta_b, stream));
+    GLF_TRY(reduce_partials(wb.cs_p, np, 2LL * Ci, Ci, 1.f, g_->phi_b, stream));
+    GLF_TRY(reduce_partials(wb.cs_g, np, 2LL * Ci, Ci, 1.f, g_->g_b, stream));
+  } else {
+    return set_error(GLF_ERR_UNSUPPORTED, "embedded backward bias gradients not wired");
+  }
+  if (m.pack_x) {
+    if (d->x_layout == GLF_LAYOUT_NCTHW)
+      GLF_TRY(transpose_cast(wb.dxtok, dx, B, N, C, GLF_DTYPE_BF16, d->io_dtype, stream));
+    else
+      GLF_TRY(transpose_cast(wb.dxtok, dx, 1, 1, static_cast<int>(m.rows * C), GLF_DTYPE_BF16, d->io_dtype, stream));
+  }
+  return 0;
+}
+
+GLF_API int glf_gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype,
+                        const void* const* f4, const float* const* cls, const float* const* ctr, void* xg, void* xl,
+                        float* gate, glf_stream_t stream) {
+  GLF_TRY(check_device_sm100());
+  if (B <= 0 || C <= 0 || h <= 0 || w <= 0 || ncls <= 0) return set_error(GLF_ERR_INVALID, "gate_concat: empty input");
+  if (f4 == nullptr || cls == nullptr || ctr == nullptr) return set_error(GLF_ERR_INVALID, "gate_concat: NULL pointer table");
+  GLF_TRY(check_ptr(xg, "xg"));
+  GLF_TRY(check_ptr(xl, "xl"));
+  return gate_concat_fwd(B, C, V, h, w, ncls, weight, io_dtype, f4, cls, ctr, xg, xl, gate,
+                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+GLF_API int glf_gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype,
+                        const void* const* f4, const float* const* cls, const float* const* ctr, const float* gate,
+                        const void* dxg, const void* dxl, void* const* df4, float* const* dcls, float* const* dctr,
+                        glf_stream_t stream) {
+  GLF_TRY(check_device_sm100());
+  if (B <= 0 || C <= 0 || h <= 0 || w <= 0 || ncls <= 0) return set_error(GLF_ERR_INVALID, "gate_concat: empty input");
+  if (f4 == nullptr || cls == nullptr || ctr == nullptr || df4 == nullptr || dcls == nullptr || dctr == nullptr)
+    return set_error(GLF_ERR_INVALID, "gate_concat: NULL pointer table");
+  GLF_TRY(check_ptr(dxg, "dxg"));
+  GLF_TRY(check_ptr(dxl, "dxl"));
+  return gate_concat_bwd(B, C, V, h, w, ncls, weight, io_dtype, f4, cls, ctr, gate, dxg, dxl, df4, dcls, dctr,
+                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+GLF_API int glf_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int batch, int a_mn, int b_mn,
+                  int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
+                  const float* bias, float alpha, const void* addend, int64_t ld_add, int64_t stride_add,
+                  int out_kind, int split_k, float* colstats, glf_stream_t stream) {
+  GLF_TRY(check_device_sm100());
+  GLF_TRY(check_ptr(A, "A"));
+  GLF_TRY(check_ptr(B, "B"));
+  GLF_TRY(check_ptr(D, "D"));
+  GemmArgs g;
+  g.A = opnd(A, a_mn, lda, strideA);
+  g.B = opnd(B, b_mn, ldb, strideB);
+  g.M = M; g.N = N; g.K = K; g.batch = batch;
+  g.alpha = alpha; g.bias = bias;
+  g.out_kind = out_kind;
+  g.D = D; g.ldd = ldd; g.strideD = strideD;
+  g.addend = reinterpret_cast<const bf16*>(addend); g.ld_add = ld_add; g.stride_add = stride_add;
+  g.colstats = colstats;
+  g.split_k = split_k;
+  return gemm(g, reinterpret_cast<cudaStream_t>(stream));
+}
+
+GLF_API int glf_transpose(const void* in, void* out, int batch, int R, int S, int in_dtype, int out_dtype,
+                  glf_stream_t stream) {
+  GLF_TRY(check_device_sm100());
+  GLF_TRY(check_ptr(in, "in"));
+  GLF_TRY(check_ptr(out, "out"));
+  return transpose_cast(in, out, batch, R, S, in_dtype, out_dtype, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,200 @@
+// glf_gate.cu — the MLFM-specific work of the reference call site (R/models/ours.py:1802-1820, 1826-1827):
+// centre-aware gate a = sigmoid(w * max_c sigmoid(cls) * sigmoid(ctr)), f4_local = f4 * a, and the view concat
+// cat([f4_v.unsqueeze(2)], dim=2) for both the global (ungated) and local (gated) inputs.  In the reference this is
+// ~10 element-wise / copy kernels per view; here one HBM-bound pass reads each per-view NCHW feature map once,
+// transposes it through shared memory and writes both token-major [B, V*h*w, C] operands with 128-bit stores.
+// The backward is the mirror pass: df4 = dXg + a * dXl (back to NCHW) plus the gate gradient da = sum_c f4 * dXl
+// chained through the two sigmoids / the class max to the logits.
+#include "glf_internal.h"
+#include "glf_ptx.cuh"
+
+namespace glf {
+
+namespace {
+
+constexpr int MAXV = 8;
+struct ViewPtrs {
+  const void* f4[MAXV];
+  const float* cls[MAXV];
+  const float* ctr[MAXV];
+  void* df4[MAXV];
+  float* dcls[MAXV];
+  float* dctr[MAXV];
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+template <typename T>
+__device__ __forceinline__ float ldf(const T* p) { return static_cast<float>(*p); }
+
+// grid: (ceil(hw/64), C/64 rounded up, B*V) ; block 256
+template <typename TIO>
+__global__ void __launch_bounds__(256)
+    gate_concat_fwd_kernel(const ViewPtrs vp, bf16* __restrict__ xg, bf16* __restrict__ xl, float* __restrict__ gate,
+                           int C, int V, int hw, int ncls, float weight) {
+  __shared__ float tile[64][65];
+  __shared__ float a_sm[64];
+  const int bv = blockIdx.z, b = bv / V, v = bv % V;
+  const int p0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const TIO* f4 = reinterpret_cast<const TIO*>(vp.f4[v]) + static_cast<long long>(b) * C * hw;
+  if (threadIdx.x < 64) {
+    const int p = p0 + threadIdx.x;
+    float a = 0.f;
+    if (p < hw) {
+      const float* cl = vp.cls[v] + static_cast<long long>(b) * ncls * hw + p;
+      float lmax = cl[0];
+      for (int k = 1; k < ncls; ++k) lmax = fmaxf(lmax, cl[static_cast<long long>(k) * hw]);
+      const float m = sigmoidf_(lmax);  // max_c sigmoid(l_c) == sigmoid(max_c l_c)
+      const float c = sigmoidf_(vp.ctr[v][static_cast<long long>(b) * hw + p]);
+      a = sigmoidf_(weight * m * c);
+      if (blockIdx.y == 0) gate[static_cast<long long>(bv) * hw + p] = a;
+    }
+    a_sm[threadIdx.x] = a;
+  }
+  {
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    for (int i = ty; i < 64; i += 4) {
+      const int c = c0 + i, p = p0 + tx;
+      tile[i][tx] = (c < C && p < hw) ? ldf(f4 + static_cast<long long>(c) * hw + p) : 0.f;
+    }
+  }
+  __syncthreads();
+  // write: 8 lanes x 16 B cover the 64 channels of one token row
+  const int chunk = threadIdx.x & 7, pr = threadIdx.x >> 3;  // 32 rows per pass
+  for (int pp = pr; pp < 64; pp += 32) {
+    const int p = p0 + pp, c = c0 + chunk * 8;
+    if (p < hw && c < C) {
+      float f[8], g[8];
+      const float a = a_sm[pp];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        f[i] = tile[chunk * 8 + i][pp];
+        g[i] = f[i] * a;
+      }
+      const long long o = (static_cast<long long>(b) * V * hw + static_cast<long long>(v) * hw + p) * C + c;
+      *reinterpret_cast<uint4*>(xg + o) =
+          make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+      *reinterpret_cast<uint4*>(xl + o) =
+          make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]), pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7]));
+    }
+  }
+}
+
+// grid: (ceil(hw/64), B*V) ; block 256 ; loops over channel tiles so the gate gradient needs no atomics
+template <typename TIO>
+__global__ void __launch_bounds__(256)
+    gate_concat_bwd_kernel(const ViewPtrs vp, const float* __restrict__ gate, const bf16* __restrict__ dxg,
+                           const bf16* __restrict__ dxl, int C, int V, int hw, int ncls, float weight) {
+  __shared__ float tg[64][65];
+  __shared__ float tl[64][65];
+  __shared__ float a_sm[64];
+  __shared__ float da_sm[4][64];
+  const int bv = blockIdx.y, b = bv / V, v = bv % V;
+  const int p0 = blockIdx.x * 64;
+  const TIO* f4 = reinterpret_cast<const TIO*>(vp.f4[v]) + static_cast<long long>(b) * C * hw;
+  TIO* df4 = reinterpret_cast<TIO*>(vp.df4[v]) + static_cast<long long>(b) * C * hw;
+  if (threadIdx.x < 64) {
+    const int p = p0 + threadIdx.x;
+    a_sm[threadIdx.x] = p < hw ? gate[static_cast<long long>(bv) * hw + p] : 0.f;
+  }
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  float da = 0.f;
+  for (int c0 = 0; c0 < C; c0 += 64) {
+    __syncthreads();
+    const int chunk = threadIdx.x & 7, pr = threadIdx.x >> 3;
+    for (int pp = pr; pp < 64; pp += 32) {
+      const int p = p0 + pp, c = c0 + chunk * 8;
+      uint4 g4 = make_uint4(0, 0, 0, 0), l4 = make_uint4(0, 0, 0, 0);
+      if (p < hw && c < C) {
+        const long long o = (static_cast<long long>(b) * V * hw + static_cast<long long>(v) * hw + p) * C + c;
+        g4 = *reinterpret_cast<const uint4*>(dxg + o);
+        l4 = *reinterpret_cast<const uint4*>(dxl + o);
+      }
+      const uint32_t* gu = reinterpret_cast<const uint32_t*>(&g4);
+      const uint32_t* lu = reinterpret_cast<const uint32_t*>(&l4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 a2 = unpack_bf16(gu[i]), b2 = unpack_bf16(lu[i]);
+        tg[pp][chunk * 8 + 2 * i] = a2.x;
+        tg[pp][chunk * 8 + 2 * i + 1] = a2.y;
+        tl[pp][chunk * 8 + 2 * i] = b2.x;
+        tl[pp][chunk * 8 + 2 * i + 1] = b2.y;
+      }
+    }
+    __syncthreads();
+    const float a = a_sm[tx];
+    for (int i = ty; i < 64; i += 4) {
+      const int c = c0 + i, p = p0 + tx;
+      if (c < C && p < hw) {
+        const float dl = tl[tx][i];
+        const float f = ldf(f4 + static_cast<long long>(c) * hw + p);
+        df4[static_cast<long long>(c) * hw + p] = static_cast<TIO>(tg[tx][i] + a * dl);
+        da = fmaf(f, dl, da);
+      }
+    }
+  }
+  da_sm[ty][tx] = da;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int p = p0 + threadIdx.x;
+    if (p < hw) {
+      const float dA = da_sm[0][threadIdx.x] + da_sm[1][threadIdx.x] + da_sm[2][threadIdx.x] + da_sm[3][threadIdx.x];
+      const float* cl = vp.cls[v] + static_cast<long long>(b) * ncls * hw + p;
+      float lmax = cl[0];
+      int arg = 0;
+      for (int k = 1; k < ncls; ++k) {
+        const float l = cl[static_cast<long long>(k) * hw];
+        if (l > lmax) { lmax = l; arg = k; }
+      }
+      const float m = sigmoidf_(lmax);
+      const float c = sigmoidf_(vp.ctr[v][static_cast<long long>(b) * hw + p]);
+      const float a = a_sm[threadIdx.x];
+      const float dt = dA * a * (1.f - a);
+      const float dm = dt * weight * c, dc = dt * weight * m;
+      vp.dctr[v][static_cast<long long>(b) * hw + p] = dc * c * (1.f - c);
+      float* dcl = vp.dcls[v] + static_cast<long long>(b) * ncls * hw + p;
+      for (int k = 0; k < ncls; ++k) dcl[static_cast<long long>(k) * hw] = (k == arg) ? dm * m * (1.f - m) : 0.f;
+    }
+  }
+}
+
+}  // namespace
+
+int gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, const void* const* f4,
+                    const float* const* cls, const float* const* ctr, void* xg, void* xl, float* gate,
+                    cudaStream_t stream) {
+  if (V < 1 || V > MAXV) return set_error(GLF_ERR_INVALID, "gate_concat: 1 <= V <= %d", MAXV);
+  if (C % 8 != 0) return set_error(GLF_ERR_INVALID, "gate_concat: C %% 8 != 0");
+  ViewPtrs vp{};
+  for (int v = 0; v < V; ++v) { vp.f4[v] = f4[v]; vp.cls[v] = cls[v]; vp.ctr[v] = ctr[v]; }
+  const int hw = h * w;
+  dim3 grid((hw + 63) / 64, (C + 63) / 64, B * V);
+  if (grid.y > 65535 || grid.z > 65535) return set_error(GLF_ERR_INVALID, "gate_concat: grid too large");
+  if (io_dtype == GLF_DTYPE_BF16)
+    gate_concat_fwd_kernel<bf16><<<grid, 256, 0, stream>>>(vp, (bf16*)xg, (bf16*)xl, gate, C, V, hw, ncls, weight);
+  else
+    gate_concat_fwd_kernel<float><<<grid, 256, 0, stream>>>(vp, (bf16*)xg, (bf16*)xl, gate, C, V, hw, ncls, weight);
+  return check_cuda(cudaGetLastError(), "gate_concat_fwd launch");
+}
+
+int gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, const void* const* f4,
+                    const float* const* cls, const float* const* ctr, const float* gate, const void* dxg,
+                    const void* dxl, void* const* df4, float* const* dcls, float* const* dctr, cudaStream_t stream) {
+  if (V < 1 || V > MAXV) return set_error(GLF_ERR_INVALID, "gate_concat: 1 <= V <= %d", MAXV);
+  if (C % 8 != 0) return set_error(GLF_ERR_INVALID, "gate_concat: C %% 8 != 0");
+  ViewPtrs vp{};
+  for (int v = 0; v < V; ++v) {
+    vp.f4[v] = f4[v]; vp.cls[v] = cls[v]; vp.ctr[v] = ctr[v];
+    vp.df4[v] = df4[v]; vp.dcls[v] = dcls[v]; vp.dctr[v] = dctr[v];
+  }
+  const int hw = h * w;
+  dim3 grid((hw + 63) / 64, B * V);
+  if (grid.y > 65535) return set_error(GLF_ERR_INVALID, "gate_concat: grid too large");
+  if (io_dtype == GLF_DTYPE_BF16)
+    gate_concat_bwd_kernel<bf16><<<grid, 256, 0, stream>>>(vp, gate, (const bf16*)dxg, (const bf16*)dxl, C, V, hw, ncls, weight);
+  else
+    gate_concat_bwd_kernel<float><<<grid, 256, 0, stream>>>(vp, gate, (const bf16*)dxg, (const bf16*)dxl, C, V, hw, ncls, weight);
+  return check_cuda(cudaGetLastError(), "gate_concat_bwd launch");
+}
+
+}  // namespace glf

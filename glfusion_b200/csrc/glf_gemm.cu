@@ -1,0 +1,391 @@
+// glf_gemm.cu — warp-specialised tcgen05 / TMEM / TMA GEMM for sm_100a.
+//
+//   D[b] = alpha * sum_p A_p[b] * B_p[b]^T (+ bias) (+ addend)          A: M x K, B: N x K, bf16 in, fp32 accumulate
+//
+// One CTA computes one 128 x BN output tile (for one batch entry and one K split):
+//   warp 0      TMA producer  : cp.async.bulk.tensor 4-D loads (inner, rows, batch, limb) into a STAGES-deep ring,
+//                               SWIZZLE_128B, completion on mbarriers
+//   warp 1      MMA issuer    : allocates TMEM, one elected lane issues tcgen05.mma (M=128, N=BN, K=16) x 4 per stage,
+//                               tcgen05.commit releases the smem slot / publishes the accumulator
+//   warps 2..5  epilogue      : tcgen05.ld the fp32 accumulator (one TMEM lane quarter per warp), alpha/bias, then
+//                               either fp32 store / fp32 red.add (split-K) straight from registers, or bf16 staging in
+//                               smem -> fully coalesced 16-byte row stores (+ residual addend) and per-tile column
+//                               statistics (sum, sum of squares) for the BatchNorm that follows W_z (ours.py:908).
+// Operands may be K-major ([rows, K]) or MN-major ([K, rows]); the latter is how the token-contraction products
+// (Phi^T G, dU^T Theta, dP^T X) read token-major activations without any transposed copy.
+#include <mutex>
+
+#include "glf_internal.h"
+#include "glf_ptx.cuh"
+
+namespace glf {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmKParams {
+  int M, N, K, batch;
+  int kb_total, kb_per_split, split_k;
+  int npairs;
+  int pairA[6], pairB[6];
+  int a_batched, b_batched;
+  float alpha;
+  const float* bias;
+  int out_kind;
+  void* D;
+  long long ldd, strideD;
+  const bf16* addend;
+  long long ld_add, stride_add;
+  float* colstats;
+  int tiles_m;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 128) ? 3 : 4;
+  static constexpr int MIN_CTAS = (BN == 256) ? 1 : 2;
+  static constexpr uint32_t A_BYTES = BM * BK * 2;
+  static constexpr uint32_t B_BYTES = BN * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+  static constexpr uint32_t STG_ROW = BN * 2 + 16;  // staging row pitch (bytes): odd multiple of 16 -> conflict free
+  static_assert(BM * STG_ROW <= STAGES * STAGE_BYTES, "staging must fit in the pipeline ring");
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <bool A_MN, bool B_MN, int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, GemmCfg<BN>::MIN_CTAS)
+    gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[STAGES];
+  __shared__ uint64_t empty_bar[STAGES];
+  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_holder;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x;
+  const int m_tile = blockIdx.y;
+  const int b = blockIdx.z / p.split_k;
+  const int split = blockIdx.z % p.split_k;
+  const int kb0 = split * p.kb_per_split;
+  const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+  const int niter = (kb1 - kb0) * p.npairs;
+  const int m0 = m_tile * BM;
+  const int n0 = n_tile * BN;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_holder), BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      const int ab = p.a_batched ? b : 0;
+      const int bb = p.b_batched ? b : 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < niter; ++it) {
+        const int pair = it % p.npairs;
+        const int k0 = (kb0 + it / p.npairs) * BK;
+        const uint32_t fb = smem_u32(&full_bar[stage]);
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+        mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+        const uint32_t sb = sa + Cfg::A_BYTES;
+        if (!A_MN) {
+          tma_load_4d(&tmA, fb, sa, k0, m0, ab, p.pairA[pair]);
+        } else {
+          tma_load_4d(&tmA, fb, sa, m0, k0, ab, p.pairA[pair]);
+          tma_load_4d(&tmA, fb, sa + 8192, m0 + 64, k0, ab, p.pairA[pair]);
+        }
+        if (!B_MN) {
+          tma_load_4d(&tmB, fb, sb, k0, n0, bb, p.pairB[pair]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_4d(&tmB, fb, sb + j * 8192, n0 + j * 64, k0, bb, p.pairB[pair]);
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < niter; ++it) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+        const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t ad = A_MN ? make_sdesc(sa + k * 2048, 8192, 1024) : make_sdesc(sa + k * 32, 16, 1024);
+          const uint64_t bd = B_MN ? make_sdesc(sb + k * 2048, 8192, 1024) : make_sdesc(sb + k * 32, 16, 1024);
+          umma_f16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&empty_bar[stage]));  // slot reusable once these MMAs have read it
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(smem_u32(&tmem_full_bar));  // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------ epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int grow = m0 + row;
+    const int e = (warp - 2) * 32 + lane;  // 0..127
+    mbar_wait(smem_u32(&tmem_full_bar), 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    if (p.out_kind != 0) {
+      float* Df = reinterpret_cast<float*>(p.D) + static_cast<long long>(b) * p.strideD +
+                  static_cast<long long>(grow) * p.ldd;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        if (grow < p.M) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int gc = n0 + c * 32 + j;
+            if (gc < p.N) {
+              float f0 = __uint_as_float(v[j]) * p.alpha, f1 = __uint_as_float(v[j + 1]) * p.alpha;
+              float f2 = __uint_as_float(v[j + 2]) * p.alpha, f3 = __uint_as_float(v[j + 3]) * p.alpha;
+              if (p.bias != nullptr && split == 0) {
+                f0 += p.bias[gc];
+                f1 += p.bias[gc + 1];
+                f2 += p.bias[gc + 2];
+                f3 += p.bias[gc + 3];
+              }
+              if (p.out_kind == 2) {
+                red_add_v4(Df + gc, f0, f1, f2, f3);
+              } else {
+                *reinterpret_cast<float4*>(Df + gc) = make_float4(f0, f1, f2, f3);
+              }
+            }
+          }
+        }
+      }
+    } else {
+      uint8_t* stg = smem_gen;  // ring is idle: every TMA load landed and every MMA that read it completed
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          float f[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            f[t] = __uint_as_float(v[j + t]) * p.alpha;
+            if (p.bias != nullptr) {
+              const int gc = n0 + c * 32 + j + t;
+              f[t] += (gc < p.N) ? p.bias[gc] : 0.f;
+            }
+          }
+          uint4 pk = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                pack_bf16(f[6], f[7]));
+          *reinterpret_cast<uint4*>(stg + row * Cfg::STG_ROW + (c * 32 + j) * 2) = pk;
+        }
+      }
+      named_bar_sync(1, 128);
+      const int rows_valid = min(BM, p.M - m0);
+      if (p.colstats != nullptr) {
+        for (int col = e; col < BN; col += 128) {
+          const int gc = n0 + col;
+          if (gc < p.N) {
+            float s = 0.f, s2 = 0.f;
+            for (int r = 0; r < rows_valid; ++r) {
+              const float x = __bfloat162float(*reinterpret_cast<const bf16*>(stg + r * Cfg::STG_ROW + col * 2));
+              s += x;
+              s2 = fmaf(x, x, s2);
+            }
+            float* cs = p.colstats + (static_cast<long long>(b) * p.tiles_m + m_tile) * 2 * p.N;
+            cs[gc] = s;
+            cs[p.N + gc] = s2;
+          }
+        }
+      }
+      bf16* Db = reinterpret_cast<bf16*>(p.D) + static_cast<long long>(b) * p.strideD;
+      const bf16* Ad = p.addend ? p.addend + static_cast<long long>(b) * p.stride_add : nullptr;
+      constexpr int CH = BN / 8;  // 16-byte chunks per row
+      for (int idx = e; idx < BM * CH; idx += 128) {
+        const int r = idx / CH, ch = idx % CH;
+        const int gr = m0 + r, gc = n0 + ch * 8;
+        if (gr < p.M && gc < p.N) {
+          uint4 pk = *reinterpret_cast<const uint4*>(stg + r * Cfg::STG_ROW + ch * 16);
+          if (Ad != nullptr) {
+            const uint4 ad = *reinterpret_cast<const uint4*>(Ad + static_cast<long long>(gr) * p.ld_add + gc);
+            const uint32_t* a32 = reinterpret_cast<const uint32_t*>(&ad);
+            uint32_t* p32 = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 x = unpack_bf16(p32[t]), y = unpack_bf16(a32[t]);
+              p32[t] = pack_bf16(x.x + y.x, x.y + y.y);
+            }
+          }
+          *reinterpret_cast<uint4*>(Db + static_cast<long long>(gr) * p.ldd + gc) = pk;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+    }
+  });
+  return fn;
+}
+
+// Tensor map over a bf16 operand: K-major -> dims {K, rows, batch, limb}; MN-major -> dims {rows, K, batch, limb}.
+int make_operand_map(CUtensorMap* tm, const GemmOperand& op, int rows, int K, int batch, int nlimbs, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return set_error(GLF_ERR_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(op.ptr) & 15) != 0) return set_error(GLF_ERR_INVALID, "GEMM operand not 16-byte aligned");
+  if (op.ld % 8 != 0) return set_error(GLF_ERR_INVALID, "GEMM leading dimension must be a multiple of 8 elements");
+  if (op.batch_stride % 8 != 0 || op.limb_stride % 8 != 0)
+    return set_error(GLF_ERR_INVALID, "GEMM batch/limb stride must be a multiple of 8 elements");
+  const cuuint64_t inner = op.mn_major ? rows : K;
+  const cuuint64_t outer = op.mn_major ? K : rows;
+  const int nb = (op.batch_stride != 0) ? batch : 1;
+  cuuint64_t dims[4] = {inner, outer, static_cast<cuuint64_t>(nb), static_cast<cuuint64_t>(nlimbs)};
+  const cuuint64_t row_bytes = static_cast<cuuint64_t>(op.ld) * 2;
+  const cuuint64_t span = outer * row_bytes;
+  cuuint64_t strides[3] = {row_bytes, nb > 1 ? static_cast<cuuint64_t>(op.batch_stride) * 2 : span,
+                           nlimbs > 1 ? static_cast<cuuint64_t>(op.limb_stride) * 2 : span * static_cast<cuuint64_t>(nb)};
+  cuuint32_t box[4] = {64u, static_cast<cuuint32_t>(op.mn_major ? 64 : box_rows), 1u, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(GLF_ERR_INVALID, "cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu ld=%lld", (int)r,
+                     (unsigned long long)inner, (unsigned long long)outer, (long long)op.ld);
+  return 0;
+}
+
+template <bool A_MN, bool B_MN, int BN>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, dim3 grid, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_kernel<A_MN, B_MN, BN>;
+  // per launch: the attribute is per device, and callers may drive several GPUs from one process (nn.DataParallel)
+  cudaError_t attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  if (attr_err != cudaSuccess) return check_cuda(attr_err, "cudaFuncSetAttribute(gemm)");
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  return check_cuda(cudaGetLastError(), "gemm launch");
+}
+
+template <int BN>
+int launch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, dim3 grid,
+                 cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch<false, false, BN>(tmA, tmB, p, grid, stream);
+  if (a_mn && b_mn) return launch<true, true, BN>(tmA, tmB, p, grid, stream);
+  if (a_mn) return launch<true, false, BN>(tmA, tmB, p, grid, stream);
+  return launch<false, true, BN>(tmA, tmB, p, grid, stream);
+}
+
+}  // namespace
+
+int gemm(const GemmArgs& a, cudaStream_t stream) {
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0 || a.batch <= 0) return set_error(GLF_ERR_INVALID, "gemm: empty problem");
+  if (a.N % 8 != 0) return set_error(GLF_ERR_INVALID, "gemm: N must be a multiple of 8 (got %d)", a.N);
+  if (a.out_kind < 0 || a.out_kind > 2) return set_error(GLF_ERR_INVALID, "gemm: bad out_kind");
+  if (a.split_k > 1 && a.out_kind != 2) return set_error(GLF_ERR_INVALID, "gemm: split_k needs atomic output");
+  if (a.out_kind != 0 && (a.addend != nullptr || a.colstats != nullptr))
+    return set_error(GLF_ERR_INVALID, "gemm: addend/colstats only with bf16 output");
+  if (a.ldd % 8 != 0 || (reinterpret_cast<uintptr_t>(a.D) & 15) != 0)
+    return set_error(GLF_ERR_INVALID, "gemm: output must be 16-byte aligned with ldd %% 8 == 0");
+  if (a.npairs < 1 || a.npairs > 6) return set_error(GLF_ERR_INVALID, "gemm: npairs out of range");
+
+  const int BN = (a.N <= 64) ? 64 : ((a.N % 256 == 0 || a.N > 384) ? 256 : 128);
+  int nlimbsA = 1, nlimbsB = 1;
+  for (int i = 0; i < a.npairs; ++i) {
+    nlimbsA = a.pairA[i] + 1 > nlimbsA ? a.pairA[i] + 1 : nlimbsA;
+    nlimbsB = a.pairB[i] + 1 > nlimbsB ? a.pairB[i] + 1 : nlimbsB;
+  }
+  CUtensorMap tmA, tmB;
+  int rc = make_operand_map(&tmA, a.A, a.M, a.K, a.batch, nlimbsA, BM);
+  if (rc) return rc;
+  rc = make_operand_map(&tmB, a.B, a.N, a.K, a.batch, nlimbsB, BN);
+  if (rc) return rc;
+
+  GemmKParams p;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.batch = a.batch;
+  p.kb_total = (a.K + BK - 1) / BK;
+  int sk = a.split_k < 1 ? 1 : a.split_k;
+  if (sk > p.kb_total) sk = p.kb_total;
+  p.kb_per_split = (p.kb_total + sk - 1) / sk;
+  p.split_k = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.npairs = a.npairs;
+  for (int i = 0; i < 6; ++i) { p.pairA[i] = a.pairA[i]; p.pairB[i] = a.pairB[i]; }
+  p.a_batched = a.A.batch_stride != 0;
+  p.b_batched = a.B.batch_stride != 0;
+  p.alpha = a.alpha;
+  p.bias = a.bias;
+  p.out_kind = a.out_kind;
+  p.D = a.D; p.ldd = a.ldd; p.strideD = a.strideD;
+  p.addend = a.addend; p.ld_add = a.ld_add; p.stride_add = a.stride_add;
+  p.colstats = a.colstats;
+  p.tiles_m = gemm_tiles_m(a.M);
+  const long long gz = static_cast<long long>(a.batch) * p.split_k;
+  if (p.tiles_m > 65535 || gz > 65535) return set_error(GLF_ERR_INVALID, "gemm: grid too large");
+  dim3 grid((a.N + BN - 1) / BN, p.tiles_m, static_cast<unsigned>(gz));
+  const bool amn = a.A.mn_major != 0, bmn = a.B.mn_major != 0;
+  switch (BN) {
+    case 64: return launch_major<64>(amn, bmn, tmA, tmB, p, grid, stream);
+    case 128: return launch_major<128>(amn, bmn, tmA, tmB, p, grid, stream);
+    default: return launch_major<256>(amn, bmn, tmA, tmB, p, grid, stream);
+  }
+}
+
+}  // namespace glf

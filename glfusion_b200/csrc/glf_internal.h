@@ -1,0 +1,87 @@
+// glf_internal.h — C++ internals shared by the translation units of libglf_sm100a.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/glfusion.h"
+
+namespace glf {
+
+int set_error(int code, const char* fmt, ...);   // records thread-local message, returns code
+int check_cuda(cudaError_t e, const char* what); // 0 or GLF_ERR_DEVICE
+int check_device_sm100();                        // 0 or GLF_ERR_DEVICE
+
+using bf16 = __nv_bfloat16;
+
+// ------------------------------------------------------------------------------------------------ GEMM
+struct GemmOperand {
+  const void* ptr = nullptr;
+  int mn_major = 0;       // 0: [rows, K] K contiguous ; 1: [K, rows] rows contiguous
+  int64_t ld = 0;         // leading dimension in elements
+  int64_t batch_stride = 0;  // elements; 0 = shared across batch
+  int64_t limb_stride = 0;   // elements between bf16 limb planes (F32X3 precision); 0 when single limb
+};
+
+struct GemmArgs {
+  GemmOperand A, B;
+  int M = 0, N = 0, K = 0, batch = 1;
+  float alpha = 1.f;
+  const float* bias = nullptr;      // [N]
+  int out_kind = 0;                 // 0 bf16 store, 1 f32 store, 2 f32 atomic add
+  void* D = nullptr;
+  int64_t ldd = 0, strideD = 0;
+  const bf16* addend = nullptr;     // optional bf16 [M, N] added in the epilogue (out_kind 0 only)
+  int64_t ld_add = 0, stride_add = 0;
+  float* colstats = nullptr;        // [batch*tiles_m][2][N]
+  int split_k = 1;
+  int npairs = 1;                   // limb products accumulated into one tile: sum_p A[pairA[p]] * B[pairB[p]]^T
+  int pairA[6] = {0, 0, 0, 0, 0, 0};
+  int pairB[6] = {0, 0, 0, 0, 0, 0};
+};
+int gemm(const GemmArgs& a, cudaStream_t stream);
+inline int gemm_tiles_m(int M) { return (M + 127) / 128; }
+
+// ------------------------------------------------------------------------------------------------ element-wise
+int transpose_cast(const void* in, void* out, int batch, int R, int S, int in_dtype, int out_dtype,
+                   cudaStream_t stream);
+int prep_weights(const glf_weights* w, int C, int Ci, bf16* wcat, bf16* wcatT, float* bcat, bf16* wz, bf16* wzT,
+                 cudaStream_t stream);
+int bn_finalize(const float* part, int np, int C, double count, const glf_desc* d, const glf_weights* w, float* mean,
+                float* rstd, float* a, float* b, cudaStream_t stream);
+int bn_res_ln_fwd(const bf16* U, const bf16* X, const float* a, const float* b, const float* lw, const float* lb,
+                  void* Z, int z_dtype, float* mu, float* r, long long rows, int C, float eps, int accumulate,
+                  cudaStream_t stream);
+int bn_res_ln_bwd_blocks(long long rows, int C);
+int bn_res_ln_bwd(const void* dZ, int dz_dtype, const bf16* U, const bf16* X, const float* a, const float* b,
+                  const float* mean, const float* rstd, const float* lw, const float* mu, const float* r, bf16* dV,
+                  float* part, long long rows, int C, cudaStream_t stream);
+int bn_bwd_finalize(const float* part, int np, int C, double count, const glf_desc* d, const glf_weights* w,
+                    const float* mean, const float* rstd, const glf_grads* g, float* k1, float* k2, float* k3,
+                    cudaStream_t stream);
+int bn_bwd_apply(const bf16* dV, const bf16* U, const float* k1, const float* k2, const float* k3, bf16* dU,
+                 long long rows, int C, cudaStream_t stream);
+// C[b] = alpha * sum_rb A[b,rb] (MxK, strides rs/cs) * B[b,rb] (KxN); outputs fp32 and/or bf16 and/or bf16 transposed
+int small_gemm(const float* A, long long a_rs, long long a_cs, long long a_bs, long long a_rbs, const float* B,
+               long long b_rs, long long b_cs, long long b_bs, long long b_rbs, int batch, int RB, int M, int N, int K,
+               float alpha, float* Cf, bf16* Cb, bf16* CbT, cudaStream_t stream);
+int reduce_partials(const float* part, int np, long long stride, int n, float alpha, float* out, cudaStream_t stream);
+int copy_f32(const float* in, float* out, long long n, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------ gate + concat
+int gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, const void* const* f4,
+                    const float* const* cls, const float* const* ctr, void* xg, void* xl, float* gate,
+                    cudaStream_t stream);
+int gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, const void* const* f4,
+                    const float* const* cls, const float* const* ctr, const float* gate, const void* dxg,
+                    const void* dxl, void* const* df4, float* const* dcls, float* const* dctr, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------ softmax attention
+// mode='embedded' (ours.py:896-897,902): Y = softmax(Theta Phi^T) G, flash-style, per batch entry.
+// P: [B, N, 3Ci] bf16 (theta | phi | g); Y: [B, N, Ci] bf16; lse: [B, N] fp32 (natural-log-sum-exp per query row)
+int flash_fwd(const bf16* P, bf16* Y, float* lse, int B, int N, int Ci, cudaStream_t stream);
+int flash_bwd(const bf16* P, const bf16* Y, const bf16* dY, const float* lse, bf16* dP, float* delta_ws, int B, int N,
+              int Ci, cudaStream_t stream);
+
+}  // namespace glf

@@ -1,0 +1,155 @@
+/* glfusion.h — C ABI of libglf_sm100a.so: the B200-native GL-Fusion cross-view fusion hot path.
+ *
+ * Reference being replaced (R = xmed-lab/GL-Fusion, GLfusion/):
+ *   - TPAVIModule.forward            R/models/ours.py:845-917  (dup R/models/TPAVI.py:86-155)   -> glf_tpavi_fwd
+ *   - its autograd backward          (implicit in the reference)                                 -> glf_tpavi_bwd
+ *   - gate + view concat             R/models/ours.py:1802-1820, 1826-1827                       -> glf_gate_concat_fwd
+ *   - their backward                 (implicit)                                                  -> glf_gate_concat_bwd
+ *   - MGFM + MLFM sum, .contiguous() R/models/ours.py:1833-1837                                  -> glf_tpavi_fwd (accumulate flag)
+ * The reference has no FFI layer for this path (pure Python nn.Module); this header is the
+ * boundary a maintainer binds with ctypes.
+ *
+ * Contract
+ *   - plain pointers and sizes only; every pointer is DEVICE memory on the current CUDA device unless noted;
+ *   - the caller allocates everything (outputs, saved-for-backward blob, workspace); the library never
+ *     allocates, frees or synchronises, and enqueues all work on the given stream (CUDA-graph capturable);
+ *   - return 0 on success, <0 on error; message via glf_last_error() (thread local); no fallback paths:
+ *     unsupported configurations and non-sm_100 devices are errors;
+ *   - re-entrant: no global mutable state besides a per-process cache of the driver entry point.
+ */
+#ifndef GLFUSION_H_
+#define GLFUSION_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLF_VERSION 100
+
+#if defined(__GNUC__)
+#define GLF_API __attribute__((visibility("default")))
+#else
+#define GLF_API
+#endif
+
+typedef void* glf_stream_t; /* cudaStream_t */
+
+enum { GLF_MODE_DOT = 0, GLF_MODE_EMBEDDED = 1 };         /* TPAVIModule(mode=...)  ours.py:896-900 */
+enum { GLF_DTYPE_BF16 = 0, GLF_DTYPE_F32 = 1 };
+enum { GLF_LAYOUT_NCTHW = 0, GLF_LAYOUT_TOKEN = 1 };      /* [B,C,T,H,W] contiguous  |  [B,T,H,W,C] contiguous */
+enum { GLF_PRECISION_BF16 = 0, GLF_PRECISION_F32X3 = 1 }; /* tensor-core operand precision */
+
+enum {
+  GLF_OK = 0,
+  GLF_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  GLF_ERR_UNSUPPORTED = -2, /* feature not available (e.g. mode='concatenate', dimension != 3) */
+  GLF_ERR_DEVICE = -3,      /* not an sm_100 device, or CUDA error */
+  GLF_ERR_WORKSPACE = -4    /* caller-provided blob too small / misaligned */
+};
+
+/* Problem descriptor: x is [B, C, T, H, W]; N = T*H*W tokens per sequence; Ci = inter_channels (C/2 by default). */
+typedef struct glf_desc {
+  int32_t B, T, H, W, C, Ci;
+  int32_t mode;       /* GLF_MODE_* */
+  int32_t io_dtype;   /* dtype of x, z, dz, dx                         GLF_DTYPE_* */
+  int32_t x_layout;   /* physical layout of x and dx                   GLF_LAYOUT_* */
+  int32_t dz_layout;  /* physical layout of dz (z itself is always GLF_LAYOUT_TOKEN, like the reference's
+                         permuted LayerNorm output, ours.py:913-915) */
+  int32_t precision;  /* GLF_PRECISION_* */
+  int32_t training;   /* BatchNorm3d uses batch statistics and updates running stats (ours.py:822-825) */
+  int32_t bn_layer;   /* 1: W_z = conv + BN ; 0: W_z = conv only (ours.py:829-833) */
+  int32_t accumulate; /* fwd: z += result instead of z = result (fuses f4_global + f4_local, ours.py:1834) */
+  float eps_bn, eps_ln, momentum;
+  int32_t reserved[4];
+} glf_desc;
+
+/* fp32 master parameters, same shapes as the reference state_dict. */
+typedef struct glf_weights {
+  const float* theta_w; /* [Ci, C]   theta.weight[Ci,C,1,1,1] */
+  const float* theta_b; /* [Ci] */
+  const float* phi_w;   /* [Ci, C] */
+  const float* phi_b;   /* [Ci] */
+  const float* g_w;     /* [Ci, C] */
+  const float* g_b;     /* [Ci] */
+  const float* wz_w;    /* [C, Ci]   W_z.0.weight (or W_z.weight when bn_layer=0) */
+  const float* wz_b;    /* [C] */
+  const float* bn_w;    /* [C]       W_z.1.weight  (unused when bn_layer=0) */
+  const float* bn_b;    /* [C]       W_z.1.bias */
+  float* bn_running_mean;          /* [C]  updated in place when training */
+  float* bn_running_var;           /* [C] */
+  int64_t* bn_num_batches_tracked; /* [1] */
+  const float* ln_w; /* [C]  norm_layer.weight */
+  const float* ln_b; /* [C]  norm_layer.bias */
+} glf_weights;
+
+/* fp32 gradients, written (not accumulated) by glf_tpavi_bwd. */
+typedef struct glf_grads {
+  float* theta_w; float* theta_b;
+  float* phi_w;   float* phi_b;
+  float* g_w;     float* g_b;
+  float* wz_w;    float* wz_b;
+  float* bn_w;    float* bn_b;
+  float* ln_w;    float* ln_b;
+} glf_grads;
+
+typedef struct glf_sizes {
+  size_t saved_bytes;  /* blob written by fwd, read by bwd (activations kept for backward) */
+  size_t ws_fwd_bytes; /* scratch for fwd */
+  size_t ws_bwd_bytes; /* scratch for bwd */
+} glf_sizes;
+
+GLF_API int glf_version(void);
+GLF_API const char* glf_last_error(void);
+
+/* Sizes of the caller-allocated blobs for a descriptor (256-byte aligned pointers required). */
+GLF_API int glf_tpavi_sizes(const glf_desc* d, glf_sizes* out);
+
+/* z = LayerNorm(BN(W_z(attn(theta(x), phi(x), g(x)))) + x).   z: [B,T,H,W,C] contiguous, io_dtype.
+ * `saved` may be NULL when no backward will follow (inference); then nothing is kept. */
+GLF_API int glf_tpavi_fwd(const glf_desc* d, const void* x, const glf_weights* w, void* z, void* saved, void* ws,
+                  glf_stream_t stream);
+
+/* dx (layout/dtype of x) and all parameter gradients from dz.  `x` is the forward input again. */
+GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, const glf_weights* w, const void* saved,
+                  void* dx, const glf_grads* g, void* ws, glf_stream_t stream);
+
+/* Gate + view concat (ours.py:1802-1820,1826-1827).
+ *   f4[v]  : [B, C, h, w]  io_dtype, NCHW contiguous, v < V (host array of V device pointers, V <= 8)
+ *   cls[v] : [B, ncls, h, w] fp32 logits of classifier[view];  ctr[v] : [B, 1, h, w] fp32 logits of centerness[view]
+ *   xg, xl : [B, V*h*w, C] bf16 token-major (view-major token order, i.e. T = V)    — MGFM / MLFM inputs
+ *   gate   : [B, V, h, w] fp32, a = sigmoid(weight * max_c sigmoid(cls) * sigmoid(ctr))   (kept for backward) */
+GLF_API int glf_gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype,
+                        const void* const* f4, const float* const* cls, const float* const* ctr, void* xg, void* xl,
+                        float* gate, glf_stream_t stream);
+
+/* df4[v] = dxg[:, v] + gate * dxl[:, v]  (NCHW, io_dtype);  dcls[v], dctr[v] fp32 logit gradients. */
+GLF_API int glf_gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype,
+                        const void* const* f4, const float* const* cls, const float* const* ctr, const float* gate,
+                        const void* dxg, const void* dxl, void* const* df4, float* const* dcls, float* const* dctr,
+                        glf_stream_t stream);
+
+/* ---- building blocks, exported for unit tests and for callers that fuse differently ------------------------ */
+
+/* D[b] = alpha * A[b] * B[b]^T (+ bias[n]) (+ addend) on tcgen05 tensor cores, bf16 operands, fp32 accumulate.
+ *   A: M x K, B: N x K.  a_mn / b_mn = 0: operand stored K-contiguous ([rows, K], leading dim ld);
+ *                                     = 1: operand stored MN-contiguous ([K, rows], leading dim ld).
+ *   out_kind 0: bf16 store, 1: fp32 store, 2: fp32 atomic add (split_k > 1 requires 2).
+ *   colstats (optional): per (batch, m-tile) partial column sums / sums of squares of the stored values,
+ *                        layout [batch * ceil(M/128)][2][N] fp32.
+ *   batch strides in elements; strideB = 0 shares B across the batch. */
+GLF_API int glf_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int batch, int a_mn, int b_mn,
+                  int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
+                  const float* bias, float alpha, const void* addend, int64_t ld_add, int64_t stride_add,
+                  int out_kind, int split_k, float* colstats, glf_stream_t stream);
+
+/* out[b, s, r] = in[b, r, s] with dtype conversion (NCTHW <-> token-major packing). dtypes: GLF_DTYPE_*. */
+GLF_API int glf_transpose(const void* in, void* out, int batch, int R, int S, int in_dtype, int out_dtype,
+                  glf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLFUSION_H_ */
