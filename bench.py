@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py — GL-Fusion fusion hot path (gate+concat -> MGFM + MLFM -> sum) forward+backward throughput on B200.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5            # our arm (libglf_sm100a.so)
+    python bench.py --impl reference --steps 3 --warmup 1     # the reference algorithm on the host CPU cores
+
+Workload = BASELINE.json configs[1]: MGFM+MLFM modules only, 4 views x 16 frames x 28x28 tokens, C=256, bf16,
+fwd+bwd, frames-as-batch layout (Global_and_Local, R/models/ours.py:1819-1821): one clip = 16 sequences of
+4*28*28 = 3136 tokens.  A step processes `--clips` clips per GPU (default 8 -> 128 sequences, 205 MB of bf16 features,
+larger than the 126 MB L2, so no L2 flush is needed between iterations).
+
+One JSON line on stdout (rank 0).  Under torchrun (N>1) clips are sharded by rank (weak scaling: fixed clips/GPU), the
+only collective is the all-reduce of the fusion-weight gradients.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+V, F, HH, WW = 4, 16, 28, 28
+NCLS = 5
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def make_inputs(clips: int, C: int, seed: int, device, pinned: bool = False):
+    B = clips * F
+    g = torch.Generator().manual_seed(seed)
+    f4 = [torch.randn(B, C, HH, WW, generator=g).to(torch.bfloat16) for _ in range(V)]
+    cls = [torch.randn(B, NCLS, HH, WW, generator=g) for _ in range(V)]
+    ctr = [torch.randn(B, 1, HH, WW, generator=g) for _ in range(V)]
+    if pinned:
+        return [t.pin_memory() for t in f4], [t.pin_memory() for t in cls], [t.pin_memory() for t in ctr]
+    return [t.to(device) for t in f4], [t.to(device) for t in cls], [t.to(device) for t in ctr]
+
+
+def seeded_fusion(C: int, device):
+    from glfusion_b200 import GlobalLocalFusion
+    from oracle import tpavi_oracle as O     # parameter recipe only (seeded init + BN/LN affine re-randomised, F3)
+    f = GlobalLocalFusion(in_channels=C)
+    f.global_attn.load_state_dict(O.init_params(C, seed=0, randomize_affine=True), strict=True)
+    f.local_attn.load_state_dict(O.init_params(C, seed=1, randomize_affine=True), strict=True)
+    return f.to(device).train()
+
+
+def algorithmic_work(clips: int, C: int):
+    """FLOPs of the algorithm actually executed (reassociated dot mode with W' = Wz M^T folded in), per step."""
+    N = V * HH * WW
+    rows = clips * F * N
+    Ci = C // 2
+    fwd = 2 * rows * C * 3 * Ci + 2 * rows * Ci * Ci + 2 * rows * Ci * C
+    bwd = 2 * rows * C * Ci * 2 + 2 * rows * Ci * Ci * 2 + 2 * rows * 3 * Ci * C * 2
+    small = clips * F * (2 * C * Ci * Ci) * 3
+    return 2 * (fwd + bwd + small), rows
+
+
+def run_ours(args):
+    from glfusion_b200 import dp
+    rank, local_rank, world = dp.init_process_group("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    C = args.channels
+    clips = args.clips
+    fusion = seeded_fusion(C, dev)
+    f4, cls, ctr = make_inputs(clips, C, 100 + rank, dev)
+    for t in f4:
+        t.requires_grad_(True)
+    B = clips * F
+    dz = torch.randn(B, V, HH, WW, C, device=dev, dtype=torch.bfloat16).permute(0, 4, 1, 2, 3)
+    bucket = dp.GradBucket(list(fusion.global_attn._plist()) + list(fusion.local_attn._plist()))
+
+    def compute():
+        for t in f4:
+            t.grad = None
+        out = fusion.forward_stacked(f4, cls, ctr)
+        out.backward(dz)
+
+    graph = None
+    if args.graph:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                compute()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            compute()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            compute()
+        if world > 1:
+            bucket.allreduce_mean()      # the only collective: fusion-weight gradients over NCCL / NVLink
+
+    for _ in range(max(args.warmup, 3)):
+        run_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        run_step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    ms = dp.max_over_ranks(ms, device=dev)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end: host (pinned) inputs -> H2D -> fwd+bwd -> D2H of the step's scalar result ----------------------
+    hf4, hcls, hctr = make_inputs(clips, C, 100 + rank, dev, pinned=True)
+    res_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in hf4 + hcls + hctr)
+
+    def e2e_step():
+        for dst, src in zip(f4 + cls + ctr, hf4 + hcls + hctr):
+            dst.detach().copy_(src, non_blocking=True)
+        run_step()
+        res_host.copy_(f4[0].grad.float().abs().mean().reshape(1), non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    e0.record()
+    esteps = max(2, min(args.steps, 10))
+    for _ in range(esteps):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = dp.max_over_ranks(e0.elapsed_time(e1) / esteps, device=dev)
+
+    if rank != 0:
+        return
+    flops, rows = algorithmic_work(clips, C)
+    pk = peaks()
+    total_clips = clips * world
+    value = total_clips / (ms * 1e-3)
+    out = {
+        "metric": "fusion fwd+bwd clips/sec", "value": round(value, 2), "unit": "clips/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: MGFM+MLFM modules only, 4 views x 16 frames x 28x28 tokens, "
+                               f"C={C}, bf16 fwd+bwd, frames-as-batch (B={clips * F} sequences x N={V * HH * WW} tokens per GPU)",
+                   "clips_per_gpu_per_step": clips, "mode": "dot", "cuda_graph": bool(args.graph),
+                   "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no flush" % (rows * C * 2 / 1e6),
+                   "parallelism": f"dp{world}"},
+        "e2e": {"value": round(total_clips / (e2e_ms * 1e-3), 2), "unit": "clips/s",
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
+        "gpu_launches": None,
+        "clocks": clocks,
+        "achieved_tflops_algorithmic": round(flops / (ms * 1e-3) / 1e12, 2),
+        "peaks": pk,
+    }
+    out.update(kernel_probe(args, dev, clips, C, pk))
+    out["gpu_launches"] = count_launches(clips, C) * args.steps
+    if not args.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_baseline(C, seconds=args.cpu_seconds)
+    print(json.dumps(out), flush=True)
+
+
+def count_launches(clips: int, C: int) -> int:
+    """Kernels launched by libglf_sm100a per step (fwd+bwd, both modules + gate), counted from the orchestration in
+    glfusion_b200/csrc/glf_api.cu (memset/memcpy nodes excluded)."""
+    fwd_mod = 7          # prep_weights, proj GEMM, M GEMM, W' small GEMM, U GEMM, bn_finalize, bn_res_ln_fwd
+    bwd_mod = 14         # ln_bwd, finalize, apply, dTheta, dW', dWz, dM, dPhi, dG, dWcat, dX, 3 bias reductions
+    return 2 * (fwd_mod + bwd_mod) + 2
+
+
+def kernel_probe(args, dev, clips, C, pk):
+    """Time the dominant HBM-bound kernel in isolation (CUDA events on the launching stream) -> roofline object.
+    Dominant kernel of the step per the ncu launch list under profiles/: bn_res_ln_bwd_kernel (LN/BN backward)."""
+    import ctypes as Ct
+    from glfusion_b200 import _lib as L
+    lib = L.load()
+    rows = clips * F * V * HH * WW
+    U = torch.randn(rows, C, device=dev).to(torch.bfloat16)
+    X = torch.randn(rows, C, device=dev).to(torch.bfloat16)
+    dZ = torch.randn(rows, C, device=dev).to(torch.bfloat16)
+    dV = torch.empty_like(U)
+    vec = torch.rand(5, C, device=dev) + 0.5
+    rowst = torch.rand(2, rows, device=dev) + 0.5
+    part = torch.empty(lib.glf_bn_res_ln_bwd_max_blocks() * 4 * C, device=dev)
+    nb = Ct.c_int(0)
+    stream = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def launch():
+        L.check(lib.glf_bn_res_ln_bwd(rows, C, L.ptr(dZ), L.DTYPE_BF16, L.ptr(U), L.ptr(X), L.ptr(vec[0]), L.ptr(vec[1]),
+                                      L.ptr(vec[2]), L.ptr(vec[3]), L.ptr(vec[4]), L.ptr(rowst[0]), L.ptr(rowst[1]),
+                                      L.ptr(dV), L.ptr(part), Ct.byref(nb), stream))
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 10
+    e0.record()
+    for _ in range(n):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    alg_bytes = 4 * rows * C * 2          # read dZ, U, X ; write dV  (bf16) — SURVEY §8d "epilogue bwd"
+    achieved = alg_bytes / (ms * 1e-3) / 1e9
+    return {"roofline": {"bound": "hbm", "kernel": "bn_res_ln_bwd_kernel", "achieved": round(achieved, 1),
+                         "peak": pk["hbm_gbs"], "peak_source": pk["source"], "unit": "GB/s",
+                         "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": None,
+                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": round(ms, 4)}}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_step(C: int, clips: int, seed: int = 0):
+    """One fwd+bwd of the reference algorithm (oracle port: literal N x N attention, fp32, autograd) on the host."""
+    from oracle import tpavi_oracle as O
+    B = clips * F
+    g = torch.Generator().manual_seed(seed)
+    f4 = [torch.randn(B, C, HH, WW, generator=g) for _ in range(V)]
+    cl = [torch.randn(B, NCLS, HH, WW, generator=g) for _ in range(V)]
+    ct = [torch.randn(B, 1, HH, WW, generator=g) for _ in range(V)]
+    do = [torch.randn(B, C, HH, WW, generator=g) for _ in range(V)]
+    pg = O.init_params(C, seed=0, randomize_affine=True)
+    pl = O.init_params(C, seed=1, randomize_affine=True)
+    t0 = time.perf_counter()
+    O.fusion_fwd_bwd(f4, cl, ct, do, pg, pl)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(C: int, seconds: float = 15.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cpu_step(C, 1)                       # warm-up
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < 3 or (time.perf_counter() - t_start < seconds and len(times) < 20):
+        times.append(cpu_step(C, 1))
+    best = min(times)
+    return {"value": round(1.0 / best, 4), "unit": "clips/s", "cores": cores, "kind": "port",
+            "sample": f"1 clip (16 sequences x 3136 tokens, C={C}) fp32 fwd+bwd of the oracle port of the reference "
+                      f"algorithm (N x N attention materialised), best of {len(times)} after 1 warm-up"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    C = args.channels
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    for _ in range(max(args.warmup, 1)):
+        cpu_step(C, 1)
+    t0 = time.perf_counter()
+    steps = max(1, args.steps)
+    for _ in range(steps):
+        cpu_step(C, 1)
+    dt = (time.perf_counter() - t0) / steps
+    val = round(1.0 / dt, 4)
+    out = {
+        "impl": "reference", "metric": "fusion fwd+bwd clips/sec", "value": val, "unit": "clips/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": max(args.warmup, 1),
+        "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[1]: MGFM+MLFM modules only, 4 views x 16 frames x 28x28 tokens, C={C}, "
+                               "fwd+bwd, frames-as-batch; bounded sample: 1 clip per step on the host CPU"},
+        "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": "port",
+                         "sample": "1 clip per step, oracle port of the reference algorithm (fp32, N x N materialised)"},
+        "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=8, help="clips per GPU per step")
+    ap.add_argument("--channels", type=int, default=256)
+    ap.add_argument("--graph", type=int, default=1, help="replay the step from a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -505,6 +505,34 @@ GLF_API int glf_gemm_bf16(const void* A, const void* B, void* D, int M, int N, i
   return gemm(g, reinterpret_cast<cudaStream_t>(stream));
 }
 
+GLF_API int glf_bn_res_ln_fwd(int64_t rows, int C, const void* U, const void* X, const float* bn_a, const float* bn_b,
+                              const float* ln_w, const float* ln_b, void* Z, int z_dtype, float* mu, float* r,
+                              float eps, int accumulate, glf_stream_t stream) {
+  GLF_TRY(check_device_sm100());
+  GLF_TRY(check_ptr(X, "X"));
+  GLF_TRY(check_ptr(Z, "Z"));
+  if (rows <= 0) return set_error(GLF_ERR_INVALID, "empty input");
+  return bn_res_ln_fwd(reinterpret_cast<const bf16*>(U), reinterpret_cast<const bf16*>(X), bn_a, bn_b, ln_w, ln_b, Z,
+                       z_dtype, mu, r, rows, C, eps, accumulate, reinterpret_cast<cudaStream_t>(stream));
+}
+
+GLF_API int glf_bn_res_ln_bwd(int64_t rows, int C, const void* dZ, int dz_dtype, const void* U, const void* X,
+                              const float* bn_a, const float* bn_b, const float* bn_mean, const float* bn_rstd,
+                              const float* ln_w, const float* mu, const float* r, void* dV, float* part,
+                              int* nblocks_out, glf_stream_t stream) {
+  GLF_TRY(check_device_sm100());
+  GLF_TRY(check_ptr(dZ, "dZ"));
+  GLF_TRY(check_ptr(X, "X"));
+  GLF_TRY(check_ptr(dV, "dV"));
+  if (rows <= 0) return set_error(GLF_ERR_INVALID, "empty input");
+  if (nblocks_out) *nblocks_out = bn_res_ln_bwd_blocks(rows, C);
+  return bn_res_ln_bwd(dZ, dz_dtype, reinterpret_cast<const bf16*>(U), reinterpret_cast<const bf16*>(X), bn_a, bn_b,
+                       bn_mean, bn_rstd, ln_w, mu, r, reinterpret_cast<bf16*>(dV), part, rows, C,
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+GLF_API int glf_bn_res_ln_bwd_max_blocks(void) { return 148 * 2; }
+
 GLF_API int glf_transpose(const void* in, void* out, int batch, int R, int S, int in_dtype, int out_dtype,
                   glf_stream_t stream) {
   GLF_TRY(check_device_sm100());

@@ -1,0 +1,92 @@
+"""Data-parallel plumbing: one process per GPU, clips sharded by rank, one gradient all-reduce (NCCL over NVLink on
+the B200 box; gloo in CPU tests).  Replaces the reference's nn.DataParallel (R/main.py:155), which re-broadcasts all
+parameters every step and reduces gradients onto GPU 0.  The fusion path itself has no collective: attention is
+within one sample's tokens and BatchNorm statistics are per replica, as in the reference."""
+from __future__ import annotations
+
+import os
+from typing import Iterable, List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def env_rank_world() -> Tuple[int, int, int]:
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
+
+
+def init_process_group(backend: str = "nccl") -> Tuple[int, int, int]:
+    rank, local_rank, world = env_rank_world()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local_rank, world
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) slice of `n_items` clips owned by `rank`; sizes differ by at most one."""
+    if n_items < 0 or world < 1 or not (0 <= rank < world):
+        raise ValueError("bad shard arguments")
+    base, rem = divmod(n_items, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+class GradBucket:
+    """Flat fp32 bucket over a fixed parameter list: gradients are packed, all-reduced once, averaged, unpacked."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        self.numel = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+
+    def pack(self) -> torch.Tensor:
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is None:
+                self.flat[off:off + n].zero_()
+            else:
+                self.flat[off:off + n].copy_(p.grad.reshape(-1))
+            off += n
+        return self.flat
+
+    def unpack(self) -> None:
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            g = self.flat[off:off + n].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone().to(p.dtype)
+            else:
+                p.grad.copy_(g)
+            off += n
+
+    def allreduce_mean(self, group=None) -> None:
+        self.pack()
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.div_(dist.get_world_size(group))
+        self.unpack()
+
+
+def broadcast_buffers(module: torch.nn.Module, src: int = 0, group=None) -> None:
+    """Mirror nn.DataParallel's behaviour of keeping replica 0's BatchNorm running statistics."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return
+    for b in module.buffers():
+        dist.broadcast(b, src=src, group=group)
+
+
+def max_over_ranks(value_ms: float, device=None, group=None) -> float:
+    """Step time of a data-parallel job = the slowest rank."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return value_ms
+    t = torch.tensor([value_ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())

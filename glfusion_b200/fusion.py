@@ -1,0 +1,139 @@
+"""Fused global-local cross-view fusion: the hot-path section of ``Global_and_Local.forward``
+(R/models/ours.py:1802-1837) as one autograd node.
+
+    gate  a_v = sigmoid(w * max_c sigmoid(cls_v) * sigmoid(ctr_v))          ours.py:1802-1815
+    X_g   = cat_v f4_v ,  X_l = cat_v f4_v * a_v                              ours.py:1816-1820, 1826-1827
+    out_v = MGFM(X_g)[:, :, v] + MLFM(X_l)[:, :, v]                           ours.py:1821-1834
+
+Inputs are what the reference has at that point: per-view backbone features ``f4[v]`` [B,C,h,w] (NCHW), the
+classifier logits ``cls[v]`` [B,5,h,w] and the centerness logits ``ctr[v]`` [B,1,h,w] (both *before* the sigmoid).
+One gate+concat kernel produces both token-major operands, the two TPAVI blocks run on them, and the second block's
+LayerNorm epilogue accumulates into the first one's output (the `+` of ours.py:1834 costs no extra pass).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Sequence
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from .tpavi import TPAVIModule, _io_dtype, _stream_ptr, tpavi_backward_raw, tpavi_forward_raw
+
+
+def gate_concat_forward(f4: Sequence[torch.Tensor], cls: Sequence[torch.Tensor], ctr: Sequence[torch.Tensor],
+                        weight: float):
+    lib = L.load()
+    V = len(f4)
+    B, C_, h, w = f4[0].shape
+    dev = f4[0].device
+    if not all(t.is_cuda for t in list(f4) + list(cls) + list(ctr)):
+        raise L.GlfError("glfusion_b200 runs on CUDA (sm_100) tensors only; there is no CPU path")
+    f4 = [t.contiguous() for t in f4]
+    cls = [t.float().contiguous() for t in cls]
+    ctr = [t.float().contiguous() for t in ctr]
+    ncls = cls[0].shape[1]
+    xg = torch.empty((B, V, h, w, C_), dtype=torch.bfloat16, device=dev)
+    xl = torch.empty_like(xg)
+    gate = torch.empty((B, V, h, w), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.glf_gate_concat_fwd(B, C_, V, h, w, ncls, float(weight), _io_dtype(f4[0]), L.ptr_table(f4),
+                                        L.ptr_table(cls), L.ptr_table(ctr), L.ptr(xg), L.ptr(xl), L.ptr(gate),
+                                        _stream_ptr()))
+    return xg, xl, gate, f4, cls, ctr
+
+
+def gate_concat_backward(f4, cls, ctr, gate, dxg, dxl, weight: float):
+    lib = L.load()
+    V = len(f4)
+    B, C_, h, w = f4[0].shape
+    ncls = cls[0].shape[1]
+    df4 = [torch.empty_like(t) for t in f4]
+    dcls = [torch.empty_like(t) for t in cls]
+    dctr = [torch.empty_like(t) for t in ctr]
+    with torch.cuda.device(f4[0].device):
+        L.check(lib.glf_gate_concat_bwd(B, C_, V, h, w, ncls, float(weight), _io_dtype(f4[0]), L.ptr_table(f4),
+                                        L.ptr_table(cls), L.ptr_table(ctr), L.ptr(gate), L.ptr(dxg), L.ptr(dxl),
+                                        L.ptr_table(df4), L.ptr_table(dcls), L.ptr_table(dctr), _stream_ptr()))
+    return df4, dcls, dctr
+
+
+class _FusionFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fusion, V, ng, *tensors):
+        f4, cls, ctr = tensors[:V], tensors[V:2 * V], tensors[2 * V:3 * V]
+        pg, pl = tensors[3 * V:3 * V + ng], tensors[3 * V + ng:]
+        mg, ml = fusion.global_attn, fusion.local_attn
+        xg, xl, gate, f4c, clsc, ctrc = gate_concat_forward(f4, cls, ctr, fusion.center_aware_weight)
+        B, V_, h, w, C_ = xg.shape
+        need = torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+        tg, tl = mg._param_table(pg), ml._param_table(pl)
+        shape = (B, V_, h, w, C_)
+        zsum, stg, svg, _ = tpavi_forward_raw(xg, tg, mg._buffer_table(), mode=mg._mode_id, training=mg.training,
+                                              bn_layer=mg._bn_layer, Ci=mg.inter_channels, keep_for_backward=need,
+                                              token_shape=shape)
+        _, stl, svl, _ = tpavi_forward_raw(xl, tl, ml._buffer_table(), mode=ml._mode_id, training=ml.training,
+                                           bn_layer=ml._bn_layer, Ci=ml.inter_channels, keep_for_backward=need,
+                                           z_out=zsum, accumulate=True, token_shape=shape)
+        ctx.fusion, ctx.V, ctx.ng = fusion, V, ng
+        ctx.states = (stg, svg, stl, svl)
+        ctx.io_dtype = f4[0].dtype
+        ctx.save_for_backward(xg, xl, gate, *f4c, *clsc, *ctrc, *pg, *pl)
+        out = zsum if zsum.dtype == f4[0].dtype else zsum.to(f4[0].dtype)
+        return out.permute(0, 4, 1, 2, 3)          # [B, C, V, h, w] view of the token-major buffer
+
+    @staticmethod
+    def backward(ctx, dout):
+        V, ng = ctx.V, ctx.ng
+        saved = ctx.saved_tensors
+        xg, xl, gate = saved[:3]
+        rest = saved[3:]
+        f4, cls, ctr = rest[:V], rest[V:2 * V], rest[2 * V:3 * V]
+        pg, pl = rest[3 * V:3 * V + ng], rest[3 * V + ng:]
+        mg, ml = ctx.fusion.global_attn, ctx.fusion.local_attn
+        stg, svg, stl, svl = ctx.states
+        if svg is None:
+            raise L.GlfError("backward called on a forward that ran without grad")
+        dz = dout.permute(0, 2, 3, 4, 1)
+        if dz.dtype != torch.bfloat16:
+            dz = dz.to(torch.bfloat16)
+        dz = dz.contiguous()                        # token-major [B,V,h,w,C]; both blocks see the same dz (ours.py:1834)
+        dxg, gg = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xg, stg, svg, mg._param_table(pg), mg._buffer_table())
+        dxl, gl = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xl, stl, svl, ml._param_table(pl), ml._buffer_table())
+        df4, dcls, dctr = gate_concat_backward(f4, cls, ctr, gate, dxg, dxl, ctx.fusion.center_aware_weight)
+        out = [None, None, None] + list(df4) + list(dcls) + list(dctr)
+        for mod, plist, gr in ((mg, pg, gg), (ml, pl, gl)):
+            for name, p in zip(mod._plist_names(), plist):
+                t = gr[mod._grad_key(name)].reshape(p.shape)
+                out.append(t if p.dtype == torch.float32 else t.to(p.dtype))
+        return tuple(out)
+
+
+class GlobalLocalFusion(nn.Module):
+    """MGFM + MLFM (attribute names follow ``Global_and_Local``: ``global_attn`` / ``local_attn``, ours.py:1746-1747,
+    so the corresponding slice of a reference checkpoint loads unchanged)."""
+
+    def __init__(self, in_channels: int = 2048, mode: str = 'dot', center_aware_weight: float = 20,
+                 inter_channels=None):
+        super().__init__()
+        self.center_aware_weight = center_aware_weight
+        self.global_attn = TPAVIModule(in_channels=in_channels, inter_channels=inter_channels, mode=mode)
+        self.local_attn = TPAVIModule(in_channels=in_channels, inter_channels=inter_channels, mode=mode)
+
+    def forward_stacked(self, f4: Sequence[torch.Tensor], cls_logits: Sequence[torch.Tensor],
+                        ctr_logits: Sequence[torch.Tensor]) -> torch.Tensor:
+        """Returns f4_fusion stacked over views: [B, C, V, h, w] (memory is token-major [B,V,h,w,C])."""
+        V = len(f4)
+        if not (len(cls_logits) == V and len(ctr_logits) == V and V >= 1):
+            raise ValueError("f4, cls_logits and ctr_logits need one entry per view")
+        pg, pl = self.global_attn._plist(), self.local_attn._plist()
+        return _FusionFunction.apply(self, V, len(pg), *f4, *cls_logits, *ctr_logits, *pg, *pl)
+
+    def forward(self, f4: Dict[str, torch.Tensor], mask_bb_logits: Dict[str, torch.Tensor],
+                ctr_logits: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Dict-keyed like the reference (view id -> tensor): returns f4_fusion[view] = global + local."""
+        views: List[str] = list(f4.keys())
+        out = self.forward_stacked([f4[v] for v in views], [mask_bb_logits[v] for v in views],
+                                   [ctr_logits[v] for v in views])
+        return {v: out[:, :, i] for i, v in enumerate(views)}

@@ -145,6 +145,21 @@ GLF_API int glf_gemm_bf16(const void* A, const void* B, void* D, int M, int N, i
                   const float* bias, float alpha, const void* addend, int64_t ld_add, int64_t stride_add,
                   int out_kind, int split_k, float* colstats, glf_stream_t stream);
 
+/* The two HBM-bound fused epilogues as standalone entry points (unit tests, roofline probes).
+ *   fwd: Z = LayerNorm_C(bn_a * U + bn_b + X) * ln_w + ln_b   (ours.py:908-915 after the W_z GEMM); U, X bf16 [rows, C];
+ *        Z [rows, C] of z_dtype; mu, r: per-row LayerNorm mean / rstd (kept for backward).
+ *   bwd: dV = d(pre-LayerNorm sum) [rows, C] bf16, and per-CTA partials [nblocks][4][C] of
+ *        (d ln_w, d ln_b, d bn_gamma, d bn_beta); *nblocks_out receives the number of partial rows written.
+ *        `part` must hold glf_bn_res_ln_bwd_max_blocks() * 4 * C floats. */
+GLF_API int glf_bn_res_ln_fwd(int64_t rows, int C, const void* U, const void* X, const float* bn_a, const float* bn_b,
+                      const float* ln_w, const float* ln_b, void* Z, int z_dtype, float* mu, float* r, float eps,
+                      int accumulate, glf_stream_t stream);
+GLF_API int glf_bn_res_ln_bwd(int64_t rows, int C, const void* dZ, int dz_dtype, const void* U, const void* X,
+                      const float* bn_a, const float* bn_b, const float* bn_mean, const float* bn_rstd,
+                      const float* ln_w, const float* mu, const float* r, void* dV, float* part, int* nblocks_out,
+                      glf_stream_t stream);
+GLF_API int glf_bn_res_ln_bwd_max_blocks(void);
+
 /* out[b, s, r] = in[b, r, s] with dtype conversion (NCTHW <-> token-major packing). dtypes: GLF_DTYPE_*. */
 GLF_API int glf_transpose(const void* in, void* out, int batch, int R, int S, int in_dtype, int out_dtype,
                   glf_stream_t stream);

@@ -1,0 +1,58 @@
+"""Helpers shared by the -m gpu parity tests: they call the CUDA path through the C ABI / the nn.Module and compare
+with the CPU oracle (oracle/tpavi_oracle.py) on the same seeded inputs."""
+import ctypes as C
+
+import torch
+
+from glfusion_b200 import _lib as L
+from oracle import tpavi_oracle as O
+
+BF16_TOL = 2e-2      # north_star: within 2e-2 relative error in bf16
+DEV = "cuda:0"
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def gemm(A, B, M, N, K, batch=1, a_mn=0, b_mn=0, out_kind=0, split_k=1, bias=None, alpha=1.0, addend=None,
+         colstats=False, shared_b=False):
+    """A: [batch, M, K] (a_mn=0) or [batch, K, M] (a_mn=1); B likewise with N.  Returns (D, colstats or None)."""
+    lib = L.load()
+    lda = A.shape[-1]
+    ldb = B.shape[-1]
+    sA = A.shape[-2] * A.shape[-1]
+    sB = 0 if shared_b else B.shape[-2] * B.shape[-1]
+    D = torch.zeros((batch, M, N), dtype=torch.bfloat16 if out_kind == 0 else torch.float32, device=A.device)
+    cs = None
+    if colstats:
+        cs = torch.zeros((batch * ((M + 127) // 128), 2, N), dtype=torch.float32, device=A.device)
+    L.check(lib.glf_gemm_bf16(L.ptr(A), L.ptr(B), L.ptr(D), M, N, K, batch, a_mn, b_mn, lda, ldb, N, sA, sB, M * N,
+                              L.ptr(bias), float(alpha), L.ptr(addend), N, M * N, out_kind, split_k, L.ptr(cs),
+                              stream()))
+    torch.cuda.synchronize()
+    return D, cs
+
+
+def load_module_from_params(cls, params, C_, mode, bn_layer, device=DEV):
+    m = cls(in_channels=C_, mode=mode, bn_layer=bn_layer)
+    m.load_state_dict({k: v.clone() for k, v in params.items()}, strict=True)
+    return m.to(device)
+
+
+def golden_params(g, prefix="param:"):
+    p = {}
+    for k, v in g.items():
+        if k.startswith(prefix):
+            p[k[len(prefix):]] = v.clone() if isinstance(v, torch.Tensor) else torch.tensor(v.item())
+    return p
+
+
+def assert_close(name, got, ref, tol, abs_floor=0.0):
+    got = got.detach().float().cpu()
+    ref = ref.detach().float().cpu()
+    if abs_floor > 0 and ref.abs().max() < abs_floor:
+        assert got.abs().max() < 10 * abs_floor + 1e-2, f"{name}: expected ~0, got max {got.abs().max()}"
+        return
+    err = O.rel_err(got, ref)
+    assert err < tol, f"{name}: rel err {err:.3e} >= {tol:.1e}"

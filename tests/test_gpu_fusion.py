@@ -1,0 +1,69 @@
+"""Gate + concat + MGFM + MLFM + sum (GlobalLocalFusion) against the glue golden (reference lines ours.py:1802-1834
+run around two reference modules) and the CPU oracle."""
+import pytest
+import torch
+
+from conftest import load_golden
+from gpu_util import BF16_TOL, DEV, assert_close, golden_params
+from glfusion_b200 import GlobalLocalFusion
+from oracle import tpavi_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(C, pg, pl):
+    f = GlobalLocalFusion(in_channels=C)
+    f.global_attn.load_state_dict({k: v.clone() for k, v in pg.items()}, strict=True)
+    f.local_attn.load_state_dict({k: v.clone() for k, v in pl.items()}, strict=True)
+    return f.to(DEV).train()
+
+
+@pytest.mark.parametrize("io", ["fp32", "bf16"])
+def test_glue_golden(io):
+    g = load_golden("glue_dot_c128")
+    B, C, V, h, w = [int(v) for v in g["meta"]]
+    dt = torch.float32 if io == "fp32" else torch.bfloat16
+    f = _build(C, golden_params(g, "param_g:"), golden_params(g, "param_l:"))
+    f4 = [g[f"f4:{v}"].to(DEV, dt).requires_grad_(True) for v in range(V)]
+    cl = [g[f"cls:{v}"].to(DEV).requires_grad_(True) for v in range(V)]
+    ct = [g[f"ctr:{v}"].to(DEV).requires_grad_(True) for v in range(V)]
+    out = f({str(v): f4[v] for v in range(V)}, {str(v): cl[v] for v in range(V)}, {str(v): ct[v] for v in range(V)})
+    torch.autograd.backward([out[str(v)] for v in range(V)], [g[f"d_out:{v}"].to(DEV, dt) for v in range(V)])
+    torch.cuda.synchronize()
+    for v in range(V):
+        assert_close(f"out:{v}", out[str(v)], g[f"out:{v}"], BF16_TOL)
+        assert_close(f"df4:{v}", f4[v].grad, g[f"df4:{v}"], BF16_TOL)
+        assert_close(f"dcls:{v}", cl[v].grad, g[f"dcls:{v}"], 4e-2)
+        assert_close(f"dctr:{v}", ct[v].grad, g[f"dctr:{v}"], 4e-2)
+    for tag, mod in (("g", f.global_attn), ("l", f.local_attn)):
+        for k, p in mod.named_parameters():
+            if not k.startswith("align_channel"):
+                assert_close(f"grad_{tag}:{k}", p.grad, g[f"grad_{tag}:{k}"], 3e-2, abs_floor=1e-3)
+
+
+def test_cfg2_shape_against_oracle():
+    """4 views x 28x28 tokens x C=256 (BASELINE cfg2 token geometry), 2 frames as batch, seeded oracle comparison."""
+    B, C, V, h, w = 2, 256, 4, 28, 28
+    pg = O.init_params(C, seed=31, randomize_affine=True)
+    pl = O.init_params(C, seed=32, randomize_affine=True)
+    gen = torch.Generator().manual_seed(33)
+    f4 = [torch.randn(B, C, h, w, generator=gen) for _ in range(V)]
+    cl = [torch.randn(B, 5, h, w, generator=gen) for _ in range(V)]
+    ct = [torch.randn(B, 1, h, w, generator=gen) for _ in range(V)]
+    do = [torch.randn(B, C, h, w, generator=gen) for _ in range(V)]
+    outs, df4, dcls, dctr, gg, gl = O.fusion_fwd_bwd(f4, cl, ct, do, {k: v.clone() for k, v in pg.items()},
+                                                     {k: v.clone() for k, v in pl.items()})
+    f = _build(C, pg, pl)
+    f4d = [t.to(DEV, torch.bfloat16).requires_grad_(True) for t in f4]
+    cld = [t.to(DEV).requires_grad_(True) for t in cl]
+    ctd = [t.to(DEV).requires_grad_(True) for t in ct]
+    out = f.forward_stacked(f4d, cld, ctd)
+    out.backward(torch.stack(do, dim=2).to(DEV, torch.bfloat16))
+    torch.cuda.synchronize()
+    for v in range(V):
+        assert_close(f"out:{v}", out[:, :, v], outs[v], BF16_TOL)
+        assert_close(f"df4:{v}", f4d[v].grad, df4[v], BF16_TOL)
+        assert_close(f"dctr:{v}", ctd[v].grad, dctr[v], 4e-2)
+    for k, p in f.local_attn.named_parameters():
+        if not k.startswith("align_channel"):
+            assert_close("grad_l:" + k, p.grad, gl[k], 3e-2, abs_floor=1e-3)

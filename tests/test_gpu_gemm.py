@@ -1,0 +1,96 @@
+"""tcgen05 GEMM building block (glf_gemm_bf16) vs torch fp32 matmul on bf16-rounded operands."""
+import pytest
+import torch
+
+from gpu_util import DEV, gemm
+from oracle import tpavi_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(batch, rows, K, mn, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    t = torch.randn(batch, rows, K, generator=g).to(torch.bfloat16)
+    dev = t.to(DEV)
+    return (dev.transpose(1, 2).contiguous() if mn else dev), t.float()
+
+
+@pytest.mark.parametrize("M,N,K,batch,a_mn,b_mn", [
+    (128, 128, 64, 1, 0, 0),          # one tile, one k-block
+    (256, 384, 256, 1, 0, 0),         # projection shape (C=256 -> 3C')
+    (300, 256, 128, 2, 0, 0),         # ragged M, BN=256, batched (U = Theta W'^T)
+    (128, 64, 192, 1, 0, 0),          # BN=64
+    (128, 128, 200, 1, 0, 0),         # ragged K (TMA zero fill)
+    (128, 128, 256, 3, 1, 1),         # token contraction, both MN-major (Phi^T G)
+    (256, 128, 105, 2, 1, 1),         # ragged K with MN-major operands
+    (384, 256, 512, 1, 1, 1),         # dWcat shape
+    (200, 128, 128, 1, 0, 1),
+    (128, 256, 128, 1, 1, 0),
+    (3136, 384, 256, 1, 0, 0),        # cfg2 one frame
+])
+def test_gemm_bf16_out(M, N, K, batch, a_mn, b_mn):
+    A, Af = _mk(batch, M, K, a_mn, 1)
+    B, Bf = _mk(batch, N, K, b_mn, 2)
+    D, _ = gemm(A, B, M, N, K, batch, a_mn, b_mn)
+    ref = torch.matmul(Af, Bf.transpose(1, 2))
+    assert O.rel_err(D, ref) < 6e-3
+
+
+def test_gemm_bias_alpha_addend_colstats():
+    M, N, K, batch = 333, 256, 128, 2
+    A, Af = _mk(batch, M, K, 0, 3)
+    B, Bf = _mk(batch, N, K, 0, 4)
+    bias = torch.randn(N, device=DEV)
+    add = torch.randn(batch, M, N, device=DEV).to(torch.bfloat16)
+    D, cs = gemm(A, B, M, N, K, batch, bias=bias, alpha=0.5, colstats=True)
+    ref = 0.5 * torch.matmul(Af, Bf.transpose(1, 2)) + bias.cpu()
+    assert O.rel_err(D, ref) < 6e-3
+    tiles = (M + 127) // 128
+    cs = cs.view(batch, tiles, 2, N).sum(1).cpu()
+    Dr = D.float().cpu()
+    assert O.rel_err(cs[:, 0], Dr.sum(1)) < 1e-4            # statistics are of the stored (bf16-rounded) values
+    assert O.rel_err(cs[:, 1], (Dr * Dr).sum(1)) < 1e-4
+    D2, _ = gemm(A, B, M, N, K, batch, bias=bias, alpha=0.5, addend=add)
+    assert O.rel_err(D2, ref + add.float().cpu()) < 6e-3
+
+
+def test_gemm_shared_b_and_strided_a():
+    # A is a column slice of a wider buffer (Theta inside P=[Theta|Phi|G]): leading dimension != K
+    import ctypes as C
+    from glfusion_b200 import _lib as L
+    from gpu_util import stream
+    M, N, K = 256, 256, 128
+    P = torch.randn(M, 3 * K, device=DEV).to(torch.bfloat16)
+    W = torch.randn(N, K, device=DEV).to(torch.bfloat16)
+    D = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+    A = P[:, K:2 * K]
+    L.check(L.load().glf_gemm_bf16(C.c_void_p(A.data_ptr()), L.ptr(W), L.ptr(D), M, N, K, 1, 0, 0, 3 * K, K, N, 0, 0, 0,
+                                   None, 1.0, None, 0, 0, 0, 1, None, stream()))
+    torch.cuda.synchronize()
+    assert O.rel_err(D, A.float() @ W.float().T) < 6e-3
+
+
+@pytest.mark.parametrize("split_k", [1, 4, 13])
+def test_gemm_splitk_fp32_atomic(split_k):
+    M, N, K, batch = 128, 128, 3136, 2
+    A, Af = _mk(batch, M, K, 1, 5)
+    B, Bf = _mk(batch, N, K, 1, 6)
+    D, _ = gemm(A, B, M, N, K, batch, 1, 1, out_kind=2, split_k=split_k, alpha=1.0 / K)
+    ref = torch.matmul(Af, Bf.transpose(1, 2)) / K
+    assert O.rel_err(D, ref) < 1e-5
+    D1, _ = gemm(A, B, M, N, K, batch, 1, 1, out_kind=1, split_k=1)
+    assert O.rel_err(D1, ref * K) < 1e-5
+
+
+def test_transpose_pack_roundtrip():
+    import ctypes as C
+    from glfusion_b200 import _lib as L
+    from gpu_util import stream
+    x = torch.randn(3, 40, 105, device=DEV)
+    out = torch.empty(3, 105, 40, dtype=torch.bfloat16, device=DEV)
+    L.check(L.load().glf_transpose(L.ptr(x), L.ptr(out), 3, 40, 105, L.DTYPE_F32, L.DTYPE_BF16, stream()))
+    back = torch.empty(3, 40, 105, device=DEV)
+    L.check(L.load().glf_transpose(L.ptr(out), L.ptr(back), 3, 105, 40, L.DTYPE_BF16, L.DTYPE_F32, stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out, x.transpose(1, 2).to(torch.bfloat16))
+    assert torch.equal(back, x.to(torch.bfloat16).float())
