@@ -42,14 +42,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
-// Bounded wait: a protocol bug traps (launch failure reported to the host) instead of hanging the GPU.
-#ifndef GLF_SPIN_LIMIT
-#define GLF_SPIN_LIMIT (1u << 26)
+// Bounded wait: a protocol bug traps after ~2 s of wall clock (launch failure reported to the host) instead of
+// hanging the GPU.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#ifndef GLF_WAIT_TIMEOUT_NS
+#define GLF_WAIT_TIMEOUT_NS 2000000000ull
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > GLF_SPIN_LIMIT) __trap();
+    if (++spins > 2048u) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) {
+        t0 = now;
+      } else if (now - t0 > GLF_WAIT_TIMEOUT_NS) {
+        __trap();
+      }
+    }
   }
 }
 
