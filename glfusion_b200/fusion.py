@@ -67,7 +67,7 @@ class _FusionFunction(torch.autograd.Function):
         mg, ml = fusion.global_attn, fusion.local_attn
         xg, xl, gate, f4c, clsc, ctrc = gate_concat_forward(f4, cls, ctr, fusion.center_aware_weight)
         B, V_, h, w, C_ = xg.shape
-        need = torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+        need = any(ctx.needs_input_grad)
         tg, tl = mg._param_table(pg), ml._param_table(pl)
         shape = (B, V_, h, w, C_)
         zsum, stg, svg, _ = tpavi_forward_raw(xg, tg, mg._buffer_table(), mode=mg._mode_id, training=mg.training,

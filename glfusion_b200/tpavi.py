@@ -148,7 +148,7 @@ class _TPAVIFunction(torch.autograd.Function):
     def forward(ctx, x, module, *plist):
         params = module._param_table(plist)
         buffers = module._buffer_table()
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in plist))
+        need_grad = any(ctx.needs_input_grad)      # grad mode is off inside Function.forward
         z, st, saved, x_used = tpavi_forward_raw(x, params, buffers, mode=module._mode_id,
                                                  training=module.training, bn_layer=module._bn_layer,
                                                  Ci=module.inter_channels, keep_for_backward=need_grad)
