@@ -51,6 +51,11 @@ def golden_params(g, prefix="param:"):
 def assert_close(name, got, ref, tol, abs_floor=0.0):
     got = got.detach().float().cpu()
     ref = ref.detach().float().cpu()
+    if name.endswith("W_z.0.bias") and got.abs().max() == 0:
+        # train-mode BatchNorm cancels any per-channel shift of U: the gradient is analytically zero; the kernels
+        # return exactly 0 and the reference returns fp32 summation noise that grows with the token count
+        assert ref.abs().max() < 0.5, f"{name}: reference value is not noise ({ref.abs().max()})"
+        return
     if abs_floor > 0 and ref.abs().max() < abs_floor:
         assert got.abs().max() < 10 * abs_floor + 1e-2, f"{name}: expected ~0, got max {got.abs().max()}"
         return
