@@ -98,8 +98,8 @@ int make_dims(const glf_desc* d, Dims* o) {
 }
 
 struct Saved {
-  bf16 *xtok, *P, *Y, *U, *Wp, *WpT, *wcat, *wcatT, *wz, *wzT;
-  float *lse, *M, *bcat, *bn_mean, *bn_rstd, *bn_a, *bn_b, *ln_mu, *ln_r;
+  bf16 *xtok, *P, *Y, *U, *Mb, *Wp, *wcat, *wcatT, *wz, *wzT;
+  float *lse, *bcat, *bn_mean, *bn_rstd, *bn_a, *bn_b, *ln_mu, *ln_r;
 };
 size_t carve_saved(const Dims& m, void* base, Saved* s) {
   Carver c(base);
@@ -109,13 +109,12 @@ size_t carve_saved(const Dims& m, void* base, Saved* s) {
   s->U = c.take<bf16>(rows * C);
   if (m.dot) {
     s->Y = nullptr; s->lse = nullptr;
-    s->M = c.take<float>(B * Ci * Ci);
+    s->Mb = c.take<bf16>(B * Ci * Ci);
     s->Wp = c.take<bf16>(B * C * Ci);
-    s->WpT = c.take<bf16>(B * Ci * C);
   } else {
     s->Y = c.take<bf16>(rows * Ci);
     s->lse = c.take<float>(rows);
-    s->M = nullptr; s->Wp = nullptr; s->WpT = nullptr;
+    s->Mb = nullptr; s->Wp = nullptr;
   }
   s->wcat = c.take<bf16>(3 * Ci * C);
   s->wcatT = c.take<bf16>(3 * Ci * C);
@@ -131,18 +130,19 @@ size_t carve_saved(const Dims& m, void* base, Saved* s) {
   return (c.off + 255) & ~static_cast<size_t>(255);
 }
 
-struct WsFwd { float* colstats; void* saved_fallback; };
+struct WsFwd { float* colstats; float* Mf; void* saved_fallback; };
 size_t carve_ws_fwd(const Dims& m, void* base, WsFwd* w, size_t saved_bytes) {
   Carver c(base);
   const size_t np = m.dot ? static_cast<size_t>(m.B) * m.tiles_seq : static_cast<size_t>(m.tiles_all);
   w->colstats = c.take<float>(np * 2 * m.C);
+  w->Mf = m.dot ? c.take<float>(static_cast<size_t>(m.B) * m.Ci * m.Ci) : nullptr;  // split-K accumulation target
   w->saved_fallback = c.take<uint8_t>(saved_bytes);  // used when the caller passes saved == NULL (inference)
   return (c.off + 255) & ~static_cast<size_t>(255);
 }
 
 struct WsBwd {
-  bf16 *dztok, *dV, *dU, *dP, *dY, *dxtok, *dM, *dMT;
-  float *dWp, *part_ln, *k1, *k2, *k3, *cs_t, *cs_p, *cs_g, *dwcat, *delta;
+  bf16 *dztok, *dV, *dU, *dP, *dY, *dxtok, *dM, *dWpb;
+  float *dWpf, *part_ln, *k1, *k2, *k3, *cs_t, *cs_p, *cs_g, *dwcat, *delta;
 };
 size_t carve_ws_bwd(const glf_desc* d, const Dims& m, void* base, WsBwd* w) {
   Carver c(base);
@@ -154,13 +154,13 @@ size_t carve_ws_bwd(const glf_desc* d, const Dims& m, void* base, WsBwd* w) {
   w->dxtok = m.pack_x ? c.take<bf16>(rows * C) : nullptr;
   if (m.dot) {
     w->dY = nullptr; w->delta = nullptr;
-    w->dWp = c.take<float>(B * C * Ci);
+    w->dWpf = c.take<float>(B * C * Ci);
+    w->dWpb = c.take<bf16>(B * C * Ci);
     w->dM = c.take<bf16>(B * Ci * Ci);
-    w->dMT = c.take<bf16>(B * Ci * Ci);
   } else {
     w->dY = c.take<bf16>(rows * Ci);
     w->delta = c.take<float>(rows);
-    w->dWp = nullptr; w->dM = nullptr; w->dMT = nullptr;
+    w->dWpf = nullptr; w->dWpb = nullptr; w->dM = nullptr;
   }
   w->part_ln = c.take<float>(static_cast<size_t>(bn_res_ln_bwd_blocks(m.rows, m.C)) * 4 * C);
   w->k1 = c.take<float>(C);
@@ -176,6 +176,7 @@ size_t carve_ws_bwd(const glf_desc* d, const Dims& m, void* base, WsBwd* w) {
 
 int pick_split(long long tiles, int K) {
   const int kb = (K + 63) / 64;
+  if (tiles >= 96) return 1;  // enough CTAs already: write the result directly, no atomics
   long long s = (2 * 148 + tiles - 1) / tiles;
   if (s < 1) s = 1;
   if (s > kb) s = kb;
@@ -260,21 +261,35 @@ GLF_API int glf_tpavi_fwd(const glf_desc* d, const void* x, const glf_weights* w
   }
   int np = 0;
   if (m.dot) {
-    GLF_TRY(check_cuda(cudaMemsetAsync(s.M, 0, sizeof(float) * B * Ci * Ci, stream), "memset M"));
-    {  // M_b[i,j] = sum_n Phi[n,i] G[n,j] / N
+    const long long CiCi = static_cast<long long>(Ci) * Ci;
+    {  // M_b[i,j] = sum_n Phi[n,i] G[n,j] / N      (token contraction: both operands MN-major views of P)
       GemmArgs g;
       g.A = opnd(s.P + Ci, 1, 3 * Ci, static_cast<long long>(N) * 3 * Ci);
       g.B = opnd(s.P + 2 * Ci, 1, 3 * Ci, static_cast<long long>(N) * 3 * Ci);
       g.M = Ci; g.N = Ci; g.K = N; g.batch = B;
       g.alpha = 1.f / static_cast<float>(N);
-      g.out_kind = 2;
-      g.D = s.M; g.ldd = Ci; g.strideD = static_cast<long long>(Ci) * Ci;
+      g.ldd = Ci; g.strideD = CiCi;
       g.split_k = pick_split(static_cast<long long>(B) * ((Ci + 127) / 128) * ((Ci + 127) / 128), N);
+      if (g.split_k > 1) {
+        GLF_TRY(check_cuda(cudaMemsetAsync(wf.Mf, 0, sizeof(float) * B * CiCi, stream), "memset M"));
+        g.out_kind = 2;
+        g.D = wf.Mf;
+        GLF_TRY(gemm(g, stream));
+        GLF_TRY(cast_bf16(wf.Mf, s.Mb, B * CiCi, stream));
+      } else {
+        g.out_kind = 0;
+        g.D = s.Mb;
+        GLF_TRY(gemm(g, stream));
+      }
+    }
+    {  // W'_b[c,i] = sum_j Wz[c,j] M_b[i,j]        (folds Y = Theta M and U = Y Wz^T into one product per token)
+      GemmArgs g;
+      g.A = opnd(s.wz, 0, Ci, 0);
+      g.B = opnd(s.Mb, 0, Ci, CiCi);
+      g.M = C; g.N = Ci; g.K = Ci; g.batch = B;
+      g.D = s.Wp; g.ldd = Ci; g.strideD = static_cast<long long>(C) * Ci;
       GLF_TRY(gemm(g, stream));
     }
-    // W'_b[c,i] = sum_j Wz[c,j] M_b[i,j]
-    GLF_TRY(small_gemm(w->wz_w, Ci, 1, 0, 0, s.M, 1, Ci, static_cast<long long>(Ci) * Ci, 0, B, 1, C, Ci, Ci, 1.f,
-                       nullptr, s.Wp, s.WpT, stream));
     {  // U_b = Theta_b W'_b^T + bz   (+ BatchNorm column statistics)
       GemmArgs g;
       g.A = opnd(s.P, 0, 3 * Ci, static_cast<long long>(N) * 3 * Ci);
@@ -348,46 +363,68 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
   }
   int np = 0;
   if (m.dot) {
-    {  // dTheta_b = dU_b W'_b
+    const long long CiCi = static_cast<long long>(Ci) * Ci;
+    const long long CCi = static_cast<long long>(C) * Ci;
+    {  // dTheta_b = dU_b W'_b          (B operand = W'_b read MN-major: stored [K=c][N=i])
       GemmArgs g;
       g.A = opnd(dU, 0, C, static_cast<long long>(N) * C);
-      g.B = opnd(s.WpT, 0, C, static_cast<long long>(Ci) * C);
+      g.B = opnd(s.Wp, 1, Ci, CCi);
       g.M = N; g.N = Ci; g.K = C; g.batch = B;
       g.D = wb.dP; g.ldd = 3 * Ci; g.strideD = seqP;
       g.colstats = wb.cs_t;
       GLF_TRY(gemm(g, stream));
     }
-    GLF_TRY(check_cuda(cudaMemsetAsync(wb.dWp, 0, sizeof(float) * B * C * Ci, stream), "memset dW'"));
     {  // dW'_b[c,i] = sum_n dU[n,c] Theta[n,i]
       GemmArgs g;
       g.A = opnd(dU, 1, C, static_cast<long long>(N) * C);
       g.B = opnd(s.P, 1, 3 * Ci, seqP);
       g.M = C; g.N = Ci; g.K = N; g.batch = B;
-      g.out_kind = 2;
-      g.D = wb.dWp; g.ldd = Ci; g.strideD = static_cast<long long>(C) * Ci;
+      g.ldd = Ci; g.strideD = CCi;
       g.split_k = pick_split(static_cast<long long>(B) * ((C + 127) / 128) * ((Ci + 127) / 128), N);
+      if (g.split_k > 1) {
+        GLF_TRY(check_cuda(cudaMemsetAsync(wb.dWpf, 0, sizeof(float) * B * CCi, stream), "memset dW'"));
+        g.out_kind = 2;
+        g.D = wb.dWpf;
+        GLF_TRY(gemm(g, stream));
+        GLF_TRY(cast_bf16(wb.dWpf, wb.dWpb, B * CCi, stream));
+      } else {
+        g.out_kind = 0;
+        g.D = wb.dWpb;
+        GLF_TRY(gemm(g, stream));
+      }
+    }
+    GLF_TRY(check_cuda(cudaMemsetAsync(g_->wz_w, 0, sizeof(float) * CCi, stream), "memset dWz"));
+    {  // dWz[c,j] = sum_b sum_i dW'_b[c,i] M_b[i,j]     (batch reduced by fp32 red.add into one output)
+      GemmArgs g;
+      g.A = opnd(wb.dWpb, 0, Ci, CCi);
+      g.B = opnd(s.Mb, 1, Ci, CiCi);
+      g.M = C; g.N = Ci; g.K = Ci; g.batch = B;
+      g.out_kind = 2;
+      g.D = g_->wz_w; g.ldd = Ci; g.strideD = 0;
       GLF_TRY(gemm(g, stream));
     }
-    // dWz[c,j] = sum_b sum_i dW'_b[c,i] M_b[i,j]
-    GLF_TRY(small_gemm(wb.dWp, Ci, 1, 0, static_cast<long long>(C) * Ci, s.M, Ci, 1, 0, static_cast<long long>(Ci) * Ci,
-                       1, B, C, Ci, Ci, 1.f, g_->wz_w, nullptr, nullptr, stream));
-    // dM_b[i,j] = sum_c dW'_b[c,i] Wz[c,j]
-    GLF_TRY(small_gemm(wb.dWp, 1, Ci, static_cast<long long>(C) * Ci, 0, w->wz_w, Ci, 1, 0, 0, B, 1, Ci, Ci, C, 1.f,
-                       nullptr, wb.dM, wb.dMT, stream));
+    {  // dM_b[i,j] = sum_c dW'_b[c,i] Wz[c,j]
+      GemmArgs g;
+      g.A = opnd(wb.dWpb, 1, Ci, CCi);
+      g.B = opnd(s.wz, 1, Ci, 0);
+      g.M = Ci; g.N = Ci; g.K = C; g.batch = B;
+      g.D = wb.dM; g.ldd = Ci; g.strideD = CiCi;
+      GLF_TRY(gemm(g, stream));
+    }
     {  // dPhi_b = G_b dM_b^T / N
       GemmArgs g;
       g.A = opnd(s.P + 2 * Ci, 0, 3 * Ci, seqP);
-      g.B = opnd(wb.dM, 0, Ci, static_cast<long long>(Ci) * Ci);
+      g.B = opnd(wb.dM, 0, Ci, CiCi);
       g.M = N; g.N = Ci; g.K = Ci; g.batch = B;
       g.alpha = 1.f / static_cast<float>(N);
       g.D = wb.dP + Ci; g.ldd = 3 * Ci; g.strideD = seqP;
       g.colstats = wb.cs_p;
       GLF_TRY(gemm(g, stream));
     }
-    {  // dG_b = Phi_b dM_b / N
+    {  // dG_b = Phi_b dM_b / N          (B operand = dM_b read MN-major)
       GemmArgs g;
       g.A = opnd(s.P + Ci, 0, 3 * Ci, seqP);
-      g.B = opnd(wb.dMT, 0, Ci, static_cast<long long>(Ci) * Ci);
+      g.B = opnd(wb.dM, 1, Ci, CiCi);
       g.M = N; g.N = Ci; g.K = Ci; g.batch = B;
       g.alpha = 1.f / static_cast<float>(N);
       g.D = wb.dP + 2 * Ci; g.ldd = 3 * Ci; g.strideD = seqP;

@@ -1,6 +1,6 @@
 // glf_eltwise.cu — the HBM-bound kernels of the fusion path: layout packing, weight preparation, BatchNorm
 // statistics finalisation, fused BN-normalise + residual + LayerNorm forward/backward, BN-backward apply,
-// small fp32 batched products on C' x C' matrices, partial-sum reductions.
+// fp32 -> bf16 casts, partial-sum reductions.
 // All row kernels use 128-bit loads/stores, one warp per (row, 256-channel slice), warp-shuffle reductions, and
 // per-CTA partials + fixed-order finalisation for every cross-row (per-channel) statistic, so results are
 // deterministic (SURVEY.md §7 "hard parts").
@@ -109,28 +109,55 @@ __global__ void prep_weights_kernel(const float* __restrict__ tw, const float* _
 }
 
 // ------------------------------------------------------------------------------------------------ BN statistics
+// Block = 32 channels x RED_Y partial groups.  Every thread sums a strided subset of the partial rows in double,
+// the RED_Y sub-sums are combined through shared memory in a fixed order -> deterministic, no atomics.
+constexpr int RED_Y = 32;
+template <int NS>
+__device__ __forceinline__ void reduce_partial_rows(const float* __restrict__ part, int np, long long row_stride,
+                                                    long long stat_stride, int c, bool cact, double (&out)[NS],
+                                                    double (*sm)[RED_Y][33]) {
+  double acc[NS];
+#pragma unroll
+  for (int j = 0; j < NS; ++j) acc[j] = 0.0;
+  if (cact) {
+    for (int i = threadIdx.y; i < np; i += RED_Y) {
+#pragma unroll
+      for (int j = 0; j < NS; ++j) acc[j] += static_cast<double>(part[i * row_stride + j * stat_stride + c]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NS; ++j) sm[j][threadIdx.y][threadIdx.x] = acc[j];
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    double t = 0.0;
+    for (int y = 0; y < RED_Y; ++y) t += sm[j][y][threadIdx.x];
+    out[j] = t;
+  }
+}
+
 // partials: [np][2][C] (sum, sum of squares) -> mean, rstd, affine a = gamma*rstd, b = beta - mean*a; running stats.
-__global__ void bn_finalize_kernel(const float* __restrict__ part, int np, int C, double count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                   float momentum, int training, int bn_layer, float* __restrict__ rm,
-                                   float* __restrict__ rv, long long* __restrict__ nbt, float* __restrict__ mean_o,
-                                   float* __restrict__ rstd_o, float* __restrict__ a_o, float* __restrict__ b_o) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32 * RED_Y)
+    bn_finalize_kernel(const float* __restrict__ part, int np, int C, double count, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, float eps, float momentum, int training, int bn_layer,
+                       float* __restrict__ rm, float* __restrict__ rv, long long* __restrict__ nbt,
+                       float* __restrict__ mean_o, float* __restrict__ rstd_o, float* __restrict__ a_o,
+                       float* __restrict__ b_o) {
+  __shared__ double sm[2][RED_Y][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool cact = c < C;
+  double st[2] = {0.0, 0.0};
+  if (training && bn_layer) reduce_partial_rows<2>(part, np, 2LL * C, C, c, cact, st, sm);
+  if (threadIdx.y != 0 || !cact) return;
   if (c == 0 && training && bn_layer && nbt != nullptr) *nbt += 1;
-  if (c >= C) return;
   if (!bn_layer) {
     mean_o[c] = 0.f; rstd_o[c] = 1.f; a_o[c] = 1.f; b_o[c] = 0.f;
     return;
   }
   double mean, var;
   if (training) {
-    double s = 0.0, s2 = 0.0;
-    for (int i = 0; i < np; ++i) {
-      s += static_cast<double>(part[(static_cast<long long>(i) * 2) * C + c]);
-      s2 += static_cast<double>(part[(static_cast<long long>(i) * 2 + 1) * C + c]);
-    }
-    mean = s / count;
-    var = s2 / count - mean * mean;
+    mean = st[0] / count;
+    var = st[1] / count - mean * mean;
     if (var < 0.0) var = 0.0;
     const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
     rm[c] = static_cast<float>((1.0 - momentum) * rm[c] + momentum * mean);
@@ -148,6 +175,45 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part, int np, int C
 }
 
 // ------------------------------------------------------------------------------------------------ BN + residual + LN fwd
+// Raw (still packed) 8-element vectors: the next row is fetched while the current one is processed, which doubles
+// the bytes in flight per warp (the kernels are latency-bound on HBM otherwise: ~45 % of peak measured without it).
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> { uint4 v; };
+template <> struct Raw8<float> { float4 a, b; };
+__device__ __forceinline__ Raw8<bf16> ldraw(const bf16* p) {
+  Raw8<bf16> r;
+  r.v = *reinterpret_cast<const uint4*>(p);
+  return r;
+}
+__device__ __forceinline__ Raw8<float> ldraw(const float* p) {
+  Raw8<float> r;
+  r.a = *reinterpret_cast<const float4*>(p);
+  r.b = *reinterpret_cast<const float4*>(p + 4);
+  return r;
+}
+__device__ __forceinline__ void cvt8(const Raw8<bf16>& r, float (&f)[8]) {
+  const uint32_t* u = reinterpret_cast<const uint32_t*>(&r.v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = unpack_bf16(u[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void cvt8(const Raw8<float>& r, float (&f)[8]) {
+  f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w;
+  f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+}
+
+// volatile 2 x 128-bit shared-memory load (keeps loop-invariant vectors out of the register file)
+__device__ __forceinline__ void lds8v(const float* p, float (&f)[8]) {
+  const uint32_t a = smem_u32(p);
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(a));
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7])
+               : "r"(a + 16));
+}
+
 // Z = LayerNorm_C(a*U + b + X) * lw + lb     (ours.py:908-915 after the W_z GEMM).  U may be nullptr (V = 0).
 template <typename TO>
 __global__ void __launch_bounds__(ROW_THREADS)
@@ -167,18 +233,30 @@ __global__ void __launch_bounds__(ROW_THREADS)
     load8(bn_a + c0, a); load8(bn_b + c0, b); load8(lw + c0, w); load8(lb + c0, bb);
   }
   const float invC = 1.f / static_cast<float>(C);
-  for (long long base = static_cast<long long>(blockIdx.x) * RPB; base < rows; base += static_cast<long long>(gridDim.x) * RPB) {
+  const long long step = static_cast<long long>(gridDim.x) * RPB;
+  long long base = static_cast<long long>(blockIdx.x) * RPB;
+  Raw8<bf16> xr = {}, ur = {};
+  if (cact && base + rslot < rows) {
+    xr = ldraw(X + (base + rslot) * C + c0);
+    if (U != nullptr) ur = ldraw(U + (base + rslot) * C + c0);
+  }
+  for (; base < rows; base += step) {
     const long long row = base + rslot;
     const bool act = cact && row < rows;
+    const Raw8<bf16> xc = xr, uc = ur;
+    if (cact && row + step < rows) {
+      xr = ldraw(X + (row + step) * C + c0);
+      if (U != nullptr) ur = ldraw(U + (row + step) * C + c0);
+    }
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = 0.f;
     if (act) {
       float x[8];
-      load8(X + row * C + c0, x);
+      cvt8(xc, x);
       if (U != nullptr) {
         float u[8];
-        load8(U + row * C + c0, u);
+        cvt8(uc, u);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = fmaf(a[i], u[i], b[i]) + x[i];
       } else {
@@ -221,53 +299,90 @@ __global__ void __launch_bounds__(ROW_THREADS)
 // From dZ: dV = dZp (gradient of the pre-LayerNorm sum, also the residual part of dX), and per-CTA partials of the
 // four per-channel reductions: d ln_w = sum dZ*xhat, d ln_b = sum dZ, d gamma = sum dV*uhat, d beta = sum dV.
 template <typename TI>
-__global__ void __launch_bounds__(ROW_THREADS)
+__global__ void __launch_bounds__(ROW_THREADS, 2)
     bn_res_ln_bwd_kernel(const TI* __restrict__ dZ, const bf16* __restrict__ U, const bf16* __restrict__ X,
                          const float* __restrict__ bn_a, const float* __restrict__ bn_b,
                          const float* __restrict__ bn_mean, const float* __restrict__ bn_rstd,
                          const float* __restrict__ lw, const float* __restrict__ mu_i, const float* __restrict__ r_i,
                          bf16* __restrict__ dV, float* __restrict__ part, long long rows, int C, int S) {
   __shared__ float red[2 * ROW_WARPS * 2];
-  __shared__ float acc_sm[ROW_WARPS][4][32 * 8 + 8];
+  // per-channel parameter vectors live in shared memory during the row loop (re-read with volatile 128-bit loads so
+  // that they do not occupy 40 registers); the same storage holds the accumulator exchange afterwards
+  constexpr int ACC_PITCH = 32 * 8 + 8;
+  constexpr int SM_FLOATS = (ROW_WARPS * 4 * ACC_PITCH > 5 * 2048) ? ROW_WARPS * 4 * ACC_PITCH : 5 * 2048;
+  __shared__ __align__(16) float smbuf[SM_FLOATS];
   int buf = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int RPB = ROW_WARPS / S;
   const int rslot = warp / S, slice = warp % S;
   const int c0 = slice * 256 + lane * 8;
   const bool cact = c0 < C;
-  float a[8], b[8], w[8], bm[8], br[8];
-  if (cact) {
-    load8(bn_a + c0, a); load8(bn_b + c0, b); load8(lw + c0, w); load8(bn_mean + c0, bm); load8(bn_rstd + c0, br);
+  const int Cs = S * 256;
+  for (int i = threadIdx.x; i < Cs; i += ROW_THREADS) {
+    const bool in = i < C;
+    smbuf[0 * Cs + i] = in ? bn_a[i] : 0.f;
+    smbuf[1 * Cs + i] = in ? bn_b[i] : 0.f;
+    smbuf[2 * Cs + i] = in ? lw[i] : 0.f;
+    smbuf[3 * Cs + i] = in ? bn_mean[i] : 0.f;
+    smbuf[4 * Cs + i] = in ? bn_rstd[i] : 0.f;
   }
+  __syncthreads();
+  const float* sp = smbuf + c0;
   float g_lw[8], g_lb[8], g_ga[8], g_be[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) g_lw[i] = g_lb[i] = g_ga[i] = g_be[i] = 0.f;
   const float invC = 1.f / static_cast<float>(C);
-  for (long long base = static_cast<long long>(blockIdx.x) * RPB; base < rows; base += static_cast<long long>(gridDim.x) * RPB) {
+  const long long step = static_cast<long long>(gridDim.x) * RPB;
+  long long base = static_cast<long long>(blockIdx.x) * RPB;
+  Raw8<bf16> xr = {}, ur = {};
+  Raw8<TI> zr = {};
+  float mu_n = 0.f, r_n = 0.f;
+  if (cact && base + rslot < rows) {
+    const long long row = base + rslot;
+    xr = ldraw(X + row * C + c0);
+    zr = ldraw(dZ + row * C + c0);
+    if (U != nullptr) ur = ldraw(U + row * C + c0);
+    mu_n = mu_i[row];
+    r_n = r_i[row];
+  }
+  for (; base < rows; base += step) {
     const long long row = base + rslot;
     const bool act = cact && row < rows;
+    const Raw8<bf16> xc = xr, uc = ur;
+    const Raw8<TI> zc = zr;
+    const float mu = mu_n, r = r_n;
+    if (cact && row + step < rows) {
+      const long long nrow = row + step;
+      xr = ldraw(X + nrow * C + c0);
+      zr = ldraw(dZ + nrow * C + c0);
+      if (U != nullptr) ur = ldraw(U + nrow * C + c0);
+      mu_n = mu_i[nrow];
+      r_n = r_i[nrow];
+    }
     float xh[8], dxh[8], dz[8], uh[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) xh[i] = dxh[i] = dz[i] = uh[i] = 0.f;
-    float r = 0.f;
     if (act) {
-      const float mu = mu_i[row];
-      r = r_i[row];
       float x[8];
-      load8(X + row * C + c0, x);
-      load8(dZ + row * C + c0, dz);
+      cvt8(xc, x);
+      cvt8(zc, dz);
       if (U != nullptr) {
-        float u[8];
-        load8(U + row * C + c0, u);
+        float u[8], a[8], b[8];
+        cvt8(uc, u);
+        lds8v(sp, a);
+        lds8v(sp + Cs, b);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          xh[i] = (fmaf(a[i], u[i], b[i]) + x[i] - mu) * r;
-          uh[i] = (u[i] - bm[i]) * br[i];
-        }
+        for (int i = 0; i < 8; ++i) xh[i] = (fmaf(a[i], u[i], b[i]) + x[i] - mu) * r;
+        lds8v(sp + 3 * Cs, a);
+        lds8v(sp + 4 * Cs, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) uh[i] = (u[i] - a[i]) * b[i];
       } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) xh[i] = (x[i] - mu) * r;
       }
+      float w[8];
+      lds8v(sp + 2 * Cs, w);
 #pragma unroll
       for (int i = 0; i < 8; ++i) dxh[i] = dz[i] * w[i];
     }
@@ -293,6 +408,8 @@ __global__ void __launch_bounds__(ROW_THREADS)
     }
   }
   // reduce the accumulators over the row slots of this CTA (fixed order), write one partial per CTA
+  __syncthreads();  // every warp is done with the parameter vectors: reuse the storage
+  float (*acc_sm)[4][ACC_PITCH] = reinterpret_cast<float (*)[4][ACC_PITCH]>(smbuf);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     acc_sm[warp][0][lane * 8 + i] = g_lw[i];
@@ -314,20 +431,19 @@ __global__ void __launch_bounds__(ROW_THREADS)
 }
 
 // partials [np][4][C] -> parameter gradients + dU coefficient vectors: dU = k1*dV + k2*U + k3   
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int np, int C, double count,
-                                       const float* __restrict__ gamma, const float* __restrict__ bn_mean,
-                                       const float* __restrict__ bn_rstd, int training, int bn_layer,
-                                       float* __restrict__ d_lnw, float* __restrict__ d_lnb,
-                                       float* __restrict__ d_gamma, float* __restrict__ d_beta,
-                                       float* __restrict__ d_bz, float* __restrict__ k1, float* __restrict__ k2,
-                                       float* __restrict__ k3) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s[4] = {0, 0, 0, 0};
-  for (int i = 0; i < np; ++i) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) s[j] += static_cast<double>(part[(static_cast<long long>(i) * 4 + j) * C + c]);
-  }
+__global__ void __launch_bounds__(32 * RED_Y)
+    bn_bwd_finalize_kernel(const float* __restrict__ part, int np, int C, double count,
+                           const float* __restrict__ gamma, const float* __restrict__ bn_mean,
+                           const float* __restrict__ bn_rstd, int training, int bn_layer, float* __restrict__ d_lnw,
+                           float* __restrict__ d_lnb, float* __restrict__ d_gamma, float* __restrict__ d_beta,
+                           float* __restrict__ d_bz, float* __restrict__ k1, float* __restrict__ k2,
+                           float* __restrict__ k3) {
+  __shared__ double sm[4][RED_Y][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool cact = c < C;
+  double s[4];
+  reduce_partial_rows<4>(part, np, 4LL * C, C, c, cact, s, sm);
+  if (threadIdx.y != 0 || !cact) return;
   d_lnw[c] = static_cast<float>(s[0]);
   d_lnb[c] = static_cast<float>(s[1]);
   if (!bn_layer) {
@@ -372,88 +488,27 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dV, const bf16* __r
   }
 }
 
-// ------------------------------------------------------------------------------------------------ small fp32 GEMM
-// C[b][m][n] = alpha * sum_{rb} sum_k A[b,rb][m][k] * B[b,rb][k][n]     generic strides, fp32 SIMT, 64x64 tiles.
-struct SmallGemmP {
-  const float* A; const float* B;
-  long long a_rs, a_cs, a_bs, a_rbs;
-  long long b_rs, b_cs, b_bs, b_rbs;
-  int M, N, K, RB;
-  float alpha;
-  float* Cf; bf16* Cb; bf16* CbT;   // any subset; Cb [b][M][N], CbT [b][N][M]
-  long long c_bs;
-};
-__global__ void __launch_bounds__(256) small_gemm_kernel(const SmallGemmP p) {
-  __shared__ float As[16][64 + 1];
-  __shared__ float Bs[16][64 + 1];
-  const int b = blockIdx.z;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16, each thread 4x4
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int rb = 0; rb < p.RB; ++rb) {
-    const float* A = p.A + b * p.a_bs + rb * p.a_rbs;
-    const float* B = p.B + b * p.b_bs + rb * p.b_rbs;
-    for (int k0 = 0; k0 < p.K; k0 += 16) {
-      for (int i = threadIdx.x; i < 16 * 64; i += 256) {
-        int kk, mm;
-        if (p.a_cs == 1) { kk = i & 15; mm = i >> 4; } else { mm = i & 63; kk = i >> 6; }
-        const int gm = m0 + mm, gk = k0 + kk;
-        As[kk][mm] = (gm < p.M && gk < p.K) ? A[gm * p.a_rs + gk * p.a_cs] : 0.f;
-        int kb, nn;
-        if (p.b_cs == 1) { nn = i & 63; kb = i >> 6; } else { kb = i & 15; nn = i >> 4; }
-        const int gn = n0 + nn, gk2 = k0 + kb;
-        Bs[kb][nn] = (gn < p.N && gk2 < p.K) ? B[gk2 * p.b_rs + gn * p.b_cs] : 0.f;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int kk = 0; kk < 16; ++kk) {
-        float av[4], bv[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-      }
-      __syncthreads();
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
-      if (gm < p.M && gn < p.N) {
-        const float v = acc[i][j] * p.alpha;
-        const long long o = b * p.c_bs + static_cast<long long>(gm) * p.N + gn;
-        if (p.Cf) p.Cf[o] = v;
-        if (p.Cb) p.Cb[o] = __float2bfloat16(v);
-        if (p.CbT) p.CbT[b * p.c_bs + static_cast<long long>(gn) * p.M + gm] = __float2bfloat16(v);
-      }
-    }
-  }
-}
-
+// ------------------------------------------------------------------------------------------------ reductions / casts
 // out[c] = alpha * sum_i part[i*stride + c]  (fixed order)
-__global__ void reduce_partials_kernel(const float* __restrict__ part, int np, long long stride, int n, float alpha,
-                                       float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
-  double s = 0.0;
-  for (int i = 0; i < np; ++i) s += static_cast<double>(part[i * stride + c]);
-  out[c] = static_cast<float>(s * alpha);
+__global__ void __launch_bounds__(32 * RED_Y)
+    reduce_partials_kernel(const float* __restrict__ part, int np, long long stride, int n, float alpha,
+                           float* __restrict__ out) {
+  __shared__ double sm[1][RED_Y][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool cact = c < n;
+  double s[1];
+  reduce_partial_rows<1>(part, np, stride, 0, c, cact, s, sm);
+  if (threadIdx.y == 0 && cact) out[c] = static_cast<float>(s[0] * alpha);
 }
 
-__global__ void copy_f32_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x)
-    out[i] = in[i];
+// fp32 -> bf16 (8 elements per thread)
+__global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long nvec) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float f[8];
+    load8(in + i * 8, f);
+    store8(out + i * 8, f);
+  }
 }
 
 int row_grid(long long rows, int S) {
@@ -494,7 +549,7 @@ int prep_weights(const glf_weights* w, int C, int Ci, bf16* wcat, bf16* wcatT, f
 
 int bn_finalize(const float* part, int np, int C, double count, const glf_desc* d, const glf_weights* w, float* mean,
                 float* rstd, float* a, float* b, cudaStream_t stream) {
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(part, np, C, count, w->bn_w, w->bn_b, d->eps_bn, d->momentum,
+  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, RED_Y), 0, stream>>>(part, np, C, count, w->bn_w, w->bn_b, d->eps_bn, d->momentum,
                                                           d->training, d->bn_layer, w->bn_running_mean,
                                                           w->bn_running_var,
                                                           reinterpret_cast<long long*>(w->bn_num_batches_tracked), mean,
@@ -540,7 +595,7 @@ int bn_res_ln_bwd(const void* dZ, int dz_dtype, const bf16* U, const bf16* X, co
 int bn_bwd_finalize(const float* part, int np, int C, double count, const glf_desc* d, const glf_weights* w,
                     const float* mean, const float* rstd, const glf_grads* g, float* k1, float* k2, float* k3,
                     cudaStream_t stream) {
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(part, np, C, count, w->bn_w, mean, rstd, d->training,
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, RED_Y), 0, stream>>>(part, np, C, count, w->bn_w, mean, rstd, d->training,
                                                               d->bn_layer, g->ln_w, g->ln_b, g->bn_w, g->bn_b, g->wz_b,
                                                               k1, k2, k3);
   return check_cuda(cudaGetLastError(), "bn_bwd_finalize launch");
@@ -555,31 +610,18 @@ int bn_bwd_apply(const bf16* dV, const bf16* U, const float* k1, const float* k2
   return check_cuda(cudaGetLastError(), "bn_bwd_apply launch");
 }
 
-int small_gemm(const float* A, long long a_rs, long long a_cs, long long a_bs, long long a_rbs, const float* B,
-               long long b_rs, long long b_cs, long long b_bs, long long b_rbs, int batch, int RB, int M, int N, int K,
-               float alpha, float* Cf, bf16* Cb, bf16* CbT, cudaStream_t stream) {
-  SmallGemmP p;
-  p.A = A; p.B = B;
-  p.a_rs = a_rs; p.a_cs = a_cs; p.a_bs = a_bs; p.a_rbs = a_rbs;
-  p.b_rs = b_rs; p.b_cs = b_cs; p.b_bs = b_bs; p.b_rbs = b_rbs;
-  p.M = M; p.N = N; p.K = K; p.RB = RB; p.alpha = alpha;
-  p.Cf = Cf; p.Cb = Cb; p.CbT = CbT;
-  p.c_bs = static_cast<long long>(M) * N;
-  dim3 grid((N + 63) / 64, (M + 63) / 64, batch);
-  small_gemm_kernel<<<grid, 256, 0, stream>>>(p);
-  return check_cuda(cudaGetLastError(), "small_gemm launch");
-}
-
 int reduce_partials(const float* part, int np, long long stride, int n, float alpha, float* out, cudaStream_t stream) {
-  reduce_partials_kernel<<<(n + 127) / 128, 128, 0, stream>>>(part, np, stride, n, alpha, out);
+  reduce_partials_kernel<<<(n + 31) / 32, dim3(32, RED_Y), 0, stream>>>(part, np, stride, n, alpha, out);
   return check_cuda(cudaGetLastError(), "reduce_partials launch");
 }
 
-int copy_f32(const float* in, float* out, long long n, cudaStream_t stream) {
-  long long blocks = (n + 255) / 256;
+int cast_bf16(const float* in, bf16* out, long long n, cudaStream_t stream) {
+  if (n % 8 != 0) return set_error(GLF_ERR_INVALID, "cast_bf16: n %% 8 != 0");
+  const long long nvec = n / 8;
+  long long blocks = (nvec + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  copy_f32_kernel<<<static_cast<int>(blocks < 1 ? 1 : blocks), 256, 0, stream>>>(in, out, n);
-  return check_cuda(cudaGetLastError(), "copy launch");
+  cast_bf16_kernel<<<static_cast<int>(blocks < 1 ? 1 : blocks), 256, 0, stream>>>(in, out, nvec);
+  return check_cuda(cudaGetLastError(), "cast_bf16 launch");
 }
 
 }  // namespace glf

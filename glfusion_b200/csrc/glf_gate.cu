@@ -26,9 +26,20 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf
 
 template <typename T>
 __device__ __forceinline__ float ldf(const T* p) { return static_cast<float>(*p); }
+// two adjacent spatial positions of one channel (NCHW side), 4-byte / 8-byte accesses
+__device__ __forceinline__ void ld2(const bf16* p, float& a, float& b) {
+  const float2 t = unpack_bf16(*reinterpret_cast<const uint32_t*>(p));
+  a = t.x; b = t.y;
+}
+__device__ __forceinline__ void ld2(const float* p, float& a, float& b) {
+  const float2 t = *reinterpret_cast<const float2*>(p);
+  a = t.x; b = t.y;
+}
+__device__ __forceinline__ void st2(bf16* p, float a, float b) { *reinterpret_cast<uint32_t*>(p) = pack_bf16(a, b); }
+__device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 
 // grid: (ceil(hw/64), C/64 rounded up, B*V) ; block 256
-template <typename TIO>
+template <typename TIO, int VEC>
 __global__ void __launch_bounds__(256)
     gate_concat_fwd_kernel(const ViewPtrs vp, bf16* __restrict__ xg, bf16* __restrict__ xl, float* __restrict__ gate,
                            int C, int V, int hw, int ncls, float weight) {
@@ -51,7 +62,17 @@ __global__ void __launch_bounds__(256)
     }
     a_sm[threadIdx.x] = a;
   }
-  {
+  if (VEC == 2) {  // hw even: every (c, even p) address is 4-byte aligned
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = ty; i < 64; i += 8) {
+      const int c = c0 + i, p = p0 + 2 * tx;
+      float a = 0.f, b = 0.f;
+      if (c < C && p < hw) ld2(f4 + static_cast<long long>(c) * hw + p, a, b);
+      tile[i][2 * tx] = a;
+      tile[i][2 * tx + 1] = b;
+    }
+  } else {
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
     for (int i = ty; i < 64; i += 4) {
       const int c = c0 + i, p = p0 + tx;
@@ -81,14 +102,14 @@ __global__ void __launch_bounds__(256)
 }
 
 // grid: (ceil(hw/64), B*V) ; block 256 ; loops over channel tiles so the gate gradient needs no atomics
-template <typename TIO>
+template <typename TIO, int VEC>
 __global__ void __launch_bounds__(256)
     gate_concat_bwd_kernel(const ViewPtrs vp, const float* __restrict__ gate, const bf16* __restrict__ dxg,
                            const bf16* __restrict__ dxl, int C, int V, int hw, int ncls, float weight) {
   __shared__ float tg[64][65];
   __shared__ float tl[64][65];
   __shared__ float a_sm[64];
-  __shared__ float da_sm[4][64];
+  __shared__ float da_sm[8][64];
   const int bv = blockIdx.y, b = bv / V, v = bv % V;
   const int p0 = blockIdx.x * 64;
   const TIO* f4 = reinterpret_cast<const TIO*>(vp.f4[v]) + static_cast<long long>(b) * C * hw;
@@ -97,8 +118,11 @@ __global__ void __launch_bounds__(256)
     const int p = p0 + threadIdx.x;
     a_sm[threadIdx.x] = p < hw ? gate[static_cast<long long>(bv) * hw + p] : 0.f;
   }
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-  float da = 0.f;
+  // NCHW side mapping: VEC==2 -> 32 position pairs x 8 channel rows ; VEC==1 -> 64 positions x 4 channel rows
+  const int tx = VEC == 2 ? (threadIdx.x & 31) : (threadIdx.x & 63);
+  const int ty = VEC == 2 ? (threadIdx.x >> 5) : (threadIdx.x >> 6);
+  constexpr int NY = VEC == 2 ? 8 : 4;
+  float da0 = 0.f, da1 = 0.f;
   for (int c0 = 0; c0 < C; c0 += 64) {
     __syncthreads();
     const int chunk = threadIdx.x & 7, pr = threadIdx.x >> 3;
@@ -122,23 +146,47 @@ __global__ void __launch_bounds__(256)
       }
     }
     __syncthreads();
-    const float a = a_sm[tx];
-    for (int i = ty; i < 64; i += 4) {
-      const int c = c0 + i, p = p0 + tx;
-      if (c < C && p < hw) {
-        const float dl = tl[tx][i];
-        const float f = ldf(f4 + static_cast<long long>(c) * hw + p);
-        df4[static_cast<long long>(c) * hw + p] = static_cast<TIO>(tg[tx][i] + a * dl);
-        da = fmaf(f, dl, da);
+    if (VEC == 2) {
+      const int pl = 2 * tx;
+      const float a0 = a_sm[pl], a1 = a_sm[pl + 1];
+#pragma unroll
+      for (int i = ty; i < 64; i += NY) {
+        const int c = c0 + i, p = p0 + pl;
+        if (c < C && p < hw) {
+          const float dl0 = tl[pl][i], dl1 = tl[pl + 1][i];
+          float f0, f1;
+          ld2(f4 + static_cast<long long>(c) * hw + p, f0, f1);
+          st2(df4 + static_cast<long long>(c) * hw + p, tg[pl][i] + a0 * dl0, tg[pl + 1][i] + a1 * dl1);
+          da0 = fmaf(f0, dl0, da0);
+          da1 = fmaf(f1, dl1, da1);
+        }
+      }
+    } else {
+      const float a = a_sm[tx];
+      for (int i = ty; i < 64; i += NY) {
+        const int c = c0 + i, p = p0 + tx;
+        if (c < C && p < hw) {
+          const float dl = tl[tx][i];
+          const float f = ldf(f4 + static_cast<long long>(c) * hw + p);
+          df4[static_cast<long long>(c) * hw + p] = static_cast<TIO>(tg[tx][i] + a * dl);
+          da0 = fmaf(f, dl, da0);
+        }
       }
     }
   }
-  da_sm[ty][tx] = da;
+  if (VEC == 2) {
+    da_sm[ty][2 * tx] = da0;
+    da_sm[ty][2 * tx + 1] = da1;
+  } else {
+    da_sm[ty][tx] = da0;
+  }
   __syncthreads();
   if (threadIdx.x < 64) {
     const int p = p0 + threadIdx.x;
     if (p < hw) {
-      const float dA = da_sm[0][threadIdx.x] + da_sm[1][threadIdx.x] + da_sm[2][threadIdx.x] + da_sm[3][threadIdx.x];
+      float dA = 0.f;
+#pragma unroll
+      for (int y = 0; y < NY; ++y) dA += da_sm[y][threadIdx.x];
       const float* cl = vp.cls[v] + static_cast<long long>(b) * ncls * hw + p;
       float lmax = cl[0];
       int arg = 0;
@@ -170,10 +218,14 @@ int gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, i
   const int hw = h * w;
   dim3 grid((hw + 63) / 64, (C + 63) / 64, B * V);
   if (grid.y > 65535 || grid.z > 65535) return set_error(GLF_ERR_INVALID, "gate_concat: grid too large");
-  if (io_dtype == GLF_DTYPE_BF16)
-    gate_concat_fwd_kernel<bf16><<<grid, 256, 0, stream>>>(vp, (bf16*)xg, (bf16*)xl, gate, C, V, hw, ncls, weight);
-  else
-    gate_concat_fwd_kernel<float><<<grid, 256, 0, stream>>>(vp, (bf16*)xg, (bf16*)xl, gate, C, V, hw, ncls, weight);
+  const bool vec2 = (hw % 2 == 0);
+  if (io_dtype == GLF_DTYPE_BF16) {
+    if (vec2) gate_concat_fwd_kernel<bf16, 2><<<grid, 256, 0, stream>>>(vp, (bf16*)xg, (bf16*)xl, gate, C, V, hw, ncls, weight);
+    else gate_concat_fwd_kernel<bf16, 1><<<grid, 256, 0, stream>>>(vp, (bf16*)xg, (bf16*)xl, gate, C, V, hw, ncls, weight);
+  } else {
+    if (vec2) gate_concat_fwd_kernel<float, 2><<<grid, 256, 0, stream>>>(vp, (bf16*)xg, (bf16*)xl, gate, C, V, hw, ncls, weight);
+    else gate_concat_fwd_kernel<float, 1><<<grid, 256, 0, stream>>>(vp, (bf16*)xg, (bf16*)xl, gate, C, V, hw, ncls, weight);
+  }
   return check_cuda(cudaGetLastError(), "gate_concat_fwd launch");
 }
 
@@ -190,10 +242,14 @@ int gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, i
   const int hw = h * w;
   dim3 grid((hw + 63) / 64, B * V);
   if (grid.y > 65535) return set_error(GLF_ERR_INVALID, "gate_concat: grid too large");
-  if (io_dtype == GLF_DTYPE_BF16)
-    gate_concat_bwd_kernel<bf16><<<grid, 256, 0, stream>>>(vp, gate, (const bf16*)dxg, (const bf16*)dxl, C, V, hw, ncls, weight);
-  else
-    gate_concat_bwd_kernel<float><<<grid, 256, 0, stream>>>(vp, gate, (const bf16*)dxg, (const bf16*)dxl, C, V, hw, ncls, weight);
+  const bool vec2 = (hw % 2 == 0);
+  if (io_dtype == GLF_DTYPE_BF16) {
+    if (vec2) gate_concat_bwd_kernel<bf16, 2><<<grid, 256, 0, stream>>>(vp, gate, (const bf16*)dxg, (const bf16*)dxl, C, V, hw, ncls, weight);
+    else gate_concat_bwd_kernel<bf16, 1><<<grid, 256, 0, stream>>>(vp, gate, (const bf16*)dxg, (const bf16*)dxl, C, V, hw, ncls, weight);
+  } else {
+    if (vec2) gate_concat_bwd_kernel<float, 2><<<grid, 256, 0, stream>>>(vp, gate, (const bf16*)dxg, (const bf16*)dxl, C, V, hw, ncls, weight);
+    else gate_concat_bwd_kernel<float, 1><<<grid, 256, 0, stream>>>(vp, gate, (const bf16*)dxg, (const bf16*)dxl, C, V, hw, ncls, weight);
+  }
   return check_cuda(cudaGetLastError(), "gate_concat_bwd launch");
 }
 

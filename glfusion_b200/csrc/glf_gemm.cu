@@ -52,7 +52,7 @@ struct GemmCfg {
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
   static constexpr uint32_t STG_ROW = BN * 2 + 16;  // staging row pitch (bytes): odd multiple of 16 -> conflict free
-  static_assert(BM * STG_ROW <= STAGES * STAGE_BYTES, "staging must fit in the pipeline ring");
+  static_assert(BM * STG_ROW + 128 * 8 * 8 * 4 <= STAGES * STAGE_BYTES, "staging + stats exchange must fit in the ring");
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -225,18 +225,46 @@ __global__ void __launch_bounds__(GEMM_THREADS, GemmCfg<BN>::MIN_CTAS)
       named_bar_sync(1, 128);
       const int rows_valid = min(BM, p.M - m0);
       if (p.colstats != nullptr) {
+        // 128 threads = (BN/8 column groups of 8) x (row groups); 128-bit shared loads, then a fixed-order combine
+        constexpr int CG = BN / 8;
+        constexpr int RG = 128 / CG;
+        constexpr int RPG = BM / RG;
+        float* redbuf = reinterpret_cast<float*>(stg + BM * Cfg::STG_ROW);  // [RG][2][BN]
+        const int cg = e % CG, rg = e / CG;
+        float s[8], s2[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) s[t] = s2[t] = 0.f;
+        const int r_end = min(rows_valid, (rg + 1) * RPG);
+        for (int r = rg * RPG; r < r_end; ++r) {
+          const uint4 pk = *reinterpret_cast<const uint4*>(stg + r * Cfg::STG_ROW + cg * 16);
+          const uint32_t* u = reinterpret_cast<const uint32_t*>(&pk);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 x = unpack_bf16(u[t]);
+            s[2 * t] += x.x;
+            s[2 * t + 1] += x.y;
+            s2[2 * t] = fmaf(x.x, x.x, s2[2 * t]);
+            s2[2 * t + 1] = fmaf(x.y, x.y, s2[2 * t + 1]);
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          redbuf[(rg * 2 + 0) * BN + cg * 8 + t] = s[t];
+          redbuf[(rg * 2 + 1) * BN + cg * 8 + t] = s2[t];
+        }
+        named_bar_sync(1, 128);
+        float* cs = p.colstats + (static_cast<long long>(b) * p.tiles_m + m_tile) * 2 * p.N;
         for (int col = e; col < BN; col += 128) {
           const int gc = n0 + col;
           if (gc < p.N) {
-            float s = 0.f, s2 = 0.f;
-            for (int r = 0; r < rows_valid; ++r) {
-              const float x = __bfloat162float(*reinterpret_cast<const bf16*>(stg + r * Cfg::STG_ROW + col * 2));
-              s += x;
-              s2 = fmaf(x, x, s2);
+            float a = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int g = 0; g < RG; ++g) {
+              a += redbuf[(g * 2 + 0) * BN + col];
+              a2 += redbuf[(g * 2 + 1) * BN + col];
             }
-            float* cs = p.colstats + (static_cast<long long>(b) * p.tiles_m + m_tile) * 2 * p.N;
-            cs[gc] = s;
-            cs[p.N + gc] = s2;
+            cs[gc] = a;
+            cs[p.N + gc] = a2;
           }
         }
       }
@@ -347,7 +375,10 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
     return set_error(GLF_ERR_INVALID, "gemm: output must be 16-byte aligned with ldd %% 8 == 0");
   if (a.npairs < 1 || a.npairs > 6) return set_error(GLF_ERR_INVALID, "gemm: npairs out of range");
 
-  const int BN = (a.N <= 64) ? 64 : ((a.N % 256 == 0 || a.N > 384) ? 256 : 128);
+  // Small-K products are HBM-bound: 128-wide tiles keep 2 CTAs per SM so one CTA's epilogue overlaps the other's
+  // loads.  Large-K (tensor-bound, e.g. C=2048) products take the 128x256 tile.
+  int BN = (a.N <= 64) ? 64 : ((a.K >= 512 && a.N % 256 == 0) ? 256 : 128);
+  if (a.bn_hint == 64 || a.bn_hint == 128 || a.bn_hint == 256) BN = a.bn_hint;
   int nlimbsA = 1, nlimbsB = 1;
   for (int i = 0; i < a.npairs; ++i) {
     nlimbsA = a.pairA[i] + 1 > nlimbsA ? a.pairA[i] + 1 : nlimbsA;

@@ -36,6 +36,7 @@ struct GemmArgs {
   int64_t ld_add = 0, stride_add = 0;
   float* colstats = nullptr;        // [batch*tiles_m][2][N]
   int split_k = 1;
+  int bn_hint = 0;                  // 0 = heuristic, else force the N tile (64 / 128 / 256)
   int npairs = 1;                   // limb products accumulated into one tile: sum_p A[pairA[p]] * B[pairB[p]]^T
   int pairA[6] = {0, 0, 0, 0, 0, 0};
   int pairB[6] = {0, 0, 0, 0, 0, 0};
@@ -62,12 +63,8 @@ int bn_bwd_finalize(const float* part, int np, int C, double count, const glf_de
                     cudaStream_t stream);
 int bn_bwd_apply(const bf16* dV, const bf16* U, const float* k1, const float* k2, const float* k3, bf16* dU,
                  long long rows, int C, cudaStream_t stream);
-// C[b] = alpha * sum_rb A[b,rb] (MxK, strides rs/cs) * B[b,rb] (KxN); outputs fp32 and/or bf16 and/or bf16 transposed
-int small_gemm(const float* A, long long a_rs, long long a_cs, long long a_bs, long long a_rbs, const float* B,
-               long long b_rs, long long b_cs, long long b_bs, long long b_rbs, int batch, int RB, int M, int N, int K,
-               float alpha, float* Cf, bf16* Cb, bf16* CbT, cudaStream_t stream);
 int reduce_partials(const float* part, int np, long long stride, int n, float alpha, float* out, cudaStream_t stream);
-int copy_f32(const float* in, float* out, long long n, cudaStream_t stream);
+int cast_bf16(const float* in, bf16* out, long long n, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------ gate + concat
 int gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, const void* const* f4,

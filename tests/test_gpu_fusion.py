@@ -67,3 +67,34 @@ def test_cfg2_shape_against_oracle():
     for k, p in f.local_attn.named_parameters():
         if not k.startswith("align_channel"):
             assert_close("grad_l:" + k, p.grad, gl[k], 3e-2, abs_floor=1e-3)
+
+
+@pytest.mark.parametrize("h,w,V,io", [(5, 7, 3, "fp32"), (5, 7, 2, "bf16"), (9, 8, 1, "bf16")])
+def test_ragged_spatial_sizes_against_oracle(h, w, V, io):
+    """Odd h*w (scalar NCHW path), tokens not a multiple of any tile, single view."""
+    B, C = 3, 128
+    dt = torch.float32 if io == "fp32" else torch.bfloat16
+    pg = O.init_params(C, seed=41, randomize_affine=True)
+    pl = O.init_params(C, seed=42, randomize_affine=True)
+    gen = torch.Generator().manual_seed(43)
+    f4 = [torch.randn(B, C, h, w, generator=gen) for _ in range(V)]
+    cl = [torch.randn(B, 5, h, w, generator=gen) for _ in range(V)]
+    ct = [torch.randn(B, 1, h, w, generator=gen) for _ in range(V)]
+    do = [torch.randn(B, C, h, w, generator=gen) for _ in range(V)]
+    outs, df4, dcls, dctr, gg, gl = O.fusion_fwd_bwd(f4, cl, ct, do, {k: v.clone() for k, v in pg.items()},
+                                                     {k: v.clone() for k, v in pl.items()})
+    f = _build(C, pg, pl)
+    f4d = [t.to(DEV, dt).requires_grad_(True) for t in f4]
+    cld = [t.to(DEV).requires_grad_(True) for t in cl]
+    ctd = [t.to(DEV).requires_grad_(True) for t in ct]
+    out = f.forward_stacked(f4d, cld, ctd)
+    out.backward(torch.stack(do, dim=2).to(DEV, dt))
+    torch.cuda.synchronize()
+    for v in range(V):
+        assert_close(f"out:{v}", out[:, :, v], outs[v], BF16_TOL)
+        assert_close(f"df4:{v}", f4d[v].grad, df4[v], BF16_TOL)
+        assert_close(f"dcls:{v}", cld[v].grad, dcls[v], 4e-2)
+        assert_close(f"dctr:{v}", ctd[v].grad, dctr[v], 4e-2)
+    for k, p in f.global_attn.named_parameters():
+        if not k.startswith("align_channel"):
+            assert_close("grad_g:" + k, p.grad, gg[k], 3e-2, abs_floor=1e-3)
