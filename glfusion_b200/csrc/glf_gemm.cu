@@ -2,11 +2,12 @@
 //
 //   D[b] = alpha * sum_p A_p[b] * B_p[b]^T (+ bias) (+ addend)          A: M x K, B: N x K, bf16 in, fp32 accumulate
 //
-// One CTA computes one 128 x BN output tile (for one batch entry and one K split):
+// Persistent kernel, one CTA per SM; each CTA loops over 128 x BN output tiles (one batch entry / K split each):
 //   warp 0      TMA producer  : cp.async.bulk.tensor 4-D loads (inner, rows, batch, limb) into a STAGES-deep ring,
 //                               SWIZZLE_128B, completion on mbarriers
-//   warp 1      MMA issuer    : allocates TMEM, one elected lane issues tcgen05.mma (M=128, N=BN, K=16) x 4 per stage,
-//                               tcgen05.commit releases the smem slot / publishes the accumulator
+//   warp 1      MMA issuer    : allocates TMEM (two accumulator stages), one elected lane issues tcgen05.mma
+//                               (M=128, N=BN, K=16) x 4 per stage; tcgen05.commit releases the smem slot / publishes
+//                               the accumulator, so tile i+1 is computed while tile i is still in its epilogue
 //   warps 2..5  epilogue      : tcgen05.ld the fp32 accumulator (one TMEM lane quarter per warp), alpha/bias, then
 //                               either fp32 store / fp32 red.add (split-K) straight from registers, or bf16 staging in
 //                               smem -> fully coalesced 16-byte row stores (+ residual addend) and per-tile column
@@ -40,50 +41,55 @@ struct GemmKParams {
   const bf16* addend;
   long long ld_add, stride_add;
   float* colstats;
-  int tiles_m;
+  int tiles_m, tiles_n;
 };
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 128) ? 3 : 4;
-  static constexpr int MIN_CTAS = (BN == 256) ? 1 : 2;
+  // persistent kernel, one CTA per SM: ring + separate epilogue staging must fit in 227 KB
+  static constexpr int STAGES = (BN == 256) ? 3 : ((BN == 128) ? 5 : 6);
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+  static constexpr uint32_t RING_BYTES = STAGES * STAGE_BYTES;
   static constexpr uint32_t STG_ROW = BN * 2 + 16;  // staging row pitch (bytes): odd multiple of 16 -> conflict free
-  static_assert(BM * STG_ROW + 128 * 8 * 8 * 4 <= STAGES * STAGE_BYTES, "staging + stats exchange must fit in the ring");
+  static constexpr uint32_t STG_BYTES = BM * STG_ROW;
+  static constexpr uint32_t RED_BYTES = 8192;       // [RG][2][BN] floats for the column-statistics combine
+  static constexpr uint32_t BIAS_BYTES = BN * 4;
+  static constexpr uint32_t SMEM_BYTES = RING_BYTES + STG_BYTES + RED_BYTES + BIAS_BYTES + 1024;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;     // two accumulator stages
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  static_assert(TMEM_COLS <= 512, "TMEM budget");
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Persistent: CTA c processes tiles c, c + gridDim.x, ... ; tile index runs n-tile fastest, then m-tile, then
+// (batch, k-split), so the CTAs that are resident together share A slabs through L2.
 template <bool A_MN, bool B_MN, int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, GemmCfg<BN>::MIN_CTAS)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES];
   __shared__ uint64_t empty_bar[STAGES];
-  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint64_t tmem_full_bar[2];
+  __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_holder;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint8_t* stg = smem_gen + Cfg::RING_BYTES;
+  float* redbuf = reinterpret_cast<float*>(stg + Cfg::STG_BYTES);
+  float* bias_sm = reinterpret_cast<float*>(stg + Cfg::STG_BYTES + Cfg::RED_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x;
-  const int m_tile = blockIdx.y;
-  const int b = blockIdx.z / p.split_k;
-  const int split = blockIdx.z % p.split_k;
-  const int kb0 = split * p.kb_per_split;
-  const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-  const int niter = (kb1 - kb0) * p.npairs;
-  const int m0 = m_tile * BM;
-  const int n0 = n_tile * BN;
+  const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int total_tiles = tiles_mn * p.batch * p.split_k;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -93,10 +99,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, GemmCfg<BN>::MIN_CTAS)
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    mbar_init(smem_u32(&tmem_full_bar), 1);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tmem_full_bar[s]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[s]), 128);
+    }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_holder), BN);
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_holder), Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -105,33 +115,40 @@ __global__ void __launch_bounds__(GEMM_THREADS, GemmCfg<BN>::MIN_CTAS)
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------ TMA producer
     if (elect_one()) {
-      const int ab = p.a_batched ? b : 0;
-      const int bb = p.b_batched ? b : 0;
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < niter; ++it) {
-        const int pair = it % p.npairs;
-        const int k0 = (kb0 + it / p.npairs) * BK;
-        const uint32_t fb = smem_u32(&full_bar[stage]);
-        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-        mbar_expect_tx(fb, Cfg::STAGE_BYTES);
-        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-        const uint32_t sb = sa + Cfg::A_BYTES;
-        if (!A_MN) {
-          tma_load_4d(&tmA, fb, sa, k0, m0, ab, p.pairA[pair]);
-        } else {
-          tma_load_4d(&tmA, fb, sa, m0, k0, ab, p.pairA[pair]);
-          tma_load_4d(&tmA, fb, sa + 8192, m0 + 64, k0, ab, p.pairA[pair]);
-        }
-        if (!B_MN) {
-          tma_load_4d(&tmB, fb, sb, k0, n0, bb, p.pairB[pair]);
-        } else {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int z = tile / tiles_mn, mn = tile % tiles_mn;
+        const int m0 = (mn / p.tiles_n) * BM, n0 = (mn % p.tiles_n) * BN;
+        const int b = z / p.split_k, split = z % p.split_k;
+        const int ab = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
+        const int kb0 = split * p.kb_per_split;
+        const int niter = (min(p.kb_total, kb0 + p.kb_per_split) - kb0) * p.npairs;
+        for (int it = 0; it < niter; ++it) {
+          const int pair = it % p.npairs;
+          const int k0 = (kb0 + it / p.npairs) * BK;
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+          mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          if (!A_MN) {
+            tma_load_4d(&tmA, fb, sa, k0, m0, ab, p.pairA[pair]);
+          } else {
+            tma_load_4d(&tmA, fb, sa, m0, k0, ab, p.pairA[pair]);
+            tma_load_4d(&tmA, fb, sa + 8192, m0 + 64, k0, ab, p.pairA[pair]);
+          }
+          if (!B_MN) {
+            tma_load_4d(&tmB, fb, sb, k0, n0, bb, p.pairB[pair]);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_4d(&tmB, fb, sb + j * 8192, n0 + j * 64, k0, bb, p.pairB[pair]);
-        }
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1u;
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_4d(&tmB, fb, sb + j * 8192, n0 + j * 64, k0, bb, p.pairB[pair]);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
       }
     }
@@ -141,159 +158,185 @@ __global__ void __launch_bounds__(GEMM_THREADS, GemmCfg<BN>::MIN_CTAS)
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < niter; ++it) {
-        mbar_wait(smem_u32(&full_bar[stage]), phase);
+      int local = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        const int z = tile / tiles_mn;
+        const int split = z % p.split_k;
+        const int kb0 = split * p.kb_per_split;
+        const int niter = (min(p.kb_total, kb0 + p.kb_per_split) - kb0) * p.npairs;
+        const int acc = local & 1;
+        const uint32_t use = static_cast<uint32_t>(local >> 1);
+        mbar_wait(smem_u32(&tmem_empty_bar[acc]), (use & 1u) ^ 1u);  // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-        const uint32_t sb = sa + Cfg::A_BYTES;
+        const uint32_t tacc = tmem_base + acc * BN;
+        for (int it = 0; it < niter; ++it) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t ad = A_MN ? make_sdesc(sa + k * 2048, 8192, 1024) : make_sdesc(sa + k * 32, 16, 1024);
-          const uint64_t bd = B_MN ? make_sdesc(sb + k * 2048, 8192, 1024) : make_sdesc(sb + k * 32, 16, 1024);
-          umma_f16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = A_MN ? make_sdesc(sa + k * 2048, 8192, 1024) : make_sdesc(sa + k * 32, 16, 1024);
+            const uint64_t bd = B_MN ? make_sdesc(sb + k * 2048, 8192, 1024) : make_sdesc(sb + k * 32, 16, 1024);
+            umma_f16(tacc, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));  // slot reusable once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
-        umma_commit(smem_u32(&empty_bar[stage]));  // slot reusable once these MMAs have read it
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1u;
-        }
+        umma_commit(smem_u32(&tmem_full_bar[acc]));  // accumulator complete
       }
-      umma_commit(smem_u32(&tmem_full_bar));  // accumulator complete
     }
   } else {
     // ------------------------------------------------------------------------------------------ epilogue
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    const int grow = m0 + row;
     const int e = (warp - 2) * 32 + lane;  // 0..127
-    mbar_wait(smem_u32(&tmem_full_bar), 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    if (p.out_kind != 0) {
-      float* Df = reinterpret_cast<float*>(p.D) + static_cast<long long>(b) * p.strideD +
-                  static_cast<long long>(grow) * p.ldd;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int z = tile / tiles_mn, mn = tile % tiles_mn;
+      const int m_tile = mn / p.tiles_n;
+      const int m0 = m_tile * BM, n0 = (mn % p.tiles_n) * BN;
+      const int b = z / p.split_k, split = z % p.split_k;
+      const int acc = local & 1;
+      const uint32_t use = static_cast<uint32_t>(local >> 1);
+      const int grow = m0 + row;
+      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+      const bool use_bias = p.bias != nullptr && split == 0;
+      if (use_bias) {
+        for (int col = e; col < BN; col += 128) bias_sm[col] = (n0 + col < p.N) ? p.bias[n0 + col] : 0.f;
+      }
+      named_bar_sync(1, 128);  // bias visible; previous tile's staging fully consumed
+      mbar_wait(smem_u32(&tmem_full_bar[acc]), use & 1u);
+      tc_fence_after();
+      if (p.out_kind != 0) {
+        float* Df = reinterpret_cast<float*>(p.D) + static_cast<long long>(b) * p.strideD +
+                    static_cast<long long>(grow) * p.ldd;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        tmem_ld_wait();
-        if (grow < p.M) {
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (grow < p.M) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int gc = n0 + c * 32 + j;
-            if (gc < p.N) {
-              float f0 = __uint_as_float(v[j]) * p.alpha, f1 = __uint_as_float(v[j + 1]) * p.alpha;
-              float f2 = __uint_as_float(v[j + 2]) * p.alpha, f3 = __uint_as_float(v[j + 3]) * p.alpha;
-              if (p.bias != nullptr && split == 0) {
-                f0 += p.bias[gc];
-                f1 += p.bias[gc + 1];
-                f2 += p.bias[gc + 2];
-                f3 += p.bias[gc + 3];
-              }
-              if (p.out_kind == 2) {
-                red_add_v4(Df + gc, f0, f1, f2, f3);
-              } else {
-                *reinterpret_cast<float4*>(Df + gc) = make_float4(f0, f1, f2, f3);
+            for (int j = 0; j < 32; j += 4) {
+              const int gc = n0 + c * 32 + j;
+              if (gc < p.N) {
+                float f0 = __uint_as_float(v[j]) * p.alpha, f1 = __uint_as_float(v[j + 1]) * p.alpha;
+                float f2 = __uint_as_float(v[j + 2]) * p.alpha, f3 = __uint_as_float(v[j + 3]) * p.alpha;
+                if (use_bias) {
+                  f0 += bias_sm[c * 32 + j];
+                  f1 += bias_sm[c * 32 + j + 1];
+                  f2 += bias_sm[c * 32 + j + 2];
+                  f3 += bias_sm[c * 32 + j + 3];
+                }
+                if (p.out_kind == 2) {
+                  red_add_v4(Df + gc, f0, f1, f2, f3);
+                } else {
+                  *reinterpret_cast<float4*>(Df + gc) = make_float4(f0, f1, f2, f3);
+                }
               }
             }
           }
         }
-      }
-    } else {
-      uint8_t* stg = smem_gen;  // ring is idle: every TMA load landed and every MMA that read it completed
+        tc_fence_before();
+        mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        tmem_ld_wait();
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          float f[8];
+          for (int j = 0; j < 32; j += 8) {
+            float f[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            f[t] = __uint_as_float(v[j + t]) * p.alpha;
-            if (p.bias != nullptr) {
-              const int gc = n0 + c * 32 + j + t;
-              f[t] += (gc < p.N) ? p.bias[gc] : 0.f;
+            for (int t = 0; t < 8; ++t) {
+              f[t] = __uint_as_float(v[j + t]) * p.alpha;
+              if (use_bias) f[t] += bias_sm[c * 32 + j + t];
             }
-          }
-          uint4 pk = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
-                                pack_bf16(f[6], f[7]));
-          *reinterpret_cast<uint4*>(stg + row * Cfg::STG_ROW + (c * 32 + j) * 2) = pk;
-        }
-      }
-      named_bar_sync(1, 128);
-      const int rows_valid = min(BM, p.M - m0);
-      if (p.colstats != nullptr) {
-        // 128 threads = (BN/8 column groups of 8) x (row groups); 128-bit shared loads, then a fixed-order combine
-        constexpr int CG = BN / 8;
-        constexpr int RG = 128 / CG;
-        constexpr int RPG = BM / RG;
-        float* redbuf = reinterpret_cast<float*>(stg + BM * Cfg::STG_ROW);  // [RG][2][BN]
-        const int cg = e % CG, rg = e / CG;
-        float s[8], s2[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) s[t] = s2[t] = 0.f;
-        const int r_end = min(rows_valid, (rg + 1) * RPG);
-        for (int r = rg * RPG; r < r_end; ++r) {
-          const uint4 pk = *reinterpret_cast<const uint4*>(stg + r * Cfg::STG_ROW + cg * 16);
-          const uint32_t* u = reinterpret_cast<const uint32_t*>(&pk);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float2 x = unpack_bf16(u[t]);
-            s[2 * t] += x.x;
-            s[2 * t + 1] += x.y;
-            s2[2 * t] = fmaf(x.x, x.x, s2[2 * t]);
-            s2[2 * t + 1] = fmaf(x.y, x.y, s2[2 * t + 1]);
+            uint4 pk = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                  pack_bf16(f[6], f[7]));
+            *reinterpret_cast<uint4*>(stg + row * Cfg::STG_ROW + (c * 32 + j) * 2) = pk;
           }
         }
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          redbuf[(rg * 2 + 0) * BN + cg * 8 + t] = s[t];
-          redbuf[(rg * 2 + 1) * BN + cg * 8 + t] = s2[t];
-        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&tmem_empty_bar[acc]));  // accumulator free: the next tile's MMAs may start
         named_bar_sync(1, 128);
-        float* cs = p.colstats + (static_cast<long long>(b) * p.tiles_m + m_tile) * 2 * p.N;
-        for (int col = e; col < BN; col += 128) {
-          const int gc = n0 + col;
-          if (gc < p.N) {
-            float a = 0.f, a2 = 0.f;
+        const int rows_valid = min(BM, p.M - m0);
+        if (p.colstats != nullptr) {
+          // 128 threads = (BN/8 column groups of 8) x (row groups); 128-bit shared loads, then a fixed-order combine
+          constexpr int CG = BN / 8;
+          constexpr int RG = 128 / CG;
+          constexpr int RPG = BM / RG;
+          const int cg = e % CG, rg = e / CG;
+          float s[8], s2[8];
 #pragma unroll
-            for (int g = 0; g < RG; ++g) {
-              a += redbuf[(g * 2 + 0) * BN + col];
-              a2 += redbuf[(g * 2 + 1) * BN + col];
-            }
-            cs[gc] = a;
-            cs[p.N + gc] = a2;
-          }
-        }
-      }
-      bf16* Db = reinterpret_cast<bf16*>(p.D) + static_cast<long long>(b) * p.strideD;
-      const bf16* Ad = p.addend ? p.addend + static_cast<long long>(b) * p.stride_add : nullptr;
-      constexpr int CH = BN / 8;  // 16-byte chunks per row
-      for (int idx = e; idx < BM * CH; idx += 128) {
-        const int r = idx / CH, ch = idx % CH;
-        const int gr = m0 + r, gc = n0 + ch * 8;
-        if (gr < p.M && gc < p.N) {
-          uint4 pk = *reinterpret_cast<const uint4*>(stg + r * Cfg::STG_ROW + ch * 16);
-          if (Ad != nullptr) {
-            const uint4 ad = *reinterpret_cast<const uint4*>(Ad + static_cast<long long>(gr) * p.ld_add + gc);
-            const uint32_t* a32 = reinterpret_cast<const uint32_t*>(&ad);
-            uint32_t* p32 = reinterpret_cast<uint32_t*>(&pk);
+          for (int t = 0; t < 8; ++t) s[t] = s2[t] = 0.f;
+          const int r_end = min(rows_valid, (rg + 1) * RPG);
+          for (int r = rg * RPG; r < r_end; ++r) {
+            const uint4 pk = *reinterpret_cast<const uint4*>(stg + r * Cfg::STG_ROW + cg * 16);
+            const uint32_t* u = reinterpret_cast<const uint32_t*>(&pk);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              const float2 x = unpack_bf16(p32[t]), y = unpack_bf16(a32[t]);
-              p32[t] = pack_bf16(x.x + y.x, x.y + y.y);
+              const float2 x = unpack_bf16(u[t]);
+              s[2 * t] += x.x;
+              s[2 * t + 1] += x.y;
+              s2[2 * t] = fmaf(x.x, x.x, s2[2 * t]);
+              s2[2 * t + 1] = fmaf(x.y, x.y, s2[2 * t + 1]);
             }
           }
-          *reinterpret_cast<uint4*>(Db + static_cast<long long>(gr) * p.ldd + gc) = pk;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            redbuf[(rg * 2 + 0) * BN + cg * 8 + t] = s[t];
+            redbuf[(rg * 2 + 1) * BN + cg * 8 + t] = s2[t];
+          }
+          named_bar_sync(1, 128);
+          float* cs = p.colstats + (static_cast<long long>(b) * p.tiles_m + m_tile) * 2 * p.N;
+          for (int col = e; col < BN; col += 128) {
+            const int gc = n0 + col;
+            if (gc < p.N) {
+              float a = 0.f, a2 = 0.f;
+#pragma unroll
+              for (int g = 0; g < RG; ++g) {
+                a += redbuf[(g * 2 + 0) * BN + col];
+                a2 += redbuf[(g * 2 + 1) * BN + col];
+              }
+              cs[gc] = a;
+              cs[p.N + gc] = a2;
+            }
+          }
+        }
+        bf16* Db = reinterpret_cast<bf16*>(p.D) + static_cast<long long>(b) * p.strideD;
+        const bf16* Ad = p.addend ? p.addend + static_cast<long long>(b) * p.stride_add : nullptr;
+        constexpr int CH = BN / 8;  // 16-byte chunks per row
+#pragma unroll 4
+        for (int idx = e; idx < BM * CH; idx += 128) {
+          const int r = idx / CH, ch = idx % CH;
+          const int gr = m0 + r, gc = n0 + ch * 8;
+          if (gr < p.M && gc < p.N) {
+            uint4 pk = *reinterpret_cast<const uint4*>(stg + r * Cfg::STG_ROW + ch * 16);
+            if (Ad != nullptr) {
+              const uint4 ad = *reinterpret_cast<const uint4*>(Ad + static_cast<long long>(gr) * p.ld_add + gc);
+              const uint32_t* a32 = reinterpret_cast<const uint32_t*>(&ad);
+              uint32_t* p32 = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 x = unpack_bf16(p32[t]), y = unpack_bf16(a32[t]);
+                p32[t] = pack_bf16(x.x + y.x, x.y + y.y);
+              }
+            }
+            *reinterpret_cast<uint4*>(Db + static_cast<long long>(gr) * p.ldd + gc) = pk;
+          }
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -343,23 +386,27 @@ int make_operand_map(CUtensorMap* tm, const GemmOperand& op, int rows, int K, in
 }
 
 template <bool A_MN, bool B_MN, int BN>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, dim3 grid, cudaStream_t stream) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKParams p, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_kernel<A_MN, B_MN, BN>;
   // per launch: the attribute is per device, and callers may drive several GPUs from one process (nn.DataParallel)
   cudaError_t attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   if (attr_err != cudaSuccess) return check_cuda(attr_err, "cudaFuncSetAttribute(gemm)");
+  p.tiles_n = (p.N + BN - 1) / BN;
+  const long long total = static_cast<long long>(p.tiles_m) * p.tiles_n * p.batch * p.split_k;
+  if (total > 0x7fffffffLL) return set_error(GLF_ERR_INVALID, "gemm: too many tiles");
+  const int grid = static_cast<int>(total < num_sms ? total : num_sms);
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   return check_cuda(cudaGetLastError(), "gemm launch");
 }
 
 template <int BN>
-int launch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, dim3 grid,
-                 cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch<false, false, BN>(tmA, tmB, p, grid, stream);
-  if (a_mn && b_mn) return launch<true, true, BN>(tmA, tmB, p, grid, stream);
-  if (a_mn) return launch<true, false, BN>(tmA, tmB, p, grid, stream);
-  return launch<false, true, BN>(tmA, tmB, p, grid, stream);
+int launch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
+                 int num_sms, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch<false, false, BN>(tmA, tmB, p, num_sms, stream);
+  if (a_mn && b_mn) return launch<true, true, BN>(tmA, tmB, p, num_sms, stream);
+  if (a_mn) return launch<true, false, BN>(tmA, tmB, p, num_sms, stream);
+  return launch<false, true, BN>(tmA, tmB, p, num_sms, stream);
 }
 
 }  // namespace
@@ -408,14 +455,16 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
   p.addend = a.addend; p.ld_add = a.ld_add; p.stride_add = a.stride_add;
   p.colstats = a.colstats;
   p.tiles_m = gemm_tiles_m(a.M);
-  const long long gz = static_cast<long long>(a.batch) * p.split_k;
-  if (p.tiles_m > 65535 || gz > 65535) return set_error(GLF_ERR_INVALID, "gemm: grid too large");
-  dim3 grid((a.N + BN - 1) / BN, p.tiles_m, static_cast<unsigned>(gz));
+  p.tiles_n = 0;  // set per tile shape in launch()
+  int dev = 0, num_sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0)
+    return set_error(GLF_ERR_DEVICE, "gemm: cannot query the SM count");
   const bool amn = a.A.mn_major != 0, bmn = a.B.mn_major != 0;
   switch (BN) {
-    case 64: return launch_major<64>(amn, bmn, tmA, tmB, p, grid, stream);
-    case 128: return launch_major<128>(amn, bmn, tmA, tmB, p, grid, stream);
-    default: return launch_major<256>(amn, bmn, tmA, tmB, p, grid, stream);
+    case 64: return launch_major<64>(amn, bmn, tmA, tmB, p, num_sms, stream);
+    case 128: return launch_major<128>(amn, bmn, tmA, tmB, p, num_sms, stream);
+    default: return launch_major<256>(amn, bmn, tmA, tmB, p, num_sms, stream);
   }
 }
 
