@@ -8,7 +8,7 @@
 //   warp 1      MMA issuer    : allocates TMEM (two accumulator stages), one elected lane issues tcgen05.mma
 //                               (M=128, N=BN, K=16) x 4 per stage; tcgen05.commit releases the smem slot / publishes
 //                               the accumulator, so tile i+1 is computed while tile i is still in its epilogue
-//   warps 2..5  epilogue      : tcgen05.ld the fp32 accumulator (one TMEM lane quarter per warp), alpha/bias, then
+//   warps 2..17 epilogue      : tcgen05.ld the fp32 accumulator (one TMEM lane quarter per warp), alpha/bias, then
 //                               either fp32 store / fp32 red.add (split-K) straight from registers, or bf16 staging in
 //                               smem -> fully coalesced 16-byte row stores (+ residual addend) and per-tile column
 //                               statistics (sum, sum of squares) for the BatchNorm that follows W_z (ours.py:908).
@@ -25,7 +25,9 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 16;                 // 4 per SM sub-partition: the epilogue is a latency chain, it needs TLP
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int GEMM_THREADS = 64 + EPI_THREADS;  // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 
 struct GemmKParams {
   int M, N, K, batch;
@@ -54,7 +56,7 @@ struct GemmCfg {
   static constexpr uint32_t RING_BYTES = STAGES * STAGE_BYTES;
   static constexpr uint32_t STG_ROW = BN * 2 + 16;  // staging row pitch (bytes): odd multiple of 16 -> conflict free
   static constexpr uint32_t STG_BYTES = BM * STG_ROW;
-  static constexpr uint32_t RED_BYTES = 8192;       // [RG][2][BN] floats for the column-statistics combine
+  static constexpr uint32_t RED_BYTES = (BN == 256) ? 0 : EPI_WARPS * 2 * BN * 4;  // [warp][2][BN] column-stat partials
   static constexpr uint32_t BIAS_BYTES = BN * 4;
   static constexpr uint32_t SMEM_BYTES = RING_BYTES + STG_BYTES + RED_BYTES + BIAS_BYTES + 1024;
   static constexpr uint32_t TMEM_COLS = 2 * BN;     // two accumulator stages
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tmem_full_bar[s]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[s]), 128);
+      mbar_init(smem_u32(&tmem_empty_bar[s]), EPI_THREADS);
     }
     fence_mbar_init();
   }
@@ -191,9 +193,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   } else {
     // ------------------------------------------------------------------------------------------ epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // 16 warps: warp (2 + ew) reads TMEM lane quarter (warp % 4) and the 32-column chunks {ew/4, ew/4 + 4, ...}.
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int cc0 = ew >> 2;
     const int row = q * 32 + lane;
-    const int e = (warp - 2) * 32 + lane;  // 0..127
+    const int e = ew * 32 + lane;  // 0..EPI_THREADS-1
+    constexpr int NCHUNK = BN / 32;
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int z = tile / tiles_mn, mn = tile % tiles_mn;
@@ -205,17 +211,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const int grow = m0 + row;
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
       const bool use_bias = p.bias != nullptr && split == 0;
-      if (use_bias) {
-        for (int col = e; col < BN; col += 128) bias_sm[col] = (n0 + col < p.N) ? p.bias[n0 + col] : 0.f;
-      }
-      named_bar_sync(1, 128);  // bias visible; previous tile's staging fully consumed
+      if (use_bias && e < BN) bias_sm[e] = (n0 + e < p.N) ? p.bias[n0 + e] : 0.f;
+      named_bar_sync(1, EPI_THREADS);  // bias visible; previous tile's staging fully consumed
       mbar_wait(smem_u32(&tmem_full_bar[acc]), use & 1u);
       tc_fence_after();
       if (p.out_kind != 0) {
         float* Df = reinterpret_cast<float*>(p.D) + static_cast<long long>(b) * p.strideD +
                     static_cast<long long>(grow) * p.ldd;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = cc0; c < NCHUNK; c += 4) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
@@ -227,10 +231,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 float f0 = __uint_as_float(v[j]) * p.alpha, f1 = __uint_as_float(v[j + 1]) * p.alpha;
                 float f2 = __uint_as_float(v[j + 2]) * p.alpha, f3 = __uint_as_float(v[j + 3]) * p.alpha;
                 if (use_bias) {
-                  f0 += bias_sm[c * 32 + j];
-                  f1 += bias_sm[c * 32 + j + 1];
-                  f2 += bias_sm[c * 32 + j + 2];
-                  f3 += bias_sm[c * 32 + j + 3];
+                  const float4 bv = *reinterpret_cast<const float4*>(bias_sm + c * 32 + j);
+                  f0 += bv.x; f1 += bv.y; f2 += bv.z; f3 += bv.w;
                 }
                 if (p.out_kind == 2) {
                   red_add_v4(Df + gc, f0, f1, f2, f3);
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
       } else {
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = cc0; c < NCHUNK; c += 4) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
@@ -253,9 +255,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           for (int j = 0; j < 32; j += 8) {
             float f[8];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              f[t] = __uint_as_float(v[j + t]) * p.alpha;
-              if (use_bias) f[t] += bias_sm[c * 32 + j + t];
+            for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(v[j + t]) * p.alpha;
+            if (use_bias) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_sm + c * 32 + j);
+              const float4 b1 = *reinterpret_cast<const float4*>(bias_sm + c * 32 + j + 4);
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
             }
             uint4 pk = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
                                   pack_bf16(f[6], f[7]));
@@ -264,13 +269,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         }
         tc_fence_before();
         mbar_arrive(smem_u32(&tmem_empty_bar[acc]));  // accumulator free: the next tile's MMAs may start
-        named_bar_sync(1, 128);
+        named_bar_sync(1, EPI_THREADS);
         const int rows_valid = min(BM, p.M - m0);
-        if (p.colstats != nullptr) {
-          // 128 threads = (BN/8 column groups of 8) x (row groups); 128-bit shared loads, then a fixed-order combine
-          constexpr int CG = BN / 8;
-          constexpr int RG = 128 / CG;
-          constexpr int RPG = BM / RG;
+        // coalesced 16-byte row stores; the residual addend loads of all iterations are issued first
+        bf16* Db = reinterpret_cast<bf16*>(p.D) + static_cast<long long>(b) * p.strideD;
+        const bf16* Ad = p.addend ? p.addend + static_cast<long long>(b) * p.stride_add : nullptr;
+        constexpr int CH = BN / 8;                       // 16-byte chunks per row
+        constexpr int NIT = (BM * CH) / EPI_THREADS;     // 2 / 4 / 8
+        uint4 adv[NIT];
+        if (Ad != nullptr) {
+#pragma unroll
+          for (int i = 0; i < NIT; ++i) {
+            const int idx = e + i * EPI_THREADS;
+            const int r = idx / CH, ch = idx % CH;
+            const int gr = m0 + r, gc = n0 + ch * 8;
+            adv[i] = (gr < p.M && gc < p.N)
+                         ? *reinterpret_cast<const uint4*>(Ad + static_cast<long long>(gr) * p.ld_add + gc)
+                         : make_uint4(0, 0, 0, 0);
+          }
+        }
+        if (BN != 256 && p.colstats != nullptr) {
+          // every thread sums 8 columns over its row group, lanes sharing a column group combine by shuffle,
+          // one partial per warp lands in shared memory and BN threads add the 16 warp partials in fixed order
+          constexpr int CG = BN / 8;                 // column groups (<= 32)
+          constexpr int RG = EPI_THREADS / CG;       // row groups
+          constexpr int RPG = BM / RG;               // rows per group
           const int cg = e % CG, rg = e / CG;
           float s[8], s2[8];
 #pragma unroll
@@ -289,38 +312,42 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             }
           }
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            redbuf[(rg * 2 + 0) * BN + cg * 8 + t] = s[t];
-            redbuf[(rg * 2 + 1) * BN + cg * 8 + t] = s2[t];
-          }
-          named_bar_sync(1, 128);
-          float* cs = p.colstats + (static_cast<long long>(b) * p.tiles_m + m_tile) * 2 * p.N;
-          for (int col = e; col < BN; col += 128) {
-            const int gc = n0 + col;
-            if (gc < p.N) {
-              float a = 0.f, a2 = 0.f;
+          for (int off = CG; off < 32; off <<= 1) {
 #pragma unroll
-              for (int g = 0; g < RG; ++g) {
-                a += redbuf[(g * 2 + 0) * BN + col];
-                a2 += redbuf[(g * 2 + 1) * BN + col];
-              }
-              cs[gc] = a;
-              cs[p.N + gc] = a2;
+            for (int t = 0; t < 8; ++t) {
+              s[t] += __shfl_xor_sync(0xffffffffu, s[t], off);
+              s2[t] += __shfl_xor_sync(0xffffffffu, s2[t], off);
             }
           }
+          if (lane < CG) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              redbuf[(ew * 2 + 0) * BN + lane * 8 + t] = s[t];
+              redbuf[(ew * 2 + 1) * BN + lane * 8 + t] = s2[t];
+            }
+          }
+          named_bar_sync(1, EPI_THREADS);
+          if (e < BN && n0 + e < p.N) {
+            float a = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int g = 0; g < EPI_WARPS; ++g) {
+              a += redbuf[(g * 2 + 0) * BN + e];
+              a2 += redbuf[(g * 2 + 1) * BN + e];
+            }
+            float* cs = p.colstats + (static_cast<long long>(b) * p.tiles_m + m_tile) * 2 * p.N;
+            cs[n0 + e] = a;
+            cs[p.N + n0 + e] = a2;
+          }
         }
-        bf16* Db = reinterpret_cast<bf16*>(p.D) + static_cast<long long>(b) * p.strideD;
-        const bf16* Ad = p.addend ? p.addend + static_cast<long long>(b) * p.stride_add : nullptr;
-        constexpr int CH = BN / 8;  // 16-byte chunks per row
-#pragma unroll 4
-        for (int idx = e; idx < BM * CH; idx += 128) {
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+          const int idx = e + i * EPI_THREADS;
           const int r = idx / CH, ch = idx % CH;
           const int gr = m0 + r, gc = n0 + ch * 8;
           if (gr < p.M && gc < p.N) {
             uint4 pk = *reinterpret_cast<const uint4*>(stg + r * Cfg::STG_ROW + ch * 16);
             if (Ad != nullptr) {
-              const uint4 ad = *reinterpret_cast<const uint4*>(Ad + static_cast<long long>(gr) * p.ld_add + gc);
-              const uint32_t* a32 = reinterpret_cast<const uint32_t*>(&ad);
+              const uint32_t* a32 = reinterpret_cast<const uint32_t*>(&adv[i]);
               uint32_t* p32 = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
@@ -426,6 +453,7 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
   // loads.  Large-K (tensor-bound, e.g. C=2048) products take the 128x256 tile.
   int BN = (a.N <= 64) ? 64 : ((a.K >= 512 && a.N % 256 == 0) ? 256 : 128);
   if (a.bn_hint == 64 || a.bn_hint == 128 || a.bn_hint == 256) BN = a.bn_hint;
+  if (a.colstats != nullptr && BN == 256) BN = 128;  // the column-statistics epilogue is built for tiles <= 128 wide
   int nlimbsA = 1, nlimbsB = 1;
   for (int i = 0; i < a.npairs; ++i) {
     nlimbsA = a.pairA[i] + 1 > nlimbsA ? a.pairA[i] + 1 : nlimbsA;
