@@ -75,8 +75,6 @@ int make_dims(const glf_desc* d, Dims* o) {
   if (d->C > 2048) return set_error(GLF_ERR_INVALID, "C <= 2048 supported (got %d)", d->C);
   if (d->mode != GLF_MODE_DOT && d->mode != GLF_MODE_EMBEDDED)
     return set_error(GLF_ERR_UNSUPPORTED, "mode must be dot or embedded ('gaussian'/'concatenate' are not built by the reference network)");
-  if (d->mode == GLF_MODE_EMBEDDED && d->Ci != 128 && d->Ci != 64)
-    return set_error(GLF_ERR_UNSUPPORTED, "mode='embedded' supports inter_channels 64 or 128 (got %d)", d->Ci);
   if (d->precision != GLF_PRECISION_BF16) return set_error(GLF_ERR_UNSUPPORTED, "only GLF_PRECISION_BF16 is implemented");
   if (d->io_dtype != GLF_DTYPE_BF16 && d->io_dtype != GLF_DTYPE_F32) return set_error(GLF_ERR_INVALID, "bad io_dtype");
   o->B = d->B;
@@ -130,12 +128,13 @@ size_t carve_saved(const Dims& m, void* base, Saved* s) {
   return (c.off + 255) & ~static_cast<size_t>(255);
 }
 
-struct WsFwd { float* colstats; float* Mf; void* saved_fallback; };
+struct WsFwd { float* colstats; float* Mf; void* attn; void* saved_fallback; };
 size_t carve_ws_fwd(const Dims& m, void* base, WsFwd* w, size_t saved_bytes) {
   Carver c(base);
   const size_t np = m.dot ? static_cast<size_t>(m.B) * m.tiles_seq : static_cast<size_t>(m.tiles_all);
   w->colstats = c.take<float>(np * 2 * m.C);
   w->Mf = m.dot ? c.take<float>(static_cast<size_t>(m.B) * m.Ci * m.Ci) : nullptr;  // split-K accumulation target
+  w->attn = m.dot ? nullptr : c.take<uint8_t>(attn_scratch_bytes(m.B, m.N, false));
   w->saved_fallback = c.take<uint8_t>(saved_bytes);  // used when the caller passes saved == NULL (inference)
   return (c.off + 255) & ~static_cast<size_t>(255);
 }
@@ -143,6 +142,7 @@ size_t carve_ws_fwd(const Dims& m, void* base, WsFwd* w, size_t saved_bytes) {
 struct WsBwd {
   bf16 *dztok, *dV, *dU, *dP, *dY, *dxtok, *dM, *dWpb;
   float *dWpf, *part_ln, *k1, *k2, *k3, *cs_t, *cs_p, *cs_g, *dwcat, *delta;
+  void* attn;
 };
 size_t carve_ws_bwd(const glf_desc* d, const Dims& m, void* base, WsBwd* w) {
   Carver c(base);
@@ -162,11 +162,12 @@ size_t carve_ws_bwd(const glf_desc* d, const Dims& m, void* base, WsBwd* w) {
     w->delta = c.take<float>(rows);
     w->dWpf = nullptr; w->dWpb = nullptr; w->dM = nullptr;
   }
+  w->attn = m.dot ? nullptr : c.take<uint8_t>(attn_scratch_bytes(m.B, m.N, true));
   w->part_ln = c.take<float>(static_cast<size_t>(bn_res_ln_bwd_blocks(m.rows, m.C)) * 4 * C);
   w->k1 = c.take<float>(C);
   w->k2 = c.take<float>(C);
   w->k3 = c.take<float>(C);
-  const size_t np = m.dot ? B * m.tiles_seq : static_cast<size_t>(m.tiles_all);
+  const size_t np = B * m.tiles_seq;
   w->cs_t = c.take<float>(np * 2 * Ci);
   w->cs_p = c.take<float>(np * 2 * Ci);
   w->cs_g = c.take<float>(np * 2 * Ci);
@@ -302,7 +303,7 @@ GLF_API int glf_tpavi_fwd(const glf_desc* d, const void* x, const glf_weights* w
     }
     np = B * m.tiles_seq;
   } else {
-    GLF_TRY(flash_fwd(s.P, s.Y, s.lse, B, N, Ci, stream));
+    GLF_TRY(flash_fwd(s.P, s.Y, s.lse, B, N, Ci, wf.attn, stream));
     {  // U = Y Wz^T + bz
       GemmArgs g;
       g.A = opnd(s.Y, 0, Ci, 0);
@@ -452,8 +453,8 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
       g.split_k = pick_split(static_cast<long long>((C + 127) / 128) * ((Ci + 127) / 128), rows);
       GLF_TRY(gemm(g, stream));
     }
-    GLF_TRY(flash_bwd(s.P, s.Y, wb.dY, s.lse, wb.dP, wb.delta, B, N, Ci, stream));
-    np = 0;
+    GLF_TRY(flash_bwd(s.P, s.Y, wb.dY, s.lse, wb.dP, wb.delta, wb.cs_t, wb.cs_p, wb.cs_g, B, N, Ci, wb.attn, stream));
+    np = B * m.tiles_seq;
   }
   GLF_TRY(check_cuda(cudaMemsetAsync(wb.dwcat, 0, sizeof(float) * 3 * Ci * C, stream), "memset dWcat"));
   {  // dWcat[r,c] = sum_n dP[n,r] X[n,c]
@@ -479,13 +480,9 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
     g.D = m.pack_x ? static_cast<void*>(wb.dxtok) : dx; g.ldd = C;
     GLF_TRY(gemm(g, stream));
   }
-  if (m.dot) {
-    GLF_TRY(reduce_partials(wb.cs_t, np, 2LL * Ci, Ci, 1.f, g_->theta_b, stream));
-    GLF_TRY(reduce_partials(wb.cs_p, np, 2LL * Ci, Ci, 1.f, g_->phi_b, stream));
-    GLF_TRY(reduce_partials(wb.cs_g, np, 2LL * Ci, Ci, 1.f, g_->g_b, stream));
-  } else {
-    return set_error(GLF_ERR_UNSUPPORTED, "embedded backward bias gradients not wired");
-  }
+  GLF_TRY(reduce_partials(wb.cs_t, np, 2LL * Ci, Ci, 1.f, g_->theta_b, stream));
+  GLF_TRY(reduce_partials(wb.cs_p, np, 2LL * Ci, Ci, 1.f, g_->phi_b, stream));
+  GLF_TRY(reduce_partials(wb.cs_g, np, 2LL * Ci, Ci, 1.f, g_->g_b, stream));
   if (m.pack_x) {
     if (d->x_layout == GLF_LAYOUT_NCTHW)
       GLF_TRY(transpose_cast(wb.dxtok, dx, B, N, C, GLF_DTYPE_BF16, d->io_dtype, stream));

@@ -460,9 +460,9 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
     nlimbsB = a.pairB[i] + 1 > nlimbsB ? a.pairB[i] + 1 : nlimbsB;
   }
   CUtensorMap tmA, tmB;
-  int rc = make_operand_map(&tmA, a.A, a.M, a.K, a.batch, nlimbsA, BM);
+  int rc = make_operand_map(&tmA, a.A, a.A.rows > 0 ? a.A.rows : a.M, a.K, a.batch, nlimbsA, BM);
   if (rc) return rc;
-  rc = make_operand_map(&tmB, a.B, a.N, a.K, a.batch, nlimbsB, BN);
+  rc = make_operand_map(&tmB, a.B, a.B.rows > 0 ? a.B.rows : a.N, a.K, a.batch, nlimbsB, BN);
   if (rc) return rc;
 
   GemmKParams p;

@@ -22,6 +22,7 @@ struct GemmOperand {
   int64_t ld = 0;         // leading dimension in elements
   int64_t batch_stride = 0;  // elements; 0 = shared across batch
   int64_t limb_stride = 0;   // elements between bf16 limb planes (F32X3 precision); 0 when single limb
+  int rows = 0;              // valid rows of the operand (0 = the GEMM's M / N); smaller values are zero-filled by TMA
 };
 
 struct GemmArgs {
@@ -77,8 +78,11 @@ int gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, i
 // ------------------------------------------------------------------------------------------------ softmax attention
 // mode='embedded' (ours.py:896-897,902): Y = softmax(Theta Phi^T) G, flash-style, per batch entry.
 // P: [B, N, 3Ci] bf16 (theta | phi | g); Y: [B, N, Ci] bf16; lse: [B, N] fp32 (natural-log-sum-exp per query row)
-int flash_fwd(const bf16* P, bf16* Y, float* lse, int B, int N, int Ci, cudaStream_t stream);
-int flash_bwd(const bf16* P, const bf16* Y, const bf16* dY, const float* lse, bf16* dP, float* delta_ws, int B, int N,
-              int Ci, cudaStream_t stream);
+int attn_ld(int N);
+int attn_chunk(long long B, long long N);
+size_t attn_scratch_bytes(long long B, long long N, bool backward);
+int flash_fwd(const bf16* P, bf16* Y, float* lse, int B, int N, int Ci, void* scratch, cudaStream_t stream);
+int flash_bwd(const bf16* P, const bf16* Y, const bf16* dY, const float* lse, bf16* dP, float* delta, float* cs_t,
+              float* cs_p, float* cs_g, int B, int N, int Ci, void* scratch, cudaStream_t stream);
 
 }  // namespace glf

@@ -102,3 +102,39 @@ def test_linearity_property_full_size_cfg2():
     assert x.grad.abs().max() == 0
     assert int(m.W_z[1].num_batches_tracked) == 1
     assert torch.isfinite(m.W_z[1].running_var).all()
+
+
+@pytest.mark.parametrize("name", ["embedded_train_c128", "embedded_eval_c128"])
+@pytest.mark.parametrize("io", ["fp32", "bf16"])
+def test_golden_embedded(name, io):
+    """mode='embedded' (softmax attention, ours.py:896-897) against the reference module's golden vectors."""
+    g = load_golden(name)
+    B, C, T, H, W, training, bn = [int(v) for v in g["meta"]]
+    m = load_module_from_params(TPAVIModule, golden_params(g), C, "embedded", bool(bn))
+    m.train(bool(training))
+    dt = torch.float32 if io == "fp32" else torch.bfloat16
+    z, dx = _run(m, g["x"].to(DEV, dt), g["dz"].to(DEV, dt))
+    assert_close("z", z, g["z"], BF16_TOL)
+    assert_close("dx", dx, g["dx"], BF16_TOL)
+    for k, p in m.named_parameters():
+        if k.startswith("align_channel"):
+            continue
+        assert_close("grad:" + k, p.grad, g["grad:" + k], 4e-2, abs_floor=1e-3)
+
+
+def test_oracle_embedded_cfg2_tokens():
+    """Softmax mode at the cfg2 sequence length (4 views x 28 x 28 = 3136 tokens, C=256), ragged batch chunking."""
+    B, C, T, H, W = 3, 256, 4, 28, 28
+    p = O.init_params(C, seed=51, randomize_affine=True)
+    # moderate logits: the reference applies no 1/sqrt(d) scale, random init gives |theta.phi| ~ 1
+    gen = torch.Generator().manual_seed(52)
+    x = torch.randn(B, C, T, H, W, generator=gen)
+    dz = torch.randn(B, C, T, H, W, generator=gen)
+    zo, dxo, go = O.tpavi_fwd_bwd(x, dz, {k: v.clone() for k, v in p.items()}, mode="embedded")
+    m = load_module_from_params(TPAVIModule, p, C, "embedded", True).train()
+    z, dx = _run(m, x.to(DEV, torch.bfloat16), dz.to(DEV, torch.bfloat16))
+    assert_close("z", z, zo, BF16_TOL)
+    assert_close("dx", dx, dxo, BF16_TOL)
+    for k, pp in m.named_parameters():
+        if not k.startswith("align_channel"):
+            assert_close("grad:" + k, pp.grad, go[k], 4e-2, abs_floor=1e-3)
