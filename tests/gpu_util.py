@@ -48,9 +48,19 @@ def golden_params(g, prefix="param:"):
     return p
 
 
-def assert_close(name, got, ref, tol, abs_floor=0.0):
+def grad_scale(ref_grads):
+    """Largest |entry| over a module's reference parameter gradients: the yardstick for analytically-zero ones."""
+    return max(float(v.detach().abs().max()) for v in ref_grads)
+
+
+def assert_close(name, got, ref, tol, abs_floor=0.0, zero_scale=None):
     got = got.detach().float().cpu()
     ref = ref.detach().float().cpu()
+    if zero_scale is not None and ref.abs().max() < 1e-3:
+        # analytically-zero gradient (a per-channel shift that BatchNorm or the softmax cancels): the reference holds
+        # fp32 summation noise, the bf16 path holds bf16 rounding noise; bound it relative to the real gradients
+        assert got.abs().max() < tol * zero_scale, f"{name}: expected ~0, got {got.abs().max():.3e} vs scale {zero_scale:.3e}"
+        return
     if name.endswith("W_z.0.bias") and got.abs().max() == 0:
         # train-mode BatchNorm cancels any per-channel shift of U: the gradient is analytically zero; the kernels
         # return exactly 0 and the reference returns fp32 summation noise that grows with the token count
