@@ -56,7 +56,7 @@ def grad_scale(ref_grads):
 def assert_close(name, got, ref, tol, abs_floor=0.0, zero_scale=None):
     got = got.detach().float().cpu()
     ref = ref.detach().float().cpu()
-    if zero_scale is not None and ref.abs().max() < 1e-3:
+    if zero_scale is not None and ref.abs().max() < max(1e-3, 1e-4 * zero_scale):
         # analytically-zero gradient (a per-channel shift that BatchNorm or the softmax cancels): the reference holds
         # fp32 summation noise, the bf16 path holds bf16 rounding noise; bound it relative to the real gradients
         assert got.abs().max() < tol * zero_scale, f"{name}: expected ~0, got {got.abs().max():.3e} vs scale {zero_scale:.3e}"
