@@ -5,7 +5,7 @@ Public surface (mirrors the reference, R/models/ours.py):
     GlobalLocalFusion    gate + view concat + MGFM + MLFM + sum as one fused autograd node
     install()            monkey-patch the reference's module namespace so Global_and_Local builds on this block
 """
-from .tpavi import TPAVIModule  # noqa: F401
+from .tpavi import TPAVIModule, set_default_precision  # noqa: F401
 from .fusion import GlobalLocalFusion  # noqa: F401
 from . import dp  # noqa: F401
 from ._lib import GlfError, load as load_library  # noqa: F401

@@ -13,6 +13,7 @@ MODE_DOT, MODE_EMBEDDED = 0, 1
 DTYPE_BF16, DTYPE_F32 = 0, 1
 LAYOUT_NCTHW, LAYOUT_TOKEN = 0, 1
 PRECISION_BF16, PRECISION_F32X3 = 0, 1
+PRECISIONS = {"bf16": PRECISION_BF16, "fp32": PRECISION_F32X3}
 
 EXPORTS = ("glf_version", "glf_last_error", "glf_tpavi_sizes", "glf_tpavi_fwd", "glf_tpavi_bwd",
            "glf_gate_concat_fwd", "glf_gate_concat_bwd", "glf_gemm_bf16", "glf_transpose", "glf_bn_res_ln_fwd",
@@ -66,8 +67,8 @@ def load() -> C.CDLL:
         lib.glf_tpavi_bwd.argtypes = [C.POINTER(GlfDesc), vp, vp, C.POINTER(GlfWeights), vp, vp, C.POINTER(GlfGrads),
                                       vp, vp]
         pp = C.POINTER(C.c_void_p)
-        lib.glf_gate_concat_fwd.argtypes = [i32] * 6 + [f32, i32, pp, pp, pp, vp, vp, vp, vp]
-        lib.glf_gate_concat_bwd.argtypes = [i32] * 6 + [f32, i32, pp, pp, pp, vp, vp, vp, pp, pp, pp, vp]
+        lib.glf_gate_concat_fwd.argtypes = [i32] * 6 + [f32, i32, i32, pp, pp, pp, vp, vp, vp, vp]
+        lib.glf_gate_concat_bwd.argtypes = [i32] * 6 + [f32, i32, i32, pp, pp, pp, vp, vp, vp, pp, pp, pp, vp]
         lib.glf_gemm_bf16.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, vp, f32,
                                       vp, i64, i64, i32, i32, vp, vp]
         lib.glf_transpose.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]

@@ -75,7 +75,10 @@ int make_dims(const glf_desc* d, Dims* o) {
   if (d->C > 2048) return set_error(GLF_ERR_INVALID, "C <= 2048 supported (got %d)", d->C);
   if (d->mode != GLF_MODE_DOT && d->mode != GLF_MODE_EMBEDDED)
     return set_error(GLF_ERR_UNSUPPORTED, "mode must be dot or embedded ('gaussian'/'concatenate' are not built by the reference network)");
-  if (d->precision != GLF_PRECISION_BF16) return set_error(GLF_ERR_UNSUPPORTED, "only GLF_PRECISION_BF16 is implemented");
+  if (d->precision != GLF_PRECISION_BF16 && d->precision != GLF_PRECISION_F32X3)
+    return set_error(GLF_ERR_INVALID, "bad precision (GLF_PRECISION_BF16 or GLF_PRECISION_F32X3)");
+  if (d->precision == GLF_PRECISION_F32X3 && d->mode != GLF_MODE_DOT)
+    return set_error(GLF_ERR_UNSUPPORTED, "GLF_PRECISION_F32X3 is implemented for mode='dot' only");
   if (d->io_dtype != GLF_DTYPE_BF16 && d->io_dtype != GLF_DTYPE_F32) return set_error(GLF_ERR_INVALID, "bad io_dtype");
   o->B = d->B;
   o->N = static_cast<long long>(d->T) * d->H * d->W;
@@ -216,6 +219,7 @@ GLF_API int glf_tpavi_sizes(const glf_desc* d, glf_sizes* out) {
   Dims m;
   GLF_TRY(make_dims(d, &m));
   if (out == nullptr) return set_error(GLF_ERR_INVALID, "out is NULL");
+  if (d->precision == GLF_PRECISION_F32X3) return tpavi_sizes_f32x3(d, out);
   Saved s; WsFwd wf; WsBwd wb;
   out->saved_bytes = carve_saved(m, nullptr, &s);
   out->ws_fwd_bytes = carve_ws_fwd(m, nullptr, &wf, out->saved_bytes);
@@ -235,6 +239,7 @@ GLF_API int glf_tpavi_fwd(const glf_desc* d, const void* x, const glf_weights* w
   if (w == nullptr) return set_error(GLF_ERR_INVALID, "weights is NULL");
   if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0 || (saved && (reinterpret_cast<uintptr_t>(saved) & 255) != 0))
     return set_error(GLF_ERR_WORKSPACE, "saved/ws blobs must be 256-byte aligned");
+  if (d->precision == GLF_PRECISION_F32X3) return tpavi_fwd_f32x3(d, x, w, z, saved, ws, stream);
   Saved s; WsFwd wf;
   const size_t saved_bytes = carve_saved(m, nullptr, &s);
   carve_ws_fwd(m, ws, &wf, saved_bytes);
@@ -318,8 +323,8 @@ GLF_API int glf_tpavi_fwd(const glf_desc* d, const void* x, const glf_weights* w
   }
   GLF_TRY(bn_finalize(wf.colstats, np, C, static_cast<double>(m.rows), d, w, s.bn_mean, s.bn_rstd, s.bn_a, s.bn_b,
                       stream));
-  GLF_TRY(bn_res_ln_fwd(s.U, X, s.bn_a, s.bn_b, w->ln_w, w->ln_b, z, d->io_dtype, s.ln_mu, s.ln_r, m.rows, C,
-                        d->eps_ln, d->accumulate, stream));
+  GLF_TRY(bn_res_ln_fwd(s.U, X, GLF_DTYPE_BF16, s.bn_a, s.bn_b, w->ln_w, w->ln_b, z, d->io_dtype, s.ln_mu, s.ln_r,
+                        m.rows, C, d->eps_ln, d->accumulate, stream));
   return 0;
 }
 
@@ -337,6 +342,7 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
   if (w == nullptr || g_ == nullptr) return set_error(GLF_ERR_INVALID, "weights/grads is NULL");
   if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0 || (reinterpret_cast<uintptr_t>(saved) & 255) != 0)
     return set_error(GLF_ERR_WORKSPACE, "saved/ws blobs must be 256-byte aligned");
+  if (d->precision == GLF_PRECISION_F32X3) return tpavi_bwd_f32x3(d, dz, x, w, saved, dx, g_, ws, stream);
   Saved s; WsBwd wb;
   carve_saved(m, const_cast<void*>(saved), &s);
   carve_ws_bwd(d, m, ws, &wb);
@@ -353,13 +359,13 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
     dz_dtype = GLF_DTYPE_BF16;
   }
   const int nb = bn_res_ln_bwd_blocks(m.rows, C);
-  GLF_TRY(bn_res_ln_bwd(dZ, dz_dtype, s.U, X, s.bn_a, s.bn_b, s.bn_mean, s.bn_rstd, w->ln_w, s.ln_mu, s.ln_r, wb.dV,
-                        wb.part_ln, m.rows, C, stream));
+  GLF_TRY(bn_res_ln_bwd(dZ, dz_dtype, s.U, X, GLF_DTYPE_BF16, s.bn_a, s.bn_b, s.bn_mean, s.bn_rstd, w->ln_w, s.ln_mu,
+                        s.ln_r, wb.dV, wb.part_ln, m.rows, C, stream));
   GLF_TRY(bn_bwd_finalize(wb.part_ln, nb, C, static_cast<double>(m.rows), d, w, s.bn_mean, s.bn_rstd, g_, wb.k1, wb.k2,
                           wb.k3, stream));
   const bf16* dU = wb.dV;
   if (d->bn_layer) {
-    GLF_TRY(bn_bwd_apply(wb.dV, s.U, wb.k1, wb.k2, wb.k3, wb.dU, m.rows, C, stream));
+    GLF_TRY(bn_bwd_apply(wb.dV, s.U, GLF_DTYPE_BF16, wb.k1, wb.k2, wb.k3, wb.dU, m.rows, C, stream));
     dU = wb.dU;
   }
   int np = 0;
@@ -492,7 +498,7 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
   return 0;
 }
 
-GLF_API int glf_gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype,
+GLF_API int glf_gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, int x_dtype,
                         const void* const* f4, const float* const* cls, const float* const* ctr, void* xg, void* xl,
                         float* gate, glf_stream_t stream) {
   GLF_TRY(check_device_sm100());
@@ -500,11 +506,11 @@ GLF_API int glf_gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, flo
   if (f4 == nullptr || cls == nullptr || ctr == nullptr) return set_error(GLF_ERR_INVALID, "gate_concat: NULL pointer table");
   GLF_TRY(check_ptr(xg, "xg"));
   GLF_TRY(check_ptr(xl, "xl"));
-  return gate_concat_fwd(B, C, V, h, w, ncls, weight, io_dtype, f4, cls, ctr, xg, xl, gate,
+  return gate_concat_fwd(B, C, V, h, w, ncls, weight, io_dtype, x_dtype, f4, cls, ctr, xg, xl, gate,
                          reinterpret_cast<cudaStream_t>(stream));
 }
 
-GLF_API int glf_gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype,
+GLF_API int glf_gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, int x_dtype,
                         const void* const* f4, const float* const* cls, const float* const* ctr, const float* gate,
                         const void* dxg, const void* dxl, void* const* df4, float* const* dcls, float* const* dctr,
                         glf_stream_t stream) {
@@ -514,7 +520,7 @@ GLF_API int glf_gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, flo
     return set_error(GLF_ERR_INVALID, "gate_concat: NULL pointer table");
   GLF_TRY(check_ptr(dxg, "dxg"));
   GLF_TRY(check_ptr(dxl, "dxl"));
-  return gate_concat_bwd(B, C, V, h, w, ncls, weight, io_dtype, f4, cls, ctr, gate, dxg, dxl, df4, dcls, dctr,
+  return gate_concat_bwd(B, C, V, h, w, ncls, weight, io_dtype, x_dtype, f4, cls, ctr, gate, dxg, dxl, df4, dcls, dctr,
                          reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -546,8 +552,8 @@ GLF_API int glf_bn_res_ln_fwd(int64_t rows, int C, const void* U, const void* X,
   GLF_TRY(check_ptr(X, "X"));
   GLF_TRY(check_ptr(Z, "Z"));
   if (rows <= 0) return set_error(GLF_ERR_INVALID, "empty input");
-  return bn_res_ln_fwd(reinterpret_cast<const bf16*>(U), reinterpret_cast<const bf16*>(X), bn_a, bn_b, ln_w, ln_b, Z,
-                       z_dtype, mu, r, rows, C, eps, accumulate, reinterpret_cast<cudaStream_t>(stream));
+  return bn_res_ln_fwd(U, X, GLF_DTYPE_BF16, bn_a, bn_b, ln_w, ln_b, Z, z_dtype, mu, r, rows, C, eps, accumulate,
+                       reinterpret_cast<cudaStream_t>(stream));
 }
 
 GLF_API int glf_bn_res_ln_bwd(int64_t rows, int C, const void* dZ, int dz_dtype, const void* U, const void* X,
@@ -560,8 +566,7 @@ GLF_API int glf_bn_res_ln_bwd(int64_t rows, int C, const void* dZ, int dz_dtype,
   GLF_TRY(check_ptr(dV, "dV"));
   if (rows <= 0) return set_error(GLF_ERR_INVALID, "empty input");
   if (nblocks_out) *nblocks_out = bn_res_ln_bwd_blocks(rows, C);
-  return bn_res_ln_bwd(dZ, dz_dtype, reinterpret_cast<const bf16*>(U), reinterpret_cast<const bf16*>(X), bn_a, bn_b,
-                       bn_mean, bn_rstd, ln_w, mu, r, reinterpret_cast<bf16*>(dV), part, rows, C,
+  return bn_res_ln_bwd(dZ, dz_dtype, U, X, GLF_DTYPE_BF16, bn_a, bn_b, bn_mean, bn_rstd, ln_w, mu, r, dV, part, rows, C,
                        reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -215,9 +215,9 @@ __device__ __forceinline__ void lds8v(const float* p, float (&f)[8]) {
 }
 
 // Z = LayerNorm_C(a*U + b + X) * lw + lb     (ours.py:908-915 after the W_z GEMM).  U may be nullptr (V = 0).
-template <typename TO>
+template <typename TO, typename TA>
 __global__ void __launch_bounds__(ROW_THREADS)
-    bn_res_ln_fwd_kernel(const bf16* __restrict__ U, const bf16* __restrict__ X, const float* __restrict__ bn_a,
+    bn_res_ln_fwd_kernel(const TA* __restrict__ U, const TA* __restrict__ X, const float* __restrict__ bn_a,
                          const float* __restrict__ bn_b, const float* __restrict__ lw, const float* __restrict__ lb,
                          TO* __restrict__ Z, float* __restrict__ mu_o, float* __restrict__ r_o, long long rows, int C,
                          int S, float eps, int accumulate) {
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(ROW_THREADS)
   const float invC = 1.f / static_cast<float>(C);
   const long long step = static_cast<long long>(gridDim.x) * RPB;
   long long base = static_cast<long long>(blockIdx.x) * RPB;
-  Raw8<bf16> xr = {}, ur = {};
+  Raw8<TA> xr = {}, ur = {};
   if (cact && base + rslot < rows) {
     xr = ldraw(X + (base + rslot) * C + c0);
     if (U != nullptr) ur = ldraw(U + (base + rslot) * C + c0);
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(ROW_THREADS)
   for (; base < rows; base += step) {
     const long long row = base + rslot;
     const bool act = cact && row < rows;
-    const Raw8<bf16> xc = xr, uc = ur;
+    const Raw8<TA> xc = xr, uc = ur;
     if (cact && row + step < rows) {
       xr = ldraw(X + (row + step) * C + c0);
       if (U != nullptr) ur = ldraw(U + (row + step) * C + c0);
@@ -298,13 +298,13 @@ __global__ void __launch_bounds__(ROW_THREADS)
 // ------------------------------------------------------------------------------------------------ BN + residual + LN bwd
 // From dZ: dV = dZp (gradient of the pre-LayerNorm sum, also the residual part of dX), and per-CTA partials of the
 // four per-channel reductions: d ln_w = sum dZ*xhat, d ln_b = sum dZ, d gamma = sum dV*uhat, d beta = sum dV.
-template <typename TI>
+template <typename TI, typename TA>
 __global__ void __launch_bounds__(ROW_THREADS, 2)
-    bn_res_ln_bwd_kernel(const TI* __restrict__ dZ, const bf16* __restrict__ U, const bf16* __restrict__ X,
+    bn_res_ln_bwd_kernel(const TI* __restrict__ dZ, const TA* __restrict__ U, const TA* __restrict__ X,
                          const float* __restrict__ bn_a, const float* __restrict__ bn_b,
                          const float* __restrict__ bn_mean, const float* __restrict__ bn_rstd,
                          const float* __restrict__ lw, const float* __restrict__ mu_i, const float* __restrict__ r_i,
-                         bf16* __restrict__ dV, float* __restrict__ part, long long rows, int C, int S) {
+                         TA* __restrict__ dV, float* __restrict__ part, long long rows, int C, int S) {
   __shared__ float red[2 * ROW_WARPS * 2];
   // per-channel parameter vectors live in shared memory during the row loop (re-read with volatile 128-bit loads so
   // that they do not occupy 40 registers); the same storage holds the accumulator exchange afterwards
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 2)
   const float invC = 1.f / static_cast<float>(C);
   const long long step = static_cast<long long>(gridDim.x) * RPB;
   long long base = static_cast<long long>(blockIdx.x) * RPB;
-  Raw8<bf16> xr = {}, ur = {};
+  Raw8<TA> xr = {}, ur = {};
   Raw8<TI> zr = {};
   float mu_n = 0.f, r_n = 0.f;
   if (cact && base + rslot < rows) {
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 2)
   for (; base < rows; base += step) {
     const long long row = base + rslot;
     const bool act = cact && row < rows;
-    const Raw8<bf16> xc = xr, uc = ur;
+    const Raw8<TA> xc = xr, uc = ur;
     const Raw8<TI> zc = zr;
     const float mu = mu_n, r = r_n;
     if (cact && row + step < rows) {
@@ -470,10 +470,11 @@ __global__ void __launch_bounds__(32 * RED_Y)
   }
 }
 
-// dU = k1*dV + k2*U + k3 (per channel), bf16 in/out, 8 channels per thread
-__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dV, const bf16* __restrict__ U,
+// dU = k1*dV + k2*U + k3 (per channel), 8 channels per thread
+template <typename TA>
+__global__ void bn_bwd_apply_kernel(const TA* __restrict__ dV, const TA* __restrict__ U,
                                     const float* __restrict__ k1, const float* __restrict__ k2,
-                                    const float* __restrict__ k3, bf16* __restrict__ dU, long long nvec, int C) {
+                                    const float* __restrict__ k3, TA* __restrict__ dU, long long nvec, int C) {
   const int cv = C / 8;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -508,6 +509,76 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict_
     float f[8];
     load8(in + i * 8, f);
     store8(out + i * 8, f);
+  }
+}
+
+// fp32 -> three bf16 limb planes (hi, mid, lo): x = l0 + l1 + l2 to 24 mantissa bits.  out: [3][n]
+__global__ void split3_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long nvec, long long plane) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float f[8], h[8], m[8], l[8];
+    load8(in + i * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      h[j] = __bfloat162float(__float2bfloat16(f[j]));
+      const float r1 = f[j] - h[j];
+      m[j] = __bfloat162float(__float2bfloat16(r1));
+      l[j] = r1 - m[j];
+    }
+    store8(out + i * 8, h);
+    store8(out + plane + i * 8, m);
+    store8(out + 2 * plane + i * 8, l);
+  }
+}
+
+// per-CTA partial column sums / sums of squares of an fp32 [rows, C] matrix: part [gridDim.x][2][C]
+__global__ void __launch_bounds__(256) colstats_f32_kernel(const float* __restrict__ A, float* __restrict__ part,
+                                                           long long rows, int C) {
+  // thread (tx = column group of 4, ty = row lane); 64 column groups x 4 row lanes per pass over 256 columns
+  __shared__ float sm[2][4][256];
+  for (int cbase = 0; cbase < C; cbase += 256) {
+    const int c = cbase + (threadIdx.x & 63) * 4;
+    const int ty = threadIdx.x >> 6;
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < C) {
+      for (long long r = static_cast<long long>(blockIdx.x) * 4 + ty; r < rows; r += static_cast<long long>(gridDim.x) * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(A + r * C + c);
+        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+        s2[0] = fmaf(v.x, v.x, s2[0]); s2[1] = fmaf(v.y, v.y, s2[1]);
+        s2[2] = fmaf(v.z, v.z, s2[2]); s2[3] = fmaf(v.w, v.w, s2[3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sm[0][ty][(threadIdx.x & 63) * 4 + j] = s[j];
+      sm[1][ty][(threadIdx.x & 63) * 4 + j] = s2[j];
+    }
+    __syncthreads();
+    const int cc = cbase + threadIdx.x;
+    if (cc < C) {
+      const float a = sm[0][0][threadIdx.x] + sm[0][1][threadIdx.x] + sm[0][2][threadIdx.x] + sm[0][3][threadIdx.x];
+      const float a2 = sm[1][0][threadIdx.x] + sm[1][1][threadIdx.x] + sm[1][2][threadIdx.x] + sm[1][3][threadIdx.x];
+      part[(static_cast<long long>(blockIdx.x) * 2) * C + cc] = a;
+      part[(static_cast<long long>(blockIdx.x) * 2 + 1) * C + cc] = a2;
+    }
+    __syncthreads();
+  }
+}
+
+// fp32 concatenated weights for the F32X3 path: Wcat [3Ci, C], WcatT [C, 3Ci], bcat [3Ci]
+__global__ void prep_weights_f32_kernel(const float* __restrict__ tw, const float* __restrict__ pw,
+                                        const float* __restrict__ gw, const float* __restrict__ tb,
+                                        const float* __restrict__ pb, const float* __restrict__ gb,
+                                        float* __restrict__ wcat, float* __restrict__ wcatT, float* __restrict__ bcat,
+                                        int C, int Ci) {
+  const int total = 3 * Ci * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / C, c = i % C;
+    const int which = r / Ci, rr = r % Ci;
+    const float v = (which == 0 ? tw : (which == 1 ? pw : gw))[rr * C + c];
+    wcat[i] = v;
+    wcatT[static_cast<long long>(c) * 3 * Ci + r] = v;
+    if (i < 3 * Ci) bcat[i] = ((i / Ci) == 0 ? tb : ((i / Ci) == 1 ? pb : gb))[i % Ci];
   }
 }
 
@@ -557,17 +628,26 @@ int bn_finalize(const float* part, int np, int C, double count, const glf_desc* 
   return check_cuda(cudaGetLastError(), "bn_finalize launch");
 }
 
-int bn_res_ln_fwd(const bf16* U, const bf16* X, const float* a, const float* b, const float* lw, const float* lb,
-                  void* Z, int z_dtype, float* mu, float* r, long long rows, int C, float eps, int accumulate,
-                  cudaStream_t stream) {
+int bn_res_ln_fwd(const void* U_, const void* X_, int act_dtype, const float* a, const float* b, const float* lw,
+                  const float* lb, void* Z, int z_dtype, float* mu, float* r, long long rows, int C, float eps,
+                  int accumulate, cudaStream_t stream) {
   if (C % 8 != 0 || C > 2048) return set_error(GLF_ERR_INVALID, "LayerNorm kernel needs C %% 8 == 0 and C <= 2048");
   int S = (C + 255) / 256;
   while (ROW_WARPS % S != 0) ++S;
   const int grid = row_grid(rows, S);
-  if (z_dtype == GLF_DTYPE_BF16)
-    bn_res_ln_fwd_kernel<bf16><<<grid, ROW_THREADS, 0, stream>>>(U, X, a, b, lw, lb, (bf16*)Z, mu, r, rows, C, S, eps, accumulate);
-  else
-    bn_res_ln_fwd_kernel<float><<<grid, ROW_THREADS, 0, stream>>>(U, X, a, b, lw, lb, (float*)Z, mu, r, rows, C, S, eps, accumulate);
+  if (act_dtype == GLF_DTYPE_BF16) {
+    const bf16* U = (const bf16*)U_; const bf16* X = (const bf16*)X_;
+    if (z_dtype == GLF_DTYPE_BF16)
+      bn_res_ln_fwd_kernel<bf16, bf16><<<grid, ROW_THREADS, 0, stream>>>(U, X, a, b, lw, lb, (bf16*)Z, mu, r, rows, C, S, eps, accumulate);
+    else
+      bn_res_ln_fwd_kernel<float, bf16><<<grid, ROW_THREADS, 0, stream>>>(U, X, a, b, lw, lb, (float*)Z, mu, r, rows, C, S, eps, accumulate);
+  } else {
+    const float* U = (const float*)U_; const float* X = (const float*)X_;
+    if (z_dtype == GLF_DTYPE_BF16)
+      bn_res_ln_fwd_kernel<bf16, float><<<grid, ROW_THREADS, 0, stream>>>(U, X, a, b, lw, lb, (bf16*)Z, mu, r, rows, C, S, eps, accumulate);
+    else
+      bn_res_ln_fwd_kernel<float, float><<<grid, ROW_THREADS, 0, stream>>>(U, X, a, b, lw, lb, (float*)Z, mu, r, rows, C, S, eps, accumulate);
+  }
   return check_cuda(cudaGetLastError(), "bn_res_ln_fwd launch");
 }
 
@@ -578,17 +658,26 @@ int bn_res_ln_bwd_blocks(long long rows, int C) {
   return g < 148 * 2 ? g : 148 * 2;
 }
 
-int bn_res_ln_bwd(const void* dZ, int dz_dtype, const bf16* U, const bf16* X, const float* a, const float* b,
-                  const float* mean, const float* rstd, const float* lw, const float* mu, const float* r, bf16* dV,
-                  float* part, long long rows, int C, cudaStream_t stream) {
+int bn_res_ln_bwd(const void* dZ, int dz_dtype, const void* U_, const void* X_, int act_dtype, const float* a,
+                  const float* b, const float* mean, const float* rstd, const float* lw, const float* mu,
+                  const float* r, void* dV_, float* part, long long rows, int C, cudaStream_t stream) {
   if (C % 8 != 0 || C > 2048) return set_error(GLF_ERR_INVALID, "LayerNorm kernel needs C %% 8 == 0 and C <= 2048");
   int S = (C + 255) / 256;
   while (ROW_WARPS % S != 0) ++S;
   const int grid = bn_res_ln_bwd_blocks(rows, C);
-  if (dz_dtype == GLF_DTYPE_BF16)
-    bn_res_ln_bwd_kernel<bf16><<<grid, ROW_THREADS, 0, stream>>>((const bf16*)dZ, U, X, a, b, mean, rstd, lw, mu, r, dV, part, rows, C, S);
-  else
-    bn_res_ln_bwd_kernel<float><<<grid, ROW_THREADS, 0, stream>>>((const float*)dZ, U, X, a, b, mean, rstd, lw, mu, r, dV, part, rows, C, S);
+  if (act_dtype == GLF_DTYPE_BF16) {
+    const bf16* U = (const bf16*)U_; const bf16* X = (const bf16*)X_; bf16* dV = (bf16*)dV_;
+    if (dz_dtype == GLF_DTYPE_BF16)
+      bn_res_ln_bwd_kernel<bf16, bf16><<<grid, ROW_THREADS, 0, stream>>>((const bf16*)dZ, U, X, a, b, mean, rstd, lw, mu, r, dV, part, rows, C, S);
+    else
+      bn_res_ln_bwd_kernel<float, bf16><<<grid, ROW_THREADS, 0, stream>>>((const float*)dZ, U, X, a, b, mean, rstd, lw, mu, r, dV, part, rows, C, S);
+  } else {
+    const float* U = (const float*)U_; const float* X = (const float*)X_; float* dV = (float*)dV_;
+    if (dz_dtype == GLF_DTYPE_BF16)
+      bn_res_ln_bwd_kernel<bf16, float><<<grid, ROW_THREADS, 0, stream>>>((const bf16*)dZ, U, X, a, b, mean, rstd, lw, mu, r, dV, part, rows, C, S);
+    else
+      bn_res_ln_bwd_kernel<float, float><<<grid, ROW_THREADS, 0, stream>>>((const float*)dZ, U, X, a, b, mean, rstd, lw, mu, r, dV, part, rows, C, S);
+  }
   return check_cuda(cudaGetLastError(), "bn_res_ln_bwd launch");
 }
 
@@ -601,18 +690,49 @@ int bn_bwd_finalize(const float* part, int np, int C, double count, const glf_de
   return check_cuda(cudaGetLastError(), "bn_bwd_finalize launch");
 }
 
-int bn_bwd_apply(const bf16* dV, const bf16* U, const float* k1, const float* k2, const float* k3, bf16* dU,
-                 long long rows, int C, cudaStream_t stream) {
+int bn_bwd_apply(const void* dV, const void* U, int act_dtype, const float* k1, const float* k2, const float* k3,
+                 void* dU, long long rows, int C, cudaStream_t stream) {
   const long long nvec = rows * C / 8;
   long long blocks = (nvec + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  bn_bwd_apply_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(dV, U, k1, k2, k3, dU, nvec, C);
+  if (act_dtype == GLF_DTYPE_BF16)
+    bn_bwd_apply_kernel<bf16><<<static_cast<int>(blocks), 256, 0, stream>>>((const bf16*)dV, (const bf16*)U, k1, k2, k3, (bf16*)dU, nvec, C);
+  else
+    bn_bwd_apply_kernel<float><<<static_cast<int>(blocks), 256, 0, stream>>>((const float*)dV, (const float*)U, k1, k2, k3, (float*)dU, nvec, C);
   return check_cuda(cudaGetLastError(), "bn_bwd_apply launch");
 }
 
 int reduce_partials(const float* part, int np, long long stride, int n, float alpha, float* out, cudaStream_t stream) {
   reduce_partials_kernel<<<(n + 31) / 32, dim3(32, RED_Y), 0, stream>>>(part, np, stride, n, alpha, out);
   return check_cuda(cudaGetLastError(), "reduce_partials launch");
+}
+
+int split3(const float* in, bf16* out, long long n, cudaStream_t stream) {
+  if (n % 8 != 0) return set_error(GLF_ERR_INVALID, "split3: n %% 8 != 0");
+  const long long nvec = n / 8;
+  long long blocks = (nvec + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  split3_kernel<<<static_cast<int>(blocks < 1 ? 1 : blocks), 256, 0, stream>>>(in, out, nvec, n);
+  return check_cuda(cudaGetLastError(), "split3 launch");
+}
+
+int colstats_f32_blocks(long long rows) {
+  long long b = (rows + 3) / 4;
+  return static_cast<int>(b < 1 ? 1 : (b > 148 * 4 ? 148 * 4 : b));
+}
+int colstats_f32(const float* A, float* part, long long rows, int C, cudaStream_t stream) {
+  if (C % 4 != 0) return set_error(GLF_ERR_INVALID, "colstats_f32: C %% 4 != 0");
+  colstats_f32_kernel<<<colstats_f32_blocks(rows), 256, 0, stream>>>(A, part, rows, C);
+  return check_cuda(cudaGetLastError(), "colstats_f32 launch");
+}
+
+int prep_weights_f32(const glf_weights* w, int C, int Ci, float* wcat, float* wcatT, float* bcat, cudaStream_t stream) {
+  const int total = 3 * Ci * C;
+  int blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  prep_weights_f32_kernel<<<blocks, 256, 0, stream>>>(w->theta_w, w->phi_w, w->g_w, w->theta_b, w->phi_b, w->g_b, wcat,
+                                                      wcatT, bcat, C, Ci);
+  return check_cuda(cudaGetLastError(), "prep_weights_f32 launch");
 }
 
 int cast_bf16(const float* in, bf16* out, long long n, cudaStream_t stream) {

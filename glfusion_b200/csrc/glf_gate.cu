@@ -37,11 +37,36 @@ __device__ __forceinline__ void ld2(const float* p, float& a, float& b) {
 }
 __device__ __forceinline__ void st2(bf16* p, float a, float b) { *reinterpret_cast<uint32_t*>(p) = pack_bf16(a, b); }
 __device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+// eight consecutive channels of one token (token-major side)
+__device__ __forceinline__ void st8(bf16* p, const float (&f)[8]) {
+  *reinterpret_cast<uint4*>(p) =
+      make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+__device__ __forceinline__ void st8(float* p, const float (&f)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+__device__ __forceinline__ void ld8(const bf16* p, float (&f)[8]) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = unpack_bf16(u[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void ld8(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
 
 // grid: (ceil(hw/64), C/64 rounded up, B*V) ; block 256
-template <typename TIO, int VEC>
+template <typename TIO, int VEC, typename TX>
 __global__ void __launch_bounds__(256)
-    gate_concat_fwd_kernel(const ViewPtrs vp, bf16* __restrict__ xg, bf16* __restrict__ xl, float* __restrict__ gate,
+    gate_concat_fwd_kernel(const ViewPtrs vp, TX* __restrict__ xg, TX* __restrict__ xl, float* __restrict__ gate,
                            int C, int V, int hw, int ncls, float weight) {
   __shared__ float tile[64][65];
   __shared__ float a_sm[64];
@@ -93,19 +118,17 @@ __global__ void __launch_bounds__(256)
         g[i] = f[i] * a;
       }
       const long long o = (static_cast<long long>(b) * V * hw + static_cast<long long>(v) * hw + p) * C + c;
-      *reinterpret_cast<uint4*>(xg + o) =
-          make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-      *reinterpret_cast<uint4*>(xl + o) =
-          make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]), pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7]));
+      st8(xg + o, f);
+      st8(xl + o, g);
     }
   }
 }
 
 // grid: (ceil(hw/64), B*V) ; block 256 ; loops over channel tiles so the gate gradient needs no atomics
-template <typename TIO, int VEC>
+template <typename TIO, int VEC, typename TX>
 __global__ void __launch_bounds__(256)
-    gate_concat_bwd_kernel(const ViewPtrs vp, const float* __restrict__ gate, const bf16* __restrict__ dxg,
-                           const bf16* __restrict__ dxl, int C, int V, int hw, int ncls, float weight) {
+    gate_concat_bwd_kernel(const ViewPtrs vp, const float* __restrict__ gate, const TX* __restrict__ dxg,
+                           const TX* __restrict__ dxl, int C, int V, int hw, int ncls, float weight) {
   __shared__ float tg[64][65];
   __shared__ float tl[64][65];
   __shared__ float a_sm[64];
@@ -128,21 +151,18 @@ __global__ void __launch_bounds__(256)
     const int chunk = threadIdx.x & 7, pr = threadIdx.x >> 3;
     for (int pp = pr; pp < 64; pp += 32) {
       const int p = p0 + pp, c = c0 + chunk * 8;
-      uint4 g4 = make_uint4(0, 0, 0, 0), l4 = make_uint4(0, 0, 0, 0);
+      float g8[8], l8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g8[i] = l8[i] = 0.f;
       if (p < hw && c < C) {
         const long long o = (static_cast<long long>(b) * V * hw + static_cast<long long>(v) * hw + p) * C + c;
-        g4 = *reinterpret_cast<const uint4*>(dxg + o);
-        l4 = *reinterpret_cast<const uint4*>(dxl + o);
+        ld8(dxg + o, g8);
+        ld8(dxl + o, l8);
       }
-      const uint32_t* gu = reinterpret_cast<const uint32_t*>(&g4);
-      const uint32_t* lu = reinterpret_cast<const uint32_t*>(&l4);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 a2 = unpack_bf16(gu[i]), b2 = unpack_bf16(lu[i]);
-        tg[pp][chunk * 8 + 2 * i] = a2.x;
-        tg[pp][chunk * 8 + 2 * i + 1] = a2.y;
-        tl[pp][chunk * 8 + 2 * i] = b2.x;
-        tl[pp][chunk * 8 + 2 * i + 1] = b2.y;
+      for (int i = 0; i < 8; ++i) {
+        tg[pp][chunk * 8 + i] = g8[i];
+        tl[pp][chunk * 8 + i] = l8[i];
       }
     }
     __syncthreads();
@@ -206,11 +226,37 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+
+template <typename TX>
+int launch_gate_fwd(dim3 grid, bool vec2, int io_dtype, const ViewPtrs& vp, void* xg, void* xl, float* gate, int C, int V,
+                    int hw, int ncls, float weight, cudaStream_t stream) {
+  if (io_dtype == GLF_DTYPE_BF16) {
+    if (vec2) gate_concat_fwd_kernel<bf16, 2, TX><<<grid, 256, 0, stream>>>(vp, (TX*)xg, (TX*)xl, gate, C, V, hw, ncls, weight);
+    else gate_concat_fwd_kernel<bf16, 1, TX><<<grid, 256, 0, stream>>>(vp, (TX*)xg, (TX*)xl, gate, C, V, hw, ncls, weight);
+  } else {
+    if (vec2) gate_concat_fwd_kernel<float, 2, TX><<<grid, 256, 0, stream>>>(vp, (TX*)xg, (TX*)xl, gate, C, V, hw, ncls, weight);
+    else gate_concat_fwd_kernel<float, 1, TX><<<grid, 256, 0, stream>>>(vp, (TX*)xg, (TX*)xl, gate, C, V, hw, ncls, weight);
+  }
+  return check_cuda(cudaGetLastError(), "gate_concat_fwd launch");
+}
+template <typename TX>
+int launch_gate_bwd(dim3 grid, bool vec2, int io_dtype, const ViewPtrs& vp, const float* gate, const void* dxg,
+                    const void* dxl, int C, int V, int hw, int ncls, float weight, cudaStream_t stream) {
+  if (io_dtype == GLF_DTYPE_BF16) {
+    if (vec2) gate_concat_bwd_kernel<bf16, 2, TX><<<grid, 256, 0, stream>>>(vp, gate, (const TX*)dxg, (const TX*)dxl, C, V, hw, ncls, weight);
+    else gate_concat_bwd_kernel<bf16, 1, TX><<<grid, 256, 0, stream>>>(vp, gate, (const TX*)dxg, (const TX*)dxl, C, V, hw, ncls, weight);
+  } else {
+    if (vec2) gate_concat_bwd_kernel<float, 2, TX><<<grid, 256, 0, stream>>>(vp, gate, (const TX*)dxg, (const TX*)dxl, C, V, hw, ncls, weight);
+    else gate_concat_bwd_kernel<float, 1, TX><<<grid, 256, 0, stream>>>(vp, gate, (const TX*)dxg, (const TX*)dxl, C, V, hw, ncls, weight);
+  }
+  return check_cuda(cudaGetLastError(), "gate_concat_bwd launch");
+}
+
 }  // namespace
 
-int gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, const void* const* f4,
-                    const float* const* cls, const float* const* ctr, void* xg, void* xl, float* gate,
-                    cudaStream_t stream) {
+int gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, int x_dtype,
+                    const void* const* f4, const float* const* cls, const float* const* ctr, void* xg, void* xl,
+                    float* gate, cudaStream_t stream) {
   if (V < 1 || V > MAXV) return set_error(GLF_ERR_INVALID, "gate_concat: 1 <= V <= %d", MAXV);
   if (C % 8 != 0) return set_error(GLF_ERR_INVALID, "gate_concat: C %% 8 != 0");
   ViewPtrs vp{};
@@ -219,19 +265,14 @@ int gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, i
   dim3 grid((hw + 63) / 64, (C + 63) / 64, B * V);
   if (grid.y > 65535 || grid.z > 65535) return set_error(GLF_ERR_INVALID, "gate_concat: grid too large");
   const bool vec2 = (hw % 2 == 0);
-  if (io_dtype == GLF_DTYPE_BF16) {
-    if (vec2) gate_concat_fwd_kernel<bf16, 2><<<grid, 256, 0, stream>>>(vp, (bf16*)xg, (bf16*)xl, gate, C, V, hw, ncls, weight);
-    else gate_concat_fwd_kernel<bf16, 1><<<grid, 256, 0, stream>>>(vp, (bf16*)xg, (bf16*)xl, gate, C, V, hw, ncls, weight);
-  } else {
-    if (vec2) gate_concat_fwd_kernel<float, 2><<<grid, 256, 0, stream>>>(vp, (bf16*)xg, (bf16*)xl, gate, C, V, hw, ncls, weight);
-    else gate_concat_fwd_kernel<float, 1><<<grid, 256, 0, stream>>>(vp, (bf16*)xg, (bf16*)xl, gate, C, V, hw, ncls, weight);
-  }
-  return check_cuda(cudaGetLastError(), "gate_concat_fwd launch");
+  if (x_dtype == GLF_DTYPE_BF16) return launch_gate_fwd<bf16>(grid, vec2, io_dtype, vp, xg, xl, gate, C, V, hw, ncls, weight, stream);
+  return launch_gate_fwd<float>(grid, vec2, io_dtype, vp, xg, xl, gate, C, V, hw, ncls, weight, stream);
 }
 
-int gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, const void* const* f4,
-                    const float* const* cls, const float* const* ctr, const float* gate, const void* dxg,
-                    const void* dxl, void* const* df4, float* const* dcls, float* const* dctr, cudaStream_t stream) {
+int gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, int x_dtype,
+                    const void* const* f4, const float* const* cls, const float* const* ctr, const float* gate,
+                    const void* dxg, const void* dxl, void* const* df4, float* const* dcls, float* const* dctr,
+                    cudaStream_t stream) {
   if (V < 1 || V > MAXV) return set_error(GLF_ERR_INVALID, "gate_concat: 1 <= V <= %d", MAXV);
   if (C % 8 != 0) return set_error(GLF_ERR_INVALID, "gate_concat: C %% 8 != 0");
   ViewPtrs vp{};
@@ -243,14 +284,8 @@ int gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, i
   dim3 grid((hw + 63) / 64, B * V);
   if (grid.y > 65535) return set_error(GLF_ERR_INVALID, "gate_concat: grid too large");
   const bool vec2 = (hw % 2 == 0);
-  if (io_dtype == GLF_DTYPE_BF16) {
-    if (vec2) gate_concat_bwd_kernel<bf16, 2><<<grid, 256, 0, stream>>>(vp, gate, (const bf16*)dxg, (const bf16*)dxl, C, V, hw, ncls, weight);
-    else gate_concat_bwd_kernel<bf16, 1><<<grid, 256, 0, stream>>>(vp, gate, (const bf16*)dxg, (const bf16*)dxl, C, V, hw, ncls, weight);
-  } else {
-    if (vec2) gate_concat_bwd_kernel<float, 2><<<grid, 256, 0, stream>>>(vp, gate, (const bf16*)dxg, (const bf16*)dxl, C, V, hw, ncls, weight);
-    else gate_concat_bwd_kernel<float, 1><<<grid, 256, 0, stream>>>(vp, gate, (const bf16*)dxg, (const bf16*)dxl, C, V, hw, ncls, weight);
-  }
-  return check_cuda(cudaGetLastError(), "gate_concat_bwd launch");
+  if (x_dtype == GLF_DTYPE_BF16) return launch_gate_bwd<bf16>(grid, vec2, io_dtype, vp, gate, dxg, dxl, C, V, hw, ncls, weight, stream);
+  return launch_gate_bwd<float>(grid, vec2, io_dtype, vp, gate, dxg, dxl, C, V, hw, ncls, weight, stream);
 }
 
 }  // namespace glf

@@ -52,28 +52,34 @@ int prep_weights(const glf_weights* w, int C, int Ci, bf16* wcat, bf16* wcatT, f
                  cudaStream_t stream);
 int bn_finalize(const float* part, int np, int C, double count, const glf_desc* d, const glf_weights* w, float* mean,
                 float* rstd, float* a, float* b, cudaStream_t stream);
-int bn_res_ln_fwd(const bf16* U, const bf16* X, const float* a, const float* b, const float* lw, const float* lb,
-                  void* Z, int z_dtype, float* mu, float* r, long long rows, int C, float eps, int accumulate,
-                  cudaStream_t stream);
+// act_dtype: storage type of the activations U, X (and dV / dU): bf16 in the default path, fp32 under F32X3
+int bn_res_ln_fwd(const void* U, const void* X, int act_dtype, const float* a, const float* b, const float* lw,
+                  const float* lb, void* Z, int z_dtype, float* mu, float* r, long long rows, int C, float eps,
+                  int accumulate, cudaStream_t stream);
 int bn_res_ln_bwd_blocks(long long rows, int C);
-int bn_res_ln_bwd(const void* dZ, int dz_dtype, const bf16* U, const bf16* X, const float* a, const float* b,
-                  const float* mean, const float* rstd, const float* lw, const float* mu, const float* r, bf16* dV,
-                  float* part, long long rows, int C, cudaStream_t stream);
+int bn_res_ln_bwd(const void* dZ, int dz_dtype, const void* U, const void* X, int act_dtype, const float* a,
+                  const float* b, const float* mean, const float* rstd, const float* lw, const float* mu,
+                  const float* r, void* dV, float* part, long long rows, int C, cudaStream_t stream);
 int bn_bwd_finalize(const float* part, int np, int C, double count, const glf_desc* d, const glf_weights* w,
                     const float* mean, const float* rstd, const glf_grads* g, float* k1, float* k2, float* k3,
                     cudaStream_t stream);
-int bn_bwd_apply(const bf16* dV, const bf16* U, const float* k1, const float* k2, const float* k3, bf16* dU,
-                 long long rows, int C, cudaStream_t stream);
+int bn_bwd_apply(const void* dV, const void* U, int act_dtype, const float* k1, const float* k2, const float* k3,
+                 void* dU, long long rows, int C, cudaStream_t stream);
+int split3(const float* in, bf16* out, long long n, cudaStream_t stream);   // fp32 [n] -> bf16 limbs [3][n]
+int colstats_f32_blocks(long long rows);
+int colstats_f32(const float* A, float* part, long long rows, int C, cudaStream_t stream);
+int prep_weights_f32(const glf_weights* w, int C, int Ci, float* wcat, float* wcatT, float* bcat, cudaStream_t stream);
 int reduce_partials(const float* part, int np, long long stride, int n, float alpha, float* out, cudaStream_t stream);
 int cast_bf16(const float* in, bf16* out, long long n, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------ gate + concat
-int gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, const void* const* f4,
-                    const float* const* cls, const float* const* ctr, void* xg, void* xl, float* gate,
+int gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, int x_dtype,
+                    const void* const* f4, const float* const* cls, const float* const* ctr, void* xg, void* xl,
+                    float* gate, cudaStream_t stream);
+int gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, int x_dtype,
+                    const void* const* f4, const float* const* cls, const float* const* ctr, const float* gate,
+                    const void* dxg, const void* dxl, void* const* df4, float* const* dcls, float* const* dctr,
                     cudaStream_t stream);
-int gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, const void* const* f4,
-                    const float* const* cls, const float* const* ctr, const float* gate, const void* dxg,
-                    const void* dxl, void* const* df4, float* const* dcls, float* const* dctr, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------ softmax attention
 // mode='embedded' (ours.py:896-897,902): Y = softmax(Theta Phi^T) G, flash-style, per batch entry.
@@ -84,5 +90,12 @@ size_t attn_scratch_bytes(long long B, long long N, bool backward);
 int flash_fwd(const bf16* P, bf16* Y, float* lse, int B, int N, int Ci, void* scratch, cudaStream_t stream);
 int flash_bwd(const bf16* P, const bf16* Y, const bf16* dY, const float* lse, bf16* dP, float* delta, float* cs_t,
               float* cs_p, float* cs_g, int B, int N, int Ci, void* scratch, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------ F32X3 precision arm
+int tpavi_sizes_f32x3(const glf_desc* d, glf_sizes* out);
+int tpavi_fwd_f32x3(const glf_desc* d, const void* x, const glf_weights* w, void* z, void* saved, void* ws,
+                    cudaStream_t stream);
+int tpavi_bwd_f32x3(const glf_desc* d, const void* dz, const void* x, const glf_weights* w, const void* saved,
+                    void* dx, const glf_grads* g, void* ws, cudaStream_t stream);
 
 }  // namespace glf

@@ -23,7 +23,7 @@ from .tpavi import TPAVIModule, _io_dtype, _stream_ptr, tpavi_backward_raw, tpav
 
 
 def gate_concat_forward(f4: Sequence[torch.Tensor], cls: Sequence[torch.Tensor], ctr: Sequence[torch.Tensor],
-                        weight: float):
+                        weight: float, x_dtype=torch.bfloat16):
     lib = L.load()
     V = len(f4)
     B, C_, h, w = f4[0].shape
@@ -34,11 +34,12 @@ def gate_concat_forward(f4: Sequence[torch.Tensor], cls: Sequence[torch.Tensor],
     cls = [t.float().contiguous() for t in cls]
     ctr = [t.float().contiguous() for t in ctr]
     ncls = cls[0].shape[1]
-    xg = torch.empty((B, V, h, w, C_), dtype=torch.bfloat16, device=dev)
+    xg = torch.empty((B, V, h, w, C_), dtype=x_dtype, device=dev)
     xl = torch.empty_like(xg)
     gate = torch.empty((B, V, h, w), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        L.check(lib.glf_gate_concat_fwd(B, C_, V, h, w, ncls, float(weight), _io_dtype(f4[0]), L.ptr_table(f4),
+        L.check(lib.glf_gate_concat_fwd(B, C_, V, h, w, ncls, float(weight), _io_dtype(f4[0]), _io_dtype(xg),
+                                        L.ptr_table(f4),
                                         L.ptr_table(cls), L.ptr_table(ctr), L.ptr(xg), L.ptr(xl), L.ptr(gate),
                                         _stream_ptr()))
     return xg, xl, gate, f4, cls, ctr
@@ -53,7 +54,8 @@ def gate_concat_backward(f4, cls, ctr, gate, dxg, dxl, weight: float):
     dcls = [torch.empty_like(t) for t in cls]
     dctr = [torch.empty_like(t) for t in ctr]
     with torch.cuda.device(f4[0].device):
-        L.check(lib.glf_gate_concat_bwd(B, C_, V, h, w, ncls, float(weight), _io_dtype(f4[0]), L.ptr_table(f4),
+        L.check(lib.glf_gate_concat_bwd(B, C_, V, h, w, ncls, float(weight), _io_dtype(f4[0]), _io_dtype(dxg),
+                                        L.ptr_table(f4),
                                         L.ptr_table(cls), L.ptr_table(ctr), L.ptr(gate), L.ptr(dxg), L.ptr(dxl),
                                         L.ptr_table(df4), L.ptr_table(dcls), L.ptr_table(dctr), _stream_ptr()))
     return df4, dcls, dctr
@@ -65,17 +67,21 @@ class _FusionFunction(torch.autograd.Function):
         f4, cls, ctr = tensors[:V], tensors[V:2 * V], tensors[2 * V:3 * V]
         pg, pl = tensors[3 * V:3 * V + ng], tensors[3 * V + ng:]
         mg, ml = fusion.global_attn, fusion.local_attn
-        xg, xl, gate, f4c, clsc, ctrc = gate_concat_forward(f4, cls, ctr, fusion.center_aware_weight)
+        prec = mg._precision_id()
+        if ml._precision_id() != prec:
+            raise ValueError("global_attn and local_attn must use the same compute_precision")
+        xdt = torch.float32 if prec == L.PRECISION_F32X3 else torch.bfloat16
+        xg, xl, gate, f4c, clsc, ctrc = gate_concat_forward(f4, cls, ctr, fusion.center_aware_weight, xdt)
         B, V_, h, w, C_ = xg.shape
         need = any(ctx.needs_input_grad)
         tg, tl = mg._param_table(pg), ml._param_table(pl)
         shape = (B, V_, h, w, C_)
         zsum, stg, svg, _ = tpavi_forward_raw(xg, tg, mg._buffer_table(), mode=mg._mode_id, training=mg.training,
                                               bn_layer=mg._bn_layer, Ci=mg.inter_channels, keep_for_backward=need,
-                                              token_shape=shape)
+                                              token_shape=shape, precision=prec)
         _, stl, svl, _ = tpavi_forward_raw(xl, tl, ml._buffer_table(), mode=ml._mode_id, training=ml.training,
                                            bn_layer=ml._bn_layer, Ci=ml.inter_channels, keep_for_backward=need,
-                                           z_out=zsum, accumulate=True, token_shape=shape)
+                                           z_out=zsum, accumulate=True, token_shape=shape, precision=prec)
         ctx.fusion, ctx.V, ctx.ng = fusion, V, ng
         ctx.states = (stg, svg, stl, svl)
         ctx.io_dtype = f4[0].dtype
@@ -96,8 +102,8 @@ class _FusionFunction(torch.autograd.Function):
         if svg is None:
             raise L.GlfError("backward called on a forward that ran without grad")
         dz = dout.permute(0, 2, 3, 4, 1)
-        if dz.dtype != torch.bfloat16:
-            dz = dz.to(torch.bfloat16)
+        if dz.dtype != xg.dtype:
+            dz = dz.to(xg.dtype)
         dz = dz.contiguous()                        # token-major [B,V,h,w,C]; both blocks see the same dz (ours.py:1834)
         dxg, gg = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xg, stg, svg, mg._param_table(pg), mg._buffer_table())
         dxl, gl = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xl, stl, svl, ml._param_table(pl), ml._buffer_table())

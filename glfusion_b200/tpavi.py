@@ -22,6 +22,17 @@ from torch import nn
 
 from . import _lib as L
 
+DEFAULT_PRECISION = "bf16"
+
+
+def set_default_precision(name: str) -> None:
+    """Default `compute_precision` of modules constructed afterwards ('bf16' or 'fp32')."""
+    global DEFAULT_PRECISION
+    if name not in L.PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(L.PRECISIONS)}")
+    DEFAULT_PRECISION = name
+
+
 _PARAM_ORDER = ("theta_w", "theta_b", "phi_w", "phi_b", "g_w", "g_b", "wz_w", "wz_b", "bn_w", "bn_b", "ln_w", "ln_b")
 
 
@@ -50,14 +61,14 @@ class TPAVIState:
     """Everything one forward/backward pair shares: descriptor, weights table, saved blob."""
 
     def __init__(self, B, C_, T, H, W, Ci, mode, io_dtype, x_layout, training, bn_layer, accumulate=False,
-                 eps_bn=1e-5, eps_ln=1e-5, momentum=0.1):
+                 eps_bn=1e-5, eps_ln=1e-5, momentum=0.1, precision=L.PRECISION_BF16):
         d = L.GlfDesc()
         d.B, d.T, d.H, d.W, d.C, d.Ci = B, T, H, W, C_, Ci
         d.mode = mode
         d.io_dtype = io_dtype
         d.x_layout = x_layout
         d.dz_layout = L.LAYOUT_TOKEN
-        d.precision = L.PRECISION_BF16
+        d.precision = precision
         d.training = int(training)
         d.bn_layer = int(bn_layer)
         d.accumulate = int(accumulate)
@@ -81,7 +92,7 @@ def _weights_struct(p, buffers) -> L.GlfWeights:
 
 def tpavi_forward_raw(x: torch.Tensor, params: dict, buffers, *, mode: int, training: bool, bn_layer: bool,
                       Ci: int, keep_for_backward: bool, z_out: Optional[torch.Tensor] = None,
-                      accumulate: bool = False, token_shape=None):
+                      accumulate: bool = False, token_shape=None, precision: int = L.PRECISION_BF16):
     """Run glf_tpavi_fwd.  ``x`` is either NCTHW-contiguous or token-major (see ``_is_token_major``), or, when
     ``token_shape=(B,T,H,W,C)`` is given, a dense token-major buffer of that shape.
     Returns (z_buffer [B,T,H,W,C], state, saved_blob)."""
@@ -98,7 +109,8 @@ def tpavi_forward_raw(x: torch.Tensor, params: dict, buffers, *, mode: int, trai
         else:
             x = x.contiguous()
             layout = L.LAYOUT_NCTHW
-    st = TPAVIState(B, C_, T, H, W, Ci, mode, _io_dtype(x), layout, training, bn_layer, accumulate)
+    st = TPAVIState(B, C_, T, H, W, Ci, mode, _io_dtype(x), layout, training, bn_layer, accumulate,
+                    precision=precision)
     dev = x.device
     if z_out is None:
         z_out = torch.empty((B, T, H, W, C_), dtype=x.dtype, device=dev)
@@ -151,7 +163,8 @@ class _TPAVIFunction(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)      # grad mode is off inside Function.forward
         z, st, saved, x_used = tpavi_forward_raw(x, params, buffers, mode=module._mode_id,
                                                  training=module.training, bn_layer=module._bn_layer,
-                                                 Ci=module.inter_channels, keep_for_backward=need_grad)
+                                                 Ci=module.inter_channels, keep_for_backward=need_grad,
+                                                 precision=module._precision_id())
         ctx.module = module
         ctx.st = st
         ctx.saved_blob = saved
@@ -226,6 +239,16 @@ class TPAVIModule(nn.Module):
         self.phi = nn.Conv3d(in_channels=self.in_channels, out_channels=self.inter_channels, kernel_size=1)
         self._bn_layer = bool(bn_layer)
         self._mode_id = L.MODE_DOT if mode == 'dot' else L.MODE_EMBEDDED
+        # tensor-core operand precision (not a reference ctor argument; set the attribute after construction):
+        #   'bf16' — bf16 operands, fp32 accumulate (throughput arm, 2e-2 tolerance)
+        #   'fp32' — fp32-exact products via 3-limb bf16 split on the same tcgen05 kernel (1e-4 tolerance, mode='dot')
+        self.compute_precision = DEFAULT_PRECISION
+
+    def _precision_id(self) -> int:
+        try:
+            return L.PRECISIONS[self.compute_precision]
+        except KeyError:
+            raise ValueError(f"compute_precision must be one of {sorted(L.PRECISIONS)}, got {self.compute_precision!r}")
 
     # ---- parameter plumbing -------------------------------------------------------------------------------------
     def _plist_names(self):

@@ -119,14 +119,15 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
 /* Gate + view concat (ours.py:1802-1820,1826-1827).
  *   f4[v]  : [B, C, h, w]  io_dtype, NCHW contiguous, v < V (host array of V device pointers, V <= 8)
  *   cls[v] : [B, ncls, h, w] fp32 logits of classifier[view];  ctr[v] : [B, 1, h, w] fp32 logits of centerness[view]
- *   xg, xl : [B, V*h*w, C] bf16 token-major (view-major token order, i.e. T = V)    — MGFM / MLFM inputs
+ *   xg, xl : [B, V*h*w, C] token-major (view-major token order, i.e. T = V), x_dtype (bf16, or fp32 for the
+ *            GLF_PRECISION_F32X3 arm)                                                 — MGFM / MLFM inputs
  *   gate   : [B, V, h, w] fp32, a = sigmoid(weight * max_c sigmoid(cls) * sigmoid(ctr))   (kept for backward) */
-GLF_API int glf_gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype,
+GLF_API int glf_gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, int x_dtype,
                         const void* const* f4, const float* const* cls, const float* const* ctr, void* xg, void* xl,
                         float* gate, glf_stream_t stream);
 
 /* df4[v] = dxg[:, v] + gate * dxl[:, v]  (NCHW, io_dtype);  dcls[v], dctr[v] fp32 logit gradients. */
-GLF_API int glf_gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype,
+GLF_API int glf_gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, int x_dtype,
                         const void* const* f4, const float* const* cls, const float* const* ctr, const float* gate,
                         const void* dxg, const void* dxl, void* const* df4, float* const* dcls, float* const* dctr,
                         glf_stream_t stream);

@@ -98,3 +98,23 @@ def test_ragged_spatial_sizes_against_oracle(h, w, V, io):
     for k, p in f.global_attn.named_parameters():
         if not k.startswith("align_channel"):
             assert_close("grad_g:" + k, p.grad, gg[k], 3e-2, abs_floor=1e-3)
+
+
+def test_glue_golden_fp32_precision():
+    """Whole fused call site with compute_precision='fp32': 1e-4 against the reference golden."""
+    g = load_golden("glue_dot_c128")
+    B, C, V, h, w = [int(v) for v in g["meta"]]
+    f = _build(C, golden_params(g, "param_g:"), golden_params(g, "param_l:"))
+    f.global_attn.compute_precision = "fp32"
+    f.local_attn.compute_precision = "fp32"
+    f4 = [g[f"f4:{v}"].to(DEV).requires_grad_(True) for v in range(V)]
+    cl = [g[f"cls:{v}"].to(DEV).requires_grad_(True) for v in range(V)]
+    ct = [g[f"ctr:{v}"].to(DEV).requires_grad_(True) for v in range(V)]
+    out = f({str(v): f4[v] for v in range(V)}, {str(v): cl[v] for v in range(V)}, {str(v): ct[v] for v in range(V)})
+    torch.autograd.backward([out[str(v)] for v in range(V)], [g[f"d_out:{v}"].to(DEV) for v in range(V)])
+    torch.cuda.synchronize()
+    for v in range(V):
+        assert_close(f"out:{v}", out[str(v)], g[f"out:{v}"], 1e-4)
+        assert_close(f"df4:{v}", f4[v].grad, g[f"df4:{v}"], 1e-4)
+        assert_close(f"dcls:{v}", cl[v].grad, g[f"dcls:{v}"], 5e-4)      # __expf sigmoids in the gate chain
+        assert_close(f"dctr:{v}", ct[v].grad, g[f"dctr:{v}"], 5e-4)

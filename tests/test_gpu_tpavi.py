@@ -140,3 +140,51 @@ def test_oracle_embedded_cfg2_tokens():
     for k, pp in m.named_parameters():
         if not k.startswith("align_channel"):
             assert_close("grad:" + k, pp.grad, go[k], 4e-2, zero_scale=scale)
+
+
+FP32_TOL = 1e-4      # north_star: within 1e-4 relative error in fp32
+
+
+@pytest.mark.parametrize("name", DOT_CASES)
+def test_golden_dot_fp32_precision(name):
+    """compute_precision='fp32' (3-limb bf16 split on tcgen05): the reference's fp32 tolerance, 1e-4."""
+    g = load_golden(name)
+    B, C, T, H, W, training, bn = [int(v) for v in g["meta"]]
+    m = load_module_from_params(TPAVIModule, golden_params(g), C, "dot", bool(bn))
+    m.compute_precision = "fp32"
+    m.train(bool(training))
+    z, dx = _run(m, g["x"].to(DEV), g["dz"].to(DEV))
+    assert z.dtype == torch.float32
+    assert_close("z", z, g["z"], FP32_TOL)
+    assert_close("dx", dx, g["dx"], FP32_TOL)
+    scale = grad_scale([v for k, v in g.items() if k.startswith("grad:")])
+    for k, p in m.named_parameters():
+        if k.startswith("align_channel"):
+            continue
+        assert_close("grad:" + k, p.grad, g["grad:" + k], FP32_TOL, zero_scale=scale)
+    if bn:
+        sd = m.state_dict()
+        for k in ("W_z.1.running_mean", "W_z.1.running_var"):
+            assert_close(k, sd[k], g["buf_after:" + k], FP32_TOL)
+
+
+def test_fp32_precision_cfg2_tokens_vs_fp64_oracle():
+    """C=256, N=3136 (cfg2 geometry), token-major fp32 input, against the fp64 closed-form oracle."""
+    B, C, T, H, W = 2, 256, 4, 28, 28
+    p = O.init_params(C, seed=61, randomize_affine=True)
+    gen = torch.Generator().manual_seed(62)
+    x = torch.randn(B, C, T, H, W, generator=gen)
+    dz = torch.randn(B, C, T, H, W, generator=gen)
+    p64 = {k: (v.double() if v.is_floating_point() else v) for k, v in p.items()}
+    zo, dxo, go, _ = O.tpavi_dot_closed_form(x.double(), dz.double(), p64, training=True)
+    m = load_module_from_params(TPAVIModule, p, C, "dot", True).train()
+    m.compute_precision = "fp32"
+    xd = x.to(DEV).permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
+    dzd = dz.to(DEV).permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
+    z, dx = _run(m, xd, dzd)
+    assert_close("z", z, zo, FP32_TOL)
+    assert_close("dx", dx, dxo, FP32_TOL)
+    scale = grad_scale(go.values())
+    for k, pp in m.named_parameters():
+        if not k.startswith("align_channel"):
+            assert_close("grad:" + k, pp.grad, go[k], FP32_TOL, zero_scale=scale)
