@@ -54,6 +54,10 @@ def test_sizes_are_host_only_and_scale_with_tokens():
     s3 = L.GlfSizes()
     assert lib.glf_tpavi_sizes(C.byref(_desc(x_layout=L.LAYOUT_NCTHW, io_dtype=L.DTYPE_F32)), C.byref(s3)) == 0
     assert s3.saved_bytes >= s1.saved_bytes + rows * 256 * 2
+    # the fp32-exact arm keeps fp32 activations plus three bf16 limb planes of the GEMM operands
+    s4 = L.GlfSizes()
+    assert lib.glf_tpavi_sizes(C.byref(_desc(precision=L.PRECISION_F32X3, io_dtype=L.DTYPE_F32)), C.byref(s4)) == 0
+    assert s4.saved_bytes >= rows * (256 * 4 + 3 * 256 * 2 + 3 * 384 * 2)
 
 
 @pytest.mark.parametrize("kw,frag", [
@@ -61,7 +65,8 @@ def test_sizes_are_host_only_and_scale_with_tokens():
     (dict(C=100), "multiples of 8"),
     (dict(C=4096, Ci=2048), "2048"),
     (dict(mode=3), "mode"),
-    (dict(precision=1), "PRECISION"),
+    (dict(precision=5), "precision"),
+    (dict(precision=1, mode=1), "F32X3"),
     (dict(io_dtype=7), "io_dtype"),
 ])
 def test_invalid_descriptors_are_errors_with_messages(kw, frag):
