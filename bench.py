@@ -282,9 +282,15 @@ def kernel_probe(args, dev, clips, C, pk):
     ms = e0.elapsed_time(e1) / n
     alg_bytes = 4 * rows * C * 2          # read dZ, U, X ; write dV  (bf16) — SURVEY §8d "epilogue bwd"
     achieved = alg_bytes / (ms * 1e-3) / 1e9
+    traffic = None                        # DRAM bytes per launch from the committed ncu --set full capture
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        t = json.load(open(tp))
+        if t.get("rows") == rows and t.get("C") == C:
+            traffic = int(t["traffic_bytes"])
     return {"roofline": {"bound": "hbm", "kernel": "bn_res_ln_bwd_kernel", "achieved": round(achieved, 1),
                          "peak": pk["hbm_gbs"], "peak_source": pk["source"], "unit": "GB/s",
-                         "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": None,
+                         "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": traffic,
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": round(ms, 4)}}
 
 
