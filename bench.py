@@ -192,12 +192,35 @@ def run_ours(args):
     res_host = torch.zeros(1, dtype=torch.float32).pin_memory()
     h2d = sum(t.numel() * t.element_size() for t in hf4 + hcls + hctr)
 
+    # double-buffered input pipeline: while step i computes, the copy stream moves step i+1's inputs host -> device
+    # into a staging set; the compute stream then takes them with one device-to-device copy (the CUDA graph reads
+    # fixed addresses).  Every timed step contains one full H2D input copy and one D2H result read.
+    dev_inputs = [t.detach() for t in f4 + cls + ctr]
+    host_inputs = hf4 + hcls + hctr
+    staging = [torch.empty_like(t) for t in dev_inputs]
+    copy_stream = torch.cuda.Stream()
+    copy_done = torch.cuda.Event()
+    staged_free = torch.cuda.Event()
+
+    def issue_h2d():
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(staged_free)
+            for dst, src in zip(staging, host_inputs):
+                dst.copy_(src, non_blocking=True)
+            copy_done.record(copy_stream)
+
     def e2e_step():
-        for dst, src in zip(f4 + cls + ctr, hf4 + hcls + hctr):
-            dst.detach().copy_(src, non_blocking=True)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(copy_done)
+        for dst, src in zip(dev_inputs, staging):
+            dst.copy_(src, non_blocking=True)
+        staged_free.record(cur)
+        issue_h2d()                       # next step's inputs, overlapped with this step's compute
         run_step()
         res_host.copy_(f4[0].grad.float().abs().mean().reshape(1), non_blocking=True)
 
+    staged_free.record(torch.cuda.current_stream())
+    issue_h2d()
     for _ in range(2):
         e2e_step()
     torch.cuda.synchronize()
@@ -225,6 +248,7 @@ def run_ours(args):
                                f"C={C}, bf16 fwd+bwd, frames-as-batch (B={clips * F} sequences x N={V * HH * WW} tokens per GPU)",
                    "clips_per_gpu_per_step": clips, "mode": "dot", "cuda_graph": bool(args.graph),
                    "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no flush" % (rows * C * 2 / 1e6),
+                   "e2e_pipeline": "pinned host inputs; H2D of step i+1 on a copy stream overlaps compute of step i",
                    "parallelism": f"dp{world}"},
         "e2e": {"value": round(total_clips / (e2e_ms * 1e-3), 2), "unit": "clips/s",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
