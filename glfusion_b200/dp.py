@@ -44,28 +44,34 @@ class GradBucket:
         self.numel = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
-
-    def pack(self) -> torch.Tensor:
+        # views of the flat bucket, one per parameter: pack / unpack are single multi-tensor copies
+        self.views: List[torch.Tensor] = []
         off = 0
         for p in self.params:
             n = p.numel()
-            if p.grad is None:
-                self.flat[off:off + n].zero_()
-            else:
-                self.flat[off:off + n].copy_(p.grad.reshape(-1))
+            self.views.append(self.flat[off:off + n].view_as(p))
             off += n
+
+    def pack(self) -> torch.Tensor:
+        if all(p.grad is not None and p.grad.dtype == torch.float32 for p in self.params):
+            torch._foreach_copy_(self.views, [p.grad for p in self.params])
+        else:
+            for v, p in zip(self.views, self.params):
+                if p.grad is None:
+                    v.zero_()
+                else:
+                    v.copy_(p.grad)
         return self.flat
 
     def unpack(self) -> None:
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            g = self.flat[off:off + n].view_as(p)
+        if all(p.grad is not None and p.grad.dtype == torch.float32 for p in self.params):
+            torch._foreach_copy_([p.grad for p in self.params], self.views)
+            return
+        for v, p in zip(self.views, self.params):
             if p.grad is None:
-                p.grad = g.clone().to(p.dtype)
+                p.grad = v.clone().to(p.dtype)
             else:
-                p.grad.copy_(g)
-            off += n
+                p.grad.copy_(v)
 
     def allreduce_mean(self, group=None) -> None:
         self.pack()

@@ -188,3 +188,22 @@ def test_fp32_precision_cfg2_tokens_vs_fp64_oracle():
     for k, pp in m.named_parameters():
         if not k.startswith("align_channel"):
             assert_close("grad:" + k, pp.grad, go[k], FP32_TOL, zero_scale=scale)
+
+
+@pytest.mark.parametrize("C,B,T,H,W", [(2048, 2, 3, 8, 8), (512, 2, 2, 9, 7), (64, 3, 2, 6, 6)])
+def test_oracle_dot_channel_widths(C, B, T, H, W):
+    """The reference network's real width (in_channels=2048, ours.py:1746-1747: 128x256 tiles, K=2048, 8 LayerNorm
+    slices per row), an odd one and a tiny one."""
+    p = O.init_params(C, seed=71, randomize_affine=True)
+    gen = torch.Generator().manual_seed(72)
+    x = torch.randn(B, C, T, H, W, generator=gen)
+    dz = torch.randn(B, C, T, H, W, generator=gen)
+    zo, dxo, go = O.tpavi_fwd_bwd(x, dz, {k: v.clone() for k, v in p.items()}, mode="dot")
+    m = load_module_from_params(TPAVIModule, p, C, "dot", True).train()
+    z, dx = _run(m, x.to(DEV, torch.bfloat16), dz.to(DEV, torch.bfloat16))
+    assert_close("z", z, zo, BF16_TOL)
+    assert_close("dx", dx, dxo, BF16_TOL)
+    scale = grad_scale(go.values())
+    for k, pp in m.named_parameters():
+        if not k.startswith("align_channel"):
+            assert_close("grad:" + k, pp.grad, go[k], 3e-2, zero_scale=scale)
