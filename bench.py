@@ -268,7 +268,7 @@ def count_launches(clips: int, C: int) -> int:
     """Kernels launched by libglf_sm100a per step (fwd+bwd, both modules + gate), counted from the orchestration in
     glfusion_b200/csrc/glf_api.cu (memset/memcpy nodes excluded)."""
     fwd_mod = 7          # prep_weights, proj GEMM, M GEMM, W' small GEMM, U GEMM, bn_finalize, bn_res_ln_fwd
-    bwd_mod = 14         # ln_bwd, finalize, apply, dTheta, dW', dWz, dM, dPhi, dG, dWcat, dX, 3 bias reductions
+    bwd_mod = 12         # ln_bwd, finalize, apply, dTheta, dW', dWz, dM, dPhi, dG, dWcat, dX, bias reductions
     return 2 * (fwd_mod + bwd_mod) + 2
 
 

@@ -486,9 +486,7 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
     g.D = m.pack_x ? static_cast<void*>(wb.dxtok) : dx; g.ldd = C;
     GLF_TRY(gemm(g, stream));
   }
-  GLF_TRY(reduce_partials(wb.cs_t, np, 2LL * Ci, Ci, 1.f, g_->theta_b, stream));
-  GLF_TRY(reduce_partials(wb.cs_p, np, 2LL * Ci, Ci, 1.f, g_->phi_b, stream));
-  GLF_TRY(reduce_partials(wb.cs_g, np, 2LL * Ci, Ci, 1.f, g_->g_b, stream));
+  GLF_TRY(reduce_partials3(wb.cs_t, wb.cs_p, wb.cs_g, np, 2LL * Ci, Ci, g_->theta_b, g_->phi_b, g_->g_b, stream));
   if (m.pack_x) {
     if (d->x_layout == GLF_LAYOUT_NCTHW)
       GLF_TRY(transpose_cast(wb.dxtok, dx, B, N, C, GLF_DTYPE_BF16, d->io_dtype, stream));

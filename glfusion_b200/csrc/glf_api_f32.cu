@@ -352,9 +352,8 @@ int tpavi_bwd_f32x3(const glf_desc* d, const void* dz, const void* x, const glf_
   {  // bias gradients = column sums of dP
     GLF_TRY(colstats_f32(wb.dPf, wb.cs, m.rows, 3 * Ci, stream));
     const int np = colstats_f32_blocks(m.rows);
-    GLF_TRY(reduce_partials(wb.cs, np, 2LL * 3 * Ci, Ci, 1.f, g_->theta_b, stream));
-    GLF_TRY(reduce_partials(wb.cs + Ci, np, 2LL * 3 * Ci, Ci, 1.f, g_->phi_b, stream));
-    GLF_TRY(reduce_partials(wb.cs + 2 * Ci, np, 2LL * 3 * Ci, Ci, 1.f, g_->g_b, stream));
+    GLF_TRY(reduce_partials3(wb.cs, wb.cs + Ci, wb.cs + 2 * Ci, np, 2LL * 3 * Ci, Ci, g_->theta_b, g_->phi_b, g_->g_b,
+                             stream));
   }
   GLF_TRY(check_cuda(cudaMemsetAsync(wb.dwcat, 0, sizeof(float) * pW, stream), "memset dWcat"));
   {  // dWcat = dP^T X

@@ -120,10 +120,25 @@ __device__ __forceinline__ void reduce_partial_rows(const float* __restrict__ pa
 #pragma unroll
   for (int j = 0; j < NS; ++j) acc[j] = 0.0;
   if (cact) {
-    for (int i = threadIdx.y; i < np; i += RED_Y) {
+    // four independent partial sums per statistic keep four loads in flight; combined in a fixed order
+    double a4[NS][4];
 #pragma unroll
-      for (int j = 0; j < NS; ++j) acc[j] += static_cast<double>(part[i * row_stride + j * stat_stride + c]);
+    for (int j = 0; j < NS; ++j) a4[j][0] = a4[j][1] = a4[j][2] = a4[j][3] = 0.0;
+    int i = threadIdx.y;
+    for (; i + 3 * RED_Y < np; i += 4 * RED_Y) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j)
+          a4[j][u] += static_cast<double>(part[(i + u * RED_Y) * row_stride + j * stat_stride + c]);
+      }
     }
+    for (; i < np; i += RED_Y) {
+#pragma unroll
+      for (int j = 0; j < NS; ++j) a4[j][0] += static_cast<double>(part[i * row_stride + j * stat_stride + c]);
+    }
+#pragma unroll
+    for (int j = 0; j < NS; ++j) acc[j] = (a4[j][0] + a4[j][1]) + (a4[j][2] + a4[j][3]);
   }
 #pragma unroll
   for (int j = 0; j < NS; ++j) sm[j][threadIdx.y][threadIdx.x] = acc[j];
@@ -502,6 +517,21 @@ __global__ void __launch_bounds__(32 * RED_Y)
   if (threadIdx.y == 0 && cact) out[c] = static_cast<float>(s[0] * alpha);
 }
 
+// three reductions in one launch (blockIdx.y selects): the bias gradients of theta / phi / g
+struct Reduce3 {
+  const float* part[3];
+  float* out[3];
+};
+__global__ void __launch_bounds__(32 * RED_Y)
+    reduce_partials3_kernel(const Reduce3 r, int np, long long stride, int n) {
+  __shared__ double sm[1][RED_Y][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool cact = c < n;
+  double s[1];
+  reduce_partial_rows<1>(r.part[blockIdx.y], np, stride, 0, c, cact, s, sm);
+  if (threadIdx.y == 0 && cact) r.out[blockIdx.y][c] = static_cast<float>(s[0]);
+}
+
 // fp32 -> bf16 (8 elements per thread)
 __global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long nvec) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
@@ -705,6 +735,15 @@ int bn_bwd_apply(const void* dV, const void* U, int act_dtype, const float* k1, 
 int reduce_partials(const float* part, int np, long long stride, int n, float alpha, float* out, cudaStream_t stream) {
   reduce_partials_kernel<<<(n + 31) / 32, dim3(32, RED_Y), 0, stream>>>(part, np, stride, n, alpha, out);
   return check_cuda(cudaGetLastError(), "reduce_partials launch");
+}
+
+int reduce_partials3(const float* p0, const float* p1, const float* p2, int np, long long stride, int n, float* o0,
+                     float* o1, float* o2, cudaStream_t stream) {
+  Reduce3 r;
+  r.part[0] = p0; r.part[1] = p1; r.part[2] = p2;
+  r.out[0] = o0; r.out[1] = o1; r.out[2] = o2;
+  reduce_partials3_kernel<<<dim3((n + 31) / 32, 3), dim3(32, RED_Y), 0, stream>>>(r, np, stride, n);
+  return check_cuda(cudaGetLastError(), "reduce_partials3 launch");
 }
 
 int split3(const float* in, bf16* out, long long n, cudaStream_t stream) {

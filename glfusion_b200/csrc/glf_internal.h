@@ -70,6 +70,8 @@ int colstats_f32_blocks(long long rows);
 int colstats_f32(const float* A, float* part, long long rows, int C, cudaStream_t stream);
 int prep_weights_f32(const glf_weights* w, int C, int Ci, float* wcat, float* wcatT, float* bcat, cudaStream_t stream);
 int reduce_partials(const float* part, int np, long long stride, int n, float alpha, float* out, cudaStream_t stream);
+int reduce_partials3(const float* p0, const float* p1, const float* p2, int np, long long stride, int n, float* o0,
+                     float* o1, float* o2, cudaStream_t stream);
 int cast_bf16(const float* in, bf16* out, long long n, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------ gate + concat
