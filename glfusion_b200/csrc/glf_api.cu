@@ -134,8 +134,8 @@ size_t carve_saved(const Dims& m, void* base, Saved* s) {
 struct WsFwd { float* colstats; float* Mf; void* attn; void* saved_fallback; };
 size_t carve_ws_fwd(const Dims& m, void* base, WsFwd* w, size_t saved_bytes) {
   Carver c(base);
-  const size_t np = m.dot ? static_cast<size_t>(m.B) * m.tiles_seq : static_cast<size_t>(m.tiles_all);
-  w->colstats = c.take<float>(np * 2 * m.C);
+  const size_t np = 4 * (m.dot ? static_cast<size_t>(m.B) * m.tiles_seq : static_cast<size_t>(m.tiles_all));
+  w->colstats = c.take<float>(np * 2 * m.C);   // one partial per (tile, 32-row quarter)
   w->Mf = m.dot ? c.take<float>(static_cast<size_t>(m.B) * m.Ci * m.Ci) : nullptr;  // split-K accumulation target
   w->attn = m.dot ? nullptr : c.take<uint8_t>(attn_scratch_bytes(m.B, m.N, false));
   w->saved_fallback = c.take<uint8_t>(saved_bytes);  // used when the caller passes saved == NULL (inference)
@@ -170,7 +170,7 @@ size_t carve_ws_bwd(const glf_desc* d, const Dims& m, void* base, WsBwd* w) {
   w->k1 = c.take<float>(C);
   w->k2 = c.take<float>(C);
   w->k3 = c.take<float>(C);
-  const size_t np = B * m.tiles_seq;
+  const size_t np = 4 * B * m.tiles_seq;       // one partial per (tile, 32-row quarter)
   w->cs_t = c.take<float>(np * 2 * Ci);
   w->cs_p = c.take<float>(np * 2 * Ci);
   w->cs_g = c.take<float>(np * 2 * Ci);
@@ -306,7 +306,7 @@ GLF_API int glf_tpavi_fwd(const glf_desc* d, const void* x, const glf_weights* w
       g.colstats = (d->training && d->bn_layer) ? wf.colstats : nullptr;
       GLF_TRY(gemm(g, stream));
     }
-    np = B * m.tiles_seq;
+    np = 4 * B * m.tiles_seq;
   } else {
     GLF_TRY(flash_fwd(s.P, s.Y, s.lse, B, N, Ci, wf.attn, stream));
     {  // U = Y Wz^T + bz
@@ -319,7 +319,7 @@ GLF_API int glf_tpavi_fwd(const glf_desc* d, const void* x, const glf_weights* w
       g.colstats = (d->training && d->bn_layer) ? wf.colstats : nullptr;
       GLF_TRY(gemm(g, stream));
     }
-    np = m.tiles_all;
+    np = 4 * m.tiles_all;
   }
   GLF_TRY(bn_finalize(wf.colstats, np, C, static_cast<double>(m.rows), d, w, s.bn_mean, s.bn_rstd, s.bn_a, s.bn_b,
                       stream));
@@ -438,7 +438,7 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
       g.colstats = wb.cs_g;
       GLF_TRY(gemm(g, stream));
     }
-    np = B * m.tiles_seq;
+    np = 4 * B * m.tiles_seq;
   } else {
     {  // dY = dU Wz
       GemmArgs g;
@@ -460,7 +460,7 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
       GLF_TRY(gemm(g, stream));
     }
     GLF_TRY(flash_bwd(s.P, s.Y, wb.dY, s.lse, wb.dP, wb.delta, wb.cs_t, wb.cs_p, wb.cs_g, B, N, Ci, wb.attn, stream));
-    np = B * m.tiles_seq;
+    np = 4 * B * m.tiles_seq;
   }
   GLF_TRY(check_cuda(cudaMemsetAsync(wb.dwcat, 0, sizeof(float) * 3 * Ci * C, stream), "memset dWcat"));
   {  // dWcat[r,c] = sum_n dP[n,r] X[n,c]

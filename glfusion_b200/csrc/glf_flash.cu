@@ -174,7 +174,7 @@ int flash_bwd(const bf16* P3, const bf16* Y, const bf16* dY, const float* lse, b
     const bf16* Pb = P3 + b0 * seqP;
     const bf16* dYb = dY + static_cast<long long>(b0) * N * Ci;
     bf16* dPb = dP3 + b0 * seqP;
-    const long long cs_off = static_cast<long long>(b0) * tiles_seq * 2 * Ci;
+    const long long cs_off = static_cast<long long>(b0) * tiles_seq * 4 * 2 * Ci;   // 4 row-quarter partials per tile
     int rc;
     {  // S = Theta Phi^T (recompute)
       GemmArgs g;

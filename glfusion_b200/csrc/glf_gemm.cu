@@ -8,10 +8,11 @@
 //   warp 1      MMA issuer    : allocates TMEM (two accumulator stages), one elected lane issues tcgen05.mma
 //                               (M=128, N=BN, K=16) x 4 per stage; tcgen05.commit releases the smem slot / publishes
 //                               the accumulator, so tile i+1 is computed while tile i is still in its epilogue
-//   warps 2..17 epilogue      : tcgen05.ld the fp32 accumulator (one TMEM lane quarter per warp), alpha/bias, then
-//                               either fp32 store / fp32 red.add (split-K) straight from registers, or bf16 staging in
-//                               smem -> fully coalesced 16-byte row stores (+ residual addend) and per-tile column
-//                               statistics (sum, sum of squares) for the BatchNorm that follows W_z (ours.py:908).
+//   warps 2..17 epilogue      : 16 independent warps (no block barriers); each tcgen05.ld's its 32x32 sub-block of the
+//                               fp32 accumulator, applies alpha/bias, then either fp32 store / fp32 red.add (split-K)
+//                               from registers, or a warp-private swizzled smem transpose -> 64-byte row-segment
+//                               stores (+ residual addend) and a per-sub-block column-statistics partial (sum, sum of
+//                               squares) for the BatchNorm that follows W_z (ours.py:908).
 // Operands may be K-major ([rows, K]) or MN-major ([K, rows]); the latter is how the token-contraction products
 // (Phi^T G, dU^T Theta, dP^T X) read token-major activations without any transposed copy.
 #include <mutex>
@@ -54,11 +55,10 @@ struct GemmCfg {
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t RING_BYTES = STAGES * STAGE_BYTES;
-  static constexpr uint32_t STG_ROW = BN * 2 + 16;  // staging row pitch (bytes): odd multiple of 16 -> conflict free
-  static constexpr uint32_t STG_BYTES = BM * STG_ROW;
-  static constexpr uint32_t RED_BYTES = (BN == 256) ? 0 : EPI_WARPS * 2 * BN * 4;  // [warp][2][BN] column-stat partials
-  static constexpr uint32_t BIAS_BYTES = BN * 4;
-  static constexpr uint32_t SMEM_BYTES = RING_BYTES + STG_BYTES + RED_BYTES + BIAS_BYTES + 1024;
+  static constexpr uint32_t WARP_STG = 32 * 64;     // warp-private 32 rows x 32 bf16, XOR-swizzled 16-byte chunks
+  static constexpr uint32_t WARP_BIAS = 32 * 4;     // warp-private bias slice of the current 32-column chunk
+  static constexpr uint32_t EPI_BYTES = EPI_WARPS * (WARP_STG + WARP_BIAS);
+  static constexpr uint32_t SMEM_BYTES = RING_BYTES + EPI_BYTES + 1024;
   static constexpr uint32_t TMEM_COLS = 2 * BN;     // two accumulator stages
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(TMEM_COLS <= 512, "TMEM budget");
@@ -84,9 +84,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  uint8_t* stg = smem_gen + Cfg::RING_BYTES;
-  float* redbuf = reinterpret_cast<float*>(stg + Cfg::STG_BYTES);
-  float* bias_sm = reinterpret_cast<float*>(stg + Cfg::STG_BYTES + Cfg::RED_BYTES);
+  uint8_t* epi_smem = smem_gen + Cfg::RING_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -193,13 +191,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   } else {
     // ------------------------------------------------------------------------------------------ epilogue
-    // 16 warps: warp (2 + ew) reads TMEM lane quarter (warp % 4) and the 32-column chunks {ew/4, ew/4 + 4, ...}.
+    // 16 independent warps, no block-level barriers.  Warp (2 + ew) owns TMEM lane quarter q = warp % 4 (rows
+    // 32q..32q+31 of the tile) and the 32-column chunks {ew/4, ew/4 + 4, ...}: it loads its sub-block from TMEM,
+    // applies alpha / bias, transposes it through a warp-private XOR-swizzled smem tile so that 4 lanes write one
+    // 64-byte row segment (full 32-byte sectors), adds the residual addend, and emits its own column-stat partial.
     const int ew = warp - 2;
     const int q = warp & 3;
     const int cc0 = ew >> 2;
-    const int row = q * 32 + lane;
-    const int e = ew * 32 + lane;  // 0..EPI_THREADS-1
     constexpr int NCHUNK = BN / 32;
+    uint8_t* wstg = epi_smem + ew * (Cfg::WARP_STG + Cfg::WARP_BIAS);
+    float* wbias = reinterpret_cast<float*>(wstg + Cfg::WARP_STG);
+    const int sw_w = (lane >> 1) & 3;          // swizzle of the row this lane WRITES (row = lane)
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int z = tile / tiles_mn, mn = tile % tiles_mn;
@@ -208,144 +210,98 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const int b = z / p.split_k, split = z % p.split_k;
       const int acc = local & 1;
       const uint32_t use = static_cast<uint32_t>(local >> 1);
-      const int grow = m0 + row;
+      const int grow = m0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
       const bool use_bias = p.bias != nullptr && split == 0;
-      if (use_bias && e < BN) bias_sm[e] = (n0 + e < p.N) ? p.bias[n0 + e] : 0.f;
-      named_bar_sync(1, EPI_THREADS);  // bias visible; previous tile's staging fully consumed
       mbar_wait(smem_u32(&tmem_full_bar[acc]), use & 1u);
       tc_fence_after();
-      if (p.out_kind != 0) {
-        float* Df = reinterpret_cast<float*>(p.D) + static_cast<long long>(b) * p.strideD +
-                    static_cast<long long>(grow) * p.ldd;
 #pragma unroll 1
-        for (int c = cc0; c < NCHUNK; c += 4) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + c * 32, v);
-          tmem_ld_wait();
+      for (int c = cc0; c < NCHUNK; c += 4) {
+        const int gc0 = n0 + c * 32;           // first global column of this chunk
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        if (use_bias) wbias[lane] = (gc0 + lane < p.N) ? p.bias[gc0 + lane] : 0.f;
+        tmem_ld_wait();
+        if (c + 4 >= NCHUNK) {                 // last TMEM read of this warp for the tile: release the accumulator
+          tc_fence_before();
+          mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+        }
+        __syncwarp();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+        if (use_bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(wbias + j);
+            f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+          }
+        }
+        if (p.out_kind != 0) {
+          float* Df = reinterpret_cast<float*>(p.D) + static_cast<long long>(b) * p.strideD +
+                      static_cast<long long>(grow) * p.ldd;
           if (grow < p.M) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const int gc = n0 + c * 32 + j;
+              const int gc = gc0 + j;
               if (gc < p.N) {
-                float f0 = __uint_as_float(v[j]) * p.alpha, f1 = __uint_as_float(v[j + 1]) * p.alpha;
-                float f2 = __uint_as_float(v[j + 2]) * p.alpha, f3 = __uint_as_float(v[j + 3]) * p.alpha;
-                if (use_bias) {
-                  const float4 bv = *reinterpret_cast<const float4*>(bias_sm + c * 32 + j);
-                  f0 += bv.x; f1 += bv.y; f2 += bv.z; f3 += bv.w;
-                }
                 if (p.out_kind == 2) {
-                  red_add_v4(Df + gc, f0, f1, f2, f3);
+                  red_add_v4(Df + gc, f[j], f[j + 1], f[j + 2], f[j + 3]);
                 } else {
-                  *reinterpret_cast<float4*>(Df + gc) = make_float4(f0, f1, f2, f3);
+                  *reinterpret_cast<float4*>(Df + gc) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
                 }
               }
             }
           }
+          __syncwarp();
+          continue;
         }
-        tc_fence_before();
-        mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
-      } else {
-#pragma unroll 1
-        for (int c = cc0; c < NCHUNK; c += 4) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + c * 32, v);
-          tmem_ld_wait();
+        // ---- bf16 output: warp-private transpose ----
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float f[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(v[j + t]) * p.alpha;
-            if (use_bias) {
-              const float4 b0 = *reinterpret_cast<const float4*>(bias_sm + c * 32 + j);
-              const float4 b1 = *reinterpret_cast<const float4*>(bias_sm + c * 32 + j + 4);
-              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-            }
-            uint4 pk = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
-                                  pack_bf16(f[6], f[7]));
-            *reinterpret_cast<uint4*>(stg + row * Cfg::STG_ROW + (c * 32 + j) * 2) = pk;
+        for (int j = 0; j < 4; ++j) {
+          const uint4 pk = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                                      pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+          *reinterpret_cast<uint4*>(wstg + lane * 64 + ((j ^ sw_w) << 4)) = pk;
+        }
+        __syncwarp();
+        const int rows_valid = min(32, p.M - (m0 + q * 32));   // valid rows of this warp's sub-block (may be <= 0)
+        if (p.colstats != nullptr) {
+          // lane = column: sum the stored (bf16-rounded) values over the sub-block's valid rows
+          float s1 = 0.f, s2 = 0.f;
+          const int cch = lane >> 3, cel = (lane & 7) * 2;
+          for (int r = 0; r < rows_valid; ++r) {
+            const float x = __bfloat162float(
+                *reinterpret_cast<const bf16*>(wstg + r * 64 + ((cch ^ ((r >> 1) & 3)) << 4) + cel));
+            s1 += x;
+            s2 = fmaf(x, x, s2);
+          }
+          if (gc0 + lane < p.N) {
+            float* cs = p.colstats + ((static_cast<long long>(b) * p.tiles_m + m_tile) * 4 + q) * 2 * p.N;
+            cs[gc0 + lane] = s1;
+            cs[p.N + gc0 + lane] = s2;
           }
         }
-        tc_fence_before();
-        mbar_arrive(smem_u32(&tmem_empty_bar[acc]));  // accumulator free: the next tile's MMAs may start
-        named_bar_sync(1, EPI_THREADS);
-        const int rows_valid = min(BM, p.M - m0);
-        // coalesced 16-byte row stores; the residual addend loads of all iterations are issued first
         bf16* Db = reinterpret_cast<bf16*>(p.D) + static_cast<long long>(b) * p.strideD;
         const bf16* Ad = p.addend ? p.addend + static_cast<long long>(b) * p.stride_add : nullptr;
-        constexpr int CH = BN / 8;                       // 16-byte chunks per row
-        constexpr int NIT = (BM * CH) / EPI_THREADS;     // 2 / 4 / 8
-        uint4 adv[NIT];
+        const int rch = lane & 3;              // 16-byte chunk of the row segment this lane stores
+        const int gc = gc0 + rch * 8;
+        uint4 adv[4];
         if (Ad != nullptr) {
 #pragma unroll
-          for (int i = 0; i < NIT; ++i) {
-            const int idx = e + i * EPI_THREADS;
-            const int r = idx / CH, ch = idx % CH;
-            const int gr = m0 + r, gc = n0 + ch * 8;
-            adv[i] = (gr < p.M && gc < p.N)
+          for (int i = 0; i < 4; ++i) {
+            const int r = (lane >> 2) + 8 * i;
+            const int gr = m0 + q * 32 + r;
+            adv[i] = (r < rows_valid && gc < p.N)
                          ? *reinterpret_cast<const uint4*>(Ad + static_cast<long long>(gr) * p.ld_add + gc)
                          : make_uint4(0, 0, 0, 0);
           }
         }
-        if (BN != 256 && p.colstats != nullptr) {
-          // every thread sums 8 columns over its row group, lanes sharing a column group combine by shuffle,
-          // one partial per warp lands in shared memory and BN threads add the 16 warp partials in fixed order
-          constexpr int CG = BN / 8;                 // column groups (<= 32)
-          constexpr int RG = EPI_THREADS / CG;       // row groups
-          constexpr int RPG = BM / RG;               // rows per group
-          const int cg = e % CG, rg = e / CG;
-          float s[8], s2[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) s[t] = s2[t] = 0.f;
-          const int r_end = min(rows_valid, (rg + 1) * RPG);
-          for (int r = rg * RPG; r < r_end; ++r) {
-            const uint4 pk = *reinterpret_cast<const uint4*>(stg + r * Cfg::STG_ROW + cg * 16);
-            const uint32_t* u = reinterpret_cast<const uint32_t*>(&pk);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 x = unpack_bf16(u[t]);
-              s[2 * t] += x.x;
-              s[2 * t + 1] += x.y;
-              s2[2 * t] = fmaf(x.x, x.x, s2[2 * t]);
-              s2[2 * t + 1] = fmaf(x.y, x.y, s2[2 * t + 1]);
-            }
-          }
-#pragma unroll
-          for (int off = CG; off < 32; off <<= 1) {
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              s[t] += __shfl_xor_sync(0xffffffffu, s[t], off);
-              s2[t] += __shfl_xor_sync(0xffffffffu, s2[t], off);
-            }
-          }
-          if (lane < CG) {
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              redbuf[(ew * 2 + 0) * BN + lane * 8 + t] = s[t];
-              redbuf[(ew * 2 + 1) * BN + lane * 8 + t] = s2[t];
-            }
-          }
-          named_bar_sync(1, EPI_THREADS);
-          if (e < BN && n0 + e < p.N) {
-            float a = 0.f, a2 = 0.f;
-#pragma unroll
-            for (int g = 0; g < EPI_WARPS; ++g) {
-              a += redbuf[(g * 2 + 0) * BN + e];
-              a2 += redbuf[(g * 2 + 1) * BN + e];
-            }
-            float* cs = p.colstats + (static_cast<long long>(b) * p.tiles_m + m_tile) * 2 * p.N;
-            cs[n0 + e] = a;
-            cs[p.N + n0 + e] = a2;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < NIT; ++i) {
-          const int idx = e + i * EPI_THREADS;
-          const int r = idx / CH, ch = idx % CH;
-          const int gr = m0 + r, gc = n0 + ch * 8;
-          if (gr < p.M && gc < p.N) {
-            uint4 pk = *reinterpret_cast<const uint4*>(stg + r * Cfg::STG_ROW + ch * 16);
+        for (int i = 0; i < 4; ++i) {
+          const int r = (lane >> 2) + 8 * i;
+          const int gr = m0 + q * 32 + r;
+          if (r < rows_valid && gc < p.N) {
+            uint4 pk = *reinterpret_cast<const uint4*>(wstg + r * 64 + ((rch ^ ((r >> 1) & 3)) << 4));
             if (Ad != nullptr) {
               const uint32_t* a32 = reinterpret_cast<const uint32_t*>(&adv[i]);
               uint32_t* p32 = reinterpret_cast<uint32_t*>(&pk);
@@ -358,6 +314,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             *reinterpret_cast<uint4*>(Db + static_cast<long long>(gr) * p.ldd + gc) = pk;
           }
         }
+        __syncwarp();                            // staging reused by the next chunk / tile
+      }
+      if (cc0 >= NCHUNK) {                       // warps without a chunk (BN = 64) still release the accumulator
+        tc_fence_before();
+        mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
       }
     }
   }
@@ -453,7 +414,6 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
   // loads.  Large-K (tensor-bound, e.g. C=2048) products take the 128x256 tile.
   int BN = (a.N <= 64) ? 64 : ((a.K >= 512 && a.N % 256 == 0) ? 256 : 128);
   if (a.bn_hint == 64 || a.bn_hint == 128 || a.bn_hint == 256) BN = a.bn_hint;
-  if (a.colstats != nullptr && BN == 256) BN = 128;  // the column-statistics epilogue is built for tiles <= 128 wide
   int nlimbsA = 1, nlimbsB = 1;
   for (int i = 0; i < a.npairs; ++i) {
     nlimbsA = a.pairA[i] + 1 > nlimbsA ? a.pairA[i] + 1 : nlimbsA;

@@ -26,7 +26,7 @@ def gemm(A, B, M, N, K, batch=1, a_mn=0, b_mn=0, out_kind=0, split_k=1, bias=Non
     D = torch.zeros((batch, M, N), dtype=torch.bfloat16 if out_kind == 0 else torch.float32, device=A.device)
     cs = None
     if colstats:
-        cs = torch.zeros((batch * ((M + 127) // 128), 2, N), dtype=torch.float32, device=A.device)
+        cs = torch.zeros((batch * ((M + 127) // 128) * 4, 2, N), dtype=torch.float32, device=A.device)
     L.check(lib.glf_gemm_bf16(L.ptr(A), L.ptr(B), L.ptr(D), M, N, K, batch, a_mn, b_mn, lda, ldb, N, sA, sB, M * N,
                               L.ptr(bias), float(alpha), L.ptr(addend), N, M * N, out_kind, split_k, L.ptr(cs),
                               stream()))
