@@ -131,11 +131,12 @@ size_t carve_saved(const Dims& m, void* base, Saved* s) {
   return (c.off + 255) & ~static_cast<size_t>(255);
 }
 
-struct WsFwd { float* colstats; float* Mf; void* attn; void* saved_fallback; };
+struct WsFwd { float* colstats; float* red1; float* Mf; void* attn; void* saved_fallback; };
 size_t carve_ws_fwd(const Dims& m, void* base, WsFwd* w, size_t saved_bytes) {
   Carver c(base);
   const size_t np = 4 * (m.dot ? static_cast<size_t>(m.B) * m.tiles_seq : static_cast<size_t>(m.tiles_all));
   w->colstats = c.take<float>(np * 2 * m.C);   // one partial per (tile, 32-row quarter)
+  w->red1 = c.take<float>(static_cast<size_t>(REDUCE_STAGE1_ROWS) * 2 * m.C);
   w->Mf = m.dot ? c.take<float>(static_cast<size_t>(m.B) * m.Ci * m.Ci) : nullptr;  // split-K accumulation target
   w->attn = m.dot ? nullptr : c.take<uint8_t>(attn_scratch_bytes(m.B, m.N, false));
   w->saved_fallback = c.take<uint8_t>(saved_bytes);  // used when the caller passes saved == NULL (inference)
@@ -144,7 +145,7 @@ size_t carve_ws_fwd(const Dims& m, void* base, WsFwd* w, size_t saved_bytes) {
 
 struct WsBwd {
   bf16 *dztok, *dV, *dU, *dP, *dY, *dxtok, *dM, *dWpb;
-  float *dWpf, *part_ln, *k1, *k2, *k3, *cs_t, *cs_p, *cs_g, *dwcat, *delta;
+  float *dWpf, *part_ln, *k1, *k2, *k3, *cs_t, *cs_p, *cs_g, *red1, *dwcat, *delta;
   void* attn;
 };
 size_t carve_ws_bwd(const glf_desc* d, const Dims& m, void* base, WsBwd* w) {
@@ -174,6 +175,7 @@ size_t carve_ws_bwd(const glf_desc* d, const Dims& m, void* base, WsBwd* w) {
   w->cs_t = c.take<float>(np * 2 * Ci);
   w->cs_p = c.take<float>(np * 2 * Ci);
   w->cs_g = c.take<float>(np * 2 * Ci);
+  w->red1 = c.take<float>(static_cast<size_t>(REDUCE_STAGE1_ROWS) * 3 * Ci);
   w->dwcat = c.take<float>(3 * Ci * C);
   return (c.off + 255) & ~static_cast<size_t>(255);
 }
@@ -321,7 +323,13 @@ GLF_API int glf_tpavi_fwd(const glf_desc* d, const void* x, const glf_weights* w
     }
     np = 4 * m.tiles_all;
   }
-  GLF_TRY(bn_finalize(wf.colstats, np, C, static_cast<double>(m.rows), d, w, s.bn_mean, s.bn_rstd, s.bn_a, s.bn_b,
+  const float* bn_part = wf.colstats;
+  if (d->training && d->bn_layer && np > 4 * REDUCE_STAGE1_ROWS) {
+    long long rs = 2LL * C;
+    GLF_TRY(reduce_stage1(wf.colstats, nullptr, nullptr, 1, &np, &rs, C, 2, C, wf.red1, stream));
+    bn_part = wf.red1;
+  }
+  GLF_TRY(bn_finalize(bn_part, np, C, static_cast<double>(m.rows), d, w, s.bn_mean, s.bn_rstd, s.bn_a, s.bn_b,
                       stream));
   GLF_TRY(bn_res_ln_fwd(s.U, X, GLF_DTYPE_BF16, s.bn_a, s.bn_b, w->ln_w, w->ln_b, z, d->io_dtype, s.ln_mu, s.ln_r,
                         m.rows, C, d->eps_ln, d->accumulate, stream));
@@ -486,7 +494,17 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
     g.D = m.pack_x ? static_cast<void*>(wb.dxtok) : dx; g.ldd = C;
     GLF_TRY(gemm(g, stream));
   }
-  GLF_TRY(reduce_partials3(wb.cs_t, wb.cs_p, wb.cs_g, np, 2LL * Ci, Ci, g_->theta_b, g_->phi_b, g_->g_b, stream));
+  {  // bias gradients = column sums of dTheta / dPhi / dG, from the per-sub-block partials of their GEMM epilogues
+    long long rs = 2LL * Ci;
+    const float *t0 = wb.cs_t, *t1 = wb.cs_p, *t2 = wb.cs_g;
+    if (np > 4 * REDUCE_STAGE1_ROWS) {
+      GLF_TRY(reduce_stage1(wb.cs_t, wb.cs_p, wb.cs_g, 3, &np, &rs, 0, 1, Ci, wb.red1, stream));
+      t0 = wb.red1;
+      t1 = wb.red1 + static_cast<long long>(REDUCE_STAGE1_ROWS) * Ci;
+      t2 = wb.red1 + 2LL * REDUCE_STAGE1_ROWS * Ci;
+    }
+    GLF_TRY(reduce_partials3(t0, t1, t2, np, rs, Ci, g_->theta_b, g_->phi_b, g_->g_b, stream));
+  }
   if (m.pack_x) {
     if (d->x_layout == GLF_LAYOUT_NCTHW)
       GLF_TRY(transpose_cast(wb.dxtok, dx, B, N, C, GLF_DTYPE_BF16, d->io_dtype, stream));

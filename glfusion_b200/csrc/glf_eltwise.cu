@@ -151,6 +151,31 @@ __device__ __forceinline__ void reduce_partial_rows(const float* __restrict__ pa
   }
 }
 
+// Stage 1 of the two-stage reductions: G row-slices of the partial table are reduced by G x (C/32) CTAs in parallel
+// (fixed order inside every slice); the finalisers then combine G rows.  Up to 3 tables per launch (blockIdx.z).
+struct Stage1 {
+  const float* part[3];
+  float* out[3];          // [G][NS][C]
+};
+template <int NS>
+__global__ void __launch_bounds__(32 * RED_Y)
+    reduce_stage1_kernel(const Stage1 t, int np, long long row_stride, long long stat_stride, int C, int G) {
+  __shared__ double sm[NS][RED_Y][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool cact = c < C;
+  const int g = blockIdx.y;
+  const int chunk = (np + G - 1) / G;
+  const int r0 = g * chunk;
+  const int cnt = max(0, min(np, r0 + chunk) - r0);
+  double s[NS];
+  reduce_partial_rows<NS>(t.part[blockIdx.z] + static_cast<long long>(r0) * row_stride, cnt, row_stride, stat_stride, c,
+                          cact, s, sm);
+  if (threadIdx.y == 0 && cact) {
+#pragma unroll
+    for (int j = 0; j < NS; ++j) t.out[blockIdx.z][(static_cast<long long>(g) * NS + j) * C + c] = static_cast<float>(s[j]);
+  }
+}
+
 // partials: [np][2][C] (sum, sum of squares) -> mean, rstd, affine a = gamma*rstd, b = beta - mean*a; running stats.
 __global__ void __launch_bounds__(32 * RED_Y)
     bn_finalize_kernel(const float* __restrict__ part, int np, int C, double count, const float* __restrict__ gamma,
@@ -646,6 +671,22 @@ int prep_weights(const glf_weights* w, int C, int Ci, bf16* wcat, bf16* wcatT, f
   prep_weights_kernel<<<blocks, 256, 0, stream>>>(w->theta_w, w->phi_w, w->g_w, w->theta_b, w->phi_b, w->g_b, w->wz_w,
                                                   wcat, wcatT, bcat, wz, wzT, C, Ci);
   return check_cuda(cudaGetLastError(), "prep_weights launch");
+}
+
+// stage-1 launcher: returns the reduced table (in `scratch`) and its row count through *np
+int reduce_stage1(const float* p0, const float* p1, const float* p2, int ntab, int* np, long long* row_stride,
+                  long long stat_stride, int NS, int C, float* scratch, cudaStream_t stream) {
+  const int G = REDUCE_STAGE1_ROWS;
+  Stage1 t;
+  const long long tab = static_cast<long long>(G) * NS * C;
+  t.part[0] = p0; t.part[1] = p1; t.part[2] = p2;
+  t.out[0] = scratch; t.out[1] = scratch + tab; t.out[2] = scratch + 2 * tab;
+  dim3 grid((C + 31) / 32, G, ntab);
+  if (NS == 1) reduce_stage1_kernel<1><<<grid, dim3(32, RED_Y), 0, stream>>>(t, *np, *row_stride, stat_stride, C, G);
+  else reduce_stage1_kernel<2><<<grid, dim3(32, RED_Y), 0, stream>>>(t, *np, *row_stride, stat_stride, C, G);
+  *np = G;
+  *row_stride = static_cast<long long>(NS) * C;
+  return check_cuda(cudaGetLastError(), "reduce_stage1 launch");
 }
 
 int bn_finalize(const float* part, int np, int C, double count, const glf_desc* d, const glf_weights* w, float* mean,
