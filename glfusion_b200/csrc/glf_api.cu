@@ -306,9 +306,9 @@ GLF_API int glf_tpavi_fwd(const glf_desc* d, const void* x, const glf_weights* w
       g.bias = w->wz_b;
       g.D = s.U; g.ldd = C; g.strideD = static_cast<long long>(N) * C;
       g.colstats = (d->training && d->bn_layer) ? wf.colstats : nullptr;
+      g.colstats_rows = &np;
       GLF_TRY(gemm(g, stream));
     }
-    np = 4 * B * m.tiles_seq;
   } else {
     GLF_TRY(flash_fwd(s.P, s.Y, s.lse, B, N, Ci, wf.attn, stream));
     {  // U = Y Wz^T + bz
@@ -319,9 +319,9 @@ GLF_API int glf_tpavi_fwd(const glf_desc* d, const void* x, const glf_weights* w
       g.bias = w->wz_b;
       g.D = s.U; g.ldd = C;
       g.colstats = (d->training && d->bn_layer) ? wf.colstats : nullptr;
+      g.colstats_rows = &np;
       GLF_TRY(gemm(g, stream));
     }
-    np = 4 * m.tiles_all;
   }
   const float* bn_part = wf.colstats;
   if (d->training && d->bn_layer && np > 4 * REDUCE_STAGE1_ROWS) {
@@ -376,7 +376,7 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
     GLF_TRY(bn_bwd_apply(wb.dV, s.U, GLF_DTYPE_BF16, wb.k1, wb.k2, wb.k3, wb.dU, m.rows, C, stream));
     dU = wb.dU;
   }
-  int np = 0;
+  int np = 0, np_p = 0, np_g = 0;
   if (m.dot) {
     const long long CiCi = static_cast<long long>(Ci) * Ci;
     const long long CCi = static_cast<long long>(C) * Ci;
@@ -387,6 +387,7 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
       g.M = N; g.N = Ci; g.K = C; g.batch = B;
       g.D = wb.dP; g.ldd = 3 * Ci; g.strideD = seqP;
       g.colstats = wb.cs_t;
+      g.colstats_rows = &np;
       GLF_TRY(gemm(g, stream));
     }
     {  // dW'_b[c,i] = sum_n dU[n,c] Theta[n,i]
@@ -434,6 +435,7 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
       g.alpha = 1.f / static_cast<float>(N);
       g.D = wb.dP + Ci; g.ldd = 3 * Ci; g.strideD = seqP;
       g.colstats = wb.cs_p;
+      g.colstats_rows = &np_p;
       GLF_TRY(gemm(g, stream));
     }
     {  // dG_b = Phi_b dM_b / N          (B operand = dM_b read MN-major)
@@ -444,9 +446,10 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
       g.alpha = 1.f / static_cast<float>(N);
       g.D = wb.dP + 2 * Ci; g.ldd = 3 * Ci; g.strideD = seqP;
       g.colstats = wb.cs_g;
+      g.colstats_rows = &np_g;
       GLF_TRY(gemm(g, stream));
     }
-    np = 4 * B * m.tiles_seq;
+    if (np_p != np || np_g != np) return set_error(GLF_ERR_INVALID, "internal: column-stat tables disagree");
   } else {
     {  // dY = dU Wz
       GemmArgs g;
@@ -467,8 +470,8 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
       g.split_k = pick_split(static_cast<long long>((C + 127) / 128) * ((Ci + 127) / 128), rows);
       GLF_TRY(gemm(g, stream));
     }
-    GLF_TRY(flash_bwd(s.P, s.Y, wb.dY, s.lse, wb.dP, wb.delta, wb.cs_t, wb.cs_p, wb.cs_g, B, N, Ci, wb.attn, stream));
-    np = 4 * B * m.tiles_seq;
+    GLF_TRY(flash_bwd(s.P, s.Y, wb.dY, s.lse, wb.dP, wb.delta, wb.cs_t, wb.cs_p, wb.cs_g, &np, B, N, Ci, wb.attn,
+                      stream));
   }
   GLF_TRY(check_cuda(cudaMemsetAsync(wb.dwcat, 0, sizeof(float) * 3 * Ci * C, stream), "memset dWcat"));
   {  // dWcat[r,c] = sum_n dP[n,r] X[n,c]

@@ -152,7 +152,7 @@ int flash_fwd(const bf16* P3, bf16* Y, float* lse, int B, int N, int Ci, void* s
 }
 
 int flash_bwd(const bf16* P3, const bf16* Y, const bf16* dY, const float* lse, bf16* dP3, float* delta, float* cs_t,
-              float* cs_p, float* cs_g, int B, int N, int Ci, void* scratch, cudaStream_t stream) {
+              float* cs_p, float* cs_g, int* cs_rows_out, int B, int N, int Ci, void* scratch, cudaStream_t stream) {
   const int ld = attn_ld(N);
   const int nb = attn_chunk(B, N);
   const size_t per = static_cast<size_t>(ld) * N;
@@ -162,7 +162,7 @@ int flash_bwd(const bf16* P3, const bf16* Y, const bf16* dY, const float* lse, b
   bf16* dS = Pm + nb * per;
   const long long seqP = static_cast<long long>(N) * 3 * Ci;
   const long long rows = static_cast<long long>(B) * N;
-  const int tiles_seq = gemm_tiles_m(N);
+  int cs_rows_total = 0;   // rows of the three column-stat tables written so far (same for all three)
   {
     const long long threads = rows * 32;
     rowdot_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(dY, Y, delta, rows, Ci);
@@ -174,7 +174,8 @@ int flash_bwd(const bf16* P3, const bf16* Y, const bf16* dY, const float* lse, b
     const bf16* Pb = P3 + b0 * seqP;
     const bf16* dYb = dY + static_cast<long long>(b0) * N * Ci;
     bf16* dPb = dP3 + b0 * seqP;
-    const long long cs_off = static_cast<long long>(b0) * tiles_seq * 4 * 2 * Ci;   // 4 row-quarter partials per tile
+    const long long cs_off = static_cast<long long>(cs_rows_total) * 2 * Ci;
+    int r_t = 0, r_p = 0, r_g = 0;
     int rc;
     {  // S = Theta Phi^T (recompute)
       GemmArgs g;
@@ -220,6 +221,7 @@ int flash_bwd(const bf16* P3, const bf16* Y, const bf16* dY, const float* lse, b
       g.M = N; g.N = Ci; g.K = N; g.batch = cb;
       g.D = dPb; g.ldd = 3 * Ci; g.strideD = seqP;
       g.colstats = cs_t + cs_off;
+      g.colstats_rows = &r_t;
       if ((rc = gemm(g, stream))) return rc;
     }
     {  // dPhi = dS^T Theta
@@ -229,6 +231,7 @@ int flash_bwd(const bf16* P3, const bf16* Y, const bf16* dY, const float* lse, b
       g.M = N; g.N = Ci; g.K = N; g.batch = cb;
       g.D = dPb + Ci; g.ldd = 3 * Ci; g.strideD = seqP;
       g.colstats = cs_p + cs_off;
+      g.colstats_rows = &r_p;
       if ((rc = gemm(g, stream))) return rc;
     }
     {  // dG = P^T dY
@@ -238,9 +241,13 @@ int flash_bwd(const bf16* P3, const bf16* Y, const bf16* dY, const float* lse, b
       g.M = N; g.N = Ci; g.K = N; g.batch = cb;
       g.D = dPb + 2 * Ci; g.ldd = 3 * Ci; g.strideD = seqP;
       g.colstats = cs_g + cs_off;
+      g.colstats_rows = &r_g;
       if ((rc = gemm(g, stream))) return rc;
     }
+    if (r_p != r_t || r_g != r_t) return set_error(GLF_ERR_INVALID, "internal: column-stat tables disagree");
+    cs_rows_total += r_t;
   }
+  *cs_rows_out = cs_rows_total;
   return 0;
 }
 

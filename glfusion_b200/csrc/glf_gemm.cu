@@ -44,6 +44,7 @@ struct GemmKParams {
   const bf16* addend;
   long long ld_add, stride_add;
   float* colstats;
+  int cs_accum;   // 1: column statistics accumulated per CTA over all its tiles (table rows = gridDim.x * 4)
   int tiles_m, tiles_n;
 };
 
@@ -202,6 +203,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     uint8_t* wstg = epi_smem + ew * (Cfg::WARP_STG + Cfg::WARP_BIAS);
     float* wbias = reinterpret_cast<float*>(wstg + Cfg::WARP_STG);
     const int sw_w = (lane >> 1) & 3;          // swizzle of the row this lane WRITES (row = lane)
+    // per-CTA column-statistics accumulators: slot = n_tile * chunks_per_warp + chunk iteration (<= CS_SLOTS)
+    constexpr int CS_SLOTS = 4;
+    constexpr int CPW = (NCHUNK + 3) / 4;      // chunks per warp per tile
+    float cs1[CS_SLOTS], cs2[CS_SLOTS];
+#pragma unroll
+    for (int i = 0; i < CS_SLOTS; ++i) cs1[i] = cs2[i] = 0.f;
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int z = tile / tiles_mn, mn = tile % tiles_mn;
@@ -275,7 +282,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             s1 += x;
             s2 = fmaf(x, x, s2);
           }
-          if (gc0 + lane < p.N) {
+          if (p.cs_accum) {
+            const int slot = (mn % p.tiles_n) * CPW + (c >> 2);
+#pragma unroll
+            for (int i = 0; i < CS_SLOTS; ++i) {
+              if (i == slot) {
+                cs1[i] += s1;
+                cs2[i] += s2;
+              }
+            }
+          } else if (gc0 + lane < p.N) {
             float* cs = p.colstats + ((static_cast<long long>(b) * p.tiles_m + m_tile) * 4 + q) * 2 * p.N;
             cs[gc0 + lane] = s1;
             cs[p.N + gc0 + lane] = s2;
@@ -319,6 +335,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       if (cc0 >= NCHUNK) {                       // warps without a chunk (BN = 64) still release the accumulator
         tc_fence_before();
         mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+      }
+    }
+    if (p.colstats != nullptr && p.cs_accum && cc0 < NCHUNK) {
+      // one partial row per (CTA, row quarter); every column owned by this warp is written, seen or not
+      float* cs = p.colstats + (static_cast<long long>(blockIdx.x) * 4 + q) * 2 * p.N;
+#pragma unroll
+      for (int i = 0; i < CS_SLOTS; ++i) {
+        const int nt = i / CPW, k = i % CPW;
+        const int col = nt * BN + (cc0 + 4 * k) * 32 + lane;
+        if (nt < p.tiles_n && cc0 + 4 * k < NCHUNK && col < p.N) {
+          cs[col] = cs1[i];
+          cs[p.N + col] = cs2[i];
+        }
       }
     }
   }
@@ -374,7 +403,8 @@ int make_operand_map(CUtensorMap* tm, const GemmOperand& op, int rows, int K, in
 }
 
 template <bool A_MN, bool B_MN, int BN>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKParams p, int num_sms, cudaStream_t stream) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKParams p, int num_sms, int* cs_rows,
+           cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_kernel<A_MN, B_MN, BN>;
   // per launch: the attribute is per device, and callers may drive several GPUs from one process (nn.DataParallel)
@@ -384,17 +414,21 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKParams p, int nu
   const long long total = static_cast<long long>(p.tiles_m) * p.tiles_n * p.batch * p.split_k;
   if (total > 0x7fffffffLL) return set_error(GLF_ERR_INVALID, "gemm: too many tiles");
   const int grid = static_cast<int>(total < num_sms ? total : num_sms);
+  // column statistics: running sums per CTA when the (n-tile, chunk) slots fit the register accumulators
+  p.cs_accum = (p.colstats != nullptr && p.tiles_n * ((BN / 32 + 3) / 4) <= 4) ? 1 : 0;
+  if (cs_rows != nullptr)
+    *cs_rows = p.colstats == nullptr ? 0 : (p.cs_accum ? grid * 4 : p.batch * p.tiles_m * 4);
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   return check_cuda(cudaGetLastError(), "gemm launch");
 }
 
 template <int BN>
 int launch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
-                 int num_sms, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch<false, false, BN>(tmA, tmB, p, num_sms, stream);
-  if (a_mn && b_mn) return launch<true, true, BN>(tmA, tmB, p, num_sms, stream);
-  if (a_mn) return launch<true, false, BN>(tmA, tmB, p, num_sms, stream);
-  return launch<false, true, BN>(tmA, tmB, p, num_sms, stream);
+                 int num_sms, int* cs_rows, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch<false, false, BN>(tmA, tmB, p, num_sms, cs_rows, stream);
+  if (a_mn && b_mn) return launch<true, true, BN>(tmA, tmB, p, num_sms, cs_rows, stream);
+  if (a_mn) return launch<true, false, BN>(tmA, tmB, p, num_sms, cs_rows, stream);
+  return launch<false, true, BN>(tmA, tmB, p, num_sms, cs_rows, stream);
 }
 
 }  // namespace
@@ -442,6 +476,7 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
   p.D = a.D; p.ldd = a.ldd; p.strideD = a.strideD;
   p.addend = a.addend; p.ld_add = a.ld_add; p.stride_add = a.stride_add;
   p.colstats = a.colstats;
+  p.cs_accum = 0;
   p.tiles_m = gemm_tiles_m(a.M);
   p.tiles_n = 0;  // set per tile shape in launch()
   int dev = 0, num_sms = 0;
@@ -450,9 +485,9 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
     return set_error(GLF_ERR_DEVICE, "gemm: cannot query the SM count");
   const bool amn = a.A.mn_major != 0, bmn = a.B.mn_major != 0;
   switch (BN) {
-    case 64: return launch_major<64>(amn, bmn, tmA, tmB, p, num_sms, stream);
-    case 128: return launch_major<128>(amn, bmn, tmA, tmB, p, num_sms, stream);
-    default: return launch_major<256>(amn, bmn, tmA, tmB, p, num_sms, stream);
+    case 64: return launch_major<64>(amn, bmn, tmA, tmB, p, num_sms, a.colstats_rows, stream);
+    case 128: return launch_major<128>(amn, bmn, tmA, tmB, p, num_sms, a.colstats_rows, stream);
+    default: return launch_major<256>(amn, bmn, tmA, tmB, p, num_sms, a.colstats_rows, stream);
   }
 }
 

@@ -35,7 +35,8 @@ struct GemmArgs {
   int64_t ldd = 0, strideD = 0;
   const bf16* addend = nullptr;     // optional bf16 [M, N] added in the epilogue (out_kind 0 only)
   int64_t ld_add = 0, stride_add = 0;
-  float* colstats = nullptr;        // [batch*tiles_m][2][N]
+  float* colstats = nullptr;        // partial table, sized for [batch*tiles_m*4][2][N]; rows actually written:
+  int* colstats_rows = nullptr;     //   <- returned here (per-CTA running sums shrink it to 4 * gridDim.x rows)
   int split_k = 1;
   int bn_hint = 0;                  // 0 = heuristic, else force the N tile (64 / 128 / 256)
   int npairs = 1;                   // limb products accumulated into one tile: sum_p A[pairA[p]] * B[pairB[p]]^T
@@ -95,7 +96,7 @@ int attn_chunk(long long B, long long N);
 size_t attn_scratch_bytes(long long B, long long N, bool backward);
 int flash_fwd(const bf16* P, bf16* Y, float* lse, int B, int N, int Ci, void* scratch, cudaStream_t stream);
 int flash_bwd(const bf16* P, const bf16* Y, const bf16* dY, const float* lse, bf16* dP, float* delta, float* cs_t,
-              float* cs_p, float* cs_g, int B, int N, int Ci, void* scratch, cudaStream_t stream);
+              float* cs_p, float* cs_g, int* cs_rows_out, int B, int N, int Ci, void* scratch, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------ F32X3 precision arm
 int tpavi_sizes_f32x3(const glf_desc* d, glf_sizes* out);

@@ -138,8 +138,9 @@ GLF_API int glf_gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, flo
  *   A: M x K, B: N x K.  a_mn / b_mn = 0: operand stored K-contiguous ([rows, K], leading dim ld);
  *                                     = 1: operand stored MN-contiguous ([K, rows], leading dim ld).
  *   out_kind 0: bf16 store, 1: fp32 store, 2: fp32 atomic add (split_k > 1 requires 2).
- *   colstats (optional): per (batch, m-tile, 32-row quarter) partial column sums / sums of squares of the stored
- *                        values, layout [batch * ceil(M/128) * 4][2][N] fp32.
+ *   colstats (optional): table of partial column sums / sums of squares of the stored values over ALL rows of ALL
+ *                        batch entries: zero it, size it [batch * ceil(M/128) * 4][2][N] fp32, and sum its rows (the
+ *                        kernel writes one row per (CTA, 32-row quarter) or per (tile, quarter)).
  *   batch strides in elements; strideB = 0 shares B across the batch. */
 GLF_API int glf_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int batch, int a_mn, int b_mn,
                   int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
