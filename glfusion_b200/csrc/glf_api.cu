@@ -326,7 +326,8 @@ GLF_API int glf_tpavi_fwd(const glf_desc* d, const void* x, const glf_weights* w
   const float* bn_part = wf.colstats;
   if (d->training && d->bn_layer && np > 4 * REDUCE_STAGE1_ROWS) {
     long long rs = 2LL * C;
-    GLF_TRY(reduce_stage1(wf.colstats, nullptr, nullptr, 1, &np, &rs, C, 2, C, wf.red1, stream));
+    const int np_in[1] = {np};
+    GLF_TRY(reduce_stage1(wf.colstats, nullptr, nullptr, 1, np_in, &np, &rs, C, 2, C, wf.red1, stream));
     bn_part = wf.red1;
   }
   GLF_TRY(bn_finalize(bn_part, np, C, static_cast<double>(m.rows), d, w, s.bn_mean, s.bn_rstd, s.bn_a, s.bn_b,
@@ -449,7 +450,6 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
       g.colstats_rows = &np_g;
       GLF_TRY(gemm(g, stream));
     }
-    if (np_p != np || np_g != np) return set_error(GLF_ERR_INVALID, "internal: column-stat tables disagree");
   } else {
     {  // dY = dU Wz
       GemmArgs g;
@@ -472,6 +472,7 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
     }
     GLF_TRY(flash_bwd(s.P, s.Y, wb.dY, s.lse, wb.dP, wb.delta, wb.cs_t, wb.cs_p, wb.cs_g, &np, B, N, Ci, wb.attn,
                       stream));
+    np_p = np_g = np;
   }
   GLF_TRY(check_cuda(cudaMemsetAsync(wb.dwcat, 0, sizeof(float) * 3 * Ci * C, stream), "memset dWcat"));
   {  // dWcat[r,c] = sum_n dP[n,r] X[n,c]
@@ -498,15 +499,13 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
     GLF_TRY(gemm(g, stream));
   }
   {  // bias gradients = column sums of dTheta / dPhi / dG, from the per-sub-block partials of their GEMM epilogues
+    // the three tables can have different row counts (tile shape and grid differ per product): stage 1 always
     long long rs = 2LL * Ci;
-    const float *t0 = wb.cs_t, *t1 = wb.cs_p, *t2 = wb.cs_g;
-    if (np > 4 * REDUCE_STAGE1_ROWS) {
-      GLF_TRY(reduce_stage1(wb.cs_t, wb.cs_p, wb.cs_g, 3, &np, &rs, 0, 1, Ci, wb.red1, stream));
-      t0 = wb.red1;
-      t1 = wb.red1 + static_cast<long long>(REDUCE_STAGE1_ROWS) * Ci;
-      t2 = wb.red1 + 2LL * REDUCE_STAGE1_ROWS * Ci;
-    }
-    GLF_TRY(reduce_partials3(t0, t1, t2, np, rs, Ci, g_->theta_b, g_->phi_b, g_->g_b, stream));
+    const int np_in[3] = {np, np_p, np_g};
+    GLF_TRY(reduce_stage1(wb.cs_t, wb.cs_p, wb.cs_g, 3, np_in, &np, &rs, 0, 1, Ci, wb.red1, stream));
+    GLF_TRY(reduce_partials3(wb.red1, wb.red1 + static_cast<long long>(REDUCE_STAGE1_ROWS) * Ci,
+                             wb.red1 + 2LL * REDUCE_STAGE1_ROWS * Ci, np, rs, Ci, g_->theta_b, g_->phi_b, g_->g_b,
+                             stream));
   }
   if (m.pack_x) {
     if (d->x_layout == GLF_LAYOUT_NCTHW)

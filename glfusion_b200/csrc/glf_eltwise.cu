@@ -156,14 +156,16 @@ __device__ __forceinline__ void reduce_partial_rows(const float* __restrict__ pa
 struct Stage1 {
   const float* part[3];
   float* out[3];          // [G][NS][C]
+  int np[3];              // rows of each table
 };
 template <int NS>
 __global__ void __launch_bounds__(32 * RED_Y)
-    reduce_stage1_kernel(const Stage1 t, int np, long long row_stride, long long stat_stride, int C, int G) {
+    reduce_stage1_kernel(const Stage1 t, long long row_stride, long long stat_stride, int C, int G) {
   __shared__ double sm[NS][RED_Y][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const bool cact = c < C;
   const int g = blockIdx.y;
+  const int np = t.np[blockIdx.z];
   const int chunk = (np + G - 1) / G;
   const int r0 = g * chunk;
   const int cnt = max(0, min(np, r0 + chunk) - r0);
@@ -725,16 +727,17 @@ int prep_weights(const glf_weights* w, int C, int Ci, bf16* wcat, bf16* wcatT, f
 }
 
 // stage-1 launcher: returns the reduced table (in `scratch`) and its row count through *np
-int reduce_stage1(const float* p0, const float* p1, const float* p2, int ntab, int* np, long long* row_stride,
-                  long long stat_stride, int NS, int C, float* scratch, cudaStream_t stream) {
+int reduce_stage1(const float* p0, const float* p1, const float* p2, int ntab, const int* np_in, int* np,
+                  long long* row_stride, long long stat_stride, int NS, int C, float* scratch, cudaStream_t stream) {
   const int G = REDUCE_STAGE1_ROWS;
   Stage1 t;
   const long long tab = static_cast<long long>(G) * NS * C;
   t.part[0] = p0; t.part[1] = p1; t.part[2] = p2;
   t.out[0] = scratch; t.out[1] = scratch + tab; t.out[2] = scratch + 2 * tab;
+  for (int i = 0; i < 3; ++i) t.np[i] = i < ntab ? np_in[i] : 0;
   dim3 grid((C + 31) / 32, G, ntab);
-  if (NS == 1) reduce_stage1_kernel<1><<<grid, dim3(32, RED_Y), 0, stream>>>(t, *np, *row_stride, stat_stride, C, G);
-  else reduce_stage1_kernel<2><<<grid, dim3(32, RED_Y), 0, stream>>>(t, *np, *row_stride, stat_stride, C, G);
+  if (NS == 1) reduce_stage1_kernel<1><<<grid, dim3(32, RED_Y), 0, stream>>>(t, *row_stride, stat_stride, C, G);
+  else reduce_stage1_kernel<2><<<grid, dim3(32, RED_Y), 0, stream>>>(t, *row_stride, stat_stride, C, G);
   *np = G;
   *row_stride = static_cast<long long>(NS) * C;
   return check_cuda(cudaGetLastError(), "reduce_stage1 launch");

@@ -415,7 +415,9 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKParams p, int nu
   if (total > 0x7fffffffLL) return set_error(GLF_ERR_INVALID, "gemm: too many tiles");
   const int grid = static_cast<int>(total < num_sms ? total : num_sms);
   // column statistics: running sums per CTA when the (n-tile, chunk) slots fit the register accumulators
-  p.cs_accum = (p.colstats != nullptr && p.tiles_n * ((BN / 32 + 3) / 4) <= 4) ? 1 : 0;
+  // (and the 4 * grid rows fit the documented table capacity of 4 * batch * tiles_m rows)
+  p.cs_accum = (p.colstats != nullptr && p.tiles_n * ((BN / 32 + 3) / 4) <= 4 &&
+                grid <= static_cast<long long>(p.batch) * p.tiles_m) ? 1 : 0;
   if (cs_rows != nullptr)
     *cs_rows = p.colstats == nullptr ? 0 : (p.cs_accum ? grid * 4 : p.batch * p.tiles_m * 4);
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);

@@ -72,8 +72,8 @@ int colstats_f32(const float* A, float* part, long long rows, int C, cudaStream_
 int prep_weights_f32(const glf_weights* w, int C, int Ci, float* wcat, float* wcatT, float* bcat, cudaStream_t stream);
 // Two-stage reductions: stage 1 shrinks a table of `np` partial rows to REDUCE_STAGE1_ROWS rows (parallel, fixed order).
 constexpr int REDUCE_STAGE1_ROWS = 64;
-int reduce_stage1(const float* p0, const float* p1, const float* p2, int ntab, int* np, long long* row_stride,
-                  long long stat_stride, int NS, int C, float* scratch, cudaStream_t stream);
+int reduce_stage1(const float* p0, const float* p1, const float* p2, int ntab, const int* np_in, int* np,
+                  long long* row_stride, long long stat_stride, int NS, int C, float* scratch, cudaStream_t stream);
 int reduce_partials(const float* part, int np, long long stride, int n, float alpha, float* out, cudaStream_t stream);
 int reduce_partials3(const float* p0, const float* p1, const float* p2, int np, long long stride, int n, float* o0,
                      float* o1, float* o2, cudaStream_t stream);
