@@ -337,45 +337,30 @@ __global__ void __launch_bounds__(ROW_THREADS)
   }
 }
 
-// ------------------------------------------------------------------------------------------------ LN/BN bwd, TMA-staged
-// Same math as bn_res_ln_bwd_kernel, different data movement: warp 8 is a producer that streams row tiles of dZ, U and
-// X through an NSTG-deep shared-memory ring with 1-D bulk copies (cp.async.bulk + mbarrier complete_tx), the 8 compute
-// warps read their 16-byte slices from shared memory.  Bytes in flight are set by the ring (3 tiles x 2 CTAs per SM),
-// not by registers, which is what the register-staged version was short of (62 % of the HBM peak measured).
-constexpr int LNB_STAGES = 3;
-constexpr int LNB_THREADS = ROW_THREADS + 32;
+// ------------------------------------------------------------------------------------------------ BN + residual + LN bwd
+// From dZ: dV = dZp (gradient of the pre-LayerNorm sum, also the residual part of dX), and per-CTA partials of the
+// four per-channel reductions: d ln_w = sum dZ*xhat, d ln_b = sum dZ, d gamma = sum dV*uhat, d beta = sum dV.
 template <typename TI, typename TA>
-__global__ void __launch_bounds__(LNB_THREADS, 2)
-    bn_res_ln_bwd_tma_kernel(const TI* __restrict__ dZ, const TA* __restrict__ U, const TA* __restrict__ X,
-                             const float* __restrict__ bn_a, const float* __restrict__ bn_b,
-                             const float* __restrict__ bn_mean, const float* __restrict__ bn_rstd,
-                             const float* __restrict__ lw, const float* __restrict__ mu_i,
-                             const float* __restrict__ r_i, TA* __restrict__ dV, float* __restrict__ part,
-                             long long rows, int C, int S, int TR) {
-  extern __shared__ __align__(128) uint8_t lnb_smem[];
-  __shared__ uint64_t full_bar[LNB_STAGES];
-  __shared__ uint64_t empty_bar[LNB_STAGES];
+__global__ void __launch_bounds__(ROW_THREADS, 2)
+    bn_res_ln_bwd_kernel(const TI* __restrict__ dZ, const TA* __restrict__ U, const TA* __restrict__ X,
+                         const float* __restrict__ bn_a, const float* __restrict__ bn_b,
+                         const float* __restrict__ bn_mean, const float* __restrict__ bn_rstd,
+                         const float* __restrict__ lw, const float* __restrict__ mu_i, const float* __restrict__ r_i,
+                         TA* __restrict__ dV, float* __restrict__ part, long long rows, int C, int S) {
   __shared__ float red[2 * ROW_WARPS * 2];
+  // per-channel parameter vectors live in shared memory during the row loop (re-read with volatile 128-bit loads so
+  // that they do not occupy 40 registers); the same storage holds the accumulator exchange afterwards
   constexpr int ACC_PITCH = 32 * 8 + 8;
   constexpr int SM_FLOATS = (ROW_WARPS * 4 * ACC_PITCH > 5 * 2048) ? ROW_WARPS * 4 * ACC_PITCH : 5 * 2048;
-  float* smbuf = reinterpret_cast<float*>(lnb_smem);                       // parameter vectors, then accumulators
-  uint8_t* ring = lnb_smem + SM_FLOATS * sizeof(float);
-  const uint32_t dz_bytes = static_cast<uint32_t>(TR) * C * sizeof(TI);
-  const uint32_t a_bytes = static_cast<uint32_t>(TR) * C * sizeof(TA);
-  const uint32_t stage_bytes = dz_bytes + 2 * a_bytes;
+  __shared__ __align__(16) float smbuf[SM_FLOATS];
+  int buf = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long ntiles = (rows + TR - 1) / TR;
-
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < LNB_STAGES; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), ROW_WARPS);
-    }
-    fence_mbar_init();
-  }
+  const int RPB = ROW_WARPS / S;
+  const int rslot = warp / S, slice = warp % S;
+  const int c0 = slice * 256 + lane * 8;
+  const bool cact = c0 < C;
   const int Cs = S * 256;
-  for (int i = threadIdx.x; i < Cs; i += LNB_THREADS) {
+  for (int i = threadIdx.x; i < Cs; i += ROW_THREADS) {
     const bool in = i < C;
     smbuf[0 * Cs + i] = in ? bn_a[i] : 0.f;
     smbuf[1 * Cs + i] = in ? bn_b[i] : 0.f;
@@ -384,141 +369,105 @@ __global__ void __launch_bounds__(LNB_THREADS, 2)
     smbuf[4 * Cs + i] = in ? bn_rstd[i] : 0.f;
   }
   __syncthreads();
-
-  if (warp == ROW_WARPS) {
-    // ------------------------------------------------------------------ producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const long long r0 = t * TR;
-        const uint32_t nr = static_cast<uint32_t>(min(static_cast<long long>(TR), rows - r0));
-        const uint32_t fb = smem_u32(&full_bar[stage]);
-        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-        const uint32_t bz = nr * C * sizeof(TI), ba = nr * C * sizeof(TA);
-        mbar_expect_tx(fb, bz + 2 * ba);
-        const uint32_t dst = smem_u32(ring + static_cast<size_t>(stage) * stage_bytes);
-        bulk_load_1d(dst, dZ + r0 * C, bz, fb);
-        bulk_load_1d(dst + dz_bytes, U + r0 * C, ba, fb);
-        bulk_load_1d(dst + dz_bytes + a_bytes, X + r0 * C, ba, fb);
-        if (++stage == LNB_STAGES) {
-          stage = 0;
-          phase ^= 1u;
-        }
-      }
+  const float* sp = smbuf + c0;
+  float g_lw[8], g_lb[8], g_ga[8], g_be[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) g_lw[i] = g_lb[i] = g_ga[i] = g_be[i] = 0.f;
+  const float invC = 1.f / static_cast<float>(C);
+  const long long step = static_cast<long long>(gridDim.x) * RPB;
+  long long base = static_cast<long long>(blockIdx.x) * RPB;
+  Raw8<TA> xr = {}, ur = {};
+  Raw8<TI> zr = {};
+  float mu_n = 0.f, r_n = 0.f;
+  if (cact && base + rslot < rows) {
+    const long long row = base + rslot;
+    xr = ldraw(X + row * C + c0);
+    zr = ldraw(dZ + row * C + c0);
+    if (U != nullptr) ur = ldraw(U + row * C + c0);
+    mu_n = mu_i[row];
+    r_n = r_i[row];
+  }
+  for (; base < rows; base += step) {
+    const long long row = base + rslot;
+    const bool act = cact && row < rows;
+    const Raw8<TA> xc = xr, uc = ur;
+    const Raw8<TI> zc = zr;
+    const float mu = mu_n, r = r_n;
+    if (cact && row + step < rows) {
+      const long long nrow = row + step;
+      xr = ldraw(X + nrow * C + c0);
+      zr = ldraw(dZ + nrow * C + c0);
+      if (U != nullptr) ur = ldraw(U + nrow * C + c0);
+      mu_n = mu_i[nrow];
+      r_n = r_i[nrow];
     }
-  } else {
-    // ------------------------------------------------------------------ consumers (8 warps)
-    int buf = 0;
-    const int RPB = ROW_WARPS / S;
-    const int rslot = warp / S, slice = warp % S;
-    const int c0 = slice * 256 + lane * 8;
-    const bool cact = c0 < C;
-    const float* sp = smbuf + c0;
-    float g_lw[8], g_lb[8], g_ga[8], g_be[8];
+    float xh[8], dxh[8], dz[8], uh[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) g_lw[i] = g_lb[i] = g_ga[i] = g_be[i] = 0.f;
-    const float invC = 1.f / static_cast<float>(C);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      const long long r0 = t * TR;
-      mbar_wait(smem_u32(&full_bar[stage]), phase);
-      const uint8_t* st = ring + static_cast<size_t>(stage) * stage_bytes;
-      const TI* sZ = reinterpret_cast<const TI*>(st);
-      const TA* sU = reinterpret_cast<const TA*>(st + dz_bytes);
-      const TA* sX = reinterpret_cast<const TA*>(st + dz_bytes + a_bytes);
-      for (int rr = rslot; rr < TR; rr += RPB) {      // TR is a multiple of RPB: uniform trip count per CTA
-        const long long row = r0 + rr;
-        const bool act = cact && row < rows;
-        float xh[8], dxh[8], dz[8], uh[8];
+    for (int i = 0; i < 8; ++i) xh[i] = dxh[i] = dz[i] = uh[i] = 0.f;
+    if (act) {
+      float x[8];
+      cvt8(xc, x);
+      cvt8(zc, dz);
+      if (U != nullptr) {
+        float u[8], a[8], b[8];
+        cvt8(uc, u);
+        lds8v(sp, a);
+        lds8v(sp + Cs, b);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) xh[i] = dxh[i] = dz[i] = uh[i] = 0.f;
-        float r = 0.f;
-        if (act) {
-          const float mu = mu_i[row];
-          r = r_i[row];
-          float x[8], u[8], a[8], b[8];
-          load8(sX + rr * C + c0, x);
-          load8(sZ + rr * C + c0, dz);
-          load8(sU + rr * C + c0, u);
-          lds8v(sp, a);
-          lds8v(sp + Cs, b);
+        for (int i = 0; i < 8; ++i) xh[i] = (fmaf(a[i], u[i], b[i]) + x[i] - mu) * r;
+        lds8v(sp + 3 * Cs, a);
+        lds8v(sp + 4 * Cs, b);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) xh[i] = (fmaf(a[i], u[i], b[i]) + x[i] - mu) * r;
-          lds8v(sp + 3 * Cs, a);
-          lds8v(sp + 4 * Cs, b);
+        for (int i = 0; i < 8; ++i) uh[i] = (u[i] - a[i]) * b[i];
+      } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) uh[i] = (u[i] - a[i]) * b[i];
-          float w[8];
-          lds8v(sp + 2 * Cs, w);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) dxh[i] = dz[i] * w[i];
-        }
-        float s2[2] = {0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          s2[0] += dxh[i];
-          s2[1] = fmaf(dxh[i], xh[i], s2[1]);
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) s2[i] = warp_sum(s2[i]);
-        if (S > 1) {
-          float* rb = red + buf * (ROW_WARPS * 2);
-          if (lane == 0) {
-            rb[(rslot * S + slice) * 2 + 0] = s2[0];
-            rb[(rslot * S + slice) * 2 + 1] = s2[1];
-          }
-          named_bar_sync(1, ROW_THREADS);
-          float t0 = 0.f, t1 = 0.f;
-          for (int j = 0; j < S; ++j) {
-            t0 += rb[(rslot * S + j) * 2 + 0];
-            t1 += rb[(rslot * S + j) * 2 + 1];
-          }
-          s2[0] = t0;
-          s2[1] = t1;
-          buf ^= 1;
-        }
-        if (act) {
-          const float m1 = s2[0] * invC, m2 = s2[1] * invC;
-          float dv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            dv[i] = r * (dxh[i] - m1 - xh[i] * m2);
-            g_lw[i] = fmaf(dz[i], xh[i], g_lw[i]);
-            g_lb[i] += dz[i];
-            g_ga[i] = fmaf(dv[i], uh[i], g_ga[i]);
-            g_be[i] += dv[i];
-          }
-          store8(dV + row * C + c0, dv);
-        }
+        for (int i = 0; i < 8; ++i) xh[i] = (x[i] - mu) * r;
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));
-      if (++stage == LNB_STAGES) {
-        stage = 0;
-        phase ^= 1u;
-      }
+      float w[8];
+      lds8v(sp + 2 * Cs, w);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dxh[i] = dz[i] * w[i];
     }
-    // accumulator exchange over the row slots of this CTA (fixed order): one partial per CTA
-    named_bar_sync(1, ROW_THREADS);     // every consumer is done with the parameter vectors
-    float (*acc_sm)[4][ACC_PITCH] = reinterpret_cast<float (*)[4][ACC_PITCH]>(smbuf);
+    float s[2] = {0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      acc_sm[warp][0][lane * 8 + i] = g_lw[i];
-      acc_sm[warp][1][lane * 8 + i] = g_lb[i];
-      acc_sm[warp][2][lane * 8 + i] = g_ga[i];
-      acc_sm[warp][3][lane * 8 + i] = g_be[i];
+      s[0] += dxh[i];
+      s[1] = fmaf(dxh[i], xh[i], s[1]);
     }
-    named_bar_sync(1, ROW_THREADS);
-    for (int idx = threadIdx.x; idx < 4 * S * 256; idx += ROW_THREADS) {
-      const int stt = idx / (S * 256), cc = idx % (S * 256);
-      const int sl = cc / 256, ci = cc % 256;
-      if (cc < C) {
-        float tsum = 0.f;
-        for (int rs = 0; rs < RPB; ++rs) tsum += acc_sm[rs * S + sl][stt][ci];
-        part[(static_cast<long long>(blockIdx.x) * 4 + stt) * C + cc] = tsum;
+    row_reduce<2>(s, S, rslot, slice, red, buf);
+    if (act) {
+      const float m1 = s[0] * invC, m2 = s[1] * invC;
+      float dv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        dv[i] = r * (dxh[i] - m1 - xh[i] * m2);
+        g_lw[i] = fmaf(dz[i], xh[i], g_lw[i]);
+        g_lb[i] += dz[i];
+        g_ga[i] = fmaf(dv[i], uh[i], g_ga[i]);
+        g_be[i] += dv[i];
       }
+      store8(dV + row * C + c0, dv);
+    }
+  }
+  // reduce the accumulators over the row slots of this CTA (fixed order), write one partial per CTA
+  __syncthreads();  // every warp is done with the parameter vectors: reuse the storage
+  float (*acc_sm)[4][ACC_PITCH] = reinterpret_cast<float (*)[4][ACC_PITCH]>(smbuf);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc_sm[warp][0][lane * 8 + i] = g_lw[i];
+    acc_sm[warp][1][lane * 8 + i] = g_lb[i];
+    acc_sm[warp][2][lane * 8 + i] = g_ga[i];
+    acc_sm[warp][3][lane * 8 + i] = g_be[i];
+  }
+  __syncthreads();
+  // output index space: 4 stats x (S*256) channels
+  for (int idx = threadIdx.x; idx < 4 * S * 256; idx += ROW_THREADS) {
+    const int st = idx / (S * 256), cc = idx % (S * 256);
+    const int sl = cc / 256, ci = cc % 256;
+    if (cc < C) {
+      float t = 0.f;
+      for (int rs = 0; rs < RPB; ++rs) t += acc_sm[rs * S + sl][st][ci];
+      part[(static_cast<long long>(blockIdx.x) * 4 + st) * C + cc] = t;
     }
   }
 }
@@ -783,48 +732,27 @@ int bn_res_ln_bwd_blocks(long long rows, int C) {
   return g < 148 * 2 ? g : 148 * 2;
 }
 
-// rows per tile of the TMA-staged backward: ~8 KB per tensor per stage, a multiple of the rows processed per step
-int lnb_tile_rows(int C, int S, size_t act_size) {
-  const int RPB = ROW_WARPS / S;
-  int tr = static_cast<int>(8192 / (static_cast<size_t>(C) * act_size));
-  if (tr < RPB) tr = RPB;
-  tr = (tr / RPB) * RPB;
-  return tr;
-}
-
-template <typename TI, typename TA>
-int launch_lnb(const void* dZ, const void* U, const void* X, const float* a, const float* b, const float* mean,
-               const float* rstd, const float* lw, const float* mu, const float* r, void* dV, float* part,
-               long long rows, int C, int S, int grid, cudaStream_t stream) {
-  const int TR = lnb_tile_rows(C, S, sizeof(TA));
-  constexpr int ACC_PITCH = 32 * 8 + 8;
-  constexpr int SM_FLOATS = (ROW_WARPS * 4 * ACC_PITCH > 5 * 2048) ? ROW_WARPS * 4 * ACC_PITCH : 5 * 2048;
-  const size_t stage = static_cast<size_t>(TR) * C * (sizeof(TI) + 2 * sizeof(TA));
-  const size_t smem = SM_FLOATS * sizeof(float) + LNB_STAGES * stage + 128;
-  auto kern = bn_res_ln_bwd_tma_kernel<TI, TA>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(bn_res_ln_bwd)");
-  kern<<<grid, LNB_THREADS, smem, stream>>>((const TI*)dZ, (const TA*)U, (const TA*)X, a, b, mean, rstd, lw, mu, r,
-                                            (TA*)dV, part, rows, C, S, TR);
-  return check_cuda(cudaGetLastError(), "bn_res_ln_bwd launch");
-}
-
 int bn_res_ln_bwd(const void* dZ, int dz_dtype, const void* U_, const void* X_, int act_dtype, const float* a,
                   const float* b, const float* mean, const float* rstd, const float* lw, const float* mu,
                   const float* r, void* dV_, float* part, long long rows, int C, cudaStream_t stream) {
   if (C % 8 != 0 || C > 2048) return set_error(GLF_ERR_INVALID, "LayerNorm kernel needs C %% 8 == 0 and C <= 2048");
-  if (U_ == nullptr) return set_error(GLF_ERR_INVALID, "bn_res_ln_bwd: U is required");
   int S = (C + 255) / 256;
   while (ROW_WARPS % S != 0) ++S;
   const int grid = bn_res_ln_bwd_blocks(rows, C);
   if (act_dtype == GLF_DTYPE_BF16) {
+    const bf16* U = (const bf16*)U_; const bf16* X = (const bf16*)X_; bf16* dV = (bf16*)dV_;
     if (dz_dtype == GLF_DTYPE_BF16)
-      return launch_lnb<bf16, bf16>(dZ, U_, X_, a, b, mean, rstd, lw, mu, r, dV_, part, rows, C, S, grid, stream);
-    return launch_lnb<float, bf16>(dZ, U_, X_, a, b, mean, rstd, lw, mu, r, dV_, part, rows, C, S, grid, stream);
+      bn_res_ln_bwd_kernel<bf16, bf16><<<grid, ROW_THREADS, 0, stream>>>((const bf16*)dZ, U, X, a, b, mean, rstd, lw, mu, r, dV, part, rows, C, S);
+    else
+      bn_res_ln_bwd_kernel<float, bf16><<<grid, ROW_THREADS, 0, stream>>>((const float*)dZ, U, X, a, b, mean, rstd, lw, mu, r, dV, part, rows, C, S);
+  } else {
+    const float* U = (const float*)U_; const float* X = (const float*)X_; float* dV = (float*)dV_;
+    if (dz_dtype == GLF_DTYPE_BF16)
+      bn_res_ln_bwd_kernel<bf16, float><<<grid, ROW_THREADS, 0, stream>>>((const bf16*)dZ, U, X, a, b, mean, rstd, lw, mu, r, dV, part, rows, C, S);
+    else
+      bn_res_ln_bwd_kernel<float, float><<<grid, ROW_THREADS, 0, stream>>>((const float*)dZ, U, X, a, b, mean, rstd, lw, mu, r, dV, part, rows, C, S);
   }
-  if (dz_dtype == GLF_DTYPE_BF16)
-    return launch_lnb<bf16, float>(dZ, U_, X_, a, b, mean, rstd, lw, mu, r, dV_, part, rows, C, S, grid, stream);
-  return launch_lnb<float, float>(dZ, U_, X_, a, b, mean, rstd, lw, mu, r, dV_, part, rows, C, S, grid, stream);
+  return check_cuda(cudaGetLastError(), "bn_res_ln_bwd launch");
 }
 
 int bn_bwd_finalize(const float* part, int np, int C, double count, const glf_desc* d, const glf_weights* w,
