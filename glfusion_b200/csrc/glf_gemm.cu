@@ -15,6 +15,7 @@
 //                               squares) for the BatchNorm that follows W_z (ours.py:908).
 // Operands may be K-major ([rows, K]) or MN-major ([K, rows]); the latter is how the token-contraction products
 // (Phi^T G, dU^T Theta, dP^T X) read token-major activations without any transposed copy.
+#include <cstdlib>
 #include <mutex>
 
 #include "glf_internal.h"
@@ -44,6 +45,7 @@ struct GemmKParams {
   const bf16* addend;
   long long ld_add, stride_add;
   float* colstats;
+  unsigned mg_mn, mg_n, mg_sk;   // multiply-high magics for / tiles_mn, / tiles_n, / split_k
   int cs_accum;   // 1: column statistics accumulated per CTA over all its tiles (table rows = gridDim.x * 4)
   int tiles_m, tiles_n;
 };
@@ -58,12 +60,22 @@ struct GemmCfg {
   static constexpr uint32_t RING_BYTES = STAGES * STAGE_BYTES;
   static constexpr uint32_t WARP_STG = 32 * 64;     // warp-private 32 rows x 32 bf16, XOR-swizzled 16-byte chunks
   static constexpr uint32_t WARP_BIAS = 32 * 4;     // warp-private bias slice of the current 32-column chunk
-  static constexpr uint32_t EPI_BYTES = EPI_WARPS * (WARP_STG + WARP_BIAS);
+  static constexpr uint32_t BIAS_ALL = 4096 * 4;   // the whole bias vector (N <= 4096) is staged once per CTA
+  static constexpr uint32_t EPI_BYTES = EPI_WARPS * (WARP_STG + WARP_BIAS) + BIAS_ALL;
   static constexpr uint32_t SMEM_BYTES = RING_BYTES + EPI_BYTES + 1024;
   static constexpr uint32_t TMEM_COLS = 2 * BN;     // two accumulator stages
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(TMEM_COLS <= 512, "TMEM budget");
 };
+
+// n / d for a runtime-uniform d with magic = floor(2^32 / d): the estimate is q or q-1 for every n < 2^32, one
+// correction step makes it exact (d == 1 is special-cased: its magic does not fit 32 bits)
+__device__ __forceinline__ void fastdivmod(int n, int d, unsigned magic, int& q, int& r) {
+  q = static_cast<int>(__umulhi(static_cast<unsigned>(n), magic));
+  r = n - q * d;
+  if (r >= d) { ++q; r -= d; }
+  if (d == 1) { q = n; r = 0; }
+}
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -119,9 +131,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int z = tile / tiles_mn, mn = tile % tiles_mn;
-        const int m0 = (mn / p.tiles_n) * BM, n0 = (mn % p.tiles_n) * BN;
-        const int b = z / p.split_k, split = z % p.split_k;
+        int z, mn, mt, nt, b, split;
+        fastdivmod(tile, tiles_mn, p.mg_mn, z, mn);
+        fastdivmod(mn, p.tiles_n, p.mg_n, mt, nt);
+        fastdivmod(z, p.split_k, p.mg_sk, b, split);
+        const int m0 = mt * BM, n0 = nt * BN;
         const int ab = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
         const int kb0 = split * p.kb_per_split;
         const int niter = (min(p.kb_total, kb0 + p.kb_per_split) - kb0) * p.npairs;
@@ -161,8 +175,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       uint32_t phase = 0;
       int local = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-        const int z = tile / tiles_mn;
-        const int split = z % p.split_k;
+        int z, mn, b, split;
+        fastdivmod(tile, tiles_mn, p.mg_mn, z, mn);
+        fastdivmod(z, p.split_k, p.mg_sk, b, split);
         const int kb0 = split * p.kb_per_split;
         const int niter = (min(p.kb_total, kb0 + p.kb_per_split) - kb0) * p.npairs;
         const int acc = local & 1;
@@ -203,6 +218,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     uint8_t* wstg = epi_smem + ew * (Cfg::WARP_STG + Cfg::WARP_BIAS);
     float* wbias = reinterpret_cast<float*>(wstg + Cfg::WARP_STG);
     const int sw_w = (lane >> 1) & 3;          // swizzle of the row this lane WRITES (row = lane)
+    // the whole bias vector goes to shared memory once (epilogue warps only; named barrier 1)
+    float* ball = reinterpret_cast<float*>(epi_smem + EPI_WARPS * (Cfg::WARP_STG + Cfg::WARP_BIAS));
+    const bool bias_all = p.bias != nullptr && p.N <= 4096;
+    if (bias_all) {
+      for (int i = ew * 32 + lane; i < p.N; i += EPI_THREADS) ball[i] = p.bias[i];
+      named_bar_sync(1, EPI_THREADS);
+    }
     // per-CTA column-statistics accumulators: slot = n_tile * chunks_per_warp + chunk iteration (<= CS_SLOTS)
     constexpr int CS_SLOTS = 4;
     constexpr int CPW = (NCHUNK + 3) / 4;      // chunks per warp per tile
@@ -211,10 +233,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     for (int i = 0; i < CS_SLOTS; ++i) cs1[i] = cs2[i] = 0.f;
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-      const int z = tile / tiles_mn, mn = tile % tiles_mn;
-      const int m_tile = mn / p.tiles_n;
-      const int m0 = m_tile * BM, n0 = (mn % p.tiles_n) * BN;
-      const int b = z / p.split_k, split = z % p.split_k;
+      int z, mn, m_tile, nt, b, split;
+      fastdivmod(tile, tiles_mn, p.mg_mn, z, mn);
+      fastdivmod(mn, p.tiles_n, p.mg_n, m_tile, nt);
+      fastdivmod(z, p.split_k, p.mg_sk, b, split);
+      const int m0 = m_tile * BM, n0 = nt * BN;
       const int acc = local & 1;
       const uint32_t use = static_cast<uint32_t>(local >> 1);
       const int grow = m0 + q * 32 + lane;
@@ -227,7 +250,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const int gc0 = n0 + c * 32;           // first global column of this chunk
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
-        if (use_bias) wbias[lane] = (gc0 + lane < p.N) ? p.bias[gc0 + lane] : 0.f;
+        if (use_bias && !bias_all) wbias[lane] = (gc0 + lane < p.N) ? p.bias[gc0 + lane] : 0.f;
         tmem_ld_wait();
         if (c + 4 >= NCHUNK) {                 // last TMEM read of this warp for the tile: release the accumulator
           tc_fence_before();
@@ -235,12 +258,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         }
         __syncwarp();
         float f[32];
+        if (p.alpha != 1.f) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        }
         if (use_bias) {
+          // full chunks read the CTA-wide copy; a ragged last chunk (N not a multiple of 32) uses the zero-padded
+          // warp-private slice
+          const float* bsrc = (bias_all && gc0 + 32 <= p.N) ? ball + gc0 : wbias;
+          if (bias_all && gc0 + 32 > p.N) {
+            wbias[lane] = (gc0 + lane < p.N) ? ball[gc0 + lane] : 0.f;
+            __syncwarp();
+          }
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 bv = *reinterpret_cast<const float4*>(wbias + j);
+            const float4 bv = *reinterpret_cast<const float4*>(bsrc + j);
             f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
           }
         }
@@ -283,7 +318,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             s2 = fmaf(x, x, s2);
           }
           if (p.cs_accum) {
-            const int slot = (mn % p.tiles_n) * CPW + (c >> 2);
+            const int slot = nt * CPW + (c >> 2);
 #pragma unroll
             for (int i = 0; i < CS_SLOTS; ++i) {
               if (i == slot) {
@@ -416,6 +451,10 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKParams p, int nu
   const int grid = static_cast<int>(total < num_sms ? total : num_sms);
   // column statistics: running sums per CTA when the (n-tile, chunk) slots fit the register accumulators
   // (and the 4 * grid rows fit the documented table capacity of 4 * batch * tiles_m rows)
+  auto magic = [](long long d) { return d <= 1 ? 0u : static_cast<unsigned>((1ULL << 32) / static_cast<unsigned long long>(d)); };
+  p.mg_mn = magic(static_cast<long long>(p.tiles_m) * p.tiles_n);
+  p.mg_n = magic(p.tiles_n);
+  p.mg_sk = magic(p.split_k);
   p.cs_accum = (p.colstats != nullptr && p.tiles_n * ((BN / 32 + 3) / 4) <= 4 &&
                 grid <= static_cast<long long>(p.batch) * p.tiles_m) ? 1 : 0;
   if (cs_rows != nullptr)
@@ -450,6 +489,10 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
   // loads.  Large-K (tensor-bound, e.g. C=2048) products take the 128x256 tile.
   int BN = (a.N <= 64) ? 64 : ((a.K >= 512 && a.N % 256 == 0) ? 256 : 128);
   if (a.bn_hint == 64 || a.bn_hint == 128 || a.bn_hint == 256) BN = a.bn_hint;
+  if (const char* e = getenv("GLF_DEBUG_BN")) {  // tuning aid: force the N tile of K-major x K-major products
+    const int v = atoi(e);
+    if ((v == 128 || v == 256) && a.N > 64 && !a.A.mn_major) BN = v;
+  }
   int nlimbsA = 1, nlimbsB = 1;
   for (int i = 0; i < a.npairs; ++i) {
     nlimbsA = a.pairA[i] + 1 > nlimbsA ? a.pairA[i] + 1 : nlimbsA;
