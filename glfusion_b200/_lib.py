@@ -17,7 +17,7 @@ PRECISIONS = {"bf16": PRECISION_BF16, "fp32": PRECISION_F32X3}
 
 EXPORTS = ("glf_version", "glf_last_error", "glf_tpavi_sizes", "glf_tpavi_fwd", "glf_tpavi_bwd",
            "glf_gate_concat_fwd", "glf_gate_concat_bwd", "glf_gemm_bf16", "glf_transpose", "glf_bn_res_ln_fwd",
-           "glf_bn_res_ln_bwd", "glf_bn_res_ln_bwd_max_blocks")
+           "glf_bn_res_ln_bwd", "glf_bn_res_ln_bwd_max_blocks", "glf_gate_concat_bwd_scratch_bytes")
 
 
 class GlfDesc(C.Structure):
@@ -68,7 +68,9 @@ def load() -> C.CDLL:
                                       vp, vp]
         pp = C.POINTER(C.c_void_p)
         lib.glf_gate_concat_fwd.argtypes = [i32] * 6 + [f32, i32, i32, pp, pp, pp, vp, vp, vp, vp]
-        lib.glf_gate_concat_bwd.argtypes = [i32] * 6 + [f32, i32, i32, pp, pp, pp, vp, vp, vp, pp, pp, pp, vp]
+        lib.glf_gate_concat_bwd.argtypes = [i32] * 6 + [f32, i32, i32, pp, pp, pp, vp, vp, vp, pp, pp, pp, vp, vp]
+        lib.glf_gate_concat_bwd_scratch_bytes.argtypes = [i32] * 5
+        lib.glf_gate_concat_bwd_scratch_bytes.restype = C.c_size_t
         lib.glf_gemm_bf16.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, vp, f32,
                                       vp, i64, i64, i32, i32, vp, vp]
         lib.glf_transpose.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
@@ -78,7 +80,7 @@ def load() -> C.CDLL:
         lib.glf_bn_res_ln_bwd_max_blocks.argtypes = []
         for name in EXPORTS:
             fn = getattr(lib, name)
-            if name not in ("glf_last_error",):
+            if name not in ("glf_last_error", "glf_gate_concat_bwd_scratch_bytes"):
                 fn.restype = C.c_int
         _lib = lib
         return lib

@@ -531,7 +531,7 @@ GLF_API int glf_gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, flo
 GLF_API int glf_gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, int x_dtype,
                         const void* const* f4, const float* const* cls, const float* const* ctr, const float* gate,
                         const void* dxg, const void* dxl, void* const* df4, float* const* dcls, float* const* dctr,
-                        glf_stream_t stream) {
+                        void* scratch, glf_stream_t stream) {
   GLF_TRY(check_device_sm100());
   if (B <= 0 || C <= 0 || h <= 0 || w <= 0 || ncls <= 0) return set_error(GLF_ERR_INVALID, "gate_concat: empty input");
   if (f4 == nullptr || cls == nullptr || ctr == nullptr || df4 == nullptr || dcls == nullptr || dctr == nullptr)
@@ -539,7 +539,11 @@ GLF_API int glf_gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, flo
   GLF_TRY(check_ptr(dxg, "dxg"));
   GLF_TRY(check_ptr(dxl, "dxl"));
   return gate_concat_bwd(B, C, V, h, w, ncls, weight, io_dtype, x_dtype, f4, cls, ctr, gate, dxg, dxl, df4, dcls, dctr,
-                         reinterpret_cast<cudaStream_t>(stream));
+                         reinterpret_cast<float*>(scratch), reinterpret_cast<cudaStream_t>(stream));
+}
+
+GLF_API size_t glf_gate_concat_bwd_scratch_bytes(int B, int C, int V, int h, int w) {
+  return gate_bwd_scratch_bytes(B, C, V, h, w);
 }
 
 GLF_API int glf_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int batch, int a_mn, int b_mn,

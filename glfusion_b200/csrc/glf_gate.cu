@@ -124,17 +124,19 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// grid: (ceil(hw/64), B*V) ; block 256 ; loops over channel tiles so the gate gradient needs no atomics
+// grid: (ceil(hw/64), ceil(C/64), B*V) ; block 256.  Each block handles one 64-position x 64-channel tile:
+// df4 = dXg + a * dXl back to NCHW, and its partial of the gate gradient da[p] = sum_c f4[c,p] * dXl[p,c], written to
+// da_part[c_tile][b,v,p] (reduced in fixed order by gate_finish_kernel: deterministic, no atomics).
 template <typename TIO, int VEC, typename TX>
 __global__ void __launch_bounds__(256)
     gate_concat_bwd_kernel(const ViewPtrs vp, const float* __restrict__ gate, const TX* __restrict__ dxg,
-                           const TX* __restrict__ dxl, int C, int V, int hw, int ncls, float weight) {
+                           const TX* __restrict__ dxl, float* __restrict__ da_part, int C, int V, int hw) {
   __shared__ float tg[64][65];
   __shared__ float tl[64][65];
   __shared__ float a_sm[64];
   __shared__ float da_sm[8][64];
-  const int bv = blockIdx.y, b = bv / V, v = bv % V;
-  const int p0 = blockIdx.x * 64;
+  const int bv = blockIdx.z, b = bv / V, v = bv % V;
+  const int p0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
   const TIO* f4 = reinterpret_cast<const TIO*>(vp.f4[v]) + static_cast<long long>(b) * C * hw;
   TIO* df4 = reinterpret_cast<TIO*>(vp.df4[v]) + static_cast<long long>(b) * C * hw;
   if (threadIdx.x < 64) {
@@ -145,10 +147,24 @@ __global__ void __launch_bounds__(256)
   const int tx = VEC == 2 ? (threadIdx.x & 31) : (threadIdx.x & 63);
   const int ty = VEC == 2 ? (threadIdx.x >> 5) : (threadIdx.x >> 6);
   constexpr int NY = VEC == 2 ? 8 : 4;
-  float da0 = 0.f, da1 = 0.f;
-  for (int c0 = 0; c0 < C; c0 += 64) {
-    __syncthreads();
+  // issue the NCHW-side f4 loads first: they do not depend on shared memory
+  float fv0[64 / NY], fv1[64 / NY];
+#pragma unroll
+  for (int k = 0; k < 64 / NY; ++k) {
+    const int i = ty + k * NY;
+    const int c = c0 + i;
+    fv0[k] = fv1[k] = 0.f;
+    if (VEC == 2) {
+      const int p = p0 + 2 * tx;
+      if (c < C && p < hw) ld2(f4 + static_cast<long long>(c) * hw + p, fv0[k], fv1[k]);
+    } else {
+      const int p = p0 + tx;
+      if (c < C && p < hw) fv0[k] = ldf(f4 + static_cast<long long>(c) * hw + p);
+    }
+  }
+  {
     const int chunk = threadIdx.x & 7, pr = threadIdx.x >> 3;
+#pragma unroll
     for (int pp = pr; pp < 64; pp += 32) {
       const int p = p0 + pp, c = c0 + chunk * 8;
       float g8[8], l8[8];
@@ -165,39 +181,37 @@ __global__ void __launch_bounds__(256)
         tl[pp][chunk * 8 + i] = l8[i];
       }
     }
-    __syncthreads();
-    if (VEC == 2) {
-      const int pl = 2 * tx;
-      const float a0 = a_sm[pl], a1 = a_sm[pl + 1];
+  }
+  __syncthreads();
+  float da0 = 0.f, da1 = 0.f;
+  if (VEC == 2) {
+    const int pl = 2 * tx;
+    const float a0 = a_sm[pl], a1 = a_sm[pl + 1];
 #pragma unroll
-      for (int i = ty; i < 64; i += NY) {
-        const int c = c0 + i, p = p0 + pl;
-        if (c < C && p < hw) {
-          const float dl0 = tl[pl][i], dl1 = tl[pl + 1][i];
-          float f0, f1;
-          ld2(f4 + static_cast<long long>(c) * hw + p, f0, f1);
-          st2(df4 + static_cast<long long>(c) * hw + p, tg[pl][i] + a0 * dl0, tg[pl + 1][i] + a1 * dl1);
-          da0 = fmaf(f0, dl0, da0);
-          da1 = fmaf(f1, dl1, da1);
-        }
-      }
-    } else {
-      const float a = a_sm[tx];
-      for (int i = ty; i < 64; i += NY) {
-        const int c = c0 + i, p = p0 + tx;
-        if (c < C && p < hw) {
-          const float dl = tl[tx][i];
-          const float f = ldf(f4 + static_cast<long long>(c) * hw + p);
-          df4[static_cast<long long>(c) * hw + p] = static_cast<TIO>(tg[tx][i] + a * dl);
-          da0 = fmaf(f, dl, da0);
-        }
+    for (int k = 0; k < 64 / NY; ++k) {
+      const int i = ty + k * NY;
+      const int c = c0 + i, p = p0 + pl;
+      if (c < C && p < hw) {
+        const float dl0 = tl[pl][i], dl1 = tl[pl + 1][i];
+        st2(df4 + static_cast<long long>(c) * hw + p, tg[pl][i] + a0 * dl0, tg[pl + 1][i] + a1 * dl1);
+        da0 = fmaf(fv0[k], dl0, da0);
+        da1 = fmaf(fv1[k], dl1, da1);
       }
     }
-  }
-  if (VEC == 2) {
-    da_sm[ty][2 * tx] = da0;
-    da_sm[ty][2 * tx + 1] = da1;
+    da_sm[ty][pl] = da0;
+    da_sm[ty][pl + 1] = da1;
   } else {
+    const float a = a_sm[tx];
+#pragma unroll
+    for (int k = 0; k < 64 / NY; ++k) {
+      const int i = ty + k * NY;
+      const int c = c0 + i, p = p0 + tx;
+      if (c < C && p < hw) {
+        const float dl = tl[tx][i];
+        df4[static_cast<long long>(c) * hw + p] = static_cast<TIO>(tg[tx][i] + a * dl);
+        da0 = fmaf(fv0[k], dl, da0);
+      }
+    }
     da_sm[ty][tx] = da0;
   }
   __syncthreads();
@@ -207,25 +221,36 @@ __global__ void __launch_bounds__(256)
       float dA = 0.f;
 #pragma unroll
       for (int y = 0; y < NY; ++y) dA += da_sm[y][threadIdx.x];
-      const float* cl = vp.cls[v] + static_cast<long long>(b) * ncls * hw + p;
-      float lmax = cl[0];
-      int arg = 0;
-      for (int k = 1; k < ncls; ++k) {
-        const float l = cl[static_cast<long long>(k) * hw];
-        if (l > lmax) { lmax = l; arg = k; }
-      }
-      const float m = sigmoidf_(lmax);
-      const float c = sigmoidf_(vp.ctr[v][static_cast<long long>(b) * hw + p]);
-      const float a = a_sm[threadIdx.x];
-      const float dt = dA * a * (1.f - a);
-      const float dm = dt * weight * c, dc = dt * weight * m;
-      vp.dctr[v][static_cast<long long>(b) * hw + p] = dc * c * (1.f - c);
-      float* dcl = vp.dcls[v] + static_cast<long long>(b) * ncls * hw + p;
-      for (int k = 0; k < ncls; ++k) dcl[static_cast<long long>(k) * hw] = (k == arg) ? dm * m * (1.f - m) : 0.f;
+      da_part[(static_cast<long long>(blockIdx.y) * gridDim.z + bv) * hw + p] = dA;
     }
   }
 }
 
+// da = sum over channel tiles (fixed order), then the chain a = sigmoid(w*m*c), m = sigmoid(max_k cls), c = sigmoid(ctr)
+__global__ void gate_finish_kernel(const ViewPtrs vp, const float* __restrict__ gate, const float* __restrict__ da_part,
+                                   int nct, int BV, int V, int hw, int ncls, float weight) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(BV) * hw) return;
+  const int bv = static_cast<int>(idx / hw), p = static_cast<int>(idx % hw);
+  const int b = bv / V, v = bv % V;
+  float dA = 0.f;
+  for (int t = 0; t < nct; ++t) dA += da_part[(static_cast<long long>(t) * BV + bv) * hw + p];
+  const float* cl = vp.cls[v] + static_cast<long long>(b) * ncls * hw + p;
+  float lmax = cl[0];
+  int arg = 0;
+  for (int k = 1; k < ncls; ++k) {
+    const float l = cl[static_cast<long long>(k) * hw];
+    if (l > lmax) { lmax = l; arg = k; }
+  }
+  const float m = sigmoidf_(lmax);
+  const float c = sigmoidf_(vp.ctr[v][static_cast<long long>(b) * hw + p]);
+  const float a = gate[idx];
+  const float dt = dA * a * (1.f - a);
+  const float dm = dt * weight * c, dc = dt * weight * m;
+  vp.dctr[v][static_cast<long long>(b) * hw + p] = dc * c * (1.f - c);
+  float* dcl = vp.dcls[v] + static_cast<long long>(b) * ncls * hw + p;
+  for (int k = 0; k < ncls; ++k) dcl[static_cast<long long>(k) * hw] = (k == arg) ? dm * m * (1.f - m) : 0.f;
+}
 
 template <typename TX>
 int launch_gate_fwd(dim3 grid, bool vec2, int io_dtype, const ViewPtrs& vp, void* xg, void* xl, float* gate, int C, int V,
@@ -241,13 +266,13 @@ int launch_gate_fwd(dim3 grid, bool vec2, int io_dtype, const ViewPtrs& vp, void
 }
 template <typename TX>
 int launch_gate_bwd(dim3 grid, bool vec2, int io_dtype, const ViewPtrs& vp, const float* gate, const void* dxg,
-                    const void* dxl, int C, int V, int hw, int ncls, float weight, cudaStream_t stream) {
+                    const void* dxl, float* da_part, int C, int V, int hw, cudaStream_t stream) {
   if (io_dtype == GLF_DTYPE_BF16) {
-    if (vec2) gate_concat_bwd_kernel<bf16, 2, TX><<<grid, 256, 0, stream>>>(vp, gate, (const TX*)dxg, (const TX*)dxl, C, V, hw, ncls, weight);
-    else gate_concat_bwd_kernel<bf16, 1, TX><<<grid, 256, 0, stream>>>(vp, gate, (const TX*)dxg, (const TX*)dxl, C, V, hw, ncls, weight);
+    if (vec2) gate_concat_bwd_kernel<bf16, 2, TX><<<grid, 256, 0, stream>>>(vp, gate, (const TX*)dxg, (const TX*)dxl, da_part, C, V, hw);
+    else gate_concat_bwd_kernel<bf16, 1, TX><<<grid, 256, 0, stream>>>(vp, gate, (const TX*)dxg, (const TX*)dxl, da_part, C, V, hw);
   } else {
-    if (vec2) gate_concat_bwd_kernel<float, 2, TX><<<grid, 256, 0, stream>>>(vp, gate, (const TX*)dxg, (const TX*)dxl, C, V, hw, ncls, weight);
-    else gate_concat_bwd_kernel<float, 1, TX><<<grid, 256, 0, stream>>>(vp, gate, (const TX*)dxg, (const TX*)dxl, C, V, hw, ncls, weight);
+    if (vec2) gate_concat_bwd_kernel<float, 2, TX><<<grid, 256, 0, stream>>>(vp, gate, (const TX*)dxg, (const TX*)dxl, da_part, C, V, hw);
+    else gate_concat_bwd_kernel<float, 1, TX><<<grid, 256, 0, stream>>>(vp, gate, (const TX*)dxg, (const TX*)dxl, da_part, C, V, hw);
   }
   return check_cuda(cudaGetLastError(), "gate_concat_bwd launch");
 }
@@ -269,23 +294,35 @@ int gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, i
   return launch_gate_fwd<float>(grid, vec2, io_dtype, vp, xg, xl, gate, C, V, hw, ncls, weight, stream);
 }
 
+size_t gate_bwd_scratch_bytes(int B, int C, int V, int h, int w) {
+  return static_cast<size_t>((C + 63) / 64) * B * V * h * w * sizeof(float);
+}
+
 int gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, int x_dtype,
                     const void* const* f4, const float* const* cls, const float* const* ctr, const float* gate,
                     const void* dxg, const void* dxl, void* const* df4, float* const* dcls, float* const* dctr,
-                    cudaStream_t stream) {
+                    float* da_part, cudaStream_t stream) {
   if (V < 1 || V > MAXV) return set_error(GLF_ERR_INVALID, "gate_concat: 1 <= V <= %d", MAXV);
   if (C % 8 != 0) return set_error(GLF_ERR_INVALID, "gate_concat: C %% 8 != 0");
+  if (da_part == nullptr) return set_error(GLF_ERR_WORKSPACE, "gate_concat_bwd: scratch is NULL");
   ViewPtrs vp{};
   for (int v = 0; v < V; ++v) {
     vp.f4[v] = f4[v]; vp.cls[v] = cls[v]; vp.ctr[v] = ctr[v];
     vp.df4[v] = df4[v]; vp.dcls[v] = dcls[v]; vp.dctr[v] = dctr[v];
   }
   const int hw = h * w;
-  dim3 grid((hw + 63) / 64, B * V);
-  if (grid.y > 65535) return set_error(GLF_ERR_INVALID, "gate_concat: grid too large");
+  const int nct = (C + 63) / 64;
+  dim3 grid((hw + 63) / 64, nct, B * V);
+  if (grid.y > 65535 || grid.z > 65535) return set_error(GLF_ERR_INVALID, "gate_concat: grid too large");
   const bool vec2 = (hw % 2 == 0);
-  if (x_dtype == GLF_DTYPE_BF16) return launch_gate_bwd<bf16>(grid, vec2, io_dtype, vp, gate, dxg, dxl, C, V, hw, ncls, weight, stream);
-  return launch_gate_bwd<float>(grid, vec2, io_dtype, vp, gate, dxg, dxl, C, V, hw, ncls, weight, stream);
+  int rc = (x_dtype == GLF_DTYPE_BF16)
+               ? launch_gate_bwd<bf16>(grid, vec2, io_dtype, vp, gate, dxg, dxl, da_part, C, V, hw, stream)
+               : launch_gate_bwd<float>(grid, vec2, io_dtype, vp, gate, dxg, dxl, da_part, C, V, hw, stream);
+  if (rc) return rc;
+  const long long n = static_cast<long long>(B) * V * hw;
+  gate_finish_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(vp, gate, da_part, nct, B * V, V, hw, ncls,
+                                                                                weight);
+  return check_cuda(cudaGetLastError(), "gate_finish launch");
 }
 
 }  // namespace glf

@@ -86,7 +86,8 @@ int gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, i
 int gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, int x_dtype,
                     const void* const* f4, const float* const* cls, const float* const* ctr, const float* gate,
                     const void* dxg, const void* dxl, void* const* df4, float* const* dcls, float* const* dctr,
-                    cudaStream_t stream);
+                    float* da_part, cudaStream_t stream);
+size_t gate_bwd_scratch_bytes(int B, int C, int V, int h, int w);
 
 // ------------------------------------------------------------------------------------------------ softmax attention
 // mode='embedded' (ours.py:896-897,902): Y = softmax(Theta Phi^T) G, flash-style, per batch entry.

@@ -53,11 +53,14 @@ def gate_concat_backward(f4, cls, ctr, gate, dxg, dxl, weight: float):
     df4 = [torch.empty_like(t) for t in f4]
     dcls = [torch.empty_like(t) for t in cls]
     dctr = [torch.empty_like(t) for t in ctr]
+    scratch = torch.empty(max(int(lib.glf_gate_concat_bwd_scratch_bytes(B, C_, V, h, w)), 256), dtype=torch.uint8,
+                          device=f4[0].device)
     with torch.cuda.device(f4[0].device):
         L.check(lib.glf_gate_concat_bwd(B, C_, V, h, w, ncls, float(weight), _io_dtype(f4[0]), _io_dtype(dxg),
                                         L.ptr_table(f4),
                                         L.ptr_table(cls), L.ptr_table(ctr), L.ptr(gate), L.ptr(dxg), L.ptr(dxl),
-                                        L.ptr_table(df4), L.ptr_table(dcls), L.ptr_table(dctr), _stream_ptr()))
+                                        L.ptr_table(df4), L.ptr_table(dcls), L.ptr_table(dctr), L.ptr(scratch),
+                                        _stream_ptr()))
     return df4, dcls, dctr
 
 

@@ -126,11 +126,14 @@ GLF_API int glf_gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, flo
                         const void* const* f4, const float* const* cls, const float* const* ctr, void* xg, void* xl,
                         float* gate, glf_stream_t stream);
 
-/* df4[v] = dxg[:, v] + gate * dxl[:, v]  (NCHW, io_dtype);  dcls[v], dctr[v] fp32 logit gradients. */
+/* df4[v] = dxg[:, v] + gate * dxl[:, v]  (NCHW, io_dtype);  dcls[v], dctr[v] fp32 logit gradients.
+ * scratch: caller-allocated, glf_gate_concat_bwd_scratch_bytes(...) bytes (per-channel-tile partials of the gate
+ * gradient, reduced in a fixed order). */
+GLF_API size_t glf_gate_concat_bwd_scratch_bytes(int B, int C, int V, int h, int w);
 GLF_API int glf_gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, int x_dtype,
                         const void* const* f4, const float* const* cls, const float* const* ctr, const float* gate,
                         const void* dxg, const void* dxl, void* const* df4, float* const* dcls, float* const* dctr,
-                        glf_stream_t stream);
+                        void* scratch, glf_stream_t stream);
 
 /* ---- building blocks, exported for unit tests and for callers that fuse differently ------------------------ */
 
