@@ -8,6 +8,8 @@
 //         dTheta = dS Phi ; dPhi = dS^T Theta ; dG = P^T dY        (transposes are MN-major operand reads, no copies)
 // Memory is O(chunk * N^2), independent of the batch size; HBM traffic is O(N^2) per sequence, which is what a
 // single-kernel flash version (scores kept in TMEM, online softmax in registers) removes — same entry points.
+#include <cstdlib>
+
 #include "glf_internal.h"
 #include "glf_ptx.cuh"
 
@@ -95,6 +97,240 @@ GemmOperand op(const void* p, int mn, long long ld, long long bs) {
   return o;
 }
 
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ flash forward
+// One CTA = one 128-query tile of one sequence; it streams 128-key tiles of K = Phi and V = G.
+//   warp 0      TMA producer: Q once, K / V tiles through 2-deep rings
+//   warp 1      MMA issuer  : S_j = Q K_j^T (smem x smem -> TMEM, two S buffers), O += P_j V_j with P read from TMEM
+//                              (tcgen05.mma A-from-TMEM) and V as an MN-major smem operand
+//   warps 2..5  softmax     : one query row per thread: tcgen05.ld the scores, online max / sum in registers, rescale O in
+//                              TMEM when the running max moved, write P as packed bf16 back over the consumed score
+//                              columns (tcgen05.st), finally O / l -> Y (bf16) and lse = m + log l
+// TMEM: columns [0,128) S0/P0, [128,256) S1/P1, [256,256+D) O.
+template <int D>
+struct FlashCfg {
+  static constexpr int BQ = 128, BKV = 128;
+  static constexpr uint32_t TILE = BQ * D * 2;               // bytes of a 128 x D bf16 tile (D/64 swizzle atoms)
+  static constexpr uint32_t SMEM = TILE * 5 + 1024;          // Q + 2 K + 2 V
+  static constexpr uint32_t COL_S0 = 0, COL_S1 = 128, COL_O = 256;
+};
+
+template <int D>
+__global__ void __launch_bounds__(192, 1)
+    flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ Y, float* __restrict__ lse, int N,
+                     int q_tiles) {
+  using Cfg = FlashCfg<D>;
+  extern __shared__ uint8_t fsm_raw[];
+  __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2], o_done;
+  __shared__ uint32_t tmem_holder;
+  const uint32_t base = (smem_u32(fsm_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base, sK = base + Cfg::TILE, sV = base + 3 * Cfg::TILE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / q_tiles, qt = blockIdx.x % q_tiles;
+  const int q0 = qt * Cfg::BQ;
+  const int T = (N + Cfg::BKV - 1) / Cfg::BKV;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(smem_u32(&q_full), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&k_full[i]), 1);
+      mbar_init(smem_u32(&k_empty[i]), 1);
+      mbar_init(smem_u32(&v_full[i]), 1);
+      mbar_init(smem_u32(&v_empty[i]), 1);
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&p_full[i]), 128);
+    }
+    mbar_init(smem_u32(&o_done), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_holder), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_holder;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(smem_u32(&q_full), Cfg::TILE);
+#pragma unroll
+      for (int kb = 0; kb < D / 64; ++kb) tma_load_4d(&tmQ, smem_u32(&q_full), sQ + kb * 16384, kb * 64, q0, b, 0);
+      for (int j = 0; j < T; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = static_cast<uint32_t>(j >> 1) & 1u;
+        mbar_wait(smem_u32(&k_empty[st]), ph ^ 1u);
+        mbar_expect_tx(smem_u32(&k_full[st]), Cfg::TILE);
+#pragma unroll
+        for (int kb = 0; kb < D / 64; ++kb)
+          tma_load_4d(&tmK, smem_u32(&k_full[st]), sK + st * Cfg::TILE + kb * 16384, kb * 64, j * Cfg::BKV, b, 0);
+        mbar_wait(smem_u32(&v_empty[st]), ph ^ 1u);
+        mbar_expect_tx(smem_u32(&v_full[st]), Cfg::TILE);
+#pragma unroll
+        for (int kb = 0; kb < D / 64; ++kb)
+          tma_load_4d(&tmV, smem_u32(&v_full[st]), sV + st * Cfg::TILE + kb * 16384, kb * 64, j * Cfg::BKV, b, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, false, false);   // S = Q K^T : both K-major
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, false, true);      // O += P V  : A in TMEM, B MN-major
+      auto issue_qk = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(smem_u32(&k_full[st]), static_cast<uint32_t>(j >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t kbase = sK + st * Cfg::TILE;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+          umma_f16(tmem + (st ? Cfg::COL_S1 : Cfg::COL_S0), make_sdesc(sQ + off, 16, 1024),
+                   make_sdesc(kbase + off, 16, 1024), idesc_qk, k != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&k_empty[st]));
+        umma_commit(smem_u32(&s_full[st]));
+      };
+      mbar_wait(smem_u32(&q_full), 0);
+      tc_fence_after();
+      issue_qk(0);
+      for (int j = 0; j < T; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = static_cast<uint32_t>(j >> 1) & 1u;
+        if (j + 1 < T) issue_qk(j + 1);          // next scores are computed while the softmax of tile j runs
+        mbar_wait(smem_u32(&p_full[st]), ph);    // P_j is in TMEM, O has been rescaled
+        mbar_wait(smem_u32(&v_full[st]), ph);
+        tc_fence_after();
+        const uint32_t vbase = sV + st * Cfg::TILE;
+        const uint32_t pcol = tmem + (st ? Cfg::COL_S1 : Cfg::COL_S0);
+#pragma unroll
+        for (int k = 0; k < Cfg::BKV / 16; ++k) {
+          umma_f16_ts(tmem + Cfg::COL_O, pcol + k * 8, make_sdesc(vbase + k * 2048, 16384, 1024), idesc_pv,
+                      (j | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&v_empty[st]));
+        umma_commit(smem_u32(&o_done));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    constexpr float LOG2E = 1.4426950408889634f;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < T; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = static_cast<uint32_t>(j >> 1) & 1u;
+      const uint32_t scol = tmem + lane_addr + (st ? Cfg::COL_S1 : Cfg::COL_S0);
+      const int key0 = j * Cfg::BKV;
+      mbar_wait(smem_u32(&s_full[st]), ph);
+      tc_fence_after();
+      // pass 1: running max
+      float mx = m;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(scol + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float sv = (key0 + c * 32 + i < N) ? __uint_as_float(v[i]) : -INFINITY;
+          mx = fmaxf(mx, sv);
+        }
+      }
+      const float alpha = exp2f((m - mx) * LOG2E);   // exp(m_old - m_new); 0 on the first tile (m = -inf)
+      if (j > 0) {
+        mbar_wait(smem_u32(&o_done), static_cast<uint32_t>(j - 1) & 1u);   // P_{j-1} V_{j-1} has landed in O
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll 1
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem + lane_addr + Cfg::COL_O + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            uint32_t lo[16], hi[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { lo[i] = v[i]; hi[i] = v[16 + i]; }
+            tmem_st_32x32_x16(tmem + lane_addr + Cfg::COL_O + c * 32, lo);
+            tmem_st_32x32_x16(tmem + lane_addr + Cfg::COL_O + c * 32 + 16, hi);
+          }
+          tmem_st_wait();
+        }
+      }
+      l *= alpha;
+      // pass 2: P = exp(S - m_new) as packed bf16 over the already consumed score columns
+      const float mb = mx * LOG2E;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(scol + c * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = (key0 + c * 32 + i < N) ? exp2f(fmaf(__uint_as_float(v[i]), LOG2E, -mb)) : 0.f;
+          const float p1 = (key0 + c * 32 + i + 1 < N) ? exp2f(fmaf(__uint_as_float(v[i + 1]), LOG2E, -mb)) : 0.f;
+          l += p0 + p1;
+          pk[i >> 1] = pack_bf16(p0, p1);
+        }
+        tmem_st_32x32_x16(scol + c * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&p_full[st]));
+      m = mx;
+    }
+    // epilogue: O / l -> Y, lse
+    mbar_wait(smem_u32(&o_done), static_cast<uint32_t>(T - 1) & 1u);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const int grow = q0 + row;
+    bf16* yrow = Y + (static_cast<long long>(b) * N + grow) * D;
+#pragma unroll 1
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem + lane_addr + Cfg::COL_O + c * 32, v);
+      tmem_ld_wait();
+      if (grow < N) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 pk = make_uint4(pack_bf16(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv),
+                                pack_bf16(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv),
+                                pack_bf16(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv),
+                                pack_bf16(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv));
+          *reinterpret_cast<uint4*>(yrow + c * 32 + i) = pk;
+        }
+      }
+    }
+    if (grow < N) lse[static_cast<long long>(b) * N + grow] = m + __logf(l);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+template <int D>
+static int launch_flash_fwd(const bf16* P3, bf16* Y, float* lse, int B, int N, cudaStream_t stream) {
+  using Cfg = FlashCfg<D>;
+  CUtensorMap tq, tk, tv;
+  const long long seq = static_cast<long long>(N) * 3 * D;
+  int rc;
+  if ((rc = make_tmap_bf16(&tq, P3, D, N, B, 3 * D, seq, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tk, P3 + D, D, N, B, 3 * D, seq, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tv, P3 + 2 * D, D, N, B, 3 * D, seq, 128))) return rc;
+  auto kern = flash_fwd_kernel<D>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(flash_fwd)");
+  const int q_tiles = (N + 127) / 128;
+  kern<<<B * q_tiles, 192, Cfg::SMEM, stream>>>(tq, tk, tv, Y, lse, N, q_tiles);
+  return check_cuda(cudaGetLastError(), "flash_fwd launch");
+}
+
+namespace {
 }  // namespace
 
 int attn_ld(int N) { return (N + 7) & ~7; }
@@ -113,7 +349,8 @@ size_t attn_scratch_bytes(long long B, long long N, bool backward) {
   return nb * per * (backward ? 12 : 6) + 1024;
 }
 
-int flash_fwd(const bf16* P3, bf16* Y, float* lse, int B, int N, int Ci, void* scratch, cudaStream_t stream) {
+static int attn_fwd_materialized(const bf16* P3, bf16* Y, float* lse, int B, int N, int Ci, void* scratch,
+                                 cudaStream_t stream) {
   const int ld = attn_ld(N);
   const int nb = attn_chunk(B, N);
   const size_t per = static_cast<size_t>(ld) * N;
@@ -149,6 +386,15 @@ int flash_fwd(const bf16* P3, bf16* Y, float* lse, int B, int N, int Ci, void* s
     }
   }
   return 0;
+}
+
+int flash_fwd(const bf16* P3, bf16* Y, float* lse, int B, int N, int Ci, void* scratch, cudaStream_t stream) {
+  if (const char* e = getenv("GLF_DEBUG_ATTN_MATERIALIZED")) {
+    if (e[0] == '1') return attn_fwd_materialized(P3, Y, lse, B, N, Ci, scratch, stream);
+  }
+  if (Ci == 128) return launch_flash_fwd<128>(P3, Y, lse, B, N, stream);
+  if (Ci == 64) return launch_flash_fwd<64>(P3, Y, lse, B, N, stream);
+  return attn_fwd_materialized(P3, Y, lse, B, N, Ci, scratch, stream);   // other head widths: exact chunked path
 }
 
 int flash_bwd(const bf16* P3, const bf16* Y, const bf16* dY, const float* lse, bf16* dP3, float* delta, float* cs_t,

@@ -437,6 +437,21 @@ int make_operand_map(CUtensorMap* tm, const GemmOperand& op, int rows, int K, in
   return 0;
 }
 
+}  // namespace
+
+// bf16 tensor map over [batch][outer][inner] with row pitch `ld` elements, SWIZZLE_128B, box {64, box_outer, 1, 1}
+int make_tmap_bf16(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long batch, long long ld,
+                   long long batch_stride, int box_outer) {
+  GemmOperand op;
+  op.ptr = ptr;
+  op.mn_major = 0;      // {K = inner, rows = outer}
+  op.ld = ld;
+  op.batch_stride = batch > 1 ? batch_stride : 0;
+  return make_operand_map(tm, op, static_cast<int>(outer), static_cast<int>(inner), static_cast<int>(batch), 1, box_outer);
+}
+
+namespace {
+
 template <bool A_MN, bool B_MN, int BN>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKParams p, int num_sms, int* cs_rows,
            cudaStream_t stream) {

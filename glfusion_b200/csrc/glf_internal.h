@@ -45,6 +45,8 @@ struct GemmArgs {
 };
 int gemm(const GemmArgs& a, cudaStream_t stream);
 inline int gemm_tiles_m(int M) { return (M + 127) / 128; }
+int make_tmap_bf16(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long batch, long long ld,
+                   long long batch_stride, int box_outer);
 
 // ------------------------------------------------------------------------------------------------ element-wise
 int transpose_cast(const void* in, void* out, int batch, int R, int S, int in_dtype, int out_dtype,
