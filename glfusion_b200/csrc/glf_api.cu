@@ -470,8 +470,8 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
       g.split_k = pick_split(static_cast<long long>((C + 127) / 128) * ((Ci + 127) / 128), rows);
       GLF_TRY(gemm(g, stream));
     }
-    GLF_TRY(flash_bwd(s.P, s.Y, wb.dY, s.lse, wb.dP, wb.delta, wb.cs_t, wb.cs_p, wb.cs_g, &np, B, N, Ci, wb.attn,
-                      stream));
+    GLF_TRY(flash_bwd(s.P, s.Y, wb.dY, s.lse, wb.dP, wb.delta, wb.cs_t, wb.cs_p, wb.cs_g, 4 * B * m.tiles_seq, &np, B, N,
+                      Ci, wb.attn, stream));
     np_p = np_g = np;
   }
   GLF_TRY(check_cuda(cudaMemsetAsync(wb.dwcat, 0, sizeof(float) * 3 * Ci * C, stream), "memset dWcat"));
@@ -501,8 +501,15 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
   {  // bias gradients = column sums of dTheta / dPhi / dG, from the per-sub-block partials of their GEMM epilogues
     // the three tables can have different row counts (tile shape and grid differ per product): stage 1 always
     long long rs = 2LL * Ci;
+    const float *t0 = wb.cs_t, *t1 = wb.cs_p, *t2 = wb.cs_g;
+    if (np < 0) {  // flash backward: one table of width 3Ci (column sums of dP = [dTheta | dPhi | dG])
+      np = np_p = np_g = -np;
+      rs = 2LL * 3 * Ci;
+      t1 = wb.cs_t + Ci;
+      t2 = wb.cs_t + 2 * Ci;
+    }
     const int np_in[3] = {np, np_p, np_g};
-    GLF_TRY(reduce_stage1(wb.cs_t, wb.cs_p, wb.cs_g, 3, np_in, &np, &rs, 0, 1, Ci, wb.red1, stream));
+    GLF_TRY(reduce_stage1(t0, t1, t2, 3, np_in, &np, &rs, 0, 1, Ci, wb.red1, stream));
     GLF_TRY(reduce_partials3(wb.red1, wb.red1 + static_cast<long long>(REDUCE_STAGE1_ROWS) * Ci,
                              wb.red1 + 2LL * REDUCE_STAGE1_ROWS * Ci, np, rs, Ci, g_->theta_b, g_->phi_b, g_->g_b,
                              stream));
