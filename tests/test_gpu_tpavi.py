@@ -207,3 +207,22 @@ def test_oracle_dot_channel_widths(C, B, T, H, W):
     for k, pp in m.named_parameters():
         if not k.startswith("align_channel"):
             assert_close("grad:" + k, pp.grad, go[k], 3e-2, zero_scale=scale)
+
+
+@pytest.mark.parametrize("C,B,T,H,W", [(128, 3, 3, 5, 7), (256, 2, 1, 9, 15), (256, 1, 2, 13, 20), (64, 2, 2, 6, 6)])
+def test_oracle_embedded_ragged(C, B, T, H, W):
+    """Softmax mode, token counts that are not multiples of the 128-wide query/key tiles (masking paths of the flash
+    kernels: N = 105, 135, 520), both head widths (C'=64, 128), and a head width served by the chunked exact path (32)."""
+    p = O.init_params(C, seed=91, randomize_affine=True)
+    gen = torch.Generator().manual_seed(92)
+    x = torch.randn(B, C, T, H, W, generator=gen)
+    dz = torch.randn(B, C, T, H, W, generator=gen)
+    zo, dxo, go = O.tpavi_fwd_bwd(x, dz, {k: v.clone() for k, v in p.items()}, mode="embedded")
+    m = load_module_from_params(TPAVIModule, p, C, "embedded", True).train()
+    z, dx = _run(m, x.to(DEV, torch.bfloat16), dz.to(DEV, torch.bfloat16))
+    assert_close("z", z, zo, BF16_TOL)
+    assert_close("dx", dx, dxo, BF16_TOL)
+    scale = grad_scale(go.values())
+    for k, pp in m.named_parameters():
+        if not k.startswith("align_channel"):
+            assert_close("grad:" + k, pp.grad, go[k], 4e-2, zero_scale=scale)
