@@ -1,7 +1,7 @@
 // glf_flash.cu — mode='embedded' (softmax) attention of TPAVIModule (R/models/ours.py:878-902 with
 // f_div_C = softmax(f, dim=-1)):   Y_b = softmax(Theta_b Phi_b^T) G_b      (no 1/sqrt(d) scale in the reference).
 //
-// Version 1 (this file): exact attention with the N x N score matrix materialised for a bounded CHUNK of sequences
+// Debug / odd-width path (this header): exact attention with the N x N score matrix materialised for a bounded CHUNK of sequences
 // at a time (scratch sized by attn_chunk()), every product on the tcgen05 GEMM of glf_gemm.cu:
 //   fwd : S = Theta Phi^T (fp32) -> row softmax (P bf16, lse fp32) -> Y = P G
 //   bwd : recompute S ; dPm = dY G^T ; P = exp(S - lse) ; dS = P o (dPm - delta) ; delta = rowsum(dY o Y)
@@ -100,38 +100,59 @@ GemmOperand op(const void* p, int mn, long long ld, long long bs) {
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------ flash kernels
+// Shared conventions of the three kernels below (all sm_100a, one CTA per SM, 320 threads):
+//   warp 0        TMA producer (cp.async.bulk.tensor, SWIZZLE_128B tiles, mbarrier completion)
+//   warp 1        MMA issuer   (one elected lane issues every tcgen05.mma; tcgen05.commit publishes results)
+//   warps 2..5    compute warpgroup 0, warps 6..9 compute warpgroup 1: one TMEM lane (= one tile row) per thread;
+//                 a warp may only touch TMEM lanes 32*(warp%4)..+31, so each group of four consecutive warps covers
+//                 all 128 lanes.
+// Scores / probabilities never leave the SM: S is accumulated in TMEM, read with tcgen05.ld, turned into bf16 P (or
+// dS) in registers and written back over the consumed score columns with tcgen05.st, from where it is the A operand
+// of the next tcgen05.mma (A-from-TMEM form).  exp() is one MUFU.EX2 per element on log2-scaled scores.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
 // ------------------------------------------------------------------------------------------------ flash forward
-// One CTA = one 128-query tile of one sequence; it streams 128-key tiles of K = Phi and V = G.
-//   warp 0      TMA producer: Q once, K / V tiles through 2-deep rings
-//   warp 1      MMA issuer  : S_j = Q K_j^T (smem x smem -> TMEM, two S buffers), O += P_j V_j with P read from TMEM
-//                              (tcgen05.mma A-from-TMEM) and V as an MN-major smem operand
-//   warps 2..5  softmax     : one query row per thread: tcgen05.ld the scores, online max / sum in registers, rescale O in
-//                              TMEM when the running max moved, write P as packed bf16 back over the consumed score
-//                              columns (tcgen05.st), finally O / l -> Y (bf16) and lse = m + log l
-// TMEM: columns [0,128) S0/P0, [128,256) S1/P1, [256,256+D) O.
+// One CTA = TWO 128-query tiles of one sequence (256 queries); it streams 128-key tiles of K = Phi and V = G.
+// The two query tiles ping-pong: while warpgroup t does the softmax of S_t, the tensor pipe computes the other
+// tile's P V product and next scores.  MMA issue order per key tile j (t = 0, 1):
+//       wait P_t(j) ;  O_t += P_t(j) V_j ;  S_t(j+1) = Q_t K_{j+1}^T
+// TMEM (512 columns): S0/P0 [0,128), S1/P1 [128,256), O0 [256,256+D), O1 [384,384+D).
+// Online softmax with a lazy reference maximum (log2 domain): the running maximum is only raised -- and O rescaled in
+// TMEM -- when a tile's maximum exceeds it by more than 8 (P <= 2^8 stays exact enough in bf16/fp32), so after the
+// first few tiles the rescale pass disappears.  lse = (m + log2 l) ln 2 is exact irrespective of the reference.
 template <int D>
 struct FlashCfg {
-  static constexpr int BQ = 128, BKV = 128;
-  static constexpr uint32_t TILE = BQ * D * 2;               // bytes of a 128 x D bf16 tile (D/64 swizzle atoms)
-  static constexpr uint32_t SMEM = TILE * 5 + 1024;          // Q + 2 K + 2 V
-  static constexpr uint32_t COL_S0 = 0, COL_S1 = 128, COL_O = 256;
+  static constexpr uint32_t TILE = 128 * D * 2;              // bytes of a 128 x D bf16 tile (D/64 swizzle atoms)
+  static constexpr uint32_t SUB = 64 * D * 2;                // bytes of a 64 x D bf16 tile
+  static constexpr uint32_t SMEM_FWD = TILE * 6 + 1024;      // 2 Q + 2 K + 2 V
+  static constexpr uint32_t SMEM_BWD = TILE * 2 + 4 * 2 * SUB + 1024;   // 2 resident tiles + 4-deep ring of sub-tile pairs
 };
+constexpr int FLASH_THREADS = 320;
 
 template <int D>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(FLASH_THREADS, 1)
     flash_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ Y, float* __restrict__ lse, int N,
-                     int q_tiles) {
+                     int q_pairs) {
   using Cfg = FlashCfg<D>;
   extern __shared__ uint8_t fsm_raw[];
-  __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2], o_done;
+  __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2], o_done[2];
   __shared__ uint32_t tmem_holder;
   const uint32_t base = (smem_u32(fsm_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = base, sK = base + Cfg::TILE, sV = base + 3 * Cfg::TILE;
+  const uint32_t sQ = base, sK = base + 2 * Cfg::TILE, sV = base + 4 * Cfg::TILE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x / q_tiles, qt = blockIdx.x % q_tiles;
-  const int q0 = qt * Cfg::BQ;
-  const int T = (N + Cfg::BKV - 1) / Cfg::BKV;
+  const int b = blockIdx.x / q_pairs, qp = blockIdx.x % q_pairs;
+  const int q0 = qp * 256;
+  const int T = (N + 127) / 128;
+  const int ntile = (q0 + 128 < N) ? 2 : 1;      // the last CTA of a sequence may own a single query tile
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
@@ -145,8 +166,8 @@ __global__ void __launch_bounds__(192, 1)
       mbar_init(smem_u32(&v_empty[i]), 1);
       mbar_init(smem_u32(&s_full[i]), 1);
       mbar_init(smem_u32(&p_full[i]), 128);
+      mbar_init(smem_u32(&o_done[i]), 1);
     }
-    mbar_init(smem_u32(&o_done), 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_holder), 512);
@@ -157,9 +178,12 @@ __global__ void __launch_bounds__(192, 1)
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_expect_tx(smem_u32(&q_full), Cfg::TILE);
+      mbar_expect_tx(smem_u32(&q_full), ntile * Cfg::TILE);
+      for (int t = 0; t < ntile; ++t) {
 #pragma unroll
-      for (int kb = 0; kb < D / 64; ++kb) tma_load_4d(&tmQ, smem_u32(&q_full), sQ + kb * 16384, kb * 64, q0, b, 0);
+        for (int kb = 0; kb < D / 64; ++kb)
+          tma_load_4d(&tmQ, smem_u32(&q_full), sQ + t * Cfg::TILE + kb * 16384, kb * 64, q0 + t * 128, b, 0);
+      }
       for (int j = 0; j < T; ++j) {
         const int st = j & 1;
         const uint32_t ph = static_cast<uint32_t>(j >> 1) & 1u;
@@ -167,146 +191,159 @@ __global__ void __launch_bounds__(192, 1)
         mbar_expect_tx(smem_u32(&k_full[st]), Cfg::TILE);
 #pragma unroll
         for (int kb = 0; kb < D / 64; ++kb)
-          tma_load_4d(&tmK, smem_u32(&k_full[st]), sK + st * Cfg::TILE + kb * 16384, kb * 64, j * Cfg::BKV, b, 0);
+          tma_load_4d(&tmK, smem_u32(&k_full[st]), sK + st * Cfg::TILE + kb * 16384, kb * 64, j * 128, b, 0);
         mbar_wait(smem_u32(&v_empty[st]), ph ^ 1u);
         mbar_expect_tx(smem_u32(&v_full[st]), Cfg::TILE);
 #pragma unroll
         for (int kb = 0; kb < D / 64; ++kb)
-          tma_load_4d(&tmV, smem_u32(&v_full[st]), sV + st * Cfg::TILE + kb * 16384, kb * 64, j * Cfg::BKV, b, 0);
+          tma_load_4d(&tmV, smem_u32(&v_full[st]), sV + st * Cfg::TILE + kb * 16384, kb * 64, j * 128, b, 0);
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, false, false);   // S = Q K^T : both K-major
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, false, true);      // O += P V  : A in TMEM, B MN-major
-      auto issue_qk = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(smem_u32(&k_full[st]), static_cast<uint32_t>(j >> 1) & 1u);
-        tc_fence_after();
-        const uint32_t kbase = sK + st * Cfg::TILE;
+      auto issue_s = [&](int t, int j) {
+        const uint32_t kbase = sK + (j & 1) * Cfg::TILE;
+        const uint32_t qbase = sQ + t * Cfg::TILE;
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
           const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-          umma_f16(tmem + (st ? Cfg::COL_S1 : Cfg::COL_S0), make_sdesc(sQ + off, 16, 1024),
-                   make_sdesc(kbase + off, 16, 1024), idesc_qk, k != 0 ? 1u : 0u);
+          umma_f16(tmem + t * 128, make_sdesc(qbase + off, 16, 1024), make_sdesc(kbase + off, 16, 1024), idesc_qk,
+                   k != 0 ? 1u : 0u);
         }
-        umma_commit(smem_u32(&k_empty[st]));
-        umma_commit(smem_u32(&s_full[st]));
+        umma_commit(smem_u32(&s_full[t]));
       };
       mbar_wait(smem_u32(&q_full), 0);
+      mbar_wait(smem_u32(&k_full[0]), 0);
       tc_fence_after();
-      issue_qk(0);
+      for (int t = 0; t < ntile; ++t) issue_s(t, 0);
+      umma_commit(smem_u32(&k_empty[0]));
       for (int j = 0; j < T; ++j) {
         const int st = j & 1;
         const uint32_t ph = static_cast<uint32_t>(j >> 1) & 1u;
-        if (j + 1 < T) issue_qk(j + 1);          // next scores are computed while the softmax of tile j runs
-        mbar_wait(smem_u32(&p_full[st]), ph);    // P_j is in TMEM, O has been rescaled
+        const bool more = j + 1 < T;
         mbar_wait(smem_u32(&v_full[st]), ph);
-        tc_fence_after();
+        if (more) mbar_wait(smem_u32(&k_full[(j + 1) & 1]), static_cast<uint32_t>((j + 1) >> 1) & 1u);
         const uint32_t vbase = sV + st * Cfg::TILE;
-        const uint32_t pcol = tmem + (st ? Cfg::COL_S1 : Cfg::COL_S0);
+        for (int t = 0; t < ntile; ++t) {
+          mbar_wait(smem_u32(&p_full[t]), static_cast<uint32_t>(j) & 1u);   // P_t(j) is in TMEM, O_t rescaled
+          tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < Cfg::BKV / 16; ++k) {
-          umma_f16_ts(tmem + Cfg::COL_O, pcol + k * 8, make_sdesc(vbase + k * 2048, 16384, 1024), idesc_pv,
-                      (j | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 8; ++k)
+            umma_f16_ts(tmem + 256 + t * 128, tmem + t * 128 + k * 8, make_sdesc(vbase + k * 2048, 16384, 1024),
+                        idesc_pv, (j | k) != 0 ? 1u : 0u);
+          umma_commit(smem_u32(&o_done[t]));
+          if (more) issue_s(t, j + 1);           // overwrites P_t(j): ordered behind the product that reads it
         }
         umma_commit(smem_u32(&v_empty[st]));
-        umma_commit(smem_u32(&o_done));
+        if (more) umma_commit(smem_u32(&k_empty[(j + 1) & 1]));
       }
     }
   } else {
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    constexpr float LOG2E = 1.4426950408889634f;
-    float m = -INFINITY, l = 0.f;
-    for (int j = 0; j < T; ++j) {
-      const int st = j & 1;
-      const uint32_t ph = static_cast<uint32_t>(j >> 1) & 1u;
-      const uint32_t scol = tmem + lane_addr + (st ? Cfg::COL_S1 : Cfg::COL_S0);
-      const int key0 = j * Cfg::BKV;
-      mbar_wait(smem_u32(&s_full[st]), ph);
-      tc_fence_after();
-      // pass 1: running max
-      float mx = m;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(scol + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float sv = (key0 + c * 32 + i < N) ? __uint_as_float(v[i]) : -INFINITY;
-          mx = fmaxf(mx, sv);
-        }
-      }
-      const float alpha = exp2f((m - mx) * LOG2E);   // exp(m_old - m_new); 0 on the first tile (m = -inf)
-      if (j > 0) {
-        mbar_wait(smem_u32(&o_done), static_cast<uint32_t>(j - 1) & 1u);   // P_{j-1} V_{j-1} has landed in O
+    const int t = (warp - 2) >> 2;
+    if (t < ntile) {
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+      const uint32_t scol = tmem + lane_addr + t * 128;
+      const uint32_t ocol = tmem + lane_addr + 256 + t * 128;
+      float m_run = -INFINITY;                   // reference maximum, log2 domain
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      for (int j = 0; j < T; ++j) {
+        mbar_wait(smem_u32(&s_full[t]), static_cast<uint32_t>(j) & 1u);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.f)) {
-#pragma unroll 1
-          for (int c = 0; c < D / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32(tmem + lane_addr + Cfg::COL_O + c * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            uint32_t lo[16], hi[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { lo[i] = v[i]; hi[i] = v[16 + i]; }
-            tmem_st_32x32_x16(tmem + lane_addr + Cfg::COL_O + c * 32, lo);
-            tmem_st_32x32_x16(tmem + lane_addr + Cfg::COL_O + c * 32 + 16, hi);
-          }
-          tmem_st_wait();
-        }
-      }
-      l *= alpha;
-      // pass 2: P = exp(S - m_new) as packed bf16 over the already consumed score columns
-      const float mb = mx * LOG2E;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(scol + c * 32, v);
+        uint32_t s[4][32];
+        tmem_ld_32x32(scol, s[0]);
+        tmem_ld_32x32(scol + 32, s[1]);
+        tmem_ld_32x32(scol + 64, s[2]);
+        tmem_ld_32x32(scol + 96, s[3]);
         tmem_ld_wait();
-        uint32_t pk[16];
+        const int kv = N - j * 128;              // valid keys in this tile (>= 128 except for the last one)
+        if (kv < 128) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = (key0 + c * 32 + i < N) ? exp2f(fmaf(__uint_as_float(v[i]), LOG2E, -mb)) : 0.f;
-          const float p1 = (key0 + c * 32 + i + 1 < N) ? exp2f(fmaf(__uint_as_float(v[i + 1]), LOG2E, -mb)) : 0.f;
-          l += p0 + p1;
-          pk[i >> 1] = pack_bf16(p0, p1);
+          for (int i = 0; i < 128; ++i)
+            if (i >= kv) s[i >> 5][i & 31] = 0xff800000u;     // -inf
         }
-        tmem_st_32x32_x16(scol + c * 16, pk);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(smem_u32(&p_full[st]));
-      m = mx;
-    }
-    // epilogue: O / l -> Y, lse
-    mbar_wait(smem_u32(&o_done), static_cast<uint32_t>(T - 1) & 1u);
-    tc_fence_after();
-    const float inv = 1.f / l;
-    const int grow = q0 + row;
-    bf16* yrow = Y + (static_cast<long long>(b) * N + grow) * D;
+        float x0 = __uint_as_float(s[0][0]), x1 = __uint_as_float(s[0][1]), x2 = __uint_as_float(s[0][2]),
+              x3 = __uint_as_float(s[0][3]);
+#pragma unroll
+        for (int i = 4; i < 128; i += 4) {
+          x0 = fmaxf(x0, __uint_as_float(s[i >> 5][i & 31]));
+          x1 = fmaxf(x1, __uint_as_float(s[i >> 5][(i & 31) + 1]));
+          x2 = fmaxf(x2, __uint_as_float(s[i >> 5][(i & 31) + 2]));
+          x3 = fmaxf(x3, __uint_as_float(s[i >> 5][(i & 31) + 3]));
+        }
+        const float mx2 = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)) * kLog2e;
+        if (__any_sync(0xffffffffu, mx2 > m_run + 8.f)) {
+          const float m_new = fmaxf(m_run, mx2);
+          const float alpha = ex2_approx(m_run - m_new);   // 0 on the first tile (m_run = -inf), 1 if unchanged
+          if (j > 0) {
+            mbar_wait(smem_u32(&o_done[t]), static_cast<uint32_t>(j - 1) & 1u);   // P(j-1) V(j-1) has landed in O
+            tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < D / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem + lane_addr + Cfg::COL_O + c * 32, v);
-      tmem_ld_wait();
-      if (grow < N) {
+            for (int c = 0; c < D / 32; ++c) {
+              uint32_t v[32];
+              tmem_ld_32x32(ocol + c * 32, v);
+              tmem_ld_wait();
+              uint32_t lo[16], hi[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 pk = make_uint4(pack_bf16(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv),
-                                pack_bf16(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv),
-                                pack_bf16(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv),
-                                pack_bf16(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv));
-          *reinterpret_cast<uint4*>(yrow + c * 32 + i) = pk;
+              for (int i = 0; i < 16; ++i) {
+                lo[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                hi[i] = __float_as_uint(__uint_as_float(v[16 + i]) * alpha);
+              }
+              tmem_st_32x32_x16(ocol + c * 32, lo);
+              tmem_st_32x32_x16(ocol + c * 32 + 16, hi);
+            }
+          }
+          l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha;
+          m_run = m_new;
+        }
+        const float nm = -m_run;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(s[c][i]), kLog2e, nm));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(s[c][i + 1]), kLog2e, nm));
+            const float p2 = ex2_approx(fmaf(__uint_as_float(s[c][i + 2]), kLog2e, nm));
+            const float p3 = ex2_approx(fmaf(__uint_as_float(s[c][i + 3]), kLog2e, nm));
+            l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+            pk[i >> 1] = pack_bf16(p0, p1);
+            pk[(i >> 1) + 1] = pack_bf16(p2, p3);
+          }
+          tmem_st_32x32_x16(scol + c * 16, pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&p_full[t]));
+      }
+      // epilogue: O / l -> Y, lse
+      mbar_wait(smem_u32(&o_done[t]), static_cast<uint32_t>(T - 1) & 1u);
+      tc_fence_after();
+      const float l = (l0 + l1) + (l2 + l3);
+      const float inv = 1.f / l;
+      const int grow = q0 + t * 128 + row;
+      bf16* yrow = Y + (static_cast<long long>(b) * N + grow) * D;
+#pragma unroll 1
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(ocol + c * 32, v);
+        tmem_ld_wait();
+        if (grow < N) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 pk = make_uint4(pack_bf16(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv),
+                                  pack_bf16(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv),
+                                  pack_bf16(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv),
+                                  pack_bf16(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv));
+            *reinterpret_cast<uint4*>(yrow + c * 32 + i) = pk;
+          }
         }
       }
+      if (grow < N) lse[static_cast<long long>(b) * N + grow] = (m_run + log2f(l)) * kLn2;
     }
-    if (grow < N) lse[static_cast<long long>(b) * N + grow] = m + __logf(l);
   }
   tc_fence_before();
   __syncthreads();
@@ -316,40 +353,48 @@ __global__ void __launch_bounds__(192, 1)
 // ------------------------------------------------------------------------------------------------ flash backward
 // Recompute-based (nothing N x N is stored): with lse from the forward and delta = rowsum(dY o Y),
 //   P = exp(S - lse) ,  dS = P o (dY V^T - delta)
-//   dQ kernel   (CTA = 128 queries, streams K/V tiles):   S = Q K^T, dP = dY V^T -> dS (bf16, TMEM) -> dQ += dS K
-//   dK/dV kernel(CTA = 128 keys, streams Q/dY tiles):     S^T = K Q^T, dP^T = V dY^T -> P^T, dS^T (bf16, TMEM)
-//                                                          -> dV += P^T dY , dK += dS^T Q
+//   dQ kernel   (CTA = 128 queries, streams 64-key sub-tiles):  S = Q K^T, dP = dY V^T -> dS (bf16, TMEM) -> dQ += dS K
+//   dK/dV kernel(CTA = 128 keys, streams 64-query sub-tiles):   S^T = K Q^T, dP^T = V dY^T -> P^T, dS^T (bf16, TMEM)
+//                                                                -> dV += P^T dY , dK += dS^T Q
 // Every product is a tcgen05.mma; P / dS never leave TMEM (they are the A operand of the second product); transposed
 // uses of a tile (Q as [q,d] and as [d,q]) are the same shared-memory bytes read through K-major / MN-major descriptors.
 // Deterministic: no atomics.  Scores are recomputed once per kernel (7 products per tile pair instead of 5).
+// Pipelining: the 128 x 64 score / dP blocks are double-buffered in TMEM (stage = sub-tile parity) and the two compute
+// warpgroups alternate sub-tiles, so the tensor pipe computes sub-tile j+1's scores and sub-tile j-1's accumulation
+// while a warpgroup turns sub-tile j's scores into dS.
+//   dQ kernel TMEM   : stage s at [128 s, 128 s + 128): S [0,64) (dS bf16 over [0,32)), dP [64,128);  dQ at [256, 256+D)
+//   dK/dV kernel TMEM: dV [0,D), dK [128,128+D); stage s at [256 + 128 s, ..): S^T [0,64) (P^T bf16 over [0,32)),
+//                      dP^T [64,128) (dS^T bf16 over [64,96))
 template <int D>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(FLASH_THREADS, 1)
     flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdY,
                         const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dP3, int N,
                         int q_tiles) {
   using Cfg = FlashCfg<D>;
+  constexpr int RING = 4;
   extern __shared__ uint8_t fsm_raw[];
-  __shared__ uint64_t q_full, k_full[2], v_full[2], kv_empty[2], s_full, ds_full, dq_done;
+  __shared__ uint64_t q_full, kv_full[RING], kv_empty[RING], s_full[2], ds_full[2], dq_done;
   __shared__ uint32_t tmem_holder;
   const uint32_t base = (smem_u32(fsm_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = base, sdY = base + Cfg::TILE, sK = base + 2 * Cfg::TILE, sV = base + 4 * Cfg::TILE;
+  const uint32_t sQ = base, sdY = base + Cfg::TILE, sRing = base + 2 * Cfg::TILE;   // ring slot: K_sub | V_sub
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / q_tiles, qt = blockIdx.x % q_tiles;
   const int q0 = qt * 128;
-  const int T = (N + 127) / 128;
-  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ = 256;
+  const int T = (N + 63) / 64;       // 64-key sub-tiles
+  constexpr uint32_t COL_DQ = 256;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdY);
     mbar_init(smem_u32(&q_full), 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&k_full[i]), 1);
-      mbar_init(smem_u32(&v_full[i]), 1);
+    for (int i = 0; i < RING; ++i) {
+      mbar_init(smem_u32(&kv_full[i]), 1);
       mbar_init(smem_u32(&kv_empty[i]), 1);
     }
-    mbar_init(smem_u32(&s_full), 1);
-    mbar_init(smem_u32(&ds_full), 128);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&ds_full[i]), 128);
+    }
     mbar_init(smem_u32(&dq_done), 1);
     fence_mbar_init();
   }
@@ -368,95 +413,104 @@ __global__ void __launch_bounds__(192, 1)
         tma_load_4d(&tmdY, smem_u32(&q_full), sdY + kb * 16384, kb * 64, q0, b, 0);
       }
       for (int j = 0; j < T; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = static_cast<uint32_t>(j >> 1) & 1u;
-        mbar_wait(smem_u32(&kv_empty[st]), ph ^ 1u);
-        mbar_expect_tx(smem_u32(&k_full[st]), Cfg::TILE);
-        mbar_expect_tx(smem_u32(&v_full[st]), Cfg::TILE);
+        const int r = j % RING;
+        const uint32_t ph = static_cast<uint32_t>(j / RING) & 1u;
+        mbar_wait(smem_u32(&kv_empty[r]), ph ^ 1u);
+        mbar_expect_tx(smem_u32(&kv_full[r]), 2 * Cfg::SUB);
+        const uint32_t slot = sRing + r * 2 * Cfg::SUB;
 #pragma unroll
         for (int kb = 0; kb < D / 64; ++kb) {
-          tma_load_4d(&tmK, smem_u32(&k_full[st]), sK + st * Cfg::TILE + kb * 16384, kb * 64, j * 128, b, 0);
-          tma_load_4d(&tmV, smem_u32(&v_full[st]), sV + st * Cfg::TILE + kb * 16384, kb * 64, j * 128, b, 0);
+          tma_load_4d(&tmK, smem_u32(&kv_full[r]), slot + kb * 8192, kb * 64, j * 64, b, 0);
+          tma_load_4d(&tmV, smem_u32(&kv_full[r]), slot + Cfg::SUB + kb * 8192, kb * 64, j * 64, b, 0);
         }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc_kk = make_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
       constexpr uint32_t idesc_dq = make_idesc_bf16(128, D, false, true);
+      auto issue_sdp = [&](int j) {
+        const int r = j % RING;
+        mbar_wait(smem_u32(&kv_full[r]), static_cast<uint32_t>(j / RING) & 1u);
+        tc_fence_after();
+        const uint32_t kb_ = sRing + r * 2 * Cfg::SUB, vb_ = kb_ + Cfg::SUB;
+        const uint32_t stage = tmem + (j & 1) * 128;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {   // S = Q K_sub^T
+          const uint32_t offa = (k >> 2) * 16384 + (k & 3) * 32, offb = (k >> 2) * 8192 + (k & 3) * 32;
+          umma_f16(stage, make_sdesc(sQ + offa, 16, 1024), make_sdesc(kb_ + offb, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {   // dP = dY V_sub^T
+          const uint32_t offa = (k >> 2) * 16384 + (k & 3) * 32, offb = (k >> 2) * 8192 + (k & 3) * 32;
+          umma_f16(stage + 64, make_sdesc(sdY + offa, 16, 1024), make_sdesc(vb_ + offb, 16, 1024), idesc_s,
+                   k != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&s_full[j & 1]));
+      };
       mbar_wait(smem_u32(&q_full), 0);
       tc_fence_after();
+      issue_sdp(0);
       for (int j = 0; j < T; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = static_cast<uint32_t>(j >> 1) & 1u;
-        mbar_wait(smem_u32(&k_full[st]), ph);
-        mbar_wait(smem_u32(&v_full[st]), ph);
+        const int r = j % RING;
+        if (j + 1 < T) issue_sdp(j + 1);     // stage (j+1)&1 was drained by sub-tile j-1 (ordered behind its dQ product)
+        mbar_wait(smem_u32(&ds_full[j & 1]), static_cast<uint32_t>(j >> 1) & 1u);   // dS (bf16) in stage columns [0,32)
         tc_fence_after();
-        const uint32_t kbase = sK + st * Cfg::TILE, vbase = sV + st * Cfg::TILE;
+        const uint32_t kb_ = sRing + r * 2 * Cfg::SUB;
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {   // S = Q K^T
-          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-          umma_f16(tmem + COL_S, make_sdesc(sQ + off, 16, 1024), make_sdesc(kbase + off, 16, 1024), idesc_kk,
-                   k != 0 ? 1u : 0u);
-        }
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k) {   // dP = dY V^T
-          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-          umma_f16(tmem + COL_DP, make_sdesc(sdY + off, 16, 1024), make_sdesc(vbase + off, 16, 1024), idesc_kk,
-                   k != 0 ? 1u : 0u);
-        }
-        umma_commit(smem_u32(&s_full));
-        mbar_wait(smem_u32(&ds_full), static_cast<uint32_t>(j) & 1u);   // dS (bf16) sits in TMEM columns [0,64)
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {        // dQ += dS K   (A from TMEM, K tile read MN-major)
-          umma_f16_ts(tmem + COL_DQ, tmem + COL_S + k * 8, make_sdesc(kbase + k * 2048, 16384, 1024), idesc_dq,
+        for (int k = 0; k < 4; ++k)          // dQ += dS K_sub   (A from TMEM, K sub-tile read MN-major)
+          umma_f16_ts(tmem + COL_DQ, tmem + (j & 1) * 128 + k * 8, make_sdesc(kb_ + k * 2048, 8192, 1024), idesc_dq,
                       (j | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(smem_u32(&kv_empty[st]));
+        umma_commit(smem_u32(&kv_empty[r]));
         if (j == T - 1) umma_commit(smem_u32(&dq_done));
       }
     }
   } else {
+    const int wg = (warp - 2) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int grow = q0 + row;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    constexpr float LOG2E = 1.4426950408889634f;
     const bool rvalid = grow < N;
-    const float l2 = rvalid ? lse[static_cast<long long>(b) * N + grow] * LOG2E : 0.f;
+    const float l2 = rvalid ? lse[static_cast<long long>(b) * N + grow] * kLog2e : 0.f;
     const float dl = rvalid ? delta[static_cast<long long>(b) * N + grow] : 0.f;
-    for (int j = 0; j < T; ++j) {
-      mbar_wait(smem_u32(&s_full), static_cast<uint32_t>(j) & 1u);
+    const uint32_t stage = tmem + lane_addr + wg * 128;
+    for (int j = wg; j < T; j += 2) {
+      mbar_wait(smem_u32(&s_full[wg]), static_cast<uint32_t>(j >> 1) & 1u);
       tc_fence_after();
-      const int key0 = j * 128;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32(tmem + lane_addr + COL_S + c * 32, sv);
-        tmem_ld_32x32(tmem + lane_addr + COL_DP + c * 32, dv);
-        tmem_ld_wait();
+      uint32_t sv[2][32], dv[2][32];
+      tmem_ld_32x32(stage, sv[0]);
+      tmem_ld_32x32(stage + 32, sv[1]);
+      tmem_ld_32x32(stage + 64, dv[0]);
+      tmem_ld_32x32(stage + 96, dv[1]);
+      tmem_ld_wait();
+      const int kv = rvalid ? N - j * 64 : 0;   // valid keys of this sub-tile for this row (0: whole row is padding)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float d0 = 0.f, d1 = 0.f;
-          if (rvalid && key0 + c * 32 + i < N)
-            d0 = exp2f(fmaf(__uint_as_float(sv[i]), LOG2E, -l2)) * (__uint_as_float(dv[i]) - dl);
-          if (rvalid && key0 + c * 32 + i + 1 < N)
-            d1 = exp2f(fmaf(__uint_as_float(sv[i + 1]), LOG2E, -l2)) * (__uint_as_float(dv[i + 1]) - dl);
+          const int e = c * 32 + i;
+          float d0 = ex2_approx(fmaf(__uint_as_float(sv[c][i]), kLog2e, -l2)) * (__uint_as_float(dv[c][i]) - dl);
+          float d1 = ex2_approx(fmaf(__uint_as_float(sv[c][i + 1]), kLog2e, -l2)) * (__uint_as_float(dv[c][i + 1]) - dl);
+          if (kv < 64) {
+            if (e >= kv) d0 = 0.f;
+            if (e + 1 >= kv) d1 = 0.f;
+          }
           pk[i >> 1] = pack_bf16(d0, d1);
         }
-        tmem_st_32x32_x16(tmem + lane_addr + COL_S + c * 16, pk);
+        tmem_st_32x32_x16(stage + c * 16, pk);
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(smem_u32(&ds_full));
+      mbar_arrive(smem_u32(&ds_full[wg]));
     }
     mbar_wait(smem_u32(&dq_done), 0);
     tc_fence_after();
     bf16* orow = dP3 + (static_cast<long long>(b) * N + grow) * 3 * D;   // dTheta slot: columns [0, D)
+    // the two warpgroups split the D columns of dQ
 #pragma unroll 1
-    for (int c = 0; c < D / 32; ++c) {
+    for (int c = wg * (D / 64); c < (wg + 1) * (D / 64); ++c) {
       uint32_t v[32];
       tmem_ld_32x32(tmem + lane_addr + COL_DQ + c * 32, v);
       tmem_ld_wait();
@@ -478,33 +532,36 @@ __global__ void __launch_bounds__(192, 1)
 }
 
 template <int D>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(FLASH_THREADS, 1)
     flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdY,
                          const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dP3,
                          int N, int kv_tiles) {
   using Cfg = FlashCfg<D>;
+  constexpr int RING = 4;
   extern __shared__ uint8_t fsm_raw[];
-  __shared__ uint64_t kv_full, q_full[2], q_empty[2], s_full, p_full, acc_done;
+  __shared__ uint64_t kv_full, q_full[RING], q_empty[RING], s_full[2], p_full[2], acc_done;
   __shared__ uint32_t tmem_holder;
-  __shared__ float lse_sm[2][128], del_sm[2][128];
+  __shared__ __align__(16) float lse_sm[2][2][64], del_sm[2][2][64];   // [warpgroup][buffer][query of the sub-tile]
   const uint32_t base = (smem_u32(fsm_raw) + 1023u) & ~1023u;
-  const uint32_t sK = base, sV = base + Cfg::TILE, sQ = base + 2 * Cfg::TILE, sdY = base + 4 * Cfg::TILE;
+  const uint32_t sK = base, sV = base + Cfg::TILE, sRing = base + 2 * Cfg::TILE;   // ring slot: Q_sub | dY_sub
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / kv_tiles, kt = blockIdx.x % kv_tiles;
   const int k0 = kt * 128;
-  const int T = (N + 127) / 128;   // query tiles
-  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 384;
+  const int T = (N + 63) / 64;   // 64-query sub-tiles
+  constexpr uint32_t COL_DV = 0, COL_DK = 128, COL_ST = 256;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdY);
     mbar_init(smem_u32(&kv_full), 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < RING; ++i) {
       mbar_init(smem_u32(&q_full[i]), 1);
       mbar_init(smem_u32(&q_empty[i]), 1);
     }
-    mbar_init(smem_u32(&s_full), 1);
-    mbar_init(smem_u32(&p_full), 128);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&p_full[i]), 128);
+    }
     mbar_init(smem_u32(&acc_done), 1);
     fence_mbar_init();
   }
@@ -523,128 +580,143 @@ __global__ void __launch_bounds__(192, 1)
         tma_load_4d(&tmV, smem_u32(&kv_full), sV + kb * 16384, kb * 64, k0, b, 0);
       }
       for (int i = 0; i < T; ++i) {
-        const int st = i & 1;
-        const uint32_t ph = static_cast<uint32_t>(i >> 1) & 1u;
-        mbar_wait(smem_u32(&q_empty[st]), ph ^ 1u);
-        mbar_expect_tx(smem_u32(&q_full[st]), 2 * Cfg::TILE);
+        const int r = i % RING;
+        const uint32_t ph = static_cast<uint32_t>(i / RING) & 1u;
+        mbar_wait(smem_u32(&q_empty[r]), ph ^ 1u);
+        mbar_expect_tx(smem_u32(&q_full[r]), 2 * Cfg::SUB);
+        const uint32_t slot = sRing + r * 2 * Cfg::SUB;
 #pragma unroll
         for (int kb = 0; kb < D / 64; ++kb) {
-          tma_load_4d(&tmQ, smem_u32(&q_full[st]), sQ + st * Cfg::TILE + kb * 16384, kb * 64, i * 128, b, 0);
-          tma_load_4d(&tmdY, smem_u32(&q_full[st]), sdY + st * Cfg::TILE + kb * 16384, kb * 64, i * 128, b, 0);
+          tma_load_4d(&tmQ, smem_u32(&q_full[r]), slot + kb * 8192, kb * 64, i * 64, b, 0);
+          tma_load_4d(&tmdY, smem_u32(&q_full[r]), slot + Cfg::SUB + kb * 8192, kb * 64, i * 64, b, 0);
         }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc_kk = make_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
       constexpr uint32_t idesc_acc = make_idesc_bf16(128, D, false, true);
+      auto issue_sdp = [&](int i) {
+        const int r = i % RING;
+        mbar_wait(smem_u32(&q_full[r]), static_cast<uint32_t>(i / RING) & 1u);
+        tc_fence_after();
+        const uint32_t qb_ = sRing + r * 2 * Cfg::SUB, yb_ = qb_ + Cfg::SUB;
+        const uint32_t stage = tmem + COL_ST + (i & 1) * 128;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {   // S^T = K Q_sub^T
+          const uint32_t offa = (k >> 2) * 16384 + (k & 3) * 32, offb = (k >> 2) * 8192 + (k & 3) * 32;
+          umma_f16(stage, make_sdesc(sK + offa, 16, 1024), make_sdesc(qb_ + offb, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {   // dP^T = V dY_sub^T
+          const uint32_t offa = (k >> 2) * 16384 + (k & 3) * 32, offb = (k >> 2) * 8192 + (k & 3) * 32;
+          umma_f16(stage + 64, make_sdesc(sV + offa, 16, 1024), make_sdesc(yb_ + offb, 16, 1024), idesc_s,
+                   k != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&s_full[i & 1]));
+      };
       mbar_wait(smem_u32(&kv_full), 0);
       tc_fence_after();
+      issue_sdp(0);
       for (int i = 0; i < T; ++i) {
-        const int st = i & 1;
-        const uint32_t ph = static_cast<uint32_t>(i >> 1) & 1u;
-        mbar_wait(smem_u32(&q_full[st]), ph);
+        const int r = i % RING;
+        if (i + 1 < T) issue_sdp(i + 1);
+        mbar_wait(smem_u32(&p_full[i & 1]), static_cast<uint32_t>(i >> 1) & 1u);   // P^T [0,32), dS^T [64,96) (bf16)
         tc_fence_after();
-        const uint32_t qbase = sQ + st * Cfg::TILE, ybase = sdY + st * Cfg::TILE;
+        const uint32_t qb_ = sRing + r * 2 * Cfg::SUB, yb_ = qb_ + Cfg::SUB;
+        const uint32_t stage = tmem + COL_ST + (i & 1) * 128;
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {   // S^T = K Q^T
-          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-          umma_f16(tmem + COL_S, make_sdesc(sK + off, 16, 1024), make_sdesc(qbase + off, 16, 1024), idesc_kk,
-                   k != 0 ? 1u : 0u);
-        }
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k) {   // dP^T = V dY^T
-          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-          umma_f16(tmem + COL_DP, make_sdesc(sV + off, 16, 1024), make_sdesc(ybase + off, 16, 1024), idesc_kk,
-                   k != 0 ? 1u : 0u);
-        }
-        umma_commit(smem_u32(&s_full));
-        mbar_wait(smem_u32(&p_full), static_cast<uint32_t>(i) & 1u);   // P^T in [0,64), dS^T in [128,192) (bf16)
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {        // dV += P^T dY   (dY tile read MN-major)
-          umma_f16_ts(tmem + COL_DV, tmem + COL_S + k * 8, make_sdesc(ybase + k * 2048, 16384, 1024), idesc_acc,
+        for (int k = 0; k < 4; ++k)          // dV += P^T dY_sub   (dY sub-tile read MN-major)
+          umma_f16_ts(tmem + COL_DV, stage + k * 8, make_sdesc(yb_ + k * 2048, 8192, 1024), idesc_acc,
                       (i | k) != 0 ? 1u : 0u);
-        }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {        // dK += dS^T Q   (Q tile read MN-major)
-          umma_f16_ts(tmem + COL_DK, tmem + COL_DP + k * 8, make_sdesc(qbase + k * 2048, 16384, 1024), idesc_acc,
+        for (int k = 0; k < 4; ++k)          // dK += dS^T Q_sub   (Q sub-tile read MN-major)
+          umma_f16_ts(tmem + COL_DK, stage + 64 + k * 8, make_sdesc(qb_ + k * 2048, 8192, 1024), idesc_acc,
                       (i | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(smem_u32(&q_empty[st]));
+        umma_commit(smem_u32(&q_empty[r]));
         if (i == T - 1) umma_commit(smem_u32(&acc_done));
       }
     }
   } else {
+    const int wg = (warp - 2) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;          // key row of this thread
     const int gkey = k0 + row;
     const bool kvalid = gkey < N;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const int e = (warp - 2) * 32 + lane;   // 0..127
-    constexpr float LOG2E = 1.4426950408889634f;
-    for (int i = 0; i < T; ++i) {
-      const int sb = i & 1;
-      {  // per-query lse / delta of this q tile (columns of S^T); double-buffered, published by a named barrier
-        const int gq = i * 128 + e;
-        lse_sm[sb][e] = gq < N ? lse[static_cast<long long>(b) * N + gq] * LOG2E : 0.f;
-        del_sm[sb][e] = gq < N ? delta[static_cast<long long>(b) * N + gq] : 0.f;
+    const int e = ((warp - 2) & 3) * 32 + lane;   // 0..127 inside the warpgroup
+    const uint32_t stage = tmem + lane_addr + COL_ST + wg * 128;
+    int sb = 0;
+    for (int i = wg; i < T; i += 2, sb ^= 1) {
+      {  // per-query lse / delta of this sub-tile (columns of S^T): published to the warpgroup by a named barrier
+        const int gq = i * 64 + (e & 63);
+        const bool ok = gq < N;
+        if (e < 64) lse_sm[wg][sb][e] = ok ? lse[static_cast<long long>(b) * N + gq] * kLog2e : 0.f;
+        else del_sm[wg][sb][e - 64] = ok ? delta[static_cast<long long>(b) * N + gq] : 0.f;
       }
-      named_bar_sync(1, 128);
-      mbar_wait(smem_u32(&s_full), static_cast<uint32_t>(i) & 1u);
+      named_bar_sync(1 + wg, 128);
+      mbar_wait(smem_u32(&s_full[wg]), static_cast<uint32_t>(i >> 1) & 1u);
       tc_fence_after();
-      const int qv = min(128, N - i * 128);   // valid queries in this tile
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32(tmem + lane_addr + COL_S + c * 32, sv);
-        tmem_ld_32x32(tmem + lane_addr + COL_DP + c * 32, dv);
-        tmem_ld_wait();
+      uint32_t sv[2][32], dv[2][32];
+      tmem_ld_32x32(stage, sv[0]);
+      tmem_ld_32x32(stage + 32, sv[1]);
+      tmem_ld_32x32(stage + 64, dv[0]);
+      tmem_ld_32x32(stage + 96, dv[1]);
+      tmem_ld_wait();
+      const int qv = kvalid ? N - i * 64 : 0;   // valid queries of this sub-tile for this key row
+      const float4* ls4 = reinterpret_cast<const float4*>(lse_sm[wg][sb]);
+      const float4* dl4 = reinterpret_cast<const float4*>(del_sm[wg][sb]);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t pp[16], pd[16];
 #pragma unroll
-        for (int t = 0; t < 32; t += 2) {
-          float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
+        for (int t = 0; t < 32; t += 4) {
           const int col = c * 32 + t;
-          if (kvalid && col < qv) {
-            p0 = exp2f(fmaf(__uint_as_float(sv[t]), LOG2E, -lse_sm[sb][col]));
-            d0 = p0 * (__uint_as_float(dv[t]) - del_sm[sb][col]);
+          const float4 L = ls4[col >> 2], Dl = dl4[col >> 2];
+          float p0 = ex2_approx(fmaf(__uint_as_float(sv[c][t]), kLog2e, -L.x));
+          float p1 = ex2_approx(fmaf(__uint_as_float(sv[c][t + 1]), kLog2e, -L.y));
+          float p2 = ex2_approx(fmaf(__uint_as_float(sv[c][t + 2]), kLog2e, -L.z));
+          float p3 = ex2_approx(fmaf(__uint_as_float(sv[c][t + 3]), kLog2e, -L.w));
+          if (qv < 64) {
+            if (col >= qv) p0 = 0.f;
+            if (col + 1 >= qv) p1 = 0.f;
+            if (col + 2 >= qv) p2 = 0.f;
+            if (col + 3 >= qv) p3 = 0.f;
           }
-          if (kvalid && col + 1 < qv) {
-            p1 = exp2f(fmaf(__uint_as_float(sv[t + 1]), LOG2E, -lse_sm[sb][col + 1]));
-            d1 = p1 * (__uint_as_float(dv[t + 1]) - del_sm[sb][col + 1]);
-          }
+          const float d0 = p0 * (__uint_as_float(dv[c][t]) - Dl.x);
+          const float d1 = p1 * (__uint_as_float(dv[c][t + 1]) - Dl.y);
+          const float d2 = p2 * (__uint_as_float(dv[c][t + 2]) - Dl.z);
+          const float d3 = p3 * (__uint_as_float(dv[c][t + 3]) - Dl.w);
           pp[t >> 1] = pack_bf16(p0, p1);
+          pp[(t >> 1) + 1] = pack_bf16(p2, p3);
           pd[t >> 1] = pack_bf16(d0, d1);
+          pd[(t >> 1) + 1] = pack_bf16(d2, d3);
         }
-        tmem_st_32x32_x16(tmem + lane_addr + COL_S + c * 16, pp);
-        tmem_st_32x32_x16(tmem + lane_addr + COL_DP + c * 16, pd);
+        tmem_st_32x32_x16(stage + c * 16, pp);
+        tmem_st_32x32_x16(stage + 64 + c * 16, pd);
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(smem_u32(&p_full));
+      mbar_arrive(smem_u32(&p_full[wg]));
     }
     mbar_wait(smem_u32(&acc_done), 0);
     tc_fence_after();
-    bf16* orow = dP3 + (static_cast<long long>(b) * N + gkey) * 3 * D;
+    // warpgroup 0 writes dK (dPhi slot), warpgroup 1 writes dV (dG slot)
+    bf16* orow = dP3 + (static_cast<long long>(b) * N + gkey) * 3 * D + (wg == 0 ? D : 2 * D);
+    const uint32_t acc = tmem + lane_addr + (wg == 0 ? COL_DK : COL_DV);
 #pragma unroll 1
     for (int c = 0; c < D / 32; ++c) {
-      uint32_t vk[32], vv[32];
-      tmem_ld_32x32(tmem + lane_addr + COL_DK + c * 32, vk);
-      tmem_ld_32x32(tmem + lane_addr + COL_DV + c * 32, vv);
+      uint32_t v[32];
+      tmem_ld_32x32(acc + c * 32, v);
       tmem_ld_wait();
       if (kvalid) {
 #pragma unroll
         for (int t = 0; t < 32; t += 8) {
-          uint4 a = make_uint4(pack_bf16(__uint_as_float(vk[t]), __uint_as_float(vk[t + 1])),
-                               pack_bf16(__uint_as_float(vk[t + 2]), __uint_as_float(vk[t + 3])),
-                               pack_bf16(__uint_as_float(vk[t + 4]), __uint_as_float(vk[t + 5])),
-                               pack_bf16(__uint_as_float(vk[t + 6]), __uint_as_float(vk[t + 7])));
-          uint4 g = make_uint4(pack_bf16(__uint_as_float(vv[t]), __uint_as_float(vv[t + 1])),
-                               pack_bf16(__uint_as_float(vv[t + 2]), __uint_as_float(vv[t + 3])),
-                               pack_bf16(__uint_as_float(vv[t + 4]), __uint_as_float(vv[t + 5])),
-                               pack_bf16(__uint_as_float(vv[t + 6]), __uint_as_float(vv[t + 7])));
-          *reinterpret_cast<uint4*>(orow + D + c * 32 + t) = a;        // dPhi slot
-          *reinterpret_cast<uint4*>(orow + 2 * D + c * 32 + t) = g;    // dG slot
+          uint4 a = make_uint4(pack_bf16(__uint_as_float(v[t]), __uint_as_float(v[t + 1])),
+                               pack_bf16(__uint_as_float(v[t + 2]), __uint_as_float(v[t + 3])),
+                               pack_bf16(__uint_as_float(v[t + 4]), __uint_as_float(v[t + 5])),
+                               pack_bf16(__uint_as_float(v[t + 6]), __uint_as_float(v[t + 7])));
+          *reinterpret_cast<uint4*>(orow + c * 32 + t) = a;
         }
       }
     }
@@ -694,27 +766,33 @@ template <int D>
 static int launch_flash_bwd(const bf16* P3, const bf16* dY, const float* lse, const float* delta, bf16* dP3, int B,
                             int N, cudaStream_t stream) {
   using Cfg = FlashCfg<D>;
-  CUtensorMap tq, tk, tv, ty;
+  // 128-row boxes for the operand that stays resident in a CTA, 64-row boxes for the streamed sub-tiles
+  CUtensorMap tq128, tk128, tv128, ty128, tq64, tk64, tv64, ty64;
   const long long seq = static_cast<long long>(N) * 3 * D;
+  const long long seqY = static_cast<long long>(N) * D;
   int rc;
-  if ((rc = make_tmap_bf16(&tq, P3, D, N, B, 3 * D, seq, 128))) return rc;
-  if ((rc = make_tmap_bf16(&tk, P3 + D, D, N, B, 3 * D, seq, 128))) return rc;
-  if ((rc = make_tmap_bf16(&tv, P3 + 2 * D, D, N, B, 3 * D, seq, 128))) return rc;
-  if ((rc = make_tmap_bf16(&ty, dY, D, N, B, D, static_cast<long long>(N) * D, 128))) return rc;
-  const uint32_t smem = Cfg::TILE * 6 + 1024;
+  if ((rc = make_tmap_bf16(&tq128, P3, D, N, B, 3 * D, seq, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tk128, P3 + D, D, N, B, 3 * D, seq, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tv128, P3 + 2 * D, D, N, B, 3 * D, seq, 128))) return rc;
+  if ((rc = make_tmap_bf16(&ty128, dY, D, N, B, D, seqY, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tq64, P3, D, N, B, 3 * D, seq, 64))) return rc;
+  if ((rc = make_tmap_bf16(&tk64, P3 + D, D, N, B, 3 * D, seq, 64))) return rc;
+  if ((rc = make_tmap_bf16(&tv64, P3 + 2 * D, D, N, B, 3 * D, seq, 64))) return rc;
+  if ((rc = make_tmap_bf16(&ty64, dY, D, N, B, D, seqY, 64))) return rc;
+  const uint32_t smem = Cfg::SMEM_BWD;
   const int tiles = (N + 127) / 128;
   {
     auto kern = flash_bwd_dq_kernel<D>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(flash_bwd_dq)");
-    kern<<<B * tiles, 192, smem, stream>>>(tq, tk, tv, ty, lse, delta, dP3, N, tiles);
+    kern<<<B * tiles, FLASH_THREADS, smem, stream>>>(tq128, tk64, tv64, ty128, lse, delta, dP3, N, tiles);
     if ((rc = check_cuda(cudaGetLastError(), "flash_bwd_dq launch"))) return rc;
   }
   {
     auto kern = flash_bwd_dkv_kernel<D>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(flash_bwd_dkv)");
-    kern<<<B * tiles, 192, smem, stream>>>(tq, tk, tv, ty, lse, delta, dP3, N, tiles);
+    kern<<<B * tiles, FLASH_THREADS, smem, stream>>>(tq64, tk128, tv128, ty64, lse, delta, dP3, N, tiles);
     if ((rc = check_cuda(cudaGetLastError(), "flash_bwd_dkv launch"))) return rc;
   }
   return 0;
@@ -730,10 +808,10 @@ static int launch_flash_fwd(const bf16* P3, bf16* Y, float* lse, int B, int N, c
   if ((rc = make_tmap_bf16(&tk, P3 + D, D, N, B, 3 * D, seq, 128))) return rc;
   if ((rc = make_tmap_bf16(&tv, P3 + 2 * D, D, N, B, 3 * D, seq, 128))) return rc;
   auto kern = flash_fwd_kernel<D>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_FWD);
   if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(flash_fwd)");
-  const int q_tiles = (N + 127) / 128;
-  kern<<<B * q_tiles, 192, Cfg::SMEM, stream>>>(tq, tk, tv, Y, lse, N, q_tiles);
+  const int q_pairs = (N + 255) / 256;
+  kern<<<B * q_pairs, FLASH_THREADS, Cfg::SMEM_FWD, stream>>>(tq, tk, tv, Y, lse, N, q_pairs);
   return check_cuda(cudaGetLastError(), "flash_fwd launch");
 }
 
