@@ -139,9 +139,13 @@ def run_ours(args):
     dz = torch.randn(B, V, HH, WW, C, device=dev, dtype=torch.bfloat16).permute(0, 4, 1, 2, 3)
     bucket = dp.GradBucket(list(fusion.global_attn._plist()) + list(fusion.local_attn._plist()))
 
+    params = [p for p in fusion.parameters() if p.requires_grad]
+
     def compute():
         for t in f4:
             t.grad = None
+        for p in params:
+            p.grad = None                # optimizer.zero_grad(set_to_none=True): gradients are assigned, not accumulated
         out = fusion.forward_stacked(f4, cls, ctr)
         out.backward(dz)
 

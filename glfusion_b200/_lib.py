@@ -17,7 +17,8 @@ PRECISIONS = {"bf16": PRECISION_BF16, "fp32": PRECISION_F32X3}
 
 EXPORTS = ("glf_version", "glf_last_error", "glf_tpavi_sizes", "glf_tpavi_fwd", "glf_tpavi_bwd",
            "glf_gate_concat_fwd", "glf_gate_concat_bwd", "glf_gemm_bf16", "glf_transpose", "glf_bn_res_ln_fwd",
-           "glf_bn_res_ln_bwd", "glf_bn_res_ln_bwd_max_blocks", "glf_gate_concat_bwd_scratch_bytes")
+           "glf_bn_res_ln_bwd", "glf_bn_res_ln_bwd_max_blocks", "glf_gate_concat_bwd_scratch_bytes",
+           "glf_fusion_ln_supported", "glf_fusion_ln_fwd", "glf_fusion_ln_bwd")
 
 
 class GlfDesc(C.Structure):
@@ -66,6 +67,11 @@ def load() -> C.CDLL:
         lib.glf_tpavi_fwd.argtypes = [C.POINTER(GlfDesc), vp, C.POINTER(GlfWeights), vp, vp, vp, vp]
         lib.glf_tpavi_bwd.argtypes = [C.POINTER(GlfDesc), vp, vp, C.POINTER(GlfWeights), vp, vp, C.POINTER(GlfGrads),
                                       vp, vp]
+        lib.glf_fusion_ln_supported.argtypes = [C.POINTER(GlfDesc)]
+        lib.glf_fusion_ln_fwd.argtypes = [C.POINTER(GlfDesc), vp, vp, C.POINTER(GlfWeights), C.POINTER(GlfWeights), vp,
+                                          vp, vp, vp]
+        lib.glf_fusion_ln_bwd.argtypes = [C.POINTER(GlfDesc), vp, vp, vp, C.POINTER(GlfWeights), C.POINTER(GlfWeights),
+                                          vp, vp, vp, vp, vp]
         pp = C.POINTER(C.c_void_p)
         lib.glf_gate_concat_fwd.argtypes = [i32] * 6 + [f32, i32, i32, pp, pp, pp, vp, vp, vp, vp]
         lib.glf_gate_concat_bwd.argtypes = [i32] * 6 + [f32, i32, i32, pp, pp, pp, vp, vp, vp, pp, pp, pp, vp, vp]

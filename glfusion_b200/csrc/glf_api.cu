@@ -183,7 +183,7 @@ size_t carve_ws_bwd(const glf_desc* d, const Dims& m, void* base, WsBwd* w) {
 int pick_split(long long tiles, int K) {
   const int kb = (K + 63) / 64;
   if (tiles >= 96) return 1;  // enough CTAs already: write the result directly, no atomics
-  long long s = (2 * 148 + tiles - 1) / tiles;
+  long long s = (2 * 148) / tiles;   // floor: tiles * s work items fill at most two full rounds of the 148 persistent CTAs
   if (s < 1) s = 1;
   if (s > kb) s = kb;
   return static_cast<int>(s);
@@ -200,6 +200,17 @@ GemmOperand opnd(const void* p, int mn, long long ld, long long bs) {
     int rc__ = (expr);       \
     if (rc__ != 0) return rc__; \
   } while (0)
+
+// reserved[0] = 1: the LayerNorm stage (forward epilogue / first backward kernel) is run for MGFM and MLFM together
+// by glf_fusion_ln_fwd / glf_fusion_ln_bwd instead of per block
+bool defer_ln(const glf_desc* d) { return d->reserved[0] == 1; }
+
+int check_pair(const glf_desc* d, const Dims& m) {
+  if (d->precision != GLF_PRECISION_BF16 || d->io_dtype != GLF_DTYPE_BF16 || m.pack_x || d->dz_layout != GLF_LAYOUT_TOKEN)
+    return set_error(GLF_ERR_UNSUPPORTED, "fused LayerNorm pair needs bf16 token-major activations");
+  if (!ln_tma_supported(m.C)) return set_error(GLF_ERR_UNSUPPORTED, "fused LayerNorm pair needs C <= 256");
+  return 0;
+}
 
 int check_ptr(const void* p, const char* name) {
   if (p == nullptr) return set_error(GLF_ERR_INVALID, "%s is NULL", name);
@@ -332,6 +343,7 @@ GLF_API int glf_tpavi_fwd(const glf_desc* d, const void* x, const glf_weights* w
   }
   GLF_TRY(bn_finalize(bn_part, np, C, static_cast<double>(m.rows), d, w, s.bn_mean, s.bn_rstd, s.bn_a, s.bn_b,
                       stream));
+  if (defer_ln(d)) return 0;   // the pair entry point glf_fusion_ln_fwd finishes both blocks in one pass
   GLF_TRY(bn_res_ln_fwd(s.U, X, GLF_DTYPE_BF16, s.bn_a, s.bn_b, w->ln_w, w->ln_b, z, d->io_dtype, s.ln_mu, s.ln_r,
                         m.rows, C, d->eps_ln, d->accumulate, stream));
   return 0;
@@ -362,14 +374,18 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
 
   const void* dZ = dz;
   int dz_dtype = d->io_dtype;
-  if (m.pack_dz) {
+  if (m.pack_dz && !defer_ln(d)) {
     GLF_TRY(transpose_cast(dz, wb.dztok, B, C, N, d->io_dtype, GLF_DTYPE_BF16, stream));
     dZ = wb.dztok;
     dz_dtype = GLF_DTYPE_BF16;
   }
-  const int nb = bn_res_ln_bwd_blocks(m.rows, C);
-  GLF_TRY(bn_res_ln_bwd(dZ, dz_dtype, s.U, X, GLF_DTYPE_BF16, s.bn_a, s.bn_b, s.bn_mean, s.bn_rstd, w->ln_w, s.ln_mu,
-                        s.ln_r, wb.dV, wb.part_ln, m.rows, C, stream));
+  int nb = 0;
+  if (defer_ln(d)) {
+    nb = ln_bwd_tma_blocks(m.rows);   // dV and the partials were written by glf_fusion_ln_bwd
+  } else {
+    GLF_TRY(bn_res_ln_bwd(dZ, dz_dtype, s.U, X, GLF_DTYPE_BF16, s.bn_a, s.bn_b, s.bn_mean, s.bn_rstd, w->ln_w, s.ln_mu,
+                          s.ln_r, wb.dV, wb.part_ln, m.rows, C, &nb, stream));
+  }
   GLF_TRY(bn_bwd_finalize(wb.part_ln, nb, C, static_cast<double>(m.rows), d, w, s.bn_mean, s.bn_rstd, g_, wb.k1, wb.k2,
                           wb.k3, stream));
   const bf16* dU = wb.dV;
@@ -523,6 +539,78 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
   return 0;
 }
 
+GLF_API int glf_fusion_ln_supported(const glf_desc* d) {
+  Dims m;
+  if (make_dims(d, &m) != 0) return 0;
+  return check_pair(d, m) == 0 ? 1 : 0;
+}
+
+GLF_API int glf_fusion_ln_fwd(const glf_desc* d, const void* xg, const void* xl, const glf_weights* wg,
+                              const glf_weights* wl, void* z, void* saved_g, void* saved_l, glf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  Dims m;
+  GLF_TRY(make_dims(d, &m));
+  GLF_TRY(check_device_sm100());
+  GLF_TRY(check_pair(d, m));
+  GLF_TRY(check_ptr(xg, "xg"));
+  GLF_TRY(check_ptr(xl, "xl"));
+  GLF_TRY(check_ptr(z, "z"));
+  GLF_TRY(check_ptr(saved_g, "saved_g"));
+  GLF_TRY(check_ptr(saved_l, "saved_l"));
+  if (wg == nullptr || wl == nullptr) return set_error(GLF_ERR_INVALID, "weights is NULL");
+  Saved sg, sl;
+  carve_saved(m, saved_g, &sg);
+  carve_saved(m, saved_l, &sl);
+  const bf16* U[2] = {sg.U, sl.U};
+  const bf16* X[2] = {reinterpret_cast<const bf16*>(xg), reinterpret_cast<const bf16*>(xl)};
+  const float* a[2] = {sg.bn_a, sl.bn_a};
+  const float* b[2] = {sg.bn_b, sl.bn_b};
+  const float* lw[2] = {wg->ln_w, wl->ln_w};
+  const float* lb[2] = {wg->ln_b, wl->ln_b};
+  float* mu[2] = {sg.ln_mu, sl.ln_mu};
+  float* r[2] = {sg.ln_r, sl.ln_r};
+  return ln_fwd_tma(2, U, X, a, b, lw, lb, mu, r, reinterpret_cast<bf16*>(z), m.rows, m.C, d->eps_ln, d->accumulate,
+                    stream);
+}
+
+GLF_API int glf_fusion_ln_bwd(const glf_desc* d, const void* dz, const void* xg, const void* xl, const glf_weights* wg,
+                              const glf_weights* wl, const void* saved_g, const void* saved_l, void* ws_g, void* ws_l,
+                              glf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  Dims m;
+  GLF_TRY(make_dims(d, &m));
+  GLF_TRY(check_device_sm100());
+  GLF_TRY(check_pair(d, m));
+  GLF_TRY(check_ptr(dz, "dz"));
+  GLF_TRY(check_ptr(xg, "xg"));
+  GLF_TRY(check_ptr(xl, "xl"));
+  GLF_TRY(check_ptr(saved_g, "saved_g"));
+  GLF_TRY(check_ptr(saved_l, "saved_l"));
+  GLF_TRY(check_ptr(ws_g, "ws_g"));
+  GLF_TRY(check_ptr(ws_l, "ws_l"));
+  if (wg == nullptr || wl == nullptr) return set_error(GLF_ERR_INVALID, "weights is NULL");
+  Saved sg, sl;
+  WsBwd bg, bl;
+  carve_saved(m, const_cast<void*>(saved_g), &sg);
+  carve_saved(m, const_cast<void*>(saved_l), &sl);
+  carve_ws_bwd(d, m, ws_g, &bg);
+  carve_ws_bwd(d, m, ws_l, &bl);
+  const bf16* U[2] = {sg.U, sl.U};
+  const bf16* X[2] = {reinterpret_cast<const bf16*>(xg), reinterpret_cast<const bf16*>(xl)};
+  const float* a[2] = {sg.bn_a, sl.bn_a};
+  const float* b[2] = {sg.bn_b, sl.bn_b};
+  const float* lw[2] = {wg->ln_w, wl->ln_w};
+  const float* mean[2] = {sg.bn_mean, sl.bn_mean};
+  const float* rstd[2] = {sg.bn_rstd, sl.bn_rstd};
+  const float* mu[2] = {sg.ln_mu, sl.ln_mu};
+  const float* r[2] = {sg.ln_r, sl.ln_r};
+  bf16* dV[2] = {bg.dV, bl.dV};
+  float* part[2] = {bg.part_ln, bl.part_ln};
+  int nb = 0;
+  return ln_bwd_tma(2, reinterpret_cast<const bf16*>(dz), U, X, a, b, lw, mean, rstd, mu, r, dV, part, m.rows, m.C, &nb,
+                    stream);
+}
+
 GLF_API int glf_gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, int x_dtype,
                         const void* const* f4, const float* const* cls, const float* const* ctr, void* xg, void* xl,
                         float* gate, glf_stream_t stream) {
@@ -594,9 +682,8 @@ GLF_API int glf_bn_res_ln_bwd(int64_t rows, int C, const void* dZ, int dz_dtype,
   GLF_TRY(check_ptr(X, "X"));
   GLF_TRY(check_ptr(dV, "dV"));
   if (rows <= 0) return set_error(GLF_ERR_INVALID, "empty input");
-  if (nblocks_out) *nblocks_out = bn_res_ln_bwd_blocks(rows, C);
   return bn_res_ln_bwd(dZ, dz_dtype, U, X, GLF_DTYPE_BF16, bn_a, bn_b, bn_mean, bn_rstd, ln_w, mu, r, dV, part, rows, C,
-                       reinterpret_cast<cudaStream_t>(stream));
+                       nblocks_out, reinterpret_cast<cudaStream_t>(stream));
 }
 
 GLF_API int glf_bn_res_ln_bwd_max_blocks(void) { return 148 * 2; }

@@ -133,7 +133,7 @@ void six_pairs(GemmArgs& g) {
 int pick_split3(long long tiles, int K) {
   const int kb = (K + 63) / 64;
   if (tiles >= 96) return 1;
-  long long s = (2 * 148 + tiles - 1) / tiles;
+  long long s = (2 * 148) / tiles;   // floor: at most two full rounds of the 148 persistent CTAs
   if (s < 1) s = 1;
   if (s > kb) s = kb;
   return static_cast<int>(s);
@@ -265,9 +265,9 @@ int tpavi_bwd_f32x3(const glf_desc* d, const void* dz, const void* x, const glf_
     dZ = wb.dZf;
     dz_dtype = GLF_DTYPE_F32;
   }
-  const int nb = bn_res_ln_bwd_blocks(m.rows, C);
+  int nb = 0;
   GLF_TRY(bn_res_ln_bwd(dZ, dz_dtype, s.Uf, Xf, GLF_DTYPE_F32, s.bn_a, s.bn_b, s.bn_mean, s.bn_rstd, w->ln_w, s.ln_mu,
-                        s.ln_r, wb.dVf, wb.part_ln, m.rows, C, stream));
+                        s.ln_r, wb.dVf, wb.part_ln, m.rows, C, &nb, stream));
   GLF_TRY(bn_bwd_finalize(wb.part_ln, nb, C, static_cast<double>(m.rows), d, w, s.bn_mean, s.bn_rstd, g_, wb.k1, wb.k2,
                           wb.k3, stream));
   const float* dUf = wb.dVf;

@@ -4,6 +4,8 @@
 // All row kernels use 128-bit loads/stores, one warp per (row, 256-channel slice), warp-shuffle reductions, and
 // per-CTA partials + fixed-order finalisation for every cross-row (per-channel) statistic, so results are
 // deterministic (SURVEY.md §7 "hard parts").
+#include <cstdlib>
+
 #include "glf_internal.h"
 #include "glf_ptx.cuh"
 
@@ -639,6 +641,16 @@ __global__ void prep_weights_f32_kernel(const float* __restrict__ tw, const floa
   }
 }
 
+template <typename... P>
+bool aligned16(const P*... ptrs) {
+  return (((reinterpret_cast<uintptr_t>(ptrs)) | ...) & 15) == 0;
+}
+// GLF_DEBUG_LN_REG=1 forces the register-prefetch LayerNorm kernels (A/B against the bulk-copy staged ones)
+bool debug_reg_ln() {
+  const char* e = getenv("GLF_DEBUG_LN_REG");
+  return e != nullptr && e[0] == '1';
+}
+
 int row_grid(long long rows, int S) {
   const int RPB = ROW_WARPS / S;
   long long blocks = (rows + RPB - 1) / RPB;
@@ -706,6 +718,14 @@ int bn_res_ln_fwd(const void* U_, const void* X_, int act_dtype, const float* a,
                   const float* lb, void* Z, int z_dtype, float* mu, float* r, long long rows, int C, float eps,
                   int accumulate, cudaStream_t stream) {
   if (C % 8 != 0 || C > 2048) return set_error(GLF_ERR_INVALID, "LayerNorm kernel needs C %% 8 == 0 and C <= 2048");
+  if (act_dtype == GLF_DTYPE_BF16 && z_dtype == GLF_DTYPE_BF16 && U_ != nullptr && ln_tma_supported(C) &&
+      aligned16(U_, X_, Z, a, b, lw, lb) && !debug_reg_ln()) {
+    const bf16* Ua[1] = {(const bf16*)U_};
+    const bf16* Xa[1] = {(const bf16*)X_};
+    const float *aa[1] = {a}, *ba[1] = {b}, *lwa[1] = {lw}, *lba[1] = {lb};
+    float *mua[1] = {mu}, *ra[1] = {r};
+    return ln_fwd_tma(1, Ua, Xa, aa, ba, lwa, lba, mua, ra, (bf16*)Z, rows, C, eps, accumulate, stream);
+  }
   int S = (C + 255) / 256;
   while (ROW_WARPS % S != 0) ++S;
   const int grid = row_grid(rows, S);
@@ -734,11 +754,22 @@ int bn_res_ln_bwd_blocks(long long rows, int C) {
 
 int bn_res_ln_bwd(const void* dZ, int dz_dtype, const void* U_, const void* X_, int act_dtype, const float* a,
                   const float* b, const float* mean, const float* rstd, const float* lw, const float* mu,
-                  const float* r, void* dV_, float* part, long long rows, int C, cudaStream_t stream) {
+                  const float* r, void* dV_, float* part, long long rows, int C, int* nblocks, cudaStream_t stream) {
   if (C % 8 != 0 || C > 2048) return set_error(GLF_ERR_INVALID, "LayerNorm kernel needs C %% 8 == 0 and C <= 2048");
+  if (act_dtype == GLF_DTYPE_BF16 && dz_dtype == GLF_DTYPE_BF16 && U_ != nullptr && ln_tma_supported(C) &&
+      aligned16(dZ, U_, X_, dV_, a, b, lw, mu, r) && !debug_reg_ln()) {
+    const bf16* Ua[1] = {(const bf16*)U_};
+    const bf16* Xa[1] = {(const bf16*)X_};
+    const float *aa[1] = {a}, *ba[1] = {b}, *lwa[1] = {lw}, *mna[1] = {mean}, *rsa[1] = {rstd}, *mua[1] = {mu},
+                *ra[1] = {r};
+    bf16* dVa[1] = {(bf16*)dV_};
+    float* pa[1] = {part};
+    return ln_bwd_tma(1, (const bf16*)dZ, Ua, Xa, aa, ba, lwa, mna, rsa, mua, ra, dVa, pa, rows, C, nblocks, stream);
+  }
   int S = (C + 255) / 256;
   while (ROW_WARPS % S != 0) ++S;
   const int grid = bn_res_ln_bwd_blocks(rows, C);
+  if (nblocks) *nblocks = grid;
   if (act_dtype == GLF_DTYPE_BF16) {
     const bf16* U = (const bf16*)U_; const bf16* X = (const bf16*)X_; bf16* dV = (bf16*)dV_;
     if (dz_dtype == GLF_DTYPE_BF16)

@@ -308,15 +308,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         __syncwarp();
         const int rows_valid = min(32, p.M - (m0 + q * 32));   // valid rows of this warp's sub-block (may be <= 0)
         if (p.colstats != nullptr) {
-          // lane = column: sum the stored (bf16-rounded) values over the sub-block's valid rows
-          float s1 = 0.f, s2 = 0.f;
-          const int cch = lane >> 3, cel = (lane & 7) * 2;
-          for (int r = 0; r < rows_valid; ++r) {
-            const float x = __bfloat162float(
-                *reinterpret_cast<const bf16*>(wstg + r * 64 + ((cch ^ ((r >> 1) & 3)) << 4) + cel));
-            s1 += x;
-            s2 = fmaf(x, x, s2);
+          // sums of the stored (bf16-rounded) values over the sub-block's valid rows: each half-warp takes 16 rows,
+          // each lane a column pair (16 independent 32-bit shared loads, fully unrolled), then the halves are
+          // combined and the result redistributed so that lane = column
+          const int hl = lane & 15, half = lane >> 4;
+          float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int r = half * 16 + i;
+            if (r < rows_valid) {
+              const float2 x = unpack_bf16(*reinterpret_cast<const uint32_t*>(
+                  wstg + r * 64 + (((hl >> 2) ^ ((i >> 1) & 3)) << 4) + (hl & 3) * 4));
+              a1 += x.x;
+              a2 = fmaf(x.x, x.x, a2);
+              b1 += x.y;
+              b2 = fmaf(x.y, x.y, b2);
+            }
           }
+          a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+          a2 += __shfl_xor_sync(0xffffffffu, a2, 16);
+          b1 += __shfl_xor_sync(0xffffffffu, b1, 16);
+          b2 += __shfl_xor_sync(0xffffffffu, b2, 16);
+          const int src = lane >> 1;
+          const float t1a = __shfl_sync(0xffffffffu, a1, src), t1b = __shfl_sync(0xffffffffu, b1, src);
+          const float t2a = __shfl_sync(0xffffffffu, a2, src), t2b = __shfl_sync(0xffffffffu, b2, src);
+          const float s1 = (lane & 1) ? t1b : t1a;
+          const float s2 = (lane & 1) ? t2b : t2a;
           if (p.cs_accum) {
             const int slot = nt * CPW + (c >> 2);
 #pragma unroll

@@ -60,9 +60,20 @@ int bn_res_ln_fwd(const void* U, const void* X, int act_dtype, const float* a, c
                   const float* lb, void* Z, int z_dtype, float* mu, float* r, long long rows, int C, float eps,
                   int accumulate, cudaStream_t stream);
 int bn_res_ln_bwd_blocks(long long rows, int C);
+// *nblocks (optional) receives the number of partial rows written to `part` (<= bn_res_ln_bwd_blocks(rows, C))
 int bn_res_ln_bwd(const void* dZ, int dz_dtype, const void* U, const void* X, int act_dtype, const float* a,
                   const float* b, const float* mean, const float* rstd, const float* lw, const float* mu,
-                  const float* r, void* dV, float* part, long long rows, int C, cudaStream_t stream);
+                  const float* r, void* dV, float* part, long long rows, int C, int* nblocks, cudaStream_t stream);
+// bulk-copy staged forms (glf_ln.cu): bf16 activations, C <= 256; nmod = 2 fuses the MGFM and MLFM LayerNorms
+bool ln_tma_supported(int C);
+int ln_bwd_tma_blocks(long long rows);
+int ln_fwd_tma(int nmod, const bf16* const* U, const bf16* const* X, const float* const* a, const float* const* b,
+               const float* const* lw, const float* const* lb, float* const* mu, float* const* r, bf16* Z,
+               long long rows, int C, float eps, int accumulate, cudaStream_t stream);
+int ln_bwd_tma(int nmod, const bf16* dZ, const bf16* const* U, const bf16* const* X, const float* const* a,
+               const float* const* b, const float* const* lw, const float* const* bn_mean,
+               const float* const* bn_rstd, const float* const* mu, const float* const* r, bf16* const* dV,
+               float* const* part, long long rows, int C, int* nblocks, cudaStream_t stream);
 int bn_bwd_finalize(const float* part, int np, int C, double count, const glf_desc* d, const glf_weights* w,
                     const float* mean, const float* rstd, const glf_grads* g, float* k1, float* k2, float* k3,
                     cudaStream_t stream);

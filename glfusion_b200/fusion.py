@@ -19,7 +19,18 @@ import torch
 from torch import nn
 
 from . import _lib as L
-from .tpavi import TPAVIModule, _io_dtype, _stream_ptr, tpavi_backward_raw, tpavi_forward_raw
+from .tpavi import (TPAVIModule, TPAVIState, _blob, _io_dtype, _stream_ptr, _weights_struct, tpavi_backward_raw,
+                    tpavi_forward_raw)
+
+
+def _pair_ln_ok(mg, ml, shape, x, prec) -> bool:
+    """True when the MGFM / MLFM LayerNorm stages can run as one fused pass (glf_fusion_ln_fwd / _bwd)."""
+    if mg.inter_channels != ml.inter_channels or mg._mode_id != ml._mode_id or mg._bn_layer != ml._bn_layer:
+        return False
+    B, T, H, W, C_ = shape
+    st = TPAVIState(B, C_, T, H, W, mg.inter_channels, mg._mode_id, _io_dtype(x), L.LAYOUT_TOKEN, mg.training,
+                    mg._bn_layer, precision=prec, defer_ln=True)
+    return bool(L.load().glf_fusion_ln_supported(C.byref(st.desc)))
 
 
 def gate_concat_forward(f4: Sequence[torch.Tensor], cls: Sequence[torch.Tensor], ctr: Sequence[torch.Tensor],
@@ -79,12 +90,24 @@ class _FusionFunction(torch.autograd.Function):
         need = any(ctx.needs_input_grad)
         tg, tl = mg._param_table(pg), ml._param_table(pl)
         shape = (B, V_, h, w, C_)
+        pair = _pair_ln_ok(mg, ml, shape, xg, prec)
         zsum, stg, svg, _ = tpavi_forward_raw(xg, tg, mg._buffer_table(), mode=mg._mode_id, training=mg.training,
-                                              bn_layer=mg._bn_layer, Ci=mg.inter_channels, keep_for_backward=need,
-                                              token_shape=shape, precision=prec)
+                                              bn_layer=mg._bn_layer, Ci=mg.inter_channels,
+                                              keep_for_backward=need or pair, token_shape=shape, precision=prec,
+                                              defer_ln=pair)
         _, stl, svl, _ = tpavi_forward_raw(xl, tl, ml._buffer_table(), mode=ml._mode_id, training=ml.training,
-                                           bn_layer=ml._bn_layer, Ci=ml.inter_channels, keep_for_backward=need,
-                                           z_out=zsum, accumulate=True, token_shape=shape, precision=prec)
+                                           bn_layer=ml._bn_layer, Ci=ml.inter_channels,
+                                           keep_for_backward=need or pair, z_out=zsum, accumulate=not pair,
+                                           token_shape=shape, precision=prec, defer_ln=pair)
+        if pair:
+            # both blocks' BN + residual + LayerNorm and the `global + local` sum (ours.py:1834) in one HBM pass
+            wg, wl = _weights_struct(tg, mg._buffer_table()), _weights_struct(tl, ml._buffer_table())
+            with torch.cuda.device(xg.device):
+                L.check(L.load().glf_fusion_ln_fwd(C.byref(stg.desc), L.ptr(xg), L.ptr(xl), C.byref(wg), C.byref(wl),
+                                                   L.ptr(zsum), L.ptr(svg), L.ptr(svl), _stream_ptr()))
+            if not need:
+                svg = svl = None
+        ctx.pair = pair
         ctx.fusion, ctx.V, ctx.ng = fusion, V, ng
         ctx.states = (stg, svg, stl, svl)
         ctx.io_dtype = f4[0].dtype
@@ -108,8 +131,19 @@ class _FusionFunction(torch.autograd.Function):
         if dz.dtype != xg.dtype:
             dz = dz.to(xg.dtype)
         dz = dz.contiguous()                        # token-major [B,V,h,w,C]; both blocks see the same dz (ours.py:1834)
-        dxg, gg = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xg, stg, svg, mg._param_table(pg), mg._buffer_table())
-        dxl, gl = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xl, stl, svl, ml._param_table(pl), ml._buffer_table())
+        tg, tl = mg._param_table(pg), ml._param_table(pl)
+        wsg = wsl = None
+        if ctx.pair:
+            # LayerNorm backward of both blocks in one pass (dz is read once); fills dV / partials inside each ws blob
+            stg.desc.dz_layout = stl.desc.dz_layout = L.LAYOUT_TOKEN
+            wsg, wsl = _blob(stg.sizes.ws_bwd_bytes, xg.device), _blob(stl.sizes.ws_bwd_bytes, xg.device)
+            wg, wl = _weights_struct(tg, mg._buffer_table()), _weights_struct(tl, ml._buffer_table())
+            with torch.cuda.device(xg.device):
+                L.check(L.load().glf_fusion_ln_bwd(C.byref(stg.desc), L.ptr(dz), L.ptr(xg), L.ptr(xl), C.byref(wg),
+                                                   C.byref(wl), L.ptr(svg), L.ptr(svl), L.ptr(wsg), L.ptr(wsl),
+                                                   _stream_ptr()))
+        dxg, gg = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xg, stg, svg, tg, mg._buffer_table(), ws=wsg)
+        dxl, gl = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xl, stl, svl, tl, ml._buffer_table(), ws=wsl)
         df4, dcls, dctr = gate_concat_backward(f4, cls, ctr, gate, dxg, dxl, ctx.fusion.center_aware_weight)
         out = [None, None, None] + list(df4) + list(dcls) + list(dctr)
         for mod, plist, gr in ((mg, pg, gg), (ml, pl, gl)):

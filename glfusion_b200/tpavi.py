@@ -61,7 +61,7 @@ class TPAVIState:
     """Everything one forward/backward pair shares: descriptor, weights table, saved blob."""
 
     def __init__(self, B, C_, T, H, W, Ci, mode, io_dtype, x_layout, training, bn_layer, accumulate=False,
-                 eps_bn=1e-5, eps_ln=1e-5, momentum=0.1, precision=L.PRECISION_BF16):
+                 eps_bn=1e-5, eps_ln=1e-5, momentum=0.1, precision=L.PRECISION_BF16, defer_ln=False):
         d = L.GlfDesc()
         d.B, d.T, d.H, d.W, d.C, d.Ci = B, T, H, W, C_, Ci
         d.mode = mode
@@ -73,6 +73,7 @@ class TPAVIState:
         d.bn_layer = int(bn_layer)
         d.accumulate = int(accumulate)
         d.eps_bn, d.eps_ln, d.momentum = eps_bn, eps_ln, momentum
+        d.reserved[0] = 1 if defer_ln else 0     # LayerNorm stage run for MGFM + MLFM together (glf_fusion_ln_*)
         self.desc = d
         sz = L.GlfSizes()
         L.check(L.load().glf_tpavi_sizes(C.byref(d), C.byref(sz)))
@@ -92,7 +93,8 @@ def _weights_struct(p, buffers) -> L.GlfWeights:
 
 def tpavi_forward_raw(x: torch.Tensor, params: dict, buffers, *, mode: int, training: bool, bn_layer: bool,
                       Ci: int, keep_for_backward: bool, z_out: Optional[torch.Tensor] = None,
-                      accumulate: bool = False, token_shape=None, precision: int = L.PRECISION_BF16):
+                      accumulate: bool = False, token_shape=None, precision: int = L.PRECISION_BF16,
+                      defer_ln: bool = False):
     """Run glf_tpavi_fwd.  ``x`` is either NCTHW-contiguous or token-major (see ``_is_token_major``), or, when
     ``token_shape=(B,T,H,W,C)`` is given, a dense token-major buffer of that shape.
     Returns (z_buffer [B,T,H,W,C], state, saved_blob)."""
@@ -110,7 +112,7 @@ def tpavi_forward_raw(x: torch.Tensor, params: dict, buffers, *, mode: int, trai
             x = x.contiguous()
             layout = L.LAYOUT_NCTHW
     st = TPAVIState(B, C_, T, H, W, Ci, mode, _io_dtype(x), layout, training, bn_layer, accumulate,
-                    precision=precision)
+                    precision=precision, defer_ln=defer_ln)
     dev = x.device
     if z_out is None:
         z_out = torch.empty((B, T, H, W, C_), dtype=x.dtype, device=dev)
@@ -124,7 +126,8 @@ def tpavi_forward_raw(x: torch.Tensor, params: dict, buffers, *, mode: int, trai
 
 
 def tpavi_backward_raw(dz: torch.Tensor, dz_layout: int, x: torch.Tensor, st: TPAVIState, saved: torch.Tensor,
-                       params: dict, buffers, dx_out: Optional[torch.Tensor] = None):
+                       params: dict, buffers, dx_out: Optional[torch.Tensor] = None,
+                       ws: Optional[torch.Tensor] = None):
     """Run glf_tpavi_bwd.  Returns (dx buffer in the layout of x, dict of fp32 parameter gradients)."""
     lib = L.load()
     dev = x.device
@@ -147,7 +150,8 @@ def tpavi_backward_raw(dz: torch.Tensor, dz_layout: int, x: torch.Tensor, st: TP
             dx_out = torch.empty((d.B, d.C, d.T, d.H, d.W), dtype=x.dtype, device=dev)
     sz = L.GlfSizes()
     L.check(lib.glf_tpavi_sizes(C.byref(d), C.byref(sz)))
-    ws = _blob(sz.ws_bwd_bytes, dev)
+    if ws is None:
+        ws = _blob(sz.ws_bwd_bytes, dev)
     w = _weights_struct(params, buffers)
     with torch.cuda.device(dev):
         L.check(lib.glf_tpavi_bwd(C.byref(d), L.ptr(dz), L.ptr(x), C.byref(w), L.ptr(saved), L.ptr(dx_out),

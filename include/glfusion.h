@@ -63,7 +63,9 @@ typedef struct glf_desc {
   int32_t bn_layer;   /* 1: W_z = conv + BN ; 0: W_z = conv only (ours.py:829-833) */
   int32_t accumulate; /* fwd: z += result instead of z = result (fuses f4_global + f4_local, ours.py:1834) */
   float eps_bn, eps_ln, momentum;
-  int32_t reserved[4];
+  int32_t reserved[4]; /* reserved[0] = 1: "deferred LayerNorm" — glf_tpavi_fwd stops after the BatchNorm statistics and
+                          glf_tpavi_bwd starts after the LayerNorm backward; the caller runs that stage for MGFM and
+                          MLFM together with glf_fusion_ln_fwd / glf_fusion_ln_bwd (below).  Others: 0. */
 } glf_desc;
 
 /* fp32 master parameters, same shapes as the reference state_dict. */
@@ -115,6 +117,22 @@ GLF_API int glf_tpavi_fwd(const glf_desc* d, const void* x, const glf_weights* w
 /* dx (layout/dtype of x) and all parameter gradients from dz.  `x` is the forward input again. */
 GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, const glf_weights* w, const void* saved,
                   void* dx, const glf_grads* g, void* ws, glf_stream_t stream);
+
+/* Fused call site (ours.py:1821-1834): out = MGFM(x_g) + MLFM(x_l).  The two blocks' residual + LayerNorm stages are
+ * HBM-bound and share a tensor each way (the output sum forward, dz backward), so they run as ONE pass:
+ *   1. glf_tpavi_fwd(d, x_g, w_g, z, saved_g, ws)  and  glf_tpavi_fwd(d, x_l, w_l, z, saved_l, ws)  with
+ *      d->reserved[0] = 1  (everything up to the BatchNorm statistics; z is not written),
+ *   2. glf_fusion_ln_fwd: z (+)= LN_g(BN_g(U_g) + x_g) + LN_l(BN_l(U_l) + x_l)   (d->accumulate honoured),
+ *   3. backward: glf_fusion_ln_bwd fills dV / the per-channel partials inside ws_g and ws_l (each sized
+ *      ws_bwd_bytes), then glf_tpavi_bwd(d, dz, x_g, ..., ws_g) and glf_tpavi_bwd(d, dz, x_l, ..., ws_l) with
+ *      d->reserved[0] = 1 continue from there.
+ * Requirements (glf_fusion_ln_supported returns 1): bf16 token-major x / dz, GLF_PRECISION_BF16, C <= 256. */
+GLF_API int glf_fusion_ln_supported(const glf_desc* d);
+GLF_API int glf_fusion_ln_fwd(const glf_desc* d, const void* xg, const void* xl, const glf_weights* wg,
+                      const glf_weights* wl, void* z, void* saved_g, void* saved_l, glf_stream_t stream);
+GLF_API int glf_fusion_ln_bwd(const glf_desc* d, const void* dz, const void* xg, const void* xl, const glf_weights* wg,
+                      const glf_weights* wl, const void* saved_g, const void* saved_l, void* ws_g, void* ws_l,
+                      glf_stream_t stream);
 
 /* Gate + view concat (ours.py:1802-1820,1826-1827).
  *   f4[v]  : [B, C, h, w]  io_dtype, NCHW contiguous, v < V (host array of V device pointers, V <= 8)
