@@ -41,17 +41,60 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle sampling during the timed region."""
+    """SM clock / throttle-reason sampling DURING the timed region: an NVML polling thread (5 ms period) in this
+    process; `nvidia-smi -lms` as the fallback when NVML cannot be loaded."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+            0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index: int):
         self.index = index
         self.rows = []
         self.proc = None
+        self.nvml = None
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        return pynvml, h
+
+    def _poll(self, nv, h):
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = int(get_reasons(h))
+                for bit, name in self.BITS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            nv, h = self._nvml_handle()
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.nvml = nv
+            self.th = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
@@ -66,6 +109,12 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.th.join(timeout=1)
+            sm = sorted(self.samples)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -89,7 +138,7 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -271,32 +320,41 @@ def run_ours(args):
 def count_launches(clips: int, C: int) -> int:
     """Kernels launched by libglf_sm100a per step (fwd+bwd, both modules + gate), counted from the orchestration in
     glfusion_b200/csrc/glf_api.cu (memset/memcpy nodes excluded)."""
-    fwd_mod = 7          # prep_weights, proj GEMM, M GEMM, W' small GEMM, U GEMM, bn_finalize, bn_res_ln_fwd
-    bwd_mod = 12         # ln_bwd, finalize, apply, dTheta, dW', dWz, dM, dPhi, dG, dWcat, dX, bias reductions
-    return 2 * (fwd_mod + bwd_mod) + 2
+    fwd_mod = 7          # prep_weights, proj GEMM, M GEMM, W' GEMM, U GEMM, BN stats reduce, bn_finalize
+    bwd_mod = 12         # finalize, apply, dTheta, dW', dWz, dM, dPhi, dG, dWcat, dX, 2 bias-gradient reductions
+    pair = 2             # fused MGFM+MLFM LayerNorm forward / backward
+    gate = 3             # gate_concat fwd, gate_concat bwd, gate_finish
+    return 2 * (fwd_mod + bwd_mod) + pair + gate
 
 
 def kernel_probe(args, dev, clips, C, pk):
-    """Time the dominant HBM-bound kernel in isolation (CUDA events on the launching stream) -> roofline object.
-    Dominant kernel of the step per the ncu launch list under profiles/: bn_res_ln_bwd_kernel (LN/BN backward)."""
+    """Time the dominant kernel of the step alone, with CUDA events on the launching stream -> roofline object.
+    Dominant kernel per the ncu launch list under profiles/: ln_bwd_tma_kernel<2>, the fused MGFM+MLFM LayerNorm /
+    BatchNorm backward (HBM-bound: reads dZ, U_g, X_g, U_l, X_l; writes dV_g, dV_l = 7 bf16 passes over [rows, C])."""
     import ctypes as Ct
     from glfusion_b200 import _lib as L
     lib = L.load()
     rows = clips * F * V * HH * WW
-    U = torch.randn(rows, C, device=dev).to(torch.bfloat16)
-    X = torch.randn(rows, C, device=dev).to(torch.bfloat16)
-    dZ = torch.randn(rows, C, device=dev).to(torch.bfloat16)
-    dV = torch.empty_like(U)
-    vec = torch.rand(5, C, device=dev) + 0.5
-    rowst = torch.rand(2, rows, device=dev) + 0.5
-    part = torch.empty(lib.glf_bn_res_ln_bwd_max_blocks() * 4 * C, device=dev)
+
+    def bf(*shape):
+        return torch.randn(*shape, device=dev).to(torch.bfloat16)
+    U, X = [bf(rows, C), bf(rows, C)], [bf(rows, C), bf(rows, C)]
+    dZ = bf(rows, C)
+    dV = [torch.empty_like(U[0]), torch.empty_like(U[0])]
+    vec = [torch.rand(5, C, device=dev) + 0.5 for _ in range(2)]
+    rowst = [torch.rand(2, rows, device=dev) + 0.5 for _ in range(2)]
+    part = [torch.empty(lib.glf_bn_res_ln_bwd_max_blocks() * 4 * C, device=dev) for _ in range(2)]
     nb = Ct.c_int(0)
     stream = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
 
+    def tab(ts):
+        return (Ct.c_void_p * 2)(*[t.data_ptr() for t in ts])
+    args_ = (rows, C, L.ptr(dZ), tab(U), tab(X), tab([v[0] for v in vec]), tab([v[1] for v in vec]),
+             tab([v[3] for v in vec]), tab([v[4] for v in vec]), tab([v[2] for v in vec]),
+             tab([t[0] for t in rowst]), tab([t[1] for t in rowst]), tab(dV), tab(part), Ct.byref(nb), stream)
+
     def launch():
-        L.check(lib.glf_bn_res_ln_bwd(rows, C, L.ptr(dZ), L.DTYPE_BF16, L.ptr(U), L.ptr(X), L.ptr(vec[0]), L.ptr(vec[1]),
-                                      L.ptr(vec[2]), L.ptr(vec[3]), L.ptr(vec[4]), L.ptr(rowst[0]), L.ptr(rowst[1]),
-                                      L.ptr(dV), L.ptr(part), Ct.byref(nb), stream))
+        L.check(lib.glf_bn_res_ln_pair_bwd(*args_))
     for _ in range(3):
         launch()
     torch.cuda.synchronize()
@@ -308,18 +366,19 @@ def kernel_probe(args, dev, clips, C, pk):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
-    alg_bytes = 4 * rows * C * 2          # read dZ, U, X ; write dV  (bf16) — SURVEY §8d "epilogue bwd"
+    alg_bytes = 7 * rows * C * 2          # read dZ, U_g, X_g, U_l, X_l ; write dV_g, dV_l  (bf16)
     achieved = alg_bytes / (ms * 1e-3) / 1e9
     traffic = None                        # DRAM bytes per launch from the committed ncu --set full capture
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         t = json.load(open(tp))
-        if t.get("rows") == rows and t.get("C") == C:
+        if t.get("rows") == rows and t.get("C") == C and t.get("kernel") == "ln_bwd_tma_kernel<2>":
             traffic = int(t["traffic_bytes"])
-    return {"roofline": {"bound": "hbm", "kernel": "bn_res_ln_bwd_kernel", "achieved": round(achieved, 1),
+    return {"roofline": {"bound": "hbm", "kernel": "ln_bwd_tma_kernel<2>", "achieved": round(achieved, 1),
                          "peak": pk["hbm_gbs"], "peak_source": pk["source"], "unit": "GB/s",
                          "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": traffic,
-                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": round(ms, 4)}}
+                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": round(ms, 4),
+                         "inputs": "7 x 205 MB per launch, larger than the 126 MB L2"}}
 
 
 # ------------------------------------------------------------------------------------------------------------------

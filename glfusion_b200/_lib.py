@@ -18,7 +18,8 @@ PRECISIONS = {"bf16": PRECISION_BF16, "fp32": PRECISION_F32X3}
 EXPORTS = ("glf_version", "glf_last_error", "glf_tpavi_sizes", "glf_tpavi_fwd", "glf_tpavi_bwd",
            "glf_gate_concat_fwd", "glf_gate_concat_bwd", "glf_gemm_bf16", "glf_transpose", "glf_bn_res_ln_fwd",
            "glf_bn_res_ln_bwd", "glf_bn_res_ln_bwd_max_blocks", "glf_gate_concat_bwd_scratch_bytes",
-           "glf_fusion_ln_supported", "glf_fusion_ln_fwd", "glf_fusion_ln_bwd")
+           "glf_fusion_ln_supported", "glf_fusion_ln_fwd", "glf_fusion_ln_bwd", "glf_bn_res_ln_pair_fwd",
+           "glf_bn_res_ln_pair_bwd")
 
 
 class GlfDesc(C.Structure):
@@ -73,6 +74,9 @@ def load() -> C.CDLL:
         lib.glf_fusion_ln_bwd.argtypes = [C.POINTER(GlfDesc), vp, vp, vp, C.POINTER(GlfWeights), C.POINTER(GlfWeights),
                                           vp, vp, vp, vp, vp]
         pp = C.POINTER(C.c_void_p)
+        lib.glf_bn_res_ln_pair_fwd.argtypes = [i64, i32, pp, pp, pp, pp, pp, pp, vp, pp, pp, f32, i32, vp]
+        lib.glf_bn_res_ln_pair_bwd.argtypes = [i64, i32, vp, pp, pp, pp, pp, pp, pp, pp, pp, pp, pp, pp,
+                                               C.POINTER(C.c_int), vp]
         lib.glf_gate_concat_fwd.argtypes = [i32] * 6 + [f32, i32, i32, pp, pp, pp, vp, vp, vp, vp]
         lib.glf_gate_concat_bwd.argtypes = [i32] * 6 + [f32, i32, i32, pp, pp, pp, vp, vp, vp, pp, pp, pp, vp, vp]
         lib.glf_gate_concat_bwd_scratch_bytes.argtypes = [i32] * 5

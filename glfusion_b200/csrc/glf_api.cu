@@ -688,6 +688,46 @@ GLF_API int glf_bn_res_ln_bwd(int64_t rows, int C, const void* dZ, int dz_dtype,
 
 GLF_API int glf_bn_res_ln_bwd_max_blocks(void) { return 148 * 2; }
 
+// Pair forms with explicit operands (unit tests, roofline probe): index 0 = MGFM, 1 = MLFM.
+GLF_API int glf_bn_res_ln_pair_fwd(int64_t rows, int C, const void* const* U, const void* const* X,
+                                   const float* const* bn_a, const float* const* bn_b, const float* const* ln_w,
+                                   const float* const* ln_b, void* Z, float* const* mu, float* const* r, float eps,
+                                   int accumulate, glf_stream_t stream) {
+  GLF_TRY(check_device_sm100());
+  if (rows <= 0) return set_error(GLF_ERR_INVALID, "empty input");
+  if (!ln_tma_supported(C)) return set_error(GLF_ERR_UNSUPPORTED, "fused LayerNorm pair needs C <= 256, C %% 8 == 0");
+  GLF_TRY(check_ptr(Z, "Z"));
+  for (int m = 0; m < 2; ++m) {
+    GLF_TRY(check_ptr(U[m], "U"));
+    GLF_TRY(check_ptr(X[m], "X"));
+  }
+  return ln_fwd_tma(2, reinterpret_cast<const bf16* const*>(U), reinterpret_cast<const bf16* const*>(X), bn_a, bn_b, ln_w,
+                    ln_b, mu, r, reinterpret_cast<bf16*>(Z), rows, C, eps, accumulate,
+                    reinterpret_cast<cudaStream_t>(stream));
+}
+
+GLF_API int glf_bn_res_ln_pair_bwd(int64_t rows, int C, const void* dZ, const void* const* U, const void* const* X,
+                                   const float* const* bn_a, const float* const* bn_b, const float* const* bn_mean,
+                                   const float* const* bn_rstd, const float* const* ln_w, const float* const* mu,
+                                   const float* const* r, void* const* dV, float* const* part, int* nblocks_out,
+                                   glf_stream_t stream) {
+  GLF_TRY(check_device_sm100());
+  if (rows <= 0) return set_error(GLF_ERR_INVALID, "empty input");
+  if (!ln_tma_supported(C)) return set_error(GLF_ERR_UNSUPPORTED, "fused LayerNorm pair needs C <= 256, C %% 8 == 0");
+  GLF_TRY(check_ptr(dZ, "dZ"));
+  for (int m = 0; m < 2; ++m) {
+    GLF_TRY(check_ptr(U[m], "U"));
+    GLF_TRY(check_ptr(X[m], "X"));
+    GLF_TRY(check_ptr(dV[m], "dV"));
+    GLF_TRY(check_ptr(mu[m], "mu"));
+    GLF_TRY(check_ptr(r[m], "r"));
+  }
+  return ln_bwd_tma(2, reinterpret_cast<const bf16*>(dZ), reinterpret_cast<const bf16* const*>(U),
+                    reinterpret_cast<const bf16* const*>(X), bn_a, bn_b, ln_w, bn_mean, bn_rstd, mu, r,
+                    reinterpret_cast<bf16* const*>(dV), part, rows, C, nblocks_out,
+                    reinterpret_cast<cudaStream_t>(stream));
+}
+
 GLF_API int glf_transpose(const void* in, void* out, int batch, int R, int S, int in_dtype, int out_dtype,
                   glf_stream_t stream) {
   GLF_TRY(check_device_sm100());

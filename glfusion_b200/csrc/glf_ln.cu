@@ -33,6 +33,29 @@ __device__ __forceinline__ void lds8(const uint8_t* p, float (&f)[8]) {   // 8 b
     f[2 * i + 1] = t.y;
   }
 }
+// 8 bf16 from shared memory as four float2 (element pairs)
+__device__ __forceinline__ void lds8p(const uint8_t* p, float2 (&f)[4]) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) f[i] = unpack_bf16(u[i]);
+}
+__device__ __forceinline__ void ldg8p(const float* p, float2 (&f)[4]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = make_float2(a.x, a.y); f[1] = make_float2(a.z, a.w);
+  f[2] = make_float2(b.x, b.y); f[3] = make_float2(b.z, b.w);
+}
+__device__ __forceinline__ void stg8p(bf16* p, const float2 (&f)[4]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(f[0].x, f[0].y), pack_bf16(f[1].x, f[1].y),
+                                            pack_bf16(f[2].x, f[2].y), pack_bf16(f[3].x, f[3].y));
+}
+__device__ __forceinline__ float hsum4(const float2 (&f)[4]) {
+  const float2 t = add2(add2(f[0], f[1]), add2(f[2], f[3]));
+  return t.x + t.y;
+}
+__device__ __forceinline__ float2 splat(float x) { return make_float2(x, x); }
+
 __device__ __forceinline__ void ldg8f(const float* p, float (&f)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p);
   const float4 b = *reinterpret_cast<const float4*>(p + 4);
@@ -68,7 +91,7 @@ struct LnFwdParams {
   float eps;
 };
 
-template <int NMOD>
+template <int NMOD, bool FULLC>   // FULLC: C == 256, every lane owns 8 live channels
 __global__ void __launch_bounds__(F_THREADS, 1) ln_fwd_tma_kernel(const LnFwdParams p) {
   extern __shared__ uint8_t lsm_raw[];
   __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
@@ -113,18 +136,24 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_fwd_tma_kernel(const LnFwdPar
     return;
   }
   // -------------------------------------------------------------------------------------------- consumers
+  // all per-element math on float2 pairs (FFMA2 / FADD2 / FMUL2): the kernel is instruction-issue bound otherwise
   const int c0 = lane * 8;
-  const bool cact = c0 < p.C;
-  float pa[NMOD][8], pb[NMOD][8], pw[NMOD][8], pl[NMOD][8];
+  const bool cact = FULLC || c0 < p.C;
+  float2 pa[NMOD][4], pb[NMOD][4], pw[NMOD][4], plsum[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) plsum[i] = splat(0.f);
 #pragma unroll
   for (int m = 0; m < NMOD; ++m) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) pa[m][i] = pb[m][i] = pw[m][i] = pl[m][i] = 0.f;
+    for (int i = 0; i < 4; ++i) pa[m][i] = pb[m][i] = pw[m][i] = splat(0.f);
     if (cact) {
-      ldg8f(p.a[m] + c0, pa[m]);
-      ldg8f(p.b[m] + c0, pb[m]);
-      ldg8f(p.lw[m] + c0, pw[m]);
-      ldg8f(p.lb[m] + c0, pl[m]);
+      float2 lb[4];
+      ldg8p(p.a[m] + c0, pa[m]);
+      ldg8p(p.b[m] + c0, pb[m]);
+      ldg8p(p.lw[m] + c0, pw[m]);
+      ldg8p(p.lb[m] + c0, lb);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) plsum[i] = add2(plsum[i], lb[i]);
     }
   }
   const float invC = 1.f / static_cast<float>(p.C);
@@ -144,47 +173,45 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_fwd_tma_kernel(const LnFwdPar
       if (rl < nrow) {
         const long long row = row0 + rl;
         const uint32_t roff = rl * row_bytes + c0 * 2;
-        float o[8];
+        float2 o[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = 0.f;
+        for (int i = 0; i < 4; ++i) o[i] = plsum[i];
+        if (cact && p.accumulate) {
+          float2 z0[4];
+          lds8p(st + 2 * NMOD * p.arr_bytes + roff, z0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = add2(o[i], z0[i]);
+        }
 #pragma unroll
         for (int m = 0; m < NMOD; ++m) {
-          float v[8];
+          float2 v[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = 0.f;
+          for (int i = 0; i < 4; ++i) v[i] = splat(0.f);
           if (cact) {
-            float u[8], x[8];
-            lds8(st + (2 * m) * p.arr_bytes + roff, u);
-            lds8(st + (2 * m + 1) * p.arr_bytes + roff, x);
+            float2 u[4], x[4];
+            lds8p(st + (2 * m) * p.arr_bytes + roff, u);
+            lds8p(st + (2 * m + 1) * p.arr_bytes + roff, x);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = fmaf(pa[m][i], u[i], pb[m][i]) + x[i];
+            for (int i = 0; i < 4; ++i) v[i] = add2(fma2(pa[m][i], u[i], pb[m][i]), x[i]);
           }
-          float sum = 0.f;
+          const float mu = warp_sum(hsum4(v)) * invC;
+          const float2 nmu = splat(-mu);
+          float2 d[4], q2 = splat(0.f);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) sum += v[i];
-          const float mu = warp_sum(sum) * invC;
-          float q = 0.f;
-          if (cact) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) q = fmaf(v[i] - mu, v[i] - mu, q);
+          for (int i = 0; i < 4; ++i) {
+            d[i] = cact ? add2(v[i], nmu) : splat(0.f);
+            q2 = fma2(d[i], d[i], q2);
           }
-          const float r = rsqrtf(warp_sum(q) * invC + p.eps);
+          const float r = rsqrtf(warp_sum(q2.x + q2.y) * invC + p.eps);
+          const float2 r2 = splat(r);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] += fmaf((v[i] - mu) * r, pw[m][i], pl[m][i]);
+          for (int i = 0; i < 4; ++i) o[i] = fma2(d[i], mul2(pw[m][i], r2), o[i]);
           if (lane == 0 && p.mu[m] != nullptr) {
             p.mu[m][row] = mu;
             p.r[m][row] = r;
           }
         }
-        if (cact) {
-          if (p.accumulate) {
-            float z0[8];
-            lds8(st + 2 * NMOD * p.arr_bytes + roff, z0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] += z0[i];
-          }
-          stg8(p.Z + row * p.C + c0, o);
-        }
+        if (cact) stg8p(p.Z + row * p.C + c0, o);
       }
     }
     __syncwarp();
@@ -216,7 +243,7 @@ struct LnBwdParams {
   uint32_t arr_bytes, stage_bytes;
 };
 
-template <int NMOD>
+template <int NMOD, bool FULLC>
 __global__ void __launch_bounds__(B_THREADS, 1) ln_bwd_tma_kernel(const LnBwdParams p) {
   extern __shared__ uint8_t lsm_raw[];
   __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
@@ -269,18 +296,18 @@ __global__ void __launch_bounds__(B_THREADS, 1) ln_bwd_tma_kernel(const LnBwdPar
     const int m = (NMOD == 2) ? warp / GW : 0;   // module of this warp
     const int wi = warp % GW;
     const int c0 = lane * 8;
-    const bool cact = c0 < p.C;
-    float pa[8], pb[8], pw[8];
+    const bool cact = FULLC || c0 < p.C;
+    float2 pa[4], pb[4], pw[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) pa[i] = pb[i] = pw[i] = 0.f;
+    for (int i = 0; i < 4; ++i) pa[i] = pb[i] = pw[i] = splat(0.f);
     if (cact) {
-      ldg8f(p.a[m] + c0, pa);
-      ldg8f(p.b[m] + c0, pb);
-      ldg8f(p.lw[m] + c0, pw);
+      ldg8p(p.a[m] + c0, pa);
+      ldg8p(p.b[m] + c0, pb);
+      ldg8p(p.lw[m] + c0, pw);
     }
-    float g_lw[8], g_lb[8], g_ga[8], g_be[8];
+    float2 g_lw[4], g_lb[4], g_ga[4], g_be[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) g_lw[i] = g_lb[i] = g_ga[i] = g_be[i] = 0.f;
+    for (int i = 0; i < 4; ++i) g_lw[i] = g_lb[i] = g_ga[i] = g_be[i] = splat(0.f);
     const float invC = 1.f / static_cast<float>(p.C);
     const uint32_t row_bytes = static_cast<uint32_t>(p.C) * 2u;
     const uint32_t u_off = (1 + 2 * m) * p.arr_bytes, x_off = (2 + 2 * m) * p.arr_bytes;
@@ -305,40 +332,39 @@ __global__ void __launch_bounds__(B_THREADS, 1) ln_bwd_tma_kernel(const LnBwdPar
           const float mu = full_tile ? mu_s[rl] : p.mu[m][row];
           const float r = full_tile ? r_s[rl] : p.r[m][row];
           const uint32_t roff = rl * row_bytes + c0 * 2;
-          float xh[8], dxh[8], dz[8], u[8];
+          float2 xh[4], dxh[4], dz[4], u[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) xh[i] = dxh[i] = dz[i] = u[i] = 0.f;
+          for (int i = 0; i < 4; ++i) xh[i] = dxh[i] = dz[i] = u[i] = splat(0.f);
           if (cact) {
-            float x[8];
-            lds8(st + roff, dz);
-            lds8(st + u_off + roff, u);
-            lds8(st + x_off + roff, x);
+            float2 x[4];
+            lds8p(st + roff, dz);
+            lds8p(st + u_off + roff, u);
+            lds8p(st + x_off + roff, x);
+            const float2 r2 = splat(r), nmur = splat(-mu * r);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              xh[i] = (fmaf(pa[i], u[i], pb[i]) + x[i] - mu) * r;
-              dxh[i] = dz[i] * pw[i];
+            for (int i = 0; i < 4; ++i) {
+              // xhat = (a u + b + x - mu) r = (a u + b + x) r - mu r
+              xh[i] = fma2(add2(fma2(pa[i], u[i], pb[i]), x[i]), r2, nmur);
+              dxh[i] = mul2(dz[i], pw[i]);
             }
           }
-          float s0 = 0.f, s1 = 0.f;
+          float2 s1p = splat(0.f);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            s0 += dxh[i];
-            s1 = fmaf(dxh[i], xh[i], s1);
-          }
-          s0 = warp_sum(s0);
-          s1 = warp_sum(s1);
+          for (int i = 0; i < 4; ++i) s1p = fma2(dxh[i], xh[i], s1p);
+          const float s0 = warp_sum(hsum4(dxh));
+          const float s1 = warp_sum(s1p.x + s1p.y);
           if (cact) {
-            const float m1 = s0 * invC, m2 = s1 * invC;
-            float dv[8];
+            const float2 nm1 = splat(-s0 * invC), nm2 = splat(-s1 * invC), r2 = splat(r);
+            float2 dv[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              dv[i] = r * (dxh[i] - m1 - xh[i] * m2);
-              g_lw[i] = fmaf(dz[i], xh[i], g_lw[i]);
-              g_lb[i] += dz[i];
-              g_ga[i] = fmaf(dv[i], u[i], g_ga[i]);    // raw U: turned into sum dv * uhat when the partial is written
-              g_be[i] += dv[i];
+            for (int i = 0; i < 4; ++i) {
+              dv[i] = mul2(r2, fma2(xh[i], nm2, add2(dxh[i], nm1)));
+              g_lw[i] = fma2(dz[i], xh[i], g_lw[i]);
+              g_lb[i] = add2(g_lb[i], dz[i]);
+              g_ga[i] = fma2(dv[i], u[i], g_ga[i]);    // raw U: turned into sum dv * uhat when the partial is written
+              g_be[i] = add2(g_be[i], dv[i]);
             }
-            stg8(dVm + row * p.C + c0, dv);
+            stg8p(dVm + row * p.C + c0, dv);
           }
         }
       }
@@ -349,11 +375,11 @@ __global__ void __launch_bounds__(B_THREADS, 1) ln_bwd_tma_kernel(const LnBwdPar
     named_bar_sync(1, B_CW * 32);
     float(*acc)[4][B_ACC_PITCH] = reinterpret_cast<float(*)[4][B_ACC_PITCH]>(ring);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      acc[warp][0][c0 + i] = g_lw[i];
-      acc[warp][1][c0 + i] = g_lb[i];
-      acc[warp][2][c0 + i] = g_ga[i];
-      acc[warp][3][c0 + i] = g_be[i];
+    for (int i = 0; i < 4; ++i) {
+      *reinterpret_cast<float2*>(&acc[warp][0][c0 + 2 * i]) = g_lw[i];
+      *reinterpret_cast<float2*>(&acc[warp][1][c0 + 2 * i]) = g_lb[i];
+      *reinterpret_cast<float2*>(&acc[warp][2][c0 + 2 * i]) = g_ga[i];
+      *reinterpret_cast<float2*>(&acc[warp][3][c0 + 2 * i]) = g_be[i];
     }
     named_bar_sync(1, B_CW * 32);
     // one partial row per CTA and module: [4][C]; index space = NMOD x C channels
@@ -416,16 +442,12 @@ int ln_fwd_tma(int nmod, const bf16* const* U, const bf16* const* X, const float
   const uint32_t smem = p.stages * p.stage_bytes + 128;
   const int sms = num_sms();
   const int grid = p.ntiles < sms ? p.ntiles : sms;
-  cudaError_t e;
-  if (nmod == 2) {
-    e = cudaFuncSetAttribute(ln_fwd_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(ln_fwd_tma<2>)");
-    ln_fwd_tma_kernel<2><<<grid, F_THREADS, smem, stream>>>(p);
-  } else {
-    e = cudaFuncSetAttribute(ln_fwd_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(ln_fwd_tma<1>)");
-    ln_fwd_tma_kernel<1><<<grid, F_THREADS, smem, stream>>>(p);
-  }
+  void (*kern)(const LnFwdParams) =
+      nmod == 2 ? (C == 256 ? ln_fwd_tma_kernel<2, true> : ln_fwd_tma_kernel<2, false>)
+                : (C == 256 ? ln_fwd_tma_kernel<1, true> : ln_fwd_tma_kernel<1, false>);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(ln_fwd_tma)");
+  kern<<<grid, F_THREADS, smem, stream>>>(p);
   return check_cuda(cudaGetLastError(), "ln_fwd_tma launch");
 }
 
@@ -456,16 +478,12 @@ int ln_bwd_tma(int nmod, const bf16* dZ, const bf16* const* U, const bf16* const
   const uint32_t smem = ring_bytes + 128;
   const int grid = ln_bwd_tma_blocks(rows);
   if (nblocks) *nblocks = grid;
-  cudaError_t e;
-  if (nmod == 2) {
-    e = cudaFuncSetAttribute(ln_bwd_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(ln_bwd_tma<2>)");
-    ln_bwd_tma_kernel<2><<<grid, B_THREADS, smem, stream>>>(p);
-  } else {
-    e = cudaFuncSetAttribute(ln_bwd_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(ln_bwd_tma<1>)");
-    ln_bwd_tma_kernel<1><<<grid, B_THREADS, smem, stream>>>(p);
-  }
+  void (*kern)(const LnBwdParams) =
+      nmod == 2 ? (C == 256 ? ln_bwd_tma_kernel<2, true> : ln_bwd_tma_kernel<2, false>)
+                : (C == 256 ? ln_bwd_tma_kernel<1, true> : ln_bwd_tma_kernel<1, false>);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(ln_bwd_tma)");
+  kern<<<grid, B_THREADS, smem, stream>>>(p);
   return check_cuda(cudaGetLastError(), "ln_bwd_tma launch");
 }
 

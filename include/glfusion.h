@@ -183,6 +183,20 @@ GLF_API int glf_bn_res_ln_bwd(int64_t rows, int C, const void* dZ, int dz_dtype,
                       glf_stream_t stream);
 GLF_API int glf_bn_res_ln_bwd_max_blocks(void);
 
+/* Pair forms (MGFM = index 0, MLFM = index 1) of the two epilogues with explicit operands: every argument that is a
+ * pointer-to-pointer is a HOST array of two device pointers.  bf16 activations, C <= 256, 16-byte aligned pointers.
+ *   fwd: Z (+)= sum_m LayerNorm_C(bn_a[m] * U[m] + bn_b[m] + X[m]) * ln_w[m] + ln_b[m]
+ *   bwd: dV[m] and part[m] ([nblocks][4][C]) for both blocks from ONE read of dZ. */
+GLF_API int glf_bn_res_ln_pair_fwd(int64_t rows, int C, const void* const* U, const void* const* X,
+                           const float* const* bn_a, const float* const* bn_b, const float* const* ln_w,
+                           const float* const* ln_b, void* Z, float* const* mu, float* const* r, float eps,
+                           int accumulate, glf_stream_t stream);
+GLF_API int glf_bn_res_ln_pair_bwd(int64_t rows, int C, const void* dZ, const void* const* U, const void* const* X,
+                           const float* const* bn_a, const float* const* bn_b, const float* const* bn_mean,
+                           const float* const* bn_rstd, const float* const* ln_w, const float* const* mu,
+                           const float* const* r, void* const* dV, float* const* part, int* nblocks_out,
+                           glf_stream_t stream);
+
 /* out[b, s, r] = in[b, r, s] with dtype conversion (NCTHW <-> token-major packing). dtypes: GLF_DTYPE_*. */
 GLF_API int glf_transpose(const void* in, void* out, int batch, int R, int S, int in_dtype, int out_dtype,
                   glf_stream_t stream);
