@@ -48,6 +48,7 @@ struct GemmKParams {
   unsigned mg_mn, mg_n, mg_sk;   // multiply-high magics for / tiles_mn, / tiles_n, / split_k
   int cs_accum;   // 1: column statistics accumulated per CTA over all its tiles (table rows = gridDim.x * 4)
   int tiles_m, tiles_n;
+  int step_n, step_m, step_z;    // (n-tile, m-tile, batch*split) advance per persistent-loop step of gridDim.x tiles
 };
 
 template <int BN>
@@ -225,29 +226,38 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       for (int i = ew * 32 + lane; i < p.N; i += EPI_THREADS) ball[i] = p.bias[i];
       named_bar_sync(1, EPI_THREADS);
     }
-    // per-CTA column-statistics accumulators: slot = n_tile * chunks_per_warp + chunk iteration (<= CS_SLOTS)
+    // per-CTA column-statistics accumulators: slot = n_tile * chunks_per_warp + chunk iteration (<= CS_SLOTS); the
+    // statistics live on column PAIRS: lane (and lane ^ 16, a duplicate) owns columns 2*(lane&15), 2*(lane&15)+1
     constexpr int CS_SLOTS = 4;
     constexpr int CPW = (NCHUNK + 3) / 4;      // chunks per warp per tile
-    float cs1[CS_SLOTS], cs2[CS_SLOTS];
+    float2 cs1[CS_SLOTS], cs2[CS_SLOTS];
 #pragma unroll
-    for (int i = 0; i < CS_SLOTS; ++i) cs1[i] = cs2[i] = 0.f;
+    for (int i = 0; i < CS_SLOTS; ++i) cs1[i] = cs2[i] = make_float2(0.f, 0.f);
+    const int hl = lane & 15, half = lane >> 4;
+    // read side of the staging tile: this lane re-reads rows (lane>>2) + 8 i, 16-byte chunk lane&3
+    const int rr0 = lane >> 2, rch = lane & 3;
+    const float2 alpha2 = make_float2(p.alpha, p.alpha);
+    // tile coordinates advance incrementally (tile += gridDim.x): no divisions in the loop
+    int z, mn, m_tile, nt;
+    fastdivmod(static_cast<int>(blockIdx.x), tiles_mn, p.mg_mn, z, mn);
+    fastdivmod(mn, p.tiles_n, p.mg_n, m_tile, nt);
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-      int z, mn, m_tile, nt, b, split;
-      fastdivmod(tile, tiles_mn, p.mg_mn, z, mn);
-      fastdivmod(mn, p.tiles_n, p.mg_n, m_tile, nt);
-      fastdivmod(z, p.split_k, p.mg_sk, b, split);
+      int b = z, split = 0;
+      if (p.split_k > 1) fastdivmod(z, p.split_k, p.mg_sk, b, split);
       const int m0 = m_tile * BM, n0 = nt * BN;
       const int acc = local & 1;
       const uint32_t use = static_cast<uint32_t>(local >> 1);
       const int grow = m0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
       const bool use_bias = p.bias != nullptr && split == 0;
+      const int rows_valid = min(32, p.M - (m0 + q * 32));   // valid rows of this warp's sub-block (may be <= 0)
       mbar_wait(smem_u32(&tmem_full_bar[acc]), use & 1u);
       tc_fence_after();
 #pragma unroll 1
       for (int c = cc0; c < NCHUNK; c += 4) {
         const int gc0 = n0 + c * 32;           // first global column of this chunk
+        const bool full = rows_valid >= 32 && gc0 + 32 <= p.N;
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         if (use_bias && !bias_all) wbias[lane] = (gc0 + lane < p.N) ? p.bias[gc0 + lane] : 0.f;
@@ -257,13 +267,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
         }
         __syncwarp();
-        float f[32];
+        float2 f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
         if (p.alpha != 1.f) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 16; ++j) f[j] = mul2(f[j], alpha2);
         }
         if (use_bias) {
           // full chunks read the CTA-wide copy; a ragged last chunk (N not a multiple of 32) uses the zero-padded
@@ -274,9 +283,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             __syncwarp();
           }
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 bv = *reinterpret_cast<const float4*>(bsrc + j);
-            f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+          for (int j = 0; j < 16; j += 2) {
+            const float4 bv = *reinterpret_cast<const float4*>(bsrc + 2 * j);
+            f[j] = add2(f[j], make_float2(bv.x, bv.y));
+            f[j + 1] = add2(f[j + 1], make_float2(bv.z, bv.w));
           }
         }
         if (p.out_kind != 0) {
@@ -284,13 +294,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                       static_cast<long long>(grow) * p.ldd;
           if (grow < p.M) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const int gc = gc0 + j;
+            for (int j = 0; j < 16; j += 2) {
+              const int gc = gc0 + 2 * j;
               if (gc < p.N) {
                 if (p.out_kind == 2) {
-                  red_add_v4(Df + gc, f[j], f[j + 1], f[j + 2], f[j + 3]);
+                  red_add_v4(Df + gc, f[j].x, f[j].y, f[j + 1].x, f[j + 1].y);
                 } else {
-                  *reinterpret_cast<float4*>(Df + gc) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                  *reinterpret_cast<float4*>(Df + gc) = make_float4(f[j].x, f[j].y, f[j + 1].x, f[j + 1].y);
                 }
               }
             }
@@ -301,85 +311,87 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         // ---- bf16 output: warp-private transpose ----
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint4 pk = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                                      pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+          const uint4 pk = make_uint4(pack_bf16(f[4 * j].x, f[4 * j].y), pack_bf16(f[4 * j + 1].x, f[4 * j + 1].y),
+                                      pack_bf16(f[4 * j + 2].x, f[4 * j + 2].y),
+                                      pack_bf16(f[4 * j + 3].x, f[4 * j + 3].y));
           *reinterpret_cast<uint4*>(wstg + lane * 64 + ((j ^ sw_w) << 4)) = pk;
         }
         __syncwarp();
-        const int rows_valid = min(32, p.M - (m0 + q * 32));   // valid rows of this warp's sub-block (may be <= 0)
         if (p.colstats != nullptr) {
           // sums of the stored (bf16-rounded) values over the sub-block's valid rows: each half-warp takes 16 rows,
-          // each lane a column pair (16 independent 32-bit shared loads, fully unrolled), then the halves are
-          // combined and the result redistributed so that lane = column
-          const int hl = lane & 15, half = lane >> 4;
-          float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
+          // each lane a column pair (16 independent 32-bit shared loads, packed fp32 accumulation), then the two
+          // halves are combined; both halves end up with the pair's statistics
+          float2 sa = make_float2(0.f, 0.f), sq = make_float2(0.f, 0.f);
+          const uint8_t* src = wstg + half * 16 * 64 + (hl & 3) * 4;
+          if (rows_valid >= 32) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int r = half * 16 + i;
-            if (r < rows_valid) {
-              const float2 x = unpack_bf16(*reinterpret_cast<const uint32_t*>(
-                  wstg + r * 64 + (((hl >> 2) ^ ((i >> 1) & 3)) << 4) + (hl & 3) * 4));
-              a1 += x.x;
-              a2 = fmaf(x.x, x.x, a2);
-              b1 += x.y;
-              b2 = fmaf(x.y, x.y, b2);
+            for (int i = 0; i < 16; ++i) {
+              const float2 x = unpack_bf16(
+                  *reinterpret_cast<const uint32_t*>(src + i * 64 + (((hl >> 2) ^ ((i >> 1) & 3)) << 4)));
+              sa = add2(sa, x);
+              sq = fma2(x, x, sq);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (half * 16 + i < rows_valid) {
+                const float2 x = unpack_bf16(
+                    *reinterpret_cast<const uint32_t*>(src + i * 64 + (((hl >> 2) ^ ((i >> 1) & 3)) << 4)));
+                sa = add2(sa, x);
+                sq = fma2(x, x, sq);
+              }
             }
           }
-          a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
-          a2 += __shfl_xor_sync(0xffffffffu, a2, 16);
-          b1 += __shfl_xor_sync(0xffffffffu, b1, 16);
-          b2 += __shfl_xor_sync(0xffffffffu, b2, 16);
-          const int src = lane >> 1;
-          const float t1a = __shfl_sync(0xffffffffu, a1, src), t1b = __shfl_sync(0xffffffffu, b1, src);
-          const float t2a = __shfl_sync(0xffffffffu, a2, src), t2b = __shfl_sync(0xffffffffu, b2, src);
-          const float s1 = (lane & 1) ? t1b : t1a;
-          const float s2 = (lane & 1) ? t2b : t2a;
+          sa.x += __shfl_xor_sync(0xffffffffu, sa.x, 16);
+          sa.y += __shfl_xor_sync(0xffffffffu, sa.y, 16);
+          sq.x += __shfl_xor_sync(0xffffffffu, sq.x, 16);
+          sq.y += __shfl_xor_sync(0xffffffffu, sq.y, 16);
           if (p.cs_accum) {
             const int slot = nt * CPW + (c >> 2);
 #pragma unroll
             for (int i = 0; i < CS_SLOTS; ++i) {
               if (i == slot) {
-                cs1[i] += s1;
-                cs2[i] += s2;
+                cs1[i] = add2(cs1[i], sa);
+                cs2[i] = add2(cs2[i], sq);
               }
             }
-          } else if (gc0 + lane < p.N) {
+          } else if (half == 0 && gc0 + 2 * hl < p.N) {
             float* cs = p.colstats + ((static_cast<long long>(b) * p.tiles_m + m_tile) * 4 + q) * 2 * p.N;
-            cs[gc0 + lane] = s1;
-            cs[p.N + gc0 + lane] = s2;
+            *reinterpret_cast<float2*>(cs + gc0 + 2 * hl) = sa;
+            *reinterpret_cast<float2*>(cs + p.N + gc0 + 2 * hl) = sq;
           }
         }
-        bf16* Db = reinterpret_cast<bf16*>(p.D) + static_cast<long long>(b) * p.strideD;
-        const bf16* Ad = p.addend ? p.addend + static_cast<long long>(b) * p.stride_add : nullptr;
-        const int rch = lane & 3;              // 16-byte chunk of the row segment this lane stores
+        bf16* Drow = reinterpret_cast<bf16*>(p.D) + static_cast<long long>(b) * p.strideD +
+                     static_cast<long long>(m0 + q * 32 + rr0) * p.ldd + gc0 + rch * 8;
+        const bf16* Arow = p.addend ? p.addend + static_cast<long long>(b) * p.stride_add +
+                                          static_cast<long long>(m0 + q * 32 + rr0) * p.ld_add + gc0 + rch * 8
+                                    : nullptr;
+        const uint8_t* rsrc = wstg + rr0 * 64;
         const int gc = gc0 + rch * 8;
         uint4 adv[4];
-        if (Ad != nullptr) {
+        if (Arow != nullptr) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int r = (lane >> 2) + 8 * i;
-            const int gr = m0 + q * 32 + r;
-            adv[i] = (r < rows_valid && gc < p.N)
-                         ? *reinterpret_cast<const uint4*>(Ad + static_cast<long long>(gr) * p.ld_add + gc)
+            adv[i] = (full || (rr0 + 8 * i < rows_valid && gc < p.N))
+                         ? *reinterpret_cast<const uint4*>(Arow + static_cast<long long>(8 * i) * p.ld_add)
                          : make_uint4(0, 0, 0, 0);
           }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int r = (lane >> 2) + 8 * i;
-          const int gr = m0 + q * 32 + r;
-          if (r < rows_valid && gc < p.N) {
-            uint4 pk = *reinterpret_cast<const uint4*>(wstg + r * 64 + ((rch ^ ((r >> 1) & 3)) << 4));
-            if (Ad != nullptr) {
+          // row rr0 + 8 i: (row >> 1) & 3 == (rr0 >> 1) & 3 because 8 i >> 1 is a multiple of 4
+          if (full || (rr0 + 8 * i < rows_valid && gc < p.N)) {
+            uint4 pk = *reinterpret_cast<const uint4*>(rsrc + i * 8 * 64 + ((rch ^ ((rr0 >> 1) & 3)) << 4));
+            if (Arow != nullptr) {
               const uint32_t* a32 = reinterpret_cast<const uint32_t*>(&adv[i]);
               uint32_t* p32 = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
-                const float2 x = unpack_bf16(p32[t]), y = unpack_bf16(a32[t]);
-                p32[t] = pack_bf16(x.x + y.x, x.y + y.y);
+                const float2 s2 = add2(unpack_bf16(p32[t]), unpack_bf16(a32[t]));
+                p32[t] = pack_bf16(s2.x, s2.y);
               }
             }
-            *reinterpret_cast<uint4*>(Db + static_cast<long long>(gr) * p.ldd + gc) = pk;
+            *reinterpret_cast<uint4*>(Drow + static_cast<long long>(8 * i) * p.ldd) = pk;
           }
         }
         __syncwarp();                            // staging reused by the next chunk / tile
@@ -388,17 +400,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         tc_fence_before();
         mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
       }
+      // next tile of this CTA
+      nt += p.step_n;
+      int carry = 0;
+      if (nt >= p.tiles_n) { nt -= p.tiles_n; carry = 1; }
+      m_tile += p.step_m + carry;
+      carry = 0;
+      if (m_tile >= p.tiles_m) { m_tile -= p.tiles_m; carry = 1; }
+      z += p.step_z + carry;
     }
-    if (p.colstats != nullptr && p.cs_accum && cc0 < NCHUNK) {
+    if (p.colstats != nullptr && p.cs_accum && cc0 < NCHUNK && half == 0) {
       // one partial row per (CTA, row quarter); every column owned by this warp is written, seen or not
       float* cs = p.colstats + (static_cast<long long>(blockIdx.x) * 4 + q) * 2 * p.N;
 #pragma unroll
       for (int i = 0; i < CS_SLOTS; ++i) {
-        const int nt = i / CPW, k = i % CPW;
-        const int col = nt * BN + (cc0 + 4 * k) * 32 + lane;
-        if (nt < p.tiles_n && cc0 + 4 * k < NCHUNK && col < p.N) {
-          cs[col] = cs1[i];
-          cs[p.N + col] = cs2[i];
+        const int nt_i = i / CPW, k = i % CPW;
+        const int col = nt_i * BN + (cc0 + 4 * k) * 32 + 2 * hl;
+        if (nt_i < p.tiles_n && cc0 + 4 * k < NCHUNK && col < p.N) {
+          *reinterpret_cast<float2*>(cs + col) = cs1[i];
+          *reinterpret_cast<float2*>(cs + p.N + col) = cs2[i];
         }
       }
     }
@@ -491,6 +511,9 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKParams p, int nu
                 grid <= static_cast<long long>(p.batch) * p.tiles_m) ? 1 : 0;
   if (cs_rows != nullptr)
     *cs_rows = p.colstats == nullptr ? 0 : (p.cs_accum ? grid * 4 : p.batch * p.tiles_m * 4);
+  p.step_n = grid % p.tiles_n;
+  p.step_m = (grid / p.tiles_n) % p.tiles_m;
+  p.step_z = grid / (p.tiles_m * p.tiles_n);
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   return check_cuda(cudaGetLastError(), "gemm launch");
 }

@@ -23,16 +23,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
-__device__ __forceinline__ void lds8(const uint8_t* p, float (&f)[8]) {   // 8 bf16 from shared memory
-  const uint4 v = *reinterpret_cast<const uint4*>(p);
-  const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = unpack_bf16(u[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
 // 8 bf16 from shared memory as four float2 (element pairs)
 __device__ __forceinline__ void lds8p(const uint8_t* p, float2 (&f)[4]) {
   const uint4 v = *reinterpret_cast<const uint4*>(p);
@@ -56,16 +46,6 @@ __device__ __forceinline__ float hsum4(const float2 (&f)[4]) {
 }
 __device__ __forceinline__ float2 splat(float x) { return make_float2(x, x); }
 
-__device__ __forceinline__ void ldg8f(const float* p, float (&f)[8]) {
-  const float4 a = *reinterpret_cast<const float4*>(p);
-  const float4 b = *reinterpret_cast<const float4*>(p + 4);
-  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
-  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-}
-__device__ __forceinline__ void stg8(bf16* p, const float (&f)[8]) {
-  *reinterpret_cast<uint4*>(p) =
-      make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-}
 
 constexpr int MAX_STAGES = 8;
 constexpr uint32_t RING_BUDGET = 218 * 1024;
