@@ -173,11 +173,34 @@ def algorithmic_work(clips: int, C: int):
     return 2 * (fwd + bwd + small), rows
 
 
+def bind_to_gpu_numa(index: int):
+    """Pin this process to the CPUs NVML reports as local to GPU `index`, so that the pinned host staging buffers of
+    the end-to-end pipeline are allocated on the GPU's own NUMA node (8 ranks otherwise contend for one socket's
+    memory and PCIe root).  Returns (original affinity, number of local CPUs) or (None, None)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(index).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (int(mask[i // 64]) >> (i % 64)) & 1]
+        orig = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in orig]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return orig, len(cpus)
+    except Exception:
+        pass
+    return None, None
+
+
 def run_ours(args):
     from glfusion_b200 import dp
     rank, local_rank, world = dp.init_process_group("nccl")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    orig_affinity, numa_cpus = bind_to_gpu_numa(local_rank)
     C = args.channels
     clips = args.clips
     fusion = seeded_fusion(C, dev)
@@ -187,6 +210,7 @@ def run_ours(args):
     B = clips * F
     dz = torch.randn(B, V, HH, WW, C, device=dev, dtype=torch.bfloat16).permute(0, 4, 1, 2, 3)
     bucket = dp.GradBucket(list(fusion.global_attn._plist()) + list(fusion.local_attn._plist()))
+    bucket.bind([fusion.global_attn, fusion.local_attn])   # gradients are written into the all-reduce bucket directly
 
     params = [p for p in fusion.parameters() if p.requires_grad]
 
@@ -312,9 +336,13 @@ def run_ours(args):
     }
     out.update(kernel_probe(args, dev, clips, C, pk))
     out["gpu_launches"] = count_launches(clips, C) * args.steps
+    out["config"]["host_numa"] = (f"process bound to the {numa_cpus} CPUs local to its GPU (NVML affinity)"
+                                  if numa_cpus else "no NUMA binding")
+    if orig_affinity is not None:
+        os.sched_setaffinity(0, orig_affinity)       # the CPU baseline below uses every host core again
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(C, seconds=args.cpu_seconds)
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def count_launches(clips: int, C: int) -> int:
@@ -438,10 +466,33 @@ def run_reference(args):
                          "sample": "1 clip per step, oracle port of the reference algorithm (fp32, N x N materialised)"},
         "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """Keep fd 1 for the ONE JSON line: anything libraries print to stdout (e.g. NCCL's version banner) goes to
+    stderr instead."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -309,12 +309,11 @@ GLF_API int glf_tpavi_fwd(const glf_desc* d, const void* x, const glf_weights* w
       g.D = s.Wp; g.ldd = Ci; g.strideD = static_cast<long long>(C) * Ci;
       GLF_TRY(gemm(g, stream));
     }
-    {  // U_b = Theta_b W'_b^T + bz   (+ BatchNorm column statistics)
+    {  // U_b = Theta_b W'_b^T   (+ BatchNorm column statistics); the bias bz is folded into the BN affine (bn_finalize)
       GemmArgs g;
       g.A = opnd(s.P, 0, 3 * Ci, static_cast<long long>(N) * 3 * Ci);
       g.B = opnd(s.Wp, 0, Ci, static_cast<long long>(C) * Ci);
       g.M = N; g.N = C; g.K = Ci; g.batch = B;
-      g.bias = w->wz_b;
       g.D = s.U; g.ldd = C; g.strideD = static_cast<long long>(N) * C;
       g.colstats = (d->training && d->bn_layer) ? wf.colstats : nullptr;
       g.colstats_rows = &np;
@@ -322,12 +321,11 @@ GLF_API int glf_tpavi_fwd(const glf_desc* d, const void* x, const glf_weights* w
     }
   } else {
     GLF_TRY(flash_fwd(s.P, s.Y, s.lse, B, N, Ci, wf.attn, stream));
-    {  // U = Y Wz^T + bz
+    {  // U = Y Wz^T   (bz folded into the BN affine)
       GemmArgs g;
       g.A = opnd(s.Y, 0, Ci, 0);
       g.B = opnd(s.wz, 0, Ci, 0);
       g.M = rows; g.N = C; g.K = Ci;
-      g.bias = w->wz_b;
       g.D = s.U; g.ldd = C;
       g.colstats = (d->training && d->bn_layer) ? wf.colstats : nullptr;
       g.colstats_rows = &np;
@@ -341,7 +339,7 @@ GLF_API int glf_tpavi_fwd(const glf_desc* d, const void* x, const glf_weights* w
     GLF_TRY(reduce_stage1(wf.colstats, nullptr, nullptr, 1, np_in, &np, &rs, C, 2, C, wf.red1, stream));
     bn_part = wf.red1;
   }
-  GLF_TRY(bn_finalize(bn_part, np, C, static_cast<double>(m.rows), d, w, s.bn_mean, s.bn_rstd, s.bn_a, s.bn_b,
+  GLF_TRY(bn_finalize(bn_part, np, C, static_cast<double>(m.rows), d, w, w->wz_b, s.bn_mean, s.bn_rstd, s.bn_a, s.bn_b,
                       stream));
   if (defer_ln(d)) return 0;   // the pair entry point glf_fusion_ln_fwd finishes both blocks in one pass
   GLF_TRY(bn_res_ln_fwd(s.U, X, GLF_DTYPE_BF16, s.bn_a, s.bn_b, w->ln_w, w->ln_b, z, d->io_dtype, s.ln_mu, s.ln_r,

@@ -237,7 +237,7 @@ int tpavi_fwd_f32x3(const glf_desc* d, const void* x, const glf_weights* w, void
     GLF_TRY(colstats_f32(s.Uf, wf.cs, m.rows, C, stream));
     np = colstats_f32_blocks(m.rows);
   }
-  GLF_TRY(bn_finalize(wf.cs, np, C, static_cast<double>(m.rows), d, w, s.bn_mean, s.bn_rstd, s.bn_a, s.bn_b, stream));
+  GLF_TRY(bn_finalize(wf.cs, np, C, static_cast<double>(m.rows), d, w, nullptr, s.bn_mean, s.bn_rstd, s.bn_a, s.bn_b, stream));
   GLF_TRY(bn_res_ln_fwd(s.Uf, Xf, GLF_DTYPE_F32, s.bn_a, s.bn_b, w->ln_w, w->ln_b, z, d->io_dtype, s.ln_mu, s.ln_r,
                         m.rows, C, d->eps_ln, d->accumulate, stream));
   return 0;

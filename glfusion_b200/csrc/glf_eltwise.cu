@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(32 * RED_Y)
 // partials: [np][2][C] (sum, sum of squares) -> mean, rstd, affine a = gamma*rstd, b = beta - mean*a; running stats.
 __global__ void __launch_bounds__(32 * RED_Y)
     bn_finalize_kernel(const float* __restrict__ part, int np, int C, double count, const float* __restrict__ gamma,
-                       const float* __restrict__ beta, float eps, float momentum, int training, int bn_layer,
+                       const float* __restrict__ beta, const float* __restrict__ bz, float eps, float momentum,
+                       int training, int bn_layer,
                        float* __restrict__ rm, float* __restrict__ rv, long long* __restrict__ nbt,
                        float* __restrict__ mean_o, float* __restrict__ rstd_o, float* __restrict__ a_o,
                        float* __restrict__ b_o) {
@@ -194,8 +195,11 @@ __global__ void __launch_bounds__(32 * RED_Y)
   if (training && bn_layer) reduce_partial_rows<2>(part, np, 2LL * C, C, c, cact, st, sm);
   if (threadIdx.y != 0 || !cact) return;
   if (c == 0 && training && bn_layer && nbt != nullptr) *nbt += 1;
+  // bz != nullptr: the W_z bias was NOT added to the stored U (train-mode BatchNorm cancels it, so the GEMM epilogue
+  // skips the add); it is folded into the affine here and restored in the running mean
+  const double shift = bz != nullptr ? static_cast<double>(bz[c]) : 0.0;
   if (!bn_layer) {
-    mean_o[c] = 0.f; rstd_o[c] = 1.f; a_o[c] = 1.f; b_o[c] = 0.f;
+    mean_o[c] = 0.f; rstd_o[c] = 1.f; a_o[c] = 1.f; b_o[c] = static_cast<float>(shift);
     return;
   }
   double mean, var;
@@ -204,10 +208,10 @@ __global__ void __launch_bounds__(32 * RED_Y)
     var = st[1] / count - mean * mean;
     if (var < 0.0) var = 0.0;
     const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-    rm[c] = static_cast<float>((1.0 - momentum) * rm[c] + momentum * mean);
+    rm[c] = static_cast<float>((1.0 - momentum) * rm[c] + momentum * (mean + shift));
     rv[c] = static_cast<float>((1.0 - momentum) * rv[c] + momentum * unbiased);
   } else {
-    mean = rm[c];
+    mean = rm[c] - shift;
     var = rv[c];
   }
   const double rstd = 1.0 / sqrt(var + static_cast<double>(eps));
@@ -704,9 +708,9 @@ int reduce_stage1(const float* p0, const float* p1, const float* p2, int ntab, c
   return check_cuda(cudaGetLastError(), "reduce_stage1 launch");
 }
 
-int bn_finalize(const float* part, int np, int C, double count, const glf_desc* d, const glf_weights* w, float* mean,
-                float* rstd, float* a, float* b, cudaStream_t stream) {
-  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, RED_Y), 0, stream>>>(part, np, C, count, w->bn_w, w->bn_b, d->eps_bn, d->momentum,
+int bn_finalize(const float* part, int np, int C, double count, const glf_desc* d, const glf_weights* w, const float* bz,
+                float* mean, float* rstd, float* a, float* b, cudaStream_t stream) {
+  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, RED_Y), 0, stream>>>(part, np, C, count, w->bn_w, w->bn_b, bz, d->eps_bn, d->momentum,
                                                           d->training, d->bn_layer, w->bn_running_mean,
                                                           w->bn_running_var,
                                                           reinterpret_cast<long long*>(w->bn_num_batches_tracked), mean,

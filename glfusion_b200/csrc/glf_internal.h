@@ -53,8 +53,9 @@ int transpose_cast(const void* in, void* out, int batch, int R, int S, int in_dt
                    cudaStream_t stream);
 int prep_weights(const glf_weights* w, int C, int Ci, bf16* wcat, bf16* wcatT, float* bcat, bf16* wz, bf16* wzT,
                  cudaStream_t stream);
-int bn_finalize(const float* part, int np, int C, double count, const glf_desc* d, const glf_weights* w, float* mean,
-                float* rstd, float* a, float* b, cudaStream_t stream);
+// bz: W_z bias that was left out of the stored U (folded into the affine / running mean here), or nullptr
+int bn_finalize(const float* part, int np, int C, double count, const glf_desc* d, const glf_weights* w, const float* bz,
+                float* mean, float* rstd, float* a, float* b, cudaStream_t stream);
 // act_dtype: storage type of the activations U, X (and dV / dU): bf16 in the default path, fp32 under F32X3
 int bn_res_ln_fwd(const void* U, const void* X, int act_dtype, const float* a, const float* b, const float* lw,
                   const float* lb, void* Z, int z_dtype, float* mu, float* r, long long rows, int C, float eps,

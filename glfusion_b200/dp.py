@@ -52,6 +52,25 @@ class GradBucket:
             self.views.append(self.flat[off:off + n].view_as(p))
             off += n
 
+    def bind(self, modules) -> None:
+        """Zero-copy mode: make the TPAVI blocks in `modules` write their parameter gradients straight into this
+        bucket (module._grad_out: kernel-side name -> bucket view), so that after backward `p.grad` aliases the flat
+        buffer and the all-reduce needs neither pack nor unpack.  Falls back to copies whenever a gradient ends up
+        elsewhere (first accumulation into an existing .grad, dtype mismatch, ...)."""
+        index = {id(p): v for p, v in zip(self.params, self.views)}
+        for mod in modules:
+            table = dict(mod.named_parameters())
+            out = {}
+            for name in mod._plist_names():
+                p = table[name]
+                if id(p) in index and p.dtype == torch.float32:
+                    out[mod._grad_key(name)] = index[id(p)]
+            mod._grad_out = out
+
+    def aliased(self) -> bool:
+        return all(p.grad is not None and p.grad.data_ptr() == v.data_ptr() and p.grad.dtype == torch.float32
+                   for p, v in zip(self.params, self.views))
+
     def pack(self) -> torch.Tensor:
         if all(p.grad is not None and p.grad.dtype == torch.float32 for p in self.params):
             torch._foreach_copy_(self.views, [p.grad for p in self.params])
@@ -74,11 +93,17 @@ class GradBucket:
                 p.grad.copy_(v)
 
     def allreduce_mean(self, group=None) -> None:
-        self.pack()
+        zero_copy = self.aliased()
+        if not zero_copy:
+            self.pack()
         if dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            self.flat.div_(dist.get_world_size(group))
-        self.unpack()
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)     # one kernel: sum and 1/world
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+                self.flat.div_(dist.get_world_size(group))
+        if not zero_copy:
+            self.unpack()
 
 
 def broadcast_buffers(module: torch.nn.Module, src: int = 0, group=None) -> None:

@@ -142,8 +142,10 @@ class _FusionFunction(torch.autograd.Function):
                 L.check(L.load().glf_fusion_ln_bwd(C.byref(stg.desc), L.ptr(dz), L.ptr(xg), L.ptr(xl), C.byref(wg),
                                                    C.byref(wl), L.ptr(svg), L.ptr(svl), L.ptr(wsg), L.ptr(wsl),
                                                    _stream_ptr()))
-        dxg, gg = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xg, stg, svg, tg, mg._buffer_table(), ws=wsg)
-        dxl, gl = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xl, stl, svl, tl, ml._buffer_table(), ws=wsl)
+        dxg, gg = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xg, stg, svg, tg, mg._buffer_table(), ws=wsg,
+                                     grad_out=getattr(mg, "_grad_out", None))
+        dxl, gl = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xl, stl, svl, tl, ml._buffer_table(), ws=wsl,
+                                     grad_out=getattr(ml, "_grad_out", None))
         df4, dcls, dctr = gate_concat_backward(f4, cls, ctr, gate, dxg, dxl, ctx.fusion.center_aware_weight)
         out = [None, None, None] + list(df4) + list(dcls) + list(dctr)
         for mod, plist, gr in ((mg, pg, gg), (ml, pl, gl)):

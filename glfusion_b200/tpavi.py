@@ -127,8 +127,10 @@ def tpavi_forward_raw(x: torch.Tensor, params: dict, buffers, *, mode: int, trai
 
 def tpavi_backward_raw(dz: torch.Tensor, dz_layout: int, x: torch.Tensor, st: TPAVIState, saved: torch.Tensor,
                        params: dict, buffers, dx_out: Optional[torch.Tensor] = None,
-                       ws: Optional[torch.Tensor] = None):
-    """Run glf_tpavi_bwd.  Returns (dx buffer in the layout of x, dict of fp32 parameter gradients)."""
+                       ws: Optional[torch.Tensor] = None, grad_out: Optional[dict] = None):
+    """Run glf_tpavi_bwd.  Returns (dx buffer in the layout of x, dict of fp32 parameter gradients).
+    `grad_out` (optional): name -> preallocated fp32 tensor the kernels write that gradient into (e.g. views of a
+    data-parallel all-reduce bucket, dp.GradBucket.bind): the returned gradient then aliases it."""
     lib = L.load()
     dev = x.device
     d = st.desc
@@ -140,7 +142,11 @@ def tpavi_backward_raw(dz: torch.Tensor, dz_layout: int, x: torch.Tensor, st: TP
         if ref is None:
             # bn_layer=False: no BN affine; the kernels still want a scratch target
             ref = params["ln_w"]
-        t = torch.empty(ref.shape, dtype=torch.float32, device=dev)
+        dst = grad_out.get(name) if grad_out is not None and params.get(name) is not None else None
+        if dst is not None and dst.dtype == torch.float32 and dst.shape == ref.shape and dst.is_contiguous():
+            t = dst.detach()        # fresh alias: autograd may adopt it as .grad without a copy
+        else:
+            t = torch.empty(ref.shape, dtype=torch.float32, device=dev)
         grads[name] = t
         setattr(g, name, t.data_ptr())
     if dx_out is None:
@@ -191,7 +197,8 @@ class _TPAVIFunction(torch.autograd.Function):
         else:
             dz = dz.contiguous()
             layout = L.LAYOUT_NCTHW
-        dx, grads = tpavi_backward_raw(dz, layout, x_used, ctx.st, ctx.saved_blob, params, module._buffer_table())
+        dx, grads = tpavi_backward_raw(dz, layout, x_used, ctx.st, ctx.saved_blob, params, module._buffer_table(),
+                                       grad_out=getattr(module, "_grad_out", None))
         if ctx.st.desc.x_layout == L.LAYOUT_TOKEN:
             dx = dx.permute(0, 4, 1, 2, 3)
         out = [dx, None]

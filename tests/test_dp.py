@@ -83,3 +83,23 @@ def test_single_process_is_a_noop():
     b.allreduce_mean()
     assert all(torch.equal(p.grad, torch.ones_like(p)) for p in lin.parameters())
     assert dp.max_over_ranks(3.0) == 3.0
+
+
+def test_grad_bucket_zero_copy_aliasing():
+    """bind()-style zero-copy mode: when .grad aliases the bucket view no pack/unpack copy is made, and a gradient
+    that lives elsewhere falls back to the copying path (single process: the all-reduce itself is a no-op)."""
+    import torch
+    from glfusion_b200.dp import GradBucket
+    ps = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5))]
+    b = GradBucket(ps)
+    for p, v in zip(ps, b.views):
+        v.copy_(torch.arange(v.numel(), dtype=torch.float32).view_as(v))
+        p.grad = v.detach()
+    assert b.aliased()
+    b.allreduce_mean()
+    assert ps[0].grad.data_ptr() == b.views[0].data_ptr()
+    assert float(ps[1].grad[4]) == 4.0
+    ps[1].grad = torch.full((5,), 7.0)          # not an alias any more -> copying path
+    assert not b.aliased()
+    b.allreduce_mean()
+    assert float(b.flat[-1]) == 7.0 and float(ps[1].grad[0]) == 7.0
