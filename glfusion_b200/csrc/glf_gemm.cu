@@ -30,6 +30,7 @@ constexpr int BK = 64;
 constexpr int EPI_WARPS = 16;                 // 4 per SM sub-partition: the epilogue is a latency chain, it needs TLP
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int GEMM_THREADS = 64 + EPI_THREADS;  // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
+constexpr int MAX_STAGES = 10;
 
 struct GemmKParams {
   int M, N, K, batch;
@@ -49,6 +50,12 @@ struct GemmKParams {
   int cs_accum;   // 1: column statistics accumulated per CTA over all its tiles (table rows = gridDim.x * 4)
   int tiles_m, tiles_n;
   int step_n, step_m, step_z;    // (n-tile, m-tile, batch*split) advance per persistent-loop step of gridDim.x tiles
+  int tma_store;                 // 1: bf16 output tiles leave through cp.async.bulk.tensor stores (tmD), no addend
+  // B-stationary mode (small shared weight operand, K-major): the CTA's whole B slab [BN, K] is loaded once and
+  // stays in shared memory; the ring then carries A only (halves the L2 -> SM traffic of the streaming projections)
+  int b_res;
+  int nstages;                   // ring depth actually used (<= MAX_STAGES)
+  unsigned stage_bytes, a_off;   // bytes per ring stage, offset of the ring behind the resident B slab
 };
 
 template <int BN>
@@ -86,12 +93,13 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 // (batch, k-split), so the CTAs that are resident together share A slabs through L2.
 template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-    gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
+    gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmD, const GemmKParams p) {
   using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[STAGES];
-  __shared__ uint64_t empty_bar[STAGES];
+  __shared__ uint64_t full_bar[MAX_STAGES];
+  __shared__ uint64_t empty_bar[MAX_STAGES];
+  __shared__ uint64_t b_full_bar;
   __shared__ uint64_t tmem_full_bar[2];
   __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_holder;
@@ -108,15 +116,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < p.nstages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
+    mbar_init(smem_u32(&b_full_bar), 1);
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tmem_full_bar[s]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[s]), EPI_THREADS);
+      mbar_init(smem_u32(&tmem_empty_bar[s]), EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -131,6 +139,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      if (p.b_res) {   // gridDim.x is a multiple of tiles_n: this CTA's n-tile never changes
+        const int nt_fixed = static_cast<int>(blockIdx.x) % p.tiles_n;
+        const uint32_t bb_ = smem_u32(&b_full_bar);
+        mbar_expect_tx(bb_, static_cast<uint32_t>(p.kb_total) * Cfg::B_BYTES);
+        for (int kb = 0; kb < p.kb_total; ++kb)
+          tma_load_4d(&tmB, bb_, smem_base + kb * Cfg::B_BYTES, kb * BK, nt_fixed * BN, 0, 0);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int z, mn, mt, nt, b, split;
         fastdivmod(tile, tiles_mn, p.mg_mn, z, mn);
@@ -145,8 +160,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           const int k0 = (kb0 + it / p.npairs) * BK;
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-          mbar_expect_tx(fb, Cfg::STAGE_BYTES);
-          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          mbar_expect_tx(fb, p.b_res ? Cfg::A_BYTES : Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + p.a_off + stage * p.stage_bytes;
           const uint32_t sb = sa + Cfg::A_BYTES;
           if (!A_MN) {
             tma_load_4d(&tmA, fb, sa, k0, m0, ab, p.pairA[pair]);
@@ -154,14 +169,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             tma_load_4d(&tmA, fb, sa, m0, k0, ab, p.pairA[pair]);
             tma_load_4d(&tmA, fb, sa + 8192, m0 + 64, k0, ab, p.pairA[pair]);
           }
-          if (!B_MN) {
+          if (p.b_res) {
+            // B slab is resident
+          } else if (!B_MN) {
             tma_load_4d(&tmB, fb, sb, k0, n0, bb, p.pairB[pair]);
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
               tma_load_4d(&tmB, fb, sb + j * 8192, n0 + j * 64, k0, bb, p.pairB[pair]);
           }
-          if (++stage == STAGES) {
+          if (++stage == p.nstages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -175,6 +192,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
+      if (p.b_res) {
+        mbar_wait(smem_u32(&b_full_bar), 0);
+        tc_fence_after();
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
         int z, mn, b, split;
         fastdivmod(tile, tiles_mn, p.mg_mn, z, mn);
@@ -189,8 +210,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         for (int it = 0; it < niter; ++it) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint32_t sa = smem_base + p.a_off + stage * p.stage_bytes;
+          const uint32_t sb = p.b_res ? smem_base + (kb0 + it) * Cfg::B_BYTES : sa + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t ad = A_MN ? make_sdesc(sa + k * 2048, 8192, 1024) : make_sdesc(sa + k * 32, 16, 1024);
@@ -198,7 +219,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             umma_f16(tacc, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
           }
           umma_commit(smem_u32(&empty_bar[stage]));  // slot reusable once these MMAs have read it
-          if (++stage == STAGES) {
+          if (++stage == p.nstages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -216,8 +237,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const int q = warp & 3;
     const int cc0 = ew >> 2;
     constexpr int NCHUNK = BN / 32;
-    uint8_t* wstg = epi_smem + ew * (Cfg::WARP_STG + Cfg::WARP_BIAS);
-    float* wbias = reinterpret_cast<float*>(wstg + Cfg::WARP_STG);
+    uint8_t* wstg = epi_smem + ew * Cfg::WARP_STG;                       // 2 KB tiles, 1 KB aligned (TMA SWIZZLE_64B)
+    float* wbias = reinterpret_cast<float*>(epi_smem + EPI_WARPS * Cfg::WARP_STG + ew * Cfg::WARP_BIAS);
     const int sw_w = (lane >> 1) & 3;          // swizzle of the row this lane WRITES (row = lane)
     // the whole bias vector goes to shared memory once (epilogue warps only; named barrier 1)
     float* ball = reinterpret_cast<float*>(epi_smem + EPI_WARPS * (Cfg::WARP_STG + Cfg::WARP_BIAS));
@@ -262,11 +283,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         tmem_ld_32x32(taddr + c * 32, v);
         if (use_bias && !bias_all) wbias[lane] = (gc0 + lane < p.N) ? p.bias[gc0 + lane] : 0.f;
         tmem_ld_wait();
-        if (c + 4 >= NCHUNK) {                 // last TMEM read of this warp for the tile: release the accumulator
-          tc_fence_before();
-          mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
-        }
+        tc_fence_before();
         __syncwarp();
+        if (c + 4 >= NCHUNK && lane == 0)      // last TMEM read of this warp for the tile: release the accumulator
+          mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
         float2 f[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
@@ -309,6 +329,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           continue;
         }
         // ---- bf16 output: warp-private transpose ----
+        if (p.tma_store) {                       // the previous bulk store of this warp must have drained the tile
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint4 pk = make_uint4(pack_bf16(f[4 * j].x, f[4 * j].y), pack_bf16(f[4 * j + 1].x, f[4 * j + 1].y),
@@ -361,6 +385,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             *reinterpret_cast<float2*>(cs + p.N + gc0 + 2 * hl) = sq;
           }
         }
+        if (p.tma_store) {
+          // one bulk tensor store per 32 x 32 sub-block: the staging tile is already in the SWIZZLE_64B layout the
+          // tensor map expects; rows / columns beyond M / N are clipped by the TMA unit
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmD, smem_u32(wstg), gc0, m0 + q * 32, b);
+            tma_store_commit();
+          }
+          continue;
+        }
         bf16* Drow = reinterpret_cast<bf16*>(p.D) + static_cast<long long>(b) * p.strideD +
                      static_cast<long long>(m0 + q * 32 + rr0) * p.ldd + gc0 + rch * 8;
         const bf16* Arow = p.addend ? p.addend + static_cast<long long>(b) * p.stride_add +
@@ -396,10 +431,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         }
         __syncwarp();                            // staging reused by the next chunk / tile
       }
-      if (cc0 >= NCHUNK) {                       // warps without a chunk (BN = 64) still release the accumulator
-        tc_fence_before();
+      if (cc0 >= NCHUNK && lane == 0)            // warps without a chunk (BN = 64) still release the accumulator
         mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
-      }
       // next tile of this CTA
       nt += p.step_n;
       int carry = 0;
@@ -409,6 +442,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       if (m_tile >= p.tiles_m) { m_tile -= p.tiles_m; carry = 1; }
       z += p.step_z + carry;
     }
+    if (p.tma_store && lane == 0) tma_store_wait_all<0>();
     if (p.colstats != nullptr && p.cs_accum && cc0 < NCHUNK && half == 0) {
       // one partial row per (CTA, row quarter); every column owned by this warp is written, seen or not
       float* cs = p.colstats + (static_cast<long long>(blockIdx.x) * 4 + q) * 2 * p.N;
@@ -474,6 +508,23 @@ int make_operand_map(CUtensorMap* tm, const GemmOperand& op, int rows, int K, in
   return 0;
 }
 
+// Tensor map for bf16 OUTPUT tiles: dims {N, M, batch}, box {32 columns, 32 rows, 1}, SWIZZLE_64B — the layout of the
+// epilogue's warp-private staging tile (16-byte chunk index XOR ((row >> 1) & 3)).
+int make_output_map(CUtensorMap* tm, void* D, int M, int N, int batch, long long ldd, long long strideD) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return set_error(GLF_ERR_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
+  const int nb = (strideD != 0) ? batch : 1;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(M), static_cast<cuuint64_t>(nb)};
+  const cuuint64_t row_bytes = static_cast<cuuint64_t>(ldd) * 2;
+  cuuint64_t strides[2] = {row_bytes, nb > 1 ? static_cast<cuuint64_t>(strideD) * 2 : row_bytes * static_cast<cuuint64_t>(M)};
+  cuuint32_t box[3] = {32u, 32u, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, D, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(GLF_ERR_INVALID, "cuTensorMapEncodeTiled (output) failed (%d)", (int)r);
+  return 0;
+}
+
 }  // namespace
 
 // bf16 tensor map over [batch][outer][inner] with row pitch `ld` elements, SWIZZLE_128B, box {64, box_outer, 1, 1}
@@ -490,8 +541,8 @@ int make_tmap_bf16(CUtensorMap* tm, const void* ptr, long long inner, long long 
 namespace {
 
 template <bool A_MN, bool B_MN, int BN>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKParams p, int num_sms, int* cs_rows,
-           cudaStream_t stream) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, GemmKParams p, int num_sms,
+           int* cs_rows, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_kernel<A_MN, B_MN, BN>;
   // per launch: the attribute is per device, and callers may drive several GPUs from one process (nn.DataParallel)
@@ -500,7 +551,28 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKParams p, int nu
   p.tiles_n = (p.N + BN - 1) / BN;
   const long long total = static_cast<long long>(p.tiles_m) * p.tiles_n * p.batch * p.split_k;
   if (total > 0x7fffffffLL) return set_error(GLF_ERR_INVALID, "gemm: too many tiles");
-  const int grid = static_cast<int>(total < num_sms ? total : num_sms);
+  int grid = static_cast<int>(total < num_sms ? total : num_sms);
+  p.b_res = 0;
+  p.nstages = Cfg::STAGES;
+  p.stage_bytes = Cfg::STAGE_BYTES;
+  p.a_off = 0;
+  {
+    const long long slab = static_cast<long long>(p.kb_total) * Cfg::B_BYTES;
+    // opt-in (GLF_BRES=1): measured on B200 it is SLOWER for the cfg2 projections (142 vs 120 us) — the streaming
+    // GEMMs are not L2 -> SM bound — so the default keeps B in the ring
+    const char* e = getenv("GLF_BRES");
+    if (!A_MN && !B_MN && !p.b_batched && p.npairs == 1 && p.split_k == 1 && slab <= 96 * 1024 &&
+        total >= 4LL * num_sms && p.tiles_n <= num_sms && e != nullptr && e[0] == '1') {
+      const int st = static_cast<int>((Cfg::RING_BYTES - slab) / Cfg::A_BYTES);
+      if (st >= 3) {
+        p.b_res = 1;
+        p.nstages = st > MAX_STAGES ? MAX_STAGES : st;
+        p.stage_bytes = Cfg::A_BYTES;
+        p.a_off = static_cast<unsigned>(slab);
+        grid = (num_sms / p.tiles_n) * p.tiles_n;   // every CTA keeps one n-tile for its whole life
+      }
+    }
+  }
   // column statistics: running sums per CTA when the (n-tile, chunk) slots fit the register accumulators
   // (and the 4 * grid rows fit the documented table capacity of 4 * batch * tiles_m rows)
   auto magic = [](long long d) { return d <= 1 ? 0u : static_cast<unsigned>((1ULL << 32) / static_cast<unsigned long long>(d)); };
@@ -514,17 +586,17 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKParams p, int nu
   p.step_n = grid % p.tiles_n;
   p.step_m = (grid / p.tiles_n) % p.tiles_m;
   p.step_z = grid / (p.tiles_m * p.tiles_n);
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, p);
   return check_cuda(cudaGetLastError(), "gemm launch");
 }
 
 template <int BN>
-int launch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
-                 int num_sms, int* cs_rows, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch<false, false, BN>(tmA, tmB, p, num_sms, cs_rows, stream);
-  if (a_mn && b_mn) return launch<true, true, BN>(tmA, tmB, p, num_sms, cs_rows, stream);
-  if (a_mn) return launch<true, false, BN>(tmA, tmB, p, num_sms, cs_rows, stream);
-  return launch<false, true, BN>(tmA, tmB, p, num_sms, cs_rows, stream);
+int launch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                 const GemmKParams& p, int num_sms, int* cs_rows, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch<false, false, BN>(tmA, tmB, tmD, p, num_sms, cs_rows, stream);
+  if (a_mn && b_mn) return launch<true, true, BN>(tmA, tmB, tmD, p, num_sms, cs_rows, stream);
+  if (a_mn) return launch<true, false, BN>(tmA, tmB, tmD, p, num_sms, cs_rows, stream);
+  return launch<false, true, BN>(tmA, tmB, tmD, p, num_sms, cs_rows, stream);
 }
 
 }  // namespace
@@ -559,7 +631,17 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
   rc = make_operand_map(&tmB, a.B, a.B.rows > 0 ? a.B.rows : a.N, a.K, a.batch, nlimbsB, BN);
   if (rc) return rc;
 
+  // bf16 outputs without a residual addend leave through bulk tensor stores (GLF_DEBUG_NO_TMA_STORE=1: per-lane stores)
+  CUtensorMap tmD = tmA;
+  bool tma_store = a.out_kind == 0 && a.addend == nullptr && a.M >= 32 && a.N >= 32 && a.strideD % 8 == 0;
+  if (const char* e = getenv("GLF_DEBUG_NO_TMA_STORE")) tma_store = tma_store && e[0] != '1';
+  if (tma_store) {
+    rc = make_output_map(&tmD, a.D, a.M, a.N, a.batch, a.ldd, a.strideD);
+    if (rc) return rc;
+  }
+
   GemmKParams p;
+  p.tma_store = tma_store ? 1 : 0;
   p.M = a.M; p.N = a.N; p.K = a.K; p.batch = a.batch;
   p.kb_total = (a.K + BK - 1) / BK;
   int sk = a.split_k < 1 ? 1 : a.split_k;
@@ -585,9 +667,9 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
     return set_error(GLF_ERR_DEVICE, "gemm: cannot query the SM count");
   const bool amn = a.A.mn_major != 0, bmn = a.B.mn_major != 0;
   switch (BN) {
-    case 64: return launch_major<64>(amn, bmn, tmA, tmB, p, num_sms, a.colstats_rows, stream);
-    case 128: return launch_major<128>(amn, bmn, tmA, tmB, p, num_sms, a.colstats_rows, stream);
-    default: return launch_major<256>(amn, bmn, tmA, tmB, p, num_sms, a.colstats_rows, stream);
+    case 64: return launch_major<64>(amn, bmn, tmA, tmB, tmD, p, num_sms, a.colstats_rows, stream);
+    case 128: return launch_major<128>(amn, bmn, tmA, tmB, tmD, p, num_sms, a.colstats_rows, stream);
+    default: return launch_major<256>(amn, bmn, tmA, tmB, tmD, p, num_sms, a.colstats_rows, stream);
   }
 }
 
