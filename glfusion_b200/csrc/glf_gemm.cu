@@ -30,7 +30,6 @@ constexpr int BK = 64;
 constexpr int EPI_WARPS = 16;                 // 4 per SM sub-partition: the epilogue is a latency chain, it needs TLP
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int GEMM_THREADS = 64 + EPI_THREADS;  // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
-constexpr int MAX_STAGES = 10;
 
 struct GemmKParams {
   int M, N, K, batch;
@@ -51,11 +50,6 @@ struct GemmKParams {
   int tiles_m, tiles_n;
   int step_n, step_m, step_z;    // (n-tile, m-tile, batch*split) advance per persistent-loop step of gridDim.x tiles
   int tma_store;                 // 1: bf16 output tiles leave through cp.async.bulk.tensor stores (tmD), no addend
-  // B-stationary mode (small shared weight operand, K-major): the CTA's whole B slab [BN, K] is loaded once and
-  // stays in shared memory; the ring then carries A only (halves the L2 -> SM traffic of the streaming projections)
-  int b_res;
-  int nstages;                   // ring depth actually used (<= MAX_STAGES)
-  unsigned stage_bytes, a_off;   // bytes per ring stage, offset of the ring behind the resident B slab
 };
 
 template <int BN>
@@ -96,10 +90,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmD, const GemmKParams p) {
   using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[MAX_STAGES];
-  __shared__ uint64_t empty_bar[MAX_STAGES];
-  __shared__ uint64_t b_full_bar;
+  __shared__ uint64_t full_bar[STAGES];
+  __shared__ uint64_t empty_bar[STAGES];
   __shared__ uint64_t tmem_full_bar[2];
   __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_holder;
@@ -116,11 +110,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < p.nstages; ++s) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    mbar_init(smem_u32(&b_full_bar), 1);
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tmem_full_bar[s]), 1);
@@ -139,13 +133,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      if (p.b_res) {   // gridDim.x is a multiple of tiles_n: this CTA's n-tile never changes
-        const int nt_fixed = static_cast<int>(blockIdx.x) % p.tiles_n;
-        const uint32_t bb_ = smem_u32(&b_full_bar);
-        mbar_expect_tx(bb_, static_cast<uint32_t>(p.kb_total) * Cfg::B_BYTES);
-        for (int kb = 0; kb < p.kb_total; ++kb)
-          tma_load_4d(&tmB, bb_, smem_base + kb * Cfg::B_BYTES, kb * BK, nt_fixed * BN, 0, 0);
-      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int z, mn, mt, nt, b, split;
         fastdivmod(tile, tiles_mn, p.mg_mn, z, mn);
@@ -160,8 +147,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           const int k0 = (kb0 + it / p.npairs) * BK;
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-          mbar_expect_tx(fb, p.b_res ? Cfg::A_BYTES : Cfg::STAGE_BYTES);
-          const uint32_t sa = smem_base + p.a_off + stage * p.stage_bytes;
+          mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
           if (!A_MN) {
             tma_load_4d(&tmA, fb, sa, k0, m0, ab, p.pairA[pair]);
@@ -169,16 +156,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             tma_load_4d(&tmA, fb, sa, m0, k0, ab, p.pairA[pair]);
             tma_load_4d(&tmA, fb, sa + 8192, m0 + 64, k0, ab, p.pairA[pair]);
           }
-          if (p.b_res) {
-            // B slab is resident
-          } else if (!B_MN) {
+          if (!B_MN) {
             tma_load_4d(&tmB, fb, sb, k0, n0, bb, p.pairB[pair]);
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
               tma_load_4d(&tmB, fb, sb + j * 8192, n0 + j * 64, k0, bb, p.pairB[pair]);
           }
-          if (++stage == p.nstages) {
+          if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
@@ -192,10 +177,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      if (p.b_res) {
-        mbar_wait(smem_u32(&b_full_bar), 0);
-        tc_fence_after();
-      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
         int z, mn, b, split;
         fastdivmod(tile, tiles_mn, p.mg_mn, z, mn);
@@ -210,8 +191,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         for (int it = 0; it < niter; ++it) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + p.a_off + stage * p.stage_bytes;
-          const uint32_t sb = p.b_res ? smem_base + (kb0 + it) * Cfg::B_BYTES : sa + Cfg::A_BYTES;
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t ad = A_MN ? make_sdesc(sa + k * 2048, 8192, 1024) : make_sdesc(sa + k * 32, 16, 1024);
@@ -219,7 +200,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             umma_f16(tacc, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
           }
           umma_commit(smem_u32(&empty_bar[stage]));  // slot reusable once these MMAs have read it
-          if (++stage == p.nstages) {
+          if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
@@ -551,28 +532,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
   p.tiles_n = (p.N + BN - 1) / BN;
   const long long total = static_cast<long long>(p.tiles_m) * p.tiles_n * p.batch * p.split_k;
   if (total > 0x7fffffffLL) return set_error(GLF_ERR_INVALID, "gemm: too many tiles");
-  int grid = static_cast<int>(total < num_sms ? total : num_sms);
-  p.b_res = 0;
-  p.nstages = Cfg::STAGES;
-  p.stage_bytes = Cfg::STAGE_BYTES;
-  p.a_off = 0;
-  {
-    const long long slab = static_cast<long long>(p.kb_total) * Cfg::B_BYTES;
-    // opt-in (GLF_BRES=1): measured on B200 it is SLOWER for the cfg2 projections (142 vs 120 us) — the streaming
-    // GEMMs are not L2 -> SM bound — so the default keeps B in the ring
-    const char* e = getenv("GLF_BRES");
-    if (!A_MN && !B_MN && !p.b_batched && p.npairs == 1 && p.split_k == 1 && slab <= 96 * 1024 &&
-        total >= 4LL * num_sms && p.tiles_n <= num_sms && e != nullptr && e[0] == '1') {
-      const int st = static_cast<int>((Cfg::RING_BYTES - slab) / Cfg::A_BYTES);
-      if (st >= 3) {
-        p.b_res = 1;
-        p.nstages = st > MAX_STAGES ? MAX_STAGES : st;
-        p.stage_bytes = Cfg::A_BYTES;
-        p.a_off = static_cast<unsigned>(slab);
-        grid = (num_sms / p.tiles_n) * p.tiles_n;   // every CTA keeps one n-tile for its whole life
-      }
-    }
-  }
+  const int grid = static_cast<int>(total < num_sms ? total : num_sms);
   // column statistics: running sums per CTA when the (n-tile, chunk) slots fit the register accumulators
   // (and the 4 * grid rows fit the documented table capacity of 4 * batch * tiles_m rows)
   auto magic = [](long long d) { return d <= 1 ? 0u : static_cast<unsigned>((1ULL << 32) / static_cast<unsigned long long>(d)); };
