@@ -5,6 +5,8 @@
 // transposes it through shared memory and writes both token-major [B, V*h*w, C] operands with 128-bit stores.
 // The backward is the mirror pass: df4 = dXg + a * dXl (back to NCHW) plus the gate gradient da = sum_c f4 * dXl
 // chained through the two sigmoids / the class max to the logits.
+#include <cstdlib>
+
 #include "glf_internal.h"
 #include "glf_ptx.cuh"
 
@@ -252,6 +254,199 @@ __global__ void gate_finish_kernel(const ViewPtrs vp, const float* __restrict__ 
   for (int k = 0; k < ncls; ++k) dcl[static_cast<long long>(k) * hw] = (k == arg) ? dm * m * (1.f - m) : 0.f;
 }
 
+// ------------------------------------------------------------------------------------------------ TMA + ldmatrix forms
+// bf16 NCHW views with hw % 8 == 0 and C % 64 == 0 (the cfg2 / network shapes).  One CTA = one (batch, view, 64-position
+// block) with ALL channels:
+//   * the NCHW side moves as TMA tensor tiles (64 channels x 64 positions, SWIZZLE_128B) and the token-major side as
+//     plain bulk copies (64 token rows are one contiguous 64*C*2-byte block), so a CTA has its whole tile (32 KB
+//     forward, 96 KB backward) in flight at once — several CTAs per SM keep ~190 KB outstanding;
+//   * the 16-bit transposition is done by ldmatrix.trans: with the row -> (channel | position) mapping below a thread
+//     receives 8 consecutive channels of one token (forward) or 8 consecutive positions of one channel (backward)
+//     as one 16-byte register quad, i.e. exactly one 128-bit global store.
+struct ViewMaps {
+  CUtensorMap tm[MAXV];
+};
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void bulk_g2s_gate(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// grid: (ceil(hw/64), B*V); block 256 (8 warps: warp w owns positions 8w..8w+7 of the block)
+__global__ void __launch_bounds__(256)
+    gate_concat_fwd_tma_kernel(const __grid_constant__ ViewMaps maps, const ViewPtrs vp, bf16* __restrict__ xg,
+                               bf16* __restrict__ xl, float* __restrict__ gate, int C, int V, int hw, int ncls,
+                               float weight) {
+  extern __shared__ uint8_t gsm_raw[];
+  __shared__ uint64_t bar;
+  __shared__ float a_sm[64];
+  const uint32_t base = (smem_u32(gsm_raw) + 1023u) & ~1023u;
+  const int bv = blockIdx.y, b = bv / V, v = bv % V;
+  const int p0 = blockIdx.x * 64;
+  const int nbox = C / 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(smem_u32(&bar), static_cast<uint32_t>(nbox) * 8192u);
+    for (int cb = 0; cb < nbox; ++cb) tma_load_4d(&maps.tm[v], smem_u32(&bar), base + cb * 8192, p0, cb * 64, b, 0);
+  }
+  if (threadIdx.x < 64) {
+    const int p = p0 + threadIdx.x;
+    float a = 0.f;
+    if (p < hw) {
+      const float* cl = vp.cls[v] + static_cast<long long>(b) * ncls * hw + p;
+      float lmax = cl[0];
+      for (int k = 1; k < ncls; ++k) lmax = fmaxf(lmax, cl[static_cast<long long>(k) * hw]);
+      const float m = sigmoidf_(lmax);  // max_c sigmoid(l_c) == sigmoid(max_c l_c)
+      const float c = sigmoidf_(vp.ctr[v][static_cast<long long>(b) * hw + p]);
+      a = sigmoidf_(weight * m * c);
+      gate[static_cast<long long>(bv) * hw + p] = a;
+    }
+    a_sm[threadIdx.x] = a;
+  }
+  __syncthreads();
+  mbar_wait(smem_u32(&bar), 0);
+  // ldmatrix row supplied by this lane: matrix j = lane / 8, row r = lane % 8  <->  channel 8 (r/2) + 2 j + (r%2)
+  // of the current 32-channel group; after .trans thread T holds channels 8 (T%4) .. +7 of position T/4
+  const int mj = lane >> 3, mr = lane & 7;
+  const int co = 8 * (mr >> 1) + 2 * mj + (mr & 1);
+  const int pl = warp * 8 + (lane >> 2);          // position of this thread inside the block
+  const int p = p0 + pl;
+  const float a = a_sm[pl];
+  const float2 a2 = make_float2(a, a);
+  const long long tok = (static_cast<long long>(b) * V * hw + static_cast<long long>(v) * hw + p) * C + (lane & 3) * 8;
+  const int ngrp = C / 32;
+#pragma unroll 2
+  for (int cg = 0; cg < ngrp; ++cg) {
+    const int ch = cg * 32 + co;                  // channel whose 8-position chunk this lane addresses
+    const int row = ch & 63;
+    const uint32_t addr = base + (ch >> 6) * 8192 + row * 128 + ((warp ^ (row & 7)) << 4);
+    uint32_t r[4];
+    ldmatrix_x4_trans(addr, r);
+    if (p < hw) {
+      *reinterpret_cast<uint4*>(xg + tok + cg * 32) = make_uint4(r[0], r[1], r[2], r[3]);
+      uint32_t g[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 y = mul2(unpack_bf16(r[i]), a2);
+        g[i] = pack_bf16(y.x, y.y);
+      }
+      *reinterpret_cast<uint4*>(xl + tok + cg * 32) = make_uint4(g[0], g[1], g[2], g[3]);
+    }
+  }
+}
+
+// grid: (ceil(hw/64), B*V); block 256.  df4 = dXg + a * dXl back to NCHW and the complete gate gradient
+// da[p] = sum_c f4[c,p] * dXl[p,c] (the CTA sees every channel, so no partial table: da_part has one slice).
+__global__ void __launch_bounds__(256)
+    gate_concat_bwd_tma_kernel(const __grid_constant__ ViewMaps maps, const ViewPtrs vp, const float* __restrict__ gate,
+                               const bf16* __restrict__ dxg, const bf16* __restrict__ dxl, float* __restrict__ da_part,
+                               int C, int V, int hw) {
+  extern __shared__ uint8_t gsm_raw[];
+  __shared__ uint64_t bar;
+  __shared__ float a_sm[64];
+  const uint32_t base = (smem_u32(gsm_raw) + 1023u) & ~1023u;
+  uint8_t* gen = gsm_raw + (base - smem_u32(gsm_raw));
+  const int bv = blockIdx.y, b = bv / V, v = bv % V;
+  const int p0 = blockIdx.x * 64;
+  const int nbox = C / 64;
+  const int valid = min(64, hw - p0);
+  const uint32_t tile_bytes = 64u * C * 2u;       // one [64 positions][C] bf16 tile
+  const uint32_t sF = base, sG = base + tile_bytes, sL = base + 2 * tile_bytes;
+  uint8_t* gG = gen + tile_bytes;
+  uint8_t* gL = gen + 2 * tile_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t tok_bytes = static_cast<uint32_t>(valid) * C * 2u;
+    mbar_expect_tx(smem_u32(&bar), static_cast<uint32_t>(nbox) * 8192u + 2u * tok_bytes);
+    for (int cb = 0; cb < nbox; ++cb) tma_load_4d(&maps.tm[v], smem_u32(&bar), sF + cb * 8192, p0, cb * 64, b, 0);
+    const long long off = (static_cast<long long>(b) * V * hw + static_cast<long long>(v) * hw + p0) * C;
+    bulk_g2s_gate(sG, dxg + off, tok_bytes, smem_u32(&bar));
+    bulk_g2s_gate(sL, dxl + off, tok_bytes, smem_u32(&bar));
+  }
+  if (threadIdx.x < 64) {
+    const int p = p0 + threadIdx.x;
+    a_sm[threadIdx.x] = p < hw ? gate[static_cast<long long>(bv) * hw + p] : 0.f;
+  }
+  __syncthreads();
+  mbar_wait(smem_u32(&bar), 0);
+  const int mj = lane >> 3, mr = lane & 7;
+  const int off8 = 8 * (mr >> 1) + 2 * mj + (mr & 1);   // row offset inside a 32-row group addressed by this lane
+  const uint32_t row_bytes = static_cast<uint32_t>(C) * 2u;
+  {
+    // phase A: warp w owns positions 8w..8w+7; per 32-channel group: f4 (transposed through ldmatrix), dXl, dXg ->
+    // gate-gradient partial and the combined gradient, written back in place over dXg
+    const int pl = warp * 8 + (lane >> 2);
+    const float a = a_sm[pl];
+    const float2 a2 = make_float2(a, a);
+    float2 acc = make_float2(0.f, 0.f);
+    const int ngrp = C / 32;
+    const uint32_t tokoff = pl * row_bytes + (lane & 3) * 16;
+#pragma unroll 2
+    for (int cg = 0; cg < ngrp; ++cg) {
+      const int ch = cg * 32 + off8;
+      const int row = ch & 63;
+      uint32_t f[4];
+      ldmatrix_x4_trans(sF + (ch >> 6) * 8192 + row * 128 + ((warp ^ (row & 7)) << 4), f);
+      const uint4 lv = *reinterpret_cast<const uint4*>(gL + tokoff + cg * 64);
+      uint4 gv = *reinterpret_cast<const uint4*>(gG + tokoff + cg * 64);
+      const uint32_t* l32 = reinterpret_cast<const uint32_t*>(&lv);
+      uint32_t* g32 = reinterpret_cast<uint32_t*>(&gv);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 dl = unpack_bf16(l32[i]);
+        acc = fma2(unpack_bf16(f[i]), dl, acc);
+        const float2 t = fma2(a2, dl, unpack_bf16(g32[i]));
+        g32[i] = pack_bf16(t.x, t.y);
+      }
+      *reinterpret_cast<uint4*>(gG + tokoff + cg * 64) = gv;
+    }
+    float da = acc.x + acc.y;
+    da += __shfl_xor_sync(0xffffffffu, da, 1);
+    da += __shfl_xor_sync(0xffffffffu, da, 2);
+    if ((lane & 3) == 0 && pl < valid) da_part[static_cast<long long>(bv) * hw + p0 + pl] = da;
+  }
+  __syncthreads();
+  {
+    // phase B: [position][channel] -> NCHW.  ldmatrix rows = positions; thread T receives positions 8 (T%4) .. +7 of
+    // channel 8 c8 + T/4
+    bf16* df4 = reinterpret_cast<bf16*>(vp.df4[v]) + static_cast<long long>(b) * C * hw;
+    const int nunits = 2 * (C / 8);               // (32-position group, 8-channel chunk)
+    for (int u = warp; u < nunits; u += 8) {
+      const int pg = u & 1, c8 = u >> 1;
+      uint32_t r[4];
+      ldmatrix_x4_trans(sG + (pg * 32 + off8) * row_bytes + c8 * 16, r);
+      const int pp = p0 + pg * 32 + (lane & 3) * 8;
+      const int c = c8 * 8 + (lane >> 2);
+      if (pp < hw) *reinterpret_cast<uint4*>(df4 + static_cast<long long>(c) * hw + pp) = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+  }
+}
+
+bool gate_tma_ok(int C, int hw, int io_dtype, int x_dtype, const void* const* f4, int V) {
+  if (io_dtype != GLF_DTYPE_BF16 || x_dtype != GLF_DTYPE_BF16) return false;
+  if (C % 64 != 0 || C > 512 || hw % 8 != 0) return false;
+  for (int v = 0; v < V; ++v)
+    if ((reinterpret_cast<uintptr_t>(f4[v]) & 15) != 0) return false;
+  if (const char* e = getenv("GLF_DEBUG_GATE_SIMT")) return e[0] != '1';
+  return true;
+}
+
 template <typename TX>
 int launch_gate_fwd(dim3 grid, bool vec2, int io_dtype, const ViewPtrs& vp, void* xg, void* xl, float* gate, int C, int V,
                     int hw, int ncls, float weight, cudaStream_t stream) {
@@ -287,6 +482,20 @@ int gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, i
   ViewPtrs vp{};
   for (int v = 0; v < V; ++v) { vp.f4[v] = f4[v]; vp.cls[v] = cls[v]; vp.ctr[v] = ctr[v]; }
   const int hw = h * w;
+  if (gate_tma_ok(C, hw, io_dtype, x_dtype, f4, V) && B * V <= 65535) {
+    ViewMaps maps;
+    for (int v = 0; v < V; ++v) {
+      int rc = make_tmap_bf16(&maps.tm[v], f4[v], hw, C, B, hw, static_cast<long long>(C) * hw, 64);
+      if (rc) return rc;
+    }
+    for (int v = V; v < MAXV; ++v) maps.tm[v] = maps.tm[0];
+    const uint32_t smem = static_cast<uint32_t>(C / 64) * 8192u + 1024u;
+    cudaError_t e = cudaFuncSetAttribute(gate_concat_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gate_fwd_tma)");
+    gate_concat_fwd_tma_kernel<<<dim3((hw + 63) / 64, B * V), 256, smem, stream>>>(
+        maps, vp, reinterpret_cast<bf16*>(xg), reinterpret_cast<bf16*>(xl), gate, C, V, hw, ncls, weight);
+    return check_cuda(cudaGetLastError(), "gate_concat_fwd_tma launch");
+  }
   dim3 grid((hw + 63) / 64, (C + 63) / 64, B * V);
   if (grid.y > 65535 || grid.z > 65535) return set_error(GLF_ERR_INVALID, "gate_concat: grid too large");
   const bool vec2 = (hw % 2 == 0);
@@ -311,7 +520,30 @@ int gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, i
     vp.df4[v] = df4[v]; vp.dcls[v] = dcls[v]; vp.dctr[v] = dctr[v];
   }
   const int hw = h * w;
-  const int nct = (C + 63) / 64;
+  int nct = (C + 63) / 64;
+  bool tma_ok = gate_tma_ok(C, hw, io_dtype, x_dtype, f4, V) && B * V <= 65535 &&
+                ((reinterpret_cast<uintptr_t>(dxg) | reinterpret_cast<uintptr_t>(dxl)) & 15) == 0;
+  for (int v = 0; v < V && tma_ok; ++v) tma_ok = (reinterpret_cast<uintptr_t>(df4[v]) & 15) == 0;
+  if (tma_ok) {
+    ViewMaps maps;
+    for (int v = 0; v < V; ++v) {
+      int rc = make_tmap_bf16(&maps.tm[v], f4[v], hw, C, B, hw, static_cast<long long>(C) * hw, 64);
+      if (rc) return rc;
+    }
+    for (int v = V; v < MAXV; ++v) maps.tm[v] = maps.tm[0];
+    const uint32_t smem = 3u * 64u * C * 2u + 1024u;
+    cudaError_t e = cudaFuncSetAttribute(gate_concat_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gate_bwd_tma)");
+    gate_concat_bwd_tma_kernel<<<dim3((hw + 63) / 64, B * V), 256, smem, stream>>>(
+        maps, vp, gate, reinterpret_cast<const bf16*>(dxg), reinterpret_cast<const bf16*>(dxl), da_part, C, V, hw);
+    int rc = check_cuda(cudaGetLastError(), "gate_concat_bwd_tma launch");
+    if (rc) return rc;
+    nct = 1;   // the gate gradient is complete: one slice of the table
+    const long long n = static_cast<long long>(B) * V * hw;
+    gate_finish_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(vp, gate, da_part, nct, B * V, V, hw,
+                                                                                  ncls, weight);
+    return check_cuda(cudaGetLastError(), "gate_finish launch");
+  }
   dim3 grid((hw + 63) / 64, nct, B * V);
   if (grid.y > 65535 || grid.z > 65535) return set_error(GLF_ERR_INVALID, "gate_concat: grid too large");
   const bool vec2 = (hw % 2 == 0);
