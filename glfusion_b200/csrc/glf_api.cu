@@ -522,11 +522,16 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
       t1 = wb.cs_t + Ci;
       t2 = wb.cs_t + 2 * Ci;
     }
-    const int np_in[3] = {np, np_p, np_g};
-    GLF_TRY(reduce_stage1(t0, t1, t2, 3, np_in, &np, &rs, 0, 1, Ci, wb.red1, stream));
-    GLF_TRY(reduce_partials3(wb.red1, wb.red1 + static_cast<long long>(REDUCE_STAGE1_ROWS) * Ci,
-                             wb.red1 + 2LL * REDUCE_STAGE1_ROWS * Ci, np, rs, Ci, g_->theta_b, g_->phi_b, g_->g_b,
-                             stream));
+    if (np == np_p && np == np_g && np <= 4 * REDUCE_STAGE1_ROWS) {
+      // short tables (one row per CTA): a single fixed-order reduction
+      GLF_TRY(reduce_partials3(t0, t1, t2, np, rs, Ci, g_->theta_b, g_->phi_b, g_->g_b, stream));
+    } else {
+      const int np_in[3] = {np, np_p, np_g};
+      GLF_TRY(reduce_stage1(t0, t1, t2, 3, np_in, &np, &rs, 0, 1, Ci, wb.red1, stream));
+      GLF_TRY(reduce_partials3(wb.red1, wb.red1 + static_cast<long long>(REDUCE_STAGE1_ROWS) * Ci,
+                               wb.red1 + 2LL * REDUCE_STAGE1_ROWS * Ci, np, rs, Ci, g_->theta_b, g_->phi_b, g_->g_b,
+                               stream));
+    }
   }
   if (m.pack_x) {
     if (d->x_layout == GLF_LAYOUT_NCTHW)

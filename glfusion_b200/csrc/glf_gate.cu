@@ -395,26 +395,41 @@ __global__ void __launch_bounds__(256)
     const float a = a_sm[pl];
     const float2 a2 = make_float2(a, a);
     float2 acc = make_float2(0.f, 0.f);
-    const int ngrp = C / 32;
-    const uint32_t tokoff = pl * row_bytes + (lane & 3) * 16;
-#pragma unroll 2
-    for (int cg = 0; cg < ngrp; ++cg) {
-      const int ch = cg * 32 + off8;
-      const int row = ch & 63;
-      uint32_t f[4];
-      ldmatrix_x4_trans(sF + (ch >> 6) * 8192 + row * 128 + ((warp ^ (row & 7)) << 4), f);
-      const uint4 lv = *reinterpret_cast<const uint4*>(gL + tokoff + cg * 64);
-      uint4 gv = *reinterpret_cast<const uint4*>(gG + tokoff + cg * 64);
-      const uint32_t* l32 = reinterpret_cast<const uint32_t*>(&lv);
-      uint32_t* g32 = reinterpret_cast<uint32_t*>(&gv);
+    const int npair = C / 64;
+    const uint32_t rowoff = pl * row_bytes;
+    // the combined gradient goes back over dXg with its 16-byte chunks XOR-swizzled by f(pos) (8 distinct values over
+    // the 8 rows of a phase-B ldmatrix), which makes the transposing reads of phase B bank-conflict free; the swizzle
+    // permutes chunks inside an aligned group of 8 = two 32-channel groups, so both are read before either is written
+    const int fsw = ((pl >> 3) & 3) * 2 + (pl & 1);
+    for (int cp = 0; cp < npair; ++cp) {
+      uint4 gv[2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 dl = unpack_bf16(l32[i]);
-        acc = fma2(unpack_bf16(f[i]), dl, acc);
-        const float2 t = fma2(a2, dl, unpack_bf16(g32[i]));
-        g32[i] = pack_bf16(t.x, t.y);
+      for (int h = 0; h < 2; ++h) {
+        const int cg = 2 * cp + h;
+        const int ch = cg * 32 + off8;
+        const int row = ch & 63;
+        uint32_t f[4];
+        ldmatrix_x4_trans(sF + (ch >> 6) * 8192 + row * 128 + ((warp ^ (row & 7)) << 4), f);
+        const uint32_t tokoff = rowoff + (cg * 4 + (lane & 3)) * 16;
+        const uint4 lv = *reinterpret_cast<const uint4*>(gL + tokoff);
+        gv[h] = *reinterpret_cast<const uint4*>(gG + tokoff);
+        const uint32_t* l32 = reinterpret_cast<const uint32_t*>(&lv);
+        uint32_t* g32 = reinterpret_cast<uint32_t*>(&gv[h]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 dl = unpack_bf16(l32[i]);
+          acc = fma2(unpack_bf16(f[i]), dl, acc);
+          const float2 t = fma2(a2, dl, unpack_bf16(g32[i]));
+          g32[i] = pack_bf16(t.x, t.y);
+        }
       }
-      *reinterpret_cast<uint4*>(gG + tokoff + cg * 64) = gv;
+      __syncwarp();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c16 = (2 * cp + h) * 4 + (lane & 3);
+        *reinterpret_cast<uint4*>(gG + rowoff + ((c16 ^ fsw) << 4)) = gv[h];
+      }
+      __syncwarp();
     }
     float da = acc.x + acc.y;
     da += __shfl_xor_sync(0xffffffffu, da, 1);
@@ -430,7 +445,8 @@ __global__ void __launch_bounds__(256)
     for (int u = warp; u < nunits; u += 8) {
       const int pg = u & 1, c8 = u >> 1;
       uint32_t r[4];
-      ldmatrix_x4_trans(sG + (pg * 32 + off8) * row_bytes + c8 * 16, r);
+      const int prow = pg * 32 + off8;
+      ldmatrix_x4_trans(sG + prow * row_bytes + ((c8 ^ (((prow >> 3) & 3) * 2 + (prow & 1))) << 4), r);
       const int pp = p0 + pg * 32 + (lane & 3) * 8;
       const int c = c8 * 8 + (lane >> 2);
       if (pp < hw) *reinterpret_cast<uint4*>(df4 + static_cast<long long>(c) * hw + pp) = make_uint4(r[0], r[1], r[2], r[3]);

@@ -46,7 +46,7 @@ struct GemmKParams {
   long long ld_add, stride_add;
   float* colstats;
   unsigned mg_mn, mg_n, mg_sk;   // multiply-high magics for / tiles_mn, / tiles_n, / split_k
-  int cs_accum;   // 1: column statistics accumulated per CTA over all its tiles (table rows = gridDim.x * 4)
+  int cs_accum;   // 1: column statistics accumulated per CTA over all its tiles (table rows = gridDim.x)
   int tiles_m, tiles_n;
   int step_n, step_m, step_z;    // (n-tile, m-tile, batch*split) advance per persistent-loop step of gridDim.x tiles
   int tma_store;                 // 1: bf16 output tiles leave through cp.async.bulk.tensor stores (tmD), no addend
@@ -424,16 +424,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       z += p.step_z + carry;
     }
     if (p.tma_store && lane == 0) tma_store_wait_all<0>();
-    if (p.colstats != nullptr && p.cs_accum && cc0 < NCHUNK && half == 0) {
-      // one partial row per (CTA, row quarter); every column owned by this warp is written, seen or not
-      float* cs = p.colstats + (static_cast<long long>(blockIdx.x) * 4 + q) * 2 * p.N;
+    if (p.colstats != nullptr && p.cs_accum) {
+      // ONE partial row per CTA: the four warps that share a column chunk (one per 32-row quarter) combine their
+      // running sums through the now idle staging tiles, in a fixed order
+      __syncwarp();
+      float2* xs = reinterpret_cast<float2*>(wstg);          // [slot][sum | sum of squares][16 column pairs]
+      if (half == 0) {
 #pragma unroll
-      for (int i = 0; i < CS_SLOTS; ++i) {
-        const int nt_i = i / CPW, k = i % CPW;
-        const int col = nt_i * BN + (cc0 + 4 * k) * 32 + 2 * hl;
-        if (nt_i < p.tiles_n && cc0 + 4 * k < NCHUNK && col < p.N) {
-          *reinterpret_cast<float2*>(cs + col) = cs1[i];
-          *reinterpret_cast<float2*>(cs + p.N + col) = cs2[i];
+        for (int i = 0; i < CS_SLOTS; ++i) {
+          xs[(2 * i) * 16 + hl] = cs1[i];
+          xs[(2 * i + 1) * 16 + hl] = cs2[i];
+        }
+      }
+      named_bar_sync(1, EPI_THREADS);
+      if ((ew & 3) == 0 && cc0 < NCHUNK && half == 0) {
+        float* cs = p.colstats + static_cast<long long>(blockIdx.x) * 2 * p.N;
+#pragma unroll
+        for (int i = 0; i < CS_SLOTS; ++i) {
+          const int nt_i = i / CPW, k = i % CPW;
+          const int col = nt_i * BN + (cc0 + 4 * k) * 32 + 2 * hl;
+          if (nt_i < p.tiles_n && cc0 + 4 * k < NCHUNK && col < p.N) {
+            float2 t1 = make_float2(0.f, 0.f), t2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int w4 = 0; w4 < 4; ++w4) {
+              const float2* o = reinterpret_cast<const float2*>(wstg + w4 * Cfg::WARP_STG);
+              t1 = add2(t1, o[(2 * i) * 16 + hl]);
+              t2 = add2(t2, o[(2 * i + 1) * 16 + hl]);
+            }
+            *reinterpret_cast<float2*>(cs + col) = t1;
+            *reinterpret_cast<float2*>(cs + p.N + col) = t2;
+          }
         }
       }
     }
@@ -542,7 +562,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
   p.cs_accum = (p.colstats != nullptr && p.tiles_n * ((BN / 32 + 3) / 4) <= 4 &&
                 grid <= static_cast<long long>(p.batch) * p.tiles_m) ? 1 : 0;
   if (cs_rows != nullptr)
-    *cs_rows = p.colstats == nullptr ? 0 : (p.cs_accum ? grid * 4 : p.batch * p.tiles_m * 4);
+    *cs_rows = p.colstats == nullptr ? 0 : (p.cs_accum ? grid : p.batch * p.tiles_m * 4);
   p.step_n = grid % p.tiles_n;
   p.step_m = (grid / p.tiles_n) % p.tiles_m;
   p.step_z = grid / (p.tiles_m * p.tiles_n);
