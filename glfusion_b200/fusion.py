@@ -23,6 +23,16 @@ from .tpavi import (TPAVIModule, TPAVIState, _blob, _io_dtype, _stream_ptr, _wei
                     tpavi_forward_raw)
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def _pair_ln_ok(mg, ml, shape, x, prec) -> bool:
     """True when the MGFM / MLFM LayerNorm stages can run as one fused pass (glf_fusion_ln_fwd / _bwd)."""
     if mg.inter_channels != ml.inter_channels or mg._mode_id != ml._mode_id or mg._bn_layer != ml._bn_layer:
@@ -91,14 +101,30 @@ class _FusionFunction(torch.autograd.Function):
         tg, tl = mg._param_table(pg), ml._param_table(pl)
         shape = (B, V_, h, w, C_)
         pair = _pair_ln_ok(mg, ml, shape, xg, prec)
-        zsum, stg, svg, _ = tpavi_forward_raw(xg, tg, mg._buffer_table(), mode=mg._mode_id, training=mg.training,
-                                              bn_layer=mg._bn_layer, Ci=mg.inter_channels,
-                                              keep_for_backward=need or pair, token_shape=shape, precision=prec,
-                                              defer_ln=pair)
-        _, stl, svl, _ = tpavi_forward_raw(xl, tl, ml._buffer_table(), mode=ml._mode_id, training=ml.training,
-                                           bn_layer=ml._bn_layer, Ci=ml.inter_channels,
-                                           keep_for_backward=need or pair, z_out=zsum, accumulate=not pair,
-                                           token_shape=shape, precision=prec, defer_ln=pair)
+        zsum = torch.empty(shape, dtype=xg.dtype, device=xg.device)
+        # MGFM and MLFM are independent up to the fused LayerNorm: the local block runs on a side stream (a parallel
+        # branch when the step is captured in a CUDA graph), so one block's short latency-bound kernels (BN statistics,
+        # the per-sequence W' products) overlap the other's streaming GEMMs
+        side = _side_stream(xg.device) if pair and fusion.overlap_blocks else None
+        if side is not None:
+            cur = torch.cuda.current_stream(xg.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                _, stl, svl, _ = tpavi_forward_raw(xl, tl, ml._buffer_table(), mode=ml._mode_id, training=ml.training,
+                                                   bn_layer=ml._bn_layer, Ci=ml.inter_channels,
+                                                   keep_for_backward=True, z_out=zsum, accumulate=False,
+                                                   token_shape=shape, precision=prec, defer_ln=True)
+        _, stg, svg, _ = tpavi_forward_raw(xg, tg, mg._buffer_table(), mode=mg._mode_id, training=mg.training,
+                                           bn_layer=mg._bn_layer, Ci=mg.inter_channels,
+                                           keep_for_backward=need or pair, z_out=zsum, token_shape=shape,
+                                           precision=prec, defer_ln=pair)
+        if side is not None:
+            cur.wait_stream(side)
+        else:
+            _, stl, svl, _ = tpavi_forward_raw(xl, tl, ml._buffer_table(), mode=ml._mode_id, training=ml.training,
+                                               bn_layer=ml._bn_layer, Ci=ml.inter_channels,
+                                               keep_for_backward=need or pair, z_out=zsum, accumulate=not pair,
+                                               token_shape=shape, precision=prec, defer_ln=pair)
         if pair:
             # both blocks' BN + residual + LayerNorm and the `global + local` sum (ours.py:1834) in one HBM pass
             wg, wl = _weights_struct(tg, mg._buffer_table()), _weights_struct(tl, ml._buffer_table())
@@ -142,10 +168,20 @@ class _FusionFunction(torch.autograd.Function):
                 L.check(L.load().glf_fusion_ln_bwd(C.byref(stg.desc), L.ptr(dz), L.ptr(xg), L.ptr(xl), C.byref(wg),
                                                    C.byref(wl), L.ptr(svg), L.ptr(svl), L.ptr(wsg), L.ptr(wsl),
                                                    _stream_ptr()))
+        side = _side_stream(xg.device) if ctx.pair and ctx.fusion.overlap_blocks else None
+        if side is not None:       # after the fused LayerNorm backward the two blocks' chains are independent again
+            cur = torch.cuda.current_stream(xg.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                dxl, gl = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xl, stl, svl, tl, ml._buffer_table(), ws=wsl,
+                                             grad_out=getattr(ml, "_grad_out", None))
         dxg, gg = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xg, stg, svg, tg, mg._buffer_table(), ws=wsg,
                                      grad_out=getattr(mg, "_grad_out", None))
-        dxl, gl = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xl, stl, svl, tl, ml._buffer_table(), ws=wsl,
-                                     grad_out=getattr(ml, "_grad_out", None))
+        if side is not None:
+            cur.wait_stream(side)
+        else:
+            dxl, gl = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xl, stl, svl, tl, ml._buffer_table(), ws=wsl,
+                                         grad_out=getattr(ml, "_grad_out", None))
         df4, dcls, dctr = gate_concat_backward(f4, cls, ctr, gate, dxg, dxl, ctx.fusion.center_aware_weight)
         out = [None, None, None] + list(df4) + list(dcls) + list(dctr)
         for mod, plist, gr in ((mg, pg, gg), (ml, pl, gl)):
@@ -163,6 +199,7 @@ class GlobalLocalFusion(nn.Module):
                  inter_channels=None):
         super().__init__()
         self.center_aware_weight = center_aware_weight
+        self.overlap_blocks = True      # run MGFM / MLFM on two streams between the fused stages
         self.global_attn = TPAVIModule(in_channels=in_channels, inter_channels=inter_channels, mode=mode)
         self.local_attn = TPAVIModule(in_channels=in_channels, inter_channels=inter_channels, mode=mode)
 
