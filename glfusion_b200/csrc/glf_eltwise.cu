@@ -518,46 +518,22 @@ __global__ void __launch_bounds__(32 * RED_Y)
   }
 }
 
-// dU = k1*dV + k2*U + k3 (per channel), 8 channels per vector, UNR vectors in flight per thread (packed fp32 math for
-// the bf16 form: the kernel is a pure stream, what matters is bytes in flight per SM)
+// dU = k1*dV + k2*U + k3 (per channel), 8 channels per thread
 template <typename TA>
-__global__ void __launch_bounds__(256)
-    bn_bwd_apply_kernel(const TA* __restrict__ dV, const TA* __restrict__ U, const float* __restrict__ k1,
-                        const float* __restrict__ k2, const float* __restrict__ k3, TA* __restrict__ dU,
-                        long long nvec, int C) {
-  constexpr int UNR = 4;
+__global__ void bn_bwd_apply_kernel(const TA* __restrict__ dV, const TA* __restrict__ U,
+                                    const float* __restrict__ k1, const float* __restrict__ k2,
+                                    const float* __restrict__ k3, TA* __restrict__ dU, long long nvec, int C) {
   const int cv = C / 8;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * UNR) {
-    Raw8<TA> rv[UNR], ru[UNR];
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(i % cv) * 8;
+    float a[8], b[8], c[8], dv[8], u[8], o[8];
+    load8(k1 + c0, a); load8(k2 + c0, b); load8(k3 + c0, c);
+    load8(dV + i * 8, dv);
+    load8(U + i * 8, u);
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const long long i = i0 + u * stride;
-      if (i < nvec) {
-        rv[u] = ldraw(dV + i * 8);
-        ru[u] = ldraw(U + i * 8);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const long long i = i0 + u * stride;
-      if (i < nvec) {
-        const int c0 = static_cast<int>(i % cv) * 8;
-        float a[8], b[8], c[8], dv[8], uu[8], o[8];
-        load8(k1 + c0, a); load8(k2 + c0, b); load8(k3 + c0, c);
-        cvt8(rv[u], dv);
-        cvt8(ru[u], uu);
-#pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-          const float2 t = fma2(make_float2(a[j], a[j + 1]), make_float2(dv[j], dv[j + 1]),
-                                fma2(make_float2(b[j], b[j + 1]), make_float2(uu[j], uu[j + 1]),
-                                     make_float2(c[j], c[j + 1])));
-          o[j] = t.x;
-          o[j + 1] = t.y;
-        }
-        store8(dU + i * 8, o);
-      }
-    }
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(a[j], dv[j], fmaf(b[j], u[j], c[j]));
+    store8(dU + i * 8, o);
   }
 }
 
