@@ -347,9 +347,9 @@ def run_ours(args):
 
 def count_launches(clips: int, C: int) -> int:
     """Kernels launched by libglf_sm100a per step (fwd+bwd, both modules + gate), counted from the orchestration in
-    glfusion_b200/csrc/glf_api.cu (memset/memcpy nodes excluded)."""
-    fwd_mod = 7          # prep_weights, proj GEMM, M GEMM, W' GEMM, U GEMM, BN stats reduce, bn_finalize
-    bwd_mod = 12         # finalize, apply, dTheta, dW', dWz, dM, dPhi, dG, dWcat, dX, 2 bias-gradient reductions
+    glfusion_b200/csrc/glf_api.cu (memset/memcpy nodes excluded); agrees with profiles/r01_v11_launches.csv (39)."""
+    fwd_mod = 6          # prep_weights, proj GEMM, M GEMM, W' GEMM, U GEMM, bn_finalize
+    bwd_mod = 11         # finalize, apply, dTheta, dW', dWz, dM, dPhi, dG, dWcat, dX, bias-gradient reduction
     pair = 2             # fused MGFM+MLFM LayerNorm forward / backward
     gate = 3             # gate_concat fwd, gate_concat bwd, gate_finish
     return 2 * (fwd_mod + bwd_mod) + pair + gate
