@@ -266,6 +266,126 @@ def tpavi_dot_closed_form(x: torch.Tensor, dz: Optional[torch.Tensor], p: Dict[s
 
 
 # --------------------------------------------------------------------------------------------------------------
+# Gram form for mode='dot' (second exact reassociation, O(N C^2) with every per-token product in channel space)
+# --------------------------------------------------------------------------------------------------------------
+def tpavi_dot_gram_form(x: torch.Tensor, dz: Optional[torch.Tensor], p: Dict[str, torch.Tensor],
+                        training: bool = True, bn_layer: bool = True):
+    """mode='dot' with theta / phi / g never materialised per token (what libglf_sm100a runs when N >> C).
+
+    With the homogeneous token  x~ = [x, 1]  and  W~ = [W | b]  (R/models/ours.py:866,878-879 are affine maps):
+        S~_b = X~_b^T X~_b                       Gram matrix of a sequence (the only token contraction, ours.py:881,902)
+        M_b  = W~phi S~_b W~g^T / N              == Phi_b^T G_b / N
+        W'_b = Wz M_b^T ;  Q~_b = W'_b W~theta   [C, C+1]
+        U_b  = X~_b Q~_b^T                       == W_z(y) without its bias (ours.py:908)
+    backward (dU = k1*dV + k2*U + k3, the BatchNorm backward, is never materialised either):
+        dQ~_b = k1*(dV_b^T X~_b) + k2*(Q~_b S~_b) + k3 (1^T X~_b)
+        ... small per-sequence products ...
+        dX_b  = dV_b (k1*Q_b) + X_b (Q_b^T k2 Q_b + dS + dS^T) + 1 e_b^T + dV_b
+    Returns (z, dx, grads, aux) like tpavi_dot_closed_form.
+    """
+    B, C = x.shape[0], x.shape[1]
+    X = x.reshape(B, C, -1).permute(0, 2, 1)                   # [B,N,C]
+    N = X.shape[1]
+    cat = lambda w, b: torch.cat([_w2d(w), b[:, None]], dim=1)
+    Wta = cat(p["theta.weight"], p["theta.bias"])              # [C',C+1]
+    Wpa = cat(p["phi.weight"], p["phi.bias"])
+    Wga = cat(p["g.weight"], p["g.bias"])
+    if bn_layer:
+        Wz, bz = _w2d(p["W_z.0.weight"]), p["W_z.0.bias"]
+    else:
+        Wz, bz = _w2d(p["W_z.weight"]), p["W_z.bias"]
+    lw, lb = p["norm_layer.weight"], p["norm_layer.bias"]
+    S = X.transpose(1, 2) @ X                                  # [B,C,C]
+    s = X.sum(1)                                               # [B,C]
+    Sa = torch.cat([torch.cat([S, s[:, :, None]], 2),
+                    torch.cat([s, torch.full((B, 1), float(N), dtype=x.dtype)], 1)[:, None, :]], 1)   # [B,C+1,C+1]
+    T = Wpa @ Sa                                               # [B,C',C+1]  (= Phi^T X~)
+    M = T @ Wga.T / N                                          # [B,C',C']
+    Wpr = Wz @ M.transpose(1, 2)                               # [B,C,C']
+    Qa = Wpr @ Wta                                             # [B,C,C+1]
+    Q, c = Qa[:, :, :C], Qa[:, :, C]
+    U = X @ Q.transpose(1, 2) + c[:, None, :]                  # without bz
+    if bn_layer:
+        if training:
+            mean = U.mean(dim=(0, 1))
+            var = U.var(dim=(0, 1), unbiased=False)
+            mean_true = mean + bz                              # what the reference's running_mean sees
+        else:
+            mean_true, var = p["W_z.1.running_mean"].to(U.dtype), p["W_z.1.running_var"].to(U.dtype)
+            mean = mean_true - bz
+        rstd = torch.rsqrt(var + BN_EPS)
+        gam, bet = p["W_z.1.weight"], p["W_z.1.bias"]
+        Uh = (U - mean) * rstd
+        V = Uh * gam + bet
+    else:
+        V = U + bz
+        mean_true = var = None
+    Zp = V + X
+    mu = Zp.mean(-1, keepdim=True)
+    r = torch.rsqrt(Zp.var(-1, unbiased=False, keepdim=True) + LN_EPS)
+    Xh = (Zp - mu) * r
+    Z = Xh * lw + lb
+    z = Z.permute(0, 2, 1).reshape(x.shape)
+    aux = {"mean": mean_true, "var": var, "M": M}
+    if dz is None:
+        return z, None, None, aux
+    dZ = dz.reshape(B, C, -1).permute(0, 2, 1)
+    grads: Dict[str, torch.Tensor] = {}
+    grads["norm_layer.weight"] = (dZ * Xh).sum((0, 1))
+    grads["norm_layer.bias"] = dZ.sum((0, 1))
+    dXh = dZ * lw
+    dV = r * (dXh - dXh.mean(-1, keepdim=True) - Xh * (dXh * Xh).mean(-1, keepdim=True))
+    n = B * N
+    if bn_layer:
+        grads["W_z.1.weight"] = (dV * Uh).sum((0, 1))
+        grads["W_z.1.bias"] = dV.sum((0, 1))
+        k1 = gam * rstd
+        if training:
+            m1 = dV.sum((0, 1)) / n
+            m2 = (dV * Uh).sum((0, 1)) / n
+            k2 = -k1 * m2 * rstd
+            k3 = -k1 * m1 + k1 * m2 * rstd * mean
+        else:
+            k2 = torch.zeros_like(k1)
+            k3 = torch.zeros_like(k1)
+    else:
+        k1 = torch.ones(C, dtype=x.dtype)
+        k2 = torch.zeros(C, dtype=x.dtype)
+        k3 = torch.zeros(C, dtype=x.dtype)
+    # column sums of dU per channel (bias gradient of W_z): sum_b (k1 rv_b + k2 colsum(U_b) + N k3)
+    R = dV.transpose(1, 2) @ X                                 # [B,C,C]
+    rv = dV.sum(1)                                             # [B,C]
+    Ra = torch.cat([R, rv[:, :, None]], 2)                     # [B,C,C+1] = dV^T X~
+    QS = Qa @ Sa                                               # [B,C,C+1] = U^T X~
+    sa = Sa[:, C, :]                                           # [B,C+1]   = 1^T X~
+    dQa = k1[None, :, None] * Ra + k2[None, :, None] * QS + k3[None, :, None] * sa[:, None, :]
+    bz_grad = dQa[:, :, C].sum(0)                              # = sum over all tokens of dU
+    grads["W_z.0.bias" if bn_layer else "W_z.bias"] = bz_grad
+    dWpr = dQa @ Wta.T                                         # [B,C,C']
+    dWta = (Wpr.transpose(1, 2) @ dQa).sum(0)                  # [C',C+1]
+    dWz = (dWpr @ M).sum(0)                                    # [C,C']
+    dM = dWpr.transpose(1, 2) @ Wz                             # [B,C',C']
+    D = dM / N
+    dWga = (D.transpose(1, 2) @ T).sum(0)
+    dT = D @ Wga                                               # [B,C',C+1]
+    dWpa = (dT @ Sa).sum(0)
+    dSa = Wpa.T @ dT                                           # [B,C+1,C+1]
+    G0 = dSa + 0.5 * (Qa.transpose(1, 2) @ (k2[None, :, None] * Qa))
+    Sym = G0 + G0.transpose(1, 2)
+    E = k1[None, :, None] * Q                                  # [B,C,C]
+    F = Sym[:, :C, :C]
+    e = Sym[:, :C, C] + (Q.transpose(1, 2) @ k3[None, :, None].expand(B, C, 1)).squeeze(-1)
+    dX = dV @ E + X @ F + e[:, None, :] + dV
+    wkey = "W_z.0.weight" if bn_layer else "W_z.weight"
+    grads[wkey] = dWz.reshape(p[wkey].shape)
+    for nm, d in (("theta", dWta), ("phi", dWpa), ("g", dWga)):
+        grads[nm + ".weight"] = d[:, :C].reshape(p[nm + ".weight"].shape)
+        grads[nm + ".bias"] = d[:, C].clone()
+    dx = dX.permute(0, 2, 1).reshape(x.shape)
+    return z, dx, grads, aux
+
+
+# --------------------------------------------------------------------------------------------------------------
 # call-site glue (R/models/ours.py:1802-1837)
 # --------------------------------------------------------------------------------------------------------------
 def gate_from_logits(cls_logits: torch.Tensor, ctr_logits: torch.Tensor, weight: float = 20.0) -> torch.Tensor:

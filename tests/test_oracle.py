@@ -66,6 +66,31 @@ def test_closed_form_dot_matches_golden(name):
         assert O.rel_err(v, ref) < 5e-5, k
 
 
+@pytest.mark.parametrize("name", ["dot_train_c128", "dot_train_c256", "dot_eval_c128", "dot_ragged_c128",
+                                  "dot_nobn_c128"])
+def test_gram_form_dot_matches_golden(name):
+    """The Gram-matrix reassociation (channel-space products only; what the CUDA path runs when N >> C) + its
+    hand-derived backward == the reference module's outputs and all 13 gradients (fp64 restatement vs fp32 golden)."""
+    g = load_golden(name)
+    B, C, T, H, W, training, bn, mode = _meta(g)
+    p = {k: (v.double() if v.is_floating_point() else v) for k, v in _params(g).items()}
+    z, dx, grads, aux = O.tpavi_dot_gram_form(g["x"].double(), g["dz"].double(), p, training=training, bn_layer=bn)
+    assert O.rel_err(z, g["z"]) < TOL
+    assert O.rel_err(dx, g["dx"]) < TOL
+    for k, v in grads.items():
+        ref = g["grad:" + k]
+        if k == "W_z.0.bias" and training:
+            assert v.abs().max() < 1e-9 * max(1.0, float(g["grad:W_z.0.weight"].abs().max()))
+            continue
+        assert O.rel_err(v, ref) < 5e-5, k
+    if bn and training:
+        n = B * T * H * W
+        rm = 0.9 * g["param:W_z.1.running_mean"].double() + 0.1 * aux["mean"]
+        rv = 0.9 * g["param:W_z.1.running_var"].double() + 0.1 * aux["var"] * n / (n - 1)
+        assert O.rel_err(rm, g["buf_after:W_z.1.running_mean"]) < TOL
+        assert O.rel_err(rv, g["buf_after:W_z.1.running_var"]) < TOL
+
+
 def test_glue_matches_golden():
     g = load_golden("glue_dot_c128")
     B, C, V, h, w = [int(v) for v in g["meta"]]
