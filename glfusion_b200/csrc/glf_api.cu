@@ -10,6 +10,9 @@
 //         BN finalise, then  Z = LN(BN(U) + X)    HBM-bound fused epilogue
 //   bwd:  LN/BN backward (two HBM-bound passes), then six tcgen05 GEMMs (dTheta, dW', dPhi, dG, dWcat, dX) and two
 //         small fp32 products (dW_z, dM).
+// When the sequences are long against the channel count (N >= 4 C) mode='dot' runs in its Gram form instead
+// (tpavi_fwd_gram / tpavi_bwd_gram below; oracle/tpavi_oracle.py: tpavi_dot_gram_form): theta / phi / g and dU are never
+// materialised, the only token-sized products are S = X^T X, U = X Q^T, R = dV^T X and dX = [dV | X] [E ; F].
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -65,6 +68,8 @@ struct Dims {
   bool pack_x;     // x must be repacked to token-major bf16
   bool pack_dz;
   bool dot;
+  bool gram;       // mode='dot' in its Gram form (channel-space products only)
+  int Ca;          // augmented width of the per-sequence matrices (gram)
 };
 
 int make_dims(const glf_desc* d, Dims* o) {
@@ -95,17 +100,51 @@ int make_dims(const glf_desc* d, Dims* o) {
     return set_error(GLF_ERR_INVALID, "token-major fp32 input too large for the cast kernel");
   o->pack_dz = d->dz_layout != GLF_LAYOUT_TOKEN;
   o->dot = d->mode == GLF_MODE_DOT;
+  // reserved[1]: 0 = choose, 1 = token-space form (theta/phi/g per token), 2 = Gram form
+  if (d->reserved[1] < 0 || d->reserved[1] > 2) return set_error(GLF_ERR_INVALID, "reserved[1] (dot algorithm) must be 0, 1 or 2");
+  const bool gram_ok = o->dot && d->precision == GLF_PRECISION_BF16 && o->B <= 65535;
+  if (d->reserved[1] == 2 && !gram_ok)
+    return set_error(GLF_ERR_UNSUPPORTED, "the Gram form needs mode='dot', GLF_PRECISION_BF16 and B <= 65535");
+  // per-sequence [C x C] products cost ~14 C^3 against 27 N C^2 saved token-space work: worth it for N >= 4 C
+  o->gram = gram_ok && (d->reserved[1] == 2 || (d->reserved[1] == 0 && o->N >= 4LL * d->C));
+  o->Ca = gram_ca(d->C);
   return 0;
 }
 
 struct Saved {
   bf16 *xtok, *P, *Y, *U, *Mb, *Wp, *wcat, *wcatT, *wz, *wzT;
   float *lse, *bcat, *bn_mean, *bn_rstd, *bn_a, *bn_b, *ln_mu, *ln_r;
+  bf16 *Sa, *T, *Qb, *waug;   // Gram form: S~ [B][Ca][Ca], T = W~phi S~ [B][Ci][Ca], Q~ [B][C][Ca], W~ [3][Ci][Ca]
+  float *sfv, *cvec;          //            s = column sums of X [B][C], c = Q~[:, :, C] [B][C]
 };
 size_t carve_saved(const Dims& m, void* base, Saved* s) {
   Carver c(base);
   const size_t rows = m.rows, C = m.C, Ci = m.Ci, B = m.B;
   s->xtok = m.pack_x ? c.take<bf16>(rows * C) : nullptr;
+  s->Sa = s->T = s->Qb = s->waug = nullptr;
+  s->sfv = s->cvec = nullptr;
+  if (m.gram) {
+    const size_t Ca = m.Ca;
+    s->P = s->Y = s->wcat = s->wcatT = s->wzT = nullptr;
+    s->lse = s->bcat = nullptr;
+    s->U = c.take<bf16>(rows * C);
+    s->Sa = c.take<bf16>(B * Ca * Ca);
+    s->T = c.take<bf16>(B * Ci * Ca);
+    s->Mb = c.take<bf16>(B * Ci * Ci);
+    s->Wp = c.take<bf16>(B * C * Ci);
+    s->Qb = c.take<bf16>(B * C * Ca);
+    s->waug = c.take<bf16>(3 * Ci * Ca);
+    s->wz = c.take<bf16>(C * Ci);
+    s->sfv = c.take<float>(B * C);
+    s->cvec = c.take<float>(B * C);
+    s->bn_mean = c.take<float>(C);
+    s->bn_rstd = c.take<float>(C);
+    s->bn_a = c.take<float>(C);
+    s->bn_b = c.take<float>(C);
+    s->ln_mu = c.take<float>(rows);
+    s->ln_r = c.take<float>(rows);
+    return (c.off + 255) & ~static_cast<size_t>(255);
+  }
   s->P = c.take<bf16>(rows * 3 * Ci);
   s->U = c.take<bf16>(rows * C);
   if (m.dot) {
@@ -131,12 +170,20 @@ size_t carve_saved(const Dims& m, void* base, Saved* s) {
   return (c.off + 255) & ~static_cast<size_t>(255);
 }
 
-struct WsFwd { float* colstats; float* red1; float* Mf; void* attn; void* saved_fallback; };
+struct WsFwd { float* colstats; float* red1; float* Mf; void* attn; void* saved_fallback; float* Sf; float* Qf; };
 size_t carve_ws_fwd(const Dims& m, void* base, WsFwd* w, size_t saved_bytes) {
   Carver c(base);
   const size_t np = 4 * (m.dot ? static_cast<size_t>(m.B) * m.tiles_seq : static_cast<size_t>(m.tiles_all));
   w->colstats = c.take<float>(np * 2 * m.C);   // one partial per (tile, 32-row quarter)
   w->red1 = c.take<float>(static_cast<size_t>(REDUCE_STAGE1_ROWS) * 2 * m.C);
+  w->Sf = w->Qf = nullptr;
+  if (m.gram) {
+    w->Mf = nullptr; w->attn = nullptr;
+    w->Sf = c.take<float>(static_cast<size_t>(m.B) * m.C * m.C);
+    w->Qf = c.take<float>(static_cast<size_t>(m.B) * m.C * m.Ca);
+    w->saved_fallback = c.take<uint8_t>(saved_bytes);
+    return (c.off + 255) & ~static_cast<size_t>(255);
+  }
   w->Mf = m.dot ? c.take<float>(static_cast<size_t>(m.B) * m.Ci * m.Ci) : nullptr;  // split-K accumulation target
   w->attn = m.dot ? nullptr : c.take<uint8_t>(attn_scratch_bytes(m.B, m.N, false));
   w->saved_fallback = c.take<uint8_t>(saved_bytes);  // used when the caller passes saved == NULL (inference)
@@ -147,12 +194,41 @@ struct WsBwd {
   bf16 *dztok, *dV, *dU, *dP, *dY, *dxtok, *dM, *dWpb;
   float *dWpf, *part_ln, *k1, *k2, *k3, *cs_t, *cs_p, *cs_g, *red1, *dwcat, *delta;
   void* attn;
+  // Gram form
+  float *Rf, *rv, *QSf, *G0, *evec, *dwaug;
+  bf16 *dQa, *Qk, *dT, *EF;
 };
 size_t carve_ws_bwd(const glf_desc* d, const Dims& m, void* base, WsBwd* w) {
   Carver c(base);
   const size_t rows = m.rows, C = m.C, Ci = m.Ci, B = m.B;
   w->dztok = m.pack_dz ? c.take<bf16>(rows * C) : nullptr;
   w->dV = c.take<bf16>(rows * C);
+  w->Rf = w->rv = w->QSf = w->G0 = w->evec = w->dwaug = nullptr;
+  w->dQa = w->Qk = w->dT = w->EF = nullptr;
+  if (m.gram) {
+    const size_t Ca = m.Ca;
+    w->dU = w->dP = w->dY = nullptr;
+    w->dWpf = w->cs_t = w->cs_p = w->cs_g = w->red1 = w->dwcat = w->delta = nullptr;
+    w->attn = nullptr;
+    w->dxtok = m.pack_x ? c.take<bf16>(rows * C) : nullptr;
+    w->part_ln = c.take<float>(static_cast<size_t>(bn_res_ln_bwd_blocks(m.rows, m.C)) * 4 * C);
+    w->k1 = c.take<float>(C);
+    w->k2 = c.take<float>(C);
+    w->k3 = c.take<float>(C);
+    w->Rf = c.take<float>(B * C * C);
+    w->rv = c.take<float>(B * C);
+    w->QSf = c.take<float>(B * C * Ca);
+    w->dQa = c.take<bf16>(B * C * Ca);
+    w->Qk = c.take<bf16>(B * C * Ca);
+    w->dWpb = c.take<bf16>(B * C * Ci);
+    w->dM = c.take<bf16>(B * Ci * Ci);
+    w->dT = c.take<bf16>(B * Ci * Ca);
+    w->G0 = c.take<float>(B * Ca * Ca);
+    w->EF = c.take<bf16>(B * 2 * C * C);
+    w->evec = c.take<float>(B * C);
+    w->dwaug = c.take<float>(3 * Ci * Ca);
+    return (c.off + 255) & ~static_cast<size_t>(255);
+  }
   w->dU = d->bn_layer ? c.take<bf16>(rows * C) : nullptr;
   w->dP = c.take<bf16>(rows * 3 * Ci);
   w->dxtok = m.pack_x ? c.take<bf16>(rows * C) : nullptr;
@@ -218,6 +294,275 @@ int check_ptr(const void* p, const char* name) {
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------ Gram form of 'dot'
+// Token-sized products of a sequence contraction S = A^T X (A = X or dV): both operands MN-major views of token-major
+// activations, fp32 result [B][C][C], the column sums of A as the GEMM's row-sum side product.
+int gram_token_contraction(const bf16* A, const bf16* X, float* Sf, float* rowsum, int B, int N, int C,
+                           cudaStream_t stream) {
+  GemmArgs g;
+  g.A = opnd(A, 1, C, static_cast<long long>(N) * C);
+  g.B = opnd(X, 1, C, static_cast<long long>(N) * C);
+  g.M = C; g.N = C; g.K = N; g.batch = B;
+  g.bn_hint = 128;
+  g.ldd = C; g.strideD = static_cast<long long>(C) * C;
+  g.D = Sf;
+  g.rowsum = rowsum; g.rowsum_stride = C;
+  g.split_k = pick_split(static_cast<long long>(B) * ((C + 127) / 128) * ((C + 127) / 128), N);
+  if (g.split_k > 1) {
+    GLF_TRY(check_cuda(cudaMemsetAsync(Sf, 0, sizeof(float) * B * C * C, stream), "memset S"));
+    GLF_TRY(check_cuda(cudaMemsetAsync(rowsum, 0, sizeof(float) * B * C, stream), "memset s"));
+    g.out_kind = 2;
+  } else {
+    g.out_kind = 1;
+  }
+  return gemm(g, stream);
+}
+
+int tpavi_fwd_gram(const glf_desc* d, const Dims& m, const void* x, const glf_weights* w, void* z, const Saved& s,
+                   const WsFwd& wf, cudaStream_t stream) {
+  const int C = m.C, Ci = m.Ci, Ca = m.Ca, C1 = m.C + 1;
+  const int N = static_cast<int>(m.N), B = static_cast<int>(m.B);
+  const long long CaCa = static_cast<long long>(Ca) * Ca, CiCa = static_cast<long long>(Ci) * Ca;
+  const long long CCa = static_cast<long long>(C) * Ca, CiCi = static_cast<long long>(Ci) * Ci;
+  const long long CCi = static_cast<long long>(C) * Ci;
+  GLF_TRY(gram_prep_weights(w, C, Ci, Ca, s.waug, s.wz, stream));
+  const bf16* X = reinterpret_cast<const bf16*>(x);
+  if (m.pack_x) {
+    if (d->x_layout == GLF_LAYOUT_NCTHW)
+      GLF_TRY(transpose_cast(x, s.xtok, B, C, N, d->io_dtype, GLF_DTYPE_BF16, stream));
+    else
+      GLF_TRY(transpose_cast(x, s.xtok, 1, 1, static_cast<int>(m.rows * C), d->io_dtype, GLF_DTYPE_BF16, stream));
+    X = s.xtok;
+  }
+  // S_b = X_b^T X_b, s_b = X_b^T 1   ->   S~_b
+  GLF_TRY(gram_token_contraction(X, X, wf.Sf, s.sfv, B, N, C, stream));
+  GLF_TRY(gram_assemble_S(wf.Sf, s.sfv, s.Sa, B, C, Ca, static_cast<float>(N), stream));
+  {  // T_b = W~phi S~_b                      [Ci x Ca]   (= Phi_b^T X~_b; S~ is symmetric)
+    GemmArgs g;
+    g.A = opnd(s.waug + CiCa, 0, Ca, 0);
+    g.B = opnd(s.Sa, 0, Ca, CaCa);
+    g.B.rows = C1;
+    g.M = Ci; g.N = Ca; g.K = C1; g.batch = B;
+    g.D = s.T; g.ldd = Ca; g.strideD = CiCa;
+    GLF_TRY(gemm(g, stream));
+  }
+  {  // M_b = T_b W~g^T / N                   [Ci x Ci]   (= Phi_b^T G_b / N)
+    GemmArgs g;
+    g.A = opnd(s.T, 0, Ca, CiCa);
+    g.B = opnd(s.waug + 2 * CiCa, 0, Ca, 0);
+    g.M = Ci; g.N = Ci; g.K = C1; g.batch = B;
+    g.alpha = 1.f / static_cast<float>(N);
+    g.D = s.Mb; g.ldd = Ci; g.strideD = CiCi;
+    GLF_TRY(gemm(g, stream));
+  }
+  {  // W'_b = Wz M_b^T                       [C x Ci]
+    GemmArgs g;
+    g.A = opnd(s.wz, 0, Ci, 0);
+    g.B = opnd(s.Mb, 0, Ci, CiCi);
+    g.M = C; g.N = Ci; g.K = Ci; g.batch = B;
+    g.D = s.Wp; g.ldd = Ci; g.strideD = CCi;
+    GLF_TRY(gemm(g, stream));
+  }
+  {  // Q~_b = W'_b W~theta                   [C x Ca]    (B operand = W~theta read MN-major: stored [K = i][rows = a])
+    GemmArgs g;
+    g.A = opnd(s.Wp, 0, Ci, CCi);
+    g.B = opnd(s.waug, 1, Ca, 0);
+    g.B.rows = C1;
+    g.M = C; g.N = Ca; g.K = Ci; g.batch = B;
+    g.out_kind = 1;
+    g.D = wf.Qf; g.ldd = Ca; g.strideD = CCa;
+    GLF_TRY(gemm(g, stream));
+  }
+  GLF_TRY(gram_convert_Q(wf.Qf, s.Qb, s.cvec, B, C, Ca, stream));
+  int np = 0;
+  {  // U_b = X_b Q_b^T + c_b   (+ BatchNorm column statistics); bz stays folded into the BN affine
+    GemmArgs g;
+    g.A = opnd(X, 0, C, static_cast<long long>(N) * C);
+    g.B = opnd(s.Qb, 0, Ca, CCa);
+    g.M = N; g.N = C; g.K = C; g.batch = B;
+    g.bias = s.cvec; g.bias_stride = C;
+    g.D = s.U; g.ldd = C; g.strideD = static_cast<long long>(N) * C;
+    g.colstats = (d->training && d->bn_layer) ? wf.colstats : nullptr;
+    g.colstats_rows = &np;
+    GLF_TRY(gemm(g, stream));
+  }
+  const float* bn_part = wf.colstats;
+  if (d->training && d->bn_layer && np > 4 * REDUCE_STAGE1_ROWS) {
+    long long rs = 2LL * C;
+    const int np_in[1] = {np};
+    GLF_TRY(reduce_stage1(wf.colstats, nullptr, nullptr, 1, np_in, &np, &rs, C, 2, C, wf.red1, stream));
+    bn_part = wf.red1;
+  }
+  GLF_TRY(bn_finalize(bn_part, np, C, static_cast<double>(m.rows), d, w, w->wz_b, s.bn_mean, s.bn_rstd, s.bn_a, s.bn_b,
+                      stream));
+  if (defer_ln(d)) return 0;
+  GLF_TRY(bn_res_ln_fwd(s.U, X, GLF_DTYPE_BF16, s.bn_a, s.bn_b, w->ln_w, w->ln_b, z, d->io_dtype, s.ln_mu, s.ln_r,
+                        m.rows, C, d->eps_ln, d->accumulate, stream));
+  return 0;
+}
+
+// Continues after the LayerNorm backward and bn_bwd_finalize: wb.dV, wb.k1..k3 are valid.
+int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved& s, const WsBwd& wb, void* dx,
+                   const glf_grads* g_, cudaStream_t stream) {
+  const int C = m.C, Ci = m.Ci, Ca = m.Ca, C1 = m.C + 1;
+  const int N = static_cast<int>(m.N), B = static_cast<int>(m.B);
+  const long long CaCa = static_cast<long long>(Ca) * Ca, CiCa = static_cast<long long>(Ci) * Ca;
+  const long long CCa = static_cast<long long>(C) * Ca, CiCi = static_cast<long long>(Ci) * Ci;
+  const long long CCi = static_cast<long long>(C) * Ci, CC = static_cast<long long>(C) * C;
+  const float invN = 1.f / static_cast<float>(N);
+  const bool bn_train = d->bn_layer && d->training;   // k2, k3 != 0 only then
+  // R_b = dV_b^T X_b, rv_b = dV_b^T 1
+  GLF_TRY(gram_token_contraction(wb.dV, X, wb.Rf, wb.rv, B, N, C, stream));
+  if (bn_train) {  // (U^T X~)_b = Q~_b S~_b   [C x Ca]
+    GemmArgs g;
+    g.A = opnd(s.Qb, 0, Ca, CCa);
+    g.B = opnd(s.Sa, 0, Ca, CaCa);
+    g.B.rows = C1;
+    g.M = C; g.N = Ca; g.K = C1; g.batch = B;
+    g.out_kind = 1;
+    g.D = wb.QSf; g.ldd = Ca; g.strideD = CCa;
+    GLF_TRY(gemm(g, stream));
+  }
+  // dQ~ = k1 [R | rv] + k2 Q~S~ + k3 [s | N] ;  Qk = k2 Q~ ;  E = k1 Q
+  GLF_TRY(gram_combine_dQ(wb.Rf, wb.rv, bn_train ? wb.QSf : nullptr, s.sfv, s.Qb, wb.k1, wb.k2, wb.k3, wb.dQa, wb.Qk,
+                          wb.EF, B, C, Ca, static_cast<float>(N), stream));
+  {  // dW'_b = dQ~_b W~theta^T               [C x Ci]
+    GemmArgs g;
+    g.A = opnd(wb.dQa, 0, Ca, CCa);
+    g.B = opnd(s.waug, 0, Ca, 0);
+    g.M = C; g.N = Ci; g.K = C1; g.batch = B;
+    g.D = wb.dWpb; g.ldd = Ci; g.strideD = CCi;
+    GLF_TRY(gemm(g, stream));
+  }
+  GLF_TRY(check_cuda(cudaMemsetAsync(wb.dwaug, 0, sizeof(float) * 3 * CiCa, stream), "memset dW~"));
+  {  // dW~theta = sum_b W'_b^T dQ~_b         [Ci x Ca]   (batch reduced by fp32 red.add)
+    GemmArgs g;
+    g.A = opnd(s.Wp, 1, Ci, CCi);
+    g.B = opnd(wb.dQa, 1, Ca, CCa);
+    g.B.rows = C1;
+    g.M = Ci; g.N = Ca; g.K = C; g.batch = B;
+    g.out_kind = 2;
+    g.D = wb.dwaug; g.ldd = Ca; g.strideD = 0;
+    GLF_TRY(gemm(g, stream));
+  }
+  GLF_TRY(check_cuda(cudaMemsetAsync(g_->wz_w, 0, sizeof(float) * CCi, stream), "memset dWz"));
+  {  // dWz = sum_b dW'_b M_b
+    GemmArgs g;
+    g.A = opnd(wb.dWpb, 0, Ci, CCi);
+    g.B = opnd(s.Mb, 1, Ci, CiCi);
+    g.M = C; g.N = Ci; g.K = Ci; g.batch = B;
+    g.out_kind = 2;
+    g.D = g_->wz_w; g.ldd = Ci; g.strideD = 0;
+    GLF_TRY(gemm(g, stream));
+  }
+  {  // dM_b = dW'_b^T Wz                     [Ci x Ci]
+    GemmArgs g;
+    g.A = opnd(wb.dWpb, 1, Ci, CCi);
+    g.B = opnd(s.wz, 1, Ci, 0);
+    g.M = Ci; g.N = Ci; g.K = C; g.batch = B;
+    g.D = wb.dM; g.ldd = Ci; g.strideD = CiCi;
+    GLF_TRY(gemm(g, stream));
+  }
+  {  // dW~g = sum_b (dM_b / N)^T T_b         [Ci x Ca]
+    GemmArgs g;
+    g.A = opnd(wb.dM, 1, Ci, CiCi);
+    g.B = opnd(s.T, 1, Ca, CiCa);
+    g.B.rows = C1;
+    g.M = Ci; g.N = Ca; g.K = Ci; g.batch = B;
+    g.alpha = invN;
+    g.out_kind = 2;
+    g.D = wb.dwaug + 2 * CiCa; g.ldd = Ca; g.strideD = 0;
+    GLF_TRY(gemm(g, stream));
+  }
+  {  // dT_b = (dM_b / N) W~g                 [Ci x Ca]
+    GemmArgs g;
+    g.A = opnd(wb.dM, 0, Ci, CiCi);
+    g.B = opnd(s.waug + 2 * CiCa, 1, Ca, 0);
+    g.B.rows = C1;
+    g.M = Ci; g.N = Ca; g.K = Ci; g.batch = B;
+    g.alpha = invN;
+    g.D = wb.dT; g.ldd = Ca; g.strideD = CiCa;
+    GLF_TRY(gemm(g, stream));
+  }
+  {  // dW~phi = sum_b dT_b S~_b              [Ci x Ca]
+    GemmArgs g;
+    g.A = opnd(wb.dT, 0, Ca, CiCa);
+    g.B = opnd(s.Sa, 0, Ca, CaCa);
+    g.B.rows = C1;
+    g.M = Ci; g.N = Ca; g.K = C1; g.batch = B;
+    g.out_kind = 2;
+    g.D = wb.dwaug + CiCa; g.ldd = Ca; g.strideD = 0;
+    GLF_TRY(gemm(g, stream));
+  }
+  {  // G0_b = dS~_b = W~phi^T dT_b           [C1 x Ca]
+    GemmArgs g;
+    g.A = opnd(s.waug + CiCa, 1, Ca, 0);
+    g.A.rows = C1;
+    g.B = opnd(wb.dT, 1, Ca, CiCa);
+    g.B.rows = C1;
+    g.M = C1; g.N = Ca; g.K = Ci; g.batch = B;
+    g.out_kind = 1;
+    g.D = wb.G0; g.ldd = Ca; g.strideD = CaCa;
+    GLF_TRY(gemm(g, stream));
+  }
+  if (bn_train) {  // G0_b += Q~_b^T (k2 Q~_b) / 2   (one add per element: deterministic)
+    GemmArgs g;
+    g.A = opnd(s.Qb, 1, Ca, CCa);
+    g.A.rows = C1;
+    g.B = opnd(wb.Qk, 1, Ca, CCa);
+    g.B.rows = C1;
+    g.M = C1; g.N = Ca; g.K = C; g.batch = B;
+    g.alpha = 0.5f;
+    g.out_kind = 2;
+    g.D = wb.G0; g.ldd = Ca; g.strideD = CaCa;
+    GLF_TRY(gemm(g, stream));
+  }
+  // F = (G0 + G0^T)[:C, :C] ;  e = (G0 + G0^T)[:C, C] + Q^T k3
+  GLF_TRY(gram_assemble_F(wb.G0, s.Qb, wb.k3, bn_train ? 1 : 0, wb.EF, wb.evec, B, C, Ca, stream));
+  {  // dX_b = dV_b E_b + X_b F_b + 1 e_b^T + dV_b : both products accumulate into one tile (the two A operands are
+     // two "limbs" of one tensor map, their distance in memory is the limb stride)
+    void* D = m.pack_x ? static_cast<void*>(wb.dxtok) : dx;
+    const bf16* dV = wb.dV;
+    const long long diff = X - dV;   // elements
+    const long long ad = diff < 0 ? -diff : diff;
+    const bool one_launch = ad != 0 && ad % 8 == 0 && ad < (1LL << 38);
+    GemmArgs g;
+    g.B = opnd(wb.EF, 1, C, 2 * CC);
+    g.B.limb_stride = CC;
+    g.M = N; g.N = C; g.K = C; g.batch = B;
+    g.bias = wb.evec; g.bias_stride = C;
+    g.addend = dV; g.ld_add = C; g.stride_add = static_cast<long long>(N) * C;
+    g.D = D; g.ldd = C; g.strideD = static_cast<long long>(N) * C;
+    if (one_launch) {
+      g.A = opnd(diff > 0 ? dV : X, 0, C, static_cast<long long>(N) * C);
+      g.A.limb_stride = ad;
+      g.npairs = 2;
+      g.pairA[0] = diff > 0 ? 0 : 1; g.pairB[0] = 0;   // dV x E
+      g.pairA[1] = diff > 0 ? 1 : 0; g.pairB[1] = 1;   // X  x F
+      GLF_TRY(gemm(g, stream));
+    } else {
+      // operands too far apart for one tensor map: two passes, the second adds onto the first in place
+      g.A = opnd(dV, 0, C, static_cast<long long>(N) * C);
+      g.bias = nullptr;
+      GLF_TRY(gemm(g, stream));
+      g.A = opnd(X, 0, C, static_cast<long long>(N) * C);
+      g.B = opnd(wb.EF + CC, 1, C, 2 * CC);
+      g.bias = wb.evec;
+      g.addend = reinterpret_cast<const bf16*>(D);
+      GLF_TRY(gemm(g, stream));
+    }
+  }
+  GLF_TRY(gram_unpack_grads(wb.dwaug, g_, C, Ci, Ca, stream));
+  if (m.pack_x) {
+    if (d->x_layout == GLF_LAYOUT_NCTHW)
+      GLF_TRY(transpose_cast(wb.dxtok, dx, B, N, C, GLF_DTYPE_BF16, d->io_dtype, stream));
+    else
+      GLF_TRY(transpose_cast(wb.dxtok, dx, 1, 1, static_cast<int>(m.rows * C), GLF_DTYPE_BF16, d->io_dtype, stream));
+  }
+  return 0;
+}
+
 }  // namespace
 }  // namespace glf
 
@@ -257,6 +602,7 @@ GLF_API int glf_tpavi_fwd(const glf_desc* d, const void* x, const glf_weights* w
   const size_t saved_bytes = carve_saved(m, nullptr, &s);
   carve_ws_fwd(m, ws, &wf, saved_bytes);
   carve_saved(m, saved ? saved : wf.saved_fallback, &s);
+  if (m.gram) return tpavi_fwd_gram(d, m, x, w, z, s, wf, stream);
   const int C = m.C, Ci = m.Ci;
   const int N = static_cast<int>(m.N), rows = static_cast<int>(m.rows), B = static_cast<int>(m.B);
 
@@ -386,6 +732,7 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
   }
   GLF_TRY(bn_bwd_finalize(wb.part_ln, nb, C, static_cast<double>(m.rows), d, w, s.bn_mean, s.bn_rstd, g_, wb.k1, wb.k2,
                           wb.k3, stream));
+  if (m.gram) return tpavi_bwd_gram(d, m, X, s, wb, dx, g_, stream);
   const bf16* dU = wb.dV;
   if (d->bn_layer) {
     GLF_TRY(bn_bwd_apply(wb.dV, s.U, GLF_DTYPE_BF16, wb.k1, wb.k2, wb.k3, wb.dU, m.rows, C, stream));
@@ -662,6 +1009,26 @@ GLF_API int glf_gemm_bf16(const void* A, const void* B, void* D, int M, int N, i
   g.addend = reinterpret_cast<const bf16*>(addend); g.ld_add = ld_add; g.stride_add = stride_add;
   g.colstats = colstats;
   g.split_k = split_k;
+  return gemm(g, reinterpret_cast<cudaStream_t>(stream));
+}
+
+GLF_API int glf_gemm_bf16_ex(const void* A, const void* B, void* D, int M, int N, int K, int batch, int a_mn, int b_mn,
+                     int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
+                     const float* bias, int64_t bias_stride, float alpha, int out_kind, int split_k, float* rowsum,
+                     glf_stream_t stream) {
+  GLF_TRY(check_device_sm100());
+  GLF_TRY(check_ptr(A, "A"));
+  GLF_TRY(check_ptr(B, "B"));
+  GLF_TRY(check_ptr(D, "D"));
+  GemmArgs g;
+  g.A = opnd(A, a_mn, lda, strideA);
+  g.B = opnd(B, b_mn, ldb, strideB);
+  g.M = M; g.N = N; g.K = K; g.batch = batch;
+  g.alpha = alpha; g.bias = bias; g.bias_stride = bias_stride;
+  g.out_kind = out_kind;
+  g.D = D; g.ldd = ldd; g.strideD = strideD;
+  g.split_k = split_k;
+  g.rowsum = rowsum; g.rowsum_stride = M;
   return gemm(g, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -50,6 +50,9 @@ struct GemmKParams {
   int tiles_m, tiles_n;
   int step_n, step_m, step_z;    // (n-tile, m-tile, batch*split) advance per persistent-loop step of gridDim.x tiles
   int tma_store;                 // 1: bf16 output tiles leave through cp.async.bulk.tensor stores (tmD), no addend
+  long long bias_stride;         // elements between the bias vectors of consecutive batch entries (0 = shared)
+  float* rowsum;                 // optional [batch][M] fp32: sum over K of the A operand's row (BN <= 128, npairs == 1)
+  long long rowsum_stride;
 };
 
 template <int BN>
@@ -64,8 +67,14 @@ struct GemmCfg {
   static constexpr uint32_t WARP_BIAS = 32 * 4;     // warp-private bias slice of the current 32-column chunk
   static constexpr uint32_t BIAS_ALL = 4096 * 4;   // the whole bias vector (N <= 4096) is staged once per CTA
   static constexpr uint32_t EPI_BYTES = EPI_WARPS * (WARP_STG + WARP_BIAS) + BIAS_ALL;
-  static constexpr uint32_t SMEM_BYTES = RING_BYTES + EPI_BYTES + 1024;
-  static constexpr uint32_t TMEM_COLS = 2 * BN;     // two accumulator stages
+  // all-ones K-major B tile [16 rows][64 k] for the row-sum side product (RING_BYTES and EPI_BYTES are multiples of
+  // 1024, so it sits on a swizzle-atom boundary)
+  static constexpr uint32_t ONES_BYTES = 2048;
+  static constexpr uint32_t SMEM_BYTES = RING_BYTES + EPI_BYTES + ONES_BYTES + 1024;
+  // two accumulator stages (+ two 16-column row-sum accumulators at column 2 BN when BN <= 128)
+  static constexpr uint32_t TMEM_COLS = (BN == 64) ? 256 : 512;
+  static constexpr uint32_t RS_COL = 2 * BN;
+  static_assert(EPI_BYTES % 1024 == 0 && RING_BYTES % 1024 == 0, "ones tile alignment");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(TMEM_COLS <= 512, "TMEM budget");
 };
@@ -123,6 +132,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_holder), Cfg::TMEM_COLS);
+  const uint32_t ones_smem = smem_base + Cfg::RING_BYTES + Cfg::EPI_BYTES;
+  if (p.rowsum != nullptr) {
+    // bf16 1.0 everywhere: the swizzle pattern is irrelevant for a constant tile
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem_gen + Cfg::RING_BYTES + Cfg::EPI_BYTES);
+    for (int i = threadIdx.x; i < static_cast<int>(Cfg::ONES_BYTES / 4); i += GEMM_THREADS) ones[i] = 0x3F803F80u;
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -174,13 +190,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     // ------------------------------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      constexpr uint32_t idesc_rs = make_idesc_bf16(BM, 16, A_MN, false);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-        int z, mn, b, split;
+        int z, mn, b, split, mt_, nt_;
         fastdivmod(tile, tiles_mn, p.mg_mn, z, mn);
         fastdivmod(z, p.split_k, p.mg_sk, b, split);
+        fastdivmod(mn, p.tiles_n, p.mg_n, mt_, nt_);
+        const bool rs = BN <= 128 && p.rowsum != nullptr && nt_ == 0;   // row sums ride along with the first n-tile
         const int kb0 = split * p.kb_per_split;
         const int niter = (min(p.kb_total, kb0 + p.kb_per_split) - kb0) * p.npairs;
         const int acc = local & 1;
@@ -198,6 +217,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             const uint64_t ad = A_MN ? make_sdesc(sa + k * 2048, 8192, 1024) : make_sdesc(sa + k * 32, 16, 1024);
             const uint64_t bd = B_MN ? make_sdesc(sb + k * 2048, 8192, 1024) : make_sdesc(sb + k * 32, 16, 1024);
             umma_f16(tacc, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          if (rs) {
+            // A x ones^T into a 16-column side accumulator: every column = sum over K of the A row
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t ad = A_MN ? make_sdesc(sa + k * 2048, 8192, 1024) : make_sdesc(sa + k * 32, 16, 1024);
+              umma_f16(tmem_base + Cfg::RS_COL + acc * 16, ad, make_sdesc(ones_smem + k * 32, 16, 1024), idesc_rs,
+                       (it | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(smem_u32(&empty_bar[stage]));  // slot reusable once these MMAs have read it
           if (++stage == STAGES) {
@@ -223,7 +251,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const int sw_w = (lane >> 1) & 3;          // swizzle of the row this lane WRITES (row = lane)
     // the whole bias vector goes to shared memory once (epilogue warps only; named barrier 1)
     float* ball = reinterpret_cast<float*>(epi_smem + EPI_WARPS * (Cfg::WARP_STG + Cfg::WARP_BIAS));
-    const bool bias_all = p.bias != nullptr && p.N <= 4096;
+    const bool bias_all = p.bias != nullptr && p.N <= 4096 && p.bias_stride == 0;
     if (bias_all) {
       for (int i = ew * 32 + lane; i < p.N; i += EPI_THREADS) ball[i] = p.bias[i];
       named_bar_sync(1, EPI_THREADS);
@@ -253,16 +281,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const int grow = m0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
       const bool use_bias = p.bias != nullptr && split == 0;
+      const float* biasb = p.bias != nullptr ? p.bias + static_cast<long long>(b) * p.bias_stride : nullptr;
       const int rows_valid = min(32, p.M - (m0 + q * 32));   // valid rows of this warp's sub-block (may be <= 0)
       mbar_wait(smem_u32(&tmem_full_bar[acc]), use & 1u);
       tc_fence_after();
+      if (BN <= 128 && p.rowsum != nullptr && nt == 0 && cc0 == 0) {
+        // side accumulator of the row sums (one warp per 32-row quarter); read before this warp's accumulator release
+        uint32_t rv[32];
+        tmem_ld_32x32(tmem_base + Cfg::RS_COL + acc * 16 + (static_cast<uint32_t>(q * 32) << 16), rv);
+        tmem_ld_wait();
+        if (grow < p.M) {
+          float* dst = p.rowsum + static_cast<long long>(b) * p.rowsum_stride + grow;
+          if (p.split_k > 1) atomicAdd(dst, __uint_as_float(rv[0]));
+          else *dst = __uint_as_float(rv[0]);
+        }
+      }
 #pragma unroll 1
       for (int c = cc0; c < NCHUNK; c += 4) {
         const int gc0 = n0 + c * 32;           // first global column of this chunk
         const bool full = rows_valid >= 32 && gc0 + 32 <= p.N;
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
-        if (use_bias && !bias_all) wbias[lane] = (gc0 + lane < p.N) ? p.bias[gc0 + lane] : 0.f;
+        if (use_bias && !bias_all) wbias[lane] = (gc0 + lane < p.N) ? biasb[gc0 + lane] : 0.f;
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -591,6 +631,7 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
   if (a.ldd % 8 != 0 || (reinterpret_cast<uintptr_t>(a.D) & 15) != 0)
     return set_error(GLF_ERR_INVALID, "gemm: output must be 16-byte aligned with ldd %% 8 == 0");
   if (a.npairs < 1 || a.npairs > 6) return set_error(GLF_ERR_INVALID, "gemm: npairs out of range");
+  if (a.rowsum != nullptr && a.npairs != 1) return set_error(GLF_ERR_INVALID, "gemm: rowsum needs a single operand pair");
 
   // Small-K products are HBM-bound: 128-wide tiles keep 2 CTAs per SM so one CTA's epilogue overlaps the other's
   // loads.  Large-K (tensor-bound, e.g. C=2048) products take the 128x256 tile.
@@ -600,6 +641,7 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
     const int v = atoi(e);
     if ((v == 128 || v == 256) && a.N > 64 && !a.A.mn_major) BN = v;
   }
+  if (a.rowsum != nullptr && BN > 128) BN = 128;   // the side accumulator needs TMEM columns beyond the two stages
   int nlimbsA = 1, nlimbsB = 1;
   for (int i = 0; i < a.npairs; ++i) {
     nlimbsA = a.pairA[i] + 1 > nlimbsA ? a.pairA[i] + 1 : nlimbsA;
@@ -638,6 +680,9 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
   p.D = a.D; p.ldd = a.ldd; p.strideD = a.strideD;
   p.addend = a.addend; p.ld_add = a.ld_add; p.stride_add = a.stride_add;
   p.colstats = a.colstats;
+  p.bias_stride = a.bias != nullptr ? a.bias_stride : 0;
+  p.rowsum = a.rowsum;
+  p.rowsum_stride = a.rowsum_stride;
   p.cs_accum = 0;
   p.tiles_m = gemm_tiles_m(a.M);
   p.tiles_n = 0;  // set per tile shape in launch()

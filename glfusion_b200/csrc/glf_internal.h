@@ -30,6 +30,9 @@ struct GemmArgs {
   int M = 0, N = 0, K = 0, batch = 1;
   float alpha = 1.f;
   const float* bias = nullptr;      // [N]
+  int64_t bias_stride = 0;          // elements between the bias vectors of consecutive batch entries (0 = shared)
+  float* rowsum = nullptr;          // optional [batch][M] fp32: sum over K of A's rows (tile N <= 128, npairs == 1);
+  int64_t rowsum_stride = 0;        //   stored, or atomically added when split_k > 1 (caller zeroes it then)
   int out_kind = 0;                 // 0 bf16 store, 1 f32 store, 2 f32 atomic add
   void* D = nullptr;
   int64_t ldd = 0, strideD = 0;
@@ -92,6 +95,19 @@ int reduce_partials(const float* part, int np, long long stride, int n, float al
 int reduce_partials3(const float* p0, const float* p1, const float* p2, int np, long long stride, int n, float* o0,
                      float* o1, float* o2, cudaStream_t stream);
 int cast_bf16(const float* in, bf16* out, long long n, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------ Gram form (glf_gram.cu)
+// Augmented width of the per-sequence matrices: column C is the homogeneous coordinate, the rest zero padding.
+inline int gram_ca(int C) { return C + 8; }
+int gram_prep_weights(const glf_weights* w, int C, int Ci, int Ca, bf16* waug, bf16* wzb, cudaStream_t stream);
+int gram_assemble_S(const float* Sf, const float* sf, bf16* Sa, int B, int C, int Ca, float ntok, cudaStream_t stream);
+int gram_convert_Q(const float* Qf, bf16* Qb, float* cvec, int B, int C, int Ca, cudaStream_t stream);
+int gram_combine_dQ(const float* Rf, const float* rv, const float* QSf, const float* sf, const bf16* Qb, const float* k1,
+                    const float* k2, const float* k3, bf16* dQa, bf16* Qk, bf16* EF, int B, int C, int Ca, float ntok,
+                    cudaStream_t stream);
+int gram_assemble_F(const float* G0, const bf16* Qb, const float* k3, int use_k3, bf16* EF, float* evec, int B, int C,
+                    int Ca, cudaStream_t stream);
+int gram_unpack_grads(const float* dwaug, const glf_grads* g, int C, int Ci, int Ca, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------ gate + concat
 int gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, int x_dtype,

@@ -14,6 +14,8 @@ sm_100 GPU every call raises.
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from typing import Optional, Tuple
 
@@ -57,6 +59,11 @@ def _blob(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+# Algorithm for mode='dot' (glf_desc.reserved[1]): 0 = the library chooses (Gram form when N >= 4 C), 1 = token-space
+# form (theta/phi/g per token), 2 = Gram form (channel-space products only).  Tests pin it; users leave it alone.
+DOT_ALGO = int(os.environ.get("GLF_DOT_ALGO", "0"))
+
+
 class TPAVIState:
     """Everything one forward/backward pair shares: descriptor, weights table, saved blob."""
 
@@ -74,6 +81,7 @@ class TPAVIState:
         d.accumulate = int(accumulate)
         d.eps_bn, d.eps_ln, d.momentum = eps_bn, eps_ln, momentum
         d.reserved[0] = 1 if defer_ln else 0     # LayerNorm stage run for MGFM + MLFM together (glf_fusion_ln_*)
+        d.reserved[1] = DOT_ALGO                 # 0 = library chooses, 1 = token-space form, 2 = Gram form
         self.desc = d
         sz = L.GlfSizes()
         L.check(L.load().glf_tpavi_sizes(C.byref(d), C.byref(sz)))

@@ -65,7 +65,11 @@ typedef struct glf_desc {
   float eps_bn, eps_ln, momentum;
   int32_t reserved[4]; /* reserved[0] = 1: "deferred LayerNorm" — glf_tpavi_fwd stops after the BatchNorm statistics and
                           glf_tpavi_bwd starts after the LayerNorm backward; the caller runs that stage for MGFM and
-                          MLFM together with glf_fusion_ln_fwd / glf_fusion_ln_bwd (below).  Others: 0. */
+                          MLFM together with glf_fusion_ln_fwd / glf_fusion_ln_bwd (below).
+                          reserved[1]: algorithm of mode='dot' (both are exact reassociations of ours.py:881-902):
+                          0 = the library chooses (Gram form when N >= 4 C), 1 = token-space form (theta/phi/g formed
+                          per token), 2 = Gram form (S = X~^T X~ per sequence, channel-space products only).
+                          Others: 0. */
 } glf_desc;
 
 /* fp32 master parameters, same shapes as the reference state_dict. */
@@ -167,6 +171,15 @@ GLF_API int glf_gemm_bf16(const void* A, const void* B, void* D, int M, int N, i
                   int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
                   const float* bias, float alpha, const void* addend, int64_t ld_add, int64_t stride_add,
                   int out_kind, int split_k, float* colstats, glf_stream_t stream);
+
+/* Same product with the two extras the Gram form of mode='dot' uses (unit tests):
+ *   bias_stride : elements between the bias vectors of consecutive batch entries (0 = one shared [N] vector);
+ *   rowsum      : optional [batch][M] fp32, rowsum[b][m] = sum_k A[b][m][k] (a side product on the tensor cores:
+ *                 A x ones^T into 16 spare TMEM columns); stored, or atomically added when split_k > 1 (zero it). */
+GLF_API int glf_gemm_bf16_ex(const void* A, const void* B, void* D, int M, int N, int K, int batch, int a_mn, int b_mn,
+                     int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
+                     const float* bias, int64_t bias_stride, float alpha, int out_kind, int split_k, float* rowsum,
+                     glf_stream_t stream);
 
 /* The two HBM-bound fused epilogues as standalone entry points (unit tests, roofline probes).
  *   fwd: Z = LayerNorm_C(bn_a * U + bn_b + X) * ln_w + ln_b   (ours.py:908-915 after the W_z GEMM); U, X bf16 [rows, C];

@@ -1,5 +1,6 @@
 """Helpers shared by the -m gpu parity tests: they call the CUDA path through the C ABI / the nn.Module and compare
 with the CPU oracle (oracle/tpavi_oracle.py) on the same seeded inputs."""
+import contextlib
 import ctypes as C
 
 import torch
@@ -9,6 +10,18 @@ from oracle import tpavi_oracle as O
 
 BF16_TOL = 2e-2      # north_star: within 2e-2 relative error in bf16
 DEV = "cuda:0"
+
+
+@contextlib.contextmanager
+def dot_algo(name):
+    """Pin the algorithm of mode='dot' (glf_desc.reserved[1]): 'auto' | 'token' | 'gram'."""
+    from glfusion_b200 import tpavi
+    old = tpavi.DOT_ALGO
+    tpavi.DOT_ALGO = {"auto": 0, "token": 1, "gram": 2}[name]
+    try:
+        yield
+    finally:
+        tpavi.DOT_ALGO = old
 
 
 def stream():

@@ -34,6 +34,7 @@ def _desc(**kw):
     d.training, d.bn_layer = 1, 1
     d.eps_bn = d.eps_ln = 1e-5
     d.momentum = 0.1
+    d.reserved[1] = kw.pop("algo", 1)      # mode='dot' algorithm: 1 = token-space form, 2 = Gram form, 0 = auto
     for k, v in kw.items():
         setattr(d, k, v)
     return d
@@ -50,6 +51,13 @@ def test_sizes_are_host_only_and_scale_with_tokens():
     assert s2.saved_bytes > 1.9 * s1.saved_bytes * 0.98
     assert s1.ws_bwd_bytes >= rows * (256 * 2 + 3 * 128) * 2
     assert s1.saved_bytes % 256 == 0 and s1.ws_fwd_bytes % 256 == 0 and s1.ws_bwd_bytes % 256 == 0
+    # the Gram form keeps U and per-sequence [C x C] matrices, never the per-token projections; auto picks it (N >= 4 C)
+    sg, sa = L.GlfSizes(), L.GlfSizes()
+    assert lib.glf_tpavi_sizes(C.byref(_desc(algo=2)), C.byref(sg)) == 0
+    assert lib.glf_tpavi_sizes(C.byref(_desc(algo=0)), C.byref(sa)) == 0
+    assert rows * 256 * 2 <= sg.saved_bytes < s1.saved_bytes
+    assert sa.saved_bytes == sg.saved_bytes and sa.ws_bwd_bytes == sg.ws_bwd_bytes
+    assert lib.glf_tpavi_sizes(C.byref(_desc(algo=2, mode=L.MODE_EMBEDDED)), C.byref(sg)) < 0
     # NCTHW / fp32 inputs need a packed copy of x as well
     s3 = L.GlfSizes()
     assert lib.glf_tpavi_sizes(C.byref(_desc(x_layout=L.LAYOUT_NCTHW, io_dtype=L.DTYPE_F32)), C.byref(s3)) == 0

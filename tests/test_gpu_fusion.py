@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from conftest import load_golden
-from gpu_util import BF16_TOL, DEV, assert_close, golden_params
+from gpu_util import BF16_TOL, DEV, assert_close, dot_algo, golden_params
 from glfusion_b200 import GlobalLocalFusion
 from oracle import tpavi_oracle as O
 
@@ -19,7 +19,8 @@ def _build(C, pg, pl):
 
 
 @pytest.mark.parametrize("io", ["fp32", "bf16"])
-def test_glue_golden(io):
+@pytest.mark.parametrize("algo", ["token", "gram"])
+def test_glue_golden(io, algo):
     g = load_golden("glue_dot_c128")
     B, C, V, h, w = [int(v) for v in g["meta"]]
     dt = torch.float32 if io == "fp32" else torch.bfloat16
@@ -27,8 +28,9 @@ def test_glue_golden(io):
     f4 = [g[f"f4:{v}"].to(DEV, dt).requires_grad_(True) for v in range(V)]
     cl = [g[f"cls:{v}"].to(DEV).requires_grad_(True) for v in range(V)]
     ct = [g[f"ctr:{v}"].to(DEV).requires_grad_(True) for v in range(V)]
-    out = f({str(v): f4[v] for v in range(V)}, {str(v): cl[v] for v in range(V)}, {str(v): ct[v] for v in range(V)})
-    torch.autograd.backward([out[str(v)] for v in range(V)], [g[f"d_out:{v}"].to(DEV, dt) for v in range(V)])
+    with dot_algo(algo):
+        out = f({str(v): f4[v] for v in range(V)}, {str(v): cl[v] for v in range(V)}, {str(v): ct[v] for v in range(V)})
+        torch.autograd.backward([out[str(v)] for v in range(V)], [g[f"d_out:{v}"].to(DEV, dt) for v in range(V)])
     torch.cuda.synchronize()
     for v in range(V):
         assert_close(f"out:{v}", out[str(v)], g[f"out:{v}"], BF16_TOL)
@@ -41,7 +43,8 @@ def test_glue_golden(io):
                 assert_close(f"grad_{tag}:{k}", p.grad, g[f"grad_{tag}:{k}"], 3e-2, abs_floor=1e-3)
 
 
-def test_cfg2_shape_against_oracle():
+@pytest.mark.parametrize("algo", ["token", "gram"])
+def test_cfg2_shape_against_oracle(algo):
     """4 views x 28x28 tokens x C=256 (BASELINE cfg2 token geometry), 2 frames as batch, seeded oracle comparison."""
     B, C, V, h, w = 2, 256, 4, 28, 28
     pg = O.init_params(C, seed=31, randomize_affine=True)
@@ -57,20 +60,23 @@ def test_cfg2_shape_against_oracle():
     f4d = [t.to(DEV, torch.bfloat16).requires_grad_(True) for t in f4]
     cld = [t.to(DEV).requires_grad_(True) for t in cl]
     ctd = [t.to(DEV).requires_grad_(True) for t in ct]
-    out = f.forward_stacked(f4d, cld, ctd)
-    out.backward(torch.stack(do, dim=2).to(DEV, torch.bfloat16))
+    with dot_algo(algo):
+        out = f.forward_stacked(f4d, cld, ctd)
+        out.backward(torch.stack(do, dim=2).to(DEV, torch.bfloat16))
     torch.cuda.synchronize()
     for v in range(V):
         assert_close(f"out:{v}", out[:, :, v], outs[v], BF16_TOL)
         assert_close(f"df4:{v}", f4d[v].grad, df4[v], BF16_TOL)
         assert_close(f"dctr:{v}", ctd[v].grad, dctr[v], 4e-2)
-    for k, p in f.local_attn.named_parameters():
-        if not k.startswith("align_channel"):
-            assert_close("grad_l:" + k, p.grad, gl[k], 3e-2, abs_floor=1e-3)
+    for mod, ref in ((f.local_attn, gl), (f.global_attn, gg)):
+        for k, p in mod.named_parameters():
+            if not k.startswith("align_channel"):
+                assert_close("grad:" + k, p.grad, ref[k], 3e-2, abs_floor=1e-3)
 
 
 @pytest.mark.parametrize("h,w,V,io", [(5, 7, 3, "fp32"), (5, 7, 2, "bf16"), (9, 8, 1, "bf16")])
-def test_ragged_spatial_sizes_against_oracle(h, w, V, io):
+@pytest.mark.parametrize("algo", ["token", "gram"])
+def test_ragged_spatial_sizes_against_oracle(h, w, V, io, algo):
     """Odd h*w (scalar NCHW path), tokens not a multiple of any tile, single view."""
     B, C = 3, 128
     dt = torch.float32 if io == "fp32" else torch.bfloat16
@@ -87,8 +93,9 @@ def test_ragged_spatial_sizes_against_oracle(h, w, V, io):
     f4d = [t.to(DEV, dt).requires_grad_(True) for t in f4]
     cld = [t.to(DEV).requires_grad_(True) for t in cl]
     ctd = [t.to(DEV).requires_grad_(True) for t in ct]
-    out = f.forward_stacked(f4d, cld, ctd)
-    out.backward(torch.stack(do, dim=2).to(DEV, dt))
+    with dot_algo(algo):
+        out = f.forward_stacked(f4d, cld, ctd)
+        out.backward(torch.stack(do, dim=2).to(DEV, dt))
     torch.cuda.synchronize()
     for v in range(V):
         assert_close(f"out:{v}", out[:, :, v], outs[v], BF16_TOL)

@@ -2,7 +2,8 @@
 import pytest
 import torch
 
-from gpu_util import DEV, gemm
+from glfusion_b200 import _lib as L
+from gpu_util import DEV, gemm, stream
 from oracle import tpavi_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -93,3 +94,38 @@ def test_transpose_pack_roundtrip():
     torch.cuda.synchronize()
     assert torch.equal(out, x.transpose(1, 2).to(torch.bfloat16))
     assert torch.equal(back, x.to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize("split_k", [1, 4])
+@pytest.mark.parametrize("N", [256, 264, 64])
+def test_gemm_rowsum_side_product(split_k, N):
+    """Token contraction S_b = A_b^T X_b (both operands MN-major) with the row sums of A^T riding along on the tensor
+    cores (the Gram form's S = X^T X, s = X^T 1)."""
+    torch.manual_seed(5)
+    batch, M, K = 3, 200, 1000
+    A = torch.randn(batch, K, M, device=DEV).to(torch.bfloat16)       # [K, M]: MN-major A
+    Bm = torch.randn(batch, K, N, device=DEV).to(torch.bfloat16)
+    D = torch.zeros(batch, M, N, device=DEV)
+    rs = torch.zeros(batch, M, device=DEV)
+    lib = L.load()
+    L.check(lib.glf_gemm_bf16_ex(L.ptr(A), L.ptr(Bm), L.ptr(D), M, N, K, batch, 1, 1, M, N, N, K * M, K * N, M * N,
+                                 None, 0, 1.0, 2 if split_k > 1 else 1, split_k, L.ptr(rs), stream()))
+    torch.cuda.synchronize()
+    ref = torch.einsum("bkm,bkn->bmn", A.float(), Bm.float())
+    assert O.rel_err(D, ref) < 1e-5
+    assert O.rel_err(rs, A.float().sum(1)) < 1e-5
+
+
+def test_gemm_per_batch_bias():
+    torch.manual_seed(6)
+    batch, M, N, K = 4, 300, 256, 256
+    A = torch.randn(batch, M, K, device=DEV).to(torch.bfloat16)
+    Bm = torch.randn(batch, N, K, device=DEV).to(torch.bfloat16)
+    bias = torch.randn(batch, N, device=DEV)
+    D = torch.zeros(batch, M, N, device=DEV, dtype=torch.bfloat16)
+    lib = L.load()
+    L.check(lib.glf_gemm_bf16_ex(L.ptr(A), L.ptr(Bm), L.ptr(D), M, N, K, batch, 0, 0, K, K, N, M * K, N * K, M * N,
+                                 L.ptr(bias), N, 1.0, 0, 1, None, stream()))
+    torch.cuda.synchronize()
+    ref = torch.einsum("bmk,bnk->bmn", A.float(), Bm.float()) + bias[:, None, :]
+    assert O.rel_err(D, ref) < 6e-3

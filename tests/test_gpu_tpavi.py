@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from conftest import load_golden
-from gpu_util import BF16_TOL, DEV, assert_close, golden_params, grad_scale, load_module_from_params
+from gpu_util import BF16_TOL, DEV, assert_close, dot_algo, golden_params, grad_scale, load_module_from_params
 from glfusion_b200 import TPAVIModule
 from oracle import tpavi_oracle as O
 
@@ -24,13 +24,16 @@ def _run(m, x, dz):
 
 @pytest.mark.parametrize("name", DOT_CASES)
 @pytest.mark.parametrize("io", ["fp32", "bf16"])
-def test_golden_dot(name, io):
+@pytest.mark.parametrize("algo", ["token", "gram"])
+def test_golden_dot(name, io, algo):
+    """Both exact reassociations of mode='dot' (token-space and Gram form) against the reference's golden vectors."""
     g = load_golden(name)
     B, C, T, H, W, training, bn = [int(v) for v in g["meta"]]
     m = load_module_from_params(TPAVIModule, golden_params(g), C, "dot", bool(bn))
     m.train(bool(training))
     dt = torch.float32 if io == "fp32" else torch.bfloat16
-    z, dx = _run(m, g["x"].to(DEV, dt), g["dz"].to(DEV, dt))
+    with dot_algo(algo):
+        z, dx = _run(m, g["x"].to(DEV, dt), g["dz"].to(DEV, dt))
     assert tuple(z.shape) == (B, C, T, H, W) and z.dtype == dt
     assert list(z.stride()) == [int(s) for s in g["z_strides"]]     # same strided view as the reference returns
     assert_close("z", z, g["z"], BF16_TOL)
@@ -48,7 +51,8 @@ def test_golden_dot(name, io):
 
 
 @pytest.mark.parametrize("layout", ["ncthw", "token"])
-def test_oracle_dot_layouts(layout):
+@pytest.mark.parametrize("algo", ["token", "gram", "auto"])
+def test_oracle_dot_layouts(layout, algo):
     """Seeded inputs, both accepted physical layouts of x (NCTHW, and channels-last 'token-major')."""
     B, C, T, H, W = 4, 256, 4, 14, 14
     p = O.init_params(C, seed=21, randomize_affine=True)
@@ -62,7 +66,8 @@ def test_oracle_dot_layouts(layout):
     if layout == "token":
         xd = xd.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
         dzd = dzd.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
-    z, dx = _run(m, xd, dzd)
+    with dot_algo(algo):
+        z, dx = _run(m, xd, dzd)
     if layout == "token":
         assert dx.permute(0, 2, 3, 4, 1).is_contiguous()
     assert_close("z", z, zo, BF16_TOL)
