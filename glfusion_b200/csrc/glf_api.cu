@@ -170,17 +170,16 @@ size_t carve_saved(const Dims& m, void* base, Saved* s) {
   return (c.off + 255) & ~static_cast<size_t>(255);
 }
 
-struct WsFwd { float* colstats; float* red1; float* Mf; void* attn; void* saved_fallback; float* Sf; float* Qf; };
+struct WsFwd { float* colstats; float* red1; float* Mf; void* attn; void* saved_fallback; float* Sf; };
 size_t carve_ws_fwd(const Dims& m, void* base, WsFwd* w, size_t saved_bytes) {
   Carver c(base);
   const size_t np = 4 * (m.dot ? static_cast<size_t>(m.B) * m.tiles_seq : static_cast<size_t>(m.tiles_all));
   w->colstats = c.take<float>(np * 2 * m.C);   // one partial per (tile, 32-row quarter)
   w->red1 = c.take<float>(static_cast<size_t>(REDUCE_STAGE1_ROWS) * 2 * m.C);
-  w->Sf = w->Qf = nullptr;
+  w->Sf = nullptr;
   if (m.gram) {
     w->Mf = nullptr; w->attn = nullptr;
-    w->Sf = c.take<float>(static_cast<size_t>(m.B) * m.C * m.C);
-    w->Qf = c.take<float>(static_cast<size_t>(m.B) * m.C * m.Ca);
+    w->Sf = c.take<float>(static_cast<size_t>(m.B) * m.C * m.C);   // split-K accumulation target of S = X^T X
     w->saved_fallback = c.take<uint8_t>(saved_bytes);
     return (c.off + 255) & ~static_cast<size_t>(255);
   }
@@ -195,16 +194,16 @@ struct WsBwd {
   float *dWpf, *part_ln, *k1, *k2, *k3, *cs_t, *cs_p, *cs_g, *red1, *dwcat, *delta;
   void* attn;
   // Gram form
-  float *Rf, *rv, *QSf, *G0, *evec, *dwaug;
-  bf16 *dQa, *Qk, *dT, *EF;
+  float *Rf, *rv, *G0, *Hf, *evec, *dwaug;
+  bf16 *Rb, *AK, *dQa, *dT, *EF;
 };
 size_t carve_ws_bwd(const glf_desc* d, const Dims& m, void* base, WsBwd* w) {
   Carver c(base);
   const size_t rows = m.rows, C = m.C, Ci = m.Ci, B = m.B;
   w->dztok = m.pack_dz ? c.take<bf16>(rows * C) : nullptr;
   w->dV = c.take<bf16>(rows * C);
-  w->Rf = w->rv = w->QSf = w->G0 = w->evec = w->dwaug = nullptr;
-  w->dQa = w->Qk = w->dT = w->EF = nullptr;
+  w->Rf = w->rv = w->G0 = w->Hf = w->evec = w->dwaug = nullptr;
+  w->Rb = w->AK = w->dQa = w->dT = w->EF = nullptr;
   if (m.gram) {
     const size_t Ca = m.Ca;
     w->dU = w->dP = w->dY = nullptr;
@@ -215,15 +214,16 @@ size_t carve_ws_bwd(const glf_desc* d, const Dims& m, void* base, WsBwd* w) {
     w->k1 = c.take<float>(C);
     w->k2 = c.take<float>(C);
     w->k3 = c.take<float>(C);
-    w->Rf = c.take<float>(B * C * C);
+    w->Rf = c.take<float>(B * C * C);        // split-K accumulation target of R = dV^T X
     w->rv = c.take<float>(B * C);
-    w->QSf = c.take<float>(B * C * Ca);
+    w->Rb = c.take<bf16>(B * Ca * Ca);       // [[R, rv], [s^T, N]]
+    w->AK = c.take<bf16>(B * 2 * C * Ca);    // [Qk ; Dk] per sequence
     w->dQa = c.take<bf16>(B * C * Ca);
-    w->Qk = c.take<bf16>(B * C * Ca);
     w->dWpb = c.take<bf16>(B * C * Ci);
     w->dM = c.take<bf16>(B * Ci * Ci);
     w->dT = c.take<bf16>(B * Ci * Ca);
     w->G0 = c.take<float>(B * Ca * Ca);
+    w->Hf = c.take<float>(B * Ca * Ca);
     w->EF = c.take<bf16>(B * 2 * C * C);
     w->evec = c.take<float>(B * C);
     w->dwaug = c.take<float>(3 * Ci * Ca);
@@ -296,26 +296,55 @@ int check_ptr(const void* p, const char* name) {
 
 
 // ------------------------------------------------------------------------------------------------ Gram form of 'dot'
-// Token-sized products of a sequence contraction S = A^T X (A = X or dV): both operands MN-major views of token-major
-// activations, fp32 result [B][C][C], the column sums of A as the GEMM's row-sum side product.
-int gram_token_contraction(const bf16* A, const bf16* X, float* Sf, float* rowsum, int B, int N, int C,
-                           cudaStream_t stream) {
+// Token contraction of a sequence, S = A^T X (A = X or dV): both operands MN-major views of token-major
+// activations, the column sums of A as the GEMM's row-sum side product; result = the augmented bf16 matrix
+// [[S, colsum(A)], [rowv^T, corner]] of width Ca.  Enough sequences: the GEMM writes bf16 straight into it and a border
+// kernel adds the homogeneous row / column; few long sequences: split-K into fp32, then one assembling pass.
+int gram_token_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* scratch, float* rowsum, const float* rowv,
+                           float corner, int B, int N, int C, int Ca, cudaStream_t stream) {
   GemmArgs g;
   g.A = opnd(A, 1, C, static_cast<long long>(N) * C);
   g.B = opnd(X, 1, C, static_cast<long long>(N) * C);
   g.M = C; g.N = C; g.K = N; g.batch = B;
   g.bn_hint = 128;
-  g.ldd = C; g.strideD = static_cast<long long>(C) * C;
-  g.D = Sf;
   g.rowsum = rowsum; g.rowsum_stride = C;
   g.split_k = pick_split(static_cast<long long>(B) * ((C + 127) / 128) * ((C + 127) / 128), N);
   if (g.split_k > 1) {
-    GLF_TRY(check_cuda(cudaMemsetAsync(Sf, 0, sizeof(float) * B * C * C, stream), "memset S"));
+    GLF_TRY(check_cuda(cudaMemsetAsync(scratch, 0, sizeof(float) * B * C * C, stream), "memset S"));
     GLF_TRY(check_cuda(cudaMemsetAsync(rowsum, 0, sizeof(float) * B * C, stream), "memset s"));
     g.out_kind = 2;
-  } else {
-    g.out_kind = 1;
+    g.D = scratch; g.ldd = C; g.strideD = static_cast<long long>(C) * C;
+    GLF_TRY(gemm(g, stream));
+    return gram_assemble_aug(scratch, rowsum, rowv ? rowv : rowsum, out_aug, B, C, Ca, corner, stream);
   }
+  g.out_kind = 0;
+  g.D = out_aug; g.ldd = Ca; g.strideD = static_cast<long long>(Ca) * Ca;
+  GLF_TRY(gemm(g, stream));
+  return gram_border(rowsum, rowv ? rowv : rowsum, out_aug, B, C, Ca, corner, stream);
+}
+
+// D = A0 B0^T + A1 B1^T (+ bias + addend), bf16 output: both products accumulate into one TMEM tile when each operand
+// pair can be described as two "limbs" of one tensor map (their distance in memory is the limb stride); otherwise two
+// passes, the second adding onto the first in place.  g.A / g.B carry layout, leading dimension and batch stride.
+int gemm_pair2(GemmArgs g, const bf16* A0, const bf16* A1, const bf16* B0, const bf16* B1, cudaStream_t stream) {
+  const long long dA = A1 - A0, dB = B1 - B0;
+  auto ok = [](long long d) {
+    const long long a = d < 0 ? -d : d;
+    return a != 0 && a % 8 == 0 && a < (1LL << 38);
+  };
+  if (ok(dA) && ok(dB)) {
+    g.A.ptr = dA > 0 ? A0 : A1; g.A.limb_stride = dA > 0 ? dA : -dA;
+    g.B.ptr = dB > 0 ? B0 : B1; g.B.limb_stride = dB > 0 ? dB : -dB;
+    g.npairs = 2;
+    g.pairA[0] = dA > 0 ? 0 : 1; g.pairA[1] = 1 - g.pairA[0];
+    g.pairB[0] = dB > 0 ? 0 : 1; g.pairB[1] = 1 - g.pairB[0];
+    return gemm(g, stream);
+  }
+  g.A.ptr = A0; g.B.ptr = B0;
+  GLF_TRY(gemm(g, stream));
+  g.A.ptr = A1; g.B.ptr = B1;
+  g.bias = nullptr;
+  g.addend = reinterpret_cast<const bf16*>(g.D); g.ld_add = g.ldd; g.stride_add = g.strideD;
   return gemm(g, stream);
 }
 
@@ -336,8 +365,7 @@ int tpavi_fwd_gram(const glf_desc* d, const Dims& m, const void* x, const glf_we
     X = s.xtok;
   }
   // S_b = X_b^T X_b, s_b = X_b^T 1   ->   S~_b
-  GLF_TRY(gram_token_contraction(X, X, wf.Sf, s.sfv, B, N, C, stream));
-  GLF_TRY(gram_assemble_S(wf.Sf, s.sfv, s.Sa, B, C, Ca, static_cast<float>(N), stream));
+  GLF_TRY(gram_token_contraction(X, X, s.Sa, wf.Sf, s.sfv, nullptr, static_cast<float>(N), B, N, C, Ca, stream));
   {  // T_b = W~phi S~_b                      [Ci x Ca]   (= Phi_b^T X~_b; S~ is symmetric)
     GemmArgs g;
     g.A = opnd(s.waug + CiCa, 0, Ca, 0);
@@ -370,11 +398,10 @@ int tpavi_fwd_gram(const glf_desc* d, const Dims& m, const void* x, const glf_we
     g.B = opnd(s.waug, 1, Ca, 0);
     g.B.rows = C1;
     g.M = C; g.N = Ca; g.K = Ci; g.batch = B;
-    g.out_kind = 1;
-    g.D = wf.Qf; g.ldd = Ca; g.strideD = CCa;
+    g.D = s.Qb; g.ldd = Ca; g.strideD = CCa;
     GLF_TRY(gemm(g, stream));
   }
-  GLF_TRY(gram_convert_Q(wf.Qf, s.Qb, s.cvec, B, C, Ca, stream));
+  GLF_TRY(gram_cvec(s.Wp, w->theta_b, s.cvec, B, C, Ci, stream));   // c_b = W'_b b_theta, kept in fp32
   int np = 0;
   {  // U_b = X_b Q_b^T + c_b   (+ BatchNorm column statistics); bz stays folded into the BN affine
     GemmArgs g;
@@ -412,21 +439,19 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved&
   const long long CCi = static_cast<long long>(C) * Ci, CC = static_cast<long long>(C) * C;
   const float invN = 1.f / static_cast<float>(N);
   const bool bn_train = d->bn_layer && d->training;   // k2, k3 != 0 only then
-  // R_b = dV_b^T X_b, rv_b = dV_b^T 1
-  GLF_TRY(gram_token_contraction(wb.dV, X, wb.Rf, wb.rv, B, N, C, stream));
-  if (bn_train) {  // (U^T X~)_b = Q~_b S~_b   [C x Ca]
+  // [[R_b, rv_b], [s_b^T, N]] with R_b = dV_b^T X_b, rv_b = dV_b^T 1
+  GLF_TRY(gram_token_contraction(wb.dV, X, wb.Rb, wb.Rf, wb.rv, s.sfv, static_cast<float>(N), B, N, C, Ca, stream));
+  // Qk = k2 Q~ (column C: k2 c + k3), Dk = diag(k1), E = k1 Q
+  GLF_TRY(gram_kprep(s.Qb, s.cvec, wb.k1, wb.k2, wb.k3, wb.AK, wb.EF, B, C, Ca, stream));
+  {  // dQ~_b = dU_b^T X~_b = Qk_b S~_b + Dk [R_b | rv_b]     [C x Ca]   (B operands read MN-major; S~ is symmetric)
     GemmArgs g;
-    g.A = opnd(s.Qb, 0, Ca, CCa);
-    g.B = opnd(s.Sa, 0, Ca, CaCa);
+    g.A = opnd(nullptr, 0, Ca, 2 * CCa);
+    g.B = opnd(nullptr, 1, Ca, CaCa);
     g.B.rows = C1;
     g.M = C; g.N = Ca; g.K = C1; g.batch = B;
-    g.out_kind = 1;
-    g.D = wb.QSf; g.ldd = Ca; g.strideD = CCa;
-    GLF_TRY(gemm(g, stream));
+    g.D = wb.dQa; g.ldd = Ca; g.strideD = CCa;
+    GLF_TRY(gemm_pair2(g, wb.AK, wb.AK + CCa, s.Sa, wb.Rb, stream));
   }
-  // dQ~ = k1 [R | rv] + k2 Q~S~ + k3 [s | N] ;  Qk = k2 Q~ ;  E = k1 Q
-  GLF_TRY(gram_combine_dQ(wb.Rf, wb.rv, bn_train ? wb.QSf : nullptr, s.sfv, s.Qb, wb.k1, wb.k2, wb.k3, wb.dQa, wb.Qk,
-                          wb.EF, B, C, Ca, static_cast<float>(N), stream));
   {  // dW'_b = dQ~_b W~theta^T               [C x Ci]
     GemmArgs g;
     g.A = opnd(wb.dQa, 0, Ca, CCa);
@@ -506,52 +531,28 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved&
     g.D = wb.G0; g.ldd = Ca; g.strideD = CaCa;
     GLF_TRY(gemm(g, stream));
   }
-  if (bn_train) {  // G0_b += Q~_b^T (k2 Q~_b) / 2   (one add per element: deterministic)
+  if (bn_train) {  // H_b = Q~_b^T Qk_b   [C1 x Ca]  (dU Q = dV E + X H[:C,:C] + 1 H[:C,C]^T: the k2 U + k3 part of dU)
     GemmArgs g;
     g.A = opnd(s.Qb, 1, Ca, CCa);
     g.A.rows = C1;
-    g.B = opnd(wb.Qk, 1, Ca, CCa);
+    g.B = opnd(wb.AK, 1, Ca, 2 * CCa);
     g.B.rows = C1;
     g.M = C1; g.N = Ca; g.K = C; g.batch = B;
-    g.alpha = 0.5f;
-    g.out_kind = 2;
-    g.D = wb.G0; g.ldd = Ca; g.strideD = CaCa;
+    g.out_kind = 1;
+    g.D = wb.Hf; g.ldd = Ca; g.strideD = CaCa;
     GLF_TRY(gemm(g, stream));
   }
-  // F = (G0 + G0^T)[:C, :C] ;  e = (G0 + G0^T)[:C, C] + Q^T k3
-  GLF_TRY(gram_assemble_F(wb.G0, s.Qb, wb.k3, bn_train ? 1 : 0, wb.EF, wb.evec, B, C, Ca, stream));
-  {  // dX_b = dV_b E_b + X_b F_b + 1 e_b^T + dV_b : both products accumulate into one tile (the two A operands are
-     // two "limbs" of one tensor map, their distance in memory is the limb stride)
-    void* D = m.pack_x ? static_cast<void*>(wb.dxtok) : dx;
-    const bf16* dV = wb.dV;
-    const long long diff = X - dV;   // elements
-    const long long ad = diff < 0 ? -diff : diff;
-    const bool one_launch = ad != 0 && ad % 8 == 0 && ad < (1LL << 38);
+  // F = (G0 + G0^T + H)[:C, :C] ;  e = (G0[:, C] + G0[C, :] + H[:, C])[:C]
+  GLF_TRY(gram_assemble_F(wb.G0, bn_train ? wb.Hf : nullptr, wb.EF, wb.evec, B, C, Ca, stream));
+  {  // dX_b = dV_b E_b + X_b F_b + 1 e_b^T + dV_b
     GemmArgs g;
-    g.B = opnd(wb.EF, 1, C, 2 * CC);
-    g.B.limb_stride = CC;
+    g.A = opnd(nullptr, 0, C, static_cast<long long>(N) * C);
+    g.B = opnd(nullptr, 1, C, 2 * CC);
     g.M = N; g.N = C; g.K = C; g.batch = B;
     g.bias = wb.evec; g.bias_stride = C;
-    g.addend = dV; g.ld_add = C; g.stride_add = static_cast<long long>(N) * C;
-    g.D = D; g.ldd = C; g.strideD = static_cast<long long>(N) * C;
-    if (one_launch) {
-      g.A = opnd(diff > 0 ? dV : X, 0, C, static_cast<long long>(N) * C);
-      g.A.limb_stride = ad;
-      g.npairs = 2;
-      g.pairA[0] = diff > 0 ? 0 : 1; g.pairB[0] = 0;   // dV x E
-      g.pairA[1] = diff > 0 ? 1 : 0; g.pairB[1] = 1;   // X  x F
-      GLF_TRY(gemm(g, stream));
-    } else {
-      // operands too far apart for one tensor map: two passes, the second adds onto the first in place
-      g.A = opnd(dV, 0, C, static_cast<long long>(N) * C);
-      g.bias = nullptr;
-      GLF_TRY(gemm(g, stream));
-      g.A = opnd(X, 0, C, static_cast<long long>(N) * C);
-      g.B = opnd(wb.EF + CC, 1, C, 2 * CC);
-      g.bias = wb.evec;
-      g.addend = reinterpret_cast<const bf16*>(D);
-      GLF_TRY(gemm(g, stream));
-    }
+    g.addend = wb.dV; g.ld_add = C; g.stride_add = static_cast<long long>(N) * C;
+    g.D = m.pack_x ? static_cast<void*>(wb.dxtok) : dx; g.ldd = C; g.strideD = static_cast<long long>(N) * C;
+    GLF_TRY(gemm_pair2(g, wb.dV, X, wb.EF, wb.EF + CC, stream));
   }
   GLF_TRY(gram_unpack_grads(wb.dwaug, g_, C, Ci, Ca, stream));
   if (m.pack_x) {

@@ -34,69 +34,107 @@ __global__ void gram_prep_weights_kernel(const float* __restrict__ tw, const flo
   }
 }
 
-// S~ [B][Ca][Ca] bf16 from S [B][C][C] fp32 and s [B][C] fp32:  [[S, s], [s^T, N]], zero padded
-__global__ void gram_assemble_S_kernel(const float* __restrict__ Sf, const float* __restrict__ sf,
-                                       bf16* __restrict__ Sa, long long total, int C, int Ca, float ntok) {
+// Augmented [B][Ca][Ca] bf16 matrix [[M, colv], [rowv^T, corner]] (zero padded) from M [B][C][C] fp32 (split-K path)
+__global__ void gram_assemble_aug_kernel(const float* __restrict__ Mf, const float* __restrict__ colv,
+                                         const float* __restrict__ rowv, bf16* __restrict__ out, long long total,
+                                         int C, int Ca, float corner) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int j = static_cast<int>(i % Ca);
     const int r = static_cast<int>((i / Ca) % Ca);
     const long long b = i / (static_cast<long long>(Ca) * Ca);
     float v = 0.f;
-    if (r < C && j < C) v = Sf[(b * C + r) * C + j];
-    else if (r < C && j == C) v = sf[b * C + r];
-    else if (r == C && j < C) v = sf[b * C + j];
-    else if (r == C && j == C) v = ntok;
-    Sa[i] = __float2bfloat16(v);
+    if (r < C && j < C) v = Mf[(b * C + r) * C + j];
+    else if (r < C && j == C) v = colv[b * C + r];
+    else if (r == C && j < C) v = rowv[b * C + j];
+    else if (r == C && j == C) v = corner;
+    out[i] = __float2bfloat16(v);
   }
 }
 
-// Q~ fp32 [B][C][Ca] -> bf16 copy (GEMM operand) + c = Q~[:, :, C] kept in fp32 (the per-sequence bias of U)
-__global__ void gram_convert_Q_kernel(const float* __restrict__ Qf, bf16* __restrict__ Qb, float* __restrict__ cvec,
-                                      long long total, int C, int Ca) {
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int j = static_cast<int>(i % Ca);
-    const float v = Qf[i];
-    Qb[i] = __float2bfloat16(j <= C ? v : 0.f);
-    if (j == C) cvec[i / Ca] = v;
+// Border of an augmented matrix whose [C x C] block a GEMM already wrote in bf16: column C = colv, row C = rowv,
+// corner, zero padding.  One block per batch entry.
+__global__ void gram_border_kernel(const float* __restrict__ colv, const float* __restrict__ rowv,
+                                   bf16* __restrict__ out, int C, int Ca, float corner) {
+  const long long b = blockIdx.x;
+  bf16* M = out + b * static_cast<long long>(Ca) * Ca;
+  const int pad = Ca - C;
+  for (int i = threadIdx.x; i < C * pad; i += blockDim.x) {        // columns C.. of rows < C
+    const int r = i / pad, j = C + i % pad;
+    M[static_cast<long long>(r) * Ca + j] = __float2bfloat16(j == C ? colv[b * C + r] : 0.f);
   }
-}
-
-// dQ~ = k1 * [R | rv] + k2 * (Q~ S~) + k3 * [s | N]   ;   Qk = k2 * Q~   ;   E = k1 * Q  (-> EF[b][0])
-// (k1, k2, k3: per output channel = row of Q~).  QSf may be null when k2 == k3 == 0 (eval-mode BN / no BN).
-__global__ void gram_combine_dQ_kernel(const float* __restrict__ Rf, const float* __restrict__ rv,
-                                       const float* __restrict__ QSf, const float* __restrict__ sf,
-                                       const bf16* __restrict__ Qb, const float* __restrict__ k1,
-                                       const float* __restrict__ k2, const float* __restrict__ k3,
-                                       bf16* __restrict__ dQa, bf16* __restrict__ Qk, bf16* __restrict__ EF,
-                                       long long total, int C, int Ca, float ntok) {
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int j = static_cast<int>(i % Ca);
-    const int r = static_cast<int>((i / Ca) % C);
-    const long long b = i / (static_cast<long long>(Ca) * C);
-    const float a1 = k1[r];
-    const float q = __bfloat162float(Qb[i]);
+  for (int i = threadIdx.x; i < pad * Ca; i += blockDim.x) {       // rows C..
+    const int r = C + i / Ca, j = i % Ca;
     float v = 0.f;
-    if (j < C) v = a1 * Rf[(b * C + r) * C + j];
-    else if (j == C) v = a1 * rv[b * C + r];
-    if (QSf != nullptr && j <= C) {
-      const float sa = j < C ? sf[b * C + j] : ntok;
-      v = fmaf(k2[r], QSf[i], fmaf(k3[r], sa, v));
-      Qk[i] = __float2bfloat16(k2[r] * q);
-    }
-    dQa[i] = __float2bfloat16(v);
-    if (j < C) EF[(b * 2 * C + r) * C + j] = __float2bfloat16(a1 * q);
+    if (r == C) v = j < C ? rowv[b * C + j] : (j == C ? corner : 0.f);
+    M[static_cast<long long>(r) * Ca + j] = __float2bfloat16(v);
   }
 }
 
-// F = (G0 + G0^T)[:C, :C] -> EF[b][1]   (32 x 32 tiles, the transposed tile goes through shared memory)
+// c_b = W'_b b_theta in fp32 (the per-sequence bias of U): one warp per (b, r) row of W'
+__global__ void gram_cvec_kernel(const bf16* __restrict__ Wp, const float* __restrict__ tb, float* __restrict__ cvec,
+                                 long long rows, int Ci) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const bf16* w = Wp + row * Ci;
+  float acc = 0.f;
+  for (int i = lane * 2; i < Ci; i += 64) {
+    const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(w + i));
+    acc = fmaf(v.x, tb[i], fmaf(v.y, tb[i + 1], acc));
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) cvec[row] = acc;
+}
+
+// Per-sequence operands of the backward products, from Q~ (bf16), c and the BatchNorm-backward coefficients
+// (dU = k1 dV + k2 U + k3 per output channel = row r of Q~):
+//   AK[b][0] = Qk = k2 Q~  with column C = k2 c + k3      (dQ~ = Qk S~ + ... ; H = Q~^T Qk)
+//   AK[b][1] = Dk = diag(k1) (column C and padding zero)   (... + Dk [R | rv])
+//   EF[b][0] = E  = k1 Q                                    (dX = dV E + ...)
+// 8 columns per thread.
+__global__ void gram_kprep_kernel(const bf16* __restrict__ Qb, const float* __restrict__ cvec,
+                                  const float* __restrict__ k1, const float* __restrict__ k2,
+                                  const float* __restrict__ k3, bf16* __restrict__ AK, bf16* __restrict__ EF,
+                                  long long total8, int C, int Ca) {
+  const int cv = Ca / 8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int j0 = static_cast<int>(i % cv) * 8;
+    const int r = static_cast<int>((i / cv) % C);
+    const long long b = i / (static_cast<long long>(cv) * C);
+    const float a1 = k1[r], a2 = k2[r];
+    const uint4 qv = *reinterpret_cast<const uint4*>(Qb + i * 8);
+    const uint32_t* q32 = reinterpret_cast<const uint32_t*>(&qv);
+    uint32_t qk[4], dk[4], ee[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 q = unpack_bf16(q32[t]);
+      const int j = j0 + 2 * t;
+      float x0 = j < C ? a2 * q.x : 0.f, x1 = j + 1 < C ? a2 * q.y : 0.f;
+      if (j == C) x0 = fmaf(a2, cvec[b * C + r], k3[r]);
+      if (j + 1 == C) x1 = fmaf(a2, cvec[b * C + r], k3[r]);
+      qk[t] = pack_bf16(x0, x1);
+      dk[t] = pack_bf16(j == r ? a1 : 0.f, j + 1 == r ? a1 : 0.f);
+      ee[t] = pack_bf16(a1 * q.x, a1 * q.y);
+    }
+    bf16* ak = AK + (b * 2 * C + r) * static_cast<long long>(Ca) + j0;
+    *reinterpret_cast<uint4*>(ak) = make_uint4(qk[0], qk[1], qk[2], qk[3]);
+    *reinterpret_cast<uint4*>(ak + static_cast<long long>(C) * Ca) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+    if (j0 < C)   // C % 8 == 0: a vector is entirely inside or outside the first C columns
+      *reinterpret_cast<uint4*>(EF + (b * 2 * C + r) * static_cast<long long>(C) + j0) = make_uint4(ee[0], ee[1], ee[2], ee[3]);
+  }
+}
+
+// F = (dS + dS^T + H)[:C, :C] -> EF[b][1]   (32 x 32 tiles, the transposed tile goes through shared memory);
+// e = (dS[:, C] + dS[C, :] + H[:, C])[:C]  (blocks of the first tile row also emit their 32 entries of e)
 __global__ void __launch_bounds__(256)
-    gram_assemble_F_kernel(const float* __restrict__ G0, bf16* __restrict__ EF, int C, int Ca) {
+    gram_assemble_F_kernel(const float* __restrict__ G0, const float* __restrict__ Hf, bf16* __restrict__ EF,
+                           float* __restrict__ evec, int C, int Ca) {
   __shared__ float t[32][33];
   const long long b = blockIdx.z;
   const float* G = G0 + b * static_cast<long long>(Ca) * Ca;
+  const float* H = Hf != nullptr ? Hf + b * static_cast<long long>(Ca) * Ca : nullptr;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
 #pragma unroll
@@ -109,33 +147,20 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int rr = r0 + ty + 8 * i, cc = c0 + tx;
-    if (rr < C && cc < C)
-      F[static_cast<long long>(rr) * C + cc] = __float2bfloat16(G[static_cast<long long>(rr) * Ca + cc] + t[tx][ty + 8 * i]);
-  }
-}
-
-// e[b][c] = G0[c][C] + G0[C][c] + sum_c' Q[c'][c] k3[c']
-__global__ void gram_evec_kernel(const float* __restrict__ G0, const bf16* __restrict__ Qb,
-                                 const float* __restrict__ k3, float* __restrict__ evec, int B, int C, int Ca,
-                                 int use_k3) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= static_cast<long long>(B) * C) return;
-  const int c = static_cast<int>(i % C);
-  const long long b = i / C;
-  const float* G = G0 + b * static_cast<long long>(Ca) * Ca;
-  float acc = G[static_cast<long long>(c) * Ca + C] + G[static_cast<long long>(C) * Ca + c];
-  if (use_k3) {
-    const bf16* Q = Qb + b * static_cast<long long>(C) * Ca;
-    float a0 = 0.f, a1 = 0.f;
-    int r = 0;
-    for (; r + 1 < C; r += 2) {
-      a0 = fmaf(__bfloat162float(Q[static_cast<long long>(r) * Ca + c]), k3[r], a0);
-      a1 = fmaf(__bfloat162float(Q[static_cast<long long>(r + 1) * Ca + c]), k3[r + 1], a1);
+    if (rr < C && cc < C) {
+      float v = G[static_cast<long long>(rr) * Ca + cc] + t[tx][ty + 8 * i];
+      if (H != nullptr) v += H[static_cast<long long>(rr) * Ca + cc];
+      F[static_cast<long long>(rr) * C + cc] = __float2bfloat16(v);
     }
-    if (r < C) a0 = fmaf(__bfloat162float(Q[static_cast<long long>(r) * Ca + c]), k3[r], a0);
-    acc += a0 + a1;
   }
-  evec[i] = acc;
+  if (blockIdx.y == 0 && ty == 0) {
+    const int c = c0 + tx;
+    if (c < C) {
+      float v = G[static_cast<long long>(c) * Ca + C] + G[static_cast<long long>(C) * Ca + c];
+      if (H != nullptr) v += H[static_cast<long long>(c) * Ca + C];
+      evec[b * C + c] = v;
+    }
+  }
 }
 
 // dW~ [3][Ci][Ca] fp32 -> the six caller-visible gradients (weight [Ci][C], bias [Ci])
@@ -166,37 +191,38 @@ int gram_prep_weights(const glf_weights* w, int C, int Ci, int Ca, bf16* waug, b
   return check_cuda(cudaGetLastError(), "gram_prep_weights launch");
 }
 
-int gram_assemble_S(const float* Sf, const float* sf, bf16* Sa, int B, int C, int Ca, float ntok, cudaStream_t stream) {
+int gram_assemble_aug(const float* Mf, const float* colv, const float* rowv, bf16* out, int B, int C, int Ca,
+                      float corner, cudaStream_t stream) {
   const long long total = static_cast<long long>(B) * Ca * Ca;
-  gram_assemble_S_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(Sf, sf, Sa, total, C, Ca, ntok);
-  return check_cuda(cudaGetLastError(), "gram_assemble_S launch");
+  gram_assemble_aug_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(Mf, colv, rowv, out, total, C, Ca, corner);
+  return check_cuda(cudaGetLastError(), "gram_assemble_aug launch");
 }
 
-int gram_convert_Q(const float* Qf, bf16* Qb, float* cvec, int B, int C, int Ca, cudaStream_t stream) {
-  const long long total = static_cast<long long>(B) * C * Ca;
-  gram_convert_Q_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(Qf, Qb, cvec, total, C, Ca);
-  return check_cuda(cudaGetLastError(), "gram_convert_Q launch");
+int gram_border(const float* colv, const float* rowv, bf16* out, int B, int C, int Ca, float corner,
+                cudaStream_t stream) {
+  gram_border_kernel<<<B, 256, 0, stream>>>(colv, rowv, out, C, Ca, corner);
+  return check_cuda(cudaGetLastError(), "gram_border launch");
 }
 
-int gram_combine_dQ(const float* Rf, const float* rv, const float* QSf, const float* sf, const bf16* Qb, const float* k1,
-                    const float* k2, const float* k3, bf16* dQa, bf16* Qk, bf16* EF, int B, int C, int Ca, float ntok,
+int gram_cvec(const bf16* Wp, const float* theta_b, float* cvec, int B, int C, int Ci, cudaStream_t stream) {
+  const long long rows = static_cast<long long>(B) * C;
+  gram_cvec_kernel<<<static_cast<int>((rows * 32 + 255) / 256), 256, 0, stream>>>(Wp, theta_b, cvec, rows, Ci);
+  return check_cuda(cudaGetLastError(), "gram_cvec launch");
+}
+
+int gram_kprep(const bf16* Qb, const float* cvec, const float* k1, const float* k2, const float* k3, bf16* AK, bf16* EF,
+               int B, int C, int Ca, cudaStream_t stream) {
+  const long long total8 = static_cast<long long>(B) * C * (Ca / 8);
+  gram_kprep_kernel<<<blocks_for(total8, 256), 256, 0, stream>>>(Qb, cvec, k1, k2, k3, AK, EF, total8, C, Ca);
+  return check_cuda(cudaGetLastError(), "gram_kprep launch");
+}
+
+int gram_assemble_F(const float* G0, const float* Hf, bf16* EF, float* evec, int B, int C, int Ca,
                     cudaStream_t stream) {
-  const long long total = static_cast<long long>(B) * C * Ca;
-  gram_combine_dQ_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(Rf, rv, QSf, sf, Qb, k1, k2, k3, dQa, Qk, EF, total,
-                                                                     C, Ca, ntok);
-  return check_cuda(cudaGetLastError(), "gram_combine_dQ launch");
-}
-
-int gram_assemble_F(const float* G0, const bf16* Qb, const float* k3, int use_k3, bf16* EF, float* evec, int B, int C,
-                    int Ca, cudaStream_t stream) {
   if (B > 65535) return set_error(GLF_ERR_INVALID, "gram form: more than 65535 sequences per call");
   dim3 grid((C + 31) / 32, (C + 31) / 32, B);
-  gram_assemble_F_kernel<<<grid, dim3(32, 8), 0, stream>>>(G0, EF, C, Ca);
-  int rc = check_cuda(cudaGetLastError(), "gram_assemble_F launch");
-  if (rc) return rc;
-  const long long n = static_cast<long long>(B) * C;
-  gram_evec_kernel<<<static_cast<int>((n + 127) / 128), 128, 0, stream>>>(G0, Qb, k3, evec, B, C, Ca, use_k3);
-  return check_cuda(cudaGetLastError(), "gram_evec launch");
+  gram_assemble_F_kernel<<<grid, dim3(32, 8), 0, stream>>>(G0, Hf, EF, evec, C, Ca);
+  return check_cuda(cudaGetLastError(), "gram_assemble_F launch");
 }
 
 int gram_unpack_grads(const float* dwaug, const glf_grads* g, int C, int Ci, int Ca, cudaStream_t stream) {

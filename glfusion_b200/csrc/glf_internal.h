@@ -100,13 +100,15 @@ int cast_bf16(const float* in, bf16* out, long long n, cudaStream_t stream);
 // Augmented width of the per-sequence matrices: column C is the homogeneous coordinate, the rest zero padding.
 inline int gram_ca(int C) { return C + 8; }
 int gram_prep_weights(const glf_weights* w, int C, int Ci, int Ca, bf16* waug, bf16* wzb, cudaStream_t stream);
-int gram_assemble_S(const float* Sf, const float* sf, bf16* Sa, int B, int C, int Ca, float ntok, cudaStream_t stream);
-int gram_convert_Q(const float* Qf, bf16* Qb, float* cvec, int B, int C, int Ca, cudaStream_t stream);
-int gram_combine_dQ(const float* Rf, const float* rv, const float* QSf, const float* sf, const bf16* Qb, const float* k1,
-                    const float* k2, const float* k3, bf16* dQa, bf16* Qk, bf16* EF, int B, int C, int Ca, float ntok,
+int gram_assemble_aug(const float* Mf, const float* colv, const float* rowv, bf16* out, int B, int C, int Ca,
+                      float corner, cudaStream_t stream);
+int gram_border(const float* colv, const float* rowv, bf16* out, int B, int C, int Ca, float corner,
+                cudaStream_t stream);
+int gram_cvec(const bf16* Wp, const float* theta_b, float* cvec, int B, int C, int Ci, cudaStream_t stream);
+int gram_kprep(const bf16* Qb, const float* cvec, const float* k1, const float* k2, const float* k3, bf16* AK, bf16* EF,
+               int B, int C, int Ca, cudaStream_t stream);
+int gram_assemble_F(const float* G0, const float* Hf, bf16* EF, float* evec, int B, int C, int Ca,
                     cudaStream_t stream);
-int gram_assemble_F(const float* G0, const bf16* Qb, const float* k3, int use_k3, bf16* EF, float* evec, int B, int C,
-                    int Ca, cudaStream_t stream);
 int gram_unpack_grads(const float* dwaug, const glf_grads* g, int C, int Ci, int Ca, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------ gate + concat
