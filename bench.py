@@ -162,11 +162,27 @@ def seeded_fusion(C: int, device):
     return f.to(device).train()
 
 
+def dot_algorithm(C: int) -> str:
+    """Which exact reassociation of mode='dot' libglf_sm100a runs for the bench shape (glf_api.cu: make_dims):
+    the Gram form when the sequences are long against the channel count (N >= 4 C), unless GLF_DOT_ALGO pins it."""
+    pin = int(os.environ.get("GLF_DOT_ALGO", "0"))
+    if pin in (1, 2):
+        return "token" if pin == 1 else "gram"
+    return "gram" if V * HH * WW >= 4 * C else "token"
+
+
 def algorithmic_work(clips: int, C: int):
-    """FLOPs of the algorithm actually executed (reassociated dot mode with W' = Wz M^T folded in), per step."""
+    """FLOPs of the algorithm actually executed, per step (both modules, fwd+bwd)."""
     N = V * HH * WW
     rows = clips * F * N
     Ci = C // 2
+    if dot_algorithm(C) == "gram":
+        # token-sized products: S = X^T X, U = X Q^T (fwd); R = dV^T X, dX = [dV | X][E ; F] (bwd) = 10 rows C^2;
+        # per-sequence [C x C] chain: 3 C^3 forward + 12 C^3 backward (in units of 2 C^3 FLOPs: 1.5 + 6)
+        big = 2 * rows * C * C * 5
+        small = clips * F * 15 * C * C * C
+        return 2 * (big + small), rows
+    # token-space form (W' = Wz M^T folded in)
     fwd = 2 * rows * C * 3 * Ci + 2 * rows * Ci * Ci + 2 * rows * Ci * C
     bwd = 2 * rows * C * Ci * 2 + 2 * rows * Ci * Ci * 2 + 2 * rows * 3 * Ci * C * 2
     small = clips * F * (2 * C * Ci * Ci) * 3
@@ -323,7 +339,8 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "BASELINE configs[1]: MGFM+MLFM modules only, 4 views x 16 frames x 28x28 tokens, "
                                f"C={C}, bf16 fwd+bwd, frames-as-batch (B={clips * F} sequences x N={V * HH * WW} tokens per GPU)",
-                   "clips_per_gpu_per_step": clips, "mode": "dot", "cuda_graph": bool(args.graph),
+                   "clips_per_gpu_per_step": clips, "mode": "dot", "dot_algorithm": dot_algorithm(C),
+                   "cuda_graph": bool(args.graph),
                    "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no flush" % (rows * C * 2 / 1e6),
                    "e2e_pipeline": "pinned host inputs; H2D of step i+1 on a copy stream overlaps compute of step i",
                    "parallelism": f"dp{world}"},
@@ -335,6 +352,8 @@ def run_ours(args):
         "peaks": pk,
     }
     out.update(kernel_probe(args, dev, clips, C, pk))
+    if dot_algorithm(C) == "gram":
+        out["roofline_secondary"] = gram_probe(dev, clips, C, pk)
     out["gpu_launches"] = count_launches(clips, C) * args.steps
     out["config"]["host_numa"] = (f"process bound to the {numa_cpus} CPUs local to its GPU (NVML affinity)"
                                   if numa_cpus else "no NUMA binding")
@@ -347,9 +366,15 @@ def run_ours(args):
 
 def count_launches(clips: int, C: int) -> int:
     """Kernels launched by libglf_sm100a per step (fwd+bwd, both modules + gate), counted from the orchestration in
-    glfusion_b200/csrc/glf_api.cu (memset/memcpy nodes excluded); agrees with profiles/r01_v11_launches.csv (39)."""
-    fwd_mod = 6          # prep_weights, proj GEMM, M GEMM, W' GEMM, U GEMM, bn_finalize
-    bwd_mod = 11         # finalize, apply, dTheta, dW', dWz, dM, dPhi, dG, dWcat, dX, bias-gradient reduction
+    glfusion_b200/csrc/glf_api.cu (memset/memcpy nodes excluded); agrees with profiles/r01_v11_launches.csv (39,
+    token-space form) and profiles/r01_v13_launches.csv (59, Gram form)."""
+    if dot_algorithm(C) == "gram":
+        fwd_mod = 10     # prep_weights, S GEMM, border, T, M, W', Q~ GEMMs, cvec, U GEMM, bn_finalize
+        bwd_mod = 17     # finalize, R GEMM, border, kprep, dQ~, dW', dW~theta, dWz, dM, dW~g, dT, dW~phi, G0, H GEMMs,
+        #                  assemble_F, dX GEMM, unpack_grads
+    else:
+        fwd_mod = 6      # prep_weights, proj GEMM, M GEMM, W' GEMM, U GEMM, bn_finalize
+        bwd_mod = 11     # finalize, apply, dTheta, dW', dWz, dM, dPhi, dG, dWcat, dX, bias-gradient reduction
     pair = 2             # fused MGFM+MLFM LayerNorm forward / backward
     gate = 3             # gate_concat fwd, gate_concat bwd, gate_finish
     return 2 * (fwd_mod + bwd_mod) + pair + gate
@@ -407,6 +432,41 @@ def kernel_probe(args, dev, clips, C, pk):
                          "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": traffic,
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": round(ms, 4),
                          "inputs": "7 x 205 MB per launch, larger than the 126 MB L2"}}
+
+
+def gram_probe(dev, clips, C, pk):
+    """The largest tensor-core product of the Gram form, timed alone: S_b = X_b^T X_b per sequence (token contraction,
+    both operands MN-major, fp32 accumulate, row sums as a side product).  2 N C^2 FLOPs per sequence over N C bf16
+    bytes = 256 FLOP/B at C = 256: above the ridge (1374.6 TFLOP/s / 6.538 TB/s = 210), so the bound is the tensor pipe."""
+    import ctypes as Ct
+    from glfusion_b200 import _lib as L
+    lib = L.load()
+    B, N = clips * F, V * HH * WW
+    X = torch.randn(B, N, C, device=dev).to(torch.bfloat16)
+    D = torch.empty(B, C, C, device=dev, dtype=torch.bfloat16)
+    rs = torch.empty(B, C, device=dev)
+    stream = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def launch():
+        L.check(lib.glf_gemm_bf16_ex(L.ptr(X), L.ptr(X), L.ptr(D), C, C, N, B, 1, 1, C, C, C, N * C, N * C, C * C,
+                                     None, 0, 1.0, 0, 1, L.ptr(rs), stream))
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 10
+    e0.record()
+    for _ in range(n):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    flops = 2.0 * B * N * C * C
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "gemm_kernel<1,1,128> (S = X^T X per sequence, + row sums)",
+            "achieved": round(ach, 1), "peak": pk["bf16_tflops"], "peak_source": pk["source"], "unit": "TFLOP/s",
+            "frac": round(ach / pk["bf16_tflops"], 4), "traffic": None,
+            "algorithmic_flops_per_launch": flops, "ms_per_launch": round(ms, 4)}
 
 
 # ------------------------------------------------------------------------------------------------------------------

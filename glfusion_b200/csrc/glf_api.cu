@@ -296,6 +296,20 @@ int check_ptr(const void* p, const char* name) {
 
 
 // ------------------------------------------------------------------------------------------------ Gram form of 'dot'
+// Tuning aids (GLF_GRAM_WIDE / GLF_GRAM_BIG = 128 | 256): N tile of the Ca-wide small products / of U and dX.
+// Measured on B200 at cfg2 (profiles/README.md): 128 / 128 is fastest (the 256-wide tile has only three ring stages
+// for four k-blocks per tile), so that is the default.
+int gram_wide_tile() {
+  const char* e = getenv("GLF_GRAM_WIDE");
+  const int v = e ? atoi(e) : 0;
+  return (v == 128 || v == 256) ? v : 128;
+}
+int gram_big_tile() {
+  const char* e = getenv("GLF_GRAM_BIG");
+  const int v = e ? atoi(e) : 0;
+  return (v == 128 || v == 256) ? v : 128;
+}
+
 // Token contraction of a sequence, S = A^T X (A = X or dV): both operands MN-major views of token-major
 // activations, the column sums of A as the GEMM's row-sum side product; result = the augmented bf16 matrix
 // [[S, colsum(A)], [rowv^T, corner]] of width Ca.  Enough sequences: the GEMM writes bf16 straight into it and a border
@@ -355,6 +369,7 @@ int tpavi_fwd_gram(const glf_desc* d, const Dims& m, const void* x, const glf_we
   const long long CaCa = static_cast<long long>(Ca) * Ca, CiCa = static_cast<long long>(Ci) * Ca;
   const long long CCa = static_cast<long long>(C) * Ca, CiCi = static_cast<long long>(Ci) * Ci;
   const long long CCi = static_cast<long long>(C) * Ci;
+  const int wide = gram_wide_tile();
   GLF_TRY(gram_prep_weights(w, C, Ci, Ca, s.waug, s.wz, stream));
   const bf16* X = reinterpret_cast<const bf16*>(x);
   if (m.pack_x) {
@@ -372,6 +387,7 @@ int tpavi_fwd_gram(const glf_desc* d, const Dims& m, const void* x, const glf_we
     g.B = opnd(s.Sa, 0, Ca, CaCa);
     g.B.rows = C1;
     g.M = Ci; g.N = Ca; g.K = C1; g.batch = B;
+    g.bn_hint = wide;
     g.D = s.T; g.ldd = Ca; g.strideD = CiCa;
     GLF_TRY(gemm(g, stream));
   }
@@ -398,6 +414,7 @@ int tpavi_fwd_gram(const glf_desc* d, const Dims& m, const void* x, const glf_we
     g.B = opnd(s.waug, 1, Ca, 0);
     g.B.rows = C1;
     g.M = C; g.N = Ca; g.K = Ci; g.batch = B;
+    g.bn_hint = wide;
     g.D = s.Qb; g.ldd = Ca; g.strideD = CCa;
     GLF_TRY(gemm(g, stream));
   }
@@ -408,6 +425,7 @@ int tpavi_fwd_gram(const glf_desc* d, const Dims& m, const void* x, const glf_we
     g.A = opnd(X, 0, C, static_cast<long long>(N) * C);
     g.B = opnd(s.Qb, 0, Ca, CCa);
     g.M = N; g.N = C; g.K = C; g.batch = B;
+    if (C % 256 == 0) g.bn_hint = gram_big_tile();
     g.bias = s.cvec; g.bias_stride = C;
     g.D = s.U; g.ldd = C; g.strideD = static_cast<long long>(N) * C;
     g.colstats = (d->training && d->bn_layer) ? wf.colstats : nullptr;
@@ -438,6 +456,7 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved&
   const long long CCa = static_cast<long long>(C) * Ca, CiCi = static_cast<long long>(Ci) * Ci;
   const long long CCi = static_cast<long long>(C) * Ci, CC = static_cast<long long>(C) * C;
   const float invN = 1.f / static_cast<float>(N);
+  const int wide = gram_wide_tile();   // N tile of the products whose output is Ca (= C + 8) columns wide
   const bool bn_train = d->bn_layer && d->training;   // k2, k3 != 0 only then
   // [[R_b, rv_b], [s_b^T, N]] with R_b = dV_b^T X_b, rv_b = dV_b^T 1
   GLF_TRY(gram_token_contraction(wb.dV, X, wb.Rb, wb.Rf, wb.rv, s.sfv, static_cast<float>(N), B, N, C, Ca, stream));
@@ -449,6 +468,7 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved&
     g.B = opnd(nullptr, 1, Ca, CaCa);
     g.B.rows = C1;
     g.M = C; g.N = Ca; g.K = C1; g.batch = B;
+    g.bn_hint = wide;
     g.D = wb.dQa; g.ldd = Ca; g.strideD = CCa;
     GLF_TRY(gemm_pair2(g, wb.AK, wb.AK + CCa, s.Sa, wb.Rb, stream));
   }
@@ -467,6 +487,7 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved&
     g.B = opnd(wb.dQa, 1, Ca, CCa);
     g.B.rows = C1;
     g.M = Ci; g.N = Ca; g.K = C; g.batch = B;
+    g.bn_hint = wide;
     g.out_kind = 2;
     g.D = wb.dwaug; g.ldd = Ca; g.strideD = 0;
     GLF_TRY(gemm(g, stream));
@@ -495,6 +516,7 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved&
     g.B = opnd(s.T, 1, Ca, CiCa);
     g.B.rows = C1;
     g.M = Ci; g.N = Ca; g.K = Ci; g.batch = B;
+    g.bn_hint = wide;
     g.alpha = invN;
     g.out_kind = 2;
     g.D = wb.dwaug + 2 * CiCa; g.ldd = Ca; g.strideD = 0;
@@ -506,6 +528,7 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved&
     g.B = opnd(s.waug + 2 * CiCa, 1, Ca, 0);
     g.B.rows = C1;
     g.M = Ci; g.N = Ca; g.K = Ci; g.batch = B;
+    g.bn_hint = wide;
     g.alpha = invN;
     g.D = wb.dT; g.ldd = Ca; g.strideD = CiCa;
     GLF_TRY(gemm(g, stream));
@@ -516,39 +539,41 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved&
     g.B = opnd(s.Sa, 0, Ca, CaCa);
     g.B.rows = C1;
     g.M = Ci; g.N = Ca; g.K = C1; g.batch = B;
+    g.bn_hint = wide;
     g.out_kind = 2;
     g.D = wb.dwaug + CiCa; g.ldd = Ca; g.strideD = 0;
     GLF_TRY(gemm(g, stream));
   }
-  {  // G0_b = dS~_b = W~phi^T dT_b           [C1 x Ca]
+  {  // G0_b = dS~_b[:C, :] = W_phi^T dT_b     [C x Ca]   (row C is only needed for e: formed in gram_assemble_F)
     GemmArgs g;
     g.A = opnd(s.waug + CiCa, 1, Ca, 0);
-    g.A.rows = C1;
     g.B = opnd(wb.dT, 1, Ca, CiCa);
     g.B.rows = C1;
-    g.M = C1; g.N = Ca; g.K = Ci; g.batch = B;
+    g.M = C; g.N = Ca; g.K = Ci; g.batch = B;
+    g.bn_hint = wide;
     g.out_kind = 1;
     g.D = wb.G0; g.ldd = Ca; g.strideD = CaCa;
     GLF_TRY(gemm(g, stream));
   }
-  if (bn_train) {  // H_b = Q~_b^T Qk_b   [C1 x Ca]  (dU Q = dV E + X H[:C,:C] + 1 H[:C,C]^T: the k2 U + k3 part of dU)
+  if (bn_train) {  // H_b = Q_b^T Qk_b    [C x Ca]  (dU Q = dV E + X H[:C,:C] + 1 H[:C,C]^T: the k2 U + k3 part of dU)
     GemmArgs g;
     g.A = opnd(s.Qb, 1, Ca, CCa);
-    g.A.rows = C1;
     g.B = opnd(wb.AK, 1, Ca, 2 * CCa);
     g.B.rows = C1;
-    g.M = C1; g.N = Ca; g.K = C; g.batch = B;
+    g.M = C; g.N = Ca; g.K = C; g.batch = B;
+    g.bn_hint = wide;
     g.out_kind = 1;
     g.D = wb.Hf; g.ldd = Ca; g.strideD = CaCa;
     GLF_TRY(gemm(g, stream));
   }
   // F = (G0 + G0^T + H)[:C, :C] ;  e = (G0[:, C] + G0[C, :] + H[:, C])[:C]
-  GLF_TRY(gram_assemble_F(wb.G0, bn_train ? wb.Hf : nullptr, wb.EF, wb.evec, B, C, Ca, stream));
+  GLF_TRY(gram_assemble_F(wb.G0, bn_train ? wb.Hf : nullptr, wb.dT, s.waug + CiCa, wb.EF, wb.evec, B, C, Ci, Ca, stream));
   {  // dX_b = dV_b E_b + X_b F_b + 1 e_b^T + dV_b
     GemmArgs g;
     g.A = opnd(nullptr, 0, C, static_cast<long long>(N) * C);
     g.B = opnd(nullptr, 1, C, 2 * CC);
     g.M = N; g.N = C; g.K = C; g.batch = B;
+    if (C % 256 == 0) g.bn_hint = gram_big_tile();
     g.bias = wb.evec; g.bias_stride = C;
     g.addend = wb.dV; g.ld_add = C; g.stride_add = static_cast<long long>(N) * C;
     g.D = m.pack_x ? static_cast<void*>(wb.dxtok) : dx; g.ldd = C; g.strideD = static_cast<long long>(N) * C;

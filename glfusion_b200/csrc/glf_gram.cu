@@ -127,10 +127,12 @@ __global__ void gram_kprep_kernel(const bf16* __restrict__ Qb, const float* __re
 }
 
 // F = (dS + dS^T + H)[:C, :C] -> EF[b][1]   (32 x 32 tiles, the transposed tile goes through shared memory);
-// e = (dS[:, C] + dS[C, :] + H[:, C])[:C]  (blocks of the first tile row also emit their 32 entries of e)
+// e = (dS[:, C] + dS[C, :] + H[:, C])[:C]  (blocks of the first tile row also emit their 32 entries of e; only rows
+// < C of dS and H are computed, the missing row dS[C, :] = b_phi^T dT is formed here)
 __global__ void __launch_bounds__(256)
-    gram_assemble_F_kernel(const float* __restrict__ G0, const float* __restrict__ Hf, bf16* __restrict__ EF,
-                           float* __restrict__ evec, int C, int Ca) {
+    gram_assemble_F_kernel(const float* __restrict__ G0, const float* __restrict__ Hf, const bf16* __restrict__ dT,
+                           const bf16* __restrict__ wphi, bf16* __restrict__ EF, float* __restrict__ evec, int C,
+                           int Ci, int Ca) {
   __shared__ float t[32][33];
   const long long b = blockIdx.z;
   const float* G = G0 + b * static_cast<long long>(Ca) * Ca;
@@ -156,9 +158,15 @@ __global__ void __launch_bounds__(256)
   if (blockIdx.y == 0 && ty == 0) {
     const int c = c0 + tx;
     if (c < C) {
-      float v = G[static_cast<long long>(c) * Ca + C] + G[static_cast<long long>(C) * Ca + c];
+      float v = G[static_cast<long long>(c) * Ca + C];
       if (H != nullptr) v += H[static_cast<long long>(c) * Ca + C];
-      evec[b * C + c] = v;
+      const bf16* dt = dT + b * static_cast<long long>(Ci) * Ca + c;
+      float a0 = 0.f, a1 = 0.f;
+      for (int i = 0; i < Ci; i += 2) {     // Ci % 8 == 0
+        a0 = fmaf(__bfloat162float(wphi[static_cast<long long>(i) * Ca + C]), __bfloat162float(dt[static_cast<long long>(i) * Ca]), a0);
+        a1 = fmaf(__bfloat162float(wphi[static_cast<long long>(i + 1) * Ca + C]), __bfloat162float(dt[static_cast<long long>(i + 1) * Ca]), a1);
+      }
+      evec[b * C + c] = v + a0 + a1;
     }
   }
 }
@@ -217,11 +225,11 @@ int gram_kprep(const bf16* Qb, const float* cvec, const float* k1, const float* 
   return check_cuda(cudaGetLastError(), "gram_kprep launch");
 }
 
-int gram_assemble_F(const float* G0, const float* Hf, bf16* EF, float* evec, int B, int C, int Ca,
-                    cudaStream_t stream) {
+int gram_assemble_F(const float* G0, const float* Hf, const bf16* dT, const bf16* wphi, bf16* EF, float* evec, int B,
+                    int C, int Ci, int Ca, cudaStream_t stream) {
   if (B > 65535) return set_error(GLF_ERR_INVALID, "gram form: more than 65535 sequences per call");
   dim3 grid((C + 31) / 32, (C + 31) / 32, B);
-  gram_assemble_F_kernel<<<grid, dim3(32, 8), 0, stream>>>(G0, Hf, EF, evec, C, Ca);
+  gram_assemble_F_kernel<<<grid, dim3(32, 8), 0, stream>>>(G0, Hf, dT, wphi, EF, evec, C, Ci, Ca);
   return check_cuda(cudaGetLastError(), "gram_assemble_F launch");
 }
 
