@@ -435,9 +435,10 @@ def kernel_probe(args, dev, clips, C, pk):
 
 
 def gram_probe(dev, clips, C, pk):
-    """The largest tensor-core product of the Gram form, timed alone: S_b = X_b^T X_b per sequence (token contraction,
-    both operands MN-major, fp32 accumulate, row sums as a side product).  2 N C^2 FLOPs per sequence over N C bf16
-    bytes = 256 FLOP/B at C = 256: above the ridge (1374.6 TFLOP/s / 6.538 TB/s = 210), so the bound is the tensor pipe."""
+    """The largest tensor-core product of the Gram form, timed alone: S_b = X_b^T X_b per sequence (glf_gramk.cu: one CTA
+    per sequence, operands streamed once, fp32 accumulate in TMEM, column sums on the side).  2 N C^2 FLOPs per sequence
+    over N C bf16 bytes = 256 FLOP/B at C = 256: above the ridge (1374.6 TFLOP/s / 6.538 TB/s = 210), so the bound is
+    the tensor pipe (the HBM time of the same launch is reported beside it)."""
     import ctypes as Ct
     from glfusion_b200 import _lib as L
     lib = L.load()
@@ -448,8 +449,7 @@ def gram_probe(dev, clips, C, pk):
     stream = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def launch():
-        L.check(lib.glf_gemm_bf16_ex(L.ptr(X), L.ptr(X), L.ptr(D), C, C, N, B, 1, 1, C, C, C, N * C, N * C, C * C,
-                                     None, 0, 1.0, 0, 1, L.ptr(rs), stream))
+        L.check(lib.glf_gram_contraction(L.ptr(X), L.ptr(X), L.ptr(D), L.ptr(rs), B, N, C, C, stream))
     for _ in range(3):
         launch()
     torch.cuda.synchronize()
@@ -463,10 +463,11 @@ def gram_probe(dev, clips, C, pk):
     ms = e0.elapsed_time(e1) / n
     flops = 2.0 * B * N * C * C
     ach = flops / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": "gemm_kernel<1,1,128> (S = X^T X per sequence, + row sums)",
+    return {"bound": "tensor", "kernel": "gram_kernel (S = X^T X per sequence, + column sums)",
             "achieved": round(ach, 1), "peak": pk["bf16_tflops"], "peak_source": pk["source"], "unit": "TFLOP/s",
             "frac": round(ach / pk["bf16_tflops"], 4), "traffic": None,
-            "algorithmic_flops_per_launch": flops, "ms_per_launch": round(ms, 4)}
+            "algorithmic_flops_per_launch": flops, "ms_per_launch": round(ms, 4),
+            "hbm_gbs_same_launch": round(B * N * C * 2 / (ms * 1e-3) / 1e9, 1)}
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -19,7 +19,7 @@ EXPORTS = ("glf_version", "glf_last_error", "glf_tpavi_sizes", "glf_tpavi_fwd", 
            "glf_gate_concat_fwd", "glf_gate_concat_bwd", "glf_gemm_bf16", "glf_transpose", "glf_bn_res_ln_fwd",
            "glf_bn_res_ln_bwd", "glf_bn_res_ln_bwd_max_blocks", "glf_gate_concat_bwd_scratch_bytes",
            "glf_fusion_ln_supported", "glf_fusion_ln_fwd", "glf_fusion_ln_bwd", "glf_bn_res_ln_pair_fwd",
-           "glf_bn_res_ln_pair_bwd", "glf_gemm_bf16_ex")
+           "glf_bn_res_ln_pair_bwd", "glf_gemm_bf16_ex", "glf_gram_contraction")
 
 
 class GlfDesc(C.Structure):
@@ -85,6 +85,7 @@ def load() -> C.CDLL:
                                       vp, i64, i64, i32, i32, vp, vp]
         lib.glf_gemm_bf16_ex.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, vp, i64,
                                          f32, i32, i32, vp, vp]
+        lib.glf_gram_contraction.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
         lib.glf_transpose.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
         lib.glf_bn_res_ln_fwd.argtypes = [i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, f32, i32, vp]
         lib.glf_bn_res_ln_bwd.argtypes = [i64, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,

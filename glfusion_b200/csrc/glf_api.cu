@@ -14,6 +14,7 @@
 // (tpavi_fwd_gram / tpavi_bwd_gram below; oracle/tpavi_oracle.py: tpavi_dot_gram_form): theta / phi / g and dU are never
 // materialised, the only token-sized products are S = X^T X, U = X Q^T, R = dV^T X and dX = [dV | X] [E ; F].
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 
@@ -316,6 +317,20 @@ int gram_big_tile() {
 // kernel adds the homogeneous row / column; few long sequences: split-K into fp32, then one assembling pass.
 int gram_token_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* scratch, float* rowsum, const float* rowv,
                            float corner, int B, int N, int C, int Ca, cudaStream_t stream) {
+  const char* ek = getenv("GLF_GRAM_KERNEL");   // tuning aid: 0 = always the generic tile GEMM
+  if (gram_contraction_supported(C) && !(ek && ek[0] == '0')) {
+    // one CTA per sequence; few long sequences are split along the tokens to fill two rounds of the SMs
+    int ks = 1;
+    if (B < 96) {
+      ks = (2 * 148) / B;
+      if (ks < 1) ks = 1;
+    }
+    GLF_TRY(gram_contraction(A, X, out_aug, scratch, rowsum, B, N, C, Ca, ks, stream));
+    const int kb = (N + 63) / 64;
+    if ((ks > kb ? kb : ks) > 1)
+      return gram_assemble_aug(scratch, rowsum, rowv ? rowv : rowsum, out_aug, B, C, Ca, corner, stream);
+    return gram_border(rowsum, rowv ? rowv : rowsum, out_aug, B, C, Ca, corner, stream);
+  }
   GemmArgs g;
   g.A = opnd(A, 1, C, static_cast<long long>(N) * C);
   g.B = opnd(X, 1, C, static_cast<long long>(N) * C);
@@ -1056,6 +1071,19 @@ GLF_API int glf_gemm_bf16_ex(const void* A, const void* B, void* D, int M, int N
   g.split_k = split_k;
   g.rowsum = rowsum; g.rowsum_stride = M;
   return gemm(g, reinterpret_cast<cudaStream_t>(stream));
+}
+
+GLF_API int glf_gram_contraction(const void* A, const void* X, void* D, float* colsum, int B, int N, int C, int ldd,
+                         glf_stream_t stream) {
+  GLF_TRY(check_device_sm100());
+  GLF_TRY(check_ptr(A, "A"));
+  GLF_TRY(check_ptr(X, "X"));
+  GLF_TRY(check_ptr(D, "D"));
+  GLF_TRY(check_ptr(colsum, "colsum"));
+  if (B <= 0 || N <= 0) return set_error(GLF_ERR_INVALID, "gram_contraction: empty input");
+  if (ldd < C || ldd % 8 != 0) return set_error(GLF_ERR_INVALID, "gram_contraction: ldd must be >= C and a multiple of 8");
+  return gram_contraction(reinterpret_cast<const bf16*>(A), reinterpret_cast<const bf16*>(X), reinterpret_cast<bf16*>(D),
+                          nullptr, colsum, B, N, C, ldd, 1, reinterpret_cast<cudaStream_t>(stream));
 }
 
 GLF_API int glf_bn_res_ln_fwd(int64_t rows, int C, const void* U, const void* X, const float* bn_a, const float* bn_b,

@@ -53,17 +53,18 @@ __global__ void gram_assemble_aug_kernel(const float* __restrict__ Mf, const flo
 }
 
 // Border of an augmented matrix whose [C x C] block a GEMM already wrote in bf16: column C = colv, row C = rowv,
-// corner, zero padding.  One block per batch entry.
+// corner, zero padding.  grid = (batch, 8).
 __global__ void gram_border_kernel(const float* __restrict__ colv, const float* __restrict__ rowv,
                                    bf16* __restrict__ out, int C, int Ca, float corner) {
   const long long b = blockIdx.x;
   bf16* M = out + b * static_cast<long long>(Ca) * Ca;
   const int pad = Ca - C;
-  for (int i = threadIdx.x; i < C * pad; i += blockDim.x) {        // columns C.. of rows < C
+  const int tid = blockIdx.y * blockDim.x + threadIdx.x, nth = gridDim.y * blockDim.x;
+  for (int i = tid; i < C * pad; i += nth) {        // columns C.. of rows < C
     const int r = i / pad, j = C + i % pad;
     M[static_cast<long long>(r) * Ca + j] = __float2bfloat16(j == C ? colv[b * C + r] : 0.f);
   }
-  for (int i = threadIdx.x; i < pad * Ca; i += blockDim.x) {       // rows C..
+  for (int i = tid; i < pad * Ca; i += nth) {       // rows C..
     const int r = C + i / Ca, j = i % Ca;
     float v = 0.f;
     if (r == C) v = j < C ? rowv[b * C + j] : (j == C ? corner : 0.f);
@@ -155,18 +156,23 @@ __global__ void __launch_bounds__(256)
       F[static_cast<long long>(rr) * C + cc] = __float2bfloat16(v);
     }
   }
-  if (blockIdx.y == 0 && ty == 0) {
+  if (blockIdx.y == 0) {     // block-uniform: the first tile row also emits e for its 32 columns
+    __shared__ float part[8][33];
     const int c = c0 + tx;
+    float a0 = 0.f;
     if (c < C) {
+      const bf16* dt = dT + b * static_cast<long long>(Ci) * Ca + c;
+      for (int i = ty; i < Ci; i += 8)
+        a0 = fmaf(__bfloat162float(wphi[static_cast<long long>(i) * Ca + C]), __bfloat162float(dt[static_cast<long long>(i) * Ca]), a0);
+    }
+    part[ty][tx] = a0;
+    __syncthreads();
+    if (ty == 0 && c < C) {
       float v = G[static_cast<long long>(c) * Ca + C];
       if (H != nullptr) v += H[static_cast<long long>(c) * Ca + C];
-      const bf16* dt = dT + b * static_cast<long long>(Ci) * Ca + c;
-      float a0 = 0.f, a1 = 0.f;
-      for (int i = 0; i < Ci; i += 2) {     // Ci % 8 == 0
-        a0 = fmaf(__bfloat162float(wphi[static_cast<long long>(i) * Ca + C]), __bfloat162float(dt[static_cast<long long>(i) * Ca]), a0);
-        a1 = fmaf(__bfloat162float(wphi[static_cast<long long>(i + 1) * Ca + C]), __bfloat162float(dt[static_cast<long long>(i + 1) * Ca]), a1);
-      }
-      evec[b * C + c] = v + a0 + a1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v += part[i][tx];
+      evec[b * C + c] = v;
     }
   }
 }
@@ -208,7 +214,7 @@ int gram_assemble_aug(const float* Mf, const float* colv, const float* rowv, bf1
 
 int gram_border(const float* colv, const float* rowv, bf16* out, int B, int C, int Ca, float corner,
                 cudaStream_t stream) {
-  gram_border_kernel<<<B, 256, 0, stream>>>(colv, rowv, out, C, Ca, corner);
+  gram_border_kernel<<<dim3(B, 8), 256, 0, stream>>>(colv, rowv, out, C, Ca, corner);
   return check_cuda(cudaGetLastError(), "gram_border launch");
 }
 

@@ -1,0 +1,217 @@
+// glf_gramk.cu — token contraction of the Gram form: per sequence b,  D_b = A_b^T X_b  ([C x C], C = 128 or 256) with
+// A = X (S = X^T X, forward) or A = dV (R = dV^T X, backward), plus the column sums of A.
+//
+// The generic tile GEMM (glf_gemm.cu) computes this product as four 128 x 128 tiles per sequence, so every 64-token
+// block of A and X is pulled from L2 twice and the kernel ends up bound by the L2 -> SM fabric (ncu: tensor pipe 43 %,
+// DRAM 31 %, profiles/r01_gram_gemm_ncu_brief.txt).  Here ONE CTA owns a whole sequence (or a K split of it): each
+// 64-token block [64 x C] of A and of X is loaded exactly once (TMA, SWIZZLE_128B, MN-major), the C x C fp32 result
+// lives in TMEM (C = 256: two 128-lane accumulators x 256 columns = all 512 columns), and the operands are read
+// straight from HBM once: the S product is tensor-bound, the R product HBM-bound (two inputs).
+//
+//   warp 0      TMA producer: per k-block C/64 boxes of A (+ C/64 boxes of X unless A == X) into a 3-stage ring
+//   warp 1      MMA issuer: tcgen05.mma M=128, N=C, K=16, both operands MN-major, C/128 accumulators
+//   warps 2..9  during the main loop: column sums of A read from the staged blocks (thread = channel); afterwards the
+//               epilogue: tcgen05.ld -> bf16 rows of the augmented [Ca x Ca] matrix, or fp32 red.add for split-K
+#include "glf_internal.h"
+#include "glf_ptx.cuh"
+
+namespace glf {
+
+namespace {
+
+constexpr int GK_THREADS = 64 + 256;
+constexpr int GK_STAGES = 3;
+constexpr uint32_t GK_BLK = 64 * 256 * 2;          // one operand block: 64 tokens x 256 channels (4 boxes of 64 x 64)
+constexpr uint32_t GK_STAGE = 2 * GK_BLK;          // A block + X block
+constexpr uint32_t GK_SMEM = GK_STAGES * GK_STAGE + 1024;
+
+struct GramKParams {
+  int B, N, C, Ca;
+  int ksplit, kb_total, kb_per_split;
+  int same;        // A == X: the X block is not loaded, the B operand is the A block
+  bf16* out;       // ksplit == 1: [B][Ca][Ca] bf16, rows/cols < C written
+  float* outf;     // ksplit  > 1: [B][C][C] fp32, atomically accumulated (zeroed by the caller)
+  float* rowsum;   // [B][C] column sums of A (stored, or atomically accumulated when ksplit > 1)
+};
+
+__global__ void __launch_bounds__(GK_THREADS, 1)
+    gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmX, const GramKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[GK_STAGES];
+  __shared__ uint64_t empty_bar[GK_STAGES];
+  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_holder;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x / p.ksplit;
+  const int split = blockIdx.x - b * p.ksplit;
+  const int kb0 = split * p.kb_per_split;
+  const int nkb = min(p.kb_total, kb0 + p.kb_per_split) - kb0;
+  const int nbox = p.C / 64;     // 64-channel boxes per block
+  const int MT = p.C / 128;      // 128-row accumulators
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmX);
+#pragma unroll
+    for (int s = 0; s < GK_STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1 + 8);   // MMA commit + the eight column-sum warps
+    }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_holder), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t bytes = static_cast<uint32_t>(nbox) * 8192u * (p.same ? 1u : 2u);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < nkb; ++it) {
+        const int k0 = (kb0 + it) * 64;
+        const uint32_t fb = smem_u32(&full_bar[stage]);
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+        mbar_expect_tx(fb, bytes);
+        const uint32_t sa = smem_base + stage * GK_STAGE;
+        for (int j = 0; j < nbox; ++j) tma_load_4d(&tmA, fb, sa + j * 8192, j * 64, k0, b, 0);
+        if (!p.same)
+          for (int j = 0; j < nbox; ++j) tma_load_4d(&tmX, fb, sa + GK_BLK + j * 8192, j * 64, k0, b, 0);
+        if (++stage == GK_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, p.C, true, true);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < nkb; ++it) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * GK_STAGE;
+        const uint32_t sb = p.same ? sa : sa + GK_BLK;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t bd = make_sdesc(sb + k * 2048, 8192, 1024);
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t ad = make_sdesc(sa + mt * 16384 + k * 2048, 8192, 1024);
+            umma_f16(tmem_base + mt * p.C, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(smem_u32(&empty_bar[stage]));
+        if (++stage == GK_STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(smem_u32(&tmem_full_bar));
+    }
+  } else {
+    // ---- column sums of A from the staged blocks: thread t = channel t
+    const int t = threadIdx.x - 64;
+    {
+      const uint32_t off0 = static_cast<uint32_t>(t >> 6) * 8192u + static_cast<uint32_t>(t & 7) * 2u;
+      const uint32_t chunk = static_cast<uint32_t>((t & 63) >> 3);
+      float acc0 = 0.f, acc1 = 0.f;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < nkb; ++it) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        if (t < p.C) {
+          const uint8_t* blk = smem_gen + stage * GK_STAGE + off0;
+#pragma unroll 8
+          for (int k = 0; k < 64; k += 2) {
+            acc0 += __bfloat162float(*reinterpret_cast<const bf16*>(blk + k * 128 + ((chunk ^ (k & 7)) << 4)));
+            acc1 += __bfloat162float(*reinterpret_cast<const bf16*>(blk + (k + 1) * 128 + ((chunk ^ ((k + 1) & 7)) << 4)));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));
+        if (++stage == GK_STAGES) { stage = 0; phase ^= 1u; }
+      }
+      if (t < p.C) {
+        float* dst = p.rowsum + static_cast<long long>(b) * p.C + t;
+        if (p.ksplit > 1) atomicAdd(dst, acc0 + acc1);
+        else *dst = acc0 + acc1;
+      }
+    }
+    // ---- epilogue: warp (mt, q) owns TMEM lanes 32q..32q+31 of accumulator mt = output rows 128 mt + 32 q + lane
+    const int q = warp & 3;
+    const int mt = (warp - 2) >> 2;
+    mbar_wait(smem_u32(&tmem_full_bar), 0);
+    tc_fence_after();
+    if (mt < MT) {
+      const int row = mt * 128 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + mt * p.C + (static_cast<uint32_t>(q * 32) << 16);
+      for (int c = 0; c < p.C / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        if (p.ksplit > 1) {
+          float* dst = p.outf + (static_cast<long long>(b) * p.C + row) * p.C + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                         "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                         : "memory");
+        } else {
+          bf16* dst = p.out + (static_cast<long long>(b) * p.Ca + row) * p.Ca + c * 32;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 pk = make_uint4(pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                                        pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                                        pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                                        pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+            *reinterpret_cast<uint4*>(dst + 8 * j) = pk;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+bool gram_contraction_supported(int C) { return C == 128 || C == 256; }
+
+// out_aug rows / columns < C (bf16, ld = Ca) when ksplit == 1, else fp32 accumulation into `scratch` (zeroed here);
+// rowsum = column sums of A.  The caller adds the homogeneous border (gram_border / gram_assemble_aug).
+int gram_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* scratch, float* rowsum, int B, int N, int C,
+                     int Ca, int ksplit, cudaStream_t stream) {
+  if (!gram_contraction_supported(C)) return set_error(GLF_ERR_UNSUPPORTED, "gram_contraction: C must be 128 or 256");
+  CUtensorMap tmA, tmX;
+  int rc = make_tmap_bf16(&tmA, A, C, N, B, C, static_cast<long long>(N) * C, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tmX, X, C, N, B, C, static_cast<long long>(N) * C, 64);
+  if (rc) return rc;
+  GramKParams p;
+  p.B = B; p.N = N; p.C = C; p.Ca = Ca;
+  p.kb_total = (N + 63) / 64;
+  int ks = ksplit < 1 ? 1 : ksplit;
+  if (ks > p.kb_total) ks = p.kb_total;
+  p.kb_per_split = (p.kb_total + ks - 1) / ks;
+  p.ksplit = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.same = (A == X) ? 1 : 0;
+  p.out = out_aug; p.outf = scratch; p.rowsum = rowsum;
+  if (p.ksplit > 1) {
+    rc = check_cuda(cudaMemsetAsync(scratch, 0, sizeof(float) * B * C * C, stream), "memset S");
+    if (rc) return rc;
+    rc = check_cuda(cudaMemsetAsync(rowsum, 0, sizeof(float) * B * C, stream), "memset s");
+    if (rc) return rc;
+  }
+  cudaError_t e = cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GK_SMEM);
+  if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gram)");
+  const long long grid = static_cast<long long>(B) * p.ksplit;
+  if (grid > 0x7fffffffLL) return set_error(GLF_ERR_INVALID, "gram_contraction: too many work items");
+  gram_kernel<<<static_cast<int>(grid), GK_THREADS, GK_SMEM, stream>>>(tmA, tmX, p);
+  return check_cuda(cudaGetLastError(), "gram_contraction launch");
+}
+
+}  // namespace glf

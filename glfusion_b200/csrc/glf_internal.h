@@ -109,6 +109,10 @@ int gram_kprep(const bf16* Qb, const float* cvec, const float* k1, const float* 
                int B, int C, int Ca, cudaStream_t stream);
 int gram_assemble_F(const float* G0, const float* Hf, const bf16* dT, const bf16* wphi, bf16* EF, float* evec, int B,
                     int C, int Ci, int Ca, cudaStream_t stream);
+// One CTA per sequence (glf_gramk.cu): D_b = A_b^T X_b for C = 128 / 256, operands streamed once
+bool gram_contraction_supported(int C);
+int gram_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* scratch, float* rowsum, int B, int N, int C,
+                     int Ca, int ksplit, cudaStream_t stream);
 int gram_unpack_grads(const float* dwaug, const glf_grads* g, int C, int Ci, int Ca, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------ gate + concat

@@ -181,6 +181,12 @@ GLF_API int glf_gemm_bf16_ex(const void* A, const void* B, void* D, int M, int N
                      const float* bias, int64_t bias_stride, float alpha, int out_kind, int split_k, float* rowsum,
                      glf_stream_t stream);
 
+/* Token contraction of the Gram form, one CTA per sequence (C = 128 or 256; unit tests, roofline probe):
+ *   D[b] = A[b]^T X[b]  with A, X: [B, N, C] bf16 token-major;  D: [B, ldd, ldd] bf16, rows / columns < C written
+ *   (ldd >= C, ldd % 8 == 0);  colsum: [B, C] fp32 column sums of A.  A == X gives the Gram matrix S = X^T X. */
+GLF_API int glf_gram_contraction(const void* A, const void* X, void* D, float* colsum, int B, int N, int C, int ldd,
+                         glf_stream_t stream);
+
 /* The two HBM-bound fused epilogues as standalone entry points (unit tests, roofline probes).
  *   fwd: Z = LayerNorm_C(bn_a * U + bn_b + X) * ln_w + ln_b   (ours.py:908-915 after the W_z GEMM); U, X bf16 [rows, C];
  *        Z [rows, C] of z_dtype; mu, r: per-row LayerNorm mean / rstd (kept for backward).

@@ -129,3 +129,20 @@ def test_gemm_per_batch_bias():
     torch.cuda.synchronize()
     ref = torch.einsum("bmk,bnk->bmn", A.float(), Bm.float()) + bias[:, None, :]
     assert O.rel_err(D, ref) < 6e-3
+
+
+@pytest.mark.parametrize("C,N,B,same", [(256, 3136, 5, True), (128, 200, 3, False), (256, 130, 150, False)])
+def test_gram_contraction_kernel(C, N, B, same):
+    """One CTA per sequence: D_b = A_b^T X_b and the column sums of A (ragged token counts, ring wrap, > 148 CTAs)."""
+    torch.manual_seed(7)
+    X = torch.randn(B, N, C, device=DEV).to(torch.bfloat16)
+    A = X if same else torch.randn(B, N, C, device=DEV).to(torch.bfloat16)
+    ldd = C + 8
+    D = torch.zeros(B, ldd, ldd, device=DEV, dtype=torch.bfloat16)
+    cs = torch.zeros(B, C, device=DEV)
+    L.check(L.load().glf_gram_contraction(L.ptr(A), L.ptr(X), L.ptr(D), L.ptr(cs), B, N, C, ldd, stream()))
+    torch.cuda.synchronize()
+    ref = torch.einsum("bnm,bnk->bmk", A.float(), X.float())
+    assert O.rel_err(D[:, :C, :C], ref) < 4e-3          # bf16 rounding of the stored result
+    assert float(D[:, C:, :].abs().max()) == 0 and float(D[:, :, C:].abs().max()) == 0   # border untouched
+    assert O.rel_err(cs, A.float().sum(1)) < 1e-5

@@ -77,6 +77,26 @@ def test_oracle_dot_layouts(layout, algo):
             assert_close("grad:" + k, pp.grad, go[k], 3e-2, abs_floor=1e-3)
 
 
+@pytest.mark.parametrize("C", [128, 256, 64])
+def test_gram_many_sequences(C):
+    """>= 96 sequences: the Gram form runs one CTA per sequence with no token split (bf16 results written straight
+    into the augmented matrices); 4 k-blocks per sequence wrap the 3-stage ring.  C = 64 takes the generic tile GEMM."""
+    B, T, H, W = 96, 4, 8, 8
+    p = O.init_params(C, seed=51, randomize_affine=True)
+    gen = torch.Generator().manual_seed(52)
+    x = torch.randn(B, C, T, H, W, generator=gen)
+    dz = torch.randn(B, C, T, H, W, generator=gen)
+    zo, dxo, go = O.tpavi_fwd_bwd(x, dz, {k: v.clone() for k, v in p.items()}, mode="dot")
+    m = load_module_from_params(TPAVIModule, p, C, "dot", True).train()
+    with dot_algo("gram"):
+        z, dx = _run(m, x.to(DEV, torch.bfloat16), dz.to(DEV, torch.bfloat16))
+    assert_close("z", z, zo, BF16_TOL)
+    assert_close("dx", dx, dxo, BF16_TOL)
+    for k, pp in m.named_parameters():
+        if not k.startswith("align_channel"):
+            assert_close("grad:" + k, pp.grad, go[k], 3e-2, abs_floor=1e-3)
+
+
 def test_eval_no_grad_inference_and_zero_init_trap():
     C = 128
     m = TPAVIModule(C).to(DEV).eval()          # reference init: BN gamma=beta=0 -> z == LayerNorm(x) exactly (F3)
