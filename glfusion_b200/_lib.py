@@ -19,7 +19,8 @@ EXPORTS = ("glf_version", "glf_last_error", "glf_tpavi_sizes", "glf_tpavi_fwd", 
            "glf_gate_concat_fwd", "glf_gate_concat_bwd", "glf_gemm_bf16", "glf_transpose", "glf_bn_res_ln_fwd",
            "glf_bn_res_ln_bwd", "glf_bn_res_ln_bwd_max_blocks", "glf_gate_concat_bwd_scratch_bytes",
            "glf_fusion_ln_supported", "glf_fusion_ln_fwd", "glf_fusion_ln_bwd", "glf_bn_res_ln_pair_fwd",
-           "glf_bn_res_ln_pair_bwd", "glf_gemm_bf16_ex", "glf_gram_contraction")
+           "glf_bn_res_ln_pair_bwd", "glf_gemm_bf16_ex", "glf_gram_contraction", "glf_p2p_signal_bytes", "glf_p2p_max_floats",
+           "glf_p2p_export", "glf_p2p_open", "glf_p2p_close", "glf_p2p_allreduce")
 
 
 class GlfDesc(C.Structure):
@@ -86,6 +87,14 @@ def load() -> C.CDLL:
         lib.glf_gemm_bf16_ex.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, vp, i64,
                                          f32, i32, i32, vp, vp]
         lib.glf_gram_contraction.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
+        lib.glf_p2p_signal_bytes.argtypes = [i32]
+        lib.glf_p2p_signal_bytes.restype = C.c_size_t
+        lib.glf_p2p_max_floats.argtypes = []
+        lib.glf_p2p_max_floats.restype = C.c_int64
+        lib.glf_p2p_export.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint64)]
+        lib.glf_p2p_open.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        lib.glf_p2p_close.argtypes = [vp, C.c_uint64]
+        lib.glf_p2p_allreduce.argtypes = [pp, pp, i32, i32, i64, f32, vp]
         lib.glf_transpose.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
         lib.glf_bn_res_ln_fwd.argtypes = [i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, f32, i32, vp]
         lib.glf_bn_res_ln_bwd.argtypes = [i64, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
@@ -93,7 +102,8 @@ def load() -> C.CDLL:
         lib.glf_bn_res_ln_bwd_max_blocks.argtypes = []
         for name in EXPORTS:
             fn = getattr(lib, name)
-            if name not in ("glf_last_error", "glf_gate_concat_bwd_scratch_bytes"):
+            if name not in ("glf_last_error", "glf_gate_concat_bwd_scratch_bytes", "glf_p2p_signal_bytes",
+                            "glf_p2p_max_floats"):
                 fn.restype = C.c_int
         _lib = lib
         return lib

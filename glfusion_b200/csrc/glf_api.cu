@@ -1032,6 +1032,30 @@ GLF_API size_t glf_gate_concat_bwd_scratch_bytes(int B, int C, int V, int h, int
   return gate_bwd_scratch_bytes(B, C, V, h, w);
 }
 
+GLF_API size_t glf_p2p_signal_bytes(int world) { return p2p_signal_bytes(world); }
+GLF_API int64_t glf_p2p_max_floats(void) { return p2p_max_floats(); }
+GLF_API int glf_p2p_export(const void* ptr, unsigned char handle[64], uint64_t* offset) {
+  if (ptr == nullptr || handle == nullptr || offset == nullptr) return set_error(GLF_ERR_INVALID, "p2p_export: NULL argument");
+  unsigned long long off = 0;
+  GLF_TRY(p2p_export(ptr, handle, &off));
+  *offset = off;
+  return 0;
+}
+GLF_API int glf_p2p_open(const unsigned char handle[64], uint64_t offset, void** out) {
+  if (handle == nullptr || out == nullptr) return set_error(GLF_ERR_INVALID, "p2p_open: NULL argument");
+  return p2p_open(handle, offset, out);
+}
+GLF_API int glf_p2p_close(void* ptr, uint64_t offset) {
+  if (ptr == nullptr) return set_error(GLF_ERR_INVALID, "p2p_close: NULL argument");
+  return p2p_close(ptr, offset);
+}
+GLF_API int glf_p2p_allreduce(void* const* bufs, void* const* sigs, int rank, int world, int64_t n, float scale,
+                      glf_stream_t stream) {
+  GLF_TRY(check_device_sm100());
+  if (bufs == nullptr || sigs == nullptr) return set_error(GLF_ERR_INVALID, "p2p_allreduce: NULL pointer table");
+  return p2p_allreduce(bufs, sigs, rank, world, n, scale, reinterpret_cast<cudaStream_t>(stream));
+}
+
 GLF_API int glf_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int batch, int a_mn, int b_mn,
                   int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
                   const float* bias, float alpha, const void* addend, int64_t ld_add, int64_t stride_add,

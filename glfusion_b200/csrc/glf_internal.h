@@ -137,6 +137,16 @@ int flash_bwd(const bf16* P, const bf16* Y, const bf16* dY, const float* lse, bf
               float* cs_p, float* cs_g, int cs_cap_rows, int* cs_rows_out, int B, int N, int Ci, void* scratch,
               cudaStream_t stream);
 
+// ------------------------------------------------------------------------------------------------ P2P all-reduce (glf_p2p.cu)
+int p2p_grid(long long n_floats);
+long long p2p_max_floats();
+size_t p2p_signal_bytes(int world);
+int p2p_allreduce(void* const* bufs, void* const* sigs, int rank, int world, long long n_floats, float scale,
+                  cudaStream_t stream);
+int p2p_export(const void* ptr, unsigned char handle[64], unsigned long long* offset);
+int p2p_open(const unsigned char handle[64], unsigned long long offset, void** out);
+int p2p_close(void* ptr, unsigned long long offset);
+
 // ------------------------------------------------------------------------------------------------ F32X3 precision arm
 int tpavi_sizes_f32x3(const glf_desc* d, glf_sizes* out);
 int tpavi_fwd_f32x3(const glf_desc* d, const void* x, const glf_weights* w, void* z, void* saved, void* ws,

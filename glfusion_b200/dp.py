@@ -35,7 +35,11 @@ def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 class GradBucket:
-    """Flat fp32 bucket over a fixed parameter list: gradients are packed, all-reduced once, averaged, unpacked."""
+    """Flat fp32 bucket over a fixed parameter list: gradients are packed, all-reduced once, averaged, unpacked.
+
+    On CUDA the bucket sits behind a zero-initialised signal pad in one device allocation, so that `enable_p2p` can
+    expose it to the other ranks through CUDA IPC; the average is then ONE kernel over NVLink / NVSwitch peer memory
+    (`glf_p2p_allreduce`, csrc/glf_p2p.cu) instead of an NCCL call, and can be captured in the step's CUDA graph."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
@@ -43,7 +47,16 @@ class GradBucket:
             raise ValueError("no trainable parameters")
         self.numel = sum(p.numel() for p in self.params)
         dev = self.params[0].device
-        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self._p2p = None
+        self._raw = None
+        if dev.type == "cuda":
+            from . import _lib as L
+            self._sig_bytes = (int(L.load().glf_p2p_signal_bytes(8)) + 255) // 256 * 256
+            self._n_pad = (self.numel + 3) // 4 * 4
+            self._raw = torch.zeros(self._sig_bytes + 4 * self._n_pad, dtype=torch.uint8, device=dev)
+            self.flat = self._raw[self._sig_bytes:].view(torch.float32)[:self.numel]
+        else:
+            self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
         # views of the flat bucket, one per parameter: pack / unpack are single multi-tensor copies
         self.views: List[torch.Tensor] = []
         off = 0
@@ -92,11 +105,68 @@ class GradBucket:
             else:
                 p.grad.copy_(v)
 
+    def enable_p2p(self, group=None) -> bool:
+        """Exchange CUDA IPC handles of the bucket allocation with the other ranks of `group` (one node, <= 8 GPUs).
+        Returns True when every rank can reach every bucket; otherwise the NCCL path stays in use."""
+        if self._raw is None or not (dist.is_initialized() and dist.get_world_size(group) > 1):
+            return False
+        import ctypes as C
+        from . import _lib as L
+        lib = L.load()
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        ok = 2 <= world <= 8 and self._n_pad <= int(lib.glf_p2p_max_floats())
+        mine = None
+        if ok:
+            handle = C.create_string_buffer(64)
+            off = C.c_uint64(0)
+            with torch.cuda.device(self._raw.device):
+                rc = lib.glf_p2p_export(L.ptr(self._raw), handle, C.byref(off))
+            ok = rc == 0
+            mine = (handle.raw, int(off.value))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine if ok else None, group=group)
+        if any(g is None for g in gathered):
+            return False
+        bases = []
+        opened_all = True
+        for r, (h, o) in enumerate(gathered):
+            if r == rank:
+                bases.append(self._raw.data_ptr())
+                continue
+            out = C.c_void_p(0)
+            with torch.cuda.device(self._raw.device):
+                rc = lib.glf_p2p_open(h, C.c_uint64(o), C.byref(out))
+            if rc != 0 or not out.value:
+                opened_all = False
+                bases.append(0)
+            else:
+                bases.append(int(out.value))
+        flags = [None] * world
+        dist.all_gather_object(flags, opened_all, group=group)
+        if not all(flags):
+            return False
+        sigs = (C.c_void_p * world)(*bases)
+        bufs = (C.c_void_p * world)(*[b + self._sig_bytes for b in bases])
+        self._p2p = (bufs, sigs, rank, world)
+        dist.barrier(group=group)
+        return True
+
+    @property
+    def p2p_enabled(self) -> bool:
+        return self._p2p is not None
+
     def allreduce_mean(self, group=None) -> None:
         zero_copy = self.aliased()
         if not zero_copy:
             self.pack()
-        if dist.is_initialized() and dist.get_world_size(group) > 1:
+        if self._p2p is not None:
+            import ctypes as C
+            from . import _lib as L
+            bufs, sigs, rank, world = self._p2p
+            with torch.cuda.device(self._raw.device):
+                L.check(L.load().glf_p2p_allreduce(bufs, sigs, rank, world, self._n_pad, 1.0 / world,
+                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        elif dist.is_initialized() and dist.get_world_size(group) > 1:
             if dist.get_backend(group) == "nccl":
                 dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)     # one kernel: sum and 1/world
             else:

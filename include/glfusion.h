@@ -157,6 +157,22 @@ GLF_API int glf_gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, flo
                         const void* dxg, const void* dxl, void* const* df4, float* const* dcls, float* const* dctr,
                         void* scratch, glf_stream_t stream);
 
+/* ---- data-parallel gradient exchange (replaces nn.DataParallel's reduce onto GPU 0, R/main.py:155) ----------------
+ * One kernel over NVLink / NVSwitch peer memory: every rank (one process per GPU) keeps its flat fp32 gradient bucket
+ * in a device allocation that the other ranks have opened through CUDA IPC, preceded by a zero-initialised signal pad
+ * of glf_p2p_signal_bytes(world) bytes.  glf_p2p_allreduce replaces every rank's bucket, in place, by
+ * scale * (sum over ranks), bitwise identical on all ranks; it is CUDA-graph capturable (no host-side state).
+ *   setup:  glf_p2p_export(ptr) -> (64-byte handle, offset) on the owner;  glf_p2p_open(handle, offset) on the peers
+ *   bufs / sigs: HOST arrays of `world` device pointers (own pointer at index `rank`)
+ *   n: floats, multiple of 4, <= glf_p2p_max_floats();  world 2..8;  every rank must call with the same n */
+GLF_API size_t glf_p2p_signal_bytes(int world);
+GLF_API int64_t glf_p2p_max_floats(void);
+GLF_API int glf_p2p_export(const void* ptr, unsigned char handle[64], uint64_t* offset);
+GLF_API int glf_p2p_open(const unsigned char handle[64], uint64_t offset, void** out);
+GLF_API int glf_p2p_close(void* ptr, uint64_t offset);
+GLF_API int glf_p2p_allreduce(void* const* bufs, void* const* sigs, int rank, int world, int64_t n, float scale,
+                      glf_stream_t stream);
+
 /* ---- building blocks, exported for unit tests and for callers that fuse differently ------------------------ */
 
 /* D[b] = alpha * A[b] * B[b]^T (+ bias[n]) (+ addend) on tcgen05 tensor cores, bf16 operands, fp32 accumulate.
