@@ -502,9 +502,15 @@ def gram_probe(dev, clips, C, pk):
     ms = e0.elapsed_time(e1) / n
     flops = 2.0 * B * N * C * C
     ach = flops / (ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        t = json.load(open(tp)).get("secondary", {})
+        if t.get("rows") == B * N and t.get("C") == C and t.get("kernel") == "gram_kernel":
+            traffic = int(t["traffic_bytes"])
     return {"bound": "tensor", "kernel": "gram_kernel (S = X^T X per sequence, + column sums)",
             "achieved": round(ach, 1), "peak": pk["bf16_tflops"], "peak_source": pk["source"], "unit": "TFLOP/s",
-            "frac": round(ach / pk["bf16_tflops"], 4), "traffic": None,
+            "frac": round(ach / pk["bf16_tflops"], 4), "traffic": traffic,
             "algorithmic_flops_per_launch": flops, "ms_per_launch": round(ms, 4),
             "hbm_gbs_same_launch": round(B * N * C * 2 / (ms * 1e-3) / 1e9, 1)}
 
