@@ -55,11 +55,15 @@ struct GemmKParams {
   long long rowsum_stride;
 };
 
-template <int BN>
+// MT = 128-row accumulators per CTA tile: MT = 2 computes a 256 x BN super-tile, so each k-block of the B operand is
+// loaded once per 256 output rows instead of once per 128 (the big K-major products at C = 256 are bound by L2 -> SM
+// traffic, not by HBM or the tensor pipe; profiles/r01_gram_gemm_ncu_brief.txt)
+template <int BN, int MT = 1>
 struct GemmCfg {
   // persistent kernel, one CTA per SM: ring + separate epilogue staging must fit in 227 KB
-  static constexpr int STAGES = (BN == 256) ? 3 : ((BN == 128) ? 5 : 6);
-  static constexpr uint32_t A_BYTES = BM * BK * 2;
+  static constexpr int STAGES = (MT == 2) ? 3 : ((BN == 256) ? 3 : ((BN == 128) ? 5 : 6));
+  static constexpr uint32_t A_TILE = BM * BK * 2;
+  static constexpr uint32_t A_BYTES = MT * A_TILE;
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t RING_BYTES = STAGES * STAGE_BYTES;
@@ -73,7 +77,10 @@ struct GemmCfg {
   static constexpr uint32_t SMEM_BYTES = RING_BYTES + EPI_BYTES + ONES_BYTES + 1024;
   // two accumulator stages (+ two 16-column row-sum accumulators at column 2 BN when BN <= 128)
   static constexpr uint32_t TMEM_COLS = (BN == 64) ? 256 : 512;
-  static constexpr uint32_t RS_COL = 2 * BN;
+  static constexpr uint32_t ACC_COLS = MT * BN;     // TMEM columns of one accumulator stage
+  static constexpr uint32_t RS_COL = 2 * BN;        // (MT == 1 only)
+  static_assert(MT == 1 || (MT == 2 && BN == 128), "MT = 2 is instantiated for BN = 128 only");
+  static_assert(2 * ACC_COLS <= TMEM_COLS, "TMEM budget of the two accumulator stages");
   static_assert(EPI_BYTES % 1024 == 0 && RING_BYTES % 1024 == 0, "ones tile alignment");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(TMEM_COLS <= 512, "TMEM budget");
@@ -94,11 +101,13 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 
 // Persistent: CTA c processes tiles c, c + gridDim.x, ... ; tile index runs n-tile fastest, then m-tile, then
 // (batch, k-split), so the CTAs that are resident together share A slabs through L2.
-template <bool A_MN, bool B_MN, int BN>
+template <bool A_MN, bool B_MN, int BN, int MT = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmD, const GemmKParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, MT>;
+  static_assert(MT == 1 || !A_MN, "MT = 2 takes a K-major A operand");
+  constexpr int BMT = BM * MT;                 // output rows of one CTA tile
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES];
@@ -154,7 +163,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         fastdivmod(tile, tiles_mn, p.mg_mn, z, mn);
         fastdivmod(mn, p.tiles_n, p.mg_n, mt, nt);
         fastdivmod(z, p.split_k, p.mg_sk, b, split);
-        const int m0 = mt * BM, n0 = nt * BN;
+        const int m0 = mt * BMT, n0 = nt * BN;
         const int ab = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
         const int kb0 = split * p.kb_per_split;
         const int niter = (min(p.kb_total, kb0 + p.kb_per_split) - kb0) * p.npairs;
@@ -167,7 +176,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
           if (!A_MN) {
-            tma_load_4d(&tmA, fb, sa, k0, m0, ab, p.pairA[pair]);
+#pragma unroll
+            for (int j = 0; j < MT; ++j) tma_load_4d(&tmA, fb, sa + j * Cfg::A_TILE, k0, m0 + j * BM, ab, p.pairA[pair]);
           } else {
             tma_load_4d(&tmA, fb, sa, m0, k0, ab, p.pairA[pair]);
             tma_load_4d(&tmA, fb, sa + 8192, m0 + 64, k0, ab, p.pairA[pair]);
@@ -199,14 +209,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         fastdivmod(tile, tiles_mn, p.mg_mn, z, mn);
         fastdivmod(z, p.split_k, p.mg_sk, b, split);
         fastdivmod(mn, p.tiles_n, p.mg_n, mt_, nt_);
-        const bool rs = BN <= 128 && p.rowsum != nullptr && nt_ == 0;   // row sums ride along with the first n-tile
+        const bool rs = MT == 1 && BN <= 128 && p.rowsum != nullptr && nt_ == 0;   // row sums ride along with the first n-tile
         const int kb0 = split * p.kb_per_split;
         const int niter = (min(p.kb_total, kb0 + p.kb_per_split) - kb0) * p.npairs;
         const int acc = local & 1;
         const uint32_t use = static_cast<uint32_t>(local >> 1);
         mbar_wait(smem_u32(&tmem_empty_bar[acc]), (use & 1u) ^ 1u);  // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t tacc = tmem_base + acc * BN;
+        const uint32_t tacc = tmem_base + acc * Cfg::ACC_COLS;
         for (int it = 0; it < niter; ++it) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
@@ -214,9 +224,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = A_MN ? make_sdesc(sa + k * 2048, 8192, 1024) : make_sdesc(sa + k * 32, 16, 1024);
             const uint64_t bd = B_MN ? make_sdesc(sb + k * 2048, 8192, 1024) : make_sdesc(sb + k * 32, 16, 1024);
-            umma_f16(tacc, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+              const uint64_t ad = A_MN ? make_sdesc(sa + k * 2048, 8192, 1024)
+                                       : make_sdesc(sa + j * Cfg::A_TILE + k * 32, 16, 1024);
+              umma_f16(tacc + j * BN, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+            }
           }
           if (rs) {
             // A x ones^T into a 16-column side accumulator: every column = sum over K of the A row
@@ -275,17 +289,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       int b = z, split = 0;
       if (p.split_k > 1) fastdivmod(z, p.split_k, p.mg_sk, b, split);
-      const int m0 = m_tile * BM, n0 = nt * BN;
+      const int n0 = nt * BN;
       const int acc = local & 1;
       const uint32_t use = static_cast<uint32_t>(local >> 1);
-      const int grow = m0 + q * 32 + lane;
-      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
       const bool use_bias = p.bias != nullptr && split == 0;
       const float* biasb = p.bias != nullptr ? p.bias + static_cast<long long>(b) * p.bias_stride : nullptr;
-      const int rows_valid = min(32, p.M - (m0 + q * 32));   // valid rows of this warp's sub-block (may be <= 0)
       mbar_wait(smem_u32(&tmem_full_bar[acc]), use & 1u);
       tc_fence_after();
-      if (BN <= 128 && p.rowsum != nullptr && nt == 0 && cc0 == 0) {
+#pragma unroll 1
+      for (int sub = 0; sub < MT; ++sub) {       // 128-row sub-tiles of the CTA tile (one TMEM accumulator each)
+      const int m0 = m_tile * BMT + sub * BM;
+      const int grow = m0 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + acc * Cfg::ACC_COLS + sub * BN + (static_cast<uint32_t>(q * 32) << 16);
+      const int rows_valid = min(32, p.M - (m0 + q * 32));   // valid rows of this warp's sub-block (may be <= 0)
+      if (MT == 1 && BN <= 128 && p.rowsum != nullptr && nt == 0 && cc0 == 0) {
         // side accumulator of the row sums (one warp per 32-row quarter); read before this warp's accumulator release
         uint32_t rv[32];
         tmem_ld_32x32(tmem_base + Cfg::RS_COL + acc * 16 + (static_cast<uint32_t>(q * 32) << 16), rv);
@@ -306,7 +323,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (c + 4 >= NCHUNK && lane == 0)      // last TMEM read of this warp for the tile: release the accumulator
+        if (sub == MT - 1 && c + 4 >= NCHUNK && lane == 0)   // last TMEM read of this warp for the tile: release it
           mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
         float2 f[16];
 #pragma unroll
@@ -401,7 +418,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               }
             }
           } else if (half == 0 && gc0 + 2 * hl < p.N) {
-            float* cs = p.colstats + ((static_cast<long long>(b) * p.tiles_m + m_tile) * 4 + q) * 2 * p.N;
+            float* cs = p.colstats + ((static_cast<long long>(b) * p.tiles_m + m_tile) * 4 + q) * 2 * p.N;  // MT == 1
             *reinterpret_cast<float2*>(cs + gc0 + 2 * hl) = sa;
             *reinterpret_cast<float2*>(cs + p.N + gc0 + 2 * hl) = sq;
           }
@@ -452,6 +469,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         }
         __syncwarp();                            // staging reused by the next chunk / tile
       }
+      }  // sub-tiles
       if (cc0 >= NCHUNK && lane == 0)            // warps without a chunk (BN = 64) still release the accumulator
         mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
       // next tile of this CTA
@@ -581,11 +599,12 @@ int make_tmap_bf16(CUtensorMap* tm, const void* ptr, long long inner, long long 
 
 namespace {
 
-template <bool A_MN, bool B_MN, int BN>
+template <bool A_MN, bool B_MN, int BN, int MT = 1>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, GemmKParams p, int num_sms,
            int* cs_rows, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_kernel<A_MN, B_MN, BN>;
+  using Cfg = GemmCfg<BN, MT>;
+  auto kern = gemm_kernel<A_MN, B_MN, BN, MT>;
+  p.tiles_m = (p.M + BM * MT - 1) / (BM * MT);
   // per launch: the attribute is per device, and callers may drive several GPUs from one process (nn.DataParallel)
   cudaError_t attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   if (attr_err != cudaSuccess) return check_cuda(attr_err, "cudaFuncSetAttribute(gemm)");
@@ -691,6 +710,20 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
       cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0)
     return set_error(GLF_ERR_DEVICE, "gemm: cannot query the SM count");
   const bool amn = a.A.mn_major != 0, bmn = a.B.mn_major != 0;
+  // 256-row super-tiles (MT = 2) for the big K-major products: halves the B-operand traffic per output row.  The
+  // column statistics need the per-CTA running-sum mode there (one partial row per CTA).
+  bool mt2 = !amn && BN == 128 && a.rowsum == nullptr && a.M >= 1024;
+  if (const char* e = getenv("GLF_GEMM_MT")) mt2 = mt2 && e[0] != '1';   // tuning aid: GLF_GEMM_MT=1 disables it
+  if (mt2 && a.colstats != nullptr) {
+    const long long tm2 = (a.M + 2 * BM - 1) / (2 * BM), tn = (a.N + 127) / 128;
+    const long long total = tm2 * tn * a.batch * p.split_k;
+    const long long grid = total < num_sms ? total : num_sms;
+    mt2 = tn <= 4 && grid <= static_cast<long long>(a.batch) * tm2;
+  }
+  if (mt2) {
+    return bmn ? launch<false, true, 128, 2>(tmA, tmB, tmD, p, num_sms, a.colstats_rows, stream)
+               : launch<false, false, 128, 2>(tmA, tmB, tmD, p, num_sms, a.colstats_rows, stream);
+  }
   switch (BN) {
     case 64: return launch_major<64>(amn, bmn, tmA, tmB, tmD, p, num_sms, a.colstats_rows, stream);
     case 128: return launch_major<128>(amn, bmn, tmA, tmB, tmD, p, num_sms, a.colstats_rows, stream);

@@ -146,3 +146,27 @@ def test_gram_contraction_kernel(C, N, B, same):
     assert O.rel_err(D[:, :C, :C], ref) < 4e-3          # bf16 rounding of the stored result
     assert float(D[:, C:, :].abs().max()) == 0 and float(D[:, :, C:].abs().max()) == 0   # border untouched
     assert O.rel_err(cs, A.float().sum(1)) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K,batch,b_mn", [
+    (1100, 256, 256, 3, 0),          # ragged last super-tile (1100 = 4 x 256 + 76), two n-tiles
+    (1153, 128, 512, 2, 1),          # the second 128-row half of the last super-tile is entirely out of range
+    (3136, 256, 256, 5, 0),          # U = X Q^T of the Gram form, one cfg2 sequence per batch entry
+])
+def test_gemm_256_row_super_tiles(M, N, K, batch, b_mn):
+    """M >= 1024 with a K-major A operand runs 256-row CTA tiles (two TMEM accumulators share each B k-block):
+    plain output, bias + residual addend, and per-CTA column statistics."""
+    A, Af = _mk(batch, M, K, 0, 11)
+    B, Bf = _mk(batch, N, K, b_mn, 12)
+    ref = torch.matmul(Af, Bf.transpose(1, 2))
+    D, _ = gemm(A, B, M, N, K, batch, 0, b_mn)
+    assert O.rel_err(D, ref) < 6e-3
+    bias = torch.randn(N, device=DEV)
+    add = torch.randn(batch, M, N, device=DEV).to(torch.bfloat16)
+    D2, _ = gemm(A, B, M, N, K, batch, 0, b_mn, bias=bias, addend=add)
+    assert O.rel_err(D2, ref + bias.cpu() + add.float().cpu()) < 6e-3
+    D3, cs = gemm(A, B, M, N, K, batch, 0, b_mn, colstats=True)
+    cs = cs.sum(0).cpu()
+    Dr = D3.float().cpu()
+    assert O.rel_err(cs[0], Dr.sum((0, 1))) < 1e-4
+    assert O.rel_err(cs[1], (Dr * Dr).sum((0, 1))) < 1e-4
