@@ -203,6 +203,20 @@ class GlobalLocalFusion(nn.Module):
         self.global_attn = TPAVIModule(in_channels=in_channels, inter_channels=inter_channels, mode=mode)
         self.local_attn = TPAVIModule(in_channels=in_channels, inter_channels=inter_channels, mode=mode)
 
+    def load_reference_checkpoint(self, ckpt, strict: bool = True):
+        """Load the MGFM / MLFM slice of a reference checkpoint: ``torch.load('net_%05d.pth')`` as written by
+        ``Trainer.save`` (R/main.py:857-872: ``{'network': model.module.state_dict()}``), the bare state dict, or one
+        whose keys carry the ``module.`` prefix that ``Trainer.test`` adds (main.py:454-457).  Keys of the rest of the
+        network (backbones, heads) are ignored; the fusion keys must match exactly when ``strict``."""
+        sd = ckpt.get("network", ckpt) if isinstance(ckpt, dict) else ckpt
+        picked = {}
+        for k, v in sd.items():
+            if k.startswith("module."):
+                k = k[len("module."):]
+            if k.startswith("global_attn.") or k.startswith("local_attn."):
+                picked[k] = v
+        return self.load_state_dict(picked, strict=strict)
+
     def forward_stacked(self, f4: Sequence[torch.Tensor], cls_logits: Sequence[torch.Tensor],
                         ctr_logits: Sequence[torch.Tensor]) -> torch.Tensor:
         """Returns f4_fusion stacked over views: [B, C, V, h, w] (memory is token-major [B,V,h,w,C])."""

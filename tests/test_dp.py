@@ -103,3 +103,26 @@ def test_grad_bucket_zero_copy_aliasing():
     assert not b.aliased()
     b.allreduce_mean()
     assert float(b.flat[-1]) == 7.0 and float(ps[1].grad[0]) == 7.0
+
+
+def test_bucket_without_cuda_keeps_the_collective_path():
+    """The peer-memory all-reduce (csrc/glf_p2p.cu) exists for CUDA buckets only: a CPU bucket reports it as
+    unavailable and keeps using the process-group collective (exercised by the gloo tests above)."""
+    import torch
+    from glfusion_b200 import dp
+    params = [torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(3, 2))]
+    b = dp.GradBucket(params)
+    assert b.enable_p2p() is False and not b.p2p_enabled
+    assert b.flat.numel() == 11
+
+
+def test_p2p_entry_points_reject_bad_arguments():
+    """Argument validation of the C ABI happens before any device work (no GPU needed)."""
+    import ctypes as C
+    import glfusion_b200
+    lib = glfusion_b200.load_library()
+    assert lib.glf_p2p_signal_bytes(8) >= 2 * 148 * 8 * 4
+    assert lib.glf_p2p_max_floats() >= 345_000
+    off = C.c_uint64(0)
+    assert lib.glf_p2p_export(None, C.create_string_buffer(64), C.byref(off)) < 0
+    assert b"NULL" in lib.glf_last_error()

@@ -72,6 +72,26 @@ def test_fusion_module_uses_reference_attribute_names():
     assert "global_attn.theta.weight" in keys and "local_attn.W_z.1.running_var" in keys   # ours.py:1746-1747
 
 
+def test_reference_network_checkpoint_slice_loads():
+    """A checkpoint in the reference's wire format (main.py:857-872, optionally with the 'module.' prefix of
+    main.py:454-457) holds the whole network; the fusion blocks take their slice with strict=True."""
+    torch.manual_seed(7)
+    src = GlobalLocalFusion(64)
+    for p in src.parameters():
+        torch.nn.init.normal_(p, std=0.1)
+    net = {"module." + k: v.clone() for k, v in src.state_dict().items()}
+    net["module.backbone.conv1.weight"] = torch.zeros(8, 1, 7, 7)          # other parts of Global_and_Local
+    net["module.classifier.1.4.weight"] = torch.zeros(5, 256, 1, 1)
+    dst = GlobalLocalFusion(64)
+    res = dst.load_reference_checkpoint({"network": net})
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in src.state_dict().items():
+        assert torch.equal(dst.state_dict()[k], v), k
+    broken = {k: v for k, v in net.items() if not k.endswith("local_attn.theta.bias")}
+    with pytest.raises(RuntimeError):
+        GlobalLocalFusion(64).load_reference_checkpoint({"network": broken})
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="live reference only in the build container")
 def test_init_rng_stream_identical_to_reference():
     sys.path.insert(0, REF)
