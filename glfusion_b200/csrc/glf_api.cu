@@ -195,16 +195,16 @@ struct WsBwd {
   float *dWpf, *part_ln, *k1, *k2, *k3, *cs_t, *cs_p, *cs_g, *red1, *dwcat, *delta;
   void* attn;
   // Gram form
-  float *Rf, *rv, *G0, *Hf, *evec, *dwaug;
-  bf16 *Rb, *AK, *dQa, *dT, *EF;
+  float *Rf, *rv, *evec, *dwaug;
+  bf16 *Rb, *AK, *dQa, *dT, *EF, *G0, *Hf;
 };
 size_t carve_ws_bwd(const glf_desc* d, const Dims& m, void* base, WsBwd* w) {
   Carver c(base);
   const size_t rows = m.rows, C = m.C, Ci = m.Ci, B = m.B;
   w->dztok = m.pack_dz ? c.take<bf16>(rows * C) : nullptr;
   w->dV = c.take<bf16>(rows * C);
-  w->Rf = w->rv = w->G0 = w->Hf = w->evec = w->dwaug = nullptr;
-  w->Rb = w->AK = w->dQa = w->dT = w->EF = nullptr;
+  w->Rf = w->rv = w->evec = w->dwaug = nullptr;
+  w->Rb = w->AK = w->dQa = w->dT = w->EF = w->G0 = w->Hf = nullptr;
   if (m.gram) {
     const size_t Ca = m.Ca;
     w->dU = w->dP = w->dY = nullptr;
@@ -223,8 +223,8 @@ size_t carve_ws_bwd(const glf_desc* d, const Dims& m, void* base, WsBwd* w) {
     w->dWpb = c.take<bf16>(B * C * Ci);
     w->dM = c.take<bf16>(B * Ci * Ci);
     w->dT = c.take<bf16>(B * Ci * Ca);
-    w->G0 = c.take<float>(B * Ca * Ca);
-    w->Hf = c.take<float>(B * Ca * Ca);
+    w->G0 = c.take<bf16>(B * C * Ca);        // dS~[:C, :] (the three terms of F are rounded to bf16, summed in fp32)
+    w->Hf = c.take<bf16>(B * C * Ca);
     w->EF = c.take<bf16>(B * 2 * C * C);
     w->evec = c.take<float>(B * C);
     w->dwaug = c.take<float>(3 * Ci * Ca);
@@ -566,8 +566,7 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved&
     g.B.rows = C1;
     g.M = C; g.N = Ca; g.K = Ci; g.batch = B;
     g.bn_hint = wide;
-    g.out_kind = 1;
-    g.D = wb.G0; g.ldd = Ca; g.strideD = CaCa;
+    g.D = wb.G0; g.ldd = Ca; g.strideD = CCa;
     GLF_TRY(gemm(g, stream));
   }
   if (bn_train) {  // H_b = Q_b^T Qk_b    [C x Ca]  (dU Q = dV E + X H[:C,:C] + 1 H[:C,C]^T: the k2 U + k3 part of dU)
@@ -577,8 +576,7 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved&
     g.B.rows = C1;
     g.M = C; g.N = Ca; g.K = C; g.batch = B;
     g.bn_hint = wide;
-    g.out_kind = 1;
-    g.D = wb.Hf; g.ldd = Ca; g.strideD = CaCa;
+    g.D = wb.Hf; g.ldd = Ca; g.strideD = CCa;
     GLF_TRY(gemm(g, stream));
   }
   // F = (G0 + G0^T + H)[:C, :C] ;  e = (G0[:, C] + G0[C, :] + H[:, C])[:C]

@@ -131,19 +131,19 @@ __global__ void gram_kprep_kernel(const bf16* __restrict__ Qb, const float* __re
 // e = (dS[:, C] + dS[C, :] + H[:, C])[:C]  (blocks of the first tile row also emit their 32 entries of e; only rows
 // < C of dS and H are computed, the missing row dS[C, :] = b_phi^T dT is formed here)
 __global__ void __launch_bounds__(256)
-    gram_assemble_F_kernel(const float* __restrict__ G0, const float* __restrict__ Hf, const bf16* __restrict__ dT,
+    gram_assemble_F_kernel(const bf16* __restrict__ G0, const bf16* __restrict__ Hf, const bf16* __restrict__ dT,
                            const bf16* __restrict__ wphi, bf16* __restrict__ EF, float* __restrict__ evec, int C,
                            int Ci, int Ca) {
   __shared__ float t[32][33];
   const long long b = blockIdx.z;
-  const float* G = G0 + b * static_cast<long long>(Ca) * Ca;
-  const float* H = Hf != nullptr ? Hf + b * static_cast<long long>(Ca) * Ca : nullptr;
+  const bf16* G = G0 + b * static_cast<long long>(C) * Ca;      // [C rows][Ca]
+  const bf16* H = Hf != nullptr ? Hf + b * static_cast<long long>(C) * Ca : nullptr;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int rr = c0 + ty + 8 * i, cc = r0 + tx;   // element (rr, cc) of G lands at t[ty + 8 i][tx]
-    t[ty + 8 * i][tx] = (rr < C && cc < C) ? G[static_cast<long long>(rr) * Ca + cc] : 0.f;
+    t[ty + 8 * i][tx] = (rr < C && cc < C) ? __bfloat162float(G[static_cast<long long>(rr) * Ca + cc]) : 0.f;
   }
   __syncthreads();
   bf16* F = EF + (b * 2 + 1) * static_cast<long long>(C) * C;
@@ -151,8 +151,8 @@ __global__ void __launch_bounds__(256)
   for (int i = 0; i < 4; ++i) {
     const int rr = r0 + ty + 8 * i, cc = c0 + tx;
     if (rr < C && cc < C) {
-      float v = G[static_cast<long long>(rr) * Ca + cc] + t[tx][ty + 8 * i];
-      if (H != nullptr) v += H[static_cast<long long>(rr) * Ca + cc];
+      float v = __bfloat162float(G[static_cast<long long>(rr) * Ca + cc]) + t[tx][ty + 8 * i];
+      if (H != nullptr) v += __bfloat162float(H[static_cast<long long>(rr) * Ca + cc]);
       F[static_cast<long long>(rr) * C + cc] = __float2bfloat16(v);
     }
   }
@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(256)
     part[ty][tx] = a0;
     __syncthreads();
     if (ty == 0 && c < C) {
-      float v = G[static_cast<long long>(c) * Ca + C];
-      if (H != nullptr) v += H[static_cast<long long>(c) * Ca + C];
+      float v = __bfloat162float(G[static_cast<long long>(c) * Ca + C]);
+      if (H != nullptr) v += __bfloat162float(H[static_cast<long long>(c) * Ca + C]);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v += part[i][tx];
       evec[b * C + c] = v;
@@ -231,7 +231,7 @@ int gram_kprep(const bf16* Qb, const float* cvec, const float* k1, const float* 
   return check_cuda(cudaGetLastError(), "gram_kprep launch");
 }
 
-int gram_assemble_F(const float* G0, const float* Hf, const bf16* dT, const bf16* wphi, bf16* EF, float* evec, int B,
+int gram_assemble_F(const bf16* G0, const bf16* Hf, const bf16* dT, const bf16* wphi, bf16* EF, float* evec, int B,
                     int C, int Ci, int Ca, cudaStream_t stream) {
   if (B > 65535) return set_error(GLF_ERR_INVALID, "gram form: more than 65535 sequences per call");
   dim3 grid((C + 31) / 32, (C + 31) / 32, B);

@@ -107,7 +107,7 @@ int gram_border(const float* colv, const float* rowv, bf16* out, int B, int C, i
 int gram_cvec(const bf16* Wp, const float* theta_b, float* cvec, int B, int C, int Ci, cudaStream_t stream);
 int gram_kprep(const bf16* Qb, const float* cvec, const float* k1, const float* k2, const float* k3, bf16* AK, bf16* EF,
                int B, int C, int Ca, cudaStream_t stream);
-int gram_assemble_F(const float* G0, const float* Hf, const bf16* dT, const bf16* wphi, bf16* EF, float* evec, int B,
+int gram_assemble_F(const bf16* G0, const bf16* Hf, const bf16* dT, const bf16* wphi, bf16* EF, float* evec, int B,
                     int C, int Ci, int Ca, cudaStream_t stream);
 // One CTA per sequence (glf_gramk.cu): D_b = A_b^T X_b for C = 128 / 256, operands streamed once
 bool gram_contraction_supported(int C);
