@@ -217,8 +217,8 @@ size_t carve_ws_bwd(const glf_desc* d, const Dims& m, void* base, WsBwd* w) {
     w->k3 = c.take<float>(C);
     w->Rf = c.take<float>(B * C * C);        // split-K accumulation target of R = dV^T X
     w->rv = c.take<float>(B * C);
-    w->Rb = c.take<bf16>(B * Ca * Ca);       // [[R, rv], [s^T, N]]
-    w->AK = c.take<bf16>(B * 2 * C * Ca);    // [Qk ; Dk] per sequence
+    w->Rb = c.take<bf16>(B * Ca * Ca);       // k1 [R | rv] (rows < C)
+    w->AK = c.take<bf16>(B * C * Ca);        // Qk = k2 Q~ (column C: k2 c + k3) per sequence
     w->dQa = c.take<bf16>(B * C * Ca);
     w->dWpb = c.take<bf16>(B * C * Ci);
     w->dM = c.take<bf16>(B * Ci * Ci);
@@ -316,7 +316,7 @@ int gram_big_tile() {
 // [[S, colsum(A)], [rowv^T, corner]] of width Ca.  Enough sequences: the GEMM writes bf16 straight into it and a border
 // kernel adds the homogeneous row / column; few long sequences: split-K into fp32, then one assembling pass.
 int gram_token_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* scratch, float* rowsum, const float* rowv,
-                           float corner, int B, int N, int C, int Ca, cudaStream_t stream) {
+                           const float* rowscale, float corner, int B, int N, int C, int Ca, cudaStream_t stream) {
   const char* ek = getenv("GLF_GRAM_KERNEL");   // tuning aid: 0 = always the generic tile GEMM
   if (gram_contraction_supported(C) && !(ek && ek[0] == '0')) {
     // one CTA per sequence; few long sequences are split along the tokens to fill two rounds of the SMs
@@ -325,11 +325,11 @@ int gram_token_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* s
       ks = (2 * 148) / B;
       if (ks < 1) ks = 1;
     }
-    GLF_TRY(gram_contraction(A, X, out_aug, scratch, rowsum, B, N, C, Ca, ks, stream));
+    GLF_TRY(gram_contraction(A, X, out_aug, scratch, rowsum, rowscale, B, N, C, Ca, ks, stream));
     const int kb = (N + 63) / 64;
     if ((ks > kb ? kb : ks) > 1)
-      return gram_assemble_aug(scratch, rowsum, rowv ? rowv : rowsum, out_aug, B, C, Ca, corner, stream);
-    return gram_border(rowsum, rowv ? rowv : rowsum, out_aug, B, C, Ca, corner, stream);
+      return gram_assemble_aug(scratch, rowsum, rowv ? rowv : rowsum, rowscale, out_aug, B, C, Ca, corner, stream);
+    return gram_border(rowsum, rowv ? rowv : rowsum, rowscale, out_aug, B, C, Ca, corner, stream);
   }
   GemmArgs g;
   g.A = opnd(A, 1, C, static_cast<long long>(N) * C);
@@ -338,18 +338,20 @@ int gram_token_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* s
   g.bn_hint = 128;
   g.rowsum = rowsum; g.rowsum_stride = C;
   g.split_k = pick_split(static_cast<long long>(B) * ((C + 127) / 128) * ((C + 127) / 128), N);
-  if (g.split_k > 1) {
-    GLF_TRY(check_cuda(cudaMemsetAsync(scratch, 0, sizeof(float) * B * C * C, stream), "memset S"));
-    GLF_TRY(check_cuda(cudaMemsetAsync(rowsum, 0, sizeof(float) * B * C, stream), "memset s"));
-    g.out_kind = 2;
+  if (g.split_k > 1 || rowscale != nullptr) {   // (a per-row scale needs the fp32 result: the GEMM's alpha is a scalar)
+    if (g.split_k > 1) {
+      GLF_TRY(check_cuda(cudaMemsetAsync(scratch, 0, sizeof(float) * B * C * C, stream), "memset S"));
+      GLF_TRY(check_cuda(cudaMemsetAsync(rowsum, 0, sizeof(float) * B * C, stream), "memset s"));
+    }
+    g.out_kind = g.split_k > 1 ? 2 : 1;
     g.D = scratch; g.ldd = C; g.strideD = static_cast<long long>(C) * C;
     GLF_TRY(gemm(g, stream));
-    return gram_assemble_aug(scratch, rowsum, rowv ? rowv : rowsum, out_aug, B, C, Ca, corner, stream);
+    return gram_assemble_aug(scratch, rowsum, rowv ? rowv : rowsum, rowscale, out_aug, B, C, Ca, corner, stream);
   }
   g.out_kind = 0;
   g.D = out_aug; g.ldd = Ca; g.strideD = static_cast<long long>(Ca) * Ca;
   GLF_TRY(gemm(g, stream));
-  return gram_border(rowsum, rowv ? rowv : rowsum, out_aug, B, C, Ca, corner, stream);
+  return gram_border(rowsum, rowv ? rowv : rowsum, nullptr, out_aug, B, C, Ca, corner, stream);
 }
 
 // D = A0 B0^T + A1 B1^T (+ bias + addend), bf16 output: both products accumulate into one TMEM tile when each operand
@@ -395,7 +397,7 @@ int tpavi_fwd_gram(const glf_desc* d, const Dims& m, const void* x, const glf_we
     X = s.xtok;
   }
   // S_b = X_b^T X_b, s_b = X_b^T 1   ->   S~_b
-  GLF_TRY(gram_token_contraction(X, X, s.Sa, wf.Sf, s.sfv, nullptr, static_cast<float>(N), B, N, C, Ca, stream));
+  GLF_TRY(gram_token_contraction(X, X, s.Sa, wf.Sf, s.sfv, nullptr, nullptr, static_cast<float>(N), B, N, C, Ca, stream));
   {  // T_b = W~phi S~_b                      [Ci x Ca]   (= Phi_b^T X~_b; S~ is symmetric)
     GemmArgs g;
     g.A = opnd(s.waug + CiCa, 0, Ca, 0);
@@ -473,19 +475,21 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved&
   const float invN = 1.f / static_cast<float>(N);
   const int wide = gram_wide_tile();   // N tile of the products whose output is Ca (= C + 8) columns wide
   const bool bn_train = d->bn_layer && d->training;   // k2, k3 != 0 only then
-  // [[R_b, rv_b], [s_b^T, N]] with R_b = dV_b^T X_b, rv_b = dV_b^T 1
-  GLF_TRY(gram_token_contraction(wb.dV, X, wb.Rb, wb.Rf, wb.rv, s.sfv, static_cast<float>(N), B, N, C, Ca, stream));
-  // Qk = k2 Q~ (column C: k2 c + k3), Dk = diag(k1), E = k1 Q
+  // k1 * [R_b | rv_b]  with R_b = dV_b^T X_b, rv_b = dV_b^T 1: the BatchNorm-backward scale k1 (per channel of dV =
+  // row of R) is applied in fp32 by the contraction's epilogue
+  GLF_TRY(gram_token_contraction(wb.dV, X, wb.Rb, wb.Rf, wb.rv, s.sfv, wb.k1, static_cast<float>(N), B, N, C, Ca, stream));
+  // Qk = k2 Q~ (column C: k2 c + k3), E = k1 Q
   GLF_TRY(gram_kprep(s.Qb, s.cvec, wb.k1, wb.k2, wb.k3, wb.AK, wb.EF, B, C, Ca, stream));
-  {  // dQ~_b = dU_b^T X~_b = Qk_b S~_b + Dk [R_b | rv_b]     [C x Ca]   (B operands read MN-major; S~ is symmetric)
+  {  // dQ~_b = dU_b^T X~_b = Qk_b S~_b + k1 [R_b | rv_b]     [C x Ca]   (S~ is symmetric; the second term is the addend)
     GemmArgs g;
-    g.A = opnd(nullptr, 0, Ca, 2 * CCa);
-    g.B = opnd(nullptr, 1, Ca, CaCa);
+    g.A = opnd(wb.AK, 0, Ca, CCa);
+    g.B = opnd(s.Sa, 0, Ca, CaCa);
     g.B.rows = C1;
     g.M = C; g.N = Ca; g.K = C1; g.batch = B;
     g.bn_hint = wide;
+    g.addend = wb.Rb; g.ld_add = Ca; g.stride_add = CaCa;
     g.D = wb.dQa; g.ldd = Ca; g.strideD = CCa;
-    GLF_TRY(gemm_pair2(g, wb.AK, wb.AK + CCa, s.Sa, wb.Rb, stream));
+    GLF_TRY(gemm(g, stream));
   }
   {  // dW'_b = dQ~_b W~theta^T               [C x Ci]
     GemmArgs g;
@@ -572,7 +576,7 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved&
   if (bn_train) {  // H_b = Q_b^T Qk_b    [C x Ca]  (dU Q = dV E + X H[:C,:C] + 1 H[:C,C]^T: the k2 U + k3 part of dU)
     GemmArgs g;
     g.A = opnd(s.Qb, 1, Ca, CCa);
-    g.B = opnd(wb.AK, 1, Ca, 2 * CCa);
+    g.B = opnd(wb.AK, 1, Ca, CCa);
     g.B.rows = C1;
     g.M = C; g.N = Ca; g.K = C; g.batch = B;
     g.bn_hint = wide;
@@ -1105,7 +1109,7 @@ GLF_API int glf_gram_contraction(const void* A, const void* X, void* D, float* c
   if (B <= 0 || N <= 0) return set_error(GLF_ERR_INVALID, "gram_contraction: empty input");
   if (ldd < C || ldd % 8 != 0) return set_error(GLF_ERR_INVALID, "gram_contraction: ldd must be >= C and a multiple of 8");
   return gram_contraction(reinterpret_cast<const bf16*>(A), reinterpret_cast<const bf16*>(X), reinterpret_cast<bf16*>(D),
-                          nullptr, colsum, B, N, C, ldd, 1, reinterpret_cast<cudaStream_t>(stream));
+                          nullptr, colsum, nullptr, B, N, C, ldd, 1, reinterpret_cast<cudaStream_t>(stream));
 }
 
 GLF_API int glf_bn_res_ln_fwd(int64_t rows, int C, const void* U, const void* X, const float* bn_a, const float* bn_b,

@@ -36,8 +36,8 @@ __global__ void gram_prep_weights_kernel(const float* __restrict__ tw, const flo
 
 // Augmented [B][Ca][Ca] bf16 matrix [[M, colv], [rowv^T, corner]] (zero padded) from M [B][C][C] fp32 (split-K path)
 __global__ void gram_assemble_aug_kernel(const float* __restrict__ Mf, const float* __restrict__ colv,
-                                         const float* __restrict__ rowv, bf16* __restrict__ out, long long total,
-                                         int C, int Ca, float corner) {
+                                         const float* __restrict__ rowv, const float* __restrict__ rowscale,
+                                         bf16* __restrict__ out, long long total, int C, int Ca, float corner) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int j = static_cast<int>(i % Ca);
@@ -48,6 +48,7 @@ __global__ void gram_assemble_aug_kernel(const float* __restrict__ Mf, const flo
     else if (r < C && j == C) v = colv[b * C + r];
     else if (r == C && j < C) v = rowv[b * C + j];
     else if (r == C && j == C) v = corner;
+    if (rowscale != nullptr && r < C) v *= rowscale[r];
     out[i] = __float2bfloat16(v);
   }
 }
@@ -55,14 +56,16 @@ __global__ void gram_assemble_aug_kernel(const float* __restrict__ Mf, const flo
 // Border of an augmented matrix whose [C x C] block a GEMM already wrote in bf16: column C = colv, row C = rowv,
 // corner, zero padding.  grid = (batch, 8).
 __global__ void gram_border_kernel(const float* __restrict__ colv, const float* __restrict__ rowv,
-                                   bf16* __restrict__ out, int C, int Ca, float corner) {
+                                   const float* __restrict__ rowscale, bf16* __restrict__ out, int C, int Ca,
+                                   float corner) {
   const long long b = blockIdx.x;
   bf16* M = out + b * static_cast<long long>(Ca) * Ca;
   const int pad = Ca - C;
   const int tid = blockIdx.y * blockDim.x + threadIdx.x, nth = gridDim.y * blockDim.x;
   for (int i = tid; i < C * pad; i += nth) {        // columns C.. of rows < C
     const int r = i / pad, j = C + i % pad;
-    M[static_cast<long long>(r) * Ca + j] = __float2bfloat16(j == C ? colv[b * C + r] : 0.f);
+    M[static_cast<long long>(r) * Ca + j] =
+        __float2bfloat16(j == C ? colv[b * C + r] * (rowscale != nullptr ? rowscale[r] : 1.f) : 0.f);
   }
   for (int i = tid; i < pad * Ca; i += nth) {       // rows C..
     const int r = C + i / Ca, j = i % Ca;
@@ -90,8 +93,7 @@ __global__ void gram_cvec_kernel(const bf16* __restrict__ Wp, const float* __res
 
 // Per-sequence operands of the backward products, from Q~ (bf16), c and the BatchNorm-backward coefficients
 // (dU = k1 dV + k2 U + k3 per output channel = row r of Q~):
-//   AK[b][0] = Qk = k2 Q~  with column C = k2 c + k3      (dQ~ = Qk S~ + ... ; H = Q~^T Qk)
-//   AK[b][1] = Dk = diag(k1) (column C and padding zero)   (... + Dk [R | rv])
+//   Qk[b]    = k2 Q~  with column C = k2 c + k3            (dQ~ = Qk S~ + k1 [R | rv] ; H = Q~^T Qk)
 //   EF[b][0] = E  = k1 Q                                    (dX = dV E + ...)
 // 8 columns per thread.
 __global__ void gram_kprep_kernel(const bf16* __restrict__ Qb, const float* __restrict__ cvec,
@@ -107,7 +109,7 @@ __global__ void gram_kprep_kernel(const bf16* __restrict__ Qb, const float* __re
     const float a1 = k1[r], a2 = k2[r];
     const uint4 qv = *reinterpret_cast<const uint4*>(Qb + i * 8);
     const uint32_t* q32 = reinterpret_cast<const uint32_t*>(&qv);
-    uint32_t qk[4], dk[4], ee[4];
+    uint32_t qk[4], ee[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const float2 q = unpack_bf16(q32[t]);
@@ -116,12 +118,9 @@ __global__ void gram_kprep_kernel(const bf16* __restrict__ Qb, const float* __re
       if (j == C) x0 = fmaf(a2, cvec[b * C + r], k3[r]);
       if (j + 1 == C) x1 = fmaf(a2, cvec[b * C + r], k3[r]);
       qk[t] = pack_bf16(x0, x1);
-      dk[t] = pack_bf16(j == r ? a1 : 0.f, j + 1 == r ? a1 : 0.f);
       ee[t] = pack_bf16(a1 * q.x, a1 * q.y);
     }
-    bf16* ak = AK + (b * 2 * C + r) * static_cast<long long>(Ca) + j0;
-    *reinterpret_cast<uint4*>(ak) = make_uint4(qk[0], qk[1], qk[2], qk[3]);
-    *reinterpret_cast<uint4*>(ak + static_cast<long long>(C) * Ca) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+    *reinterpret_cast<uint4*>(AK + i * 8) = make_uint4(qk[0], qk[1], qk[2], qk[3]);
     if (j0 < C)   // C % 8 == 0: a vector is entirely inside or outside the first C columns
       *reinterpret_cast<uint4*>(EF + (b * 2 * C + r) * static_cast<long long>(C) + j0) = make_uint4(ee[0], ee[1], ee[2], ee[3]);
   }
@@ -205,16 +204,17 @@ int gram_prep_weights(const glf_weights* w, int C, int Ci, int Ca, bf16* waug, b
   return check_cuda(cudaGetLastError(), "gram_prep_weights launch");
 }
 
-int gram_assemble_aug(const float* Mf, const float* colv, const float* rowv, bf16* out, int B, int C, int Ca,
-                      float corner, cudaStream_t stream) {
+int gram_assemble_aug(const float* Mf, const float* colv, const float* rowv, const float* rowscale, bf16* out, int B,
+                      int C, int Ca, float corner, cudaStream_t stream) {
   const long long total = static_cast<long long>(B) * Ca * Ca;
-  gram_assemble_aug_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(Mf, colv, rowv, out, total, C, Ca, corner);
+  gram_assemble_aug_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(Mf, colv, rowv, rowscale, out, total, C, Ca,
+                                                                       corner);
   return check_cuda(cudaGetLastError(), "gram_assemble_aug launch");
 }
 
-int gram_border(const float* colv, const float* rowv, bf16* out, int B, int C, int Ca, float corner,
-                cudaStream_t stream) {
-  gram_border_kernel<<<dim3(B, 8), 256, 0, stream>>>(colv, rowv, out, C, Ca, corner);
+int gram_border(const float* colv, const float* rowv, const float* rowscale, bf16* out, int B, int C, int Ca,
+                float corner, cudaStream_t stream) {
+  gram_border_kernel<<<dim3(B, 8), 256, 0, stream>>>(colv, rowv, rowscale, out, C, Ca, corner);
   return check_cuda(cudaGetLastError(), "gram_border launch");
 }
 

@@ -32,6 +32,7 @@ struct GramKParams {
   bf16* out;       // ksplit == 1: [B][Ca][Ca] bf16, rows/cols < C written
   float* outf;     // ksplit  > 1: [B][C][C] fp32, atomically accumulated (zeroed by the caller)
   float* rowsum;   // [B][C] column sums of A (stored, or atomically accumulated when ksplit > 1)
+  const float* rowscale;   // optional [C]: bf16 output row r is scaled by rowscale[r] (ksplit == 1 path)
 };
 
 __global__ void __launch_bounds__(GK_THREADS, 1)
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
     tc_fence_after();
     if (mt < MT) {
       const int row = mt * 128 + q * 32 + lane;
+      const float rsc = (p.rowscale != nullptr && p.ksplit == 1) ? p.rowscale[row] : 1.f;
       const uint32_t taddr = tmem_base + mt * p.C + (static_cast<uint32_t>(q * 32) << 16);
       for (int c = 0; c < p.C / 32; ++c) {
         uint32_t v[32];
@@ -162,10 +164,10 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
           bf16* dst = p.out + (static_cast<long long>(b) * p.Ca + row) * p.Ca + c * 32;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint4 pk = make_uint4(pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
-                                        pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
-                                        pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
-                                        pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+            const uint4 pk = make_uint4(pack_bf16(rsc * __uint_as_float(v[8 * j]), rsc * __uint_as_float(v[8 * j + 1])),
+                                        pack_bf16(rsc * __uint_as_float(v[8 * j + 2]), rsc * __uint_as_float(v[8 * j + 3])),
+                                        pack_bf16(rsc * __uint_as_float(v[8 * j + 4]), rsc * __uint_as_float(v[8 * j + 5])),
+                                        pack_bf16(rsc * __uint_as_float(v[8 * j + 6]), rsc * __uint_as_float(v[8 * j + 7])));
             *reinterpret_cast<uint4*>(dst + 8 * j) = pk;
           }
         }
@@ -181,10 +183,10 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
 
 bool gram_contraction_supported(int C) { return C == 128 || C == 256; }
 
-// out_aug rows / columns < C (bf16, ld = Ca) when ksplit == 1, else fp32 accumulation into `scratch` (zeroed here);
-// rowsum = column sums of A.  The caller adds the homogeneous border (gram_border / gram_assemble_aug).
-int gram_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* scratch, float* rowsum, int B, int N, int C,
-                     int Ca, int ksplit, cudaStream_t stream) {
+// out_aug rows / columns < C (bf16, ld = Ca, row r scaled by rowscale[r] if given) when ksplit == 1, else fp32
+// accumulation into `scratch` (zeroed here, unscaled); rowsum = column sums of A (unscaled).  The caller adds the homogeneous border (gram_border / gram_assemble_aug).
+int gram_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* scratch, float* rowsum, const float* rowscale,
+                     int B, int N, int C, int Ca, int ksplit, cudaStream_t stream) {
   if (!gram_contraction_supported(C)) return set_error(GLF_ERR_UNSUPPORTED, "gram_contraction: C must be 128 or 256");
   CUtensorMap tmA, tmX;
   int rc = make_tmap_bf16(&tmA, A, C, N, B, C, static_cast<long long>(N) * C, 64);
@@ -199,7 +201,7 @@ int gram_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* scratch
   p.kb_per_split = (p.kb_total + ks - 1) / ks;
   p.ksplit = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.same = (A == X) ? 1 : 0;
-  p.out = out_aug; p.outf = scratch; p.rowsum = rowsum;
+  p.out = out_aug; p.outf = scratch; p.rowsum = rowsum; p.rowscale = rowscale;
   if (p.ksplit > 1) {
     rc = check_cuda(cudaMemsetAsync(scratch, 0, sizeof(float) * B * C * C, stream), "memset S");
     if (rc) return rc;

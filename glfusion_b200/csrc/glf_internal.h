@@ -100,10 +100,11 @@ int cast_bf16(const float* in, bf16* out, long long n, cudaStream_t stream);
 // Augmented width of the per-sequence matrices: column C is the homogeneous coordinate, the rest zero padding.
 inline int gram_ca(int C) { return C + 8; }
 int gram_prep_weights(const glf_weights* w, int C, int Ci, int Ca, bf16* waug, bf16* wzb, cudaStream_t stream);
-int gram_assemble_aug(const float* Mf, const float* colv, const float* rowv, bf16* out, int B, int C, int Ca,
-                      float corner, cudaStream_t stream);
-int gram_border(const float* colv, const float* rowv, bf16* out, int B, int C, int Ca, float corner,
-                cudaStream_t stream);
+// rowscale (optional, [C]): rows < C of the augmented matrix (column C included) are scaled per row
+int gram_assemble_aug(const float* Mf, const float* colv, const float* rowv, const float* rowscale, bf16* out, int B,
+                      int C, int Ca, float corner, cudaStream_t stream);
+int gram_border(const float* colv, const float* rowv, const float* rowscale, bf16* out, int B, int C, int Ca,
+                float corner, cudaStream_t stream);
 int gram_cvec(const bf16* Wp, const float* theta_b, float* cvec, int B, int C, int Ci, cudaStream_t stream);
 int gram_kprep(const bf16* Qb, const float* cvec, const float* k1, const float* k2, const float* k3, bf16* AK, bf16* EF,
                int B, int C, int Ca, cudaStream_t stream);
@@ -111,8 +112,8 @@ int gram_assemble_F(const bf16* G0, const bf16* Hf, const bf16* dT, const bf16* 
                     int C, int Ci, int Ca, cudaStream_t stream);
 // One CTA per sequence (glf_gramk.cu): D_b = A_b^T X_b for C = 128 / 256, operands streamed once
 bool gram_contraction_supported(int C);
-int gram_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* scratch, float* rowsum, int B, int N, int C,
-                     int Ca, int ksplit, cudaStream_t stream);
+int gram_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* scratch, float* rowsum, const float* rowscale,
+                     int B, int N, int C, int Ca, int ksplit, cudaStream_t stream);
 int gram_unpack_grads(const float* dwaug, const glf_grads* g, int C, int Ci, int Ca, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------ gate + concat
