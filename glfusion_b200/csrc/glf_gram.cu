@@ -126,51 +126,68 @@ __global__ void gram_kprep_kernel(const bf16* __restrict__ Qb, const float* __re
   }
 }
 
-// F = (dS + dS^T + H)[:C, :C] -> EF[b][1]   (32 x 32 tiles, the transposed tile goes through shared memory);
-// e = (dS[:, C] + dS[C, :] + H[:, C])[:C]  (blocks of the first tile row also emit their 32 entries of e; only rows
-// < C of dS and H are computed, the missing row dS[C, :] = b_phi^T dT is formed here)
+// F = (dS + dS^T + H)[:C, :C] -> EF[b][1]   (64 x 64 tiles, the transposed tile goes through shared memory; every
+// thread moves bf16 pairs);  e = (dS[:, C] + dS[C, :] + H[:, C])[:C]  (blocks of the first tile row also emit their 64
+// entries of e; only rows < C of dS and H are computed, the missing row dS[C, :] = b_phi^T dT is formed here)
 __global__ void __launch_bounds__(256)
     gram_assemble_F_kernel(const bf16* __restrict__ G0, const bf16* __restrict__ Hf, const bf16* __restrict__ dT,
                            const bf16* __restrict__ wphi, bf16* __restrict__ EF, float* __restrict__ evec, int C,
                            int Ci, int Ca) {
-  __shared__ float t[32][33];
+  __shared__ float t[64][65];
   const long long b = blockIdx.z;
   const bf16* G = G0 + b * static_cast<long long>(C) * Ca;      // [C rows][Ca]
   const bf16* H = Hf != nullptr ? Hf + b * static_cast<long long>(C) * Ca : nullptr;
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8: thread = column pair 2 tx, rows ty + 8 i
+  // stage G[c0 + a][r0 + bb] at t[a][bb]  (C % 8 == 0: a pair is inside or outside the matrix together)
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int rr = c0 + ty + 8 * i, cc = r0 + tx;   // element (rr, cc) of G lands at t[ty + 8 i][tx]
-    t[ty + 8 * i][tx] = (rr < C && cc < C) ? __bfloat162float(G[static_cast<long long>(rr) * Ca + cc]) : 0.f;
+  for (int i = 0; i < 8; ++i) {
+    const int a = ty + 8 * i, rr = c0 + a, cc = r0 + 2 * tx;
+    float2 v = make_float2(0.f, 0.f);
+    if (rr < C && cc < C) v = unpack_bf16(*reinterpret_cast<const uint32_t*>(G + static_cast<long long>(rr) * Ca + cc));
+    t[a][2 * tx] = v.x;
+    t[a][2 * tx + 1] = v.y;
   }
   __syncthreads();
   bf16* F = EF + (b * 2 + 1) * static_cast<long long>(C) * C;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int rr = r0 + ty + 8 * i, cc = c0 + tx;
+  for (int i = 0; i < 8; ++i) {
+    const int a = ty + 8 * i, rr = r0 + a, cc = c0 + 2 * tx;
     if (rr < C && cc < C) {
-      float v = __bfloat162float(G[static_cast<long long>(rr) * Ca + cc]) + t[tx][ty + 8 * i];
-      if (H != nullptr) v += __bfloat162float(H[static_cast<long long>(rr) * Ca + cc]);
-      F[static_cast<long long>(rr) * C + cc] = __float2bfloat16(v);
+      float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(G + static_cast<long long>(rr) * Ca + cc));
+      v.x += t[2 * tx][a];          // G[cc][rr]
+      v.y += t[2 * tx + 1][a];      // G[cc + 1][rr]
+      if (H != nullptr) {
+        const float2 h = unpack_bf16(*reinterpret_cast<const uint32_t*>(H + static_cast<long long>(rr) * Ca + cc));
+        v.x += h.x; v.y += h.y;
+      }
+      *reinterpret_cast<uint32_t*>(F + static_cast<long long>(rr) * C + cc) = pack_bf16(v.x, v.y);
     }
   }
-  if (blockIdx.y == 0) {     // block-uniform: the first tile row also emits e for its 32 columns
-    __shared__ float part[8][33];
-    const int c = c0 + tx;
-    float a0 = 0.f;
-    if (c < C) {
-      const bf16* dt = dT + b * static_cast<long long>(Ci) * Ca + c;
-      for (int i = ty; i < Ci; i += 8)
-        a0 = fmaf(__bfloat162float(wphi[static_cast<long long>(i) * Ca + C]), __bfloat162float(dt[static_cast<long long>(i) * Ca]), a0);
-    }
-    part[ty][tx] = a0;
+  if (blockIdx.y == 0) {     // block-uniform: the first tile row also emits e for its 64 columns
     __syncthreads();
-    if (ty == 0 && c < C) {
+    float* part = &t[0][0];  // reuse: [8][64]
+    const int cA = c0 + 2 * tx;
+    float a0 = 0.f, a1 = 0.f;
+    if (cA < C) {
+      const bf16* dt = dT + b * static_cast<long long>(Ci) * Ca + cA;
+      for (int i = ty; i < Ci; i += 8) {
+        const float w = __bfloat162float(wphi[static_cast<long long>(i) * Ca + C]);
+        const float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(dt + static_cast<long long>(i) * Ca));
+        a0 = fmaf(w, d.x, a0);
+        a1 = fmaf(w, d.y, a1);
+      }
+    }
+    part[ty * 64 + 2 * tx] = a0;
+    part[ty * 64 + 2 * tx + 1] = a1;
+    __syncthreads();
+    const int tid = ty * 32 + tx;
+    if (tid < 64 && c0 + tid < C) {
+      const int c = c0 + tid;
       float v = __bfloat162float(G[static_cast<long long>(c) * Ca + C]);
       if (H != nullptr) v += __bfloat162float(H[static_cast<long long>(c) * Ca + C]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v += part[i][tx];
+      for (int i = 0; i < 8; ++i) v += part[i * 64 + tid];
       evec[b * C + c] = v;
     }
   }
@@ -234,7 +251,7 @@ int gram_kprep(const bf16* Qb, const float* cvec, const float* k1, const float* 
 int gram_assemble_F(const bf16* G0, const bf16* Hf, const bf16* dT, const bf16* wphi, bf16* EF, float* evec, int B,
                     int C, int Ci, int Ca, cudaStream_t stream) {
   if (B > 65535) return set_error(GLF_ERR_INVALID, "gram form: more than 65535 sequences per call");
-  dim3 grid((C + 31) / 32, (C + 31) / 32, B);
+  dim3 grid((C + 63) / 64, (C + 63) / 64, B);
   gram_assemble_F_kernel<<<grid, dim3(32, 8), 0, stream>>>(G0, Hf, dT, wphi, EF, evec, C, Ci, Ca);
   return check_cuda(cudaGetLastError(), "gram_assemble_F launch");
 }
