@@ -274,8 +274,8 @@ def run_ours(args):
             graph.replay()
         else:
             compute()
-        if world > 1 and not allreduce_in_graph and not os.environ.get("GLF_BENCH_SKIP_ALLREDUCE"):   # (debug aid)
-            bucket.allreduce_mean()      # the only collective: fusion-weight gradients over NCCL / NVLink
+        if world > 1 and not allreduce_in_graph:
+            bucket.allreduce_mean()      # the only collective: fusion-weight gradients over NVLink (peer kernel / NCCL)
 
     for _ in range(max(args.warmup, 3)):
         run_step()
