@@ -406,10 +406,10 @@ def run_ours(args):
 def count_launches(clips: int, C: int) -> int:
     """Kernels launched by libglf_sm100a per step (fwd+bwd, both modules + gate), counted from the orchestration in
     glfusion_b200/csrc/glf_api.cu (memset/memcpy nodes excluded); agrees with profiles/r01_v11_launches.csv (39,
-    token-space form) and profiles/r01_v13_launches.csv (59, Gram form)."""
+    token-space form) and profiles/r01_v17_launches.csv (55, Gram form)."""
     if dot_algorithm(C) == "gram":
-        fwd_mod = 10     # prep_weights, S GEMM, border, T, M, W', Q~ GEMMs, cvec, U GEMM, bn_finalize
-        bwd_mod = 17     # finalize, R GEMM, border, kprep, dQ~, dW', dW~theta, dWz, dM, dW~g, dT, dW~phi, G0, H GEMMs,
+        fwd_mod = 9      # prep_weights, S (gram_kernel), T, M, W', Q~ GEMMs, cvec, U GEMM, bn_finalize
+        bwd_mod = 16     # finalize, R (gram_kernel), kprep, dQ~, dW', dW~theta, dWz, dM, dW~g, dT, dW~phi, G0, H GEMMs,
         #                  assemble_F, dX GEMM, unpack_grads
     else:
         fwd_mod = 6      # prep_weights, proj GEMM, M GEMM, W' GEMM, U GEMM, bn_finalize

@@ -325,11 +325,11 @@ int gram_token_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* s
       ks = (2 * 148) / B;
       if (ks < 1) ks = 1;
     }
-    GLF_TRY(gram_contraction(A, X, out_aug, scratch, rowsum, rowscale, B, N, C, Ca, ks, stream));
+    GLF_TRY(gram_contraction(A, X, out_aug, scratch, rowsum, rowscale, rowv, corner, 1, B, N, C, Ca, ks, stream));
     const int kb = (N + 63) / 64;
     if ((ks > kb ? kb : ks) > 1)
       return gram_assemble_aug(scratch, rowsum, rowv ? rowv : rowsum, rowscale, out_aug, B, C, Ca, corner, stream);
-    return gram_border(rowsum, rowv ? rowv : rowsum, rowscale, out_aug, B, C, Ca, corner, stream);
+    return 0;   // one CTA per sequence: the kernel wrote the border as well
   }
   GemmArgs g;
   g.A = opnd(A, 1, C, static_cast<long long>(N) * C);
@@ -1109,7 +1109,8 @@ GLF_API int glf_gram_contraction(const void* A, const void* X, void* D, float* c
   if (B <= 0 || N <= 0) return set_error(GLF_ERR_INVALID, "gram_contraction: empty input");
   if (ldd < C || ldd % 8 != 0) return set_error(GLF_ERR_INVALID, "gram_contraction: ldd must be >= C and a multiple of 8");
   return gram_contraction(reinterpret_cast<const bf16*>(A), reinterpret_cast<const bf16*>(X), reinterpret_cast<bf16*>(D),
-                          nullptr, colsum, nullptr, B, N, C, ldd, 1, reinterpret_cast<cudaStream_t>(stream));
+                          nullptr, colsum, nullptr, nullptr, 0.f, 0, B, N, C, ldd, 1,
+                          reinterpret_cast<cudaStream_t>(stream));
 }
 
 GLF_API int glf_bn_res_ln_fwd(int64_t rows, int C, const void* U, const void* X, const float* bn_a, const float* bn_b,

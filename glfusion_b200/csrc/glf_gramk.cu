@@ -33,6 +33,11 @@ struct GramKParams {
   float* outf;     // ksplit  > 1: [B][C][C] fp32, atomically accumulated (zeroed by the caller)
   float* rowsum;   // [B][C] column sums of A (stored, or atomically accumulated when ksplit > 1)
   const float* rowscale;   // optional [C]: bf16 output row r is scaled by rowscale[r] (ksplit == 1 path)
+  // ksplit == 1: the homogeneous border of the augmented matrix is written here as well (no separate launch):
+  //   column C = rowscale * column sums of A, row C = rowv (or the column sums when rowv is null), corner, zero padding
+  const float* rowv;       // optional [B][C]
+  float corner;
+  int border;              // 1: write the border (needs Ca >= C + 1)
 };
 
 __global__ void __launch_bounds__(GK_THREADS, 1)
@@ -135,9 +140,28 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
         if (++stage == GK_STAGES) { stage = 0; phase ^= 1u; }
       }
       if (t < p.C) {
+        const float cs = acc0 + acc1;
         float* dst = p.rowsum + static_cast<long long>(b) * p.C + t;
-        if (p.ksplit > 1) atomicAdd(dst, acc0 + acc1);
-        else *dst = acc0 + acc1;
+        if (p.ksplit > 1) {
+          atomicAdd(dst, cs);
+        } else {
+          *dst = cs;
+          if (p.border) {
+          // border of the augmented matrix: out[t][C .. Ca) = {scaled column sum, 0 ...}; out[C][t] = rowv or the sum
+          bf16* M = p.out + static_cast<long long>(b) * p.Ca * p.Ca;
+          const float rs = p.rowscale != nullptr ? p.rowscale[t] : 1.f;
+          if (p.Ca - p.C == 8) {
+            *reinterpret_cast<uint4*>(M + static_cast<long long>(t) * p.Ca + p.C) = make_uint4(pack_bf16(cs * rs, 0.f), 0u, 0u, 0u);
+          } else {
+            for (int j = p.C; j < p.Ca; ++j) M[static_cast<long long>(t) * p.Ca + j] = __float2bfloat16(j == p.C ? cs * rs : 0.f);
+          }
+          M[static_cast<long long>(p.C) * p.Ca + t] =
+              __float2bfloat16(p.rowv != nullptr ? p.rowv[static_cast<long long>(b) * p.C + t] : cs);
+          if (t == 0)
+            for (int j = p.C; j < p.Ca; ++j)
+              M[static_cast<long long>(p.C) * p.Ca + j] = __float2bfloat16(j == p.C ? p.corner : 0.f);
+          }
+        }
       }
     }
     // ---- epilogue: warp (mt, q) owns TMEM lanes 32q..32q+31 of accumulator mt = output rows 128 mt + 32 q + lane
@@ -183,10 +207,13 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
 
 bool gram_contraction_supported(int C) { return C == 128 || C == 256; }
 
-// out_aug rows / columns < C (bf16, ld = Ca, row r scaled by rowscale[r] if given) when ksplit == 1, else fp32
-// accumulation into `scratch` (zeroed here, unscaled); rowsum = column sums of A (unscaled).  The caller adds the homogeneous border (gram_border / gram_assemble_aug).
+// ksplit == 1: out_aug rows / columns < C (bf16, ld = Ca, row r scaled by rowscale[r] if given) and, with `border`, the
+// homogeneous border (column C = scaled column sums of A, row C = rowv or the column sums, corner, zero padding);
+// ksplit > 1: fp32 accumulation into `scratch` (zeroed here, unscaled) for gram_assemble_aug.
+// rowsum = column sums of A (unscaled).
 int gram_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* scratch, float* rowsum, const float* rowscale,
-                     int B, int N, int C, int Ca, int ksplit, cudaStream_t stream) {
+                     const float* rowv, float corner, int border, int B, int N, int C, int Ca, int ksplit,
+                     cudaStream_t stream) {
   if (!gram_contraction_supported(C)) return set_error(GLF_ERR_UNSUPPORTED, "gram_contraction: C must be 128 or 256");
   CUtensorMap tmA, tmX;
   int rc = make_tmap_bf16(&tmA, A, C, N, B, C, static_cast<long long>(N) * C, 64);
@@ -202,6 +229,8 @@ int gram_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* scratch
   p.ksplit = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.same = (A == X) ? 1 : 0;
   p.out = out_aug; p.outf = scratch; p.rowsum = rowsum; p.rowscale = rowscale;
+  p.rowv = rowv; p.corner = corner;
+  p.border = (border && Ca > C) ? 1 : 0;
   if (p.ksplit > 1) {
     rc = check_cuda(cudaMemsetAsync(scratch, 0, sizeof(float) * B * C * C, stream), "memset S");
     if (rc) return rc;

@@ -113,7 +113,8 @@ int gram_assemble_F(const bf16* G0, const bf16* Hf, const bf16* dT, const bf16* 
 // One CTA per sequence (glf_gramk.cu): D_b = A_b^T X_b for C = 128 / 256, operands streamed once
 bool gram_contraction_supported(int C);
 int gram_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* scratch, float* rowsum, const float* rowscale,
-                     int B, int N, int C, int Ca, int ksplit, cudaStream_t stream);
+                     const float* rowv, float corner, int border, int B, int N, int C, int Ca, int ksplit,
+                     cudaStream_t stream);
 int gram_unpack_grads(const float* dwaug, const glf_grads* g, int C, int Ci, int Ca, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------ gate + concat
