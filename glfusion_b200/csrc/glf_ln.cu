@@ -162,32 +162,54 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_fwd_tma_kernel(const LnFwdPar
 #pragma unroll
           for (int i = 0; i < 4; ++i) o[i] = add2(o[i], z0[i]);
         }
+        // both blocks' rows go through the two warp reductions TOGETHER (same two-pass arithmetic per block, half the
+        // dependent shuffle chains per row)
+        float2 v[NMOD][4];
+        float red[NMOD];
 #pragma unroll
         for (int m = 0; m < NMOD; ++m) {
-          float2 v[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = splat(0.f);
+          for (int i = 0; i < 4; ++i) v[m][i] = splat(0.f);
           if (cact) {
             float2 u[4], x[4];
             lds8p(st + (2 * m) * p.arr_bytes + roff, u);
             lds8p(st + (2 * m + 1) * p.arr_bytes + roff, x);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = add2(fma2(pa[m][i], u[i], pb[m][i]), x[i]);
+            for (int i = 0; i < 4; ++i) v[m][i] = add2(fma2(pa[m][i], u[i], pb[m][i]), x[i]);
           }
-          const float mu = warp_sum(hsum4(v)) * invC;
-          const float2 nmu = splat(-mu);
-          float2 d[4], q2 = splat(0.f);
+          red[m] = hsum4(v[m]);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+          for (int m = 0; m < NMOD; ++m) red[m] += __shfl_xor_sync(0xffffffffu, red[m], off);
+        }
+        float mu[NMOD];
+#pragma unroll
+        for (int m = 0; m < NMOD; ++m) {
+          mu[m] = red[m] * invC;
+          const float2 nmu = splat(-mu[m]);
+          float2 q2 = splat(0.f);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            d[i] = cact ? add2(v[i], nmu) : splat(0.f);
-            q2 = fma2(d[i], d[i], q2);
+            v[m][i] = cact ? add2(v[m][i], nmu) : splat(0.f);     // v now holds the centred values
+            q2 = fma2(v[m][i], v[m][i], q2);
           }
-          const float r = rsqrtf(warp_sum(q2.x + q2.y) * invC + p.eps);
+          red[m] = q2.x + q2.y;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+          for (int m = 0; m < NMOD; ++m) red[m] += __shfl_xor_sync(0xffffffffu, red[m], off);
+        }
+#pragma unroll
+        for (int m = 0; m < NMOD; ++m) {
+          const float r = rsqrtf(red[m] * invC + p.eps);
           const float2 r2 = splat(r);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) o[i] = fma2(d[i], mul2(pw[m][i], r2), o[i]);
+          for (int i = 0; i < 4; ++i) o[i] = fma2(v[m][i], mul2(pw[m][i], r2), o[i]);
           if (lane == 0 && p.mu[m] != nullptr) {
-            p.mu[m][row] = mu;
+            p.mu[m][row] = mu[m];
             p.r[m][row] = r;
           }
         }
