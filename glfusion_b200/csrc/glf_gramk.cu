@@ -20,7 +20,8 @@ namespace glf {
 namespace {
 
 constexpr int GK_THREADS = 64 + 256;
-constexpr int GK_STAGES = 3;
+constexpr int GK_STAGES = 3;                       // A != X: three stages of (A block + X block)
+constexpr int GK_MAX_STAGES = 6;                   // A == X: the same ring holds six single-block stages
 constexpr uint32_t GK_BLK = 64 * 256 * 2;          // one operand block: 64 tokens x 256 channels (4 boxes of 64 x 64)
 constexpr uint32_t GK_STAGE = 2 * GK_BLK;          // A block + X block
 constexpr uint32_t GK_SMEM = GK_STAGES * GK_STAGE + 1024;
@@ -43,8 +44,8 @@ struct GramKParams {
 __global__ void __launch_bounds__(GK_THREADS, 1)
     gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmX, const GramKParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[GK_STAGES];
-  __shared__ uint64_t empty_bar[GK_STAGES];
+  __shared__ uint64_t full_bar[GK_MAX_STAGES];
+  __shared__ uint64_t empty_bar[GK_MAX_STAGES];
   __shared__ uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_holder;
 
@@ -58,12 +59,16 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
   const int nkb = min(p.kb_total, kb0 + p.kb_per_split) - kb0;
   const int nbox = p.C / 64;     // 64-channel boxes per block
   const int MT = p.C / 128;      // 128-row accumulators
+  // S = X^T X loads one block per k-step: twice the stages in the same ring (more bytes in flight per SM: the product
+  // is bound by the latency of its own HBM stream otherwise)
+  const int nstages = p.same ? GK_MAX_STAGES : GK_STAGES;
+  const uint32_t stage_bytes = p.same ? GK_BLK : GK_STAGE;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmX);
 #pragma unroll
-    for (int s = 0; s < GK_STAGES; ++s) {
+    for (int s = 0; s < GK_MAX_STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1 + 8);   // MMA commit + the eight column-sum warps
     }
@@ -86,11 +91,11 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
         const uint32_t fb = smem_u32(&full_bar[stage]);
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
         mbar_expect_tx(fb, bytes);
-        const uint32_t sa = smem_base + stage * GK_STAGE;
+        const uint32_t sa = smem_base + stage * stage_bytes;
         for (int j = 0; j < nbox; ++j) tma_load_4d(&tmA, fb, sa + j * 8192, j * 64, k0, b, 0);
         if (!p.same)
           for (int j = 0; j < nbox; ++j) tma_load_4d(&tmX, fb, sa + GK_BLK + j * 8192, j * 64, k0, b, 0);
-        if (++stage == GK_STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -101,7 +106,7 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
       for (int it = 0; it < nkb; ++it) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         tc_fence_after();
-        const uint32_t sa = smem_base + stage * GK_STAGE;
+        const uint32_t sa = smem_base + stage * stage_bytes;
         const uint32_t sb = p.same ? sa : sa + GK_BLK;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -112,7 +117,7 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
           }
         }
         umma_commit(smem_u32(&empty_bar[stage]));
-        if (++stage == GK_STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
       umma_commit(smem_u32(&tmem_full_bar));
     }
@@ -128,7 +133,7 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
       for (int it = 0; it < nkb; ++it) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         if (t < p.C) {
-          const uint8_t* blk = smem_gen + stage * GK_STAGE + off0;
+          const uint8_t* blk = smem_gen + stage * stage_bytes + off0;
 #pragma unroll 8
           for (int k = 0; k < 64; k += 2) {
             acc0 += __bfloat162float(*reinterpret_cast<const bf16*>(blk + k * 128 + ((chunk ^ (k & 7)) << 4)));
@@ -137,7 +142,7 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));
-        if (++stage == GK_STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
       if (t < p.C) {
         const float cs = acc0 + acc1;
