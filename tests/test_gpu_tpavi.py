@@ -97,6 +97,28 @@ def test_gram_many_sequences(C):
             assert_close("grad:" + k, pp.grad, go[k], 3e-2, abs_floor=1e-3)
 
 
+@pytest.mark.parametrize("C,T,H,W", [(96, 2, 16, 16), (512, 4, 24, 24), (192, 3, 20, 20)])
+@pytest.mark.parametrize("algo", ["gram", "token"])
+def test_dot_other_widths(C, T, H, W, algo):
+    """Channel counts away from the tuned 128 / 256: C = 96 and 192 (the Gram contraction falls back to the tile GEMM
+    with its row-sum side product, ragged 64-column boxes), C = 512 (two n-tiles per product, C > 256 LayerNorm path)."""
+    B = 2
+    p = O.init_params(C, seed=61, randomize_affine=True)
+    gen = torch.Generator().manual_seed(62)
+    x = torch.randn(B, C, T, H, W, generator=gen)
+    dz = torch.randn(B, C, T, H, W, generator=gen)
+    zo, dxo, go, _ = O.tpavi_dot_closed_form(x.double(), dz.double(), {k: (v.double() if v.is_floating_point() else v)
+                                                                       for k, v in p.items()})
+    m = load_module_from_params(TPAVIModule, p, C, "dot", True).train()
+    with dot_algo(algo):
+        z, dx = _run(m, x.to(DEV, torch.bfloat16), dz.to(DEV, torch.bfloat16))
+    assert_close("z", z, zo, BF16_TOL)
+    assert_close("dx", dx, dxo, BF16_TOL)
+    for k, pp in m.named_parameters():
+        if not k.startswith("align_channel"):
+            assert_close("grad:" + k, pp.grad, go[k], 3e-2, abs_floor=1e-3)
+
+
 def test_eval_no_grad_inference_and_zero_init_trap():
     C = 128
     m = TPAVIModule(C).to(DEV).eval()          # reference init: BN gamma=beta=0 -> z == LayerNorm(x) exactly (F3)
