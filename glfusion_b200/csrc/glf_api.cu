@@ -10,7 +10,7 @@
 //         BN finalise, then  Z = LN(BN(U) + X)    HBM-bound fused epilogue
 //   bwd:  LN/BN backward (two HBM-bound passes), then six tcgen05 GEMMs (dTheta, dW', dPhi, dG, dWcat, dX) and two
 //         small fp32 products (dW_z, dM).
-// When the sequences are long against the channel count (N >= 4 C) mode='dot' runs in its Gram form instead
+// When the sequences are long against the channel count (N >= 5 C) mode='dot' runs in its Gram form instead
 // (tpavi_fwd_gram / tpavi_bwd_gram below; oracle/tpavi_oracle.py: tpavi_dot_gram_form): theta / phi / g and dU are never
 // materialised, the only token-sized products are S = X^T X, U = X Q^T, R = dV^T X and dX = [dV | X] [E ; F].
 #include <cstdarg>
@@ -106,8 +106,12 @@ int make_dims(const glf_desc* d, Dims* o) {
   const bool gram_ok = o->dot && d->precision == GLF_PRECISION_BF16 && o->B <= 65535;
   if (d->reserved[1] == 2 && !gram_ok)
     return set_error(GLF_ERR_UNSUPPORTED, "the Gram form needs mode='dot', GLF_PRECISION_BF16 and B <= 65535");
-  // per-sequence [C x C] products cost ~14 C^3 against 27 N C^2 saved token-space work: worth it for N >= 4 C
-  o->gram = gram_ok && (d->reserved[1] == 2 || (d->reserved[1] == 0 && o->N >= 4LL * d->C));
+  // per-sequence [C x C] products cost ~15 C^3 against 3.5 N C^2 of saved token-space FLOPs and 11 saved activation
+  // passes.  Measured crossover on B200 (profiles/algo_crossover.py, r01_algo_crossover.txt): N/C between 3 and 6 at
+  // C = 128 / 256 / 1024; at C = 512 the token-space form still wins at N/C = 6 (no one-CTA-per-sequence contraction
+  // kernel above C = 256, and the products are not yet tensor-bound as at C = 1024).
+  const long long thr = (d->C > 256 && d->C <= 768) ? 8 : 5;
+  o->gram = gram_ok && (d->reserved[1] == 2 || (d->reserved[1] == 0 && o->N >= thr * d->C));
   o->Ca = gram_ca(d->C);
   return 0;
 }

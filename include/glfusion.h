@@ -67,7 +67,7 @@ typedef struct glf_desc {
                           glf_tpavi_bwd starts after the LayerNorm backward; the caller runs that stage for MGFM and
                           MLFM together with glf_fusion_ln_fwd / glf_fusion_ln_bwd (below).
                           reserved[1]: algorithm of mode='dot' (both are exact reassociations of ours.py:881-902):
-                          0 = the library chooses (Gram form when N >= 4 C), 1 = token-space form (theta/phi/g formed
+                          0 = the library chooses (Gram form when N >= 5 C), 1 = token-space form (theta/phi/g formed
                           per token), 2 = Gram form (S = X~^T X~ per sequence, channel-space products only).
                           Others: 0. */
 } glf_desc;

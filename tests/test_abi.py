@@ -51,7 +51,7 @@ def test_sizes_are_host_only_and_scale_with_tokens():
     assert s2.saved_bytes > 1.9 * s1.saved_bytes * 0.98
     assert s1.ws_bwd_bytes >= rows * (256 * 2 + 3 * 128) * 2
     assert s1.saved_bytes % 256 == 0 and s1.ws_fwd_bytes % 256 == 0 and s1.ws_bwd_bytes % 256 == 0
-    # the Gram form keeps U and per-sequence [C x C] matrices, never the per-token projections; auto picks it (N >= 4 C)
+    # the Gram form keeps U and per-sequence [C x C] matrices, never the per-token projections; auto picks it (N >= 5 C)
     sg, sa = L.GlfSizes(), L.GlfSizes()
     assert lib.glf_tpavi_sizes(C.byref(_desc(algo=2)), C.byref(sg)) == 0
     assert lib.glf_tpavi_sizes(C.byref(_desc(algo=0)), C.byref(sa)) == 0
