@@ -191,6 +191,33 @@ class _FusionFunction(torch.autograd.Function):
         return tuple(out)
 
 
+class _GateConcatFunction(torch.autograd.Function):
+    """gate + view concat alone (ours.py:1802-1820, 1826-1827): -> X_g, X_l as [B,C,V,h,w] views of token-major buffers."""
+
+    @staticmethod
+    def forward(ctx, weight, V, x_dtype, *tensors):
+        f4, cls, ctr = tensors[:V], tensors[V:2 * V], tensors[2 * V:3 * V]
+        xg, xl, gate, f4c, clsc, ctrc = gate_concat_forward(f4, cls, ctr, weight, x_dtype)
+        ctx.weight, ctx.V = weight, V
+        ctx.save_for_backward(gate, *f4c, *clsc, *ctrc)
+        return xg.permute(0, 4, 1, 2, 3), xl.permute(0, 4, 1, 2, 3)
+
+    @staticmethod
+    def backward(ctx, dxg, dxl):
+        V = ctx.V
+        saved = ctx.saved_tensors
+        gate, rest = saved[0], saved[1:]
+        f4, cls, ctr = rest[:V], rest[V:2 * V], rest[2 * V:3 * V]
+
+        def tok(t, like):
+            t = torch.zeros_like(like) if t is None else t
+            return t.permute(0, 2, 3, 4, 1).contiguous()
+        like = torch.empty((f4[0].shape[0], f4[0].shape[1], V) + tuple(f4[0].shape[2:]), dtype=dxg.dtype if dxg is not None
+                           else dxl.dtype, device=f4[0].device)
+        df4, dcls, dctr = gate_concat_backward(f4, cls, ctr, gate, tok(dxg, like), tok(dxl, like), ctx.weight)
+        return (None, None, None) + tuple(df4) + tuple(dcls) + tuple(dctr)
+
+
 class GlobalLocalFusion(nn.Module):
     """MGFM + MLFM (attribute names follow ``Global_and_Local``: ``global_attn`` / ``local_attn``, ours.py:1746-1747,
     so the corresponding slice of a reference checkpoint loads unchanged)."""
@@ -225,6 +252,27 @@ class GlobalLocalFusion(nn.Module):
             raise ValueError("f4, cls_logits and ctr_logits need one entry per view")
         pg, pl = self.global_attn._plist(), self.local_attn._plist()
         return _FusionFunction.apply(self, V, len(pg), *f4, *cls_logits, *ctr_logits, *pg, *pl)
+
+    def forward_parts(self, f4: Dict[str, torch.Tensor], mask_bb_logits: Dict[str, torch.Tensor],
+                      ctr_logits: Dict[str, torch.Tensor]):
+        """Like ``forward`` but also returns the two parts the reference network hands back to its trainer
+        (ours.py:1843 ``return mask, mask_bb, f4_global_fusion, f4_local_fusion``; the cycle-consistency pass of
+        R/main.py:211-235 uses ``f4_global_fusion`` alone): ``(f4_fusion, f4_global_fusion, f4_local_fusion)``, dicts
+        view -> [B,C,h,w].  The parts need their own outputs, so the two blocks run as separate autograd nodes (gate
+        kernel, then one ``TPAVIModule`` call each) instead of the single fused node of ``forward``."""
+        views: List[str] = list(f4.keys())
+        V = len(views)
+        xs = [f4[v] for v in views]
+        x_dtype = torch.float32 if self.global_attn._precision_id() == L.PRECISION_F32X3 else torch.bfloat16
+        xg, xl = _GateConcatFunction.apply(self.center_aware_weight, V, x_dtype, *xs,
+                                           *[mask_bb_logits[v] for v in views], *[ctr_logits[v] for v in views])
+        zg, _ = self.global_attn(xg)
+        zl, _ = self.local_attn(xl)
+        if zg.dtype != xs[0].dtype:
+            zg, zl = zg.to(xs[0].dtype), zl.to(xs[0].dtype)
+        glob = {v: zg[:, :, i] for i, v in enumerate(views)}
+        loc = {v: zl[:, :, i] for i, v in enumerate(views)}
+        return {v: glob[v] + loc[v] for v in views}, glob, loc
 
     def forward(self, f4: Dict[str, torch.Tensor], mask_bb_logits: Dict[str, torch.Tensor],
                 ctr_logits: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:

@@ -125,3 +125,41 @@ def test_glue_golden_fp32_precision():
         assert_close(f"df4:{v}", f4[v].grad, g[f"df4:{v}"], 1e-4)
         assert_close(f"dcls:{v}", cl[v].grad, g[f"dcls:{v}"], 5e-4)      # __expf sigmoids in the gate chain
         assert_close(f"dctr:{v}", ct[v].grad, g[f"dctr:{v}"], 5e-4)
+
+
+def test_forward_parts_matches_reference_return_values():
+    """ours.py:1843 returns f4_global_fusion / f4_local_fusion next to the fused sum, and the cycle-consistency pass
+    (main.py:211-235) back-propagates through the spatial sums of the GLOBAL part alone."""
+    B, C, V, h, w = 3, 128, 3, 12, 10
+    pg = O.init_params(C, seed=71, randomize_affine=True)
+    pl = O.init_params(C, seed=72, randomize_affine=True)
+    gen = torch.Generator().manual_seed(73)
+    f4 = [torch.randn(B, C, h, w, generator=gen) for _ in range(V)]
+    cl = [torch.randn(B, 5, h, w, generator=gen) for _ in range(V)]
+    ct = [torch.randn(B, 1, h, w, generator=gen) for _ in range(V)]
+    wsum = torch.randn(B, C, generator=gen)
+    # oracle: the reference's lines on CPU
+    f4o = [t.clone().requires_grad_(True) for t in f4]
+    qg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and k not in O.BUFFER_KEYS else v.clone()) for k, v in pg.items()}
+    ql = {k: v.clone() for k, v in pl.items()}
+    xg, xl = O.gate_concat(f4o, cl, ct)
+    zg = O.tpavi_forward(xg, qg)
+    zl = O.tpavi_forward(xl, ql)
+    cyc = sum((zg[:, :, i].sum(dim=(2, 3)) * wsum).sum() for i in range(V))      # main.py:229 spatial sums
+    cyc.backward()
+    f = _build(C, pg, pl)
+    f4d = [t.to(DEV, torch.bfloat16).requires_grad_(True) for t in f4]
+    keys = [str(i) for i in range(V)]
+    fus, glob, loc = f.forward_parts(dict(zip(keys, f4d)), dict(zip(keys, [t.to(DEV) for t in cl])),
+                                     dict(zip(keys, [t.to(DEV) for t in ct])))
+    for i, k in enumerate(keys):
+        assert_close(f"global:{k}", glob[k], zg[:, :, i], BF16_TOL)
+        assert_close(f"local:{k}", loc[k], zl[:, :, i], BF16_TOL)
+        assert_close(f"fusion:{k}", fus[k], zg[:, :, i] + zl[:, :, i], BF16_TOL)
+    cyc_d = sum((glob[k].float().sum(dim=(2, 3)) * wsum.to(DEV)).sum() for k in keys)
+    cyc_d.backward()
+    torch.cuda.synchronize()
+    for i in range(V):
+        assert_close(f"df4:{i}", f4d[i].grad, f4o[i].grad, 3e-2)
+    assert f.local_attn.theta.weight.grad is None            # the local block is not on the cycle pass's path
+    assert_close("grad_g:theta.weight", f.global_attn.theta.weight.grad, qg["theta.weight"].grad, 3e-2)
