@@ -85,3 +85,24 @@ def test_invalid_descriptors_are_errors_with_messages(kw, frag):
     assert frag.lower() in lib.glf_last_error().decode().lower()
     with pytest.raises(L.GlfError):
         L.check(rc)
+
+
+@pytest.mark.parametrize("C_,T,H,W", [(256, 4, 28, 28), (256, 4, 14, 14), (256, 4, 16, 20), (512, 4, 28, 28),
+                                      (512, 8, 24, 24), (1024, 4, 40, 40), (128, 2, 16, 20), (2048, 3, 28, 28)])
+def test_automatic_dot_algorithm_follows_the_documented_rule(C_, T, H, W):
+    """reserved[1] = 0: Gram form iff N >= 5 C (8 C for 256 < C <= 768) — observable through the blob sizes; bench.py
+    mirrors the same rule for its FLOP / launch accounting."""
+    import bench
+    lib = glfusion_b200.load_library()
+    N = T * H * W
+    thr = 8 if 256 < C_ <= 768 else 5
+    expect = 2 if N >= thr * C_ else 1
+    kw = dict(C=C_, Ci=C_ // 2, T=T, H=H, W=W)
+    sa, se, so = L.GlfSizes(), L.GlfSizes(), L.GlfSizes()
+    assert lib.glf_tpavi_sizes(C.byref(_desc(algo=0, **kw)), C.byref(sa)) == 0
+    assert lib.glf_tpavi_sizes(C.byref(_desc(algo=expect, **kw)), C.byref(se)) == 0
+    assert lib.glf_tpavi_sizes(C.byref(_desc(algo=3 - expect, **kw)), C.byref(so)) == 0
+    assert (sa.saved_bytes, sa.ws_bwd_bytes) == (se.saved_bytes, se.ws_bwd_bytes)
+    assert (sa.saved_bytes, sa.ws_bwd_bytes) != (so.saved_bytes, so.ws_bwd_bytes)
+    if (T, H, W) == (bench.V, bench.HH, bench.WW):
+        assert bench.dot_algorithm(C_) == ("gram" if expect == 2 else "token")
