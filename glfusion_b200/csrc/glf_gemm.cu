@@ -294,6 +294,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const uint32_t use = static_cast<uint32_t>(local >> 1);
       const bool use_bias = p.bias != nullptr && split == 0;
       const float* biasb = p.bias != nullptr ? p.bias + static_cast<long long>(b) * p.bias_stride : nullptr;
+      // per-batch bias (not staged CTA-wide): when this warp owns a single 32-column chunk per tile, its bias slice is
+      // fetched BEFORE the wait for the accumulator, so the global-load latency hides behind the tile's MMAs
+      constexpr bool BIAS_EARLY = NCHUNK <= 4;
+      if (BIAS_EARLY && use_bias && !bias_all && cc0 < NCHUNK) {
+        const int gcb = n0 + cc0 * 32 + lane;
+        wbias[lane] = gcb < p.N ? biasb[gcb] : 0.f;
+      }
       mbar_wait(smem_u32(&tmem_full_bar[acc]), use & 1u);
       tc_fence_after();
 #pragma unroll 1
@@ -319,7 +326,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const bool full = rows_valid >= 32 && gc0 + 32 <= p.N;
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
-        if (use_bias && !bias_all) wbias[lane] = (gc0 + lane < p.N) ? biasb[gc0 + lane] : 0.f;
+        if (!BIAS_EARLY && use_bias && !bias_all) wbias[lane] = (gc0 + lane < p.N) ? biasb[gc0 + lane] : 0.f;
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
