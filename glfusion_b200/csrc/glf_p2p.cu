@@ -34,16 +34,38 @@ struct P2PParams {
   float scale;
 };
 
+// Bounded spins: a rank that never arrives (crashed peer, mismatched call counts) traps this kernel after ~20 s of wall
+// clock -- the launch then reports an error on the host -- instead of hanging the GPU.
+constexpr unsigned long long P2P_TIMEOUT_NS = 20000000000ull;
+__device__ __forceinline__ unsigned long long p2p_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void signal_peer(uint32_t* addr) {
   uint32_t old;
+  unsigned long long t0 = 0;
+  unsigned spins = 0;
   do {
     asm volatile("atom.global.release.sys.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "l"(addr) : "memory");
+    if (old != 0u && ++spins > 4096u) {
+      const unsigned long long now = p2p_now_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > P2P_TIMEOUT_NS) __trap();
+    }
   } while (old != 0u);
 }
 __device__ __forceinline__ void wait_own(uint32_t* addr) {
   uint32_t old;
+  unsigned long long t0 = 0;
+  unsigned spins = 0;
   do {
     asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], 1, 0;" : "=r"(old) : "l"(addr) : "memory");
+    if (old != 1u && ++spins > 4096u) {
+      const unsigned long long now = p2p_now_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > P2P_TIMEOUT_NS) __trap();
+    }
   } while (old != 1u);
 }
 __device__ __forceinline__ float4 ld_sys_v4(const float* p) {
