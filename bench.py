@@ -395,6 +395,7 @@ def run_ours(args):
     out.update(kernel_probe(args, dev, clips, C, pk))
     if dot_algorithm(C) == "gram":
         out["roofline_secondary"] = gram_probe(dev, clips, C, pk)
+        out["roofline_gemm"] = dx_gemm_probe(dev, clips, C, pk)
     out["gpu_launches"] = (count_launches(clips, C) + (1 if p2p else 0)) * args.steps
     out["config"]["host_numa"] = (f"process bound to the {numa_cpus} CPUs local to its GPU (NVML affinity)"
                                   if numa_cpus else "no NUMA binding")
@@ -515,6 +516,42 @@ def gram_probe(dev, clips, C, pk):
             "frac": round(ach / pk["bf16_tflops"], 4), "traffic": traffic,
             "algorithmic_flops_per_launch": flops, "ms_per_launch": round(ms, 4),
             "hbm_gbs_same_launch": round(B * N * C * 2 / (ms * 1e-3) / 1e9, 1)}
+
+
+def dx_gemm_probe(dev, clips, C, pk):
+    """The largest tile-GEMM launch of the step, timed alone: dX_b = [dV_b | X_b] [E_b ; F_b] + e_b + dV_b (K = 2C, per
+    sequence B operand, residual addend = the first half of the A operand, 256-row CTA super-tiles).  HBM-bound at
+    C = 256: reads dV and X, writes dX = 3 bf16 passes over [rows, C]."""
+    import ctypes as Ct
+    from glfusion_b200 import _lib as L
+    lib = L.load()
+    B, N = clips * F, V * HH * WW
+    A = torch.randn(B, N, 2 * C, device=dev).to(torch.bfloat16)           # [dV | X] side by side
+    Bm = (torch.randn(B, C, 2 * C, device=dev) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(C, device=dev)
+    D = torch.empty(B, N, C, device=dev, dtype=torch.bfloat16)
+    stream = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def launch():
+        L.check(lib.glf_gemm_bf16(L.ptr(A), L.ptr(Bm), L.ptr(D), N, C, 2 * C, B, 0, 0, 2 * C, 2 * C, C, N * 2 * C,
+                                  C * 2 * C, N * C, L.ptr(bias), 1.0, L.ptr(A), 2 * C, N * 2 * C, 0, 1, None, stream))
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 10
+    e0.record()
+    for _ in range(n):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    alg_bytes = 3 * B * N * C * 2
+    ach = alg_bytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "gemm_kernel<0,*,128,2> (dX = [dV | X][E ; F] + e + dV, K = 2C)",
+            "achieved": round(ach, 1), "peak": pk["hbm_gbs"], "peak_source": pk["source"], "unit": "GB/s",
+            "frac": round(ach / pk["hbm_gbs"], 4), "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+            "ms_per_launch": round(ms, 4), "inputs": "617 MB per launch, larger than the 126 MB L2"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
