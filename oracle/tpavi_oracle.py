@@ -21,13 +21,16 @@ nn.LayerNorm, and is pinned against the *real* reference module:
   ``tests/test_oracle.py`` checks this file against those vectors (and against the live reference when
   ``/root/reference`` exists).  So parity is pinned on outputs of the reference itself run here.
 
-Two restatements are provided:
+Three restatements are provided:
 
 1. ``tpavi_forward``                — literal order of operations (materialises the N x N matrix), autograd gives
                                      the backward exactly as the reference's autograd would.
 2. ``tpavi_dot_closed_form``        — the reassociated ``mode='dot'`` algorithm  y = Theta (Phi^T G) / N with a
                                      hand-derived backward, chunkable, usable in fp64 at
                                      sequence lengths where N x N cannot be materialised.
+3. ``tpavi_dot_gram_form``          — the second exact reassociation (Gram matrix S = X~^T X~ per sequence, every
+                                     other product in channel space) that libglf_sm100a runs when N >= 5 C, with its
+                                     hand-derived backward; pinned to the same golden vectors.
 """
 from __future__ import annotations
 
