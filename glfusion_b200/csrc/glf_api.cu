@@ -402,44 +402,50 @@ int tpavi_fwd_gram(const glf_desc* d, const Dims& m, const void* x, const glf_we
   }
   // S_b = X_b^T X_b, s_b = X_b^T 1   ->   S~_b
   GLF_TRY(gram_token_contraction(X, X, s.Sa, wf.Sf, s.sfv, nullptr, nullptr, static_cast<float>(N), B, N, C, Ca, stream));
-  {  // T_b = W~phi S~_b                      [Ci x Ca]   (= Phi_b^T X~_b; S~ is symmetric)
-    GemmArgs g;
-    g.A = opnd(s.waug + CiCa, 0, Ca, 0);
-    g.B = opnd(s.Sa, 0, Ca, CaCa);
-    g.B.rows = C1;
-    g.M = Ci; g.N = Ca; g.K = C1; g.batch = B;
-    g.bn_hint = wide;
-    g.D = s.T; g.ldd = Ca; g.strideD = CiCa;
-    GLF_TRY(gemm(g, stream));
+  if (gram_chain_supported(C, Ci)) {
+    // T~, M, W', Q~ and c of every sequence in one launch, one CTA per sequence (glf_chain.cu)
+    GLF_TRY(gram_chain_fwd(s.Sa, s.sfv, s.waug, s.wz, w->phi_b, w->g_b, w->theta_b, s.T, s.Mb, s.Wp, s.Qb, s.cvec, B, N,
+                           stream));
+  } else {
+    {  // T_b = W~phi S~_b                      [Ci x Ca]   (= Phi_b^T X~_b; S~ is symmetric)
+      GemmArgs g;
+      g.A = opnd(s.waug + CiCa, 0, Ca, 0);
+      g.B = opnd(s.Sa, 0, Ca, CaCa);
+      g.B.rows = C1;
+      g.M = Ci; g.N = Ca; g.K = C1; g.batch = B;
+      g.bn_hint = wide;
+      g.D = s.T; g.ldd = Ca; g.strideD = CiCa;
+      GLF_TRY(gemm(g, stream));
+    }
+    {  // M_b = T_b W~g^T / N                   [Ci x Ci]   (= Phi_b^T G_b / N)
+      GemmArgs g;
+      g.A = opnd(s.T, 0, Ca, CiCa);
+      g.B = opnd(s.waug + 2 * CiCa, 0, Ca, 0);
+      g.M = Ci; g.N = Ci; g.K = C1; g.batch = B;
+      g.alpha = 1.f / static_cast<float>(N);
+      g.D = s.Mb; g.ldd = Ci; g.strideD = CiCi;
+      GLF_TRY(gemm(g, stream));
+    }
+    {  // W'_b = Wz M_b^T                       [C x Ci]
+      GemmArgs g;
+      g.A = opnd(s.wz, 0, Ci, 0);
+      g.B = opnd(s.Mb, 0, Ci, CiCi);
+      g.M = C; g.N = Ci; g.K = Ci; g.batch = B;
+      g.D = s.Wp; g.ldd = Ci; g.strideD = CCi;
+      GLF_TRY(gemm(g, stream));
+    }
+    {  // Q~_b = W'_b W~theta                   [C x Ca]    (B operand = W~theta read MN-major: stored [K = i][rows = a])
+      GemmArgs g;
+      g.A = opnd(s.Wp, 0, Ci, CCi);
+      g.B = opnd(s.waug, 1, Ca, 0);
+      g.B.rows = C1;
+      g.M = C; g.N = Ca; g.K = Ci; g.batch = B;
+      g.bn_hint = wide;
+      g.D = s.Qb; g.ldd = Ca; g.strideD = CCa;
+      GLF_TRY(gemm(g, stream));
+    }
+    GLF_TRY(gram_cvec(s.Wp, w->theta_b, s.cvec, B, C, Ci, stream));   // c_b = W'_b b_theta, kept in fp32
   }
-  {  // M_b = T_b W~g^T / N                   [Ci x Ci]   (= Phi_b^T G_b / N)
-    GemmArgs g;
-    g.A = opnd(s.T, 0, Ca, CiCa);
-    g.B = opnd(s.waug + 2 * CiCa, 0, Ca, 0);
-    g.M = Ci; g.N = Ci; g.K = C1; g.batch = B;
-    g.alpha = 1.f / static_cast<float>(N);
-    g.D = s.Mb; g.ldd = Ci; g.strideD = CiCi;
-    GLF_TRY(gemm(g, stream));
-  }
-  {  // W'_b = Wz M_b^T                       [C x Ci]
-    GemmArgs g;
-    g.A = opnd(s.wz, 0, Ci, 0);
-    g.B = opnd(s.Mb, 0, Ci, CiCi);
-    g.M = C; g.N = Ci; g.K = Ci; g.batch = B;
-    g.D = s.Wp; g.ldd = Ci; g.strideD = CCi;
-    GLF_TRY(gemm(g, stream));
-  }
-  {  // Q~_b = W'_b W~theta                   [C x Ca]    (B operand = W~theta read MN-major: stored [K = i][rows = a])
-    GemmArgs g;
-    g.A = opnd(s.Wp, 0, Ci, CCi);
-    g.B = opnd(s.waug, 1, Ca, 0);
-    g.B.rows = C1;
-    g.M = C; g.N = Ca; g.K = Ci; g.batch = B;
-    g.bn_hint = wide;
-    g.D = s.Qb; g.ldd = Ca; g.strideD = CCa;
-    GLF_TRY(gemm(g, stream));
-  }
-  GLF_TRY(gram_cvec(s.Wp, w->theta_b, s.cvec, B, C, Ci, stream));   // c_b = W'_b b_theta, kept in fp32
   int np = 0;
   {  // U_b = X_b Q_b^T + c_b   (+ BatchNorm column statistics); bz stays folded into the BN affine
     GemmArgs g;
@@ -469,8 +475,8 @@ int tpavi_fwd_gram(const glf_desc* d, const Dims& m, const void* x, const glf_we
 }
 
 // Continues after the LayerNorm backward and bn_bwd_finalize: wb.dV, wb.k1..k3 are valid.
-int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved& s, const WsBwd& wb, void* dx,
-                   const glf_grads* g_, cudaStream_t stream) {
+int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const glf_weights* w, const Saved& s, const WsBwd& wb,
+                   void* dx, const glf_grads* g_, cudaStream_t stream) {
   const int C = m.C, Ci = m.Ci, Ca = m.Ca, C1 = m.C + 1;
   const int N = static_cast<int>(m.N), B = static_cast<int>(m.B);
   const long long CaCa = static_cast<long long>(Ca) * Ca, CiCa = static_cast<long long>(Ci) * Ca;
@@ -482,9 +488,16 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved&
   // k1 * [R_b | rv_b]  with R_b = dV_b^T X_b, rv_b = dV_b^T 1: the BatchNorm-backward scale k1 (per channel of dV =
   // row of R) is applied in fp32 by the contraction's epilogue
   GLF_TRY(gram_token_contraction(wb.dV, X, wb.Rb, wb.Rf, wb.rv, s.sfv, wb.k1, static_cast<float>(N), B, N, C, Ca, stream));
+  // One CTA per sequence runs dQ~ -> dW' -> dM -> dT~ -> F (and E, e) in a single launch (glf_chain.cu); the four
+  // weight-gradient sums over the sequences below then read its dQ~, dW', dM / N and dT~.
+  const bool chain = gram_chain_supported(C, Ci);
+  if (chain)
+    GLF_TRY(gram_chain_bwd(s.Sa, s.Qb, s.waug, s.wz, wb.Rb, s.sfv, s.cvec, wb.rv, wb.k1, wb.k2, wb.k3, w->theta_b,
+                           w->phi_b, w->g_b, bn_train ? 1 : 0, wb.dQa, wb.dWpb, wb.dM, wb.dT, wb.EF, wb.evec, B, N,
+                           stream));
   // Qk = k2 Q~ (column C: k2 c + k3), E = k1 Q
-  GLF_TRY(gram_kprep(s.Qb, s.cvec, wb.k1, wb.k2, wb.k3, wb.AK, wb.EF, B, C, Ca, stream));
-  {  // dQ~_b = dU_b^T X~_b = Qk_b S~_b + k1 [R_b | rv_b]     [C x Ca]   (S~ is symmetric; the second term is the addend)
+  if (!chain) GLF_TRY(gram_kprep(s.Qb, s.cvec, wb.k1, wb.k2, wb.k3, wb.AK, wb.EF, B, C, Ca, stream));
+  if (!chain) {  // dQ~_b = dU_b^T X~_b = Qk_b S~_b + k1 [R_b | rv_b]     [C x Ca]   (S~ is symmetric; the second term is the addend)
     GemmArgs g;
     g.A = opnd(wb.AK, 0, Ca, CCa);
     g.B = opnd(s.Sa, 0, Ca, CaCa);
@@ -495,7 +508,7 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved&
     g.D = wb.dQa; g.ldd = Ca; g.strideD = CCa;
     GLF_TRY(gemm(g, stream));
   }
-  {  // dW'_b = dQ~_b W~theta^T               [C x Ci]
+  if (!chain) {  // dW'_b = dQ~_b W~theta^T               [C x Ci]
     GemmArgs g;
     g.A = opnd(wb.dQa, 0, Ca, CCa);
     g.B = opnd(s.waug, 0, Ca, 0);
@@ -525,7 +538,7 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved&
     g.D = g_->wz_w; g.ldd = Ci; g.strideD = 0;
     GLF_TRY(gemm(g, stream));
   }
-  {  // dM_b = dW'_b^T Wz                     [Ci x Ci]
+  if (!chain) {  // dM_b = dW'_b^T Wz                     [Ci x Ci]
     GemmArgs g;
     g.A = opnd(wb.dWpb, 1, Ci, CCi);
     g.B = opnd(s.wz, 1, Ci, 0);
@@ -540,12 +553,12 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved&
     g.B.rows = C1;
     g.M = Ci; g.N = Ca; g.K = Ci; g.batch = B;
     g.bn_hint = wide;
-    g.alpha = invN;
+    g.alpha = chain ? 1.f : invN;   // the chain kernel stores dM / N
     g.out_kind = 2;
     g.D = wb.dwaug + 2 * CiCa; g.ldd = Ca; g.strideD = 0;
     GLF_TRY(gemm(g, stream));
   }
-  {  // dT_b = (dM_b / N) W~g                 [Ci x Ca]
+  if (!chain) {  // dT_b = (dM_b / N) W~g                 [Ci x Ca]
     GemmArgs g;
     g.A = opnd(wb.dM, 0, Ci, CiCi);
     g.B = opnd(s.waug + 2 * CiCa, 1, Ca, 0);
@@ -567,7 +580,7 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved&
     g.D = wb.dwaug + CiCa; g.ldd = Ca; g.strideD = 0;
     GLF_TRY(gemm(g, stream));
   }
-  {  // G0_b = dS~_b[:C, :] = W_phi^T dT_b     [C x Ca]   (row C is only needed for e: formed in gram_assemble_F)
+  if (!chain) {  // G0_b = dS~_b[:C, :] = W_phi^T dT_b     [C x Ca]   (row C is only needed for e: formed in gram_assemble_F)
     GemmArgs g;
     g.A = opnd(s.waug + CiCa, 1, Ca, 0);
     g.B = opnd(wb.dT, 1, Ca, CiCa);
@@ -577,7 +590,7 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved&
     g.D = wb.G0; g.ldd = Ca; g.strideD = CCa;
     GLF_TRY(gemm(g, stream));
   }
-  if (bn_train) {  // H_b = Q_b^T Qk_b    [C x Ca]  (dU Q = dV E + X H[:C,:C] + 1 H[:C,C]^T: the k2 U + k3 part of dU)
+  if (bn_train && !chain) {  // H_b = Q_b^T Qk_b    [C x Ca]  (dU Q = dV E + X H[:C,:C] + 1 H[:C,C]^T: the k2 U + k3 part of dU)
     GemmArgs g;
     g.A = opnd(s.Qb, 1, Ca, CCa);
     g.B = opnd(wb.AK, 1, Ca, CCa);
@@ -588,7 +601,7 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const Saved&
     GLF_TRY(gemm(g, stream));
   }
   // F = (G0 + G0^T + H)[:C, :C] ;  e = (G0[:, C] + G0[C, :] + H[:, C])[:C]
-  GLF_TRY(gram_assemble_F(wb.G0, bn_train ? wb.Hf : nullptr, wb.dT, s.waug + CiCa, wb.EF, wb.evec, B, C, Ci, Ca, stream));
+  if (!chain) GLF_TRY(gram_assemble_F(wb.G0, bn_train ? wb.Hf : nullptr, wb.dT, s.waug + CiCa, wb.EF, wb.evec, B, C, Ci, Ca, stream));
   {  // dX_b = dV_b E_b + X_b F_b + 1 e_b^T + dV_b
     GemmArgs g;
     g.A = opnd(nullptr, 0, C, static_cast<long long>(N) * C);
@@ -779,7 +792,7 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
   }
   GLF_TRY(bn_bwd_finalize(wb.part_ln, nb, C, static_cast<double>(m.rows), d, w, s.bn_mean, s.bn_rstd, g_, wb.k1, wb.k2,
                           wb.k3, stream));
-  if (m.gram) return tpavi_bwd_gram(d, m, X, s, wb, dx, g_, stream);
+  if (m.gram) return tpavi_bwd_gram(d, m, X, w, s, wb, dx, g_, stream);
   const bf16* dU = wb.dV;
   if (d->bn_layer) {
     GLF_TRY(bn_bwd_apply(wb.dV, s.U, GLF_DTYPE_BF16, wb.k1, wb.k2, wb.k3, wb.dU, m.rows, C, stream));

@@ -116,6 +116,16 @@ int gram_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* scratch
                      const float* rowv, float corner, int border, int B, int N, int C, int Ca, int ksplit,
                      cudaStream_t stream);
 int gram_unpack_grads(const float* dwaug, const glf_grads* g, int C, int Ci, int Ca, cudaStream_t stream);
+// One CTA per sequence runs the whole [C x C] chain between the token-sized products (glf_chain.cu), C = 256, C' = 128
+bool gram_chain_supported(int C, int Ci);
+int gram_chain_fwd(const bf16* Sa, const float* sfv, const bf16* waug, const bf16* wz, const float* bphi,
+                   const float* bg, const float* bth, bf16* T, bf16* Mb, bf16* Wp, bf16* Qb, float* cvec, int B, int N,
+                   cudaStream_t stream);
+// dMn = dM / N.  has_k2 = 0 skips the Q^T (k2 Q) term (k2 = k3 = 0: eval-mode BatchNorm or bn_layer = False)
+int gram_chain_bwd(const bf16* Sa, const bf16* Qb, const bf16* waug, const bf16* wz, const bf16* Rb, const float* sfv,
+                   const float* cvec, const float* rv, const float* k1, const float* k2, const float* k3,
+                   const float* bth, const float* bphi, const float* bg, int has_k2, bf16* dQa, bf16* dWp, bf16* dMn,
+                   bf16* dT, bf16* EF, float* evec, int B, int N, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------ gate + concat
 int gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, int x_dtype,
