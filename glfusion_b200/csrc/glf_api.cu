@@ -121,13 +121,14 @@ struct Saved {
   float *lse, *bcat, *bn_mean, *bn_rstd, *bn_a, *bn_b, *ln_mu, *ln_r;
   bf16 *Sa, *T, *Qb, *waug;   // Gram form: S~ [B][Ca][Ca], T = W~phi S~ [B][Ci][Ca], Q~ [B][C][Ca], W~ [3][Ci][Ca]
   float *sfv, *cvec;          //            s = column sums of X [B][C], c = Q~[:, :, C] [B][C]
+  float *tv;                  //            t = T~[:, :, C] [B][Ci] in fp32 (chain kernels)
 };
 size_t carve_saved(const Dims& m, void* base, Saved* s) {
   Carver c(base);
   const size_t rows = m.rows, C = m.C, Ci = m.Ci, B = m.B;
   s->xtok = m.pack_x ? c.take<bf16>(rows * C) : nullptr;
   s->Sa = s->T = s->Qb = s->waug = nullptr;
-  s->sfv = s->cvec = nullptr;
+  s->sfv = s->cvec = s->tv = nullptr;
   if (m.gram) {
     const size_t Ca = m.Ca;
     s->P = s->Y = s->wcat = s->wcatT = s->wzT = nullptr;
@@ -142,6 +143,7 @@ size_t carve_saved(const Dims& m, void* base, Saved* s) {
     s->wz = c.take<bf16>(C * Ci);
     s->sfv = c.take<float>(B * C);
     s->cvec = c.take<float>(B * C);
+    s->tv = c.take<float>(B * Ci);
     s->bn_mean = c.take<float>(C);
     s->bn_rstd = c.take<float>(C);
     s->bn_a = c.take<float>(C);
@@ -199,7 +201,7 @@ struct WsBwd {
   float *dWpf, *part_ln, *k1, *k2, *k3, *cs_t, *cs_p, *cs_g, *red1, *dwcat, *delta;
   void* attn;
   // Gram form
-  float *Rf, *rv, *evec, *dwaug;
+  float *Rf, *rv, *evec, *dwaug, *dcv, *dtv, *wpart;
   bf16 *Rb, *AK, *dQa, *dT, *EF, *G0, *Hf;
 };
 size_t carve_ws_bwd(const glf_desc* d, const Dims& m, void* base, WsBwd* w) {
@@ -207,7 +209,7 @@ size_t carve_ws_bwd(const glf_desc* d, const Dims& m, void* base, WsBwd* w) {
   const size_t rows = m.rows, C = m.C, Ci = m.Ci, B = m.B;
   w->dztok = m.pack_dz ? c.take<bf16>(rows * C) : nullptr;
   w->dV = c.take<bf16>(rows * C);
-  w->Rf = w->rv = w->evec = w->dwaug = nullptr;
+  w->Rf = w->rv = w->evec = w->dwaug = w->dcv = w->dtv = w->wpart = nullptr;
   w->Rb = w->AK = w->dQa = w->dT = w->EF = w->G0 = w->Hf = nullptr;
   if (m.gram) {
     const size_t Ca = m.Ca;
@@ -232,6 +234,9 @@ size_t carve_ws_bwd(const glf_desc* d, const Dims& m, void* base, WsBwd* w) {
     w->EF = c.take<bf16>(B * 2 * C * C);
     w->evec = c.take<float>(B * C);
     w->dwaug = c.take<float>(3 * Ci * Ca);
+    w->dcv = c.take<float>(B * C);
+    w->dtv = c.take<float>(B * Ci);
+    w->wpart = gram_chain_supported(m.C, m.Ci) ? c.take<float>(gram_wgrad_scratch_floats()) : nullptr;
     return (c.off + 255) & ~static_cast<size_t>(255);
   }
   w->dU = d->bn_layer ? c.take<bf16>(rows * C) : nullptr;
@@ -404,8 +409,8 @@ int tpavi_fwd_gram(const glf_desc* d, const Dims& m, const void* x, const glf_we
   GLF_TRY(gram_token_contraction(X, X, s.Sa, wf.Sf, s.sfv, nullptr, nullptr, static_cast<float>(N), B, N, C, Ca, stream));
   if (gram_chain_supported(C, Ci)) {
     // T~, M, W', Q~ and c of every sequence in one launch, one CTA per sequence (glf_chain.cu)
-    GLF_TRY(gram_chain_fwd(s.Sa, s.sfv, s.waug, s.wz, w->phi_b, w->g_b, w->theta_b, s.T, s.Mb, s.Wp, s.Qb, s.cvec, B, N,
-                           stream));
+    GLF_TRY(gram_chain_fwd(s.Sa, s.sfv, s.waug, s.wz, w->phi_b, w->g_b, w->theta_b, s.T, s.Mb, s.Wp, s.Qb, s.cvec, s.tv, B,
+                           N, stream));
   } else {
     {  // T_b = W~phi S~_b                      [Ci x Ca]   (= Phi_b^T X~_b; S~ is symmetric)
       GemmArgs g;
@@ -493,8 +498,11 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const glf_we
   const bool chain = gram_chain_supported(C, Ci);
   if (chain)
     GLF_TRY(gram_chain_bwd(s.Sa, s.Qb, s.waug, s.wz, wb.Rb, s.sfv, s.cvec, wb.rv, wb.k1, wb.k2, wb.k3, w->theta_b,
-                           w->phi_b, w->g_b, bn_train ? 1 : 0, wb.dQa, wb.dWpb, wb.dM, wb.dT, wb.EF, wb.evec, B, N,
-                           stream));
+                           w->phi_b, w->g_b, bn_train ? 1 : 0, wb.dQa, wb.dWpb, wb.dM, wb.dT, wb.EF, wb.evec, wb.dcv,
+                           wb.dtv, B, N, stream));
+  if (chain)   // dW~theta, dWz, dW~g, dW~phi: one launch of K-concatenated products + a fixed-order reduction
+    GLF_TRY(gram_wgrad(s.Wp, wb.dQa, wb.dWpb, s.Mb, wb.dM, s.T, wb.dT, s.Sa, wb.dcv, s.tv, wb.dtv, s.sfv, wb.wpart, g_, B, N,
+                       stream));
   // Qk = k2 Q~ (column C: k2 c + k3), E = k1 Q
   if (!chain) GLF_TRY(gram_kprep(s.Qb, s.cvec, wb.k1, wb.k2, wb.k3, wb.AK, wb.EF, B, C, Ca, stream));
   if (!chain) {  // dQ~_b = dU_b^T X~_b = Qk_b S~_b + k1 [R_b | rv_b]     [C x Ca]   (S~ is symmetric; the second term is the addend)
@@ -516,8 +524,8 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const glf_we
     g.D = wb.dWpb; g.ldd = Ci; g.strideD = CCi;
     GLF_TRY(gemm(g, stream));
   }
-  GLF_TRY(check_cuda(cudaMemsetAsync(wb.dwaug, 0, sizeof(float) * 3 * CiCa, stream), "memset dW~"));
-  {  // dW~theta = sum_b W'_b^T dQ~_b         [Ci x Ca]   (batch reduced by fp32 red.add)
+  if (!chain) GLF_TRY(check_cuda(cudaMemsetAsync(wb.dwaug, 0, sizeof(float) * 3 * CiCa, stream), "memset dW~"));
+  if (!chain) {  // dW~theta = sum_b W'_b^T dQ~_b         [Ci x Ca]   (batch reduced by fp32 red.add)
     GemmArgs g;
     g.A = opnd(s.Wp, 1, Ci, CCi);
     g.B = opnd(wb.dQa, 1, Ca, CCa);
@@ -528,8 +536,8 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const glf_we
     g.D = wb.dwaug; g.ldd = Ca; g.strideD = 0;
     GLF_TRY(gemm(g, stream));
   }
-  GLF_TRY(check_cuda(cudaMemsetAsync(g_->wz_w, 0, sizeof(float) * CCi, stream), "memset dWz"));
-  {  // dWz = sum_b dW'_b M_b
+  if (!chain) GLF_TRY(check_cuda(cudaMemsetAsync(g_->wz_w, 0, sizeof(float) * CCi, stream), "memset dWz"));
+  if (!chain) {  // dWz = sum_b dW'_b M_b
     GemmArgs g;
     g.A = opnd(wb.dWpb, 0, Ci, CCi);
     g.B = opnd(s.Mb, 1, Ci, CiCi);
@@ -546,14 +554,14 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const glf_we
     g.D = wb.dM; g.ldd = Ci; g.strideD = CiCi;
     GLF_TRY(gemm(g, stream));
   }
-  {  // dW~g = sum_b (dM_b / N)^T T_b         [Ci x Ca]
+  if (!chain) {  // dW~g = sum_b (dM_b / N)^T T_b         [Ci x Ca]
     GemmArgs g;
     g.A = opnd(wb.dM, 1, Ci, CiCi);
     g.B = opnd(s.T, 1, Ca, CiCa);
     g.B.rows = C1;
     g.M = Ci; g.N = Ca; g.K = Ci; g.batch = B;
     g.bn_hint = wide;
-    g.alpha = chain ? 1.f : invN;   // the chain kernel stores dM / N
+    g.alpha = invN;
     g.out_kind = 2;
     g.D = wb.dwaug + 2 * CiCa; g.ldd = Ca; g.strideD = 0;
     GLF_TRY(gemm(g, stream));
@@ -569,7 +577,7 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const glf_we
     g.D = wb.dT; g.ldd = Ca; g.strideD = CiCa;
     GLF_TRY(gemm(g, stream));
   }
-  {  // dW~phi = sum_b dT_b S~_b              [Ci x Ca]
+  if (!chain) {  // dW~phi = sum_b dT_b S~_b              [Ci x Ca]
     GemmArgs g;
     g.A = opnd(wb.dT, 0, Ca, CiCa);
     g.B = opnd(s.Sa, 0, Ca, CaCa);
@@ -613,7 +621,7 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const glf_we
     g.D = m.pack_x ? static_cast<void*>(wb.dxtok) : dx; g.ldd = C; g.strideD = static_cast<long long>(N) * C;
     GLF_TRY(gemm_pair2(g, wb.dV, X, wb.EF, wb.EF + CC, stream));
   }
-  GLF_TRY(gram_unpack_grads(wb.dwaug, g_, C, Ci, Ca, stream));
+  if (!chain) GLF_TRY(gram_unpack_grads(wb.dwaug, g_, C, Ci, Ca, stream));
   if (m.pack_x) {
     if (d->x_layout == GLF_LAYOUT_NCTHW)
       GLF_TRY(transpose_cast(wb.dxtok, dx, B, N, C, GLF_DTYPE_BF16, d->io_dtype, stream));

@@ -21,6 +21,7 @@
 //                                dT~ = dM W~g / N,  F = Wphi^T dT + dT^T Wphi + Q^T k2 Q,  E = k1 Q,  e
 // The four weight-gradient sums over the sequences (dW~theta, dWz, dW~g, dW~phi) are NOT formed here: the kernel leaves
 // dQ~, dW', dM / N and dT~ in global memory and the caller reduces them with K-concatenated products.
+#include <cstdio>
 #include <cstdlib>
 
 #include "glf_internal.h"
@@ -139,6 +140,38 @@ __device__ __forceinline__ void load_256x128(const CUtensorMap* tm, uint32_t bar
   }
 }
 
+// the mirror image: bulk tensor stores of bf16 tiles that the drain warps left in shared memory
+__device__ __forceinline__ void store_256x256(const CUtensorMap* tm, uint32_t src, int row0, int b) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    tma_store_4d(tm, src + t * 32768u, 64 * t, row0, b, 0);
+    tma_store_4d(tm, src + t * 32768u + 16384u, 64 * t, row0 + 128, b, 0);
+  }
+}
+__device__ __forceinline__ void store_128x256(const CUtensorMap* tm, uint32_t src, int b) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) tma_store_4d(tm, src + t * 16384u, 64 * t, 0, b, 0);
+}
+__device__ __forceinline__ void store_256x128(const CUtensorMap* tm, uint32_t src, int b) {
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    tma_store_4d(tm, src + t * 32768u, 64 * t, 0, b, 0);
+    tma_store_4d(tm, src + t * 32768u + 16384u, 64 * t, 128, b, 0);
+  }
+}
+__device__ __forceinline__ void store_128x128(const CUtensorMap* tm, uint32_t src, int b) {
+#pragma unroll
+  for (int t = 0; t < 2; ++t) tma_store_4d(tm, src + t * 16384u, 64 * t, 0, b, 0);
+}
+
+// Debug aid (GLF_CHAIN_TRACE=1): the control thread of CTA 0 records the SM clock each time one of its waits completes;
+// the host prints the phase timeline after a stream synchronisation.
+__device__ long long g_chain_trace[64];
+#define CH_TRACE(i)                                                \
+  do {                                                             \
+    if (p.trace && blockIdx.x == 0) g_chain_trace[i] = clock64();  \
+  } while (0)
+
 constexpr uint32_t IDESC_KK_128 = make_idesc_bf16(128, 128, false, false);
 constexpr uint32_t IDESC_KK_256 = make_idesc_bf16(128, 256, false, false);
 constexpr uint32_t IDESC_KM_256 = make_idesc_bf16(128, 256, false, true);
@@ -150,6 +183,7 @@ struct ChainFwdParams {
   const float *sfv, *bphi, *bg, *bth;   // s [B][C]; biases [C'] fp32
   bf16 *T, *Mb, *Wp, *Qb;               // T~ [B][C'][Ca], M [B][C'][C'], W' [B][C][C'], Q~ [B][C][Ca]
   float* cvec;                          // c = W' b_theta  [B][C]
+  float* tv;                            // t = T~[:, C]    [B][C'] (fp32 copy for the weight-gradient kernel)
 };
 
 // ---------------------------------------------------------------------------------------------- forward chain
@@ -160,7 +194,9 @@ struct ChainFwdParams {
 //   F4  Q  = W' Wtheta ,  c = W' btheta     [256 x 256]   A = W' (K-major), B = Wtheta (MN-major)
 __global__ void __launch_bounds__(CH_THREADS, 1)
     chain_fwd_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmW,
-                     const __grid_constant__ CUtensorMap tmWz, const ChainFwdParams p) {
+                     const __grid_constant__ CUtensorMap tmWz, const __grid_constant__ CUtensorMap tmT,
+                     const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmWp,
+                     const __grid_constant__ CUtensorMap tmQ, const ChainFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -171,7 +207,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
   float* v_t = v_bth + 128;                                // [128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sgen + VEC_OFF + 8192);
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(sgen + VEC_OFF + 8192 + 256);
-  enum { LD0 = 0, LD1, LD2, LD3, MMA0, MMA1, MMA2, MMA3, DR0, DR1, DR2, NBAR };
+  enum { LD0 = 0, LD1, LD2, LD3, MMA0, MMA1, MMA2, MMA3, DR0, DR1, DR2, DR3, NBAR };
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -206,23 +242,31 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       mbar_expect_tx(bar(LD2), 4 * BOX_BYTES);
       load_256x128(&tmWz, bar(LD2), sbase + Z1, 0, 0);         // Wz -> Z1
       mbar_wait(bar(DR0), 0);                                   // T (bf16) in Z2
+      store_128x256(&tmT, sbase + Z2, b);
+      tma_store_commit();
       mbar_wait(bar(LD1), 0);
       tc_fence_after();
       for (int k = 0; k < 16; ++k)
         umma_f16(tmem + 256, kdesc(sbase + Z2, 16384, k), kdesc(sbase + Z0, 16384, k), IDESC_KK_128, k > 0);
       umma_commit(bar(MMA1));
       mbar_wait(bar(MMA1), 0);                                  // T and Wg are dead
+      tma_store_wait_read<0>();                                 // ... and the store of T has read Z2
       mbar_expect_tx(bar(LD3), 4 * BOX_BYTES);
       load_128x256(&tmW, bar(LD3), sbase + Z2, 0, 0);          // Wtheta -> Z2
       mbar_wait(bar(DR1), 0);                                   // M (bf16) in Z0
+      store_128x128(&tmM, sbase + Z0, b);
+      tma_store_commit();
       mbar_wait(bar(LD2), 0);
       tc_fence_after();
       for (int h = 0; h < 2; ++h)
         for (int k = 0; k < 8; ++k)
           umma_f16(tmem + h * 128, kdesc(sbase + Z1 + h * 16384, 32768, k), kdesc(sbase + Z0, 16384, k), IDESC_KK_128,
                    k > 0);
+      tma_store_wait_read<0>();      // before the accumulator is published: the drain of W' overwrites M in Z0
       umma_commit(bar(MMA2));
       mbar_wait(bar(DR2), 0);                                   // W' (bf16) in Z0
+      store_256x128(&tmWp, sbase + Z0, b);
+      tma_store_commit();
       mbar_wait(bar(LD3), 0);
       tc_fence_after();
       for (int h = 0; h < 2; ++h)
@@ -230,6 +274,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
           umma_f16(tmem + h * 256, kdesc(sbase + Z0 + h * 16384, 32768, k), mdesc(sbase + Z2, 16384, k), IDESC_KM_256,
                    k > 0);
       umma_commit(bar(MMA3));
+      mbar_wait(bar(DR3), 0);                                   // Q (bf16) in Z1, Z2
+      store_256x256(&tmQ, sbase + Z1, 0, b);
+      tma_store_commit();
+      tma_store_wait_all<0>();
     }
   } else {
     // ------------------------------------------------------------------------------------------ drain warps
@@ -245,7 +293,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     }
     named_bar_sync(1, CH_DRAIN_THREADS);
     mbar_wait(bar(LD0), 0);
-    if (tid < CI) v_t[tid] = fmaf(fN, v_bphi[tid], row_dot256(sgen + Z2, 128, tid, v_s));
+    if (tid < CI) {
+      v_t[tid] = fmaf(fN, v_bphi[tid], row_dot256(sgen + Z2, 128, tid, v_s));
+      p.tv[static_cast<long long>(b) * CI + tid] = v_t[tid];
+    }
     named_bar_sync(1, CH_DRAIN_THREADS);
     // ---- T = acc + bphi s^T  -> Z2 ([128][64] x 4) and global
     mbar_wait(bar(MMA0), 0);
@@ -264,7 +315,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         uint32_t pk[16];
         pack32(f, pk);
         st_tile32(sgen + Z2, 128, i, col0, pk);
-        st_global32(Trow + col0, pk);
       }
       if (hf == 1) *reinterpret_cast<uint4*>(Trow + CC) = make_uint4(pack_bf16(v_t[i], 0.f), 0u, 0u, 0u);
     }
@@ -278,7 +328,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     {
       const int i = q * 32 + lane;
       const float ti = v_t[i];
-      bf16* Mrow = p.Mb + (static_cast<long long>(b) * CI + i) * CI;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         const int col0 = hf * 64 + c * 32;
@@ -289,7 +338,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         uint32_t pk[16];
         pack32(f, pk);
         st_tile32(sgen + Z0, 128, i, col0, pk);
-        st_global32(Mrow + col0, pk);
       }
     }
     fence_proxy_async_smem();
@@ -302,7 +350,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     mbar_wait(bar(MMA2), 0);
     tc_fence_after();
     {
-      bf16* Wrow = p.Wp + (static_cast<long long>(b) * CC + r) * CI;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const int col0 = c * 32;
@@ -317,7 +364,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
           cv = fmaf(x.y, v_bth[col0 + 2 * j + 1], cv);
         }
         st_tile32(sgen + Z0, 256, r, col0, pk);
-        st_global32(Wrow + col0, pk);
       }
       p.cvec[static_cast<long long>(b) * CC + r] = cv;
     }
@@ -337,10 +383,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         ld_acc32(tlane + hf * 256 + col0, f);
         uint32_t pk[16];
         pack32(f, pk);
-        st_global32(Qrow + col0, pk);
+        st_tile32(sgen + Z1, 256, r, col0, pk);
       }
       *reinterpret_cast<uint4*>(Qrow + CC) = make_uint4(pack_bf16(cv, 0.f), 0u, 0u, 0u);
     }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar(DR3));
   }
   tc_fence_before();
   __syncthreads();
@@ -348,12 +397,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
 }
 
 struct ChainBwdParams {
-  int N, has_k2;
+  int N, has_k2, trace;
   const float *sfv, *cvec, *rv, *k1, *k2, *k3;   // s, c, rv [B][C]; BatchNorm-backward coefficients [C]
   const float *bth, *bphi, *bg;                  // biases [C'] fp32
   const bf16* Rb;                                // [B][Ca][Ca]: rows < C hold k1 [R | rv]
   bf16 *dQa, *dWp, *dMn, *dT, *EF;               // dQ~ [B][C][Ca], dW' [B][C][C'], dM/N [B][C'][C'], dT~ [B][C'][Ca], [E;F] [B][2C][C]
   float* evec;                                   // e [B][C]
+  float *dcv, *dtv;                              // fp32 copies of dQ~[:, C] [B][C] and dT~[:, C] [B][C'] (weight gradients)
 };
 
 // ---------------------------------------------------------------------------------------------- backward chain
@@ -367,7 +417,9 @@ struct ChainBwdParams {
 __global__ void __launch_bounds__(CH_THREADS, 1)
     chain_bwd_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmQ,
                      const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWz,
-                     const ChainBwdParams p) {
+                     const __grid_constant__ CUtensorMap tmdQ, const __grid_constant__ CUtensorMap tmdWp,
+                     const __grid_constant__ CUtensorMap tmdM, const __grid_constant__ CUtensorMap tmdT,
+                     const __grid_constant__ CUtensorMap tmEF, const ChainBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -384,7 +436,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sgen + VEC_OFF + 8192);
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(sgen + VEC_OFF + 8192 + 256);
   enum { LDA = 0, LDB, LDC, LDD, LDE, LDF, LDG, LDH, MMAA, MMAB, MMAC, MMAD, MMAE, MMAF, MMAG0, MMAG1,
-         DRA, DRB, DRC, DRD, DRE, DRK0, DRK1, NBAR };
+         DRA, DRB, DRC, DRD, DRE, DRK0, DRK1, DRF, NBAR };
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -406,64 +458,76 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
   if (warp == CH_DRAIN_WARPS) {
     // ------------------------------------------------------------------------------------------ control warp
     if (elect_one()) {
+      CH_TRACE(0);
       mbar_expect_tx(bar(LDA), 12 * BOX_BYTES);
       load_256x256(&tmQ, bar(LDA), sbase + Z0, b);             // Q -> Z0, Z1
       load_128x256(&tmS, bar(LDA), sbase + Z2, 0, b);          // S rows 0..127 -> Z2
-      mbar_wait(bar(LDA), 0);
+      mbar_wait(bar(LDA), 0); CH_TRACE(1);
       tc_fence_after();
       for (int h = 0; h < 2; ++h)
         for (int k = 0; k < 16; ++k)
           umma_f16(tmem + h * 256, kdesc(sbase + Z0 + h * 16384, 32768, k), kdesc(sbase + Z2, 16384, k), IDESC_KK_128,
                    k > 0);
       umma_commit(bar(MMAA));
-      mbar_wait(bar(MMAA), 0);
+      mbar_wait(bar(MMAA), 0); CH_TRACE(2);
       mbar_expect_tx(bar(LDB), 4 * BOX_BYTES);
       load_128x256(&tmS, bar(LDB), sbase + Z2, 128, b);        // S rows 128..255 -> Z2
-      mbar_wait(bar(LDB), 0);
+      mbar_wait(bar(LDB), 0); CH_TRACE(3);
       tc_fence_after();
       for (int h = 0; h < 2; ++h)
         for (int k = 0; k < 16; ++k)
           umma_f16(tmem + h * 256 + 128, kdesc(sbase + Z0 + h * 16384, 32768, k), kdesc(sbase + Z2, 16384, k),
                    IDESC_KK_128, k > 0);
       umma_commit(bar(MMAB));
-      mbar_wait(bar(MMAB), 0);
+      mbar_wait(bar(MMAB), 0); CH_TRACE(4);
       mbar_expect_tx(bar(LDC), 4 * BOX_BYTES);
       load_128x256(&tmW, bar(LDC), sbase + Z2, 0, 0);          // Wtheta -> Z2
-      mbar_wait(bar(DRA), 0);                                   // dQ (bf16) in Z0, Z1
-      mbar_wait(bar(LDC), 0);
+      mbar_wait(bar(DRA), 0); CH_TRACE(5);                                   // dQ (bf16) in Z0, Z1
+      store_256x256(&tmdQ, sbase + Z0, 0, b);
+      tma_store_commit();
+      mbar_wait(bar(LDC), 0); CH_TRACE(6);
       tc_fence_after();
       for (int h = 0; h < 2; ++h)
         for (int k = 0; k < 16; ++k)
           umma_f16(tmem + h * 128, kdesc(sbase + Z0 + h * 16384, 32768, k), kdesc(sbase + Z2, 16384, k), IDESC_KK_128,
                    k > 0);
+      tma_store_wait_read<0>();      // before the accumulator is published: the drain of dW' overwrites dQ in Z0
       umma_commit(bar(MMAC));
-      mbar_wait(bar(MMAC), 0);
+      mbar_wait(bar(MMAC), 0); CH_TRACE(7);
       mbar_expect_tx(bar(LDD), 4 * BOX_BYTES);
       load_256x128(&tmWz, bar(LDD), sbase + Z2, 0, 0);         // Wz -> Z2
-      mbar_wait(bar(DRB), 0);                                   // dW' (bf16) in Z0
-      mbar_wait(bar(LDD), 0);
+      mbar_wait(bar(DRB), 0); CH_TRACE(8);                                   // dW' (bf16) in Z0
+      store_256x128(&tmdWp, sbase + Z0, b);
+      tma_store_commit();
+      mbar_wait(bar(LDD), 0); CH_TRACE(9);
       tc_fence_after();
       for (int k = 0; k < 16; ++k)
         umma_f16(tmem + 256, mdesc(sbase + Z0, 32768, k), mdesc(sbase + Z2, 32768, k), IDESC_MM_128, k > 0);
+      tma_store_wait_read<0>();
       umma_commit(bar(MMAD));
-      mbar_wait(bar(MMAD), 0);
+      mbar_wait(bar(MMAD), 0); CH_TRACE(10);
       mbar_expect_tx(bar(LDE), 4 * BOX_BYTES);
       load_128x256(&tmW, bar(LDE), sbase + Z1, 2 * CI, 0);     // Wg -> Z1
       mbar_expect_tx(bar(LDF), 4 * BOX_BYTES);
       load_128x256(&tmW, bar(LDF), sbase + Z2, CI, 0);         // Wphi -> Z2
-      mbar_wait(bar(DRC), 0);                                   // dM / N (bf16) in Z0
-      mbar_wait(bar(LDE), 0);
+      mbar_wait(bar(DRC), 0); CH_TRACE(11);                                   // dM / N (bf16) in Z0
+      store_128x128(&tmdM, sbase + Z0, b);
+      tma_store_commit();
+      mbar_wait(bar(LDE), 0); CH_TRACE(12);
       tc_fence_after();
       for (int k = 0; k < 8; ++k)
         umma_f16(tmem, kdesc(sbase + Z0, 16384, k), mdesc(sbase + Z1, 16384, k), IDESC_KM_256, k > 0);
+      tma_store_wait_read<0>();
       umma_commit(bar(MMAE));
-      mbar_wait(bar(MMAE), 0);
+      mbar_wait(bar(MMAE), 0); CH_TRACE(13);
       if (p.has_k2) {
         mbar_expect_tx(bar(LDG), 4 * BOX_BYTES);
         load_256x128(&tmQ, bar(LDG), sbase + Z1, 0, b);        // Q columns 0..127 -> Z1
       }
-      mbar_wait(bar(DRD), 0);                                   // dT (bf16) in Z0
-      mbar_wait(bar(LDF), 0);
+      mbar_wait(bar(DRD), 0); CH_TRACE(14);                                   // dT (bf16) in Z0
+      store_128x256(&tmdT, sbase + Z0, b);
+      tma_store_commit();
+      mbar_wait(bar(LDF), 0); CH_TRACE(15);
       tc_fence_after();
       for (int h = 0; h < 2; ++h) {
         for (int k = 0; k < 8; ++k)
@@ -472,15 +536,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         for (int k = 0; k < 8; ++k)
           umma_f16(tmem + h * 256, mdesc(sbase + Z0 + h * 32768, 16384, k), mdesc(sbase + Z2, 16384, k), IDESC_MM_256, 1);
       }
+      tma_store_wait_read<0>();      // dT has been stored before anything (drain of F, next Q half) overwrites Z0
       umma_commit(bar(MMAF));
       if (p.has_k2) {
-        mbar_wait(bar(MMAF), 0);
-        mbar_wait(bar(DRE), 0);                                 // the e terms that read dT / Wphi are done
+        mbar_wait(bar(MMAF), 0); CH_TRACE(16);
+        mbar_wait(bar(DRE), 0); CH_TRACE(17);                                 // the e terms that read dT / Wphi are done
         mbar_expect_tx(bar(LDH), 4 * BOX_BYTES);
         load_256x128(&tmQ, bar(LDH), sbase + Z0, 128, b);      // Q columns 128..255 -> Z0
-        mbar_wait(bar(LDH), 0);
+        mbar_wait(bar(LDH), 0); CH_TRACE(18);
         for (int g = 0; g < 2; ++g) {
-          mbar_wait(bar(DRK0 + g), 0);                          // k2 Q[:, 128 g ..] in Z2
+          mbar_wait(bar(DRK0 + g), 0); CH_TRACE(19 + g);                          // k2 Q[:, 128 g ..] in Z2
           tc_fence_after();
           for (int h = 0; h < 2; ++h)
             for (int k = 0; k < 16; ++k)
@@ -489,6 +554,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
           umma_commit(bar(MMAG0 + g));
         }
       }
+      mbar_wait(bar(DRF), 0); CH_TRACE(21);                                   // F (bf16) in Z0, Z1
+      store_256x256(&tmEF, sbase + Z0, CC, b);
+      tma_store_commit();
+      tma_store_wait_all<0>();
     }
   } else {
     // ------------------------------------------------------------------------------------------ drain warps
@@ -517,6 +586,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       // dc = k1 rv + k2 (Q s + N c) + N k3       (thread = row of Q)
       const float qs = row_dot256(sgen + Z0, 256, tid, v_s);
       v_dc[tid] = fmaf(v_k1[tid], p.rv[bC + tid], fmaf(v_k2[tid], fmaf(fN, my_c, qs), fN * p.k3[tid]));
+      p.dcv[bC + tid] = v_dc[tid];
       // E = k1 Q -> EF[b][0]   (a warp moves one 512-byte row per iteration)
       bf16* E = p.EF + static_cast<long long>(b) * 2 * CC * CC;
 #pragma unroll 4
@@ -536,26 +606,30 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     }
     named_bar_sync(1, CH_DRAIN_THREADS);      // every reader of Q (Z0, Z1) is done before dQ overwrites it
     const int r = hf * 128 + q * 32 + lane;   // row of the 256-row matrices owned by this thread
-    // ---- dQ = k1 R + k2 QS + v s^T  -> Z0, Z1 ([256][64] x 4) and global
-    mbar_wait(bar(MMAB), 0);
-    tc_fence_after();
+    // ---- dQ = k1 R + k2 QS + v s^T  -> Z0, Z1 ([256][64] x 4), stored by the control thread
     {
-      const float a2 = v_k2[r], vr = v_v[r];
+      // this thread's row of k1 R comes from global memory through a 4-deep register ring; the first three chunks are
+      // requested before the wait for the accumulator
       const bf16* Rrow = p.Rb + (static_cast<long long>(b) * CA + r) * CA;
-      bf16* Drow = p.dQa + (bC + r) * CA;
-      uint4 rk[4], rk_next[4];
+      uint4 rk[4][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) rk[j] = *reinterpret_cast<const uint4*>(Rrow + 8 * j);
-#pragma unroll 1
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rk[c][j] = *reinterpret_cast<const uint4*>(Rrow + c * 32 + 8 * j);
+      mbar_wait(bar(MMAB), 0);
+      tc_fence_after();
+      const float a2 = v_k2[r], vr = v_v[r];
+      bf16* Drow = p.dQa + (bC + r) * CA;
+#pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int col0 = c * 32;
-        if (c + 1 < 8) {
+        if (c + 3 < 8) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rk_next[j] = *reinterpret_cast<const uint4*>(Rrow + col0 + 32 + 8 * j);
+          for (int j = 0; j < 4; ++j) rk[(c + 3) & 3][j] = *reinterpret_cast<const uint4*>(Rrow + col0 + 96 + 8 * j);
         }
         float f[32];
         ld_acc32(tlane + hf * 256 + col0, f);
-        const uint32_t* r32 = reinterpret_cast<const uint32_t*>(rk);
+        const uint32_t* r32 = reinterpret_cast<const uint32_t*>(rk[c & 3]);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float2 x = unpack_bf16(r32[j]);
@@ -565,9 +639,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         uint32_t pk[16];
         pack32(f, pk);
         st_tile32(sgen + Z0, 256, r, col0, pk);
-        st_global32(Drow + col0, pk);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rk[j] = rk_next[j];
       }
       *reinterpret_cast<uint4*>(Drow + CC) = make_uint4(pack_bf16(v_dc[r], 0.f), 0u, 0u, 0u);
     }
@@ -580,7 +651,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     tc_fence_after();
     {
       const float dcr = v_dc[r];
-      bf16* Wrow = p.dWp + (bC + r) * CI;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const int col0 = c * 32;
@@ -591,7 +661,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         uint32_t pk[16];
         pack32(f, pk);
         st_tile32(sgen + Z0, 256, r, col0, pk);
-        st_global32(Wrow + col0, pk);
       }
     }
     fence_proxy_async_smem();
@@ -603,7 +672,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     tc_fence_after();
     {
       const int i = q * 32 + lane;
-      bf16* Mrow = p.dMn + (static_cast<long long>(b) * CI + i) * CI;
       float dtp = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
@@ -621,7 +689,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
           dtp = fmaf(x.y, v_bg[col0 + 2 * j + 1], dtp);
         }
         st_tile32(sgen + Z0, 128, i, col0, pk);
-        st_global32(Mrow + col0, pk);
       }
       v_dt[hf * 128 + i] = dtp;
     }
@@ -633,7 +700,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     float my_dt = 0.f;
     if (tid < CI) my_dt = v_dt[tid] + v_dt[128 + tid];
     named_bar_sync(1, CH_DRAIN_THREADS);
-    if (tid < CI) v_dt[tid] = my_dt;
+    if (tid < CI) {
+      v_dt[tid] = my_dt;
+      p.dtv[static_cast<long long>(b) * CI + tid] = my_dt;
+    }
     named_bar_sync(1, CH_DRAIN_THREADS);
     // ---- dT -> Z0 ([128][64] x 4) and global (column C = dt)
     mbar_wait(bar(MMAE), 0);
@@ -649,7 +719,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         uint32_t pk[16];
         pack32(f, pk);
         st_tile32(sgen + Z0, 128, i, col0, pk);
-        st_global32(Trow + col0, pk);
       }
       if (hf == 1) *reinterpret_cast<uint4*>(Trow + CC) = make_uint4(pack_bf16(v_dt[i], 0.f), 0u, 0u, 0u);
     }
@@ -710,7 +779,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     mbar_wait(bar(p.has_k2 ? MMAG1 : MMAF), 0);
     tc_fence_after();
     {
-      bf16* Frow = p.EF + (static_cast<long long>(b) * 2 * CC + CC + r) * CC;
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
         const int col0 = c * 32;
@@ -718,9 +786,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         ld_acc32(tlane + hf * 256 + col0, f);
         uint32_t pk[16];
         pack32(f, pk);
-        st_global32(Frow + col0, pk);
+        st_tile32(sgen + Z0, 256, r, col0, pk);
       }
     }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar(DRF));
     named_bar_sync(1, CH_DRAIN_THREADS);
     p.evec[bC + tid] = v_e[tid];
   }
@@ -739,40 +810,62 @@ bool gram_chain_supported(int C, int Ci) {
 }
 
 int gram_chain_fwd(const bf16* Sa, const float* sfv, const bf16* waug, const bf16* wz, const float* bphi,
-                   const float* bg, const float* bth, bf16* T, bf16* Mb, bf16* Wp, bf16* Qb, float* cvec, int B, int N,
-                   cudaStream_t stream) {
-  CUtensorMap tmS, tmW, tmWz;
+                   const float* bg, const float* bth, bf16* T, bf16* Mb, bf16* Wp, bf16* Qb, float* cvec, float* tv, int B,
+                   int N, cudaStream_t stream) {
+  CUtensorMap tmS, tmW, tmWz, tmT, tmM, tmWp, tmQ;
   GLF_TRY_RC(make_tmap_bf16(&tmS, Sa, CC, CC, B, CA, static_cast<long long>(CA) * CA, 128));
   GLF_TRY_RC(make_tmap_bf16(&tmW, waug, CC, 3 * CI, 1, CA, 0, 128));
   GLF_TRY_RC(make_tmap_bf16(&tmWz, wz, CI, CC, 1, CI, 0, 128));
+  GLF_TRY_RC(make_tmap_bf16(&tmT, T, CC, CI, B, CA, static_cast<long long>(CI) * CA, 128));
+  GLF_TRY_RC(make_tmap_bf16(&tmM, Mb, CI, CI, B, CI, static_cast<long long>(CI) * CI, 128));
+  GLF_TRY_RC(make_tmap_bf16(&tmWp, Wp, CI, CC, B, CI, static_cast<long long>(CC) * CI, 128));
+  GLF_TRY_RC(make_tmap_bf16(&tmQ, Qb, CC, CC, B, CA, static_cast<long long>(CC) * CA, 128));
   ChainFwdParams p;
   p.N = N;
   p.sfv = sfv; p.bphi = bphi; p.bg = bg; p.bth = bth;
-  p.T = T; p.Mb = Mb; p.Wp = Wp; p.Qb = Qb; p.cvec = cvec;
+  p.T = T; p.Mb = Mb; p.Wp = Wp; p.Qb = Qb; p.cvec = cvec; p.tv = tv;
   cudaError_t e = cudaFuncSetAttribute(chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM);
   if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(chain_fwd)");
-  chain_fwd_kernel<<<B, CH_THREADS, CH_SMEM, stream>>>(tmS, tmW, tmWz, p);
+  chain_fwd_kernel<<<B, CH_THREADS, CH_SMEM, stream>>>(tmS, tmW, tmWz, tmT, tmM, tmWp, tmQ, p);
   return check_cuda(cudaGetLastError(), "chain_fwd launch");
 }
 
 int gram_chain_bwd(const bf16* Sa, const bf16* Qb, const bf16* waug, const bf16* wz, const bf16* Rb, const float* sfv,
                    const float* cvec, const float* rv, const float* k1, const float* k2, const float* k3,
                    const float* bth, const float* bphi, const float* bg, int has_k2, bf16* dQa, bf16* dWp, bf16* dMn,
-                   bf16* dT, bf16* EF, float* evec, int B, int N, cudaStream_t stream) {
+                   bf16* dT, bf16* EF, float* evec, float* dcv, float* dtv, int B, int N, cudaStream_t stream) {
   CUtensorMap tmS, tmQ, tmW, tmWz;
   GLF_TRY_RC(make_tmap_bf16(&tmS, Sa, CC, CC, B, CA, static_cast<long long>(CA) * CA, 128));
   GLF_TRY_RC(make_tmap_bf16(&tmQ, Qb, CC, CC, B, CA, static_cast<long long>(CC) * CA, 128));
   GLF_TRY_RC(make_tmap_bf16(&tmW, waug, CC, 3 * CI, 1, CA, 0, 128));
   GLF_TRY_RC(make_tmap_bf16(&tmWz, wz, CI, CC, 1, CI, 0, 128));
+  CUtensorMap tmdQ, tmdWp, tmdM, tmdT, tmEF;
+  GLF_TRY_RC(make_tmap_bf16(&tmdQ, dQa, CC, CC, B, CA, static_cast<long long>(CC) * CA, 128));
+  GLF_TRY_RC(make_tmap_bf16(&tmdWp, dWp, CI, CC, B, CI, static_cast<long long>(CC) * CI, 128));
+  GLF_TRY_RC(make_tmap_bf16(&tmdM, dMn, CI, CI, B, CI, static_cast<long long>(CI) * CI, 128));
+  GLF_TRY_RC(make_tmap_bf16(&tmdT, dT, CC, CI, B, CA, static_cast<long long>(CI) * CA, 128));
+  GLF_TRY_RC(make_tmap_bf16(&tmEF, EF, CC, 2 * CC, B, CC, 2LL * CC * CC, 128));
   ChainBwdParams p;
   p.N = N; p.has_k2 = has_k2;
+  const char* tr = getenv("GLF_CHAIN_TRACE");
+  p.trace = (tr && tr[0] == '1') ? 1 : 0;
   p.sfv = sfv; p.cvec = cvec; p.rv = rv; p.k1 = k1; p.k2 = k2; p.k3 = k3;
   p.bth = bth; p.bphi = bphi; p.bg = bg;
   p.Rb = Rb;
   p.dQa = dQa; p.dWp = dWp; p.dMn = dMn; p.dT = dT; p.EF = EF; p.evec = evec;
+  p.dcv = dcv; p.dtv = dtv;
   cudaError_t e = cudaFuncSetAttribute(chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM);
   if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(chain_bwd)");
-  chain_bwd_kernel<<<B, CH_THREADS, CH_SMEM, stream>>>(tmS, tmQ, tmW, tmWz, p);
+  chain_bwd_kernel<<<B, CH_THREADS, CH_SMEM, stream>>>(tmS, tmQ, tmW, tmWz, tmdQ, tmdWp, tmdM, tmdT, tmEF, p);
+  if (p.trace) {
+    static const char* names[] = {"start", "LDA", "MMAA", "LDB", "MMAB", "DRA", "LDC", "MMAC", "DRB", "LDD", "MMAD", "DRC", "LDE", "MMAE", "DRD", "LDF", "MMAF", "DRE", "LDH", "DRK0", "DRK1", "DRF", "end"};
+    long long t[64];
+    cudaStreamSynchronize(stream);
+    cudaMemcpyFromSymbol(t, g_chain_trace, sizeof(t));
+    fprintf(stderr, "chain_bwd trace (SM cycles since start, delta):");
+    for (int i = 1; i <= 21; ++i) fprintf(stderr, " %s=%lld(+%lld)", names[i], t[i] - t[0], t[i] - t[i - 1]);
+    fprintf(stderr, "\n");
+  }
   return check_cuda(cudaGetLastError(), "chain_bwd launch");
 }
 

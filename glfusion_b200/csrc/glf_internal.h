@@ -119,13 +119,19 @@ int gram_unpack_grads(const float* dwaug, const glf_grads* g, int C, int Ci, int
 // One CTA per sequence runs the whole [C x C] chain between the token-sized products (glf_chain.cu), C = 256, C' = 128
 bool gram_chain_supported(int C, int Ci);
 int gram_chain_fwd(const bf16* Sa, const float* sfv, const bf16* waug, const bf16* wz, const float* bphi,
-                   const float* bg, const float* bth, bf16* T, bf16* Mb, bf16* Wp, bf16* Qb, float* cvec, int B, int N,
-                   cudaStream_t stream);
+                   const float* bg, const float* bth, bf16* T, bf16* Mb, bf16* Wp, bf16* Qb, float* cvec, float* tv, int B,
+                   int N, cudaStream_t stream);
 // dMn = dM / N.  has_k2 = 0 skips the Q^T (k2 Q) term (k2 = k3 = 0: eval-mode BatchNorm or bn_layer = False)
 int gram_chain_bwd(const bf16* Sa, const bf16* Qb, const bf16* waug, const bf16* wz, const bf16* Rb, const float* sfv,
                    const float* cvec, const float* rv, const float* k1, const float* k2, const float* k3,
                    const float* bth, const float* bphi, const float* bg, int has_k2, bf16* dQa, bf16* dWp, bf16* dMn,
-                   bf16* dT, bf16* EF, float* evec, int B, int N, cudaStream_t stream);
+                   bf16* dT, bf16* EF, float* evec, float* dcv, float* dtv, int B, int N, cudaStream_t stream);
+// The four weight-gradient sums over the sequences as ONE launch of K-concatenated products + a fixed-order reduction
+// of the per-CTA partials (glf_wgrad.cu); writes theta / phi / g weight + bias gradients and wz_w.
+size_t gram_wgrad_scratch_floats();
+int gram_wgrad(const bf16* Wp, const bf16* dQa, const bf16* dWp, const bf16* Mb, const bf16* dMn, const bf16* T,
+               const bf16* dT, const bf16* Sa, const float* dcv, const float* tv, const float* dtv, const float* sfv,
+               float* part, const glf_grads* g, int B, int N, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------ gate + concat
 int gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, int x_dtype,
