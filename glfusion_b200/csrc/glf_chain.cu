@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
 }
 
 struct ChainBwdParams {
-  int N, has_k2, trace;
+  int N, has_k2, trace, e_plus_i;
   const float *sfv, *cvec, *rv, *k1, *k2, *k3;   // s, c, rv [B][C]; BatchNorm-backward coefficients [C]
   const float *bth, *bphi, *bg;                  // biases [C'] fp32
   const bf16* Rb;                                // [B][Ca][Ca]: rows < C hold k1 [R | rv]
@@ -599,7 +599,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float2 x = unpack_bf16(q32[t]);
-          o[t] = pack_bf16(a1 * x.x, a1 * x.y);
+          const int col = lane * 8 + 2 * t;
+          o[t] = pack_bf16(a1 * x.x + ((p.e_plus_i && col == row) ? 1.f : 0.f),
+                           a1 * x.y + ((p.e_plus_i && col + 1 == row) ? 1.f : 0.f));
         }
         *reinterpret_cast<uint4*>(E + static_cast<long long>(row) * CC + lane * 8) = make_uint4(o[0], o[1], o[2], o[3]);
       }
@@ -849,6 +851,8 @@ int gram_chain_bwd(const bf16* Sa, const bf16* Qb, const bf16* waug, const bf16*
   p.N = N; p.has_k2 = has_k2;
   const char* tr = getenv("GLF_CHAIN_TRACE");
   p.trace = (tr && tr[0] == '1') ? 1 : 0;
+  const char* ei = getenv("GLF_EXP_EI");
+  p.e_plus_i = (ei && ei[0] == '1') ? 1 : 0;
   p.sfv = sfv; p.cvec = cvec; p.rv = rv; p.k1 = k1; p.k2 = k2; p.k3 = k3;
   p.bth = bth; p.bphi = bphi; p.bg = bg;
   p.Rb = Rb;
