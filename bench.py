@@ -36,8 +36,8 @@ def peaks():
     if os.path.exists(p):
         d = json.load(open(p))
         return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
-                "source": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback"}
+                "bf16_tflops_burst": float(d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "bf16_tflops_burst": 1590.0, "source": "fallback"}
 
 
 class ClockSampler:
@@ -153,12 +153,22 @@ def make_inputs(clips: int, C: int, seed: int, device, pinned: bool = False):
     return [t.to(device) for t in f4], [t.to(device) for t in cls], [t.to(device) for t in ctr]
 
 
+def randomize_affine_(module, seed: int):
+    """BatchNorm gamma / beta are initialised to 0 in the reference (the attention branch then outputs 0 and
+    its gradients vanish), so a benchmark on "random-init" weights re-randomises the BN and LayerNorm affines."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for p, mean in ((module.W_z[1].weight, 1.0), (module.W_z[1].bias, 0.0), (module.norm_layer.weight, 1.0),
+                        (module.norm_layer.bias, 0.0)):
+            p.copy_(mean + 0.2 * torch.randn(p.shape, generator=g))
+
+
 def seeded_fusion(C: int, device):
     from glfusion_b200 import GlobalLocalFusion
-    from oracle import tpavi_oracle as O     # parameter recipe only (seeded init + BN/LN affine re-randomised, F3)
-    f = GlobalLocalFusion(in_channels=C)
-    f.global_attn.load_state_dict(O.init_params(C, seed=0, randomize_affine=True), strict=True)
-    f.local_attn.load_state_dict(O.init_params(C, seed=1, randomize_affine=True), strict=True)
+    torch.manual_seed(0)
+    f = GlobalLocalFusion(in_channels=C)     # the reference's own initialisers (identical RNG stream, tests/test_module_cpu.py)
+    randomize_affine_(f.global_attn, 10)
+    randomize_affine_(f.local_attn, 11)
     return f.to(device).train()
 
 
@@ -191,7 +201,7 @@ def algorithmic_work(clips: int, C: int):
     return 2 * (fwd + bwd + small), rows
 
 
-def bind_to_gpu_numa(index: int):
+def bind_to_gpu_numa(index: int, world: int = 1):
     """Pin this process to the CPUs NVML reports as local to GPU `index`, so that the pinned host staging buffers of
     the end-to-end pipeline are allocated on the GPU's own NUMA node (8 ranks otherwise contend for one socket's
     memory and PCIe root).  Returns (original affinity, number of local CPUs) or (None, None)."""
@@ -201,16 +211,32 @@ def bind_to_gpu_numa(index: int):
         uuid = str(torch.cuda.get_device_properties(index).uuid)
         h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
         ncpu = os.cpu_count() or 1
-        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
-        cpus = [i for i in range(ncpu) if (int(mask[i // 64]) >> (i % 64)) & 1]
+
+        def cpus_of(handle):
+            mask = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+            return [i for i in range(ncpu) if (int(mask[i // 64]) >> (i % 64)) & 1]
+        cpus = cpus_of(h)
         orig = os.sched_getaffinity(0)
         cpus = [c for c in cpus if c in orig]
+        note = "NVML affinity"
+        if world > 1 and cpus:
+            # when NVML reports the SAME CPU set for every GPU (one NUMA node for the whole box) binding all ranks to
+            # it would stack them on the same cores: each rank takes its own slice of the set instead.  The pinned
+            # staging memory of all ranks then still comes from that one node - a platform limit, stated in the line.
+            same = True
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                if i != index and cpus_of(pynvml.nvmlDeviceGetHandleByIndex(i)) != cpus_of(h):
+                    same = False
+            if same:
+                per = max(1, len(cpus) // world)
+                cpus = cpus[(index % world) * per:(index % world) * per + per] or cpus
+                note = "one CPU set for all GPUs (single NUMA node): ranks take disjoint slices of it"
         if cpus:
             os.sched_setaffinity(0, cpus)
-            return orig, len(cpus)
+            return orig, len(cpus), note
     except Exception:
         pass
-    return None, None
+    return None, None, None
 
 
 def run_ours(args):
@@ -218,7 +244,7 @@ def run_ours(args):
     rank, local_rank, world = dp.init_process_group("nccl")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    orig_affinity, numa_cpus = bind_to_gpu_numa(local_rank)
+    orig_affinity, numa_cpus, numa_note = bind_to_gpu_numa(local_rank, world)
     C = args.channels
     clips = args.clips
     fusion = seeded_fusion(C, dev)
@@ -392,15 +418,39 @@ def run_ours(args):
         "achieved_tflops_algorithmic": round(flops / (ms * 1e-3) / 1e12, 2),
         "peaks": pk,
     }
-    out.update(kernel_probe(args, dev, clips, C, pk))
+    # roofline = the dominant kernel BY TIME PER KERNEL NAME of the step (profiles/r02_*_launches.csv): the big K-major
+    # tile GEMM that forms dX (two launches per step); the largest single launch (fused LayerNorm backward pair) and the
+    # largest tensor-core product (S = X^T X) are reported beside it, and the whole step against its HBM floor.
+    ln = kernel_probe(args, dev, clips, C, pk)["roofline"]
     if dot_algorithm(C) == "gram":
+        gm = dx_gemm_probe(dev, clips, C, pk)
+        gm["launches_per_step"] = 2
+        gm["share_of_step"] = round(2 * gm["ms_per_launch"] / burst_ms, 3)
+        gm["share_note"] = "launches_per_step x ms_per_launch / burst ms_per_step (both timed at boost clocks)"
+        out["roofline"] = gm
+        ln["launches_per_step"] = 1
+        ln["share_of_step"] = round(ln["ms_per_launch"] / burst_ms, 3)
+        out["roofline_ln_bwd"] = ln
         out["roofline_secondary"] = gram_probe(dev, clips, C, pk)
-        out["roofline_gemm"] = dx_gemm_probe(dev, clips, C, pk)
+        # the algorithm that runs (Gram form): gate 3P + 2 x (S 1P + U 2P) + LN pair 5P forward,
+        # LN pair 7P + 2 x (R 2P + dX 3P) + gate 4P backward = 35 passes of P = rows x C x 2 bytes
+        step_bytes = 35 * rows * C * 2
+        out["roofline_step"] = {
+            "bound": "hbm", "executed_bytes_per_step": step_bytes, "passes": 35,
+            "achieved": round(step_bytes / (ms * 1e-3) / 1e9, 1), "achieved_burst": round(step_bytes / (burst_ms * 1e-3) / 1e9, 1),
+            "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(step_bytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4),
+            "frac_burst": round(step_bytes / (burst_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4),
+            "note": "token-sized activation passes only; the per-sequence [C x C] matrices (1/12 of a pass each) are not counted"}
+    else:
+        out["roofline"] = ln
     out["gpu_launches"] = (count_launches(clips, C) + (1 if p2p else 0)) * args.steps
-    out["config"]["host_numa"] = (f"process bound to the {numa_cpus} CPUs local to its GPU (NVML affinity)"
+    out["e2e"]["per_gpu"] = round(out["e2e"]["value"] / world, 2)
+    out["config"]["host_numa"] = (f"process bound to {numa_cpus} CPUs local to its GPU ({numa_note})"
                                   if numa_cpus else "no NUMA binding")
     if orig_affinity is not None:
         os.sched_setaffinity(0, orig_affinity)       # the CPU baseline below uses every host core again
+    if world == 1 and not args.no_gpu_reference:
+        out["gpu_reference"] = gpu_reference(C, dev)
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(C, seconds=args.cpu_seconds)
     emit(out)
@@ -409,8 +459,12 @@ def run_ours(args):
 def count_launches(clips: int, C: int) -> int:
     """Kernels launched by libglf_sm100a per step (fwd+bwd, both modules + gate), counted from the orchestration in
     glfusion_b200/csrc/glf_api.cu (memset/memcpy nodes excluded); agrees with profiles/r01_v11_launches.csv (39,
-    token-space form) and profiles/r01_v17_launches.csv (55, Gram form)."""
-    if dot_algorithm(C) == "gram":
+    token-space form), profiles/r01_v17_launches.csv (55, Gram form as batched tile GEMMs) and
+    profiles/r02_v3_launches.csv (27, Gram form with the per-sequence chain kernels)."""
+    if dot_algorithm(C) == "gram" and C == 256 and os.environ.get("GLF_GRAM_CHAIN", "1") != "0":
+        fwd_mod = 5      # prep_weights, S (gram_kernel), chain_fwd, U GEMM, bn_finalize
+        bwd_mod = 6      # finalize, R (gram_kernel), chain_bwd, wgrad, wgrad_reduce, dX GEMM
+    elif dot_algorithm(C) == "gram":
         fwd_mod = 9      # prep_weights, S (gram_kernel), T, M, W', Q~ GEMMs, cvec, U GEMM, bn_finalize
         bwd_mod = 16     # finalize, R (gram_kernel), kprep, dQ~, dW', dW~theta, dWz, dM, dW~g, dT, dW~phi, G0, H GEMMs,
         #                  assemble_F, dX GEMM, unpack_grads
@@ -512,8 +566,10 @@ def gram_probe(dev, clips, C, pk):
         if t.get("rows") == B * N and t.get("C") == C and t.get("kernel") == "gram_kernel":
             traffic = int(t["traffic_bytes"])
     return {"bound": "tensor", "kernel": "gram_kernel (S = X^T X per sequence, + column sums)",
-            "achieved": round(ach, 1), "peak": pk["bf16_tflops"], "peak_source": pk["source"], "unit": "TFLOP/s",
-            "frac": round(ach / pk["bf16_tflops"], 4), "traffic": traffic,
+            "achieved": round(ach, 1), "peak": pk["bf16_tflops_burst"],
+            "peak_source": pk["source"] + " (burst figure: the kernel is timed alone)", "unit": "TFLOP/s",
+            "frac": round(ach / pk["bf16_tflops_burst"], 4), "frac_of_sustained": round(ach / pk["bf16_tflops"], 4),
+            "traffic": traffic,
             "algorithmic_flops_per_launch": flops, "ms_per_launch": round(ms, 4),
             "hbm_gbs_same_launch": round(B * N * C * 2 / (ms * 1e-3) / 1e9, 1)}
 
@@ -527,13 +583,13 @@ def dx_gemm_probe(dev, clips, C, pk):
     lib = L.load()
     B, N = clips * F, V * HH * WW
     A = torch.randn(B, N, 2 * C, device=dev).to(torch.bfloat16)           # [dV | X] side by side
-    Bm = (torch.randn(B, C, 2 * C, device=dev) * 0.05).to(torch.bfloat16)
+    Bm = (torch.randn(B, 2 * C, C, device=dev) * 0.05).to(torch.bfloat16)   # [E ; F] per sequence, read MN-major
     bias = torch.randn(C, device=dev)
     D = torch.empty(B, N, C, device=dev, dtype=torch.bfloat16)
     stream = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def launch():
-        L.check(lib.glf_gemm_bf16(L.ptr(A), L.ptr(Bm), L.ptr(D), N, C, 2 * C, B, 0, 0, 2 * C, 2 * C, C, N * 2 * C,
+        L.check(lib.glf_gemm_bf16(L.ptr(A), L.ptr(Bm), L.ptr(D), N, C, 2 * C, B, 0, 1, 2 * C, C, C, N * 2 * C,
                                   C * 2 * C, N * C, L.ptr(bias), 1.0, L.ptr(A), 2 * C, N * 2 * C, 0, 1, None, stream))
     for _ in range(3):
         launch()
@@ -548,15 +604,31 @@ def dx_gemm_probe(dev, clips, C, pk):
     ms = e0.elapsed_time(e1) / n
     alg_bytes = 3 * B * N * C * 2
     ach = alg_bytes / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "gemm_kernel<0,*,128,2> (dX = [dV | X][E ; F] + e + dV, K = 2C)",
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    traffic = None
+    if os.path.exists(tp):
+        t = json.load(open(tp)).get("gemm_dx", {})
+        if t.get("rows") == B * N and t.get("C") == C:
+            traffic = int(t["traffic_bytes"])
+    return {"bound": "hbm", "kernel": "gemm_kernel<0,1,128,2> (dX = [dV | X][E ; F] + e + dV, K = 2C)",
             "achieved": round(ach, 1), "peak": pk["hbm_gbs"], "peak_source": pk["source"], "unit": "GB/s",
-            "frac": round(ach / pk["hbm_gbs"], 4), "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+            "frac": round(ach / pk["hbm_gbs"], 4), "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
             "ms_per_launch": round(ms, 4), "inputs": "617 MB per launch, larger than the 126 MB L2"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def reference_kind() -> str:
+    """'reference' when oracle/_ref holds the unmodified reference module (staged by build() from /root/reference),
+    else 'port' (the oracle's op-for-op restatement)."""
+    from oracle import build_ref
+    return "reference" if build_ref.load_reference_tpavi() is not None else "port"
+
+
 def cpu_step(C: int, clips: int, seed: int = 0):
-    """One fwd+bwd of the reference algorithm (oracle port: literal N x N attention, fp32, autograd) on the host."""
+    """One fwd+bwd of the reference's own fusion path on the host: two UNMODIFIED reference TPAVIModules
+    (oracle/_ref/models/TPAVI.py) inside the literal call-site lines R/models/ours.py:1802-1834 (fp32, N x N attention
+    materialised, autograd backward); the oracle port of the same algorithm when oracle/_ref was never staged."""
+    from oracle import build_ref
     from oracle import tpavi_oracle as O
     B = clips * F
     g = torch.Generator().manual_seed(seed)
@@ -566,9 +638,47 @@ def cpu_step(C: int, clips: int, seed: int = 0):
     do = [torch.randn(B, C, HH, WW, generator=g) for _ in range(V)]
     pg = O.init_params(C, seed=0, randomize_affine=True)
     pl = O.init_params(C, seed=1, randomize_affine=True)
+    TPAVI = build_ref.load_reference_tpavi()
     t0 = time.perf_counter()
-    O.fusion_fwd_bwd(f4, cl, ct, do, pg, pl)
+    if TPAVI is not None:
+        build_ref.reference_fusion_fwd_bwd(TPAVI, f4, cl, ct, do, pg, pl)
+    else:
+        O.fusion_fwd_bwd(f4, cl, ct, do, pg, pl)
     return time.perf_counter() - t0
+
+
+def gpu_reference(C: int, dev):
+    """The number to beat on the same box: the UNMODIFIED reference module pair in PyTorch
+    eager mode on this GPU, fp32 (as shipped) and under bf16 autocast, one clip (16 sequences) per step."""
+    from oracle import build_ref
+    from oracle import tpavi_oracle as O
+    TPAVI = build_ref.load_reference_tpavi()
+    if TPAVI is None:
+        return {"unavailable": "oracle/_ref was not staged (no /root/reference at build time)"}
+    B = F
+    g = torch.Generator().manual_seed(0)
+    f4 = [torch.randn(B, C, HH, WW, generator=g).to(dev) for _ in range(V)]
+    cl = [torch.randn(B, NCLS, HH, WW, generator=g).to(dev) for _ in range(V)]
+    ct = [torch.randn(B, 1, HH, WW, generator=g).to(dev) for _ in range(V)]
+    do = [torch.randn(B, C, HH, WW, generator=g).to(dev) for _ in range(V)]
+    pg = {k: v.to(dev) for k, v in O.init_params(C, seed=0, randomize_affine=True).items()}
+    pl = {k: v.to(dev) for k, v in O.init_params(C, seed=1, randomize_affine=True).items()}
+    res = {"unit": "clips/s", "sample": "1 clip (16 sequences x 3136 tokens) per step, unmodified R/models/TPAVI.py x 2 + "
+                                        "the call-site lines ours.py:1802-1834, PyTorch eager, CUDA-event timed, best of 5"}
+    for name, ac in (("fp32", False), ("bf16_autocast", True)):
+        ts = []
+        for i in range(7):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+                build_ref.reference_fusion_fwd_bwd(TPAVI, f4, cl, ct, do, pg, pl)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ts.append(e0.elapsed_time(e1))
+        res[name] = round(1.0 / (min(ts) * 1e-3), 2)
+    return res
 
 
 def cpu_baseline(C: int, seconds: float = 15.0):
@@ -580,9 +690,12 @@ def cpu_baseline(C: int, seconds: float = 15.0):
     while len(times) < 3 or (time.perf_counter() - t_start < seconds and len(times) < 20):
         times.append(cpu_step(C, 1))
     best = min(times)
-    return {"value": round(1.0 / best, 4), "unit": "clips/s", "cores": cores, "kind": "port",
-            "sample": f"1 clip (16 sequences x 3136 tokens, C={C}) fp32 fwd+bwd of the oracle port of the reference "
-                      f"algorithm (N x N attention materialised), best of {len(times)} after 1 warm-up"}
+    kind = reference_kind()
+    what = ("the unmodified reference module pair (oracle/_ref/models/TPAVI.py) in the call-site lines ours.py:1802-1834"
+            if kind == "reference" else "the oracle port of the reference algorithm")
+    return {"value": round(1.0 / best, 4), "unit": "clips/s", "cores": cores, "kind": kind,
+            "sample": f"1 clip (16 sequences x 3136 tokens, C={C}) fp32 fwd+bwd of {what} "
+                      f"(N x N attention materialised), best of {len(times)} after 1 warm-up"}
 
 
 def run_reference(args):
@@ -607,8 +720,11 @@ def run_reference(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"BASELINE configs[1]: MGFM+MLFM modules only, 4 views x 16 frames x 28x28 tokens, C={C}, "
                                "fwd+bwd, frames-as-batch; bounded sample: 1 clip per step on the host CPU"},
-        "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": "port",
-                         "sample": "1 clip per step, oracle port of the reference algorithm (fp32, N x N materialised)"},
+        "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": reference_kind(),
+                         "sample": "1 clip per step, " + ("the unmodified reference module pair (oracle/_ref/models/TPAVI.py)"
+                                                          if reference_kind() == "reference" else
+                                                          "oracle port of the reference algorithm") +
+                                   " in the call-site lines ours.py:1802-1834 (fp32, N x N materialised)"},
         "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(out)
@@ -657,6 +773,7 @@ def main():
     ap.add_argument("--p2p-allreduce", type=int, default=1, help="gradient all-reduce as one NVLink peer-memory kernel")
     ap.add_argument("--graph-allreduce", type=int, default=-1, help="capture the NCCL gradient all-reduce in the step graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":

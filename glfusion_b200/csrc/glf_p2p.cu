@@ -16,6 +16,8 @@
 // the kernel has no epoch argument and replays unchanged from a CUDA graph.
 #include <cstring>
 
+#include <cstdlib>
+
 #include "glf_internal.h"
 
 namespace glf {
@@ -32,17 +34,22 @@ struct P2PParams {
   int rank, world;
   long long n4;     // float4 vectors
   float scale;
+  unsigned long long timeout_ns;   // 0 = wait for the peers as long as it takes (the default, like an NCCL collective)
 };
 
-// Bounded spins: a rank that never arrives (crashed peer, mismatched call counts) traps this kernel after ~20 s of wall
-// clock -- the launch then reports an error on the host -- instead of hanging the GPU.
-constexpr unsigned long long P2P_TIMEOUT_NS = 20000000000ull;
+// Ranks of a training job drift apart by far more than any fixed bound (rank-0 checkpoints, validation, data-loader
+// stalls), so by default the spins below wait indefinitely, exactly as an NCCL collective would; a hung peer is the host
+// watchdog's business.  GLF_P2P_TIMEOUT_S=<seconds> (debugging aid, read at launch) bounds them: on expiry the kernel
+// traps, which is sticky for the CUDA context -- use it to find mismatched call counts, not in production.
+// Co-residency: block b of rank A waits for block b of rank B, so every block of the grid must be resident on every
+// rank at the same time; p2p_allreduce() checks grid <= SMs x blocks-per-SM before launching, and callers must not
+// run another kernel that holds all SMs indefinitely on the same device.
 __device__ __forceinline__ unsigned long long p2p_now_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void signal_peer(uint32_t* addr) {
+__device__ __forceinline__ void signal_peer(uint32_t* addr, unsigned long long P2P_TIMEOUT_NS) {
   uint32_t old;
   unsigned long long t0 = 0;
   unsigned spins = 0;
@@ -51,11 +58,11 @@ __device__ __forceinline__ void signal_peer(uint32_t* addr) {
     if (old != 0u && ++spins > 4096u) {
       const unsigned long long now = p2p_now_ns();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > P2P_TIMEOUT_NS) __trap();
+      else if (P2P_TIMEOUT_NS != 0 && now - t0 > P2P_TIMEOUT_NS) __trap();
     }
   } while (old != 0u);
 }
-__device__ __forceinline__ void wait_own(uint32_t* addr) {
+__device__ __forceinline__ void wait_own(uint32_t* addr, unsigned long long P2P_TIMEOUT_NS) {
   uint32_t old;
   unsigned long long t0 = 0;
   unsigned spins = 0;
@@ -64,7 +71,7 @@ __device__ __forceinline__ void wait_own(uint32_t* addr) {
     if (old != 1u && ++spins > 4096u) {
       const unsigned long long now = p2p_now_ns();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > P2P_TIMEOUT_NS) __trap();
+      else if (P2P_TIMEOUT_NS != 0 && now - t0 > P2P_TIMEOUT_NS) __trap();
     }
   } while (old != 1u);
 }
@@ -81,8 +88,8 @@ __device__ __forceinline__ void block_barrier(const P2PParams& p, int phase) {
   if (t < p.world && t != p.rank) {
     __threadfence_system();
     const long long slot = (static_cast<long long>(phase) * gridDim.x + blockIdx.x) * p.world;
-    signal_peer(p.sigs[t] + slot + p.rank);
-    wait_own(p.sigs[p.rank] + slot + t);
+    signal_peer(p.sigs[t] + slot + p.rank, p.timeout_ns);
+    wait_own(p.sigs[p.rank] + slot + t, p.timeout_ns);
   }
   __syncthreads();
 }
@@ -141,6 +148,18 @@ int p2p_allreduce(void* const* bufs, void* const* sigs, int rank, int world, lon
   p.rank = rank; p.world = world;
   p.n4 = n_floats / 4;
   p.scale = scale;
+  p.timeout_ns = 0;
+  if (const char* e = getenv("GLF_P2P_TIMEOUT_S")) {
+    const double sec = atof(e);
+    if (sec > 0) p.timeout_ns = static_cast<unsigned long long>(sec * 1e9);
+  }
+  // every block spins on its peers: the whole grid must be co-resident
+  int dev = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p2p_allreduce_kernel, P2P_THREADS, 0) != cudaSuccess)
+    return set_error(GLF_ERR_DEVICE, "p2p all-reduce: cannot query occupancy");
+  if (static_cast<long long>(sms) * per_sm < p2p_grid(n_floats))
+    return set_error(GLF_ERR_DEVICE, "p2p all-reduce: %d blocks cannot be co-resident on %d SMs", p2p_grid(n_floats), sms);
   p2p_allreduce_kernel<<<p2p_grid(n_floats), P2P_THREADS, 0, stream>>>(p);
   return check_cuda(cudaGetLastError(), "p2p all-reduce launch");
 }

@@ -68,8 +68,16 @@ class GradBucket:
     def bind(self, modules) -> None:
         """Zero-copy mode: make the TPAVI blocks in `modules` write their parameter gradients straight into this
         bucket (module._grad_out: kernel-side name -> bucket view), so that after backward `p.grad` aliases the flat
-        buffer and the all-reduce needs neither pack nor unpack.  Falls back to copies whenever a gradient ends up
-        elsewhere (first accumulation into an existing .grad, dtype mismatch, ...)."""
+        buffer and the all-reduce needs neither pack nor unpack.
+
+        The kernels assign, they never accumulate, so the views are handed out only to the first backward node of a
+        step that touches a module and only while its parameters have no .grad yet (tpavi.claim_grad_out): a module
+        that runs twice before one backward (the reference's cycle pass, R/main.py:209/:221), gradient accumulation
+        and zero_grad(set_to_none=False) all fall back to fresh gradient tensors that autograd sums, and
+        allreduce_mean() then packs / unpacks.  The zero-copy path therefore needs zero_grad(set_to_none=True)
+        (PyTorch's default) and one use of each module per backward; everything else stays correct, just not
+        zero-copy.  Only the parameters a block really differentiates (module._plist()) belong in the bucket:
+        align_channel.* never receives a gradient on the fusion path."""
         index = {id(p): v for p, v in zip(self.params, self.views)}
         for mod in modules:
             table = dict(mod.named_parameters())
@@ -101,9 +109,10 @@ class GradBucket:
             return
         for v, p in zip(self.views, self.params):
             if p.grad is None:
-                p.grad = v.clone().to(p.dtype)
-            else:
-                p.grad.copy_(v)
+                # no rank-local gradient: leave it None (the reference optimizer skips such parameters; giving them
+                # a zero .grad would subject them to weight decay / momentum)
+                continue
+            p.grad.copy_(v)
 
     def enable_p2p(self, group=None) -> bool:
         """Exchange CUDA IPC handles of the bucket allocation with the other ranks of `group` (one node, <= 8 GPUs).
@@ -129,6 +138,7 @@ class GradBucket:
             return False
         bases = []
         opened_all = True
+        self._opened = []          # (peer base pointer, offset) of every IPC mapping this bucket holds
         for r, (h, o) in enumerate(gathered):
             if r == rank:
                 bases.append(self._raw.data_ptr())
@@ -141,15 +151,36 @@ class GradBucket:
                 bases.append(0)
             else:
                 bases.append(int(out.value))
+                self._opened.append((int(out.value), int(o)))
         flags = [None] * world
         dist.all_gather_object(flags, opened_all, group=group)
         if not all(flags):
+            self.close_p2p()       # some rank could not map a peer: drop the mappings that did open
             return False
         sigs = (C.c_void_p * world)(*bases)
         bufs = (C.c_void_p * world)(*[b + self._sig_bytes for b in bases])
         self._p2p = (bufs, sigs, rank, world)
         dist.barrier(group=group)
         return True
+
+    def close_p2p(self) -> None:
+        """Unmap the peers' buckets (cudaIpcCloseMemHandle through glf_p2p_close) and return to the NCCL path."""
+        opened, self._opened = getattr(self, "_opened", []), []
+        self._p2p = None
+        if not opened:
+            return
+        import ctypes as C
+        from . import _lib as L
+        lib = L.load()
+        for ptr, off in opened:
+            with torch.cuda.device(self._raw.device):
+                lib.glf_p2p_close(C.c_void_p(ptr), C.c_uint64(off))
+
+    def __del__(self):
+        try:
+            self.close_p2p()
+        except Exception:      # interpreter shutdown: the driver reclaims the mappings with the context
+            pass
 
     @property
     def p2p_enabled(self) -> bool:

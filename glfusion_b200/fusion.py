@@ -19,18 +19,22 @@ import torch
 from torch import nn
 
 from . import _lib as L
-from .tpavi import (TPAVIModule, TPAVIState, _blob, _io_dtype, _stream_ptr, _weights_struct, tpavi_backward_raw,
-                    tpavi_forward_raw)
+import threading
+
+from .tpavi import (TPAVIModule, TPAVIState, _blob, _io_dtype, _stream_ptr, _weights_struct, claim_grad_out,
+                    tpavi_backward_raw, tpavi_forward_raw)
 
 
 _SIDE_STREAMS = {}
+_SIDE_LOCK = threading.Lock()      # nn.DataParallel drives one Python thread per GPU through this module
 
 
 def _side_stream(device) -> "torch.cuda.Stream":
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
-    if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
-    return _SIDE_STREAMS[key]
+    with _SIDE_LOCK:
+        if key not in _SIDE_STREAMS:
+            _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+        return _SIDE_STREAMS[key]
 
 
 def _pair_ln_ok(mg, ml, shape, x, prec) -> bool:
@@ -38,8 +42,10 @@ def _pair_ln_ok(mg, ml, shape, x, prec) -> bool:
     if mg.inter_channels != ml.inter_channels or mg._mode_id != ml._mode_id or mg._bn_layer != ml._bn_layer:
         return False
     B, T, H, W, C_ = shape
-    st = TPAVIState(B, C_, T, H, W, mg.inter_channels, mg._mode_id, _io_dtype(x), L.LAYOUT_TOKEN, mg.training,
-                    mg._bn_layer, precision=prec, defer_ln=True)
+    if mg._norm_config() != ml._norm_config():
+        return False
+    st = TPAVIState(B, C_, T, H, W, mg.inter_channels, mg._mode_id, _io_dtype(x), L.LAYOUT_TOKEN,
+                    mg._norm_config()["training"], mg._bn_layer, precision=prec, defer_ln=True)
     return bool(L.load().glf_fusion_ln_supported(C.byref(st.desc)))
 
 
@@ -91,6 +97,7 @@ class _FusionFunction(torch.autograd.Function):
         f4, cls, ctr = tensors[:V], tensors[V:2 * V], tensors[2 * V:3 * V]
         pg, pl = tensors[3 * V:3 * V + ng], tensors[3 * V + ng:]
         mg, ml = fusion.global_attn, fusion.local_attn
+        mg._grad_out_claimed = ml._grad_out_claimed = False      # a new autograd graph (tpavi.claim_grad_out)
         prec = mg._precision_id()
         if ml._precision_id() != prec:
             raise ValueError("global_attn and local_attn must use the same compute_precision")
@@ -110,18 +117,18 @@ class _FusionFunction(torch.autograd.Function):
             cur = torch.cuda.current_stream(xg.device)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                _, stl, svl, _ = tpavi_forward_raw(xl, tl, ml._buffer_table(), mode=ml._mode_id, training=ml.training,
+                _, stl, svl, _ = tpavi_forward_raw(xl, tl, ml._buffer_table(), mode=ml._mode_id, **ml._norm_config(),
                                                    bn_layer=ml._bn_layer, Ci=ml.inter_channels,
                                                    keep_for_backward=True, z_out=zsum, accumulate=False,
                                                    token_shape=shape, precision=prec, defer_ln=True)
-        _, stg, svg, _ = tpavi_forward_raw(xg, tg, mg._buffer_table(), mode=mg._mode_id, training=mg.training,
+        _, stg, svg, _ = tpavi_forward_raw(xg, tg, mg._buffer_table(), mode=mg._mode_id, **mg._norm_config(),
                                            bn_layer=mg._bn_layer, Ci=mg.inter_channels,
                                            keep_for_backward=need or pair, z_out=zsum, token_shape=shape,
                                            precision=prec, defer_ln=pair)
         if side is not None:
             cur.wait_stream(side)
         else:
-            _, stl, svl, _ = tpavi_forward_raw(xl, tl, ml._buffer_table(), mode=ml._mode_id, training=ml.training,
+            _, stl, svl, _ = tpavi_forward_raw(xl, tl, ml._buffer_table(), mode=ml._mode_id, **ml._norm_config(),
                                                bn_layer=ml._bn_layer, Ci=ml.inter_channels,
                                                keep_for_backward=need or pair, z_out=zsum, accumulate=not pair,
                                                token_shape=shape, precision=prec, defer_ln=pair)
@@ -168,20 +175,21 @@ class _FusionFunction(torch.autograd.Function):
                 L.check(L.load().glf_fusion_ln_bwd(C.byref(stg.desc), L.ptr(dz), L.ptr(xg), L.ptr(xl), C.byref(wg),
                                                    C.byref(wl), L.ptr(svg), L.ptr(svl), L.ptr(wsg), L.ptr(wsl),
                                                    _stream_ptr()))
+        gout_g, gout_l = claim_grad_out(mg), claim_grad_out(ml)
         side = _side_stream(xg.device) if ctx.pair and ctx.fusion.overlap_blocks else None
         if side is not None:       # after the fused LayerNorm backward the two blocks' chains are independent again
             cur = torch.cuda.current_stream(xg.device)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 dxl, gl = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xl, stl, svl, tl, ml._buffer_table(), ws=wsl,
-                                             grad_out=getattr(ml, "_grad_out", None))
+                                             grad_out=gout_l)
         dxg, gg = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xg, stg, svg, tg, mg._buffer_table(), ws=wsg,
-                                     grad_out=getattr(mg, "_grad_out", None))
+                                     grad_out=gout_g)
         if side is not None:
             cur.wait_stream(side)
         else:
             dxl, gl = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xl, stl, svl, tl, ml._buffer_table(), ws=wsl,
-                                         grad_out=getattr(ml, "_grad_out", None))
+                                         grad_out=gout_l)
         df4, dcls, dctr = gate_concat_backward(f4, cls, ctr, gate, dxg, dxl, ctx.fusion.center_aware_weight)
         out = [None, None, None] + list(df4) + list(dcls) + list(dctr)
         for mod, plist, gr in ((mg, pg, gg), (ml, pl, gl)):

@@ -102,7 +102,7 @@ def _weights_struct(p, buffers) -> L.GlfWeights:
 def tpavi_forward_raw(x: torch.Tensor, params: dict, buffers, *, mode: int, training: bool, bn_layer: bool,
                       Ci: int, keep_for_backward: bool, z_out: Optional[torch.Tensor] = None,
                       accumulate: bool = False, token_shape=None, precision: int = L.PRECISION_BF16,
-                      defer_ln: bool = False):
+                      defer_ln: bool = False, eps_bn: float = 1e-5, eps_ln: float = 1e-5, momentum: float = 0.1):
     """Run glf_tpavi_fwd.  ``x`` is either NCTHW-contiguous or token-major (see ``_is_token_major``), or, when
     ``token_shape=(B,T,H,W,C)`` is given, a dense token-major buffer of that shape.
     Returns (z_buffer [B,T,H,W,C], state, saved_blob)."""
@@ -120,7 +120,7 @@ def tpavi_forward_raw(x: torch.Tensor, params: dict, buffers, *, mode: int, trai
             x = x.contiguous()
             layout = L.LAYOUT_NCTHW
     st = TPAVIState(B, C_, T, H, W, Ci, mode, _io_dtype(x), layout, training, bn_layer, accumulate,
-                    precision=precision, defer_ln=defer_ln)
+                    eps_bn=eps_bn, eps_ln=eps_ln, momentum=momentum, precision=precision, defer_ln=defer_ln)
     dev = x.device
     if z_out is None:
         z_out = torch.empty((B, T, H, W, C_), dtype=x.dtype, device=dev)
@@ -173,16 +173,37 @@ def tpavi_backward_raw(dz: torch.Tensor, dz_layout: int, x: torch.Tensor, st: TP
     return dx_out, grads
 
 
+def claim_grad_out(module):
+    """dp.GradBucket.bind() lets a block's backward write its parameter gradients straight into the all-reduce bucket.
+    The kernels ASSIGN (they never accumulate), so the bucket views may be handed out only to the FIRST backward node of
+    a step that touches the module, and only while no gradient has been accumulated yet:
+
+      * a module used twice before one backward (the reference's cycle pass, R/main.py:209 and :221): the second node
+        gets fresh tensors and autograd adds the two contributions;
+      * gradient accumulation / zero_grad(set_to_none=False): p.grad already exists (it may even alias the bucket), so
+        the node writes to fresh tensors and autograd accumulates into p.grad.
+
+    The claim is released by the next forward of the module (a new autograd graph)."""
+    table = getattr(module, "_grad_out", None)
+    if not table or getattr(module, "_grad_out_claimed", False):
+        return None
+    if any(p.grad is not None for p in module._plist()):
+        return None
+    module._grad_out_claimed = True
+    return table
+
+
 class _TPAVIFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, module, *plist):
+        module._grad_out_claimed = False
         params = module._param_table(plist)
         buffers = module._buffer_table()
         need_grad = any(ctx.needs_input_grad)      # grad mode is off inside Function.forward
         z, st, saved, x_used = tpavi_forward_raw(x, params, buffers, mode=module._mode_id,
-                                                 training=module.training, bn_layer=module._bn_layer,
+                                                 bn_layer=module._bn_layer,
                                                  Ci=module.inter_channels, keep_for_backward=need_grad,
-                                                 precision=module._precision_id())
+                                                 precision=module._precision_id(), **module._norm_config())
         ctx.module = module
         ctx.st = st
         ctx.saved_blob = saved
@@ -206,7 +227,7 @@ class _TPAVIFunction(torch.autograd.Function):
             dz = dz.contiguous()
             layout = L.LAYOUT_NCTHW
         dx, grads = tpavi_backward_raw(dz, layout, x_used, ctx.st, ctx.saved_blob, params, module._buffer_table(),
-                                       grad_out=getattr(module, "_grad_out", None))
+                                       grad_out=claim_grad_out(module))
         if ctx.st.desc.x_layout == L.LAYOUT_TOKEN:
             dx = dx.permute(0, 4, 1, 2, 3)
         out = [dx, None]
@@ -268,6 +289,21 @@ class TPAVIModule(nn.Module):
             return L.PRECISIONS[self.compute_precision]
         except KeyError:
             raise ValueError(f"compute_precision must be one of {sorted(L.PRECISIONS)}, got {self.compute_precision!r}")
+
+    def _norm_config(self) -> dict:
+        """eps / momentum / train-or-eval of the normalisation layers, read from the nn holders (not assumed): a loaded
+        non-default configuration, or the usual 'freeze BatchNorm only' pattern (model.train(); bn.eval()), must act on
+        the kernels exactly as it would on the reference's layers.  Configurations the kernels do not implement raise."""
+        cfg = {"eps_bn": 1e-5, "eps_ln": float(self.norm_layer.eps), "momentum": 0.1, "training": bool(self.training)}
+        if not self.norm_layer.elementwise_affine:
+            raise NotImplementedError("LayerNorm without affine parameters is not supported")
+        if self._bn_layer:
+            bn = self.W_z[1]
+            if bn.momentum is None or not bn.track_running_stats or not bn.affine:
+                raise NotImplementedError("BatchNorm3d with momentum=None (cumulative average), track_running_stats=False "
+                                          "or affine=False is not supported by the sm_100a kernels")
+            cfg.update(eps_bn=float(bn.eps), momentum=float(bn.momentum), training=bool(bn.training))
+        return cfg
 
     # ---- parameter plumbing -------------------------------------------------------------------------------------
     def _plist_names(self):

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from conftest import load_golden
-from gpu_util import BF16_TOL, DEV, assert_close, dot_algo, golden_params
+from gpu_util import BF16_TOL, DEV, assert_close, grad_tol, dot_algo, golden_params
 from glfusion_b200 import GlobalLocalFusion
 from oracle import tpavi_oracle as O
 
@@ -40,7 +40,7 @@ def test_glue_golden(io, algo):
     for tag, mod in (("g", f.global_attn), ("l", f.local_attn)):
         for k, p in mod.named_parameters():
             if not k.startswith("align_channel"):
-                assert_close(f"grad_{tag}:{k}", p.grad, g[f"grad_{tag}:{k}"], 3e-2, abs_floor=1e-3)
+                assert_close(f"grad_{tag}:{k}", p.grad, g[f"grad_{tag}:{k}"], grad_tol(k), abs_floor=1e-3)
 
 
 @pytest.mark.parametrize("algo", ["token", "gram"])
@@ -71,7 +71,7 @@ def test_cfg2_shape_against_oracle(algo):
     for mod, ref in ((f.local_attn, gl), (f.global_attn, gg)):
         for k, p in mod.named_parameters():
             if not k.startswith("align_channel"):
-                assert_close("grad:" + k, p.grad, ref[k], 3e-2, abs_floor=1e-3)
+                assert_close("grad:" + k, p.grad, ref[k], grad_tol(k), abs_floor=1e-3)
 
 
 @pytest.mark.parametrize("h,w,V,io", [(5, 7, 3, "fp32"), (5, 7, 2, "bf16"), (9, 8, 1, "bf16")])
@@ -104,7 +104,7 @@ def test_ragged_spatial_sizes_against_oracle(h, w, V, io, algo):
         assert_close(f"dctr:{v}", ctd[v].grad, dctr[v], 4e-2)
     for k, p in f.global_attn.named_parameters():
         if not k.startswith("align_channel"):
-            assert_close("grad_g:" + k, p.grad, gg[k], 3e-2, abs_floor=1e-3)
+            assert_close("grad_g:" + k, p.grad, gg[k], grad_tol(k), abs_floor=1e-3)
 
 
 def test_glue_golden_fp32_precision():
@@ -163,3 +163,76 @@ def test_forward_parts_matches_reference_return_values():
         assert_close(f"df4:{i}", f4d[i].grad, f4o[i].grad, 3e-2)
     assert f.local_attn.theta.weight.grad is None            # the local block is not on the cycle pass's path
     assert_close("grad_g:theta.weight", f.global_attn.theta.weight.grad, qg["theta.weight"].grad, 3e-2)
+
+
+def test_bench_configuration_graph_replay():
+    """The EXACT configuration bench.py times: 8 clips = 128 sequences x 3136 tokens (4 views x 28 x 28), C = 256, bf16,
+    forward_stacked (fused two-stream node, Gram form with the per-sequence chain kernels), the step captured in a CUDA
+    graph and REPLAYED; outputs and input gradients of the replay against the oracle's closed form evaluated in fp64
+    (O(N C^2) per sequence: the N x N reference cannot be materialised at this size).  The oracle restatement itself
+    runs on the GPU here only because fp64 matmuls over 1.6 M tokens take minutes on the host; it is the same
+    oracle/tpavi_oracle.py code, pinned to the reference's golden vectors by tests/test_oracle.py."""
+    clips, Fr, V, h, w, C = 8, 16, 4, 28, 28, 256
+    B = clips * Fr
+    pg = O.init_params(C, seed=61, randomize_affine=True)
+    pl = O.init_params(C, seed=62, randomize_affine=True)
+    gen = torch.Generator().manual_seed(63)
+    f4 = [torch.randn(B, C, h, w, generator=gen).to(torch.bfloat16) for _ in range(V)]
+    cl = [torch.randn(B, 5, h, w, generator=gen) for _ in range(V)]
+    ct = [torch.randn(B, 1, h, w, generator=gen) for _ in range(V)]
+    dz = torch.randn(B, V, h, w, C, generator=gen).to(torch.bfloat16)
+    f = _build(C, pg, pl)
+    f4d = [t.to(DEV).requires_grad_(True) for t in f4]
+    cld, ctd = [t.to(DEV) for t in cl], [t.to(DEV) for t in ct]
+    dzd = dz.to(DEV).permute(0, 4, 1, 2, 3)
+    params = [p for p in f.parameters() if p.requires_grad]
+    holder = {}
+
+    def compute():
+        for t in f4d:
+            t.grad = None
+        for p in params:
+            p.grad = None
+        holder["out"] = f.forward_stacked(f4d, cld, ctd)
+        holder["out"].backward(dzd)
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            compute()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        compute()
+    # poison what the graph writes, then replay twice: the compared values are those of the LAST replay
+    holder["out"].detach().zero_()
+    for t in f4d:
+        t.grad.detach().zero_()
+    graph.replay()
+    graph.replay()
+    torch.cuda.synchronize()
+    out = holder["out"]
+
+    # ---- oracle: closed form in fp64
+    with torch.no_grad():
+        x = [t.to(DEV, torch.float64) for t in f4]
+        xg, xl = O.gate_concat(x, [t.to(DEV, torch.float64) for t in cl], [t.to(DEV, torch.float64) for t in ct])
+        gates = [O.gate_from_logits(a.to(DEV, torch.float64), b.to(DEV, torch.float64)) for a, b in zip(cl, ct)]
+        dz64 = dzd.to(torch.float64)
+        p64g = {k: (v.to(DEV, torch.float64) if v.is_floating_point() else v.to(DEV)) for k, v in pg.items()}
+        p64l = {k: (v.to(DEV, torch.float64) if v.is_floating_point() else v.to(DEV)) for k, v in pl.items()}
+        zg, dxg, gg, _ = O.tpavi_dot_closed_form(xg, dz64, p64g)
+        del xg
+        zl, dxl, gl, _ = O.tpavi_dot_closed_form(xl, dz64, p64l)
+        del xl
+        ref_out = zg + zl
+        del zg, zl
+        for v in range(V):
+            assert_close(f"out:{v}", out[:, :, v], ref_out[:, :, v], BF16_TOL)
+            assert_close(f"df4:{v}", f4d[v].grad, dxg[:, :, v] + gates[v] * dxl[:, :, v], BF16_TOL)
+        for mod, ref in ((f.global_attn, gg), (f.local_attn, gl)):
+            for k, p in mod.named_parameters():
+                if not k.startswith("align_channel"):
+                    assert_close("grad:" + k, p.grad, ref[k], grad_tol(k), abs_floor=1e-3)

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from conftest import load_golden
-from gpu_util import BF16_TOL, DEV, assert_close, dot_algo, golden_params, grad_scale, load_module_from_params
+from gpu_util import BF16_TOL, DEV, assert_close, grad_tol, dot_algo, golden_params, grad_scale, load_module_from_params
 from glfusion_b200 import TPAVIModule
 from oracle import tpavi_oracle as O
 
@@ -42,7 +42,7 @@ def test_golden_dot(name, io, algo):
         if k.startswith("align_channel"):
             assert p.grad is None
             continue
-        assert_close("grad:" + k, p.grad, g["grad:" + k], 3e-2, abs_floor=1e-3)
+        assert_close("grad:" + k, p.grad, g["grad:" + k], grad_tol(k), abs_floor=1e-3)
     if bn:
         sd = m.state_dict()
         for k in ("W_z.1.running_mean", "W_z.1.running_var"):
@@ -74,7 +74,7 @@ def test_oracle_dot_layouts(layout, algo):
     assert_close("dx", dx, dxo, BF16_TOL)
     for k, pp in m.named_parameters():
         if not k.startswith("align_channel"):
-            assert_close("grad:" + k, pp.grad, go[k], 3e-2, abs_floor=1e-3)
+            assert_close("grad:" + k, pp.grad, go[k], grad_tol(k), abs_floor=1e-3)
 
 
 @pytest.mark.parametrize("C", [128, 256, 64])
@@ -94,7 +94,7 @@ def test_gram_many_sequences(C):
     assert_close("dx", dx, dxo, BF16_TOL)
     for k, pp in m.named_parameters():
         if not k.startswith("align_channel"):
-            assert_close("grad:" + k, pp.grad, go[k], 3e-2, abs_floor=1e-3)
+            assert_close("grad:" + k, pp.grad, go[k], grad_tol(k), abs_floor=1e-3)
 
 
 @pytest.mark.parametrize("C,T,H,W", [(96, 2, 16, 16), (512, 4, 24, 24), (192, 3, 20, 20)])
@@ -116,7 +116,7 @@ def test_dot_other_widths(C, T, H, W, algo):
     assert_close("dx", dx, dxo, BF16_TOL)
     for k, pp in m.named_parameters():
         if not k.startswith("align_channel"):
-            assert_close("grad:" + k, pp.grad, go[k], 3e-2, abs_floor=1e-3)
+            assert_close("grad:" + k, pp.grad, go[k], grad_tol(k), abs_floor=1e-3)
 
 
 def test_eval_no_grad_inference_and_zero_init_trap():
@@ -167,7 +167,7 @@ def test_golden_embedded(name, io):
     for k, p in m.named_parameters():
         if k.startswith("align_channel"):
             continue
-        assert_close("grad:" + k, p.grad, g["grad:" + k], 4e-2, zero_scale=scale)
+        assert_close("grad:" + k, p.grad, g["grad:" + k], grad_tol(k, "embedded"), zero_scale=scale)
 
 
 def test_oracle_embedded_cfg2_tokens():
@@ -186,7 +186,7 @@ def test_oracle_embedded_cfg2_tokens():
     scale = grad_scale(go.values())
     for k, pp in m.named_parameters():
         if not k.startswith("align_channel"):
-            assert_close("grad:" + k, pp.grad, go[k], 4e-2, zero_scale=scale)
+            assert_close("grad:" + k, pp.grad, go[k], grad_tol(k, "embedded"), zero_scale=scale)
 
 
 FP32_TOL = 1e-4      # north_star: within 1e-4 relative error in fp32
@@ -253,7 +253,7 @@ def test_oracle_dot_channel_widths(C, B, T, H, W):
     scale = grad_scale(go.values())
     for k, pp in m.named_parameters():
         if not k.startswith("align_channel"):
-            assert_close("grad:" + k, pp.grad, go[k], 3e-2, zero_scale=scale)
+            assert_close("grad:" + k, pp.grad, go[k], grad_tol(k), zero_scale=scale)
 
 
 @pytest.mark.parametrize("C,B,T,H,W", [(128, 3, 3, 5, 7), (256, 2, 1, 9, 15), (256, 1, 2, 13, 20), (64, 2, 2, 6, 6)])
@@ -272,4 +272,95 @@ def test_oracle_embedded_ragged(C, B, T, H, W):
     scale = grad_scale(go.values())
     for k, pp in m.named_parameters():
         if not k.startswith("align_channel"):
-            assert_close("grad:" + k, pp.grad, go[k], 4e-2, zero_scale=scale)
+            assert_close("grad:" + k, pp.grad, go[k], grad_tol(k, "embedded"), zero_scale=scale)
+
+
+# ------------------------------------------------------------------------------------------------ dp.GradBucket.bind
+def _bucket_case(seed=71):
+    from glfusion_b200 import dp
+    B, C, T, H, W = 2, 128, 2, 8, 8
+    p = O.init_params(C, seed=seed, randomize_affine=True)
+    gen = torch.Generator().manual_seed(seed + 1)
+    xs = [torch.randn(B, C, T, H, W, generator=gen).to(DEV, torch.bfloat16) for _ in range(2)]
+    dzs = [torch.randn(B, C, T, H, W, generator=gen).to(DEV, torch.bfloat16) for _ in range(2)]
+    m = load_module_from_params(TPAVIModule, p, C, "dot", True).train()
+    return dp, m, xs, dzs
+
+
+def _grads(m):
+    return {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+
+
+def test_bucket_bind_module_used_twice_in_one_backward():
+    """The reference's training step runs the network twice before ONE backward (R/main.py:209 and :221, the cycle pass):
+    with the zero-copy bucket bound, the second backward node must not overwrite the first one's gradients."""
+    dp, m, xs, dzs = _bucket_case()
+
+    def step():
+        for p in m.parameters():
+            p.grad = None
+        z0, _ = m(xs[0])
+        z1, _ = m(xs[1])
+        torch.autograd.backward([z0, z1], dzs)
+        torch.cuda.synchronize()
+        return _grads(m)
+    ref = step()                                     # unbound: autograd sums two fresh gradient tensors
+    bucket = dp.GradBucket(m._plist())
+    bucket.bind([m])
+    got = step()
+    for k in ref:
+        assert_close("twice:" + k, got[k], ref[k], 1e-5, abs_floor=1e-6)
+    bucket.allreduce_mean()                          # world size 1: pack / unpack must leave the values alone
+    torch.cuda.synchronize()
+    for k in ref:
+        assert_close("twice+allreduce:" + k, dict(m.named_parameters())[k].grad, ref[k], 1e-5, abs_floor=1e-6)
+
+
+def test_bucket_bind_gradient_accumulation():
+    """Two forward/backward pairs without zeroing in between (gradient accumulation, zero_grad(set_to_none=False)):
+    once .grad aliases the bucket view the kernels must not write into it again."""
+    dp, m, xs, dzs = _bucket_case(seed=81)
+
+    def two_steps():
+        for p in m.parameters():
+            p.grad = None
+        for x, dz in zip(xs, dzs):
+            z, _ = m(x)
+            z.backward(dz)
+        torch.cuda.synchronize()
+        return _grads(m)
+    ref = two_steps()
+    bucket = dp.GradBucket(m._plist())
+    bucket.bind([m])
+    got = two_steps()
+    for k in ref:
+        assert_close("accum:" + k, got[k], ref[k], 1e-5, abs_floor=1e-6)
+    # and the single-use step still takes the zero-copy path
+    for p in m.parameters():
+        p.grad = None
+    z, _ = m(xs[0])
+    z.backward(dzs[0])
+    assert bucket.aliased()
+
+
+def test_frozen_batchnorm_follows_the_holder_layer():
+    """model.train() with the BatchNorm layer alone in eval mode (the usual 'freeze BN' pattern): the kernels must take
+    train / eval, eps and momentum from the nn layers themselves."""
+    B, C, T, H, W = 2, 128, 2, 8, 8
+    p = O.init_params(C, seed=91, randomize_affine=True)
+    p["W_z.1.running_mean"] = torch.randn(C) * 0.1
+    p["W_z.1.running_var"] = torch.rand(C) + 0.5
+    gen = torch.Generator().manual_seed(92)
+    x = torch.randn(B, C, T, H, W, generator=gen)
+    dz = torch.randn(B, C, T, H, W, generator=gen)
+    zo, dxo, _ = O.tpavi_fwd_bwd(x, dz, {k: v.clone() for k, v in p.items()}, mode="dot", training=False)
+    m = load_module_from_params(TPAVIModule, p, C, "dot", True).train()
+    m.W_z[1].eval()
+    before = m.W_z[1].running_mean.clone()
+    z, dx = _run(m, x.to(DEV, torch.bfloat16), dz.to(DEV, torch.bfloat16))
+    assert_close("z", z, zo, BF16_TOL)
+    assert_close("dx", dx, dxo, BF16_TOL)
+    assert torch.equal(m.W_z[1].running_mean, before)          # eval-mode BatchNorm does not touch its statistics
+    m.W_z[1].momentum = None
+    with pytest.raises(NotImplementedError):
+        m(x.to(DEV, torch.bfloat16))
