@@ -617,8 +617,7 @@ int tpavi_bwd_gram(const glf_desc* d, const Dims& m, const bf16* X, const glf_we
     g.M = N; g.N = C; g.K = C; g.batch = B;
     if (C % 256 == 0) g.bn_hint = gram_big_tile();
     g.bias = wb.evec; g.bias_stride = C;
-    const char* ei = getenv("GLF_EXP_EI");
-    if (!(chain && ei && ei[0] == '1')) { g.addend = wb.dV; g.ld_add = C; g.stride_add = static_cast<long long>(N) * C; }
+    if (!(chain && gram_residual_in_E())) { g.addend = wb.dV; g.ld_add = C; g.stride_add = static_cast<long long>(N) * C; }
     g.D = m.pack_x ? static_cast<void*>(wb.dxtok) : dx; g.ldd = C; g.strideD = static_cast<long long>(N) * C;
     GLF_TRY(gemm_pair2(g, wb.dV, X, wb.EF, wb.EF + CC, stream));
   }

@@ -108,6 +108,17 @@ __device__ __forceinline__ float row_dot256(const uint8_t* mat, int R, int row, 
   }
   return a0 + a1;
 }
+// acc[0..7] += w * (the 8 bf16 of one 16-byte chunk)
+__device__ __forceinline__ void fma_chunk8(const uint8_t* chunk, float w, float (&acc)[8]) {
+  const uint4 q = *reinterpret_cast<const uint4*>(chunk);
+  const uint32_t* q32 = reinterpret_cast<const uint32_t*>(&q);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 x = unpack_bf16(q32[t]);
+    acc[2 * t] = fmaf(x.x, w, acc[2 * t]);
+    acc[2 * t + 1] = fmaf(x.y, w, acc[2 * t + 1]);
+  }
+}
 // element (row, col) of a tile matrix
 __device__ __forceinline__ float tile_elem(const uint8_t* mat, int R, int row, int col) {
   return __bfloat162float(
@@ -419,7 +430,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
                      const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWz,
                      const __grid_constant__ CUtensorMap tmdQ, const __grid_constant__ CUtensorMap tmdWp,
                      const __grid_constant__ CUtensorMap tmdM, const __grid_constant__ CUtensorMap tmdT,
-                     const __grid_constant__ CUtensorMap tmEF, const ChainBwdParams p) {
+                     const __grid_constant__ CUtensorMap tmEF, const __grid_constant__ CUtensorMap tmR,
+                     const ChainBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -432,11 +444,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
   float* v_bth = v_e + 256;       // [128]
   float* v_bphi = v_bth + 128;
   float* v_bg = v_bphi + 128;
-  float* v_dt = v_bg + 128;       // [2][128] partial, then [128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sgen + VEC_OFF + 8192);
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(sgen + VEC_OFF + 8192 + 256);
+  float* v_dt = v_bg + 128;       // [2][128] partial, then [128]   (the vectors end at byte 8704)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sgen + VEC_OFF + 10240);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(sgen + VEC_OFF + 10240 + 256);
+  static_assert(10240 + 256 + 16 <= VEC_BYTES, "vector area");
   enum { LDA = 0, LDB, LDC, LDD, LDE, LDF, LDG, LDH, MMAA, MMAB, MMAC, MMAD, MMAE, MMAF, MMAG0, MMAG1,
-         DRA, DRB, DRC, DRD, DRE, DRK0, DRK1, DRF, NBAR };
+         LDR, DRA, DRB, DRC, DRD, DRE, DRK0, DRK1, DRF, DRQ, NBAR };
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -448,6 +461,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     tma_prefetch_desc(&tmWz);
     for (int i = 0; i < NBAR; ++i) mbar_init(bar(i), (i >= DRA) ? CH_DRAIN_WARPS : 1);
     fence_mbar_init();
+    tma_prefetch_desc(&tmR);
   }
   if (warp == CH_DRAIN_WARPS) tmem_alloc(smem_u32(tmem_holder), 512);
   tc_fence_before();
@@ -480,6 +494,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
                    IDESC_KK_128, k > 0);
       umma_commit(bar(MMAB));
       mbar_wait(bar(MMAB), 0); CH_TRACE(4);
+      mbar_wait(bar(DRQ), 0);                                   // the drain warps have finished reading Q (Q s, E)
+      mbar_expect_tx(bar(LDR), 8 * BOX_BYTES);
+      load_256x256(&tmR, bar(LDR), sbase + Z0, b);             // k1 R -> Z0, Z1: dQ is formed in place on top of it
       mbar_expect_tx(bar(LDC), 4 * BOX_BYTES);
       load_128x256(&tmW, bar(LDC), sbase + Z2, 0, 0);          // Wtheta -> Z2
       mbar_wait(bar(DRA), 0); CH_TRACE(5);                                   // dQ (bf16) in Z0, Z1
@@ -589,7 +606,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       p.dcv[bC + tid] = v_dc[tid];
       // E = k1 Q -> EF[b][0]   (a warp moves one 512-byte row per iteration)
       bf16* E = p.EF + static_cast<long long>(b) * 2 * CC * CC;
-#pragma unroll 4
+#pragma unroll 2
       for (int it = 0; it < 32; ++it) {
         const int row = it * 8 + warp;
         const float a1 = v_k1[row];
@@ -606,32 +623,30 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         *reinterpret_cast<uint4*>(E + static_cast<long long>(row) * CC + lane * 8) = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
-    named_bar_sync(1, CH_DRAIN_THREADS);      // every reader of Q (Z0, Z1) is done before dQ overwrites it
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar(DRQ));     // every reader of Q (Z0, Z1) is done before k1 R is loaded on top of it
+    named_bar_sync(1, CH_DRAIN_THREADS);      // v_dc is read by other threads below
     const int r = hf * 128 + q * 32 + lane;   // row of the 256-row matrices owned by this thread
     // ---- dQ = k1 R + k2 QS + v s^T  -> Z0, Z1 ([256][64] x 4), stored by the control thread
     {
-      // this thread's row of k1 R comes from global memory through a 4-deep register ring; the first three chunks are
-      // requested before the wait for the accumulator
-      const bf16* Rrow = p.Rb + (static_cast<long long>(b) * CA + r) * CA;
-      uint4 rk[4][4];
-#pragma unroll
-      for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rk[c][j] = *reinterpret_cast<const uint4*>(Rrow + c * 32 + 8 * j);
+      // k1 R was brought into Z0 / Z1 by TMA in the layout dQ takes: every thread reads its own 64 bytes of a chunk
+      // and writes the result back to the same place
       mbar_wait(bar(MMAB), 0);
+      mbar_wait(bar(LDR), 0);
       tc_fence_after();
       const float a2 = v_k2[r], vr = v_v[r];
       bf16* Drow = p.dQa + (bC + r) * CA;
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < 8; ++c) {
         const int col0 = c * 32;
-        if (c + 3 < 8) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rk[(c + 3) & 3][j] = *reinterpret_cast<const uint4*>(Rrow + col0 + 96 + 8 * j);
-        }
         float f[32];
         ld_acc32(tlane + hf * 256 + col0, f);
-        const uint32_t* r32 = reinterpret_cast<const uint32_t*>(rk[c & 3]);
+        uint8_t* tile = sgen + Z0;
+        const int t = col0 >> 6, ch0 = (col0 & 63) >> 3;
+        uint4 rk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rk[j] = *reinterpret_cast<const uint4*>(tile + tile_chunk(256, t, r, ch0 + j));
+        const uint32_t* r32 = reinterpret_cast<const uint32_t*>(rk);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float2 x = unpack_bf16(r32[j]);
@@ -732,15 +747,30 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     // ---- e  = Wphi^T dt + dT^T bphi     (thread = column m; Wphi in Z2, dT in Z0, both [128][64] x 4)
     mbar_wait(bar(LDF), 0);
     {
-      float acc = 0.f;
-#pragma unroll 4
-      for (int i = 0; i < CI; ++i)
-        acc = fmaf(tile_elem(sgen + Z2, 128, i, tid), v_dt[i], fmaf(tile_elem(sgen + Z0, 128, i, tid), v_bphi[i], acc));
-      v_e[tid] = acc;
+      // a warp owns four 8-column chunks; lane = (chunk sub = lane / 8, row residue rl = lane % 8): 16 rows x 8 columns
+      // of both matrices per lane, then a shuffle reduction over the eight row residues
+      const int cc = warp * 4 + (lane >> 3), rl = lane & 7;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+      for (int i = rl; i < CI; i += 8) {
+        const uint32_t off = tile_chunk(128, cc >> 3, i, cc & 7);
+        fma_chunk8(sgen + Z2 + off, v_dt[i], acc);
+        fma_chunk8(sgen + Z0 + off, v_bphi[i], acc);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 2);
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
+      }
+      if (rl == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v_e[cc * 8 + j] = acc[j];
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(bar(DRE));
-    named_bar_sync(1, CH_DRAIN_THREADS);      // v_e is complete before other threads add to it
+    named_bar_sync(1, CH_DRAIN_THREADS);      // v_e is complete before its owners change below
     if (p.has_k2) {
       // ---- k2 Q[:, 128 g .. 128 g + 127] -> Z2 ([256][64] x 2);  e += Q^T (k2 c + k3)
       mbar_wait(bar(MMAF), 0);                // Wphi (Z2) has been consumed
@@ -748,7 +778,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         mbar_wait(bar(g == 0 ? LDG : LDH), 0);
         if (g == 1) mbar_wait(bar(MMAG0), 0); // the previous half of k2 Q has been consumed
         const uint8_t* src = sgen + (g == 0 ? Z1 : Z0);
-#pragma unroll 4
+        // (small unroll factors throughout: every phase of this kernel runs once, so its code is fetched cold and a
+        // long unrolled body costs more in instruction-cache misses than it saves in issue slots)
+#pragma unroll 2
         for (int it = 0; it < 16; ++it) {
           const int idx = it * CH_DRAIN_THREADS + tid;      // 2 tiles x 256 rows x 8 chunks
           const int row = (idx >> 3) & 255;
@@ -765,12 +797,22 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
           *reinterpret_cast<uint4*>(sgen + Z2 + off) = make_uint4(o[0], o[1], o[2], o[3]);
         }
         {
-          // column m = 128 g + (tid & 127) of Q, rows split between the two thread halves
-          const int m = tid & 127, r0 = (tid >> 7) * 128;
-          float acc = 0.f;
-#pragma unroll 4
-          for (int i = 0; i < 128; ++i) acc = fmaf(tile_elem(src, 256, r0 + i, m), v_v[r0 + i], acc);
-          atomicAdd(&v_e[g * 128 + m], acc);
+          // a warp owns two 8-column chunks of this half of Q; lane = (chunk sub = lane / 16, row residue rl = lane % 16)
+          const int cc = warp * 2 + (lane >> 4), rl = lane & 15;
+          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+          for (int i = rl; i < CC; i += 16) fma_chunk8(src + tile_chunk(256, cc >> 3, i, cc & 7), v_v[i], acc);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
+            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 2);
+            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
+            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+          }
+          if (rl == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v_e[g * 128 + cc * 8 + j] += acc[j];
+          }
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -803,6 +845,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
 }
 
 }  // namespace
+
+// dX = dV E + X F + 1 e^T + dV: the residual term dV is folded into the first operand, E' = E + I (one more bf16 rounding
+// of the 256 diagonal entries: <= 2^-9 |dV_j| on dX_j, an order below the bf16 rounding of dX itself), so the dX GEMM
+// needs no addend pass over dV in its epilogue and its tiles leave through bulk tensor stores.  GLF_GRAM_RESIDUAL_IN_E=0
+// restores the separate addend.
+bool gram_residual_in_E() {
+  const char* e = getenv("GLF_GRAM_RESIDUAL_IN_E");
+  return !(e && e[0] == '0');
+}
 
 bool gram_chain_supported(int C, int Ci) {
   if (const char* e = getenv("GLF_GRAM_CHAIN")) {   // tuning aid: GLF_GRAM_CHAIN=0 keeps the batched tile GEMMs
@@ -841,7 +892,8 @@ int gram_chain_bwd(const bf16* Sa, const bf16* Qb, const bf16* waug, const bf16*
   GLF_TRY_RC(make_tmap_bf16(&tmQ, Qb, CC, CC, B, CA, static_cast<long long>(CC) * CA, 128));
   GLF_TRY_RC(make_tmap_bf16(&tmW, waug, CC, 3 * CI, 1, CA, 0, 128));
   GLF_TRY_RC(make_tmap_bf16(&tmWz, wz, CI, CC, 1, CI, 0, 128));
-  CUtensorMap tmdQ, tmdWp, tmdM, tmdT, tmEF;
+  CUtensorMap tmdQ, tmdWp, tmdM, tmdT, tmEF, tmR;
+  GLF_TRY_RC(make_tmap_bf16(&tmR, Rb, CC, CC, B, CA, static_cast<long long>(CA) * CA, 128));
   GLF_TRY_RC(make_tmap_bf16(&tmdQ, dQa, CC, CC, B, CA, static_cast<long long>(CC) * CA, 128));
   GLF_TRY_RC(make_tmap_bf16(&tmdWp, dWp, CI, CC, B, CI, static_cast<long long>(CC) * CI, 128));
   GLF_TRY_RC(make_tmap_bf16(&tmdM, dMn, CI, CI, B, CI, static_cast<long long>(CI) * CI, 128));
@@ -851,8 +903,7 @@ int gram_chain_bwd(const bf16* Sa, const bf16* Qb, const bf16* waug, const bf16*
   p.N = N; p.has_k2 = has_k2;
   const char* tr = getenv("GLF_CHAIN_TRACE");
   p.trace = (tr && tr[0] == '1') ? 1 : 0;
-  const char* ei = getenv("GLF_EXP_EI");
-  p.e_plus_i = (ei && ei[0] == '1') ? 1 : 0;
+  p.e_plus_i = gram_residual_in_E() ? 1 : 0;
   p.sfv = sfv; p.cvec = cvec; p.rv = rv; p.k1 = k1; p.k2 = k2; p.k3 = k3;
   p.bth = bth; p.bphi = bphi; p.bg = bg;
   p.Rb = Rb;
@@ -860,7 +911,7 @@ int gram_chain_bwd(const bf16* Sa, const bf16* Qb, const bf16* waug, const bf16*
   p.dcv = dcv; p.dtv = dtv;
   cudaError_t e = cudaFuncSetAttribute(chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM);
   if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(chain_bwd)");
-  chain_bwd_kernel<<<B, CH_THREADS, CH_SMEM, stream>>>(tmS, tmQ, tmW, tmWz, tmdQ, tmdWp, tmdM, tmdT, tmEF, p);
+  chain_bwd_kernel<<<B, CH_THREADS, CH_SMEM, stream>>>(tmS, tmQ, tmW, tmWz, tmdQ, tmdWp, tmdM, tmdT, tmEF, tmR, p);
   if (p.trace) {
     static const char* names[] = {"start", "LDA", "MMAA", "LDB", "MMAB", "DRA", "LDC", "MMAC", "DRB", "LDD", "MMAD", "DRC", "LDE", "MMAE", "DRD", "LDF", "MMAF", "DRE", "LDH", "DRK0", "DRK1", "DRF", "end"};
     long long t[64];

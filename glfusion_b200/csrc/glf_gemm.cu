@@ -63,7 +63,9 @@ struct GemmKParams {
 template <int BN, int MT = 1>
 struct GemmCfg {
   // persistent kernel, one CTA per SM: ring + separate epilogue staging must fit in 227 KB
-  static constexpr int STAGES = (MT == 2) ? 3 : ((BN == 256) ? 3 : ((BN == 128) ? 5 : 6));
+  // MT = 2: every spare byte goes to the ring (the big K-major products are bound by bytes in flight per SM: with
+  // three 48 KB stages the ring turns over once per HBM round trip, ~76 GB/s per SM; profiles/r02_gemm_bound_probe.txt)
+  static constexpr int STAGES = (MT == 2) ? ((BN == 256) ? 3 : 4) : ((BN == 256) ? 3 : ((BN == 128) ? 5 : 6));
   static constexpr uint32_t A_TILE = BM * BK * 2;
   static constexpr uint32_t A_BYTES = MT * A_TILE;
   static constexpr uint32_t B_BYTES = BN * BK * 2;
@@ -73,7 +75,7 @@ struct GemmCfg {
   static constexpr uint32_t WARP_BIAS = 32 * 4;     // warp-private bias slice of the current 32-column chunk
   // 256 x 256 CTA tiles (MT = 2, BN = 256): every byte of shared memory goes to the ring; no CTA-wide bias copy, no
   // ones tile, a single accumulator stage (all 512 TMEM columns)
-  static constexpr bool WIDE2 = (MT == 2 && BN == 256);
+  static constexpr bool WIDE2 = (MT == 2);          // (both MT = 2 shapes run without the CTA-wide bias copy / ones tile)
   static constexpr uint32_t BIAS_ALL = WIDE2 ? 0 : 4096 * 4;   // the whole bias vector (N <= 4096) is staged once per CTA
   static constexpr uint32_t EPI_BYTES = EPI_WARPS * (WARP_STG + WARP_BIAS) + BIAS_ALL;
   // all-ones K-major B tile [16 rows][64 k] for the row-sum side product (RING_BYTES and EPI_BYTES are multiples of

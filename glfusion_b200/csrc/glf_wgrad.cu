@@ -250,8 +250,17 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int c0, int 
   const int prod = idx / per, e = idx - prod * per;
   const int a = prod == 0 ? c0 : (prod == 1 ? c1 : (prod == 2 ? c2 : c3));
   const int z = prod == 0 ? c1 : (prod == 1 ? c2 : (prod == 2 ? c3 : c4));
-  float acc = 0.f;
-  for (int c = a; c < z; ++c) acc += part[static_cast<long long>(c) * WG_PART + e];
+  // four independent chains, combined in a fixed order (the partials are read with memory-level parallelism)
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int c = a;
+  for (; c + 4 <= z; c += 4) {
+    a0 += part[static_cast<long long>(c) * WG_PART + e];
+    a1 += part[static_cast<long long>(c + 1) * WG_PART + e];
+    a2 += part[static_cast<long long>(c + 2) * WG_PART + e];
+    a3 += part[static_cast<long long>(c + 3) * WG_PART + e];
+  }
+  for (; c < z; ++c) a0 += part[static_cast<long long>(c) * WG_PART + e];
+  const float acc = (a0 + a1) + (a2 + a3);
   float* W = prod == 0 ? tw : (prod == 1 ? zw : (prod == 2 ? gw : pw));
   float* bb = prod == 0 ? tb : (prod == 1 ? nullptr : (prod == 2 ? gb : pb));
   if (e < 128 * 256) W[e] = acc;               // both layouts are the row-major layout of the gradient tensor
