@@ -257,6 +257,10 @@ def run_ours(args):
     bucket.bind([fusion.global_attn, fusion.local_attn])   # gradients are written into the all-reduce bucket directly
     # the fusion-weight gradient average as one kernel over NVLink peer memory (NCCL stays the fallback)
     p2p = bool(world > 1 and args.p2p_allreduce and bucket.enable_p2p())
+    # (the side-stream launch must be joined inside the same capture: only when the exchange is captured with the step)
+    overlap = bool(p2p and args.overlap_allreduce and (not args.graph or args.graph_allreduce != 0))
+    if overlap:
+        bucket.overlap_with(fusion)      # the exchange starts before the gate backward, on a side stream
 
     params = [p for p in fusion.parameters() if p.requires_grad]
 
@@ -403,7 +407,9 @@ def run_ours(args):
                    "clips_per_gpu_per_step": clips, "mode": "dot", "dot_algorithm": dot_algorithm(C),
                    "cuda_graph": bool(args.graph), "allreduce_in_graph": allreduce_in_graph,
                    "allreduce": ("none (1 GPU)" if world == 1 else
-                                 ("glf_p2p_allreduce kernel over NVLink peer memory" if p2p else "NCCL all_reduce(AVG)")),
+                                 ("glf_p2p_allreduce kernel over NVLink peer memory" +
+                                  (", launched from the backward pass beside the gate backward" if overlap else "")
+                                  if p2p else "NCCL all_reduce(AVG)")),
                    "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no flush" % (rows * C * 2 / 1e6),
                    "e2e_pipeline": "pinned host inputs; H2D of step i+1 on a copy stream overlaps compute of step i",
                    "parallelism": f"dp{world}",
@@ -772,6 +778,8 @@ def main():
                     help="untimed load before the timed region (steady-state clocks); 0 = time the cold burst only")
     ap.add_argument("--p2p-allreduce", type=int, default=1, help="gradient all-reduce as one NVLink peer-memory kernel")
     ap.add_argument("--graph-allreduce", type=int, default=-1, help="capture the NCCL gradient all-reduce in the step graph")
+    ap.add_argument("--overlap-allreduce", type=int, default=1,
+                    help="start the peer-memory all-reduce as soon as the weight gradients are final (beside the gate backward)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

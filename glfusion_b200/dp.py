@@ -186,17 +186,48 @@ class GradBucket:
     def p2p_enabled(self) -> bool:
         return self._p2p is not None
 
+    def overlap_with(self, fusion) -> None:
+        """Overlap the gradient exchange with the tail of the backward pass: `fusion` (a GlobalLocalFusion whose two
+        blocks are bound to this bucket) calls back as soon as both blocks' parameter gradients are final, i.e. before
+        its gate backward; the peer-memory all-reduce is launched there on a side stream and joined by
+        `allreduce_mean()`, which then has nothing left to do.  Needs the zero-copy peer path (bind + enable_p2p); in
+        every other configuration the callback does nothing and `allreduce_mean()` runs the exchange as before."""
+        self._ar_stream = None
+        self._ar_done = False
+
+        def ready():
+            if self._p2p is None:
+                return
+            cur = torch.cuda.current_stream(self._raw.device)
+            if self._ar_stream is None:
+                self._ar_stream = torch.cuda.Stream(device=self._raw.device)
+            self._ar_stream.wait_stream(cur)
+            with torch.cuda.stream(self._ar_stream):
+                self._launch_p2p()
+            self._ar_done = True
+        fusion.on_weight_grads_ready = ready
+
+    def _launch_p2p(self) -> None:
+        import ctypes as C
+        from . import _lib as L
+        bufs, sigs, rank, world = self._p2p
+        with torch.cuda.device(self._raw.device):
+            L.check(L.load().glf_p2p_allreduce(bufs, sigs, rank, world, self._n_pad, 1.0 / world,
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
     def allreduce_mean(self, group=None) -> None:
+        if getattr(self, "_ar_done", False):
+            # the exchange was launched from the backward pass (overlap_with): join it
+            self._ar_done = False
+            torch.cuda.current_stream(self._raw.device).wait_stream(self._ar_stream)
+            if self.aliased():
+                return
+            # (some gradient did not land in the bucket after all: fall through to the packed exchange)
         zero_copy = self.aliased()
         if not zero_copy:
             self.pack()
         if self._p2p is not None:
-            import ctypes as C
-            from . import _lib as L
-            bufs, sigs, rank, world = self._p2p
-            with torch.cuda.device(self._raw.device):
-                L.check(L.load().glf_p2p_allreduce(bufs, sigs, rank, world, self._n_pad, 1.0 / world,
-                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            self._launch_p2p()
         elif dist.is_initialized() and dist.get_world_size(group) > 1:
             if dist.get_backend(group) == "nccl":
                 dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)     # one kernel: sum and 1/world

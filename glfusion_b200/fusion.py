@@ -190,6 +190,9 @@ class _FusionFunction(torch.autograd.Function):
         else:
             dxl, gl = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xl, stl, svl, tl, ml._buffer_table(), ws=wsl,
                                          grad_out=gout_l)
+        hook = ctx.fusion.on_weight_grads_ready
+        if hook is not None and gout_g is not None and gout_l is not None:
+            hook()      # the gradients sit in the bucket views: the all-reduce may start now, beside the gate backward
         df4, dcls, dctr = gate_concat_backward(f4, cls, ctr, gate, dxg, dxl, ctx.fusion.center_aware_weight)
         out = [None, None, None] + list(df4) + list(dcls) + list(dctr)
         for mod, plist, gr in ((mg, pg, gg), (ml, pl, gl)):
@@ -235,6 +238,10 @@ class GlobalLocalFusion(nn.Module):
         super().__init__()
         self.center_aware_weight = center_aware_weight
         self.overlap_blocks = True      # run MGFM / MLFM on two streams between the fused stages
+        # data-parallel hook: called from the fused backward as soon as BOTH blocks' parameter gradients are final
+        # (before the gate backward), so that a gradient all-reduce can run beside the rest of the backward pass
+        # (dp.GradBucket.overlap_with).  None = no hook.
+        self.on_weight_grads_ready = None
         self.global_attn = TPAVIModule(in_channels=in_channels, inter_channels=inter_channels, mode=mode)
         self.local_attn = TPAVIModule(in_channels=in_channels, inter_channels=inter_channels, mode=mode)
 

@@ -236,3 +236,40 @@ def test_bench_configuration_graph_replay():
             for k, p in mod.named_parameters():
                 if not k.startswith("align_channel"):
                     assert_close("grad:" + k, p.grad, ref[k], grad_tol(k), abs_floor=1e-3)
+
+
+def test_reference_checkpoint_inference(tmp_path):
+    """a checkpoint in the reference trainer's wire format (R/main.py:857-872 writes
+    {'network': model.module.state_dict()}; Trainer.test re-prefixes the keys with 'module.', main.py:454-457) is
+    loaded from disk into the B200 path and run in inference mode (eval BatchNorm = running statistics, applied as a
+    per-channel affine inside the fused LayerNorm pass: no statistics kernel, nothing to un-fold), against the oracle."""
+    B, C, V, h, w = 3, 256, 4, 28, 28
+    pg = O.init_params(C, seed=71, randomize_affine=True)
+    pl = O.init_params(C, seed=72, randomize_affine=True)
+    for p in (pg, pl):                       # a trained network has non-trivial running statistics
+        p["W_z.1.running_mean"] = torch.randn(C) * 0.2
+        p["W_z.1.running_var"] = torch.rand(C) + 0.5
+        p["W_z.1.num_batches_tracked"] = torch.tensor(1234)
+    net = {"module.global_attn." + k: v for k, v in pg.items()}
+    net.update({"module.local_attn." + k: v for k, v in pl.items()})
+    net["module.layer1.1.0.conv1.weight"] = torch.randn(8, 8, 1, 1)       # the rest of the network is ignored
+    net["module.classifier.1.4.bias"] = torch.randn(5)
+    path = tmp_path / "net_00099.pth"
+    torch.save({"network": net}, path)
+
+    f = GlobalLocalFusion(in_channels=C)
+    f.load_reference_checkpoint(torch.load(path, map_location="cpu"), strict=True)
+    f = f.to(DEV).eval()
+    gen = torch.Generator().manual_seed(73)
+    f4 = [torch.randn(B, C, h, w, generator=gen) for _ in range(V)]
+    cl = [torch.randn(B, 5, h, w, generator=gen) for _ in range(V)]
+    ct = [torch.randn(B, 1, h, w, generator=gen) for _ in range(V)]
+    ref = O.global_local_fusion(f4, cl, ct, pg, pl, training=False)
+    before = f.global_attn.W_z[1].running_mean.clone()
+    with torch.no_grad():
+        out = f.forward_stacked([t.to(DEV, torch.bfloat16) for t in f4], [t.to(DEV) for t in cl], [t.to(DEV) for t in ct])
+    torch.cuda.synchronize()
+    for v in range(V):
+        assert_close(f"out:{v}", out[:, :, v], ref[v], BF16_TOL)
+    assert torch.equal(f.global_attn.W_z[1].running_mean, before)
+    assert int(f.global_attn.W_z[1].num_batches_tracked) == 1234
