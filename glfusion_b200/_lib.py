@@ -18,7 +18,8 @@ PRECISIONS = {"bf16": PRECISION_BF16, "fp32": PRECISION_F32X3}
 EXPORTS = ("glf_version", "glf_last_error", "glf_tpavi_sizes", "glf_tpavi_fwd", "glf_tpavi_bwd",
            "glf_gate_concat_fwd", "glf_gate_concat_bwd", "glf_gemm_bf16", "glf_transpose", "glf_bn_res_ln_fwd",
            "glf_bn_res_ln_bwd", "glf_bn_res_ln_bwd_max_blocks", "glf_gate_concat_bwd_scratch_bytes",
-           "glf_fusion_ln_supported", "glf_fusion_ln_fwd", "glf_fusion_ln_bwd", "glf_bn_res_ln_pair_fwd",
+           "glf_fusion_ln_supported", "glf_fusion_ln_fwd", "glf_fusion_ln_fwd_parts", "glf_fusion_ln_bwd",
+           "glf_bn_res_ln_pair_fwd",
            "glf_bn_res_ln_pair_bwd", "glf_gemm_bf16_ex", "glf_gram_contraction", "glf_p2p_signal_bytes", "glf_p2p_max_floats",
            "glf_p2p_export", "glf_p2p_open", "glf_p2p_close", "glf_p2p_allreduce")
 
@@ -72,6 +73,8 @@ def load() -> C.CDLL:
         lib.glf_fusion_ln_supported.argtypes = [C.POINTER(GlfDesc)]
         lib.glf_fusion_ln_fwd.argtypes = [C.POINTER(GlfDesc), vp, vp, C.POINTER(GlfWeights), C.POINTER(GlfWeights), vp,
                                           vp, vp, vp]
+        lib.glf_fusion_ln_fwd_parts.argtypes = [C.POINTER(GlfDesc), vp, vp, C.POINTER(GlfWeights), C.POINTER(GlfWeights),
+                                                vp, vp, vp, vp, vp]
         lib.glf_fusion_ln_bwd.argtypes = [C.POINTER(GlfDesc), vp, vp, vp, C.POINTER(GlfWeights), C.POINTER(GlfWeights),
                                           vp, vp, vp, vp, vp]
         pp = C.POINTER(C.c_void_p)

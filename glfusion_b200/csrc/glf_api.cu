@@ -965,7 +965,17 @@ GLF_API int glf_fusion_ln_supported(const glf_desc* d) {
 
 GLF_API int glf_fusion_ln_fwd(const glf_desc* d, const void* xg, const void* xl, const glf_weights* wg,
                               const glf_weights* wl, void* z, void* saved_g, void* saved_l, glf_stream_t stream_) {
+  return glf_fusion_ln_fwd_parts(d, xg, xl, wg, wl, z, nullptr, saved_g, saved_l, stream_);
+}
+
+GLF_API int glf_fusion_ln_fwd_parts(const glf_desc* d, const void* xg, const void* xl, const glf_weights* wg,
+                                    const glf_weights* wl, void* z, void* z_global, void* saved_g, void* saved_l,
+                                    glf_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (z_global != nullptr) {
+    GLF_TRY(check_ptr(z_global, "z_global"));
+    if (d != nullptr && d->accumulate) return set_error(GLF_ERR_INVALID, "glf_fusion_ln_fwd_parts: accumulate is not supported");
+  }
   Dims m;
   GLF_TRY(make_dims(d, &m));
   GLF_TRY(check_device_sm100());
@@ -988,7 +998,7 @@ GLF_API int glf_fusion_ln_fwd(const glf_desc* d, const void* xg, const void* xl,
   float* mu[2] = {sg.ln_mu, sl.ln_mu};
   float* r[2] = {sg.ln_r, sl.ln_r};
   return ln_fwd_tma(2, U, X, a, b, lw, lb, mu, r, reinterpret_cast<bf16*>(z), m.rows, m.C, d->eps_ln, d->accumulate,
-                    stream);
+                    stream, reinterpret_cast<bf16*>(z_global));
 }
 
 GLF_API int glf_fusion_ln_bwd(const glf_desc* d, const void* dz, const void* xg, const void* xl, const glf_weights* wg,

@@ -73,7 +73,7 @@ bool ln_tma_supported(int C);
 int ln_bwd_tma_blocks(long long rows);
 int ln_fwd_tma(int nmod, const bf16* const* U, const bf16* const* X, const float* const* a, const float* const* b,
                const float* const* lw, const float* const* lb, float* const* mu, float* const* r, bf16* Z,
-               long long rows, int C, float eps, int accumulate, cudaStream_t stream);
+               long long rows, int C, float eps, int accumulate, cudaStream_t stream, bf16* Z0 = nullptr);
 int ln_bwd_tma(int nmod, const bf16* dZ, const bf16* const* U, const bf16* const* X, const float* const* a,
                const float* const* b, const float* const* lw, const float* const* bn_mean,
                const float* const* bn_rstd, const float* const* mu, const float* const* r, bf16* const* dV,

@@ -65,13 +65,16 @@ struct LnFwdParams {
   float* mu[2];
   float* r[2];
   bf16* Z;
+  bf16* Z0;        // PARTS only: the first module's own output (MGFM's f4_global_fusion, ours.py:1823), bf16 [rows, C]
   long long rows;
   int C, ntiles, stages, accumulate;
   uint32_t arr_bytes, stage_bytes;
   float eps;
 };
 
-template <int NMOD, bool FULLC>   // FULLC: C == 256, every lane owns 8 live channels
+// FULLC: C == 256, every lane owns 8 live channels.  PARTS: also store module 0's LayerNorm output on its own (the
+// cycle-consistency pass of the trainer, R/main.py:211-235, consumes f4_global_fusion beside the fused sum).
+template <int NMOD, bool FULLC, bool PARTS = false>
 __global__ void __launch_bounds__(F_THREADS, 1) ln_fwd_tma_kernel(const LnFwdParams p) {
   extern __shared__ uint8_t lsm_raw[];
   __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
@@ -119,9 +122,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_fwd_tma_kernel(const LnFwdPar
   // all per-element math on float2 pairs (FFMA2 / FADD2 / FMUL2): the kernel is instruction-issue bound otherwise
   const int c0 = lane * 8;
   const bool cact = FULLC || c0 < p.C;
-  float2 pa[NMOD][4], pb[NMOD][4], pw[NMOD][4], plsum[4];
+  float2 pa[NMOD][4], pb[NMOD][4], pw[NMOD][4], plsum[4], plb0[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) plsum[i] = splat(0.f);
+  for (int i = 0; i < 4; ++i) plsum[i] = plb0[i] = splat(0.f);
 #pragma unroll
   for (int m = 0; m < NMOD; ++m) {
 #pragma unroll
@@ -134,6 +137,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_fwd_tma_kernel(const LnFwdPar
       ldg8p(p.lb[m] + c0, lb);
 #pragma unroll
       for (int i = 0; i < 4; ++i) plsum[i] = add2(plsum[i], lb[i]);
+      if (PARTS && m == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) plb0[i] = lb[i];
+      }
     }
   }
   const float invC = 1.f / static_cast<float>(p.C);
@@ -208,6 +215,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_fwd_tma_kernel(const LnFwdPar
           const float2 r2 = splat(r);
 #pragma unroll
           for (int i = 0; i < 4; ++i) o[i] = fma2(v[m][i], mul2(pw[m][i], r2), o[i]);
+          if (PARTS && m == 0 && cact) {
+            float2 o0[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o0[i] = fma2(v[0][i], mul2(pw[0][i], r2), plb0[i]);
+            stg8p(p.Z0 + row * p.C + c0, o0);
+          }
           if (lane == 0 && p.mu[m] != nullptr) {
             p.mu[m][row] = mu[m];
             p.r[m][row] = r;
@@ -425,9 +438,11 @@ int ln_bwd_tma_blocks(long long rows) {
 // Z (+)= sum over the nmod modules of LayerNorm(a U + b + X) lw + lb.  All activations bf16 [rows, C].
 int ln_fwd_tma(int nmod, const bf16* const* U, const bf16* const* X, const float* const* a, const float* const* b,
                const float* const* lw, const float* const* lb, float* const* mu, float* const* r, bf16* Z,
-               long long rows, int C, float eps, int accumulate, cudaStream_t stream) {
+               long long rows, int C, float eps, int accumulate, cudaStream_t stream, bf16* Z0) {
   if (!ln_tma_supported(C) || nmod < 1 || nmod > 2) return set_error(GLF_ERR_INVALID, "ln_fwd_tma: unsupported shape");
+  if (Z0 != nullptr && nmod != 2) return set_error(GLF_ERR_INVALID, "ln_fwd_tma: the parts output needs both modules");
   LnFwdParams p;
+  p.Z0 = Z0;
   for (int m = 0; m < 2; ++m) {
     const int k = m < nmod ? m : 0;
     p.U[m] = U[k]; p.X[m] = X[k]; p.a[m] = a[k]; p.b[m] = b[k]; p.lw[m] = lw[k]; p.lb[m] = lb[k];
@@ -447,6 +462,7 @@ int ln_fwd_tma(int nmod, const bf16* const* U, const bf16* const* X, const float
   void (*kern)(const LnFwdParams) =
       nmod == 2 ? (C == 256 ? ln_fwd_tma_kernel<2, true> : ln_fwd_tma_kernel<2, false>)
                 : (C == 256 ? ln_fwd_tma_kernel<1, true> : ln_fwd_tma_kernel<1, false>);
+  if (Z0 != nullptr) kern = C == 256 ? ln_fwd_tma_kernel<2, true, true> : ln_fwd_tma_kernel<2, false, true>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(ln_fwd_tma)");
   kern<<<grid, F_THREADS, smem, stream>>>(p);

@@ -92,8 +92,14 @@ def gate_concat_backward(f4, cls, ctr, gate, dxg, dxl, weight: float):
 
 
 class _FusionFunction(torch.autograd.Function):
+    """ONE autograd node for gate + concat + MGFM + MLFM + sum.  With ``parts`` it has a second output, the MGFM part
+    on its own (f4_global_fusion, ours.py:1823), written by the same fused LayerNorm pass; gradients that arrive
+    through that output (the cycle-consistency pass, R/main.py:211-235) take the per-block LayerNorm backward, and a
+    backward that carries NO gradient for the fused sum skips the MLFM block altogether."""
+
     @staticmethod
-    def forward(ctx, fusion, V, ng, *tensors):
+    def forward(ctx, fusion, V, ng, parts, *tensors):
+        ctx.set_materialize_grads(False)
         f4, cls, ctr = tensors[:V], tensors[V:2 * V], tensors[2 * V:3 * V]
         pg, pl = tensors[3 * V:3 * V + ng], tensors[3 * V + ng:]
         mg, ml = fusion.global_attn, fusion.local_attn
@@ -109,6 +115,8 @@ class _FusionFunction(torch.autograd.Function):
         shape = (B, V_, h, w, C_)
         pair = _pair_ln_ok(mg, ml, shape, xg, prec)
         zsum = torch.empty(shape, dtype=xg.dtype, device=xg.device)
+        parts = bool(parts) and pair
+        zglob = torch.empty(shape, dtype=xg.dtype, device=xg.device) if parts else None
         # MGFM and MLFM are independent up to the fused LayerNorm: the local block runs on a side stream (a parallel
         # branch when the step is captured in a CUDA graph), so one block's short latency-bound kernels (BN statistics,
         # the per-sequence W' products) overlap the other's streaming GEMMs
@@ -136,8 +144,9 @@ class _FusionFunction(torch.autograd.Function):
             # both blocks' BN + residual + LayerNorm and the `global + local` sum (ours.py:1834) in one HBM pass
             wg, wl = _weights_struct(tg, mg._buffer_table()), _weights_struct(tl, ml._buffer_table())
             with torch.cuda.device(xg.device):
-                L.check(L.load().glf_fusion_ln_fwd(C.byref(stg.desc), L.ptr(xg), L.ptr(xl), C.byref(wg), C.byref(wl),
-                                                   L.ptr(zsum), L.ptr(svg), L.ptr(svl), _stream_ptr()))
+                L.check(L.load().glf_fusion_ln_fwd_parts(C.byref(stg.desc), L.ptr(xg), L.ptr(xl), C.byref(wg),
+                                                         C.byref(wl), L.ptr(zsum), L.ptr(zglob), L.ptr(svg), L.ptr(svl),
+                                                         _stream_ptr()))
             if not need:
                 svg = svl = None
         ctx.pair = pair
@@ -146,10 +155,14 @@ class _FusionFunction(torch.autograd.Function):
         ctx.io_dtype = f4[0].dtype
         ctx.save_for_backward(xg, xl, gate, *f4c, *clsc, *ctrc, *pg, *pl)
         out = zsum if zsum.dtype == f4[0].dtype else zsum.to(f4[0].dtype)
+        ctx.parts = parts
+        if parts:
+            og = zglob if zglob.dtype == f4[0].dtype else zglob.to(f4[0].dtype)
+            return out.permute(0, 4, 1, 2, 3), og.permute(0, 4, 1, 2, 3)
         return out.permute(0, 4, 1, 2, 3)          # [B, C, V, h, w] view of the token-major buffer
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, dglob=None):
         V, ng = ctx.V, ctx.ng
         saved = ctx.saved_tensors
         xg, xl, gate = saved[:3]
@@ -160,43 +173,68 @@ class _FusionFunction(torch.autograd.Function):
         stg, svg, stl, svl = ctx.states
         if svg is None:
             raise L.GlfError("backward called on a forward that ran without grad")
-        dz = dout.permute(0, 2, 3, 4, 1)
-        if dz.dtype != xg.dtype:
-            dz = dz.to(xg.dtype)
-        dz = dz.contiguous()                        # token-major [B,V,h,w,C]; both blocks see the same dz (ours.py:1834)
+        def token(t):                               # [B,C,V,h,w] gradient -> token-major [B,V,h,w,C] in the x dtype
+            t = t.permute(0, 2, 3, 4, 1)
+            if t.dtype != xg.dtype:
+                t = t.to(xg.dtype)
+            return t.contiguous()
+        n_in = 4 + 3 * V + 2 * ng
+        if dout is None and dglob is None:
+            return (None,) * n_in
         tg, tl = mg._param_table(pg), ml._param_table(pl)
-        wsg = wsl = None
-        if ctx.pair:
-            # LayerNorm backward of both blocks in one pass (dz is read once); fills dV / partials inside each ws blob
-            stg.desc.dz_layout = stl.desc.dz_layout = L.LAYOUT_TOKEN
-            wsg, wsl = _blob(stg.sizes.ws_bwd_bytes, xg.device), _blob(stl.sizes.ws_bwd_bytes, xg.device)
-            wg, wl = _weights_struct(tg, mg._buffer_table()), _weights_struct(tl, ml._buffer_table())
-            with torch.cuda.device(xg.device):
-                L.check(L.load().glf_fusion_ln_bwd(C.byref(stg.desc), L.ptr(dz), L.ptr(xg), L.ptr(xl), C.byref(wg),
-                                                   C.byref(wl), L.ptr(svg), L.ptr(svl), L.ptr(wsg), L.ptr(wsl),
-                                                   _stream_ptr()))
-        gout_g, gout_l = claim_grad_out(mg), claim_grad_out(ml)
-        side = _side_stream(xg.device) if ctx.pair and ctx.fusion.overlap_blocks else None
-        if side is not None:       # after the fused LayerNorm backward the two blocks' chains are independent again
-            cur = torch.cuda.current_stream(xg.device)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
+        gl = None
+        if dglob is None:
+            dz = token(dout)                        # both blocks see the same dz (ours.py:1834)
+            wsg = wsl = None
+            if ctx.pair:
+                # LayerNorm backward of both blocks in one pass (dz is read once); fills dV / partials inside each ws blob
+                stg.desc.dz_layout = stl.desc.dz_layout = L.LAYOUT_TOKEN
+                stg.desc.reserved[0] = stl.desc.reserved[0] = 1
+                wsg, wsl = _blob(stg.sizes.ws_bwd_bytes, xg.device), _blob(stl.sizes.ws_bwd_bytes, xg.device)
+                wg, wl = _weights_struct(tg, mg._buffer_table()), _weights_struct(tl, ml._buffer_table())
+                with torch.cuda.device(xg.device):
+                    L.check(L.load().glf_fusion_ln_bwd(C.byref(stg.desc), L.ptr(dz), L.ptr(xg), L.ptr(xl), C.byref(wg),
+                                                       C.byref(wl), L.ptr(svg), L.ptr(svl), L.ptr(wsg), L.ptr(wsl),
+                                                       _stream_ptr()))
+            gout_g, gout_l = claim_grad_out(mg), claim_grad_out(ml)
+            side = _side_stream(xg.device) if ctx.pair and ctx.fusion.overlap_blocks else None
+            if side is not None:   # after the fused LayerNorm backward the two blocks' chains are independent again
+                cur = torch.cuda.current_stream(xg.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    dxl, gl = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xl, stl, svl, tl, ml._buffer_table(), ws=wsl,
+                                                 grad_out=gout_l)
+            dxg, gg = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xg, stg, svg, tg, mg._buffer_table(), ws=wsg,
+                                         grad_out=gout_g)
+            if side is not None:
+                cur.wait_stream(side)
+            else:
                 dxl, gl = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xl, stl, svl, tl, ml._buffer_table(), ws=wsl,
                                              grad_out=gout_l)
-        dxg, gg = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xg, stg, svg, tg, mg._buffer_table(), ws=wsg,
-                                     grad_out=gout_g)
-        if side is not None:
-            cur.wait_stream(side)
+            hook = ctx.fusion.on_weight_grads_ready
+            if hook is not None and gout_g is not None and gout_l is not None:
+                hook()  # the gradients sit in the bucket views: the all-reduce may start now, beside the gate backward
         else:
-            dxl, gl = tpavi_backward_raw(dz, L.LAYOUT_TOKEN, xl, stl, svl, tl, ml._buffer_table(), ws=wsl,
-                                         grad_out=gout_l)
-        hook = ctx.fusion.on_weight_grads_ready
-        if hook is not None and gout_g is not None and gout_l is not None:
-            hook()      # the gradients sit in the bucket views: the all-reduce may start now, beside the gate backward
+            # a gradient arrived through the MGFM part (cycle-consistency pass): the two blocks no longer share dz, so
+            # each runs its own LayerNorm backward (reserved[0] = 0); without a gradient for the fused sum the MLFM
+            # block is not on the path at all
+            dzg = token(dglob) if dout is None else token(dout) + token(dglob)
+            stg.desc.reserved[0] = 0
+            dxg, gg = tpavi_backward_raw(dzg, L.LAYOUT_TOKEN, xg, stg, svg, tg, mg._buffer_table(),
+                                         grad_out=claim_grad_out(mg))
+            if dout is not None:
+                stl.desc.reserved[0] = 0
+                dxl, gl = tpavi_backward_raw(token(dout), L.LAYOUT_TOKEN, xl, stl, svl, tl, ml._buffer_table(),
+                                             grad_out=claim_grad_out(ml))
+            else:
+                dxl = torch.zeros_like(dxg)
         df4, dcls, dctr = gate_concat_backward(f4, cls, ctr, gate, dxg, dxl, ctx.fusion.center_aware_weight)
-        out = [None, None, None] + list(df4) + list(dcls) + list(dctr)
+        out = [None, None, None, None] + list(df4) + list(dcls) + list(dctr)
         for mod, plist, gr in ((mg, pg, gg), (ml, pl, gl)):
             for name, p in zip(mod._plist_names(), plist):
+                if gr is None:
+                    out.append(None)
+                    continue
                 t = gr[mod._grad_key(name)].reshape(p.shape)
                 out.append(t if p.dtype == torch.float32 else t.to(p.dtype))
         return tuple(out)
@@ -266,18 +304,31 @@ class GlobalLocalFusion(nn.Module):
         if not (len(cls_logits) == V and len(ctr_logits) == V and V >= 1):
             raise ValueError("f4, cls_logits and ctr_logits need one entry per view")
         pg, pl = self.global_attn._plist(), self.local_attn._plist()
-        return _FusionFunction.apply(self, V, len(pg), *f4, *cls_logits, *ctr_logits, *pg, *pl)
+        return _FusionFunction.apply(self, V, len(pg), False, *f4, *cls_logits, *ctr_logits, *pg, *pl)
 
     def forward_parts(self, f4: Dict[str, torch.Tensor], mask_bb_logits: Dict[str, torch.Tensor],
-                      ctr_logits: Dict[str, torch.Tensor]):
+                      ctr_logits: Dict[str, torch.Tensor], need_local: bool = True):
         """Like ``forward`` but also returns the two parts the reference network hands back to its trainer
         (ours.py:1843 ``return mask, mask_bb, f4_global_fusion, f4_local_fusion``; the cycle-consistency pass of
         R/main.py:211-235 uses ``f4_global_fusion`` alone): ``(f4_fusion, f4_global_fusion, f4_local_fusion)``, dicts
-        view -> [B,C,h,w].  The parts need their own outputs, so the two blocks run as separate autograd nodes (gate
-        kernel, then one ``TPAVIModule`` call each) instead of the single fused node of ``forward``."""
+        view -> [B,C,h,w].  It is the same single fused autograd node as ``forward``: the fused LayerNorm pass stores the
+        MGFM part beside the sum (glf_fusion_ln_fwd_parts), the MLFM part is their difference (``need_local=False``
+        skips forming it: the trainer ignores it, main.py:220).  A backward that arrives only through
+        ``f4_global_fusion`` (the cycle pass) never touches the MLFM block."""
         views: List[str] = list(f4.keys())
         V = len(views)
         xs = [f4[v] for v in views]
+        pg, pl = self.global_attn._plist(), self.local_attn._plist()
+        res = _FusionFunction.apply(self, V, len(pg), True, *xs, *[mask_bb_logits[v] for v in views],
+                                    *[ctr_logits[v] for v in views], *pg, *pl)
+        if isinstance(res, tuple):
+            # the single fused node, with the MGFM part as its second output (one more store in the LayerNorm pass)
+            zs, zg = res
+            fus = {v: zs[:, :, i] for i, v in enumerate(views)}
+            glob = {v: zg[:, :, i] for i, v in enumerate(views)}
+            loc = {v: fus[v] - glob[v] for v in views} if need_local else None
+            return fus, glob, loc
+        # shapes / precisions the fused LayerNorm pair does not cover: the two blocks as separate autograd nodes
         x_dtype = torch.float32 if self.global_attn._precision_id() == L.PRECISION_F32X3 else torch.bfloat16
         xg, xl = _GateConcatFunction.apply(self.center_aware_weight, V, x_dtype, *xs,
                                            *[mask_bb_logits[v] for v in views], *[ctr_logits[v] for v in views])

@@ -134,6 +134,12 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
 GLF_API int glf_fusion_ln_supported(const glf_desc* d);
 GLF_API int glf_fusion_ln_fwd(const glf_desc* d, const void* xg, const void* xl, const glf_weights* wg,
                       const glf_weights* wl, void* z, void* saved_g, void* saved_l, glf_stream_t stream);
+/* Same pass, also storing the MGFM part on its own: z_global = LN_g(BN_g(U_g) + x_g) (bf16 token-major, like z) —
+ * f4_global_fusion of R/models/ours.py:1823, which the trainer's cycle-consistency pass consumes (R/main.py:211-235);
+ * the MLFM part is z - z_global.  z_global == NULL is glf_fusion_ln_fwd. */
+GLF_API int glf_fusion_ln_fwd_parts(const glf_desc* d, const void* xg, const void* xl, const glf_weights* wg,
+                            const glf_weights* wl, void* z, void* z_global, void* saved_g, void* saved_l,
+                            glf_stream_t stream);
 GLF_API int glf_fusion_ln_bwd(const glf_desc* d, const void* dz, const void* xg, const void* xl, const glf_weights* wg,
                       const glf_weights* wl, const void* saved_g, const void* saved_l, void* ws_g, void* ws_l,
                       glf_stream_t stream);

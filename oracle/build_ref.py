@@ -20,11 +20,54 @@ REF_DST = os.path.join(REF_DIR, "models", "TPAVI.py")
 
 
 def build_ref() -> bool:
-    """Stage the reference file; True when oracle/_ref holds it afterwards."""
+    """Stage the reference's ``models/`` package (the fusion block and, for the full-network harness of
+    tests/test_gpu_network.py, the network that calls it); True when oracle/_ref holds it afterwards."""
+    src_dir = os.path.dirname(REF_SRC)
     if os.path.exists(REF_SRC):
         os.makedirs(os.path.dirname(REF_DST), exist_ok=True)
-        shutil.copyfile(REF_SRC, REF_DST)
+        for name in sorted(os.listdir(src_dir)):
+            if name.endswith(".py"):
+                shutil.copyfile(os.path.join(src_dir, name), os.path.join(os.path.dirname(REF_DST), name))
     return os.path.exists(REF_DST)
+
+
+def import_reference_network():
+    """``models.ours`` of the staged reference, importable in this image: the harness-side shim of SURVEY.md 8(c) —
+    stub modules for the packages the file imports but the fusion network never uses (monai, matplotlib, tensorboardX)
+    and ``resnet50(weights=None)`` instead of the ImageNet download (no network here).  Nothing of the reference is
+    edited.  Returns the module, or None when oracle/_ref was never staged."""
+    import importlib
+    import sys
+    import types
+    if not os.path.exists(os.path.join(REF_DIR, "models", "ours.py")):
+        return None
+    for name in ("monai", "monai.data", "matplotlib", "matplotlib.pyplot", "tensorboardX"):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    sys.modules["monai.data"].DataLoader = getattr(sys.modules["monai.data"], "DataLoader", object)
+    sys.modules["monai"].data = sys.modules["monai.data"]
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["tensorboardX"].SummaryWriter = getattr(sys.modules["tensorboardX"], "SummaryWriter", object)
+    import torchvision.models.resnet as tvr
+    if not getattr(tvr, "_glf_no_download", False):
+        orig = tvr.resnet50
+
+        def resnet50_no_download(*args, **kwargs):
+            kwargs.pop("pretrained", None)
+            kwargs["weights"] = None
+            return orig(*args, **kwargs)
+        tvr.resnet50 = resnet50_no_download
+        tvr.__dict__["resnet50"] = resnet50_no_download
+        tvr._glf_no_download = True
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+        if not getattr(sys.modules[k], "__file__", "").startswith(REF_DIR):
+            del sys.modules[k]
+    return importlib.import_module("models.ours")
 
 
 def load_reference_tpavi():

@@ -273,3 +273,44 @@ def test_reference_checkpoint_inference(tmp_path):
         assert_close(f"out:{v}", out[:, :, v], ref[v], BF16_TOL)
     assert torch.equal(f.global_attn.W_z[1].running_mean, before)
     assert int(f.global_attn.W_z[1].num_batches_tracked) == 1234
+
+
+def test_forward_parts_combined_segmentation_and_cycle_gradients():
+    """One backward that carries BOTH a gradient for the fused sum (segmentation loss) and one for the MGFM part alone
+    (cycle loss on its spatial sums, R/main.py:229-237): the fused node then runs the per-block LayerNorm backward."""
+    B, C, V, h, w = 4, 256, 4, 14, 14
+    pg = O.init_params(C, seed=81, randomize_affine=True)
+    pl = O.init_params(C, seed=82, randomize_affine=True)
+    gen = torch.Generator().manual_seed(83)
+    f4 = [torch.randn(B, C, h, w, generator=gen) for _ in range(V)]
+    cl = [torch.randn(B, 5, h, w, generator=gen) for _ in range(V)]
+    ct = [torch.randn(B, 1, h, w, generator=gen) for _ in range(V)]
+    dseg = [torch.randn(B, C, h, w, generator=gen) for _ in range(V)]
+    wsum = torch.randn(B, C, generator=gen)
+    f4o = [t.clone().requires_grad_(True) for t in f4]
+
+    def leaf(p):
+        return {k: (v.clone().requires_grad_(True) if v.is_floating_point() and k not in O.BUFFER_KEYS else v.clone())
+                for k, v in p.items()}
+    qg, ql = leaf(pg), leaf(pl)
+    xg, xl = O.gate_concat(f4o, cl, ct)
+    zg, zl = O.tpavi_forward(xg, qg), O.tpavi_forward(xl, ql)
+    loss = sum(((zg[:, :, i] + zl[:, :, i]) * dseg[i]).sum() + 0.5 * (zg[:, :, i].sum(dim=(2, 3)) * wsum).sum()
+               for i in range(V))
+    loss.backward()
+    f = _build(C, pg, pl)
+    f4d = [t.to(DEV, torch.bfloat16).requires_grad_(True) for t in f4]
+    keys = [str(i) for i in range(V)]
+    fus, glob, loc = f.forward_parts(dict(zip(keys, f4d)), dict(zip(keys, [t.to(DEV) for t in cl])),
+                                     dict(zip(keys, [t.to(DEV) for t in ct])), need_local=False)
+    assert loc is None
+    loss_d = sum((fus[k].float() * dseg[i].to(DEV)).sum() + 0.5 * (glob[k].float().sum(dim=(2, 3)) * wsum.to(DEV)).sum()
+                 for i, k in enumerate(keys))
+    loss_d.backward()
+    torch.cuda.synchronize()
+    for i in range(V):
+        assert_close(f"df4:{i}", f4d[i].grad, f4o[i].grad, BF16_TOL)
+    for mod, ref in ((f.global_attn, qg), (f.local_attn, ql)):
+        for k, p in mod.named_parameters():
+            if not k.startswith("align_channel") and k != "W_z.0.bias":
+                assert_close("grad:" + k, p.grad, ref[k].grad, grad_tol(k), abs_floor=1e-3)
