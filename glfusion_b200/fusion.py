@@ -98,8 +98,9 @@ class _FusionFunction(torch.autograd.Function):
     backward that carries NO gradient for the fused sum skips the MLFM block altogether."""
 
     @staticmethod
-    def forward(ctx, fusion, V, ng, parts, *tensors):
+    def forward(ctx, fusion, V, ng, parts, per_view, *tensors):
         ctx.set_materialize_grads(False)
+        ctx.per_view = bool(per_view)
         f4, cls, ctr = tensors[:V], tensors[V:2 * V], tensors[2 * V:3 * V]
         pg, pl = tensors[3 * V:3 * V + ng], tensors[3 * V + ng:]
         mg, ml = fusion.global_attn, fusion.local_attn
@@ -156,13 +157,22 @@ class _FusionFunction(torch.autograd.Function):
         ctx.save_for_backward(xg, xl, gate, *f4c, *clsc, *ctrc, *pg, *pl)
         out = zsum if zsum.dtype == f4[0].dtype else zsum.to(f4[0].dtype)
         ctx.parts = parts
+        og = None
         if parts:
             og = zglob if zglob.dtype == f4[0].dtype else zglob.to(f4[0].dtype)
+        if ctx.per_view:
+            # one output per view ([B,C,h,w] views of the token-major buffers): the dict-keyed callers then get one
+            # gradient per view in backward, instead of autograd materialising V full-size zero tensors for V slices
+            res = [out[:, v].permute(0, 3, 1, 2) for v in range(V_)]
+            if parts:
+                res += [og[:, v].permute(0, 3, 1, 2) for v in range(V_)]
+            return tuple(res)
+        if parts:
             return out.permute(0, 4, 1, 2, 3), og.permute(0, 4, 1, 2, 3)
         return out.permute(0, 4, 1, 2, 3)          # [B, C, V, h, w] view of the token-major buffer
 
     @staticmethod
-    def backward(ctx, dout, dglob=None):
+    def backward(ctx, *grads):
         V, ng = ctx.V, ctx.ng
         saved = ctx.saved_tensors
         xg, xl, gate = saved[:3]
@@ -174,11 +184,30 @@ class _FusionFunction(torch.autograd.Function):
         if svg is None:
             raise L.GlfError("backward called on a forward that ran without grad")
         def token(t):                               # [B,C,V,h,w] gradient -> token-major [B,V,h,w,C] in the x dtype
+            if ctx.per_view:
+                return t                            # assembled token-major below
             t = t.permute(0, 2, 3, 4, 1)
             if t.dtype != xg.dtype:
                 t = t.to(xg.dtype)
             return t.contiguous()
-        n_in = 4 + 3 * V + 2 * ng
+
+        def assemble(gs):                           # per-view [B,C,h,w] gradients -> one token-major [B,V,h,w,C] buffer
+            if all(g is None for g in gs):
+                return None
+            buf = torch.empty(xg.shape, dtype=xg.dtype, device=xg.device)
+            for v, g in enumerate(gs):
+                if g is None:
+                    buf[:, v].zero_()
+                else:
+                    buf[:, v].copy_(g.permute(0, 2, 3, 1))
+            return buf
+        if ctx.per_view:
+            dout = assemble(grads[:V])
+            dglob = assemble(grads[V:2 * V]) if ctx.parts else None
+        else:
+            dout = grads[0]
+            dglob = grads[1] if len(grads) > 1 else None
+        n_in = 5 + 3 * V + 2 * ng
         if dout is None and dglob is None:
             return (None,) * n_in
         tg, tl = mg._param_table(pg), ml._param_table(pl)
@@ -229,7 +258,7 @@ class _FusionFunction(torch.autograd.Function):
             else:
                 dxl = torch.zeros_like(dxg)
         df4, dcls, dctr = gate_concat_backward(f4, cls, ctr, gate, dxg, dxl, ctx.fusion.center_aware_weight)
-        out = [None, None, None, None] + list(df4) + list(dcls) + list(dctr)
+        out = [None, None, None, None, None] + list(df4) + list(dcls) + list(dctr)
         for mod, plist, gr in ((mg, pg, gg), (ml, pl, gl)):
             for name, p in zip(mod._plist_names(), plist):
                 if gr is None:
@@ -304,7 +333,7 @@ class GlobalLocalFusion(nn.Module):
         if not (len(cls_logits) == V and len(ctr_logits) == V and V >= 1):
             raise ValueError("f4, cls_logits and ctr_logits need one entry per view")
         pg, pl = self.global_attn._plist(), self.local_attn._plist()
-        return _FusionFunction.apply(self, V, len(pg), False, *f4, *cls_logits, *ctr_logits, *pg, *pl)
+        return _FusionFunction.apply(self, V, len(pg), False, False, *f4, *cls_logits, *ctr_logits, *pg, *pl)
 
     def forward_parts(self, f4: Dict[str, torch.Tensor], mask_bb_logits: Dict[str, torch.Tensor],
                       ctr_logits: Dict[str, torch.Tensor], need_local: bool = True):
@@ -319,13 +348,12 @@ class GlobalLocalFusion(nn.Module):
         V = len(views)
         xs = [f4[v] for v in views]
         pg, pl = self.global_attn._plist(), self.local_attn._plist()
-        res = _FusionFunction.apply(self, V, len(pg), True, *xs, *[mask_bb_logits[v] for v in views],
+        res = _FusionFunction.apply(self, V, len(pg), True, True, *xs, *[mask_bb_logits[v] for v in views],
                                     *[ctr_logits[v] for v in views], *pg, *pl)
-        if isinstance(res, tuple):
-            # the single fused node, with the MGFM part as its second output (one more store in the LayerNorm pass)
-            zs, zg = res
-            fus = {v: zs[:, :, i] for i, v in enumerate(views)}
-            glob = {v: zg[:, :, i] for i, v in enumerate(views)}
+        if len(res) == 2 * V:
+            # the single fused node, with the MGFM parts as further outputs (one more store in the LayerNorm pass)
+            fus = {v: res[i] for i, v in enumerate(views)}
+            glob = {v: res[V + i] for i, v in enumerate(views)}
             loc = {v: fus[v] - glob[v] for v in views} if need_local else None
             return fus, glob, loc
         # shapes / precisions the fused LayerNorm pair does not cover: the two blocks as separate autograd nodes
@@ -344,6 +372,8 @@ class GlobalLocalFusion(nn.Module):
                 ctr_logits: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """Dict-keyed like the reference (view id -> tensor): returns f4_fusion[view] = global + local."""
         views: List[str] = list(f4.keys())
-        out = self.forward_stacked([f4[v] for v in views], [mask_bb_logits[v] for v in views],
-                                   [ctr_logits[v] for v in views])
-        return {v: out[:, :, i] for i, v in enumerate(views)}
+        V = len(views)
+        pg, pl = self.global_attn._plist(), self.local_attn._plist()
+        res = _FusionFunction.apply(self, V, len(pg), False, True, *[f4[v] for v in views],
+                                    *[mask_bb_logits[v] for v in views], *[ctr_logits[v] for v in views], *pg, *pl)
+        return {v: res[i] for i, v in enumerate(views)}
