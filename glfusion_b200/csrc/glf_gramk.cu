@@ -12,6 +12,8 @@
 //   warp 1      MMA issuer: tcgen05.mma M=128, N=C, K=16, both operands MN-major, C/128 accumulators
 //   warps 2..9  during the main loop: column sums of A read from the staged blocks (thread = channel); afterwards the
 //               epilogue: tcgen05.ld -> bf16 rows of the augmented [Ca x Ca] matrix, or fp32 red.add for split-K
+#include <cstdlib>
+
 #include "glf_internal.h"
 #include "glf_ptx.cuh"
 
@@ -30,6 +32,7 @@ struct GramKParams {
   int B, N, C, Ca;
   int ksplit, kb_total, kb_per_split;
   int same;        // A == X: the X block is not loaded, the B operand is the A block
+  int sym;         // same && C == 256 && ksplit == 1: the lower-left 128 x 128 block is mirrored, not computed
   bf16* out;       // ksplit == 1: [B][Ca][Ca] bf16, rows/cols < C written
   float* outf;     // ksplit  > 1: [B][C][C] fp32, atomically accumulated (zeroed by the caller)
   float* rowsum;   // [B][C] column sums of A (stored, or atomically accumulated when ksplit > 1)
@@ -70,12 +73,18 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
 #pragma unroll
     for (int s = 0; s < GK_MAX_STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1 + 8);   // MMA commit + the eight column-sum warps
+      // MMA commit + the eight column-sum warps (symmetric S: the column sums come from the tensor core as well)
+      mbar_init(smem_u32(&empty_bar[s]), p.sym ? 1 : 1 + 8);
     }
     mbar_init(smem_u32(&tmem_full_bar), 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_holder), 512);
+  __shared__ __align__(1024) uint8_t ones_tile[2048];          // K-major [16 rows][64 k] of bf16 1.0 (swizzle-invariant)
+  if (p.sym) {
+    for (int i = threadIdx.x; i < 512; i += GK_THREADS) reinterpret_cast<uint32_t*>(ones_tile)[i] = 0x3F803F80u;
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -101,6 +110,8 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
   } else if (warp == 1) {
     if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(128, p.C, true, true);
+      const uint32_t idesc_half = make_idesc_bf16(128, 128, true, true);
+      const uint32_t idesc_ones = make_idesc_bf16(128, 16, true, false);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < nkb; ++it) {
@@ -108,12 +119,31 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
         tc_fence_after();
         const uint32_t sa = smem_base + stage * stage_bytes;
         const uint32_t sb = p.same ? sa : sa + GK_BLK;
+        if (p.sym) {
+          // S = X^T X is symmetric: rows 0..127 take all 256 columns, rows 128..255 only columns 128..255; the
+          // epilogue mirrors the upper-right block into the lower-left one (a quarter of the MMA work and of its
+          // shared-memory operand traffic saved: the kernel is bound by shared-memory bandwidth, not by the tensor pipe)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t bd = make_sdesc(sb + k * 2048, 8192, 1024);
-          for (int mt = 0; mt < MT; ++mt) {
-            const uint64_t ad = make_sdesc(sa + mt * 16384 + k * 2048, 8192, 1024);
-            umma_f16(tmem_base + mt * p.C, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            umma_f16(tmem_base, make_sdesc(sa + k * 2048, 8192, 1024), make_sdesc(sa + k * 2048, 8192, 1024), idesc,
+                     (it | k) != 0 ? 1u : 0u);
+            umma_f16(tmem_base + 256 + 128, make_sdesc(sa + 16384 + k * 2048, 8192, 1024),
+                     make_sdesc(sa + 16384 + k * 2048, 8192, 1024), idesc_half, (it | k) != 0 ? 1u : 0u);
+            // column sums of X = X^T 1: both 128-channel halves against the ones tile, into the TMEM columns the
+            // mirrored block leaves free (256 .. 271 and 272 .. 287)
+            const uint64_t od = make_sdesc(smem_u32(ones_tile) + k * 32, 16, 1024);
+            umma_f16(tmem_base + 256, make_sdesc(sa + k * 2048, 8192, 1024), od, idesc_ones, (it | k) != 0 ? 1u : 0u);
+            umma_f16(tmem_base + 256 + 16, make_sdesc(sa + 16384 + k * 2048, 8192, 1024), od, idesc_ones,
+                     (it | k) != 0 ? 1u : 0u);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t bd = make_sdesc(sb + k * 2048, 8192, 1024);
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint64_t ad = make_sdesc(sa + mt * 16384 + k * 2048, 8192, 1024);
+              umma_f16(tmem_base + mt * p.C, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+            }
           }
         }
         umma_commit(smem_u32(&empty_bar[stage]));
@@ -122,52 +152,63 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
       umma_commit(smem_u32(&tmem_full_bar));
     }
   } else {
-    // ---- column sums of A from the staged blocks: thread t = channel t
+    // ---- column sums of A from the staged blocks: thread = (channel pair cp, half of the 64 rows); 32-bit loads (the
+    //      kernel is bound by shared-memory bandwidth: 2-byte loads waste half of every wavefront)
     const int t = threadIdx.x - 64;
-    {
-      const uint32_t off0 = static_cast<uint32_t>(t >> 6) * 8192u + static_cast<uint32_t>(t & 7) * 2u;
-      const uint32_t chunk = static_cast<uint32_t>((t & 63) >> 3);
-      float acc0 = 0.f, acc1 = 0.f;
+    __shared__ float cs_x[2][256];
+    // column sum `cs` of channel `ch`: stored (or atomically added for a token split), plus the homogeneous border
+    auto emit_colsum = [&](int ch, float cs) {
+      float* dst = p.rowsum + static_cast<long long>(b) * p.C + ch;
+      if (p.ksplit > 1) {
+        atomicAdd(dst, cs);
+        return;
+      }
+      *dst = cs;
+      if (!p.border) return;
+      // border of the augmented matrix: out[ch][C .. Ca) = {scaled column sum, 0 ...}; out[C][ch] = rowv or the sum
+      bf16* M = p.out + static_cast<long long>(b) * p.Ca * p.Ca;
+      const float rs = p.rowscale != nullptr ? p.rowscale[ch] : 1.f;
+      if (p.Ca - p.C == 8) {
+        *reinterpret_cast<uint4*>(M + static_cast<long long>(ch) * p.Ca + p.C) = make_uint4(pack_bf16(cs * rs, 0.f), 0u, 0u, 0u);
+      } else {
+        for (int j = p.C; j < p.Ca; ++j) M[static_cast<long long>(ch) * p.Ca + j] = __float2bfloat16(j == p.C ? cs * rs : 0.f);
+      }
+      M[static_cast<long long>(p.C) * p.Ca + ch] =
+          __float2bfloat16(p.rowv != nullptr ? p.rowv[static_cast<long long>(b) * p.C + ch] : cs);
+      if (ch == 0)
+        for (int j = p.C; j < p.Ca; ++j)
+          M[static_cast<long long>(p.C) * p.Ca + j] = __float2bfloat16(j == p.C ? p.corner : 0.f);
+    };
+    if (!p.sym) {
+      const int cp = t & 127, rh = t >> 7;                       // channels 2 cp, 2 cp + 1 ; rows 32 rh .. 32 rh + 31
+      const int ch = 2 * cp;
+      const uint32_t off0 = static_cast<uint32_t>(ch >> 6) * 8192u + static_cast<uint32_t>(ch & 7) * 2u;
+      const uint32_t chunk = static_cast<uint32_t>((ch & 63) >> 3);
+      float2 a2 = make_float2(0.f, 0.f), b2 = make_float2(0.f, 0.f);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < nkb; ++it) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
-        if (t < p.C) {
-          const uint8_t* blk = smem_gen + stage * stage_bytes + off0;
+        if (ch < p.C) {
+          const uint8_t* blk = smem_gen + stage * stage_bytes + off0 + rh * 32 * 128;
 #pragma unroll 8
-          for (int k = 0; k < 64; k += 2) {
-            acc0 += __bfloat162float(*reinterpret_cast<const bf16*>(blk + k * 128 + ((chunk ^ (k & 7)) << 4)));
-            acc1 += __bfloat162float(*reinterpret_cast<const bf16*>(blk + (k + 1) * 128 + ((chunk ^ ((k + 1) & 7)) << 4)));
+          for (int k = 0; k < 32; k += 2) {
+            a2 = add2(a2, unpack_bf16(*reinterpret_cast<const uint32_t*>(blk + k * 128 + ((chunk ^ (k & 7)) << 4))));
+            b2 = add2(b2, unpack_bf16(*reinterpret_cast<const uint32_t*>(blk + (k + 1) * 128 + ((chunk ^ ((k + 1) & 7)) << 4))));
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));
         if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
-      if (t < p.C) {
-        const float cs = acc0 + acc1;
-        float* dst = p.rowsum + static_cast<long long>(b) * p.C + t;
-        if (p.ksplit > 1) {
-          atomicAdd(dst, cs);
-        } else {
-          *dst = cs;
-          if (p.border) {
-          // border of the augmented matrix: out[t][C .. Ca) = {scaled column sum, 0 ...}; out[C][t] = rowv or the sum
-          bf16* M = p.out + static_cast<long long>(b) * p.Ca * p.Ca;
-          const float rs = p.rowscale != nullptr ? p.rowscale[t] : 1.f;
-          if (p.Ca - p.C == 8) {
-            *reinterpret_cast<uint4*>(M + static_cast<long long>(t) * p.Ca + p.C) = make_uint4(pack_bf16(cs * rs, 0.f), 0u, 0u, 0u);
-          } else {
-            for (int j = p.C; j < p.Ca; ++j) M[static_cast<long long>(t) * p.Ca + j] = __float2bfloat16(j == p.C ? cs * rs : 0.f);
-          }
-          M[static_cast<long long>(p.C) * p.Ca + t] =
-              __float2bfloat16(p.rowv != nullptr ? p.rowv[static_cast<long long>(b) * p.C + t] : cs);
-          if (t == 0)
-            for (int j = p.C; j < p.Ca; ++j)
-              M[static_cast<long long>(p.C) * p.Ca + j] = __float2bfloat16(j == p.C ? p.corner : 0.f);
-          }
-        }
+      const float2 tot = add2(a2, b2);
+      if (ch < p.C) {
+        cs_x[rh][ch] = tot.x;
+        cs_x[rh][ch + 1] = tot.y;
       }
+      named_bar_sync(1, 256);
+      const float acc0 = t < p.C ? cs_x[0][t] : 0.f, acc1 = t < p.C ? cs_x[1][t] : 0.f;
+      if (t < p.C) emit_colsum(t, acc0 + acc1);
     }
     // ---- epilogue: warp (mt, q) owns TMEM lanes 32q..32q+31 of accumulator mt = output rows 128 mt + 32 q + lane
     const int q = warp & 3;
@@ -177,11 +218,27 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
     if (mt < MT) {
       const int row = mt * 128 + q * 32 + lane;
       const float rsc = (p.rowscale != nullptr && p.ksplit == 1) ? p.rowscale[row] : 1.f;
+      if (p.sym) {            // the column sums sit in TMEM columns 256 + 16 mt (every column of the group holds them)
+        uint32_t sv[32];
+        tmem_ld_32x32(tmem_base + 256 + (static_cast<uint32_t>(q * 32) << 16), sv);
+        tmem_ld_wait();
+        emit_colsum(row, __uint_as_float(sv[mt * 16]));
+      }
       const uint32_t taddr = tmem_base + mt * p.C + (static_cast<uint32_t>(q * 32) << 16);
-      for (int c = 0; c < p.C / 32; ++c) {
+      // symmetric S: rows 128..255 hold only columns 128..255 in TMEM; rows 0..127 also leave their columns 128..255
+      // TRANSPOSED in the (now idle) ring, [128 columns][128 rows] bf16 with a 272-byte pitch, for the mirror below
+      constexpr uint32_t SYM_PITCH = 272;
+      for (int c = (p.sym && mt == 1) ? 4 : 0; c < p.C / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         tmem_ld_wait();
+        if (p.sym && mt == 0 && c >= 4) {
+          uint8_t* stg = const_cast<uint8_t*>(smem_gen) + (row & 127) * 2;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            *reinterpret_cast<bf16*>(stg + static_cast<uint32_t>((c - 4) * 32 + j) * SYM_PITCH) =
+                __float2bfloat16(__uint_as_float(v[j]));
+        }
         if (p.ksplit > 1) {
           float* dst = p.outf + (static_cast<long long>(b) * p.C + row) * p.C + c * 32;
 #pragma unroll
@@ -199,6 +256,15 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
                                         pack_bf16(rsc * __uint_as_float(v[8 * j + 6]), rsc * __uint_as_float(v[8 * j + 7])));
             *reinterpret_cast<uint4*>(dst + 8 * j) = pk;
           }
+        }
+      }
+      if (p.sym) {
+        named_bar_sync(1, 256);
+        if (mt == 1) {        // S[128 + i][0..127] = S[0..127][128 + i]: row i of the transposed staging tile
+          const uint8_t* src = smem_gen + static_cast<uint32_t>(q * 32 + lane) * SYM_PITCH;
+          bf16* dst = p.out + (static_cast<long long>(b) * p.Ca + row) * p.Ca;
+#pragma unroll 4
+          for (int j = 0; j < 16; ++j) *reinterpret_cast<uint4*>(dst + 8 * j) = *reinterpret_cast<const uint4*>(src + 16 * j);
         }
       }
     }
@@ -233,6 +299,10 @@ int gram_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* scratch
   p.kb_per_split = (p.kb_total + ks - 1) / ks;
   p.ksplit = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.same = (A == X) ? 1 : 0;
+  {
+    const char* e = getenv("GLF_GRAM_SYM");      // tuning aid: GLF_GRAM_SYM=0 computes all four blocks of S
+    p.sym = (p.same && C == 256 && p.ksplit == 1 && rowscale == nullptr && out_aug != nullptr && !(e && e[0] == '0')) ? 1 : 0;
+  }
   p.out = out_aug; p.outf = scratch; p.rowsum = rowsum; p.rowscale = rowscale;
   p.rowv = rowv; p.corner = corner;
   p.border = (border && Ca > C) ? 1 : 0;
