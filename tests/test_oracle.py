@@ -153,3 +153,27 @@ def test_oracle_matches_live_reference(mode):
     sd = m.state_dict()
     for k in O.BUFFER_KEYS:
         assert O.rel_err(p[k].float(), sd[k].float()) < TOL
+
+
+def test_reference_arm_wrapper_matches_oracle():
+    """bench.py's reference arm / cpu_baseline / gpu_reference leg drive the UNMODIFIED reference module pair inside
+    the literal call-site lines ours.py:1802-1834 (oracle/build_ref.py::reference_fusion_fwd_bwd, on the staged
+    oracle/_ref copy): it must agree with the oracle's restatement of the same path."""
+    from oracle import build_ref
+    TPAVI = build_ref.load_reference_tpavi()
+    if TPAVI is None:
+        pytest.skip("oracle/_ref not staged (no /root/reference at build time)")
+    B, C, V, h, w = 2, 64, 3, 6, 5
+    pg = O.init_params(C, seed=1, randomize_affine=True)
+    pl = O.init_params(C, seed=2, randomize_affine=True)
+    gen = torch.Generator().manual_seed(3)
+    f4 = [torch.randn(B, C, h, w, generator=gen) for _ in range(V)]
+    cl = [torch.randn(B, 5, h, w, generator=gen) for _ in range(V)]
+    ct = [torch.randn(B, 1, h, w, generator=gen) for _ in range(V)]
+    do = [torch.randn(B, C, h, w, generator=gen) for _ in range(V)]
+    outs, df4, _, _, _, _ = O.fusion_fwd_bwd(f4, cl, ct, do, {k: v.clone() for k, v in pg.items()},
+                                             {k: v.clone() for k, v in pl.items()})
+    r_out, r_df4 = build_ref.reference_fusion_fwd_bwd(TPAVI, f4, cl, ct, do, pg, pl)
+    for v in range(V):
+        assert O.rel_err(r_out[v].detach(), outs[v]) < 2e-5
+        assert O.rel_err(r_df4[v], df4[v]) < 2e-5
