@@ -13,6 +13,9 @@
 // a fixed order (deterministic gradients, no atomics) straight into the caller's gradient tensors.
 // The homogeneous column of the augmented matrices (the bias gradients) and the rank-1 term dt s^T of dWphi are formed
 // in fp32 by the SIMT warps from the staged tiles.
+#include <cstdio>
+#include <cstdlib>
+
 #include "glf_internal.h"
 #include "glf_ptx.cuh"
 
@@ -33,8 +36,15 @@ constexpr uint32_t WG_STAGE = 49152;           // one K slab of both operands
 constexpr uint32_t WG_SMEM = WG_STAGES * WG_STAGE + 4096 + 1024;
 constexpr int WG_PART = 128 * 256 + 256;       // floats per partial: the matrix + the bias vector (padded)
 
+// Debug aid (GLF_WGRAD_TRACE=1): SM clock at a few points of selected CTAs (one per product), printed by the host.
+__device__ long long g_wgrad_trace[4][8];
+#define WG_TRACE(i)                                                                              \
+  do {                                                                                           \
+    if (p.trace && j == 0) g_wgrad_trace[prod][i] = clock64();                                   \
+  } while (0)
+
 struct WgradParams {
-  int B, N;
+  int B, N, trace;
   int cta0[5];            // first CTA of product p (theta, z, g, phi); cta0[4] = number of CTAs
   const float *dcv, *tv, *dtv, *sfv;   // dc [B][C], t [B][C'], dt [B][C'], s [B][C]
   float* part;            // [n_cta][WG_PART]
@@ -87,6 +97,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_holder;
+  if (threadIdx.x == 0) WG_TRACE(0);
 
   if (warp == 0) {
     if (elect_one()) {
@@ -142,6 +153,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
       }
       umma_commit(acc_bar);
+      WG_TRACE(1);
     }
   } else {
     // ------------------------------------------------------------------------------------------ SIMT warps
@@ -149,10 +161,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     // bias gradients from the staged tiles: theta: sum_r W'[r,i] dc[r]; g: sum_i (dM/N)[i,j] t[i];
     // phi: sum_k dT[i,k] s[k] (+ N dt[i] once per sequence).  Thread pairs split the 64 slab rows / columns.
     float bacc = 0.f;
+    float cacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // products theta / g: 8 columns of this thread's chunk
     {
       int stage = 0;
       uint32_t phase = 0;
       const int i = tid & 127, half = tid >> 7;
+      const int cc = tid & 15, rg = tid >> 4;                    // theta / g: column chunk (of 16), row group (of 16)
       for (int it = 0; it < nsl; ++it) {
         const int sl = sl0 + it, b = sl / spq, k = sl - b * spq;
         mbar_wait(full(stage), phase);
@@ -160,9 +174,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         if (prod == 0 || prod == 2) {
           const float* vec = prod == 0 ? p.dcv + static_cast<long long>(b) * CC + 64 * k
                                        : p.tv + static_cast<long long>(b) * CI + 64 * k;
-          const uint8_t* tile = sa + (i >> 6) * 8192;      // A tile holding column i
-#pragma unroll 8
-          for (int r = half * 32; r < half * 32 + 32; ++r) bacc = fmaf(tile64(tile, r, i & 63), vec[r], bacc);
+          const uint8_t* tile = sa + (cc >> 3) * 8192;     // A tile ([64 rows][64 columns]) holding this column chunk
+#pragma unroll
+          for (int r = rg * 4; r < rg * 4 + 4; ++r) {
+            const uint4 qv = *reinterpret_cast<const uint4*>(tile + r * 128 + (((cc & 7) ^ (r & 7)) << 4));
+            const uint32_t* q32 = reinterpret_cast<const uint32_t*>(&qv);
+            const float wv = vec[r];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 x = unpack_bf16(q32[t]);
+              cacc[2 * t] = fmaf(x.x, wv, cacc[2 * t]);
+              cacc[2 * t + 1] = fmaf(x.y, wv, cacc[2 * t + 1]);
+            }
+          }
         } else if (prod == 3) {
           const float* vec = p.sfv + static_cast<long long>(b) * CC + 64 * k;
 #pragma unroll
@@ -181,57 +205,100 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         if (lane == 0) mbar_arrive(empty(stage));
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
       }
-      if (half == 1) v_bias[i] = bacc;
-      named_bar_sync(1, 256);
-      if (half == 0) v_bias[i] += bacc;
-      named_bar_sync(1, 256);
+      if (tid == 0) WG_TRACE(2);
+      if (prod == 1 || prod == 3) {
+        if (half == 1) v_bias[i] = bacc;
+        named_bar_sync(1, 256);
+        if (half == 0) v_bias[i] += bacc;
+        named_bar_sync(1, 256);
+      }
     }
     // ---- epilogue: fp32 partial of this CTA.  Layout [256 rows][128] for dWz, [128 rows][256] otherwise.
     const int w = warp - 2, q = warp & 3, hf = w >> 2;
     float* out = p.part + static_cast<long long>(blockIdx.x) * WG_PART;
     mbar_wait(acc_bar, 0);
     tc_fence_after();
-    const uint32_t tlane = tmem + (static_cast<uint32_t>(q * 32) << 16);
-    if (prod == 1) {
-      const int row = hf * 128 + q * 32 + lane;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tlane + hf * 128 + c * 32, v);
-        tmem_ld_wait();
-        float4* dst = reinterpret_cast<float4*>(out + row * 128 + c * 32);
+    if (tid == 0) WG_TRACE(3);
+    const int cc = tid & 15;
+    if (prod == 0 || prod == 2) {    // (after the accumulator wait: the MMAs no longer read the ring)
+      // 16 row groups hold partial sums of the same column chunk: lanes l and l ^ 16 first, then the 8 warps
+      float* xs = reinterpret_cast<float*>(sgen);     // the ring is idle now: [8 warps][128 columns]
 #pragma unroll
-        for (int t = 0; t < 8; ++t)
-          dst[t] = make_float4(__uint_as_float(v[4 * t]), __uint_as_float(v[4 * t + 1]), __uint_as_float(v[4 * t + 2]),
-                               __uint_as_float(v[4 * t + 3]));
+      for (int t = 0; t < 8; ++t) cacc[t] += __shfl_xor_sync(0xffffffffu, cacc[t], 16);
+      named_bar_sync(1, 256);                          // (every warp has left the ring's last stage)
+      if (lane < 16) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) xs[(warp - 2) * 128 + cc * 8 + t] = cacc[t];
       }
-    } else {
-      const int row = q * 32 + lane;
-      // phi: + sum over the sequences that START in this CTA's range of dt_b[row] s_b[n]
-      const int bs0 = (sl0 + spq - 1) / spq, bs1 = (sl1 + spq - 1) / spq;   // sequences whose slab 0 lies in [sl0, sl1)
+      named_bar_sync(1, 256);
+      if (tid < 128) {
+        float a = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) a += xs[wv * 128 + tid];
+        v_bias[tid] = a;
+      }
+      named_bar_sync(1, 256);
+    }
+
+    const uint32_t tlane = tmem + (static_cast<uint32_t>(q * 32) << 16);
+    // the accumulator goes through the (idle) ring as fp32 rows with a padded pitch, then out with coalesced 16-byte
+    // stores: thread-per-row stores straight from registers touched 32 lines per instruction
+    constexpr uint32_t PITCH = 1040;                    // bytes per staged row of 256 floats (+ 4 floats: bank spread)
+    uint8_t* stg = sgen + 4096;                          // (the first 4 KB held the bias exchange above)
+    const int nrow = prod == 1 ? 256 : 128, ncol = prod == 1 ? 128 : 256;
+    const int bs0 = (sl0 + spq - 1) / spq, bs1 = (sl1 + spq - 1) / spq;   // sequences whose slab 0 lies in [sl0, sl1)
+    for (int pass = 0; pass < (prod == 1 ? 2 : 1); ++pass) {             // dWz: two 128-row halves, one at a time
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        const int col0 = hf * 128 + c * 32;
+        const int srow = q * 32 + lane;
+        int col0;
+        uint32_t taddr;
+        if (prod == 1) {
+          if (hf != pass) break;                         // (warps of the other half idle in this pass)
+          col0 = c * 32;
+          taddr = tlane + pass * 128 + col0;
+        } else {
+          col0 = hf * 128 + c * 32;
+          taddr = tlane + col0;
+        }
         uint32_t v[32];
-        tmem_ld_32x32(tlane + col0, v);
+        tmem_ld_32x32(taddr, v);
         tmem_ld_wait();
         float f[32];
 #pragma unroll
         for (int t = 0; t < 32; ++t) f[t] = __uint_as_float(v[t]);
-        if (prod == 3) {
+        if (prod == 3) {       // + sum over the sequences that START in this CTA's range of dt_b[row] s_b[n]
           for (int b = bs0; b < bs1; ++b) {
-            const float d = p.dtv[static_cast<long long>(b) * CI + row];
-            const float* sv = p.sfv + static_cast<long long>(b) * CC + col0;
+            const float d = p.dtv[static_cast<long long>(b) * CI + srow];
+            const float4* sv = reinterpret_cast<const float4*>(p.sfv + static_cast<long long>(b) * CC + col0);
 #pragma unroll
-            for (int t = 0; t < 32; ++t) f[t] = fmaf(d, sv[t], f[t]);
+            for (int t = 0; t < 8; ++t) {
+              const float4 s4 = sv[t];
+              f[4 * t] = fmaf(d, s4.x, f[4 * t]);
+              f[4 * t + 1] = fmaf(d, s4.y, f[4 * t + 1]);
+              f[4 * t + 2] = fmaf(d, s4.z, f[4 * t + 2]);
+              f[4 * t + 3] = fmaf(d, s4.w, f[4 * t + 3]);
+            }
           }
         }
-        float4* dst = reinterpret_cast<float4*>(out + row * 256 + col0);
+        float4* dst = reinterpret_cast<float4*>(stg + srow * PITCH + col0 * 4);
 #pragma unroll
         for (int t = 0; t < 8; ++t) dst[t] = make_float4(f[4 * t], f[4 * t + 1], f[4 * t + 2], f[4 * t + 3]);
       }
+      named_bar_sync(1, 256);
+      // 128 staged rows x ncol floats -> global rows [pass * 128, +128) of the partial
+      const int v4_per_row = ncol / 4;
+      float* obase = out + static_cast<long long>(pass) * 128 * ncol;
+      for (int idx = tid; idx < 128 * v4_per_row; idx += 256) {
+        const int r_ = idx / v4_per_row, c4 = idx - r_ * v4_per_row;
+        *reinterpret_cast<float4*>(obase + static_cast<long long>(r_) * ncol + c4 * 4) =
+            *reinterpret_cast<const float4*>(stg + r_ * PITCH + c4 * 16);
+      }
+      named_bar_sync(1, 256);
     }
+    (void)nrow;
     if (tid < 128) out[128 * 256 + tid] = (prod == 1) ? 0.f : v_bias[tid];
+    if (tid == 0) WG_TRACE(4);
   }
   tc_fence_before();
   __syncthreads();
@@ -290,10 +357,13 @@ int gram_wgrad(const bf16* Wp, const bf16* dQa, const bf16* dWp, const bf16* Mb,
   if (num_sms > 160) num_sms = 160;
   // CTAs per product in proportion to its K slabs (theta 4, z 2, g 2, phi 4 per sequence), at least one, at most one
   // per slab
+  // (CTA shares 4 : 2 : 2 : 5 — the phi product also forms dt s^T in its epilogue and streams S~ from HBM, measured with
+  //  GLF_WGRAD_TRACE: with equal shares per slab its CTAs finished 30 % after the theta / g ones)
   const int w[4] = {4, 2, 2, 4};
+  const int share[4] = {4, 2, 2, 5};
   int n[4], used = 0;
   for (int i = 0; i < 4; ++i) {
-    long long c = static_cast<long long>(num_sms) * w[i] / 12;
+    long long c = static_cast<long long>(num_sms) * share[i] / 13;
     const long long slabs = static_cast<long long>(w[i]) * B;
     if (c > slabs) c = slabs;
     if (c < 1) c = 1;
@@ -306,6 +376,10 @@ int gram_wgrad(const bf16* Wp, const bf16* dQa, const bf16* dWp, const bf16* Mb,
   }
   WgradParams p;
   p.B = B; p.N = N;
+  {
+    const char* tr = getenv("GLF_WGRAD_TRACE");
+    p.trace = (tr && tr[0] == '1') ? 1 : 0;
+  }
   p.cta0[0] = 0;
   for (int i = 0; i < 4; ++i) p.cta0[i + 1] = p.cta0[i] + n[i];
   p.dcv = dcv; p.tv = tv; p.dtv = dtv; p.sfv = sfv;
@@ -314,6 +388,14 @@ int gram_wgrad(const bf16* Wp, const bf16* dQa, const bf16* dWp, const bf16* Mb,
   if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(wgrad)");
   wgrad_kernel<<<p.cta0[4], WG_THREADS, WG_SMEM, stream>>>(tmWp, tmdQ, tmdWp, tmM, tmdM, tmT, tmdT, tmS, p);
   GLF_TRY_RC(check_cuda(cudaGetLastError(), "wgrad launch"));
+  if (p.trace) {
+    long long t[4][8];
+    cudaStreamSynchronize(stream);
+    cudaMemcpyFromSymbol(t, g_wgrad_trace, sizeof(t));
+    for (int i = 0; i < 4; ++i)
+      fprintf(stderr, "wgrad trace product %d (%d CTAs): mma issued %lld, simt loop done %lld, accumulator ready %lld, partial written %lld cycles after the prologue\n",
+              i, n[i], t[i][1] - t[i][0], t[i][2] - t[i][0], t[i][3] - t[i][0], t[i][4] - t[i][0]);
+  }
   const int total = 4 * (128 * 256 + 128);
   wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(part, p.cta0[0], p.cta0[1], p.cta0[2], p.cta0[3],
                                                               p.cta0[4], g->theta_w, g->theta_b, g->wz_w, g->g_w,
