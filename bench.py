@@ -581,9 +581,9 @@ def gram_probe(dev, clips, C, pk):
 
 
 def dx_gemm_probe(dev, clips, C, pk):
-    """The largest tile-GEMM launch of the step, timed alone: dX_b = [dV_b | X_b] [E_b ; F_b] + e_b + dV_b (K = 2C, per
-    sequence B operand, residual addend = the first half of the A operand, 256-row CTA super-tiles).  HBM-bound at
-    C = 256: reads dV and X, writes dX = 3 bf16 passes over [rows, C]."""
+    """The largest tile-GEMM launch of the step, timed alone: dX_b = [dV_b | X_b] [E'_b ; F_b] + e_b (K = 2C, per-sequence
+    MN-major B operand, E' = k1 Q + I carries the residual dV; 256 x 256 tiles on CTA pairs, tcgen05.mma.cta_group::2,
+    glf_gemm2.cu).  HBM-bound at C = 256: reads dV and X, writes dX = 3 bf16 passes over [rows, C]."""
     import ctypes as Ct
     from glfusion_b200 import _lib as L
     lib = L.load()
@@ -595,8 +595,9 @@ def dx_gemm_probe(dev, clips, C, pk):
     stream = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def launch():
+        # (no addend: the residual dV is folded into the first operand, E' = E + I, glf_chain.cu)
         L.check(lib.glf_gemm_bf16(L.ptr(A), L.ptr(Bm), L.ptr(D), N, C, 2 * C, B, 0, 1, 2 * C, C, C, N * 2 * C,
-                                  C * 2 * C, N * C, L.ptr(bias), 1.0, L.ptr(A), 2 * C, N * 2 * C, 0, 1, None, stream))
+                                  C * 2 * C, N * C, L.ptr(bias), 1.0, None, 2 * C, N * 2 * C, 0, 1, None, stream))
     for _ in range(3):
         launch()
     torch.cuda.synchronize()
@@ -616,7 +617,7 @@ def dx_gemm_probe(dev, clips, C, pk):
         t = json.load(open(tp)).get("gemm_dx", {})
         if t.get("rows") == B * N and t.get("C") == C:
             traffic = int(t["traffic_bytes"])
-    return {"bound": "hbm", "kernel": "gemm_kernel<0,1,128,2> (dX = [dV | X][E ; F] + e + dV, K = 2C)",
+    return {"bound": "hbm", "kernel": "gemm_pair_kernel<1> (dX = [dV | X][E' ; F] + e, K = 2C, cta_group::2)",
             "achieved": round(ach, 1), "peak": pk["hbm_gbs"], "peak_source": pk["source"], "unit": "GB/s",
             "frac": round(ach / pk["hbm_gbs"], 4), "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
             "ms_per_launch": round(ms, 4), "inputs": "617 MB per launch, larger than the 126 MB L2"}

@@ -620,6 +620,13 @@ int make_output_map(CUtensorMap* tm, void* D, int M, int N, int batch, long long
 
 }  // namespace
 
+int make_operand_tmap(CUtensorMap* tm, const GemmOperand& op, int rows, int K, int batch, int nlimbs, int box_rows) {
+  return make_operand_map(tm, op, rows, K, batch, nlimbs, box_rows);
+}
+int make_output_tmap(CUtensorMap* tm, void* D, int M, int N, int batch, long long ldd, long long strideD) {
+  return make_output_map(tm, D, M, N, batch, ldd, strideD);
+}
+
 // bf16 tensor map over [batch][outer][inner] with row pitch `ld` elements, SWIZZLE_128B, box {64, box_outer, 1, 1}
 int make_tmap_bf16(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long batch, long long ld,
                    long long batch_stride, int box_outer) {
@@ -716,6 +723,8 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
       cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0)
     return set_error(GLF_ERR_DEVICE, "gemm: cannot query the SM count");
   const bool amn = a.A.mn_major != 0, bmn = a.B.mn_major != 0;
+  // the big K-major products with N = 256 (U, dX of the Gram form) run on CTA pairs (glf_gemm2.cu)
+  if (gemm_pair_applicable(a, num_sms)) return gemm_pair(a, num_sms, stream);
   // GLF_GEMM_WIDE2=1 (or bn_hint = 512): 256 x 256 CTA tiles for N == 256 (one n-tile: the A operand crosses the
   // L2 -> SM fabric once, the B operand once per 256 rows)
   bool wide2 = !amn && a.N == 256 && a.rowsum == nullptr && a.M >= 1024 && a.split_k <= 1;

@@ -48,6 +48,13 @@ struct GemmArgs {
 };
 int gemm(const GemmArgs& a, cudaStream_t stream);
 inline int gemm_tiles_m(int M) { return (M + 127) / 128; }
+// (glf_gemm.cu) operand map: K-major -> dims {K, rows, batch, limb}, MN-major -> {rows, K, batch, limb}; SWIZZLE_128B,
+// box {64, box_rows or 64}.  Output map: dims {N, M, batch}, box {32, 32}, SWIZZLE_64B (the epilogue's staging tile).
+int make_operand_tmap(CUtensorMap* tm, const GemmOperand& op, int rows, int K, int batch, int nlimbs, int box_rows);
+int make_output_tmap(CUtensorMap* tm, void* D, int M, int N, int batch, long long ldd, long long strideD);
+// (glf_gemm2.cu) the big K-major products with N = 256 on CTA pairs (cta_group::2); false = not applicable / disabled
+bool gemm_pair_applicable(const GemmArgs& a, int num_sms);
+int gemm_pair(const GemmArgs& a, int num_sms, cudaStream_t stream);
 int make_tmap_bf16(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long batch, long long ld,
                    long long batch_stride, int box_outer);
 
