@@ -176,6 +176,13 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
       const uint32_t use = static_cast<uint32_t>(local >> 1);
       const float* biasb = p.bias != nullptr ? p.bias + static_cast<long long>(b) * p.bias_stride : nullptr;
       const int rows_valid = min(32, p.M - (m0 + q * 32));
+      // this warp's two bias slices are fetched BEFORE the wait for the accumulator: the global-load latency hides
+      // behind the tile's MMAs
+      float bpre0 = 0.f, bpre1 = 0.f;
+      if (biasb != nullptr) {
+        bpre0 = biasb[nt * BN2 + cc0 * 32 + lane];
+        bpre1 = biasb[nt * BN2 + (cc0 + 4) * 32 + lane];
+      }
       mbar_wait(smem_u32(&tmem_full_bar[acc]), use & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN2 + (static_cast<uint32_t>(q * 32) << 16);
@@ -185,7 +192,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
         const int gc0 = nt * BN2 + c * 32;
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
-        if (biasb != nullptr) wbias[lane] = biasb[gc0 + lane];
+        if (biasb != nullptr) wbias[lane] = ci == 0 ? bpre0 : bpre1;
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();

@@ -225,20 +225,16 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
         emit_colsum(row, __uint_as_float(sv[mt * 16]));
       }
       const uint32_t taddr = tmem_base + mt * p.C + (static_cast<uint32_t>(q * 32) << 16);
-      // symmetric S: rows 128..255 hold only columns 128..255 in TMEM; rows 0..127 also leave their columns 128..255
-      // TRANSPOSED in the (now idle) ring, [128 columns][128 rows] bf16 with a 272-byte pitch, for the mirror below
-      constexpr uint32_t SYM_PITCH = 272;
+      // ksplit == 1: the bf16 rows are staged in the (now idle) ring, row pitch 528 bytes (= Ca of C = 256: successive
+      // rows are four banks apart), and leave with coalesced 16-byte stores below: a row per thread straight from
+      // registers touched 32 lines per store instruction.  Symmetric S: rows 128..255 hold only columns 128..255 in
+      // TMEM; rows 0..127 also write their columns 128..255 TRANSPOSED into the staged rows 128..255 (the mirror).
+      constexpr uint32_t STG_PITCH = 528;
+      uint8_t* stg = const_cast<uint8_t*>(smem_gen);
       for (int c = (p.sym && mt == 1) ? 4 : 0; c < p.C / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         tmem_ld_wait();
-        if (p.sym && mt == 0 && c >= 4) {
-          uint8_t* stg = const_cast<uint8_t*>(smem_gen) + (row & 127) * 2;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            *reinterpret_cast<bf16*>(stg + static_cast<uint32_t>((c - 4) * 32 + j) * SYM_PITCH) =
-                __float2bfloat16(__uint_as_float(v[j]));
-        }
         if (p.ksplit > 1) {
           float* dst = p.outf + (static_cast<long long>(b) * p.C + row) * p.C + c * 32;
 #pragma unroll
@@ -247,25 +243,45 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
                          "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
                          : "memory");
         } else {
-          bf16* dst = p.out + (static_cast<long long>(b) * p.Ca + row) * p.Ca + c * 32;
+          uint8_t* dst = stg + static_cast<uint32_t>(row) * STG_PITCH + c * 64;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 pk = make_uint4(pack_bf16(rsc * __uint_as_float(v[8 * j]), rsc * __uint_as_float(v[8 * j + 1])),
                                         pack_bf16(rsc * __uint_as_float(v[8 * j + 2]), rsc * __uint_as_float(v[8 * j + 3])),
                                         pack_bf16(rsc * __uint_as_float(v[8 * j + 4]), rsc * __uint_as_float(v[8 * j + 5])),
                                         pack_bf16(rsc * __uint_as_float(v[8 * j + 6]), rsc * __uint_as_float(v[8 * j + 7])));
-            *reinterpret_cast<uint4*>(dst + 8 * j) = pk;
+            *reinterpret_cast<uint4*>(dst + 16 * j) = pk;
+          }
+          if (p.sym && mt == 0 && c >= 4) {
+            uint8_t* tdst = stg + row * 2;          // element (col, row) of the staged matrix, col = 32 c + j >= 128
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              *reinterpret_cast<bf16*>(tdst + static_cast<uint32_t>(c * 32 + j) * STG_PITCH) =
+                  __float2bfloat16(__uint_as_float(v[j]));
           }
         }
       }
-      if (p.sym) {
-        named_bar_sync(1, 256);
-        if (mt == 1) {        // S[128 + i][0..127] = S[0..127][128 + i]: row i of the transposed staging tile
-          const uint8_t* src = smem_gen + static_cast<uint32_t>(q * 32 + lane) * SYM_PITCH;
-          bf16* dst = p.out + (static_cast<long long>(b) * p.Ca + row) * p.Ca;
+    }
+    if (p.ksplit == 1 && p.C == 256) {
+      named_bar_sync(1, 256);
+      // 256 rows x 512 bytes -> global rows of pitch Ca; a warp moves one row per iteration
+      uint8_t* gout = reinterpret_cast<uint8_t*>(p.out + static_cast<long long>(b) * p.Ca * p.Ca);
+      const uint8_t* stg = smem_gen;
 #pragma unroll 4
-          for (int j = 0; j < 16; ++j) *reinterpret_cast<uint4*>(dst + 8 * j) = *reinterpret_cast<const uint4*>(src + 16 * j);
-        }
+      for (int it = 0; it < 32; ++it) {
+        const int r = it * 8 + (warp - 2);
+        *reinterpret_cast<uint4*>(gout + static_cast<long long>(r) * p.Ca * 2 + lane * 16) =
+            *reinterpret_cast<const uint4*>(stg + static_cast<uint32_t>(r) * 528u + lane * 16);
+      }
+    } else if (p.ksplit == 1) {
+      named_bar_sync(1, 256);
+      // C = 128: 128 rows x 256 bytes
+      uint8_t* gout = reinterpret_cast<uint8_t*>(p.out + static_cast<long long>(b) * p.Ca * p.Ca);
+      const uint8_t* stg = smem_gen;
+      for (int idx = t; idx < 128 * 16; idx += 256) {
+        const int r = idx >> 4, ch = idx & 15;
+        *reinterpret_cast<uint4*>(gout + static_cast<long long>(r) * p.Ca * 2 + ch * 16) =
+            *reinterpret_cast<const uint4*>(stg + static_cast<uint32_t>(r) * 528u + ch * 16);
       }
     }
   }
