@@ -16,12 +16,13 @@ PRECISION_BF16, PRECISION_F32X3 = 0, 1
 PRECISIONS = {"bf16": PRECISION_BF16, "fp32": PRECISION_F32X3}
 
 EXPORTS = ("glf_version", "glf_last_error", "glf_tpavi_sizes", "glf_tpavi_fwd", "glf_tpavi_bwd",
-           "glf_gate_concat_fwd", "glf_gate_concat_bwd", "glf_gemm_bf16", "glf_transpose", "glf_bn_res_ln_fwd",
+           "glf_gate_concat_fwd", "glf_gate_concat_bwd", "glf_views_to_tokens", "glf_gemm_bf16", "glf_transpose", "glf_bn_res_ln_fwd",
            "glf_bn_res_ln_bwd", "glf_bn_res_ln_bwd_max_blocks", "glf_gate_concat_bwd_scratch_bytes",
            "glf_fusion_ln_supported", "glf_fusion_ln_fwd", "glf_fusion_ln_fwd_parts", "glf_fusion_ln_bwd",
            "glf_bn_res_ln_pair_fwd",
            "glf_bn_res_ln_pair_bwd", "glf_gemm_bf16_ex", "glf_gram_contraction", "glf_p2p_signal_bytes", "glf_p2p_max_floats",
-           "glf_p2p_export", "glf_p2p_open", "glf_p2p_close", "glf_p2p_allreduce")
+           "glf_p2p_export", "glf_p2p_open", "glf_p2p_close", "glf_p2p_allreduce", "glf_spatial_sums",
+           "glf_cycle_loss_scratch_bytes", "glf_cycle_loss")
 
 
 class GlfDesc(C.Structure):
@@ -99,6 +100,11 @@ def load() -> C.CDLL:
         lib.glf_p2p_close.argtypes = [vp, C.c_uint64]
         lib.glf_p2p_allreduce.argtypes = [pp, pp, i32, i32, i64, f32, vp]
         lib.glf_transpose.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+        lib.glf_spatial_sums.argtypes = [vp, i32, i32, i32, i32, i64, i64, i64, vp, vp]
+        lib.glf_cycle_loss_scratch_bytes.argtypes = [i32, i32, i32]
+        lib.glf_cycle_loss_scratch_bytes.restype = C.c_size_t
+        lib.glf_cycle_loss.argtypes = [vp, i32, i32, i32, i32, i32, f32, i32, i32, i32, i32, f32, vp, vp, vp, vp]
+        lib.glf_views_to_tokens.argtypes = [i32, i32, i32, i32, i32, pp, vp, vp, vp, vp, vp]
         lib.glf_bn_res_ln_fwd.argtypes = [i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, f32, i32, vp]
         lib.glf_bn_res_ln_bwd.argtypes = [i64, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                           C.POINTER(C.c_int), vp]

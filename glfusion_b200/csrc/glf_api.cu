@@ -1069,6 +1069,20 @@ GLF_API size_t glf_gate_concat_bwd_scratch_bytes(int B, int C, int V, int h, int
   return gate_bwd_scratch_bytes(B, C, V, h, w);
 }
 
+GLF_API int glf_views_to_tokens(int B, int C, int V, int T, int src_dtype, const void* const* src,
+                                const int64_t* stride_b, const int64_t* stride_c, const int64_t* stride_t, void* out,
+                                glf_stream_t stream) {
+  GLF_TRY(check_device_sm100());
+  if (B <= 0 || C <= 0 || T <= 0) return set_error(GLF_ERR_INVALID, "views_to_tokens: empty input");
+  if (src == nullptr || stride_b == nullptr || stride_c == nullptr || stride_t == nullptr)
+    return set_error(GLF_ERR_INVALID, "views_to_tokens: NULL table");
+  GLF_TRY(check_ptr(out, "out"));
+  static_assert(sizeof(long long) == sizeof(int64_t), "stride tables are passed through unchanged");
+  return views_to_tokens(B, C, V, T, src_dtype, src, reinterpret_cast<const long long*>(stride_b),
+                         reinterpret_cast<const long long*>(stride_c), reinterpret_cast<const long long*>(stride_t), out,
+                         reinterpret_cast<cudaStream_t>(stream));
+}
+
 GLF_API size_t glf_p2p_signal_bytes(int world) { return p2p_signal_bytes(world); }
 GLF_API int64_t glf_p2p_max_floats(void) { return p2p_max_floats(); }
 GLF_API int glf_p2p_export(const void* ptr, unsigned char handle[64], uint64_t* offset) {
@@ -1212,6 +1226,30 @@ GLF_API int glf_bn_res_ln_pair_bwd(int64_t rows, int C, const void* dZ, const vo
                     reinterpret_cast<const bf16* const*>(X), bn_a, bn_b, ln_w, bn_mean, bn_rstd, mu, r,
                     reinterpret_cast<bf16* const*>(dV), part, rows, C, nblocks_out,
                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+GLF_API size_t glf_cycle_loss_scratch_bytes(int T, int C, int n_starts) {
+  if (T <= 0 || C <= 0 || n_starts <= 0) return 0;
+  return cycle_loss_scratch_bytes(T, C, n_starts);
+}
+
+GLF_API int glf_cycle_loss(const float* feat, int T, int C, int target_region, int cyc_off, int chunk_size,
+                           float temperature, int start, int step, int n_starts, int soft_label, float scale,
+                           float* loss, float* dfeat, void* scratch, glf_stream_t stream) {
+  GLF_TRY(check_device_sm100());
+  GLF_TRY(check_ptr(feat, "feat"));
+  GLF_TRY(check_ptr(loss, "loss"));
+  GLF_TRY(check_ptr(dfeat, "dfeat"));
+  GLF_TRY(check_ptr(scratch, "scratch"));
+  return cycle_loss(feat, T, C, target_region, cyc_off, chunk_size, temperature, start, step, n_starts, soft_label,
+                    scale, loss, dfeat, reinterpret_cast<float*>(scratch), reinterpret_cast<cudaStream_t>(stream));
+}
+
+GLF_API int glf_spatial_sums(const void* x, int dtype, int B, int C, int T, int64_t stride_b, int64_t stride_c,
+                             int64_t stride_t, float* out, glf_stream_t stream) {
+  GLF_TRY(check_device_sm100());
+  if (x == nullptr || out == nullptr) return set_error(GLF_ERR_INVALID, "spatial_sums: NULL pointer");   // any element alignment
+  return spatial_sums(x, dtype, B, C, T, stride_b, stride_c, stride_t, out, reinterpret_cast<cudaStream_t>(stream));
 }
 
 GLF_API int glf_transpose(const void* in, void* out, int batch, int R, int S, int in_dtype, int out_dtype,

@@ -488,7 +488,135 @@ int launch_gate_bwd(dim3 grid, bool vec2, int io_dtype, const ViewPtrs& vp, cons
   return check_cuda(cudaGetLastError(), "gate_concat_bwd launch");
 }
 
+// ---------------------------------------------------------------------------------------------- views -> tokens
+// The dict-keyed call site hands the backward one gradient per view ([B, C, h, w], NCHW or channels-last strides);
+// the blocks want ONE token-major [B, V, h*w, C] bf16 buffer (the layout ours.py:1819-1820 builds forward).  One
+// 64 x 64 tile per CTA; NCHW sources are transposed through shared memory, channels-last sources are row copies.
+struct ViewsToTokens {
+  const void* src[8];
+  long long sb[8], sc[8], st[8];       // element strides of batch / channel / token (= h*w collapsed)
+  int present[8];
+  int vec[8];                          // channels-last source whose rows can be read 16 bytes at a time
+};
+
+template <typename TIn>
+__device__ __forceinline__ float ld_as_float(const TIn* p);
+template <> __device__ __forceinline__ float ld_as_float<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ld_as_float<bf16>(const bf16* p) { return __bfloat162float(*p); }
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) views_to_tokens_kernel(ViewsToTokens P, bf16* __restrict__ out, int V, int C,
+                                                              int T) {
+  __shared__ float tile[64][65];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tiles_c = C / 64;
+  const int t0 = (blockIdx.x / tiles_c) * 64, c0 = (blockIdx.x % tiles_c) * 64;
+  const int v = blockIdx.y, b = blockIdx.z;
+  bf16* o = out + ((static_cast<long long>(b) * V + v) * T) * C;
+  if (!P.present[v]) {                                       // a view without a gradient contributes zeros
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = t0 + ty + 8 * i;
+      if (t < T) *reinterpret_cast<__nv_bfloat162*>(o + static_cast<long long>(t) * C + c0 + 2 * tx) = __floats2bfloat162_rn(0.f, 0.f);
+    }
+    return;
+  }
+  const TIn* src = reinterpret_cast<const TIn*>(P.src[v]) + b * P.sb[v];
+  const long long sc = P.sc[v], st = P.st[v];
+  if (sc == 1) {                                             // channels-last: rows of C contiguous elements
+    if (P.vec[v]) {                                          // 16-byte accesses: 8 channels per thread, loads first
+      float f[2][8];
+      int tt[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int item = threadIdx.x + 256 * i;
+        tt[i] = t0 + (item >> 3);
+        const TIn* r = src + tt[i] * st + c0 + 8 * (item & 7);
+        if (tt[i] < T) {
+          if constexpr (sizeof(TIn) == 2) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(r));
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float2 p = __bfloat1622float2(h2[j]); f[i][2 * j] = p.x; f[i][2 * j + 1] = p.y; }
+          } else {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(r)), b4 = __ldg(reinterpret_cast<const float4*>(r) + 1);
+            f[i][0] = a.x; f[i][1] = a.y; f[i][2] = a.z; f[i][3] = a.w;
+            f[i][4] = b4.x; f[i][5] = b4.y; f[i][6] = b4.z; f[i][7] = b4.w;
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (tt[i] < T) {
+          uint4 q;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(f[i][2 * j], f[i][2 * j + 1]);
+          *reinterpret_cast<uint4*>(o + static_cast<long long>(tt[i]) * C + c0 + 8 * ((threadIdx.x + 256 * i) & 7)) = q;
+        }
+      }
+      return;
+    }
+    float lo[8], hi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = t0 + ty + 8 * i;
+      const TIn* r = src + t * st + c0 + 2 * tx;
+      lo[i] = t < T ? ld_as_float<TIn>(r) : 0.f;
+      hi[i] = t < T ? ld_as_float<TIn>(r + 1) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = t0 + ty + 8 * i;
+      if (t < T) *reinterpret_cast<__nv_bfloat162*>(o + static_cast<long long>(t) * C + c0 + 2 * tx) = __floats2bfloat162_rn(lo[i], hi[i]);
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {                              // NCHW: coalesced along tokens, transposed on the way out
+    const int c = ty + 8 * i;
+    const TIn* r = src + (c0 + c) * sc;
+    const int ta = t0 + tx, tb = t0 + 32 + tx;
+    tile[c][tx] = ta < T ? ld_as_float<TIn>(r + ta * st) : 0.f;
+    tile[c][32 + tx] = tb < T ? ld_as_float<TIn>(r + tb * st) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int tl = ty + 8 * i, t = t0 + tl;
+    if (t < T)
+      *reinterpret_cast<__nv_bfloat162*>(o + static_cast<long long>(t) * C + c0 + 2 * tx) =
+          __floats2bfloat162_rn(tile[2 * tx][tl], tile[2 * tx + 1][tl]);
+  }
+}
+
 }  // namespace
+
+int views_to_tokens(int B, int C, int V, int T, int src_dtype, const void* const* src, const long long* sb,
+                    const long long* sc, const long long* st, void* out, cudaStream_t stream) {
+  if (V < 1 || V > 8) return set_error(GLF_ERR_INVALID, "views_to_tokens: V must be 1..8");
+  if (C % 64 != 0) return set_error(GLF_ERR_UNSUPPORTED, "views_to_tokens: C %% 64 != 0");
+  if (B > 65535) return set_error(GLF_ERR_UNSUPPORTED, "views_to_tokens: B > 65535");
+  ViewsToTokens P;
+  for (int v = 0; v < 8; ++v) {
+    const bool on = v < V && src[v] != nullptr;
+    P.src[v] = on ? src[v] : nullptr;
+    P.sb[v] = on ? sb[v] : 0; P.sc[v] = on ? sc[v] : 0; P.st[v] = on ? st[v] : 0;
+    P.present[v] = on ? 1 : 0;
+    const long long per16 = src_dtype == GLF_DTYPE_BF16 ? 8 : 4;
+    P.vec[v] = on && sc[v] == 1 && reinterpret_cast<uintptr_t>(src[v]) % 16 == 0 && sb[v] % per16 == 0 && st[v] % per16 == 0;
+    if (on && sc[v] != 1 && st[v] != 1)
+      return set_error(GLF_ERR_UNSUPPORTED, "views_to_tokens: a view needs unit channel or unit token stride");
+  }
+  const dim3 grid(((T + 63) / 64) * (C / 64), V, B);
+  if (src_dtype == GLF_DTYPE_BF16)
+    views_to_tokens_kernel<bf16><<<grid, 256, 0, stream>>>(P, reinterpret_cast<bf16*>(out), V, C, T);
+  else if (src_dtype == GLF_DTYPE_F32)
+    views_to_tokens_kernel<float><<<grid, 256, 0, stream>>>(P, reinterpret_cast<bf16*>(out), V, C, T);
+  else
+    return set_error(GLF_ERR_INVALID, "views_to_tokens: bad dtype");
+  return check_cuda(cudaGetLastError(), "views_to_tokens launch");
+}
 
 int gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, int x_dtype,
                     const void* const* f4, const float* const* cls, const float* const* ctr, void* xg, void* xl,

@@ -150,6 +150,20 @@ int gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, i
                     const void* dxg, const void* dxl, void* const* df4, float* const* dcls, float* const* dctr,
                     float* da_part, cudaStream_t stream);
 size_t gate_bwd_scratch_bytes(int B, int C, int V, int h, int w);
+// per-view [B,C,h,w] tensors (element strides sb / sc / st of batch, channel, collapsed h*w) -> token-major
+// [B, V, T, C] bf16; a NULL view is written as zeros
+int views_to_tokens(int B, int C, int V, int T, int src_dtype, const void* const* src, const long long* sb,
+                    const long long* sc, const long long* st, void* out, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------ cycle step
+// (glf_cycle.cu) the consumer of the MGFM output: per-view spatial sums (R/main.py:229) and the cycle-consistency
+// loss with its gradient (R/main.py:650-798), n_starts start positions start, start+step, ...
+size_t cycle_loss_scratch_bytes(int T, int C, int n_starts);
+int cycle_loss(const float* feat, int T, int C, int R, int off, int ch, float temperature, int start, int step,
+               int n_starts, int soft_label, float scale, float* loss, float* dfeat, float* scratch,
+               cudaStream_t stream);
+int spatial_sums(const void* x, int dtype, int B, int C, int T, long long sb, long long sc, long long st, float* out,
+                 cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------ softmax attention
 // mode='embedded' (ours.py:896-897,902): Y = softmax(Theta Phi^T) G, flash-style, per batch entry.

@@ -13,7 +13,7 @@ LayerNorm epilogue accumulates into the first one's output (the `+` of ours.py:1
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Sequence
+from typing import Dict, List, Optional, Sequence
 
 import torch
 from torch import nn
@@ -70,6 +70,39 @@ def gate_concat_forward(f4: Sequence[torch.Tensor], cls: Sequence[torch.Tensor],
                                         L.ptr_table(cls), L.ptr_table(ctr), L.ptr(xg), L.ptr(xl), L.ptr(gate),
                                         _stream_ptr()))
     return xg, xl, gate, f4, cls, ctr
+
+
+def views_to_tokens(views: Sequence[Optional[torch.Tensor]], out: torch.Tensor) -> bool:
+    """Gather per-view [B,C,h,w] tensors (NCHW or channels-last strides, bf16 or fp32; None = zeros) into the
+    token-major bf16 buffer `out` [B,V,h,w,C] with one kernel (glf_views_to_tokens) — the inverse of handing the
+    dict-keyed caller one [B,C,h,w] view per key.  Returns False, having done nothing, when the kernel does not cover
+    the case (other dtypes / strides); the caller then copies view by view."""
+    if out.dtype != torch.bfloat16 or not out.is_contiguous():
+        return False
+    B, V, h, w, Cn = out.shape
+    live = [g for g in views if g is not None]
+    if not live or Cn % 64 or V > 8 or B > 65535:
+        return False
+    dt = live[0].dtype
+    if dt not in (torch.bfloat16, torch.float32):
+        return False
+    sb, sc, st = [], [], []
+    for g in views:
+        if g is None:
+            sb.append(0); sc.append(0); st.append(0)
+            continue
+        if g.dtype != dt or tuple(g.shape) != (B, Cn, h, w) or g.device != out.device:
+            return False
+        b_, c_, h_, w_ = g.stride()
+        if h_ != w * w_ or (c_ != 1 and w_ != 1) or min(b_, c_) < 1 or w_ < 0:   # h*w must collapse; one unit stride
+            return False                   # (w_ == 0: the broadcast gradient of a spatial sum, R/main.py:229)
+        sb.append(b_); sc.append(c_); st.append(w_)
+    ptrs = (C.c_void_p * V)(*[None if g is None else g.data_ptr() for g in views])
+    i64 = C.c_int64 * V
+    with torch.cuda.device(out.device):
+        L.check(L.load().glf_views_to_tokens(B, Cn, V, h * w, _io_dtype(live[0]), ptrs, i64(*sb), i64(*sc), i64(*st), L.ptr(out),
+                                             _stream_ptr()))
+    return True
 
 
 def gate_concat_backward(f4, cls, ctr, gate, dxg, dxl, weight: float):
@@ -195,6 +228,8 @@ class _FusionFunction(torch.autograd.Function):
             if all(g is None for g in gs):
                 return None
             buf = torch.empty(xg.shape, dtype=xg.dtype, device=xg.device)
+            if views_to_tokens(gs, buf):
+                return buf
             for v, g in enumerate(gs):
                 if g is None:
                     buf[:, v].zero_()

@@ -163,6 +163,14 @@ GLF_API int glf_gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, flo
                         const void* dxg, const void* dxl, void* const* df4, float* const* dcls, float* const* dctr,
                         void* scratch, glf_stream_t stream);
 
+/* The dict-keyed call site's backward: V per-view gradients ([B, C, h, w]; element strides of batch / channel / the
+ * collapsed h*w axis given per view, one of the last two must be 1: NCHW or channels-last) gathered into ONE
+ * token-major [B, V, T, C] bf16 buffer, the transposition ours.py:1819-1820 performs forward (permute + cat).  A NULL
+ * entry of `src` (a view whose output received no gradient) is written as zeros.  C % 64 == 0, V <= 8. */
+GLF_API int glf_views_to_tokens(int B, int C, int V, int T, int src_dtype, const void* const* src,
+                        const int64_t* stride_b, const int64_t* stride_c, const int64_t* stride_t, void* out,
+                        glf_stream_t stream);
+
 /* ---- data-parallel gradient exchange (replaces nn.DataParallel's reduce onto GPU 0, R/main.py:155) ----------------
  * One kernel over NVLink / NVSwitch peer memory: every rank (one process per GPU) keeps its flat fp32 gradient bucket
  * in a device allocation that the other ranks have opened through CUDA IPC, preceded by a zero-initialised signal pad
@@ -237,6 +245,22 @@ GLF_API int glf_bn_res_ln_pair_bwd(int64_t rows, int C, const void* dZ, const vo
                            const float* const* bn_rstd, const float* const* ln_w, const float* const* mu,
                            const float* const* r, void* const* dV, float* const* part, int* nblocks_out,
                            glf_stream_t stream);
+
+/* ---- the cycle-consistency step that consumes the MGFM output (R/main.py:229-235) ---------------------------------
+ * glf_spatial_sums: out[b, c] = sum_t x[b, c, t] (fp32) for one view [B, C, h*w] given by element strides — replaces
+ *   cyc_feat_out[view].sum(dim=(2, 3)) (R/main.py:229); channels-last views (stride_c == 1, what the fusion path
+ *   returns) are read coalesced along C.
+ * glf_cycle_loss: Trainer.seg_cycle (R/main.py:650-717: n_starts = 1, start = the np.random.choice draw, scale = 1)
+ *   and Trainer.dense_seg_cycle (R/main.py:719-798: start = 0, step = 1 or chunk_size, n_starts positions, scale =
+ *   1 / (target_region - chunk_size - cyc_off + 1), soft_label as there) on the [T, C] fp32 per-frame features.
+ *   Writes the scalar loss AND d loss / d feat ([T, C] fp32) in the same call: the loss is a scalar, so the autograd
+ *   backward is grad_output * dfeat.  scratch: glf_cycle_loss_scratch_bytes(T, C, n_starts) bytes.  Deterministic. */
+GLF_API int glf_spatial_sums(const void* x, int dtype, int B, int C, int T, int64_t stride_b, int64_t stride_c,
+                     int64_t stride_t, float* out, glf_stream_t stream);
+GLF_API size_t glf_cycle_loss_scratch_bytes(int T, int C, int n_starts);
+GLF_API int glf_cycle_loss(const float* feat, int T, int C, int target_region, int cyc_off, int chunk_size,
+                   float temperature, int start, int step, int n_starts, int soft_label, float scale, float* loss,
+                   float* dfeat, void* scratch, glf_stream_t stream);
 
 /* out[b, s, r] = in[b, r, s] with dtype conversion (NCTHW <-> token-major packing). dtypes: GLF_DTYPE_*. */
 GLF_API int glf_transpose(const void* in, void* out, int batch, int R, int S, int in_dtype, int out_dtype,

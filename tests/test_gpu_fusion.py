@@ -314,3 +314,33 @@ def test_forward_parts_combined_segmentation_and_cycle_gradients():
         for k, p in mod.named_parameters():
             if not k.startswith("align_channel") and k != "W_z.0.bias":
                 assert_close("grad:" + k, p.grad, ref[k].grad, grad_tol(k), abs_floor=1e-3)
+
+
+@pytest.mark.parametrize("h,w,Cn", [(28, 28, 256), (5, 7, 64), (3, 33, 128)])
+@pytest.mark.parametrize("src", [torch.bfloat16, torch.float32])
+def test_views_to_tokens_is_the_per_view_transposition(h, w, Cn, src):
+    """The dict-keyed backward gathers one gradient per view into the token-major stack (the transposition
+    ours.py:1819-1820 builds forward with permute + cat).  Bit-exact: it is a copy with one round-to-nearest cast."""
+    from glfusion_b200.fusion import views_to_tokens
+    B, V = 3, 4
+    gen = torch.Generator(device="cpu").manual_seed(11)
+    views = [torch.randn(B, Cn, h, w, generator=gen).to(DEV).to(src) for _ in range(V)]
+    views[1] = views[1].contiguous(memory_format=torch.channels_last)            # channels-last strides
+    big = torch.randn(B, V, h, w, Cn, generator=gen).to(DEV).to(src)
+    views[2] = big[:, 2].permute(0, 3, 1, 2)                                      # a view into a token-major stack
+    views[3] = None                                                               # an output nobody differentiated
+    if Cn == 128:                                                                 # the gradient of .sum((2, 3)): a broadcast
+        views[0] = torch.randn(B, Cn, 1, 1, generator=gen).to(DEV).to(src).expand(B, Cn, h, w)
+    if Cn == 64:                                                                  # rows that are not 16-byte aligned
+        odd = torch.randn(B, h, w, Cn + 1, generator=gen).to(DEV).to(src)
+        views[0] = odd[..., 1:].permute(0, 3, 1, 2)
+    out = torch.full((B, V, h, w, Cn), 7.0, dtype=torch.bfloat16, device=DEV)
+    assert views_to_tokens(views, out)
+    for v, g in enumerate(views):
+        want = torch.zeros(B, h, w, Cn, device=DEV) if g is None else g.permute(0, 2, 3, 1).float()
+        assert torch.equal(out[:, v].float(), want.to(torch.bfloat16).float()), v
+    # cases the kernel does not take are reported, not mangled
+    assert not views_to_tokens([v.half() if v is not None else None for v in views], out)
+    assert not views_to_tokens([None] * V, out)
+    if w > 1:
+        assert not views_to_tokens([views[0].transpose(2, 3).contiguous().transpose(2, 3)] + views[1:], out)   # h-major
