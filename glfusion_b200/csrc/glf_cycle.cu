@@ -23,7 +23,7 @@ namespace glf {
 
 namespace {
 
-constexpr int CY_THREADS = 256;
+constexpr int CY_THREADS = 1024;
 constexpr int CY_WARPS = CY_THREADS / 32;
 constexpr int CY_MAXPOS = 1024;          // upper bound on the key / query position counts (shared-memory vectors)
 
@@ -92,12 +92,18 @@ __global__ void __launch_bounds__(CY_THREADS) cycle_start_kernel(CycleParams P) 
   }
   __syncthreads();
   // w_j = sum_i beta_i K[off+i+j] (main.py:685-693)
-  for (int c = tid; c < C; c += CY_THREADS)
-    for (int j = 0; j < ch; ++j) {
-      float acc = 0.f;
-      for (int i = 0; i < Lk; ++i) acc = fmaf(beta[i], K[static_cast<long long>(off + i + j) * C + c], acc);
-      w[j * C + c] = acc;
+  for (int it = tid; it < ch * C; it += CY_THREADS) {        // one (j, c) pair per thread, coalesced along c
+    const int j = it / C, c = it - j * C;
+    const float* kc = K + static_cast<long long>(off + j) * C + c;
+    float a0 = 0.f, a1 = 0.f;
+    int i = 0;
+    for (; i + 1 < Lk; i += 2) {
+      a0 = fmaf(beta[i], kc[static_cast<long long>(i) * C], a0);
+      a1 = fmaf(beta[i + 1], kc[static_cast<long long>(i + 1) * C], a1);
     }
+    if (i < Lk) a0 = fmaf(beta[i], kc[static_cast<long long>(i) * C], a0);
+    w[it] = a0 + a1;
+  }
   __syncthreads();
   // z_m, the loss and d loss / d z (main.py:697-717)
   float bce = 0.f;
@@ -124,21 +130,15 @@ __global__ void __launch_bounds__(CY_THREADS) cycle_start_kernel(CycleParams P) 
     for (int i = 0; i < CY_WARPS; ++i) t += red[i];
     P.loss_part[blockIdx.x] = t / static_cast<float>(Lq);
   }
-  // ---- backward.  Each thread owns channels c, c + 256, ...: every row of its gradient columns is touched by that
-  // thread only, in program order, so the read-modify-writes below need no atomics and the result is deterministic.
-  for (int c = tid; c < C; c += CY_THREADS) {
-    for (int r = 0; r < T; ++r) part[static_cast<long long>(r) * C + c] = 0.f;
-    for (int j = 0; j < ch; ++j) {
-      const float wj = w[j * C + c];
-      float acc = 0.f;
-      for (int m = 0; m < Lq; ++m) {
-        const long long idx = static_cast<long long>(off + m + j) * C + c;
-        const float t = 2.f * a * dz[m] * (feat[idx] - wj);
-        acc += t;
-        part[idx] -= t;
-      }
-      dw[j * C + c] = acc;
-    }
+  // ---- backward, gather form: every gradient row is written once by the thread that owns its channel, from
+  // independent loads (no read-modify-write chains, no atomics; deterministic).
+  //   dw_j = 2a sum_m dz_m (feat[off+m+j] - w_j)
+  for (int it = tid; it < ch * C; it += CY_THREADS) {
+    const int j = it / C, c = it - j * C;
+    const float wj = w[it];
+    float acc = 0.f;
+    for (int m = 0; m < Lq; ++m) acc = fmaf(dz[m], feat[static_cast<long long>(off + m + j) * C + c] - wj, acc);
+    dw[it] = 2.f * a * acc;
   }
   __syncthreads();
   // d beta_i = sum_j <dw_j, K[off+i+j]>
@@ -162,24 +162,43 @@ __global__ void __launch_bounds__(CY_THREADS) cycle_start_kernel(CycleParams P) 
   __syncthreads();
   {
     const float dot = bcast;
-    __syncthreads();
-    for (int i = tid; i < Lk; i += CY_THREADS) dsim[i] = beta[i] * (dsim[i] - dot);
+    for (int i = tid; i < Lk; i += CY_THREADS) dsim[i] = beta[i] * (dsim[i] - dot);     // d sim (softmax backward)
   }
   __syncthreads();
-  for (int c = tid; c < C; c += CY_THREADS) {
-    float* kpart = part + static_cast<long long>(R) * C + c;
-    for (int j = 0; j < ch; ++j) {
-      const float dwj = dw[j * C + c];
-      const float qj = q[static_cast<long long>(j) * C + c];
-      float dq = 0.f;
-      for (int i = 0; i < Lk; ++i) {
-        kpart[static_cast<long long>(off + i + j) * C] += beta[i] * dwj;
-        const float t = 2.f * a * dsim[i] * (K[static_cast<long long>(i + j) * C + c] - qj);
-        kpart[static_cast<long long>(i + j) * C] -= t;
-        dq += t;
+  // one (row, channel) element per thread and step, coalesced along the channels
+  for (int it = tid; it < T * C; it += CY_THREADS) {
+    const int r = it / C, c = it - r * C;
+    const float x = feat[it];
+    float g = 0.f;
+    if (r < R) {
+      // query region:  -2a sum_j dz_{r-off-j} (feat[r] - w_j)   [0 <= r-off-j < Lq]
+      //                + dq_{r-s}   [0 <= r-s < ch],  dq_j = 2a sum_i dsim_i (K[i+j] - q_j)
+      for (int j = 0; j < ch; ++j) {
+        const int m = r - off - j;
+        if (m >= 0 && m < Lq) g = fmaf(-2.f * a * dz[m], x - w[j * C + c], g);
       }
-      part[static_cast<long long>(s + j) * C + c] += dq;
+      const int jq = r - s;
+      if (jq >= 0 && jq < ch) {                              // feat[s + jq] is this row: x = q_jq
+        const float* kc = K + static_cast<long long>(jq) * C + c;
+        float d0 = 0.f, d1 = 0.f;
+        int i = 0;
+        for (; i + 1 < Lk; i += 2) {
+          d0 = fmaf(dsim[i], kc[static_cast<long long>(i) * C] - x, d0);
+          d1 = fmaf(dsim[i + 1], kc[static_cast<long long>(i + 1) * C] - x, d1);
+        }
+        if (i < Lk) d0 = fmaf(dsim[i], kc[static_cast<long long>(i) * C] - x, d0);
+        g = fmaf(2.f * a, d0 + d1, g);
+      }
+    } else {
+      // key region, k = r - R:  sum_j beta_{k-off-j} dw_j  [0 <= k-off-j < Lk]  - 2a sum_j dsim_{k-j} (K[k] - q_j)  [0 <= k-j < Lk]
+      const int k = r - R;
+      for (int j = 0; j < ch; ++j) {
+        const int ib = k - off - j, is = k - j;
+        if (ib >= 0 && ib < Lk) g = fmaf(beta[ib], dw[j * C + c], g);
+        if (is >= 0 && is < Lk) g = fmaf(-2.f * a * dsim[is], x - q[static_cast<long long>(j) * C + c], g);
+      }
     }
+    part[it] = g;
   }
 }
 

@@ -117,11 +117,24 @@ def parts_section(out):
         zero()
         fus, glob, _ = f.forward_parts(dict(zip(keys, f4)), dict(zip(keys, cl)), dict(zip(keys, ct)), need_local=False)
         sum((glob[k].float().sum(dim=(2, 3)) * dsum).sum() for k in keys).backward()
+
+    from glfusion_b200 import cycle
+
+    def parts_cycle_fused():  # the same pass through the library's cycle step: spatial_sum + dense_seg_cycle kernels
+        zero()
+        fus, glob, _ = f.forward_parts(dict(zip(keys, f4)), dict(zip(keys, cl)), dict(zip(keys, ct)), need_local=False)
+        sum(cycle.dense_seg_cycle(cycle.spatial_sum(glob[k]), 16, 2, 3, 10.0) for k in keys).backward()
     res = {}
     for name, fn in (("forward_stacked", stacked), ("forward_dict_api", dict_api), ("forward_parts_supervised_pass", parts_seg),
-                     ("forward_parts_cycle_pass", parts_cycle)):
+                     ("forward_parts_cycle_pass", parts_cycle), ("forward_parts_cycle_pass_fused_loss", parts_cycle_fused)):
         ms = graph_time(fn)
         res[name] = {"ms_per_step": round(ms, 4), "clips_per_s": round(clips / (ms * 1e-3), 1)}
+    feat = torch.randn(B, C, device=DEV).cumsum(0).requires_grad_(True)
+
+    def loss_alone():         # dense_seg_cycle forward + backward on [128 frames, 256] features: 2 launches + 1 multiply
+        feat.grad = None
+        cycle.dense_seg_cycle(feat, 16, 2, 3, 10.0).backward()
+    res["dense_seg_cycle_fwd_bwd_us"] = round(graph_time(loss_alone) * 1e3, 2)
     res["parts_over_stacked"] = round(res["forward_parts_supervised_pass"]["ms_per_step"] / res["forward_stacked"]["ms_per_step"], 4)
     res["parts_over_dict_api"] = round(res["forward_parts_supervised_pass"]["ms_per_step"] / res["forward_dict_api"]["ms_per_step"], 4)
     out["parts"] = res
