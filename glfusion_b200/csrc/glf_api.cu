@@ -275,6 +275,24 @@ int pick_split(long long tiles, int K) {
   return static_cast<int>(s);
 }
 
+// Split of a long token contraction (K = all rows) whose output tiles alone leave the last round of the 148 persistent
+// CTAs mostly empty: e.g. dWcat at C = 2048 is 24 x 8 = 192 tiles of 128 x 256 = 1.3 rounds (0.65 of the machine);
+// three K-slices make 576 work items = 3.9 rounds of a third the length (0.97).  Mirrors gemm()'s tile choice.
+int pick_split_rounds(long long M, long long N, long long batch, int K) {
+  const long long BNt = N <= 64 ? 64 : ((K >= 512 && N % 256 == 0) ? 256 : 128);
+  const long long tiles = ((M + 127) / 128) * ((N + BNt - 1) / BNt) * batch;
+  if (tiles < 96) return pick_split(tiles, K);
+  const int kb = (K + 63) / 64;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int sp = 1; sp <= 4 && kb / sp >= 16; ++sp) {
+    const long long items = tiles * sp;
+    const double eff = static_cast<double>(items) / (148.0 * static_cast<double>((items + 147) / 148));
+    if (eff > best_eff + 0.08) { best_eff = eff; best = sp; }     // a further slice has to buy 8 % of the machine
+  }
+  return best;
+}
+
 GemmOperand opnd(const void* p, int mn, long long ld, long long bs) {
   GemmOperand o;
   o.ptr = p; o.mn_major = mn; o.ld = ld; o.batch_stride = bs;
@@ -896,7 +914,7 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
       g.M = C; g.N = Ci; g.K = rows;
       g.out_kind = 2;
       g.D = g_->wz_w; g.ldd = Ci;
-      g.split_k = pick_split(static_cast<long long>((C + 127) / 128) * ((Ci + 127) / 128), rows);
+      g.split_k = pick_split_rounds(C, Ci, 1, rows);
       GLF_TRY(gemm(g, stream));
     }
     GLF_TRY(flash_bwd(s.P, s.Y, wb.dY, s.lse, wb.dP, wb.delta, wb.cs_t, wb.cs_p, wb.cs_g, 4 * B * m.tiles_seq, &np, B, N,
@@ -911,7 +929,7 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
     g.M = 3 * Ci; g.N = C; g.K = rows;
     g.out_kind = 2;
     g.D = wb.dwcat; g.ldd = C;
-    g.split_k = pick_split(static_cast<long long>((3 * Ci + 127) / 128) * ((C + 127) / 128), rows);
+    g.split_k = pick_split_rounds(3 * Ci, C, 1, rows);
     GLF_TRY(gemm(g, stream));
   }
   const size_t wbytes = sizeof(float) * Ci * C;

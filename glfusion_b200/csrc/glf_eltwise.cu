@@ -83,31 +83,53 @@ __global__ void transpose_kernel(const TI* __restrict__ in, TO* __restrict__ out
 
 // ------------------------------------------------------------------------------------------------ weights
 // fp32 masters -> bf16 operands: Wcat [3Ci, C] (theta | phi | g), WcatT [C, 3Ci], bcat [3Ci] fp32, Wz [C, Ci], WzT [Ci, C]
-__global__ void prep_weights_kernel(const float* __restrict__ tw, const float* __restrict__ pw,
+// 32 x 32 tiles, transposed through shared memory: every global access is coalesced (the element-per-thread version
+// spent 80 us at C = 2048 on its strided transposed stores).
+__global__ void __launch_bounds__(256) prep_weights_kernel(const float* __restrict__ tw, const float* __restrict__ pw,
                                     const float* __restrict__ gw, const float* __restrict__ tb,
                                     const float* __restrict__ pb, const float* __restrict__ gb,
                                     const float* __restrict__ wz, bf16* __restrict__ wcat, bf16* __restrict__ wcatT,
                                     float* __restrict__ bcat, bf16* __restrict__ wzb, bf16* __restrict__ wzT, int C,
                                     int Ci) {
-  const int total = 3 * Ci * C;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int r = i / C, c = i % C;
-    const int which = r / Ci, rr = r % Ci;
-    const float* src = which == 0 ? tw : (which == 1 ? pw : gw);
-    const float v = src[rr * C + c];
-    wcat[i] = __float2bfloat16(v);
-    wcatT[static_cast<long long>(c) * 3 * Ci + r] = __float2bfloat16(v);
-    if (i < Ci * C) {  // W_z is [C, Ci]: same element count as one projection
-      const int zc = i / Ci, zk = i % Ci;
-      const float z = wz[i];
-      wzb[i] = __float2bfloat16(z);
-      wzT[static_cast<long long>(zk) * C + zc] = __float2bfloat16(z);
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+  const int tc = (C + 31) / 32, tci = (Ci + 31) / 32;
+  const int n_cat = 3 * tci * tc;                                // tiles of Wcat: rows 3Ci (tile rows never straddle a projection)
+  int t = blockIdx.x;
+  const float* src; bf16* dst; bf16* dstT;
+  int R, Cc, r0, c0;                                             // source [R, Cc] row-major; destination row offset for the concatenation
+  long long dst_ld, dstT_ld; int dst_row_off;
+  if (t < n_cat) {
+    const int which = t / (tci * tc), rem = t % (tci * tc);
+    src = which == 0 ? tw : (which == 1 ? pw : gw);
+    R = Ci; Cc = C; r0 = (rem / tc) * 32; c0 = (rem % tc) * 32;
+    dst = wcat; dst_ld = C; dstT = wcatT; dstT_ld = 3LL * Ci; dst_row_off = which * Ci;
+  } else {
+    t -= n_cat;
+    src = wz; R = C; Cc = Ci; r0 = (t / tci) * 32; c0 = (t % tci) * 32;
+    dst = wzb; dst_ld = Ci; dstT = wzT; dstT_ld = C; dst_row_off = 0;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    float v = 0.f;
+    if (r < R && c < Cc) {
+      v = src[static_cast<long long>(r) * Cc + c];
+      dst[static_cast<long long>(dst_row_off + r) * dst_ld + c] = __float2bfloat16(v);
     }
-    if (i < 3 * Ci) {
+    tile[ty + 8 * i][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + tx;                  // transposed: row c of the destination, column (offset + r)
+    if (r < R && c < Cc) dstT[static_cast<long long>(c) * dstT_ld + dst_row_off + r] = __float2bfloat16(tile[tx][ty + 8 * i]);
+  }
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < 3 * Ci; i += 256) {
       const int w2 = i / Ci, k = i % Ci;
       bcat[i] = (w2 == 0 ? tb : (w2 == 1 ? pb : gb))[k];
     }
-  }
 }
 
 // ------------------------------------------------------------------------------------------------ BN statistics
@@ -683,9 +705,7 @@ int transpose_cast(const void* in, void* out, int batch, int R, int S, int in_dt
 
 int prep_weights(const glf_weights* w, int C, int Ci, bf16* wcat, bf16* wcatT, float* bcat, bf16* wz, bf16* wzT,
                  cudaStream_t stream) {
-  const int total = 3 * Ci * C;
-  int blocks = (total + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  const int blocks = 4 * ((C + 31) / 32) * ((Ci + 31) / 32);      // three projections + W_z, 32 x 32 tiles
   prep_weights_kernel<<<blocks, 256, 0, stream>>>(w->theta_w, w->phi_w, w->g_w, w->theta_b, w->phi_b, w->g_b, w->wz_w,
                                                   wcat, wcatT, bcat, wz, wzT, C, Ci);
   return check_cuda(cudaGetLastError(), "prep_weights launch");
@@ -694,9 +714,14 @@ int prep_weights(const glf_weights* w, int C, int Ci, bf16* wcat, bf16* wcatT, f
 // stage-1 launcher: returns the reduced table (in `scratch`) and its row count through *np
 int reduce_stage1(const float* p0, const float* p1, const float* p2, int ntab, const int* np_in, int* np,
                   long long* row_stride, long long stat_stride, int NS, int C, float* scratch, cudaStream_t stream) {
-  const int G = REDUCE_STAGE1_ROWS;
+  // rows of the reduced table: enough groups that each of a block's RED_Y row-threads sums ~4 partial rows, never
+  // more than the scratch holds (a table of a few hundred rows needs a handful of blocks per channel slab, not 64)
+  int np_max = 0;
+  for (int i = 0; i < ntab; ++i) np_max = np_in[i] > np_max ? np_in[i] : np_max;
+  int G = (np_max + 4 * RED_Y - 1) / (4 * RED_Y);
+  G = G < 1 ? 1 : (G > REDUCE_STAGE1_ROWS ? REDUCE_STAGE1_ROWS : G);
   Stage1 t;
-  const long long tab = static_cast<long long>(G) * NS * C;
+  const long long tab = static_cast<long long>(REDUCE_STAGE1_ROWS) * NS * C;   // table pitch in the scratch: fixed, whatever G
   t.part[0] = p0; t.part[1] = p1; t.part[2] = p2;
   t.out[0] = scratch; t.out[1] = scratch + tab; t.out[2] = scratch + 2 * tab;
   for (int i = 0; i < 3; ++i) t.np[i] = i < ntab ? np_in[i] : 0;
