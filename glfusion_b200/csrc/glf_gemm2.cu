@@ -48,6 +48,11 @@ struct Gemm2Params {
   const float* bias;
   long long bias_stride;
   float* colstats;         // [gridDim.x][2][N] per-CTA running sums (or null)
+  int cs_blocks;           // 1: N spans several column tiles -> one partial row per 32-row sub-block instead,
+  int tiles_m128;          //    [batch * tiles_m128 * 4][2][N] (the single-CTA kernel's table layout)
+  float alpha;
+  const bf16* addend;      // optional bf16 [M, N] added before the store
+  long long ld_add, stride_add;
   int dbg;                 // tuning aid (GLF_GEMM_DBG & 2): skip the epilogue's staging and stores (results WRONG)
 };
 
@@ -201,12 +206,29 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
         float2 f[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        if (p.alpha != 1.f) {
+          const float2 al = make_float2(p.alpha, p.alpha);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = mul2(f[j], al);
+        }
         if (biasb != nullptr) {
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
             const float4 bv = *reinterpret_cast<const float4*>(wbias + 2 * j);
             f[j] = add2(f[j], make_float2(bv.x, bv.y));
             f[j + 1] = add2(f[j + 1], make_float2(bv.z, bv.w));
+          }
+        }
+        if (p.addend != nullptr && lane < rows_valid) {       // this lane's row: 32 bf16 = 64 contiguous bytes
+          const uint4* ar = reinterpret_cast<const uint4*>(p.addend + static_cast<long long>(b) * p.stride_add +
+                                                           static_cast<long long>(m0 + q * 32 + lane) * p.ld_add + gc0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 a4 = __ldg(ar + j);
+            f[4 * j] = add2(f[4 * j], unpack_bf16(a4.x));
+            f[4 * j + 1] = add2(f[4 * j + 1], unpack_bf16(a4.y));
+            f[4 * j + 2] = add2(f[4 * j + 2], unpack_bf16(a4.z));
+            f[4 * j + 3] = add2(f[4 * j + 3], unpack_bf16(a4.w));
           }
         }
         uint8_t* wstg = wstg0 + (nchunk & 1) * WARP_STG;
@@ -248,7 +270,13 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
           sa2.y += __shfl_xor_sync(0xffffffffu, sa2.y, 16);
           sq2.x += __shfl_xor_sync(0xffffffffu, sq2.x, 16);
           sq2.y += __shfl_xor_sync(0xffffffffu, sq2.y, 16);
-          if (ci == 0) { cs1[0] = add2(cs1[0], sa2); cs2[0] = add2(cs2[0], sq2); }
+          if (p.cs_blocks) {
+            if (half == 0 && m0 < p.M) {                       // (a 128-row half entirely beyond M has no table rows)
+              float* cs = p.colstats + ((static_cast<long long>(b) * p.tiles_m128 + (m0 >> 7)) * 4 + q) * 2 * p.N;
+              *reinterpret_cast<float2*>(cs + gc0 + 2 * hl) = sa2;
+              *reinterpret_cast<float2*>(cs + p.N + gc0 + 2 * hl) = sq2;
+            }
+          } else if (ci == 0) { cs1[0] = add2(cs1[0], sa2); cs2[0] = add2(cs2[0], sq2); }
           else { cs1[1] = add2(cs1[1], sa2); cs2[1] = add2(cs2[1], sq2); }
         }
         fence_proxy_async_smem();
@@ -260,7 +288,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
       }
     }
     if (lane == 0) tma_store_wait_all<0>();
-    if (p.colstats != nullptr) {
+    if (p.colstats != nullptr && !p.cs_blocks) {
       // ONE partial row per CTA: the four warps that share a column chunk (one per 32-row quarter) combine their
       // running sums through the idle staging tiles, in a fixed order
       __syncwarp();
@@ -324,17 +352,21 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
 bool gemm_pair_applicable(const GemmArgs& a, int num_sms) {
   const char* e = getenv("GLF_GEMM_PAIR");       // tuning aid: GLF_GEMM_PAIR=0 keeps the single-CTA tiles
   if (e && e[0] == '0') return false;
-  if (a.A.mn_major || a.N % BN2 != 0 || (a.N != BN2 && a.colstats != nullptr) || a.M < 1024 || a.out_kind != 0 || a.addend != nullptr || a.rowsum != nullptr) return false;
-  if (a.split_k > 1 || a.alpha != 1.f || a.K % BK != 0 || a.npairs > 6) return false;
+  if (a.A.mn_major || a.N % BN2 != 0 || a.M < 1024 || a.out_kind != 0 || a.rowsum != nullptr) return false;
+  if (a.split_k > 1 || a.K % BK != 0 || a.npairs > 6) return false;
   if (a.strideD % 8 != 0 || num_sms < 2) return false;
-  if (a.colstats != nullptr) {       // measured: with the column statistics in the epilogue the single-CTA tile is faster
-    const char* ec = getenv("GLF_GEMM_PAIR_STATS");
+  if (a.addend != nullptr && (a.ld_add % 8 != 0 || a.stride_add % 8 != 0 || (reinterpret_cast<uintptr_t>(a.addend) & 15) != 0))
+    return false;
+  if (a.colstats != nullptr && a.N == BN2) {   // measured at K = 256: with the column statistics in the epilogue the
+    const char* ec = getenv("GLF_GEMM_PAIR_STATS");   // single-CTA tile is faster (HBM-bound shape)
     if (!(ec && ec[0] == '1')) return false;
   }
+  // several column tiles (the C = 2048 products): per-sub-block partial rows; worth it once the product is tensor-bound
+  if (a.colstats != nullptr && a.N != BN2 && a.K < 1024) return false;
   const long long tiles = static_cast<long long>((a.M + 255) / 256) * a.batch * (a.N / BN2);
   const int grid = (num_sms / 2) * 2;
   if (tiles < grid / 2) return false;            // not enough pair tiles to fill the machine
-  if (a.colstats != nullptr && grid > static_cast<long long>(a.batch) * ((a.M + 127) / 128) * 4) return false;
+  if (a.colstats != nullptr && a.N == BN2 && grid > static_cast<long long>(a.batch) * ((a.M + 127) / 128) * 4) return false;
   return true;
 }
 
@@ -364,12 +396,19 @@ int gemm_pair(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   p.bias = a.bias;
   p.bias_stride = a.bias != nullptr ? a.bias_stride : 0;
   p.colstats = a.colstats;
+  p.cs_blocks = a.colstats != nullptr && a.N != BN2;
+  p.tiles_m128 = gemm_tiles_m(a.M);
+  p.alpha = a.alpha;
+  p.addend = a.addend;
+  p.ld_add = a.ld_add;
+  p.stride_add = a.stride_add;
   {
     const char* e = getenv("GLF_GEMM_DBG");
     p.dbg = e ? atoi(e) : 0;
   }
   const int grid = (num_sms / 2) * 2;
-  if (a.colstats_rows != nullptr) *a.colstats_rows = a.colstats != nullptr ? grid : 0;
+  if (a.colstats_rows != nullptr)
+    *a.colstats_rows = a.colstats == nullptr ? 0 : (p.cs_blocks ? a.batch * p.tiles_m128 * 4 : grid);
   return a.B.mn_major ? launch_pair<true>(tmA, tmB, tmD, p, grid, stream)
                       : launch_pair<false>(tmA, tmB, tmD, p, grid, stream);
 }
