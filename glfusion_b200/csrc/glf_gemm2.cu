@@ -53,10 +53,17 @@ struct Gemm2Params {
   float alpha;
   const bf16* addend;      // optional bf16 [M, N] added before the store
   long long ld_add, stride_add;
+  int split_k, kb_per_split;   // K slices per tile (fp32 atomic output only)
+  float* Df;               // out_kind 2: fp32 output, red.global.add (split-K slices / batch-reduced products)
+  long long ldd, strideD;
   int dbg;                 // tuning aid (GLF_GEMM_DBG & 2): skip the epilogue's staging and stores (results WRONG)
 };
 
-template <bool B_MN>
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(G2_THREADS, 1)
     gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmD, const Gemm2Params p) {
@@ -105,20 +112,27 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < p.total; tile += nclusters) {
+      for (int item = cluster_id; item < p.total * p.split_k; item += nclusters) {
+        const int tile = item / p.split_k, ks = item - tile * p.split_k;
         const int nt = tile % p.tiles_n, bm = tile / p.tiles_n;
         const int b = bm / p.tiles_m, mt = bm - b * p.tiles_m;
         const int m0 = mt * 256 + static_cast<int>(rank) * BM, n0 = nt * BN2 + static_cast<int>(rank) * 128;
         const int ab = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
-        const int niter = p.kb_total * p.npairs;
+        const int kb0 = ks * p.kb_per_split;
+        const int niter = (min(p.kb_total, kb0 + p.kb_per_split) - kb0) * p.npairs;
         for (int it = 0; it < niter; ++it) {
           const int pair = it % p.npairs;
-          const int k0 = (it / p.npairs) * BK;
+          const int k0 = (kb0 + it / p.npairs) * BK;
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
           if (leader) mbar_expect_tx(smem_u32(&full_bar[stage]), 2 * G2_STAGE);   // both CTAs' bytes
           const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
           const uint32_t sa = smem_base + stage * G2_STAGE, sb = sa + G2_A;
-          tma_load_4d_cg2(&tmA, fb, sa, k0, m0, ab, p.pairA[pair]);
+          if (!A_MN) {
+            tma_load_4d_cg2(&tmA, fb, sa, k0, m0, ab, p.pairA[pair]);
+          } else {                 // MN-major A (token contractions): two [64 k][64 m] boxes, the image `mdesc` reads
+            tma_load_4d_cg2(&tmA, fb, sa, m0, k0, ab, p.pairA[pair]);
+            tma_load_4d_cg2(&tmA, fb, sa + 8192, m0 + 64, k0, ab, p.pairA[pair]);
+          }
           if (!B_MN) {
             tma_load_4d_cg2(&tmB, fb, sb, k0, n0, bb, p.pairB[pair]);
           } else {
@@ -132,12 +146,13 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------ MMA issuer (leader)
     if (leader && elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(256, BN2, false, B_MN);
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN2, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int tile = cluster_id; tile < p.total; tile += nclusters, ++local) {
-        const int niter = p.kb_total * p.npairs;
+      for (int item = cluster_id; item < p.total * p.split_k; item += nclusters, ++local) {
+        const int kb0 = (item % p.split_k) * p.kb_per_split;
+        const int niter = (min(p.kb_total, kb0 + p.kb_per_split) - kb0) * p.npairs;
         const int acc = local & 1;
         const uint32_t use = static_cast<uint32_t>(local >> 1);
         mbar_wait(smem_u32(&tmem_empty_bar[acc]), (use & 1u) ^ 1u);   // both CTAs' epilogues drained this stage
@@ -149,7 +164,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
           const uint32_t sa = smem_base + stage * G2_STAGE, sb = sa + G2_A;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = make_sdesc(sa + k * 32, 16, 1024);
+            const uint64_t ad = A_MN ? make_sdesc(sa + k * 2048, 8192, 1024) : make_sdesc(sa + k * 32, 16, 1024);
             const uint64_t bd = B_MN ? make_sdesc(sb + k * 2048, 8192, 1024) : make_sdesc(sb + k * 32, 16, 1024);
             umma_f16_cg2(tacc, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
           }
@@ -173,7 +188,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
     const uint32_t leader_empty0 = mapa_shared(smem_u32(&tmem_empty_bar[0]), 0);
     const uint32_t leader_empty1 = mapa_shared(smem_u32(&tmem_empty_bar[1]), 0);
     int local = 0;
-    for (int tile = cluster_id; tile < p.total; tile += nclusters, ++local) {
+    for (int item = cluster_id; item < p.total * p.split_k; item += nclusters, ++local) {
+      const int tile = item / p.split_k;
       const int nt = tile % p.tiles_n, bm = tile / p.tiles_n;
       const int b = bm / p.tiles_m, mt = bm - b * p.tiles_m;
       const int m0 = mt * 256 + static_cast<int>(rank) * BM;
@@ -218,6 +234,15 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
             f[j] = add2(f[j], make_float2(bv.x, bv.y));
             f[j + 1] = add2(f[j + 1], make_float2(bv.z, bv.w));
           }
+        }
+        if (p.Df != nullptr) {                                // fp32 atomic output: no staging, no bulk store
+          if (lane < rows_valid) {
+            float* dr = p.Df + static_cast<long long>(b) * p.strideD + static_cast<long long>(m0 + q * 32 + lane) * p.ldd + gc0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) red_add_v4(dr + 2 * j, f[j].x, f[j].y, f[j + 1].x, f[j + 1].y);
+          }
+          __syncwarp();
+          continue;
         }
         if (p.addend != nullptr && lane < rows_valid) {       // this lane's row: 32 bf16 = 64 contiguous bytes
           const uint4* ar = reinterpret_cast<const uint4*>(p.addend + static_cast<long long>(b) * p.stride_add +
@@ -326,10 +351,10 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
   if (warp == 1) tmem_dealloc_cg2(tmem_base, 512);
 }
 
-template <bool B_MN>
+template <bool A_MN, bool B_MN>
 int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const Gemm2Params& p, int grid,
                 cudaStream_t stream) {
-  auto kern = gemm_pair_kernel<B_MN>;
+  auto kern = gemm_pair_kernel<A_MN, B_MN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
   if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm_pair)");
   cudaLaunchConfig_t cfg = {};
@@ -352,9 +377,15 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
 bool gemm_pair_applicable(const GemmArgs& a, int num_sms) {
   const char* e = getenv("GLF_GEMM_PAIR");       // tuning aid: GLF_GEMM_PAIR=0 keeps the single-CTA tiles
   if (e && e[0] == '0') return false;
-  if (a.A.mn_major || a.N % BN2 != 0 || a.M < 1024 || a.out_kind != 0 || a.rowsum != nullptr) return false;
-  if (a.split_k > 1 || a.K % BK != 0 || a.npairs > 6) return false;
-  if (a.strideD % 8 != 0 || num_sms < 2) return false;
+  if (a.N % BN2 != 0 || a.M < 1024 || a.out_kind == 1 || a.rowsum != nullptr) return false;
+  if (a.npairs > 6 || num_sms < 2) return false;
+  if (a.out_kind == 0 && (a.split_k > 1 || a.strideD % 8 != 0)) return false;
+  if (a.out_kind == 2 && (a.bias != nullptr || a.addend != nullptr || a.colstats != nullptr || a.ldd % 4 != 0 ||
+                          a.strideD % 4 != 0 || (reinterpret_cast<uintptr_t>(a.D) & 15) != 0))
+    return false;
+  // MN-major A is the token contraction of the token-space path (K = tokens): worth a pair only when tensor-bound
+  if (a.A.mn_major && (a.M % 128 != 0 || static_cast<long long>(a.M) * a.N < 1024 * 1024)) return false;
+  if (a.K % BK != 0 && !(a.A.mn_major && a.B.mn_major)) return false;   // (a K tail is zero-filled by TMA for MN-major operands)
   if (a.addend != nullptr && (a.ld_add % 8 != 0 || a.stride_add % 8 != 0 || (reinterpret_cast<uintptr_t>(a.addend) & 15) != 0))
     return false;
   if (a.colstats != nullptr && a.N == BN2) {   // measured at K = 256: with the column statistics in the epilogue the
@@ -363,7 +394,7 @@ bool gemm_pair_applicable(const GemmArgs& a, int num_sms) {
   }
   // several column tiles (the C = 2048 products): per-sub-block partial rows; worth it once the product is tensor-bound
   if (a.colstats != nullptr && a.N != BN2 && a.K < 1024) return false;
-  const long long tiles = static_cast<long long>((a.M + 255) / 256) * a.batch * (a.N / BN2);
+  const long long tiles = static_cast<long long>((a.M + 255) / 256) * a.batch * (a.N / BN2) * (a.split_k > 1 ? a.split_k : 1);
   const int grid = (num_sms / 2) * 2;
   if (tiles < grid / 2) return false;            // not enough pair tiles to fill the machine
   if (a.colstats != nullptr && a.N == BN2 && grid > static_cast<long long>(a.batch) * ((a.M + 127) / 128) * 4) return false;
@@ -381,11 +412,23 @@ int gemm_pair(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   if (rc) return rc;
   rc = make_operand_tmap(&tmB, a.B, a.B.rows > 0 ? a.B.rows : a.N, a.K, a.batch, nlimbsB, 128);
   if (rc) return rc;
-  rc = make_output_tmap(&tmD, a.D, a.M, a.N, a.batch, a.ldd, a.strideD);
-  if (rc) return rc;
+  if (a.out_kind == 0) {
+    rc = make_output_tmap(&tmD, a.D, a.M, a.N, a.batch, a.ldd, a.strideD);
+    if (rc) return rc;
+  } else {
+    tmD = tmA;     // unused by the fp32 atomic epilogue
+  }
   Gemm2Params p;
   p.M = a.M; p.N = a.N; p.batch = a.batch;
-  p.kb_total = a.K / BK;
+  p.kb_total = (a.K + BK - 1) / BK;
+  {
+    const int sk = a.split_k < 1 ? 1 : a.split_k;
+    p.kb_per_split = (p.kb_total + sk - 1) / sk;
+    p.split_k = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  }
+  p.Df = a.out_kind == 2 ? reinterpret_cast<float*>(a.D) : nullptr;
+  p.ldd = a.ldd;
+  p.strideD = a.strideD;
   p.npairs = a.npairs;
   for (int i = 0; i < 6; ++i) { p.pairA[i] = a.pairA[i]; p.pairB[i] = a.pairB[i]; }
   p.a_batched = a.A.batch_stride != 0;
@@ -409,8 +452,11 @@ int gemm_pair(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   const int grid = (num_sms / 2) * 2;
   if (a.colstats_rows != nullptr)
     *a.colstats_rows = a.colstats == nullptr ? 0 : (p.cs_blocks ? a.batch * p.tiles_m128 * 4 : grid);
-  return a.B.mn_major ? launch_pair<true>(tmA, tmB, tmD, p, grid, stream)
-                      : launch_pair<false>(tmA, tmB, tmD, p, grid, stream);
+  if (a.A.mn_major)
+    return a.B.mn_major ? launch_pair<true, true>(tmA, tmB, tmD, p, grid, stream)
+                        : launch_pair<true, false>(tmA, tmB, tmD, p, grid, stream);
+  return a.B.mn_major ? launch_pair<false, true>(tmA, tmB, tmD, p, grid, stream)
+                      : launch_pair<false, false>(tmA, tmB, tmD, p, grid, stream);
 }
 
 }  // namespace glf

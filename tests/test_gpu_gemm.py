@@ -82,6 +82,50 @@ def test_gemm_splitk_fp32_atomic(split_k):
     assert O.rel_err(D1, ref * K) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K,batch,a_mn,b_mn", [
+    (2048, 1024, 200, 10, 1, 1),      # dW'_b at the network's width: token contraction, ragged K tail, batched
+    (1024, 1024, 320, 40, 1, 1),      # Phi^T G / dM
+    (4736, 1024, 256, 4, 0, 1),       # dTheta = dU W' (B read MN-major), ragged M (4736 = 18.5 x 256)
+    (18944, 512, 128, 1, 0, 0),       # K-major, several column tiles
+    (1152, 512, 128, 40, 1, 0),       # MN-major A with a K-major B
+])
+def test_gemm_cta_pair_operand_layouts(M, N, K, batch, a_mn, b_mn):
+    """Shapes that route to the CTA-pair kernel (tcgen05 cta_group::2, csrc/glf_gemm2.cu): every operand-layout
+    combination, ragged M and K, batched operands."""
+    A, Af = _mk(batch, M, K, a_mn, 11)
+    B, Bf = _mk(batch, N, K, b_mn, 12)
+    D, _ = gemm(A, B, M, N, K, batch, a_mn, b_mn)
+    ref = torch.matmul(Af, Bf.transpose(1, 2))
+    assert O.rel_err(D, ref) < 6e-3
+
+
+def test_gemm_cta_pair_epilogues():
+    """alpha, bias, residual addend, BatchNorm column statistics over several column tiles, fp32 atomic output with K
+    slices and a batch-reduced output — the epilogues the C = 2048 token-space path uses on the pair kernel."""
+    M, N, K, batch = 2352, 1024, 1024, 8
+    A, Af = _mk(batch, M, K, 0, 13)
+    B, Bf = _mk(batch, N, K, 0, 14)
+    ref = torch.matmul(Af, Bf.transpose(1, 2))
+    bias = torch.randn(N, device=DEV)
+    add = torch.randn(batch, M, N, device=DEV).to(torch.bfloat16)
+    D, cs = gemm(A, B, M, N, K, batch, bias=bias, alpha=0.25, colstats=True)
+    want = 0.25 * ref + bias.cpu()
+    assert O.rel_err(D, want) < 6e-3
+    cs = cs.sum(0).cpu()
+    Dr = D.float().cpu()
+    assert O.rel_err(cs[0], Dr.sum((0, 1))) < 1e-4
+    assert O.rel_err(cs[1], (Dr * Dr).sum((0, 1))) < 1e-4
+    D2, _ = gemm(A, B, M, N, K, batch, alpha=0.25, addend=add)
+    assert O.rel_err(D2, 0.25 * ref + add.float().cpu()) < 6e-3
+    # token contraction into fp32 with K slices (dWcat = dP^T X): A, B MN-major, K = rows
+    M2, N2, K2 = 3072, 2048, 2368
+    A2, A2f = _mk(1, M2, K2, 1, 15)
+    B2, B2f = _mk(1, N2, K2, 1, 16)
+    for split in (1, 3):
+        D3, _ = gemm(A2, B2, M2, N2, K2, 1, 1, 1, out_kind=2, split_k=split, alpha=1.0 / K2)
+        assert O.rel_err(D3, torch.matmul(A2f, B2f.transpose(1, 2)) / K2) < 1e-5
+
+
 def test_transpose_pack_roundtrip():
     import ctypes as C
     from glfusion_b200 import _lib as L
