@@ -459,6 +459,12 @@ def run_ours(args):
                                   if numa_cpus else "no NUMA binding")
     if orig_affinity is not None:
         os.sched_setaffinity(0, orig_affinity)       # the CPU baseline below uses every host core again
+    if world == 1 and not args.no_width2048:
+        try:
+            out["width2048"] = width2048(dev, pk)
+        except Exception as exc:       # noqa: BLE001  (a secondary object must not take the bench line down)
+            out["width2048"] = {"unavailable": repr(exc)[:200]}
+        torch.cuda.empty_cache()
     if world == 1 and not args.no_gpu_reference:
         out["gpu_reference"] = gpu_reference(C, dev)
     if not args.no_cpu_baseline and world == 1:
@@ -660,7 +666,7 @@ def dx_gemm_probe(dev, clips, C, pk):
         t = json.load(open(tp)).get("gemm_dx", {})
         if t.get("rows") == B * N and t.get("C") == C:
             traffic = int(t["traffic_bytes"])
-    return {"bound": "hbm", "kernel": "gemm_pair_kernel<1> (dX = [dV | X][E' ; F] + e, K = 2C, cta_group::2)",
+    return {"bound": "hbm", "kernel": "gemm_pair_kernel<A_MN=0, B_MN=1> (dX = [dV | X][E' ; F] + e, K = 2C, cta_group::2)",
             "achieved": round(ach, 1), "peak": pk["hbm_gbs"], "peak_source": pk["source"], "unit": "GB/s",
             "frac": round(ach / pk["hbm_gbs"], 4), "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
             "ms_per_launch": round(ms, 4), "inputs": "617 MB per launch, larger than the 126 MB L2"}
@@ -695,6 +701,55 @@ def cpu_step(C: int, clips: int, seed: int = 0):
     else:
         O.fusion_fwd_bwd(f4, cl, ct, do, pg, pl)
     return time.perf_counter() - t0
+
+
+def width2048(dev, pk, reps: int = 10):
+    """Secondary object: the same fused node at the reference NETWORK's own fusion width (R/models/ours.py:1746-1747:
+    in_channels = 2048; 3 views x 28 x 28 = 2 352 tokens per frame, N < 5 C -> token-space form), 8 frames, fwd + bwd
+    replayed from a CUDA graph.  Tensor-bound: reported against the sustained bf16 tensor peak."""
+    C2, V2, B2 = 2048, 3, 8
+    f = seeded_fusion(C2, dev)
+    g = torch.Generator().manual_seed(5)
+    f4 = [torch.randn(B2, C2, HH, WW, generator=g).to(dev).to(torch.bfloat16).requires_grad_(True) for _ in range(V2)]
+    cl = [torch.randn(B2, NCLS, HH, WW, generator=g).to(dev) for _ in range(V2)]
+    ct = [torch.randn(B2, 1, HH, WW, generator=g).to(dev) for _ in range(V2)]
+    dz = torch.randn(B2, V2, HH, WW, C2, generator=g).to(dev).to(torch.bfloat16).permute(0, 4, 1, 2, 3)
+    params = [p for p in f.parameters() if p.requires_grad]
+
+    def step():
+        for t in f4:
+            t.grad = None
+        for p in params:
+            p.grad = None
+        f.forward_stacked(f4, cl, ct).backward(dz)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    for _ in range(3):
+        graph.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(reps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    rows = B2 * V2 * HH * WW
+    flops = 2 * 13.5 * rows * C2 * C2      # token-space form, both blocks, fwd + bwd (DESIGN.md section 2)
+    tf = flops / (ms * 1e-3) / 1e12
+    return {"workload": "C=2048, 3 views x 28x28 = 2352 tokens per frame, 8 frames, fwd+bwd of the fused node (token-space form)",
+            "ms_per_step": round(ms, 4), "frames_per_s": round(B2 / (ms * 1e-3), 1), "clips_per_s": round(B2 / F / (ms * 1e-3), 1),
+            "bound": "tensor", "achieved": round(tf, 1), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": round(tf / pk["bf16_tflops"], 4), "frac_of_burst_peak": round(tf / pk["bf16_tflops_burst"], 4),
+            "flops_per_step": flops, "timing": f"{reps} CUDA-graph replays after 3 warm-up replays, 2.7 GB working set >> L2"}
 
 
 def gpu_reference(C: int, dev):
@@ -826,6 +881,7 @@ def main():
                     help="start the peer-memory all-reduce as soon as the weight gradients are final (beside the gate backward)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-width2048", action="store_true", help="skip the C=2048 secondary object")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":
