@@ -500,6 +500,246 @@ __global__ void __launch_bounds__(ROW_THREADS, 2)
   }
 }
 
+// ------------------------------------------------------------------------------------------------ wide rows (C > 256)
+// Rows wider than 256 channels are sliced over S warps, so a CTA of 8 warps holds one or two rows per step and the
+// register-prefetch kernels above keep ~48 KB per SM in flight: 2.7 - 3.7 TB/s at C = 2048.  (More rows per thread was
+// tried: 139 registers, one CTA per SM, slower.)  These bf16 variants prefetch through a per-thread ring in shared memory
+// instead: every thread issues 16-byte cp.async copies LN_DEPTH - 1 steps ahead into slots only it reads back, so there
+// is nothing to synchronise beyond cp.async.wait_group and the depth costs no registers.
+constexpr int LN_DEPTH = 4;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ring layout: [LN_DEPTH][nops][ROW_THREADS] uint4
+__global__ void __launch_bounds__(ROW_THREADS)
+    bn_res_ln_fwd_ring_kernel(const bf16* __restrict__ U, const bf16* __restrict__ X, const float* __restrict__ bn_a,
+                              const float* __restrict__ bn_b, const float* __restrict__ lw, const float* __restrict__ lb,
+                              bf16* __restrict__ Z, float* __restrict__ mu_o, float* __restrict__ r_o, long long rows, int C,
+                              int S, float eps, int accumulate) {
+  extern __shared__ __align__(16) uint4 ln_ring[];
+  __shared__ float red[2 * ROW_WARPS * 2];
+  int buf = 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int RPB = ROW_WARPS / S;
+  const int rslot = warp / S, slice = warp % S;
+  const int c0 = slice * 256 + lane * 8;
+  const bool cact = c0 < C;
+  float a[8], b[8], w[8], bb[8];
+  if (cact) {
+    load8(bn_a + c0, a); load8(bn_b + c0, b); load8(lw + c0, w); load8(lb + c0, bb);
+  }
+  const float invC = 1.f / static_cast<float>(C);
+  const long long step = static_cast<long long>(gridDim.x) * RPB;
+  const long long first = static_cast<long long>(blockIdx.x) * RPB + rslot;
+  uint4* mine = ln_ring + threadIdx.x;
+  auto issue = [&](long long row, int slot) {
+    if (cact && row < rows) {
+      uint4* dst = mine + slot * 3 * ROW_THREADS;
+      cp_async16(dst, X + row * C + c0);
+      if (U != nullptr) cp_async16(dst + ROW_THREADS, U + row * C + c0);
+      if (accumulate) cp_async16(dst + 2 * ROW_THREADS, Z + row * C + c0);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int d = 0; d < LN_DEPTH - 1; ++d) issue(first + d * step, d);
+  int it = 0;
+  for (long long base = static_cast<long long>(blockIdx.x) * RPB; base < rows; base += step, ++it) {
+    const long long row = base + rslot;
+    const bool act = cact && row < rows;
+    issue(row + (LN_DEPTH - 1) * step, (it + LN_DEPTH - 1) % LN_DEPTH);
+    cp_async_wait<LN_DEPTH - 1>();
+    const uint4* src = mine + (it % LN_DEPTH) * 3 * ROW_THREADS;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (act) {
+      Raw8<bf16> xc, uc;
+      xc.v = src[0];
+      float x[8];
+      cvt8(xc, x);
+      if (U != nullptr) {
+        uc.v = src[ROW_THREADS];
+        float u[8];
+        cvt8(uc, u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fmaf(a[i], u[i], b[i]) + x[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = x[i];
+      }
+    }
+    float sm1[1] = {0.f};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm1[0] += v[i];
+    row_reduce<1>(sm1, S, rslot, slice, red, buf);
+    const float mu = sm1[0] * invC;
+    float q[1] = {0.f};
+    if (act) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[0] = fmaf(v[i] - mu, v[i] - mu, q[0]);
+    }
+    row_reduce<1>(q, S, rslot, slice, red, buf);
+    const float r = rsqrtf(q[0] * invC + eps);
+    if (act) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf((v[i] - mu) * r, w[i], bb[i]);
+      if (accumulate) {
+        Raw8<bf16> zc;
+        zc.v = src[2 * ROW_THREADS];
+        float z0[8];
+        cvt8(zc, z0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += z0[i];
+      }
+      store8(Z + row * C + c0, o);
+      if (slice == 0 && lane == 0 && mu_o != nullptr) {
+        mu_o[row] = mu;
+        r_o[row] = r;
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
+__global__ void __launch_bounds__(ROW_THREADS, 2)
+    bn_res_ln_bwd_ring_kernel(const bf16* __restrict__ dZ, const bf16* __restrict__ U, const bf16* __restrict__ X,
+                              const float* __restrict__ bn_a, const float* __restrict__ bn_b,
+                              const float* __restrict__ bn_mean, const float* __restrict__ bn_rstd,
+                              const float* __restrict__ lw, const float* __restrict__ mu_i, const float* __restrict__ r_i,
+                              bf16* __restrict__ dV, float* __restrict__ part, long long rows, int C, int S) {
+  extern __shared__ __align__(16) uint4 ln_ring[];
+  __shared__ float red[2 * ROW_WARPS * 2];
+  constexpr int ACC_PITCH = 32 * 8 + 8;
+  constexpr int SM_FLOATS = (ROW_WARPS * 4 * ACC_PITCH > 5 * 2048) ? ROW_WARPS * 4 * ACC_PITCH : 5 * 2048;
+  __shared__ __align__(16) float smbuf[SM_FLOATS];
+  int buf = 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int RPB = ROW_WARPS / S;
+  const int rslot = warp / S, slice = warp % S;
+  const int c0 = slice * 256 + lane * 8;
+  const bool cact = c0 < C;
+  const int Cs = S * 256;
+  for (int i = threadIdx.x; i < Cs; i += ROW_THREADS) {
+    const bool in = i < C;
+    smbuf[0 * Cs + i] = in ? bn_a[i] : 0.f;
+    smbuf[1 * Cs + i] = in ? bn_b[i] : 0.f;
+    smbuf[2 * Cs + i] = in ? lw[i] : 0.f;
+    smbuf[3 * Cs + i] = in ? bn_mean[i] : 0.f;
+    smbuf[4 * Cs + i] = in ? bn_rstd[i] : 0.f;
+  }
+  __syncthreads();
+  const float* sp = smbuf + c0;
+  float g_lw[8], g_lb[8], g_ga[8], g_be[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) g_lw[i] = g_lb[i] = g_ga[i] = g_be[i] = 0.f;
+  const float invC = 1.f / static_cast<float>(C);
+  const long long step = static_cast<long long>(gridDim.x) * RPB;
+  const long long first = static_cast<long long>(blockIdx.x) * RPB + rslot;
+  uint4* mine = ln_ring + threadIdx.x;
+  auto issue = [&](long long row, int slot) {
+    if (cact && row < rows) {
+      uint4* dst = mine + slot * 3 * ROW_THREADS;
+      cp_async16(dst, X + row * C + c0);
+      cp_async16(dst + ROW_THREADS, dZ + row * C + c0);
+      if (U != nullptr) cp_async16(dst + 2 * ROW_THREADS, U + row * C + c0);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int d = 0; d < LN_DEPTH - 1; ++d) issue(first + d * step, d);
+  float mu_n = 0.f, r_n = 0.f;            // the row statistics travel one step ahead in registers
+  if (cact && first < rows) { mu_n = mu_i[first]; r_n = r_i[first]; }
+  int it = 0;
+  for (long long base = static_cast<long long>(blockIdx.x) * RPB; base < rows; base += step, ++it) {
+    const long long row = base + rslot;
+    const bool act = cact && row < rows;
+    issue(row + (LN_DEPTH - 1) * step, (it + LN_DEPTH - 1) % LN_DEPTH);
+    const float mu = mu_n, r = r_n;
+    if (cact && row + step < rows) { mu_n = mu_i[row + step]; r_n = r_i[row + step]; }
+    cp_async_wait<LN_DEPTH - 1>();
+    const uint4* src = mine + (it % LN_DEPTH) * 3 * ROW_THREADS;
+    float xh[8], dxh[8], dz[8], uh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xh[i] = dxh[i] = dz[i] = uh[i] = 0.f;
+    if (act) {
+      Raw8<bf16> xc, zc;
+      xc.v = src[0];
+      zc.v = src[ROW_THREADS];
+      float x[8];
+      cvt8(xc, x);
+      cvt8(zc, dz);
+      if (U != nullptr) {
+        Raw8<bf16> uc;
+        uc.v = src[2 * ROW_THREADS];
+        float u[8], a[8], b[8];
+        cvt8(uc, u);
+        lds8v(sp, a);
+        lds8v(sp + Cs, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xh[i] = (fmaf(a[i], u[i], b[i]) + x[i] - mu) * r;
+        lds8v(sp + 3 * Cs, a);
+        lds8v(sp + 4 * Cs, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) uh[i] = (u[i] - a[i]) * b[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xh[i] = (x[i] - mu) * r;
+      }
+      float w[8];
+      lds8v(sp + 2 * Cs, w);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dxh[i] = dz[i] * w[i];
+    }
+    float s2[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s2[0] += dxh[i];
+      s2[1] = fmaf(dxh[i], xh[i], s2[1]);
+    }
+    row_reduce<2>(s2, S, rslot, slice, red, buf);
+    if (act) {
+      const float m1 = s2[0] * invC, m2 = s2[1] * invC;
+      float dv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        dv[i] = r * (dxh[i] - m1 - xh[i] * m2);
+        g_lw[i] = fmaf(dz[i], xh[i], g_lw[i]);
+        g_lb[i] += dz[i];
+        g_ga[i] = fmaf(dv[i], uh[i], g_ga[i]);
+        g_be[i] += dv[i];
+      }
+      store8(dV + row * C + c0, dv);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  float (*acc_sm)[4][ACC_PITCH] = reinterpret_cast<float (*)[4][ACC_PITCH]>(smbuf);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc_sm[warp][0][lane * 8 + i] = g_lw[i];
+    acc_sm[warp][1][lane * 8 + i] = g_lb[i];
+    acc_sm[warp][2][lane * 8 + i] = g_ga[i];
+    acc_sm[warp][3][lane * 8 + i] = g_be[i];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 4 * S * 256; idx += ROW_THREADS) {
+    const int st = idx / (S * 256), cc = idx % (S * 256);
+    const int sl = cc / 256, ci = cc % 256;
+    if (cc < C) {
+      float t = 0.f;
+      for (int rs = 0; rs < RPB; ++rs) t += acc_sm[rs * S + sl][st][ci];
+      part[(static_cast<long long>(blockIdx.x) * 4 + st) * C + cc] = t;
+    }
+  }
+}
+
 // partials [np][4][C] -> parameter gradients + dU coefficient vectors: dU = k1*dV + k2*U + k3   
 __global__ void __launch_bounds__(32 * RED_Y)
     bn_bwd_finalize_kernel(const float* __restrict__ part, int np, int C, double count,
@@ -760,7 +1000,12 @@ int bn_res_ln_fwd(const void* U_, const void* X_, int act_dtype, const float* a,
   const int grid = row_grid(rows, S);
   if (act_dtype == GLF_DTYPE_BF16) {
     const bf16* U = (const bf16*)U_; const bf16* X = (const bf16*)X_;
-    if (z_dtype == GLF_DTYPE_BF16)
+    if (S > 1 && z_dtype == GLF_DTYPE_BF16 && aligned16(U_ != nullptr ? U_ : X_, X_, Z) && !debug_reg_ln()) {
+      const size_t ring = LN_DEPTH * 3 * ROW_THREADS * sizeof(uint4);       // 48 KB
+      cudaError_t e = cudaFuncSetAttribute(bn_res_ln_fwd_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ring));
+      if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(ln fwd ring)");
+      bn_res_ln_fwd_ring_kernel<<<grid, ROW_THREADS, ring, stream>>>(U, X, a, b, lw, lb, (bf16*)Z, mu, r, rows, C, S, eps, accumulate);
+    } else if (z_dtype == GLF_DTYPE_BF16)
       bn_res_ln_fwd_kernel<bf16, bf16><<<grid, ROW_THREADS, 0, stream>>>(U, X, a, b, lw, lb, (bf16*)Z, mu, r, rows, C, S, eps, accumulate);
     else
       bn_res_ln_fwd_kernel<float, bf16><<<grid, ROW_THREADS, 0, stream>>>(U, X, a, b, lw, lb, (float*)Z, mu, r, rows, C, S, eps, accumulate);
@@ -801,7 +1046,12 @@ int bn_res_ln_bwd(const void* dZ, int dz_dtype, const void* U_, const void* X_, 
   if (nblocks) *nblocks = grid;
   if (act_dtype == GLF_DTYPE_BF16) {
     const bf16* U = (const bf16*)U_; const bf16* X = (const bf16*)X_; bf16* dV = (bf16*)dV_;
-    if (dz_dtype == GLF_DTYPE_BF16)
+    if (S > 1 && dz_dtype == GLF_DTYPE_BF16 && aligned16(U_ != nullptr ? U_ : X_, X_, dZ, dV_) && !debug_reg_ln()) {
+      const size_t ring = LN_DEPTH * 3 * ROW_THREADS * sizeof(uint4);
+      cudaError_t e = cudaFuncSetAttribute(bn_res_ln_bwd_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ring));
+      if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(ln bwd ring)");
+      bn_res_ln_bwd_ring_kernel<<<grid, ROW_THREADS, ring, stream>>>((const bf16*)dZ, U, X, a, b, mean, rstd, lw, mu, r, dV, part, rows, C, S);
+    } else if (dz_dtype == GLF_DTYPE_BF16)
       bn_res_ln_bwd_kernel<bf16, bf16><<<grid, ROW_THREADS, 0, stream>>>((const bf16*)dZ, U, X, a, b, mean, rstd, lw, mu, r, dV, part, rows, C, S);
     else
       bn_res_ln_bwd_kernel<float, bf16><<<grid, ROW_THREADS, 0, stream>>>((const float*)dZ, U, X, a, b, mean, rstd, lw, mu, r, dV, part, rows, C, S);
