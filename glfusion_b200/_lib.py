@@ -16,7 +16,8 @@ PRECISION_BF16, PRECISION_F32X3 = 0, 1
 PRECISIONS = {"bf16": PRECISION_BF16, "fp32": PRECISION_F32X3}
 
 EXPORTS = ("glf_version", "glf_last_error", "glf_tpavi_sizes", "glf_tpavi_fwd", "glf_tpavi_bwd",
-           "glf_gate_concat_fwd", "glf_gate_concat_bwd", "glf_views_to_tokens", "glf_gemm_bf16", "glf_transpose", "glf_bn_res_ln_fwd",
+           "glf_gate_concat_fwd", "glf_gate_concat_bwd", "glf_gate_concat_cl_fwd", "glf_gate_concat_cl_bwd",
+           "glf_views_to_tokens", "glf_gemm_bf16", "glf_transpose", "glf_bn_res_ln_fwd",
            "glf_bn_res_ln_bwd", "glf_bn_res_ln_bwd_max_blocks", "glf_gate_concat_bwd_scratch_bytes",
            "glf_fusion_ln_supported", "glf_fusion_ln_fwd", "glf_fusion_ln_fwd_parts", "glf_fusion_ln_bwd",
            "glf_bn_res_ln_pair_fwd",
@@ -104,6 +105,9 @@ def load() -> C.CDLL:
         lib.glf_cycle_loss_scratch_bytes.argtypes = [i32, i32, i32]
         lib.glf_cycle_loss_scratch_bytes.restype = C.c_size_t
         lib.glf_cycle_loss.argtypes = [vp, i32, i32, i32, i32, i32, f32, i32, i32, i32, i32, f32, vp, vp, vp, vp]
+        lib.glf_gate_concat_cl_fwd.argtypes = [i32, i32, i32, i32, i32, i32, f32, i32, pp, vp, vp, pp, pp, vp, vp, vp, vp]
+        lib.glf_gate_concat_cl_bwd.argtypes = [i32, i32, i32, i32, i32, i32, f32, i32, pp, vp, vp, pp, pp, vp, vp, vp, pp, vp,
+                                               vp, pp, pp, vp, vp]
         lib.glf_views_to_tokens.argtypes = [i32, i32, i32, i32, i32, pp, vp, vp, vp, vp, vp]
         lib.glf_bn_res_ln_fwd.argtypes = [i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, f32, i32, vp]
         lib.glf_bn_res_ln_bwd.argtypes = [i64, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,

@@ -1087,6 +1087,39 @@ GLF_API size_t glf_gate_concat_bwd_scratch_bytes(int B, int C, int V, int h, int
   return gate_bwd_scratch_bytes(B, C, V, h, w);
 }
 
+GLF_API int glf_gate_concat_cl_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype,
+                                   const void* const* f4, const int64_t* stride_b, const int64_t* stride_t,
+                                   const float* const* cls, const float* const* ctr, void* xg, void* xl, float* gate,
+                                   glf_stream_t stream) {
+  GLF_TRY(check_device_sm100());
+  if (B <= 0 || C <= 0 || h <= 0 || w <= 0 || ncls <= 0) return set_error(GLF_ERR_INVALID, "gate_concat: empty input");
+  if (f4 == nullptr || cls == nullptr || ctr == nullptr || stride_b == nullptr || stride_t == nullptr)
+    return set_error(GLF_ERR_INVALID, "gate_concat: NULL table");
+  GLF_TRY(check_ptr(xg, "xg"));
+  GLF_TRY(check_ptr(xl, "xl"));
+  return gate_concat_cl_fwd(B, C, V, h, w, ncls, weight, io_dtype, f4, reinterpret_cast<const long long*>(stride_b),
+                            reinterpret_cast<const long long*>(stride_t), cls, ctr, xg, xl, gate,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+GLF_API int glf_gate_concat_cl_bwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype,
+                                   const void* const* f4, const int64_t* stride_b, const int64_t* stride_t,
+                                   const float* const* cls, const float* const* ctr, const float* gate, const void* dxg,
+                                   const void* dxl, void* const* df4, const int64_t* dstride_b, const int64_t* dstride_t,
+                                   float* const* dcls, float* const* dctr, void* scratch, glf_stream_t stream) {
+  GLF_TRY(check_device_sm100());
+  if (B <= 0 || C <= 0 || h <= 0 || w <= 0 || ncls <= 0) return set_error(GLF_ERR_INVALID, "gate_concat: empty input");
+  if (f4 == nullptr || cls == nullptr || ctr == nullptr || df4 == nullptr || dcls == nullptr || dctr == nullptr ||
+      stride_b == nullptr || stride_t == nullptr || dstride_b == nullptr || dstride_t == nullptr)
+    return set_error(GLF_ERR_INVALID, "gate_concat: NULL table");
+  GLF_TRY(check_ptr(dxg, "dxg"));
+  GLF_TRY(check_ptr(dxl, "dxl"));
+  return gate_concat_cl_bwd(B, C, V, h, w, ncls, weight, io_dtype, f4, reinterpret_cast<const long long*>(stride_b),
+                            reinterpret_cast<const long long*>(stride_t), cls, ctr, gate, dxg, dxl, df4,
+                            reinterpret_cast<const long long*>(dstride_b), reinterpret_cast<const long long*>(dstride_t),
+                            dcls, dctr, reinterpret_cast<float*>(scratch), reinterpret_cast<cudaStream_t>(stream));
+}
+
 GLF_API int glf_views_to_tokens(int B, int C, int V, int T, int src_dtype, const void* const* src,
                                 const int64_t* stride_b, const int64_t* stride_c, const int64_t* stride_t, void* out,
                                 glf_stream_t stream) {

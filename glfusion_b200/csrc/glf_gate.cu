@@ -488,6 +488,117 @@ int launch_gate_bwd(dim3 grid, bool vec2, int io_dtype, const ViewPtrs& vp, cons
   return check_cuda(cudaGetLastError(), "gate_concat_bwd launch");
 }
 
+// ---------------------------------------------------------------------------------------------- channels-last views
+// when the backbones / heads run channels_last (bf16 autocast), f4[view] arrives as [B, h*w, C]
+// rows already - the layout the blocks want - and the NCHW transposition above disappears: gate + concat is a pure row
+// kernel (one warp per token, 16-byte accesses along C), and df4 goes back in the same memory format so that the conv
+// backward that consumes it stays channels_last.  CL_TOK tokens per warp are kept in flight together.
+constexpr int CL_TOK = 4;
+struct ClViews {
+  const void* f4[MAXV];
+  void* df4[MAXV];
+  long long sb[MAXV], st[MAXV];       // element strides of batch / token of f4[v]   (channel stride 1)
+  long long dsb[MAXV], dst[MAXV];     // ... of df4[v]
+};
+
+template <typename TIO>
+__global__ void __launch_bounds__(256)
+    gate_cl_fwd_kernel(const ClViews cv, const ViewPtrs vp, bf16* __restrict__ xg, bf16* __restrict__ xl,
+                       float* __restrict__ gate, int C, int V, int hw, int ncls, float weight) {
+  __shared__ float a_sm[8 * CL_TOK];
+  const int bv = blockIdx.y, b = bv / V, v = bv % V;
+  const int p0 = blockIdx.x * 8 * CL_TOK;
+  if (threadIdx.x < 8 * CL_TOK) {
+    const int p = p0 + threadIdx.x;
+    float a = 0.f;
+    if (p < hw) {
+      const float* cl = vp.cls[v] + static_cast<long long>(b) * ncls * hw + p;
+      float lmax = cl[0];
+      for (int k = 1; k < ncls; ++k) lmax = fmaxf(lmax, cl[static_cast<long long>(k) * hw]);
+      const float m = sigmoidf_(lmax);
+      const float c = sigmoidf_(vp.ctr[v][static_cast<long long>(b) * hw + p]);
+      a = sigmoidf_(weight * m * c);
+      gate[static_cast<long long>(bv) * hw + p] = a;
+    }
+    a_sm[threadIdx.x] = a;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const TIO* src = reinterpret_cast<const TIO*>(cv.f4[v]) + b * cv.sb[v];
+  const long long st = cv.st[v];
+  for (int c = lane * 8; c < C; c += 256) {
+    float f[CL_TOK][8];
+#pragma unroll
+    for (int k = 0; k < CL_TOK; ++k) {
+      const int p = p0 + warp * CL_TOK + k;
+      if (p < hw) ld8(src + p * st + c, f[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < CL_TOK; ++k) {
+      const int p = p0 + warp * CL_TOK + k;
+      if (p < hw) {
+        const float a = a_sm[warp * CL_TOK + k];
+        float g[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = f[k][i] * a;
+        const long long o = (static_cast<long long>(bv) * hw + p) * C + c;
+        st8(xg + o, f[k]);
+        st8(xl + o, g);
+      }
+    }
+  }
+}
+
+template <typename TIO>
+__global__ void __launch_bounds__(256)
+    gate_cl_bwd_kernel(const ClViews cv, const float* __restrict__ gate, const bf16* __restrict__ dxg,
+                       const bf16* __restrict__ dxl, float* __restrict__ da, int C, int V, int hw) {
+  const int bv = blockIdx.y, b = bv / V, v = bv % V;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p0 = blockIdx.x * 8 * CL_TOK + warp * CL_TOK;
+  const TIO* src = reinterpret_cast<const TIO*>(cv.f4[v]) + b * cv.sb[v];
+  TIO* dst = reinterpret_cast<TIO*>(cv.df4[v]) + b * cv.dsb[v];
+  const long long st = cv.st[v], dstt = cv.dst[v];
+  float a[CL_TOK], acc[CL_TOK];
+#pragma unroll
+  for (int k = 0; k < CL_TOK; ++k) {
+    a[k] = p0 + k < hw ? gate[static_cast<long long>(bv) * hw + p0 + k] : 0.f;
+    acc[k] = 0.f;
+  }
+  for (int c = lane * 8; c < C; c += 256) {
+    float f[CL_TOK][8], g[CL_TOK][8], l[CL_TOK][8];
+#pragma unroll
+    for (int k = 0; k < CL_TOK; ++k) {
+      const int p = p0 + k;
+      if (p < hw) {
+        const long long o = (static_cast<long long>(bv) * hw + p) * C + c;
+        ld8(src + p * st + c, f[k]);
+        ld8(dxg + o, g[k]);
+        ld8(dxl + o, l[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < CL_TOK; ++k) {
+      const int p = p0 + k;
+      if (p < hw) {
+        float d[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          d[i] = fmaf(a[k], l[k][i], g[k][i]);
+          acc[k] = fmaf(f[k][i], l[k][i], acc[k]);
+        }
+        st8(dst + p * dstt + c, d);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < CL_TOK; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    if (lane == 0 && p0 + k < hw) da[static_cast<long long>(bv) * hw + p0 + k] = acc[k];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- views -> tokens
 // The dict-keyed call site hands the backward one gradient per view ([B, C, h, w], NCHW or channels-last strides);
 // the blocks want ONE token-major [B, V, h*w, C] bf16 buffer (the layout ours.py:1819-1820 builds forward).  One
@@ -698,6 +809,73 @@ int gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, i
   const long long n = static_cast<long long>(B) * V * hw;
   gate_finish_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(vp, gate, da_part, nct, B * V, V, hw, ncls,
                                                                                 weight);
+  return check_cuda(cudaGetLastError(), "gate_finish launch");
+}
+
+namespace {
+int cl_check(int B, int C, int V, int hw, int io_dtype, const void* const* f4, const long long* sb, const long long* st) {
+  if (V < 1 || V > MAXV) return set_error(GLF_ERR_INVALID, "gate_concat: 1 <= V <= %d", MAXV);
+  if (C % 8 != 0) return set_error(GLF_ERR_INVALID, "gate_concat: C %% 8 != 0");
+  if (io_dtype != GLF_DTYPE_BF16 && io_dtype != GLF_DTYPE_F32) return set_error(GLF_ERR_INVALID, "gate_concat: bad dtype");
+  if (static_cast<long long>(B) * V > 65535) return set_error(GLF_ERR_UNSUPPORTED, "gate_concat: B * V > 65535");
+  const long long per16 = io_dtype == GLF_DTYPE_BF16 ? 8 : 4;
+  for (int v = 0; v < V; ++v)
+    if (f4[v] == nullptr || (reinterpret_cast<uintptr_t>(f4[v]) & 15) != 0 || sb[v] % per16 != 0 || st[v] % per16 != 0 ||
+        st[v] < C || (B > 1 && sb[v] < 1))
+      return set_error(GLF_ERR_INVALID, "gate_concat (channels-last): view %d needs 16-byte aligned rows of C channels", v);
+  (void)hw;
+  return 0;
+}
+}  // namespace
+
+int gate_concat_cl_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, const void* const* f4,
+                       const long long* sb, const long long* st, const float* const* cls, const float* const* ctr,
+                       void* xg, void* xl, float* gate, cudaStream_t stream) {
+  const int hw = h * w;
+  int rc = cl_check(B, C, V, hw, io_dtype, f4, sb, st);
+  if (rc) return rc;
+  ViewPtrs vp{};
+  ClViews cv{};
+  for (int v = 0; v < V; ++v) {
+    vp.cls[v] = cls[v]; vp.ctr[v] = ctr[v];
+    cv.f4[v] = f4[v]; cv.sb[v] = sb[v]; cv.st[v] = st[v];
+  }
+  const dim3 grid((hw + 8 * CL_TOK - 1) / (8 * CL_TOK), B * V);
+  if (io_dtype == GLF_DTYPE_BF16)
+    gate_cl_fwd_kernel<bf16><<<grid, 256, 0, stream>>>(cv, vp, reinterpret_cast<bf16*>(xg), reinterpret_cast<bf16*>(xl), gate, C, V, hw, ncls, weight);
+  else
+    gate_cl_fwd_kernel<float><<<grid, 256, 0, stream>>>(cv, vp, reinterpret_cast<bf16*>(xg), reinterpret_cast<bf16*>(xl), gate, C, V, hw, ncls, weight);
+  return check_cuda(cudaGetLastError(), "gate_cl_fwd launch");
+}
+
+int gate_concat_cl_bwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, const void* const* f4,
+                       const long long* sb, const long long* st, const float* const* cls, const float* const* ctr,
+                       const float* gate, const void* dxg, const void* dxl, void* const* df4, const long long* dsb,
+                       const long long* dst, float* const* dcls, float* const* dctr, float* da, cudaStream_t stream) {
+  const int hw = h * w;
+  int rc = cl_check(B, C, V, hw, io_dtype, f4, sb, st);
+  if (rc) return rc;
+  rc = cl_check(B, C, V, hw, io_dtype, df4, dsb, dst);
+  if (rc) return rc;
+  if (da == nullptr) return set_error(GLF_ERR_WORKSPACE, "gate_concat_bwd: scratch is NULL");
+  if (((reinterpret_cast<uintptr_t>(dxg) | reinterpret_cast<uintptr_t>(dxl)) & 15) != 0)
+    return set_error(GLF_ERR_INVALID, "gate_concat_bwd: dxg / dxl must be 16-byte aligned");
+  ViewPtrs vp{};
+  ClViews cv{};
+  for (int v = 0; v < V; ++v) {
+    vp.cls[v] = cls[v]; vp.ctr[v] = ctr[v]; vp.dcls[v] = dcls[v]; vp.dctr[v] = dctr[v];
+    cv.f4[v] = f4[v]; cv.sb[v] = sb[v]; cv.st[v] = st[v];
+    cv.df4[v] = df4[v]; cv.dsb[v] = dsb[v]; cv.dst[v] = dst[v];
+  }
+  const dim3 grid((hw + 8 * CL_TOK - 1) / (8 * CL_TOK), B * V);
+  if (io_dtype == GLF_DTYPE_BF16)
+    gate_cl_bwd_kernel<bf16><<<grid, 256, 0, stream>>>(cv, gate, reinterpret_cast<const bf16*>(dxg), reinterpret_cast<const bf16*>(dxl), da, C, V, hw);
+  else
+    gate_cl_bwd_kernel<float><<<grid, 256, 0, stream>>>(cv, gate, reinterpret_cast<const bf16*>(dxg), reinterpret_cast<const bf16*>(dxl), da, C, V, hw);
+  rc = check_cuda(cudaGetLastError(), "gate_cl_bwd launch");
+  if (rc) return rc;
+  const long long n = static_cast<long long>(B) * V * hw;
+  gate_finish_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(vp, gate, da, 1, B * V, V, hw, ncls, weight);
   return check_cuda(cudaGetLastError(), "gate_finish launch");
 }
 

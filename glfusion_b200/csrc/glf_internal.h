@@ -150,6 +150,15 @@ int gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, i
                     const void* dxg, const void* dxl, void* const* df4, float* const* dcls, float* const* dctr,
                     float* da_part, cudaStream_t stream);
 size_t gate_bwd_scratch_bytes(int B, int C, int V, int h, int w);
+// channels-last views (element (b, c, t) at b*sb + t*st + c): gate + concat / its backward as row kernels; df4 in the
+// layout given by dsb / dst; da: [B*V*h*w] floats of scratch (gate_bwd_scratch_bytes covers it)
+int gate_concat_cl_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, const void* const* f4,
+                       const long long* sb, const long long* st, const float* const* cls, const float* const* ctr,
+                       void* xg, void* xl, float* gate, cudaStream_t stream);
+int gate_concat_cl_bwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, const void* const* f4,
+                       const long long* sb, const long long* st, const float* const* cls, const float* const* ctr,
+                       const float* gate, const void* dxg, const void* dxl, void* const* df4, const long long* dsb,
+                       const long long* dst, float* const* dcls, float* const* dctr, float* da, cudaStream_t stream);
 // per-view [B,C,h,w] tensors (element strides sb / sc / st of batch, channel, collapsed h*w) -> token-major
 // [B, V, T, C] bf16; a NULL view is written as zeros
 int views_to_tokens(int B, int C, int V, int T, int src_dtype, const void* const* src, const long long* sb,

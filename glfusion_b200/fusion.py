@@ -49,6 +49,29 @@ def _pair_ln_ok(mg, ml, shape, x, prec) -> bool:
     return bool(L.load().glf_fusion_ln_supported(C.byref(st.desc)))
 
 
+def _channels_last_rows(views: Sequence[torch.Tensor], x_dtype) -> Optional[tuple]:
+    """(batch strides, token strides) when every [B,C,h,w] view is made of 16-byte aligned rows of C channels
+    (channels_last tensors, or views of a token-major stack): the case the row kernels glf_gate_concat_cl_* take
+    without any transposition.  None otherwise."""
+    if x_dtype != torch.bfloat16 or len(views) > 8:
+        return None
+    dt = views[0].dtype
+    if dt not in (torch.bfloat16, torch.float32):
+        return None
+    per16 = 8 if dt == torch.bfloat16 else 4
+    B, C_, h, w = views[0].shape
+    if C_ % 8 or B * len(views) > 65535:
+        return None
+    sb, st = [], []
+    for t in views:
+        b_, c_, h_, w_ = t.stride()
+        if (t.dtype != dt or tuple(t.shape) != (B, C_, h, w) or c_ != 1 or h_ != w * w_ or w_ < C_ or w_ % per16
+                or b_ % per16 or t.data_ptr() % 16 or (B > 1 and b_ < 1)):
+            return None
+        sb.append(b_); st.append(w_)
+    return sb, st
+
+
 def gate_concat_forward(f4: Sequence[torch.Tensor], cls: Sequence[torch.Tensor], ctr: Sequence[torch.Tensor],
                         weight: float, x_dtype=torch.bfloat16):
     lib = L.load()
@@ -57,13 +80,23 @@ def gate_concat_forward(f4: Sequence[torch.Tensor], cls: Sequence[torch.Tensor],
     dev = f4[0].device
     if not all(t.is_cuda for t in list(f4) + list(cls) + list(ctr)):
         raise L.GlfError("glfusion_b200 runs on CUDA (sm_100) tensors only; there is no CPU path")
-    f4 = [t.contiguous() for t in f4]
     cls = [t.float().contiguous() for t in cls]
     ctr = [t.float().contiguous() for t in ctr]
     ncls = cls[0].shape[1]
     xg = torch.empty((B, V, h, w, C_), dtype=x_dtype, device=dev)
     xl = torch.empty_like(xg)
     gate = torch.empty((B, V, h, w), dtype=torch.float32, device=dev)
+    rows = _channels_last_rows(f4, x_dtype)
+    if rows is not None:
+        # channels_last hand-off: the views are already rows of C channels, nothing is transposed
+        f4 = list(f4)
+        i64 = C.c_int64 * V
+        with torch.cuda.device(dev):
+            L.check(lib.glf_gate_concat_cl_fwd(B, C_, V, h, w, ncls, float(weight), _io_dtype(f4[0]), L.ptr_table(f4),
+                                               i64(*rows[0]), i64(*rows[1]), L.ptr_table(cls), L.ptr_table(ctr),
+                                               L.ptr(xg), L.ptr(xl), L.ptr(gate), _stream_ptr()))
+        return xg, xl, gate, f4, cls, ctr
+    f4 = [t.contiguous() for t in f4]
     with torch.cuda.device(dev):
         L.check(lib.glf_gate_concat_fwd(B, C_, V, h, w, ncls, float(weight), _io_dtype(f4[0]), _io_dtype(xg),
                                         L.ptr_table(f4),
@@ -110,11 +143,25 @@ def gate_concat_backward(f4, cls, ctr, gate, dxg, dxl, weight: float):
     V = len(f4)
     B, C_, h, w = f4[0].shape
     ncls = cls[0].shape[1]
-    df4 = [torch.empty_like(t) for t in f4]
     dcls = [torch.empty_like(t) for t in cls]
     dctr = [torch.empty_like(t) for t in ctr]
     scratch = torch.empty(max(int(lib.glf_gate_concat_bwd_scratch_bytes(B, C_, V, h, w)), 256), dtype=torch.uint8,
                           device=f4[0].device)
+    rows = _channels_last_rows(f4, dxg.dtype)
+    if rows is not None and dxg.is_contiguous() and dxl.is_contiguous():
+        # gradients go back in the views' own memory format (channels_last), so the conv backward stays channels_last
+        df4 = [torch.empty((B, h, w, C_), dtype=t.dtype, device=t.device).permute(0, 3, 1, 2) for t in f4]
+        i64 = C.c_int64 * V
+        dsb, dst = [h * w * C_] * V, [C_] * V
+        with torch.cuda.device(f4[0].device):
+            L.check(lib.glf_gate_concat_cl_bwd(B, C_, V, h, w, ncls, float(weight), _io_dtype(f4[0]), L.ptr_table(f4),
+                                               i64(*rows[0]), i64(*rows[1]), L.ptr_table(cls), L.ptr_table(ctr),
+                                               L.ptr(gate), L.ptr(dxg), L.ptr(dxl), L.ptr_table(df4), i64(*dsb),
+                                               i64(*dst), L.ptr_table(dcls), L.ptr_table(dctr), L.ptr(scratch),
+                                               _stream_ptr()))
+        return df4, dcls, dctr
+    f4 = [t.contiguous() for t in f4]
+    df4 = [torch.empty_like(t) for t in f4]
     with torch.cuda.device(f4[0].device):
         L.check(lib.glf_gate_concat_bwd(B, C_, V, h, w, ncls, float(weight), _io_dtype(f4[0]), _io_dtype(dxg),
                                         L.ptr_table(f4),

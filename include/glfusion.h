@@ -163,6 +163,22 @@ GLF_API int glf_gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, flo
                         const void* dxg, const void* dxl, void* const* df4, float* const* dcls, float* const* dctr,
                         void* scratch, glf_stream_t stream);
 
+/* The same two steps for CHANNELS-LAST views (backbones / heads run channels_last, so
+ * f4[v] arrives as rows of C channels — element (b, c, t) at b*stride_b[v] + t*stride_t[v] + c, t = y*w + x): no
+ * transposition is left, gate + concat is a row kernel, and df4[v] is written in the layout dstride_b / dstride_t
+ * describe (channels-last again, so the conv backward that consumes it stays channels_last).  io_dtype: dtype of f4 /
+ * df4; xg / xl / dxg / dxl bf16 token-major; cls / ctr logits and their gradients fp32 NCHW as above; rows must be
+ * 16-byte aligned.  scratch: glf_gate_concat_bwd_scratch_bytes bytes. */
+GLF_API int glf_gate_concat_cl_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype,
+                           const void* const* f4, const int64_t* stride_b, const int64_t* stride_t,
+                           const float* const* cls, const float* const* ctr, void* xg, void* xl, float* gate,
+                           glf_stream_t stream);
+GLF_API int glf_gate_concat_cl_bwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype,
+                           const void* const* f4, const int64_t* stride_b, const int64_t* stride_t,
+                           const float* const* cls, const float* const* ctr, const float* gate, const void* dxg,
+                           const void* dxl, void* const* df4, const int64_t* dstride_b, const int64_t* dstride_t,
+                           float* const* dcls, float* const* dctr, void* scratch, glf_stream_t stream);
+
 /* The dict-keyed call site's backward: V per-view gradients ([B, C, h, w]; element strides of batch / channel / the
  * collapsed h*w axis given per view, one of the last two must be 1: NCHW or channels-last) gathered into ONE
  * token-major [B, V, T, C] bf16 buffer, the transposition ours.py:1819-1820 performs forward (permute + cat).  A NULL

@@ -129,6 +129,22 @@ def parts_section(out):
                      ("forward_parts_cycle_pass", parts_cycle), ("forward_parts_cycle_pass_fused_loss", parts_cycle_fused)):
         ms = graph_time(fn)
         res[name] = {"ms_per_step": round(ms, 4), "clips_per_s": round(clips / (ms * 1e-3), 1)}
+    # the same step WITHOUT a CUDA graph (nn.DataParallel callers of the reference are eager): device time per step and
+    # the host time it takes to enqueue one (blob allocation, parameter tables, ~100 tensor-map encodes, 27 launches)
+    import time
+    for _ in range(5):
+        stacked()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        stacked()
+    t1 = time.perf_counter()
+    e1.record()
+    torch.cuda.synchronize()
+    res["forward_stacked_eager"] = {"ms_per_step": round(e0.elapsed_time(e1) / 20, 4),
+                                    "host_enqueue_ms_per_step": round((t1 - t0) * 1e3 / 20, 4)}
     feat = torch.randn(B, C, device=DEV).cumsum(0).requires_grad_(True)
 
     def loss_alone():         # dense_seg_cycle forward + backward on [128 frames, 256] features: 2 launches + 1 multiply

@@ -344,3 +344,48 @@ def test_views_to_tokens_is_the_per_view_transposition(h, w, Cn, src):
     assert not views_to_tokens([None] * V, out)
     if w > 1:
         assert not views_to_tokens([views[0].transpose(2, 3).contiguous().transpose(2, 3)] + views[1:], out)   # h-major
+
+
+@pytest.mark.parametrize("io", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("Cn,h,w", [(256, 28, 28), (128, 5, 7), (2048, 6, 6)])
+def test_channels_last_hand_off_matches_nchw(io, Cn, h, w):
+    """backbones / heads that run channels_last hand f4 over as rows of C channels.  The fused
+    node then takes the row kernels (glf_gate_concat_cl_*, no transposition) and returns df4 channels_last; outputs and
+    every gradient agree with the NCHW path on the same values."""
+    torch.manual_seed(0)
+    B, V = 3, 3
+    fus = GlobalLocalFusion(Cn).to(DEV)
+    from bench import randomize_affine_
+    randomize_affine_(fus.global_attn, 5)
+    randomize_affine_(fus.local_attn, 6)
+    gen = torch.Generator().manual_seed(4)
+    base = [torch.randn(B, Cn, h, w, generator=gen).to(DEV).to(io) for _ in range(V)]
+    cl = [torch.randn(B, 4, h, w, generator=gen).to(DEV) for _ in range(V)]
+    ct = [torch.randn(B, 1, h, w, generator=gen).to(DEV) for _ in range(V)]
+    dz = torch.randn(B, V, h, w, Cn, generator=gen).to(DEV).to(torch.bfloat16).permute(0, 4, 1, 2, 3)
+    res = []
+    for fmt in ("nchw", "channels_last"):
+        f4 = [t.clone() if fmt == "nchw" else t.clone().contiguous(memory_format=torch.channels_last) for t in base]
+        lc = [t.clone().requires_grad_(True) for t in cl]
+        lt = [t.clone().requires_grad_(True) for t in ct]
+        for t in f4:
+            t.requires_grad_(True)
+        for p in fus.parameters():
+            p.grad = None
+        out = fus.forward_stacked(f4, lc, lt)
+        out.backward(dz)
+        if fmt == "channels_last":
+            for t in f4:     # the gradient comes back in the view's own memory format
+                assert t.grad.is_contiguous(memory_format=torch.channels_last) and t.grad.dtype == io
+        res.append((out.detach().float(), [t.grad.float() for t in f4], [t.grad for t in lc], [t.grad for t in lt],
+                    [p.grad.clone() for p in fus.parameters() if p.grad is not None]))
+    (o0, g0, c0, t0, p0), (o1, g1, c1, t1, p1) = res
+    # forward: the same products, only the read pattern differs; not bit-equal because fewer than 96 sequences split the
+    # token contractions with fp32 atomics (run-to-run summation order)
+    assert (o0 - o1).abs().max().item() <= 1e-2 * o0.abs().max().item()
+    for a, b in zip(g0, g1):
+        assert (a - b).abs().max().item() <= 8e-3 * a.abs().max().item()      # one bf16 rounding of dxg + a * dxl
+    for a, b in zip(c0 + t0, c1 + t1):
+        assert (a - b).abs().max().item() <= 2e-2 * max(a.abs().max().item(), 1e-6) + 1e-9   # sums of bf16 dxl products
+    for a, b in zip(p0, p1):                         # the blocks see identical inputs
+        assert (a - b).abs().max().item() <= 5e-3 * max(a.abs().max().item(), 1e-6) + 1e-7
