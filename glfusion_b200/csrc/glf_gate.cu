@@ -501,8 +501,32 @@ struct ClViews {
   long long dsb[MAXV], dst[MAXV];     // ... of df4[v]
 };
 
+// raw (still packed) 8-channel vectors: all of a step's loads are issued before the first conversion, and the packed
+// form keeps CL_TOK tokens x 3 operands within ~50 registers (the converted form needed 156: one CTA per SM)
+template <typename T> struct RawCl;
+template <> struct RawCl<bf16> { uint4 v; };
+template <> struct RawCl<float> { float4 a, b; };
+__device__ __forceinline__ void ldr(const bf16* p, RawCl<bf16>& r) { r.v = __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void ldr(const float* p, RawCl<float>& r) {
+  r.a = __ldg(reinterpret_cast<const float4*>(p));
+  r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+}
+__device__ __forceinline__ void cvr(const RawCl<bf16>& r, float (&f)[8]) {
+  const uint32_t* u = reinterpret_cast<const uint32_t*>(&r.v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = unpack_bf16(u[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void cvr(const RawCl<float>& r, float (&f)[8]) {
+  f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w;
+  f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+}
+
 template <typename TIO>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
     gate_cl_fwd_kernel(const ClViews cv, const ViewPtrs vp, bf16* __restrict__ xg, bf16* __restrict__ xl,
                        float* __restrict__ gate, int C, int V, int hw, int ncls, float weight) {
   __shared__ float a_sm[8 * CL_TOK];
@@ -527,22 +551,23 @@ __global__ void __launch_bounds__(256)
   const TIO* src = reinterpret_cast<const TIO*>(cv.f4[v]) + b * cv.sb[v];
   const long long st = cv.st[v];
   for (int c = lane * 8; c < C; c += 256) {
-    float f[CL_TOK][8];
+    RawCl<TIO> r[CL_TOK];
 #pragma unroll
     for (int k = 0; k < CL_TOK; ++k) {
       const int p = p0 + warp * CL_TOK + k;
-      if (p < hw) ld8(src + p * st + c, f[k]);
+      if (p < hw) ldr(src + p * st + c, r[k]);
     }
 #pragma unroll
     for (int k = 0; k < CL_TOK; ++k) {
       const int p = p0 + warp * CL_TOK + k;
       if (p < hw) {
         const float a = a_sm[warp * CL_TOK + k];
-        float g[8];
+        float f[8], g[8];
+        cvr(r[k], f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = f[k][i] * a;
+        for (int i = 0; i < 8; ++i) g[i] = f[i] * a;
         const long long o = (static_cast<long long>(bv) * hw + p) * C + c;
-        st8(xg + o, f[k]);
+        st8(xg + o, f);
         st8(xl + o, g);
       }
     }
@@ -550,7 +575,7 @@ __global__ void __launch_bounds__(256)
 }
 
 template <typename TIO>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
     gate_cl_bwd_kernel(const ClViews cv, const float* __restrict__ gate, const bf16* __restrict__ dxg,
                        const bf16* __restrict__ dxl, float* __restrict__ da, int C, int V, int hw) {
   const int bv = blockIdx.y, b = bv / V, v = bv % V;
@@ -566,26 +591,30 @@ __global__ void __launch_bounds__(256)
     acc[k] = 0.f;
   }
   for (int c = lane * 8; c < C; c += 256) {
-    float f[CL_TOK][8], g[CL_TOK][8], l[CL_TOK][8];
+    RawCl<TIO> rf[CL_TOK];
+    RawCl<bf16> rg[CL_TOK], rl[CL_TOK];
 #pragma unroll
     for (int k = 0; k < CL_TOK; ++k) {
       const int p = p0 + k;
       if (p < hw) {
         const long long o = (static_cast<long long>(bv) * hw + p) * C + c;
-        ld8(src + p * st + c, f[k]);
-        ld8(dxg + o, g[k]);
-        ld8(dxl + o, l[k]);
+        ldr(src + p * st + c, rf[k]);
+        ldr(dxg + o, rg[k]);
+        ldr(dxl + o, rl[k]);
       }
     }
 #pragma unroll
     for (int k = 0; k < CL_TOK; ++k) {
       const int p = p0 + k;
       if (p < hw) {
-        float d[8];
+        float f[8], g[8], l[8], d[8];
+        cvr(rf[k], f);
+        cvr(rg[k], g);
+        cvr(rl[k], l);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          d[i] = fmaf(a[k], l[k][i], g[k][i]);
-          acc[k] = fmaf(f[k][i], l[k][i], acc[k]);
+          d[i] = fmaf(a[k], l[i], g[i]);
+          acc[k] = fmaf(f[i], l[i], acc[k]);
         }
         st8(dst + p * dstt + c, d);
       }

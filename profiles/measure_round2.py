@@ -124,8 +124,16 @@ def parts_section(out):
         zero()
         fus, glob, _ = f.forward_parts(dict(zip(keys, f4)), dict(zip(keys, cl)), dict(zip(keys, ct)), need_local=False)
         sum(cycle.dense_seg_cycle(cycle.spatial_sum(glob[k]), 16, 2, 3, 10.0) for k in keys).backward()
+    f4cl = [t.detach().clone().contiguous(memory_format=torch.channels_last).requires_grad_(True) for t in f4]
+
+    def stacked_cl():         # channels_last views -> the row kernels, no transposition either way
+        for t in f4cl:
+            t.grad = None
+        for p in params:
+            p.grad = None
+        f.forward_stacked(f4cl, cl, ct).backward(dz)
     res = {}
-    for name, fn in (("forward_stacked", stacked), ("forward_dict_api", dict_api), ("forward_parts_supervised_pass", parts_seg),
+    for name, fn in (("forward_stacked", stacked), ("forward_stacked_channels_last_inputs", stacked_cl), ("forward_dict_api", dict_api), ("forward_parts_supervised_pass", parts_seg),
                      ("forward_parts_cycle_pass", parts_cycle), ("forward_parts_cycle_pass_fused_loss", parts_cycle_fused)):
         ms = graph_time(fn)
         res[name] = {"ms_per_step": round(ms, 4), "clips_per_s": round(clips / (ms * 1e-3), 1)}
