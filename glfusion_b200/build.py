@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libglf_sm100a.so")
 STAMP = os.path.join(HERE, ".libglf_sm100a.stamp")
-SOURCES = ["glf_api.cu", "glf_api_f32.cu", "glf_gemm.cu", "glf_gemm2.cu", "glf_eltwise.cu", "glf_gate.cu", "glf_flash.cu", "glf_ln.cu", "glf_gram.cu", "glf_gramk.cu", "glf_chain.cu", "glf_wgrad.cu", "glf_cycle.cu", "glf_p2p.cu"]
+SOURCES = ["glf_api.cu", "glf_api_f32.cu", "glf_gemm.cu", "glf_gemm2.cu", "glf_gemm3.cu", "glf_eltwise.cu", "glf_gate.cu", "glf_flash.cu", "glf_ln.cu", "glf_gram.cu", "glf_gramk.cu", "glf_chain.cu", "glf_wgrad.cu", "glf_cycle.cu", "glf_p2p.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-cudart", "static"]
 

@@ -724,6 +724,7 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
     return set_error(GLF_ERR_DEVICE, "gemm: cannot query the SM count");
   const bool amn = a.A.mn_major != 0, bmn = a.B.mn_major != 0;
   // the big K-major products with N = 256 (U, dX of the Gram form) run on CTA pairs (glf_gemm2.cu)
+  if (gemm_bres_applicable(a, num_sms)) return gemm_bres(a, num_sms, stream);
   if (gemm_pair_applicable(a, num_sms)) return gemm_pair(a, num_sms, stream);
   // GLF_GEMM_WIDE2=1 (or bn_hint = 512): 256 x 256 CTA tiles for N == 256 (one n-tile: the A operand crosses the
   // L2 -> SM fabric once, the B operand once per 256 rows)

@@ -55,6 +55,10 @@ int make_output_tmap(CUtensorMap* tm, void* D, int M, int N, int batch, long lon
 // (glf_gemm2.cu) the big K-major products with N = 256 on CTA pairs (cta_group::2); false = not applicable / disabled
 bool gemm_pair_applicable(const GemmArgs& a, int num_sms);
 int gemm_pair(const GemmArgs& a, int num_sms, cudaStream_t stream);
+// (glf_gemm3.cu) K-major products with N = 256, K <= 256 whose B operand is shared by many row tiles (U = X Q^T + c per
+// sequence): B resident in shared memory, only A streams
+bool gemm_bres_applicable(const GemmArgs& a, int num_sms);
+int gemm_bres(const GemmArgs& a, int num_sms, cudaStream_t stream);
 int make_tmap_bf16(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long batch, long long ld,
                    long long batch_stride, int box_outer);
 

@@ -126,6 +126,27 @@ def test_gemm_cta_pair_epilogues():
         assert O.rel_err(D3, torch.matmul(A2f, B2f.transpose(1, 2)) / K2) < 1e-5
 
 
+@pytest.mark.parametrize("M,K,batch,shared_b", [(3136, 256, 16, False), (1000, 128, 40, False), (50176, 128, 1, True),
+                                                 (2049, 64, 20, False)])
+def test_gemm_resident_b_operand(M, K, batch, shared_b):
+    """N = 256, K <= 256, many row tiles per B operand: the kernel that keeps B in shared memory and streams only A
+    (csrc/glf_gemm3.cu; U = X Q^T + c of the Gram form).  CTAs own contiguous tile ranges that straddle batch entries;
+    ragged M; per-batch bias; BatchNorm column statistics as per-CTA running sums."""
+    N = 256
+    A, Af = _mk(batch, M, K, 0, 21)
+    B, Bf = _mk(1 if shared_b else batch, N, K, 0, 22)
+    ref = torch.matmul(Af, Bf.transpose(1, 2))
+    D, _ = gemm(A, B, M, N, K, batch, shared_b=shared_b)
+    assert O.rel_err(D, ref) < 6e-3
+    bias = torch.randn(N, device=DEV)
+    D, cs = gemm(A, B, M, N, K, batch, bias=bias, alpha=0.5, colstats=True, shared_b=shared_b)
+    assert O.rel_err(D, 0.5 * ref + bias.cpu()) < 6e-3
+    cs = cs.sum(0).cpu()
+    Dr = D.float().cpu()
+    assert O.rel_err(cs[0], Dr.sum((0, 1))) < 1e-4
+    assert O.rel_err(cs[1], (Dr * Dr).sum((0, 1))) < 1e-4
+
+
 def test_transpose_pack_roundtrip():
     import ctypes as C
     from glfusion_b200 import _lib as L
