@@ -650,83 +650,80 @@ __global__ void __launch_bounds__(256) views_to_tokens_kernel(ViewsToTokens P, b
   __shared__ float tile[64][65];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int tiles_c = C / 64;
-  const int t0 = (blockIdx.x / tiles_c) * 64, c0 = (blockIdx.x % tiles_c) * 64;
+  // a CTA owns TWO consecutive 64-token tiles of one 64-channel slab: four 16-byte accesses in flight per thread
+  const int tbase = (blockIdx.x / tiles_c) * 128, c0 = (blockIdx.x % tiles_c) * 64;
   const int v = blockIdx.y, b = blockIdx.z;
   bf16* o = out + ((static_cast<long long>(b) * V + v) * T) * C;
   if (!P.present[v]) {                                       // a view without a gradient contributes zeros
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int t = t0 + ty + 8 * i;
+    for (int i = 0; i < 16; ++i) {
+      const int t = tbase + ty + 8 * i;
       if (t < T) *reinterpret_cast<__nv_bfloat162*>(o + static_cast<long long>(t) * C + c0 + 2 * tx) = __floats2bfloat162_rn(0.f, 0.f);
     }
     return;
   }
   const TIn* src = reinterpret_cast<const TIn*>(P.src[v]) + b * P.sb[v];
   const long long sc = P.sc[v], st = P.st[v];
-  if (sc == 1) {                                             // channels-last: rows of C contiguous elements
-    if (P.vec[v]) {                                          // 16-byte accesses: 8 channels per thread, loads first
-      float f[2][8];
-      int tt[2];
+  if (sc == 1 && P.vec[v]) {                                 // channels-last rows, 16-byte accesses, loads first
+    RawCl<TIn> raw[4];
+    int tt[4];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int item = threadIdx.x + 256 * i;
-        tt[i] = t0 + (item >> 3);
-        const TIn* r = src + tt[i] * st + c0 + 8 * (item & 7);
-        if (tt[i] < T) {
-          if constexpr (sizeof(TIn) == 2) {
-            const uint4 q = __ldg(reinterpret_cast<const uint4*>(r));
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { const float2 p = __bfloat1622float2(h2[j]); f[i][2 * j] = p.x; f[i][2 * j + 1] = p.y; }
-          } else {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(r)), b4 = __ldg(reinterpret_cast<const float4*>(r) + 1);
-            f[i][0] = a.x; f[i][1] = a.y; f[i][2] = a.z; f[i][3] = a.w;
-            f[i][4] = b4.x; f[i][5] = b4.y; f[i][6] = b4.z; f[i][7] = b4.w;
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        if (tt[i] < T) {
-          uint4 q;
-          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&q);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(f[i][2 * j], f[i][2 * j + 1]);
-          *reinterpret_cast<uint4*>(o + static_cast<long long>(tt[i]) * C + c0 + 8 * ((threadIdx.x + 256 * i) & 7)) = q;
-        }
-      }
-      return;
-    }
-    float lo[8], hi[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int t = t0 + ty + 8 * i;
-      const TIn* r = src + t * st + c0 + 2 * tx;
-      lo[i] = t < T ? ld_as_float<TIn>(r) : 0.f;
-      hi[i] = t < T ? ld_as_float<TIn>(r + 1) : 0.f;
+    for (int i = 0; i < 4; ++i) {
+      const int item = threadIdx.x + 256 * i;                // 128 tokens x 8 vectors of 8 channels
+      tt[i] = tbase + (item >> 3);
+      if (tt[i] < T) ldr(src + tt[i] * st + c0 + 8 * (item & 7), raw[i]);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int t = t0 + ty + 8 * i;
-      if (t < T) *reinterpret_cast<__nv_bfloat162*>(o + static_cast<long long>(t) * C + c0 + 2 * tx) = __floats2bfloat162_rn(lo[i], hi[i]);
+    for (int i = 0; i < 4; ++i) {
+      if (tt[i] < T) {
+        bf16* dst = o + static_cast<long long>(tt[i]) * C + c0 + 8 * ((threadIdx.x + 256 * i) & 7);
+        if constexpr (sizeof(TIn) == 2) {
+          *reinterpret_cast<uint4*>(dst) = raw[i].v;          // bf16 -> bf16: the packed vector as it is
+        } else {
+          float f[8];
+          cvr(raw[i], f);
+          st8(dst, f);
+        }
+      }
     }
     return;
   }
+  for (int half = 0; half < 2; ++half) {
+    const int t0 = tbase + 64 * half;
+    if (t0 >= T) break;
+    if (sc == 1) {                                           // channels-last rows that are not 16-byte aligned
+      float lo[8], hi[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {                              // NCHW: coalesced along tokens, transposed on the way out
-    const int c = ty + 8 * i;
-    const TIn* r = src + (c0 + c) * sc;
-    const int ta = t0 + tx, tb = t0 + 32 + tx;
-    tile[c][tx] = ta < T ? ld_as_float<TIn>(r + ta * st) : 0.f;
-    tile[c][32 + tx] = tb < T ? ld_as_float<TIn>(r + tb * st) : 0.f;
-  }
-  __syncthreads();
+      for (int i = 0; i < 8; ++i) {
+        const int t = t0 + ty + 8 * i;
+        const TIn* r = src + t * st + c0 + 2 * tx;
+        lo[i] = t < T ? ld_as_float<TIn>(r) : 0.f;
+        hi[i] = t < T ? ld_as_float<TIn>(r + 1) : 0.f;
+      }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int tl = ty + 8 * i, t = t0 + tl;
-    if (t < T)
-      *reinterpret_cast<__nv_bfloat162*>(o + static_cast<long long>(t) * C + c0 + 2 * tx) =
-          __floats2bfloat162_rn(tile[2 * tx][tl], tile[2 * tx + 1][tl]);
+      for (int i = 0; i < 8; ++i) {
+        const int t = t0 + ty + 8 * i;
+        if (t < T) *reinterpret_cast<__nv_bfloat162*>(o + static_cast<long long>(t) * C + c0 + 2 * tx) = __floats2bfloat162_rn(lo[i], hi[i]);
+      }
+      continue;
+    }
+    if (half) __syncthreads();                               // the first half's tile has been read
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {                            // NCHW: coalesced along tokens, transposed on the way out
+      const int c = ty + 8 * i;
+      const TIn* r = src + (c0 + c) * sc;
+      const int ta = t0 + tx, tb = t0 + 32 + tx;
+      tile[c][tx] = ta < T ? ld_as_float<TIn>(r + ta * st) : 0.f;
+      tile[c][32 + tx] = tb < T ? ld_as_float<TIn>(r + tb * st) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int tl = ty + 8 * i, t = t0 + tl;
+      if (t < T)
+        *reinterpret_cast<__nv_bfloat162*>(o + static_cast<long long>(t) * C + c0 + 2 * tx) =
+            __floats2bfloat162_rn(tile[2 * tx][tl], tile[2 * tx + 1][tl]);
+    }
   }
 }
 
@@ -748,7 +745,7 @@ int views_to_tokens(int B, int C, int V, int T, int src_dtype, const void* const
     if (on && sc[v] != 1 && st[v] != 1)
       return set_error(GLF_ERR_UNSUPPORTED, "views_to_tokens: a view needs unit channel or unit token stride");
   }
-  const dim3 grid(((T + 63) / 64) * (C / 64), V, B);
+  const dim3 grid(((T + 127) / 128) * (C / 64), V, B);
   if (src_dtype == GLF_DTYPE_BF16)
     views_to_tokens_kernel<bf16><<<grid, 256, 0, stream>>>(P, reinterpret_cast<bf16*>(out), V, C, T);
   else if (src_dtype == GLF_DTYPE_F32)
