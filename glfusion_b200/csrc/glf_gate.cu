@@ -228,15 +228,9 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// da = sum over channel tiles (fixed order), then the chain a = sigmoid(w*m*c), m = sigmoid(max_k cls), c = sigmoid(ctr)
-__global__ void gate_finish_kernel(const ViewPtrs vp, const float* __restrict__ gate, const float* __restrict__ da_part,
-                                   int nct, int BV, int V, int hw, int ncls, float weight) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<long long>(BV) * hw) return;
-  const int bv = static_cast<int>(idx / hw), p = static_cast<int>(idx % hw);
-  const int b = bv / V, v = bv % V;
-  float dA = 0.f;
-  for (int t = 0; t < nct; ++t) dA += da_part[(static_cast<long long>(t) * BV + bv) * hw + p];
+// the chain a = sigmoid(w*m*c), m = sigmoid(max_k cls), c = sigmoid(ctr) backwards for one position
+__device__ __forceinline__ void gate_finish_one(const ViewPtrs& vp, int v, int b, int p, int hw, int ncls, float weight,
+                                                float a, float dA) {
   const float* cl = vp.cls[v] + static_cast<long long>(b) * ncls * hw + p;
   float lmax = cl[0];
   int arg = 0;
@@ -246,12 +240,23 @@ __global__ void gate_finish_kernel(const ViewPtrs vp, const float* __restrict__ 
   }
   const float m = sigmoidf_(lmax);
   const float c = sigmoidf_(vp.ctr[v][static_cast<long long>(b) * hw + p]);
-  const float a = gate[idx];
   const float dt = dA * a * (1.f - a);
   const float dm = dt * weight * c, dc = dt * weight * m;
   vp.dctr[v][static_cast<long long>(b) * hw + p] = dc * c * (1.f - c);
   float* dcl = vp.dcls[v] + static_cast<long long>(b) * ncls * hw + p;
   for (int k = 0; k < ncls; ++k) dcl[static_cast<long long>(k) * hw] = (k == arg) ? dm * m * (1.f - m) : 0.f;
+}
+
+// da = sum over channel tiles (fixed order), then the chain a = sigmoid(w*m*c), m = sigmoid(max_k cls), c = sigmoid(ctr)
+__global__ void gate_finish_kernel(const ViewPtrs vp, const float* __restrict__ gate, const float* __restrict__ da_part,
+                                   int nct, int BV, int V, int hw, int ncls, float weight) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(BV) * hw) return;
+  const int bv = static_cast<int>(idx / hw), p = static_cast<int>(idx % hw);
+  const int b = bv / V, v = bv % V;
+  float dA = 0.f;
+  for (int t = 0; t < nct; ++t) dA += da_part[(static_cast<long long>(t) * BV + bv) * hw + p];
+  gate_finish_one(vp, v, b, p, hw, ncls, weight, gate[idx], dA);
 }
 
 // ------------------------------------------------------------------------------------------------ TMA + ldmatrix forms
@@ -350,11 +355,12 @@ __global__ void __launch_bounds__(256)
 // da[p] = sum_c f4[c,p] * dXl[p,c] (the CTA sees every channel, so no partial table: da_part has one slice).
 __global__ void __launch_bounds__(256)
     gate_concat_bwd_tma_kernel(const __grid_constant__ ViewMaps maps, const ViewPtrs vp, const float* __restrict__ gate,
-                               const bf16* __restrict__ dxg, const bf16* __restrict__ dxl, float* __restrict__ da_part,
-                               int C, int V, int hw) {
+                               const bf16* __restrict__ dxg, const bf16* __restrict__ dxl, int C, int V, int hw,
+                               int ncls, float weight) {
   extern __shared__ uint8_t gsm_raw[];
   __shared__ uint64_t bar;
   __shared__ float a_sm[64];
+  __shared__ float da_sm[64];
   const uint32_t base = (smem_u32(gsm_raw) + 1023u) & ~1023u;
   uint8_t* gen = gsm_raw + (base - smem_u32(gsm_raw));
   const int bv = blockIdx.y, b = bv / V, v = bv % V;
@@ -434,7 +440,7 @@ __global__ void __launch_bounds__(256)
     float da = acc.x + acc.y;
     da += __shfl_xor_sync(0xffffffffu, da, 1);
     da += __shfl_xor_sync(0xffffffffu, da, 2);
-    if ((lane & 3) == 0 && pl < valid) da_part[static_cast<long long>(bv) * hw + p0 + pl] = da;
+    if ((lane & 3) == 0) da_sm[pl] = da;
   }
   __syncthreads();
   {
@@ -452,6 +458,10 @@ __global__ void __launch_bounds__(256)
       if (pp < hw) *reinterpret_cast<uint4*>(df4 + static_cast<long long>(c) * hw + pp) = make_uint4(r[0], r[1], r[2], r[3]);
     }
   }
+  // the CTA saw every channel, so the gate gradient of its 64 positions is complete: finish the chain to the logits here
+  // (coalesced along the positions) instead of in a second launch
+  if (threadIdx.x < valid)
+    gate_finish_one(vp, v, b, p0 + threadIdx.x, hw, ncls, weight, a_sm[threadIdx.x], da_sm[threadIdx.x]);
 }
 
 bool gate_tma_ok(int C, int hw, int io_dtype, int x_dtype, const void* const* f4, int V) {
@@ -816,14 +826,8 @@ int gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, i
     cudaError_t e = cudaFuncSetAttribute(gate_concat_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gate_bwd_tma)");
     gate_concat_bwd_tma_kernel<<<dim3((hw + 63) / 64, B * V), 256, smem, stream>>>(
-        maps, vp, gate, reinterpret_cast<const bf16*>(dxg), reinterpret_cast<const bf16*>(dxl), da_part, C, V, hw);
-    int rc = check_cuda(cudaGetLastError(), "gate_concat_bwd_tma launch");
-    if (rc) return rc;
-    nct = 1;   // the gate gradient is complete: one slice of the table
-    const long long n = static_cast<long long>(B) * V * hw;
-    gate_finish_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(vp, gate, da_part, nct, B * V, V, hw,
-                                                                                  ncls, weight);
-    return check_cuda(cudaGetLastError(), "gate_finish launch");
+        maps, vp, gate, reinterpret_cast<const bf16*>(dxg), reinterpret_cast<const bf16*>(dxl), C, V, hw, ncls, weight);
+    return check_cuda(cudaGetLastError(), "gate_concat_bwd_tma launch");   // (the chain to the logits is finished inside)
   }
   dim3 grid((hw + 63) / 64, nct, B * V);
   if (grid.y > 65535 || grid.z > 65535) return set_error(GLF_ERR_INVALID, "gate_concat: grid too large");
