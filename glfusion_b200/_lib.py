@@ -19,7 +19,8 @@ EXPORTS = ("glf_version", "glf_last_error", "glf_tpavi_sizes", "glf_tpavi_fwd", 
            "glf_gate_concat_fwd", "glf_gate_concat_bwd", "glf_gate_concat_cl_fwd", "glf_gate_concat_cl_bwd",
            "glf_views_to_tokens", "glf_gemm_bf16", "glf_transpose", "glf_bn_res_ln_fwd",
            "glf_bn_res_ln_bwd", "glf_bn_res_ln_bwd_max_blocks", "glf_gate_concat_bwd_scratch_bytes",
-           "glf_fusion_ln_supported", "glf_fusion_ln_fwd", "glf_fusion_ln_fwd_parts", "glf_fusion_ln_bwd",
+           "glf_fusion_ln_supported", "glf_fusion_ln_fwd", "glf_fusion_ln_fwd_parts", "glf_fusion_ln_bwd", "glf_fusion_ln_bwd_views",
+           "glf_fusion_ln_bwd_views_supported",
            "glf_bn_res_ln_pair_fwd",
            "glf_bn_res_ln_pair_bwd", "glf_gemm_bf16_ex", "glf_gram_contraction", "glf_p2p_signal_bytes", "glf_p2p_max_floats",
            "glf_p2p_export", "glf_p2p_open", "glf_p2p_close", "glf_p2p_allreduce", "glf_spatial_sums",
@@ -80,6 +81,9 @@ def load() -> C.CDLL:
         lib.glf_fusion_ln_bwd.argtypes = [C.POINTER(GlfDesc), vp, vp, vp, C.POINTER(GlfWeights), C.POINTER(GlfWeights),
                                           vp, vp, vp, vp, vp]
         pp = C.POINTER(C.c_void_p)
+        lib.glf_fusion_ln_bwd_views.argtypes = [C.POINTER(GlfDesc), vp, pp, vp, vp, vp, C.POINTER(GlfWeights),
+                                                C.POINTER(GlfWeights), vp, vp, vp, vp, vp]
+        lib.glf_fusion_ln_bwd_views_supported.argtypes = [C.POINTER(GlfDesc)]
         lib.glf_bn_res_ln_pair_fwd.argtypes = [i64, i32, pp, pp, pp, pp, pp, pp, vp, pp, pp, f32, i32, vp]
         lib.glf_bn_res_ln_pair_bwd.argtypes = [i64, i32, vp, pp, pp, pp, pp, pp, pp, pp, pp, pp, pp, pp,
                                                C.POINTER(C.c_int), vp]

@@ -1022,12 +1022,27 @@ GLF_API int glf_fusion_ln_fwd_parts(const glf_desc* d, const void* xg, const voi
 GLF_API int glf_fusion_ln_bwd(const glf_desc* d, const void* dz, const void* xg, const void* xl, const glf_weights* wg,
                               const glf_weights* wl, const void* saved_g, const void* saved_l, void* ws_g, void* ws_l,
                               glf_stream_t stream_) {
+  return glf_fusion_ln_bwd_views(d, dz, nullptr, nullptr, xg, xl, wg, wl, saved_g, saved_l, ws_g, ws_l, stream_);
+}
+
+GLF_API int glf_fusion_ln_bwd_views_supported(const glf_desc* d) {
+  Dims m;
+  if (d == nullptr || make_dims(d, &m) != 0 || check_pair(d, m) != 0) return 0;
+  return (static_cast<long long>(d->H) * d->W) % ln_bwd_tma_tile_rows() == 0 && d->T <= 8 ? 1 : 0;
+}
+
+GLF_API int glf_fusion_ln_bwd_views(const glf_desc* d, const void* dz, const void* const* dz_views,
+                                    const int64_t* dz_stride_b, const void* xg, const void* xl, const glf_weights* wg,
+                                    const glf_weights* wl, const void* saved_g, const void* saved_l, void* ws_g,
+                                    void* ws_l, glf_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   Dims m;
   GLF_TRY(make_dims(d, &m));
   GLF_TRY(check_device_sm100());
   GLF_TRY(check_pair(d, m));
-  GLF_TRY(check_ptr(dz, "dz"));
+  const bool views = dz_views != nullptr;
+  if (views && dz_stride_b == nullptr) return set_error(GLF_ERR_INVALID, "dz_stride_b is NULL");
+  if (!views) GLF_TRY(check_ptr(dz, "dz"));
   GLF_TRY(check_ptr(xg, "xg"));
   GLF_TRY(check_ptr(xl, "xl"));
   GLF_TRY(check_ptr(saved_g, "saved_g"));
@@ -1053,8 +1068,9 @@ GLF_API int glf_fusion_ln_bwd(const glf_desc* d, const void* dz, const void* xg,
   bf16* dV[2] = {bg.dV, bl.dV};
   float* part[2] = {bg.part_ln, bl.part_ln};
   int nb = 0;
+  static_assert(sizeof(long long) == sizeof(int64_t), "stride tables are passed through unchanged");
   return ln_bwd_tma(2, reinterpret_cast<const bf16*>(dz), U, X, a, b, lw, mean, rstd, mu, r, dV, part, m.rows, m.C, &nb,
-                    stream);
+                    stream, views ? d->T : 0, dz_views, reinterpret_cast<const long long*>(dz_stride_b), d->H * d->W);
 }
 
 GLF_API int glf_gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, int io_dtype, int x_dtype,

@@ -88,7 +88,9 @@ int ln_fwd_tma(int nmod, const bf16* const* U, const bf16* const* X, const float
 int ln_bwd_tma(int nmod, const bf16* dZ, const bf16* const* U, const bf16* const* X, const float* const* a,
                const float* const* b, const float* const* lw, const float* const* bn_mean,
                const float* const* bn_rstd, const float* const* mu, const float* const* r, bf16* const* dV,
-               float* const* part, long long rows, int C, int* nblocks, cudaStream_t stream);
+               float* const* part, long long rows, int C, int* nblocks, cudaStream_t stream, int dz_nv = 0,
+               const void* const* dz_views = nullptr, const long long* dz_sb = nullptr, int dz_hw = 0);
+int ln_bwd_tma_tile_rows();
 int bn_bwd_finalize(const float* part, int np, int C, double count, const glf_desc* d, const glf_weights* w,
                     const float* mean, const float* rstd, const glf_grads* g, float* k1, float* k2, float* k3,
                     cudaStream_t stream);

@@ -256,6 +256,12 @@ struct LnBwdParams {
   long long rows;
   int C, ntiles, stages;
   uint32_t arr_bytes, stage_bytes;
+  // dZ given per view (the dict-keyed call site: one gradient per view, rows of C channels): row (b, v, t) of the stack
+  // lives at dzv[v] + b * dz_sb[v] + t * C.  dz_nv = 0: dZ is the token-major stack itself.  Needs hw % B_TR == 0 so
+  // that a tile never straddles two views.
+  const bf16* dzv[8];
+  long long dz_sb[8];
+  int dz_nv, dz_hw;
 };
 
 template <int NMOD, bool FULLC>
@@ -293,7 +299,13 @@ __global__ void __launch_bounds__(B_THREADS, 1) ln_bwd_tma_kernel(const LnBwdPar
         mbar_expect_tx(fb, bytes * (1 + 2 * NMOD) + (full_tile ? 2u * NMOD * B_TR * 4u : 0u));
         const uint32_t dst = ring_u32 + s * p.stage_bytes;
         const long long off = row0 * p.C;
-        bulk_g2s(dst, p.dZ + off, bytes, fb);
+        const bf16* dzsrc = p.dZ + off;
+        if (p.dz_nv > 0) {
+          const long long bv = row0 / p.dz_hw;
+          const int v = static_cast<int>(bv % p.dz_nv);
+          dzsrc = p.dzv[v] + (bv / p.dz_nv) * p.dz_sb[v] + (row0 - bv * p.dz_hw) * p.C;
+        }
+        bulk_g2s(dst, dzsrc, bytes, fb);
 #pragma unroll
         for (int m = 0; m < NMOD; ++m) {
           bulk_g2s(dst + (1 + 2 * m) * p.arr_bytes, p.U[m] + off, bytes, fb);
@@ -469,14 +481,32 @@ int ln_fwd_tma(int nmod, const bf16* const* U, const bf16* const* X, const float
   return check_cuda(cudaGetLastError(), "ln_fwd_tma launch");
 }
 
+int ln_bwd_tma_tile_rows() { return B_TR; }
+
 // dV_m and per-CTA partials [blocks][4][C] per module; returns the number of partial rows through *nblocks.
 int ln_bwd_tma(int nmod, const bf16* dZ, const bf16* const* U, const bf16* const* X, const float* const* a,
                const float* const* b, const float* const* lw, const float* const* bn_mean,
                const float* const* bn_rstd, const float* const* mu, const float* const* r, bf16* const* dV,
-               float* const* part, long long rows, int C, int* nblocks, cudaStream_t stream) {
+               float* const* part, long long rows, int C, int* nblocks, cudaStream_t stream, int dz_nv,
+               const void* const* dz_views, const long long* dz_sb, int dz_hw) {
   if (!ln_tma_supported(C) || nmod < 1 || nmod > 2) return set_error(GLF_ERR_INVALID, "ln_bwd_tma: unsupported shape");
   LnBwdParams p;
   p.dZ = dZ;
+  p.dz_nv = 0; p.dz_hw = 1;
+  for (int v = 0; v < 8; ++v) { p.dzv[v] = nullptr; p.dz_sb[v] = 0; }
+  if (dz_nv > 0) {
+    if (dz_nv > 8 || dz_views == nullptr || dz_sb == nullptr || dz_hw <= 0 || dz_hw % B_TR != 0 ||
+        rows % (static_cast<long long>(dz_nv) * dz_hw) != 0)
+      return set_error(GLF_ERR_UNSUPPORTED, "ln_bwd_tma: per-view dz needs h*w %% %d == 0 and <= 8 views", B_TR);
+    for (int v = 0; v < dz_nv; ++v) {
+      if (dz_views[v] == nullptr || (reinterpret_cast<uintptr_t>(dz_views[v]) & 15) != 0 || dz_sb[v] % 8 != 0)
+        return set_error(GLF_ERR_INVALID, "ln_bwd_tma: per-view dz must be 16-byte aligned");
+      p.dzv[v] = reinterpret_cast<const bf16*>(dz_views[v]);
+      p.dz_sb[v] = dz_sb[v];
+    }
+    p.dz_nv = dz_nv; p.dz_hw = dz_hw;
+    p.dZ = p.dzv[0];
+  }
   for (int m = 0; m < 2; ++m) {
     const int k = m < nmod ? m : 0;
     p.U[m] = U[k]; p.X[m] = X[k]; p.a[m] = a[k]; p.b[m] = b[k]; p.lw[m] = lw[k];

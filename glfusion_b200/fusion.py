@@ -138,6 +138,27 @@ def views_to_tokens(views: Sequence[Optional[torch.Tensor]], out: torch.Tensor) 
     return True
 
 
+def _views_as_rows(grads, xg: torch.Tensor, st) -> Optional[tuple]:
+    """The V per-view gradients as (tensors, batch strides) when the fused LayerNorm backward can read them in place
+    (glf_fusion_ln_bwd_views): all present, bf16, rows of C contiguous channels with contiguous tokens (channels_last or
+    views of a token-major stack), 16-byte aligned, h*w a multiple of the pass's row tile.  None otherwise: the caller
+    gathers them into one token-major buffer first."""
+    B, V, h, w, Cn = xg.shape
+    if any(g is None for g in grads) or xg.dtype != torch.bfloat16:
+        return None
+    if not L.load().glf_fusion_ln_bwd_views_supported(C.byref(st.desc)):
+        return None
+    sb = []
+    for g in grads:
+        if g.dtype != torch.bfloat16 or tuple(g.shape) != (B, Cn, h, w) or g.device != xg.device:
+            return None
+        b_, c_, h_, w_ = g.stride()
+        if c_ != 1 or w_ != Cn or h_ != w * Cn or b_ % 8 or g.data_ptr() % 16 or (B > 1 and b_ < h * w * Cn):
+            return None
+        sb.append(b_)
+    return list(grads), sb
+
+
 def gate_concat_backward(f4, cls, ctr, gate, dxg, dxl, weight: float):
     lib = L.load()
     V = len(f4)
@@ -283,9 +304,12 @@ class _FusionFunction(torch.autograd.Function):
                 else:
                     buf[:, v].copy_(g.permute(0, 2, 3, 1))
             return buf
+        dz_rows = None          # per-view gradients that the fused LayerNorm backward can read where they lie
         if ctx.per_view:
-            dout = assemble(grads[:V])
             dglob = assemble(grads[V:2 * V]) if ctx.parts else None
+            if dglob is None and ctx.pair:
+                dz_rows = _views_as_rows(grads[:V], xg, stg)
+            dout = grads[0] if dz_rows is not None else assemble(grads[:V])
         else:
             dout = grads[0]
             dglob = grads[1] if len(grads) > 1 else None
@@ -295,7 +319,9 @@ class _FusionFunction(torch.autograd.Function):
         tg, tl = mg._param_table(pg), ml._param_table(pl)
         gl = None
         if dglob is None:
-            dz = token(dout)                        # both blocks see the same dz (ours.py:1834)
+            # both blocks see the same dz (ours.py:1834); with dz_rows it stays where autograd delivered it, one tensor
+            # per view, and `dz` is only a placeholder (the blocks' backward continues from dV, it never reads dz)
+            dz = xg if dz_rows is not None else token(dout)
             wsg = wsl = None
             if ctx.pair:
                 # LayerNorm backward of both blocks in one pass (dz is read once); fills dV / partials inside each ws blob
@@ -304,9 +330,16 @@ class _FusionFunction(torch.autograd.Function):
                 wsg, wsl = _blob(stg.sizes.ws_bwd_bytes, xg.device), _blob(stl.sizes.ws_bwd_bytes, xg.device)
                 wg, wl = _weights_struct(tg, mg._buffer_table()), _weights_struct(tl, ml._buffer_table())
                 with torch.cuda.device(xg.device):
-                    L.check(L.load().glf_fusion_ln_bwd(C.byref(stg.desc), L.ptr(dz), L.ptr(xg), L.ptr(xl), C.byref(wg),
-                                                       C.byref(wl), L.ptr(svg), L.ptr(svl), L.ptr(wsg), L.ptr(wsl),
-                                                       _stream_ptr()))
+                    if dz_rows is not None:
+                        views, sb = dz_rows
+                        L.check(L.load().glf_fusion_ln_bwd_views(C.byref(stg.desc), None, L.ptr_table(views),
+                                                                 (C.c_int64 * V)(*sb), L.ptr(xg), L.ptr(xl), C.byref(wg),
+                                                                 C.byref(wl), L.ptr(svg), L.ptr(svl), L.ptr(wsg),
+                                                                 L.ptr(wsl), _stream_ptr()))
+                    else:
+                        L.check(L.load().glf_fusion_ln_bwd(C.byref(stg.desc), L.ptr(dz), L.ptr(xg), L.ptr(xl),
+                                                           C.byref(wg), C.byref(wl), L.ptr(svg), L.ptr(svl), L.ptr(wsg),
+                                                           L.ptr(wsl), _stream_ptr()))
             gout_g, gout_l = claim_grad_out(mg), claim_grad_out(ml)
             side = _side_stream(xg.device) if ctx.pair and ctx.fusion.overlap_blocks else None
             if side is not None:   # after the fused LayerNorm backward the two blocks' chains are independent again

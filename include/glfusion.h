@@ -143,6 +143,16 @@ GLF_API int glf_fusion_ln_fwd_parts(const glf_desc* d, const void* xg, const voi
 GLF_API int glf_fusion_ln_bwd(const glf_desc* d, const void* dz, const void* xg, const void* xl, const glf_weights* wg,
                       const glf_weights* wl, const void* saved_g, const void* saved_l, void* ws_g, void* ws_l,
                       glf_stream_t stream);
+/* The same backward pass with dz given PER VIEW, as the dict-keyed call site receives it (one [B, C, h, w] gradient per
+ * view, ours.py:1833-1837): dz_views[v] points at view v's gradient stored as rows of C channels (channels_last, or a
+ * view of a token-major stack): element (b, c, t) at b * dz_stride_b[v] + t * C + c, v < d->T.  The pass reads each
+ * view where it lies; nothing is gathered first.  Needs h*w to be a multiple of the pass's 28-row tile
+ * (glf_fusion_ln_bwd_views_supported returns 1); dz_views == NULL is glf_fusion_ln_bwd. */
+GLF_API int glf_fusion_ln_bwd_views_supported(const glf_desc* d);
+GLF_API int glf_fusion_ln_bwd_views(const glf_desc* d, const void* dz, const void* const* dz_views,
+                            const int64_t* dz_stride_b, const void* xg, const void* xl, const glf_weights* wg,
+                            const glf_weights* wl, const void* saved_g, const void* saved_l, void* ws_g, void* ws_l,
+                            glf_stream_t stream);
 
 /* Gate + view concat (ours.py:1802-1820,1826-1827).
  *   f4[v]  : [B, C, h, w]  io_dtype, NCHW contiguous, v < V (host array of V device pointers, V <= 8)

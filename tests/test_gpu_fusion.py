@@ -389,3 +389,40 @@ def test_channels_last_hand_off_matches_nchw(io, Cn, h, w):
         assert (a - b).abs().max().item() <= 2e-2 * max(a.abs().max().item(), 1e-6) + 1e-9   # sums of bf16 dxl products
     for a, b in zip(p0, p1):                         # the blocks see identical inputs
         assert (a - b).abs().max().item() <= 2e-2 * max(a.abs().max().item(), 1e-6) + 1e-7   # bf16 chain, run-to-run order
+
+
+@pytest.mark.parametrize("h,w", [(4, 7), (28, 28), (5, 7)])
+def test_dict_api_backward_reads_per_view_gradients_in_place(h, w):
+    """The dict-keyed call hands the backward one gradient per view.  When they are rows of C channels (channels_last, or
+    views of one token-major buffer) and h*w is a multiple of the LayerNorm pass's row tile, the fused LayerNorm backward
+    reads them where they lie (glf_fusion_ln_bwd_views); NCHW gradients (and 5x7, which does not tile) are gathered
+    first.  All three deliveries of the same gradient values give the same input and parameter gradients."""
+    torch.manual_seed(0)
+    B, V, Cn = 3, 2, 128
+    fus = GlobalLocalFusion(Cn).to(DEV)
+    from bench import randomize_affine_
+    randomize_affine_(fus.global_attn, 7)
+    randomize_affine_(fus.local_attn, 8)
+    keys = ["1", "3"]
+    gen = torch.Generator().manual_seed(6)
+    f4v = [torch.randn(B, Cn, h, w, generator=gen).to(DEV).to(torch.bfloat16) for _ in keys]
+    cl = {k: torch.randn(B, 3, h, w, generator=gen).to(DEV) for k in keys}
+    ct = {k: torch.randn(B, 1, h, w, generator=gen).to(DEV) for k in keys}
+    dzs = torch.randn(B, V, h, w, Cn, generator=gen).to(DEV).to(torch.bfloat16)      # token-major stack of gradients
+    res = []
+    for delivery in ("stack_views", "channels_last", "nchw"):
+        f4 = {k: t.clone().requires_grad_(True) for k, t in zip(keys, f4v)}
+        for p in fus.parameters():
+            p.grad = None
+        out = fus(f4, cl, ct)
+        if delivery == "stack_views":
+            gs = [dzs[:, i].permute(0, 3, 1, 2) for i in range(V)]
+        elif delivery == "channels_last":
+            gs = [dzs[:, i].permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last) for i in range(V)]
+        else:
+            gs = [dzs[:, i].permute(0, 3, 1, 2).contiguous() for i in range(V)]
+        torch.autograd.backward([out[k] for k in keys], gs)
+        res.append(([f4[k].grad.float() for k in keys], [p.grad.clone() for p in fus.parameters() if p.grad is not None]))
+    for other in res[1:]:
+        for a, b in zip(res[0][0] + res[0][1], other[0] + other[1]):
+            assert (a - b).abs().max().item() <= 2e-2 * max(a.abs().max().item(), 1e-6) + 1e-7
