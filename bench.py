@@ -174,12 +174,12 @@ def seeded_fusion(C: int, device):
 
 def dot_algorithm(C: int) -> str:
     """Which exact reassociation of mode='dot' libglf_sm100a runs for the bench shape (glf_api.cu: make_dims):
-    the Gram form when the sequences are long against the channel count (N >= 5 C; 8 C for 256 < C <= 768), unless
-    GLF_DOT_ALGO pins it."""
+    the Gram form when the sequences are long against the channel count (N >= 3 C at C = 256 where the per-sequence
+    chain kernels exist, 5 C below, 8 C above), unless GLF_DOT_ALGO pins it."""
     pin = int(os.environ.get("GLF_DOT_ALGO", "0"))
     if pin in (1, 2):
         return "token" if pin == 1 else "gram"
-    thr = 8 if 256 < C <= 768 else 5
+    thr = 3 if (C == 256 and os.environ.get("GLF_GRAM_CHAIN", "1") != "0") else (8 if C > 256 else 5)
     return "gram" if V * HH * WW >= thr * C else "token"
 
 

@@ -107,10 +107,11 @@ int make_dims(const glf_desc* d, Dims* o) {
   if (d->reserved[1] == 2 && !gram_ok)
     return set_error(GLF_ERR_UNSUPPORTED, "the Gram form needs mode='dot', GLF_PRECISION_BF16 and B <= 65535");
   // per-sequence [C x C] products cost ~15 C^3 against 3.5 N C^2 of saved token-space FLOPs and 11 saved activation
-  // passes.  Measured crossover on B200 (profiles/algo_crossover.py, r01_algo_crossover.txt): N/C between 3 and 6 at
-  // C = 128 / 256 / 1024; at C = 512 the token-space form still wins at N/C = 6 (no one-CTA-per-sequence contraction
-  // kernel above C = 256, and the products are not yet tensor-bound as at C = 1024).
-  const long long thr = (d->C > 256 && d->C <= 768) ? 8 : 5;
+  // passes.  Measured crossover on B200 (profiles/algo_crossover.py, r02_algo_crossover.txt): with the one-CTA-per-
+  // sequence chain kernels (C = 256, C' = 128) the Gram form wins from N/C = 3 (1.00 vs 1.11 ms at N = 784, B = 512);
+  // at C = 128 between 3 and 24; above C = 256 the token-space form (every GEMM on CTA pairs) still wins at N/C = 6
+  // (C = 512: 1.37 vs 1.46 ms; C = 1024: 1.85 vs 1.96 ms).
+  const long long thr = gram_chain_supported(d->C, d->Ci) ? 3 : (d->C > 256 ? 8 : 5);
   o->gram = gram_ok && (d->reserved[1] == 2 || (d->reserved[1] == 0 && o->N >= thr * d->C));
   o->Ca = gram_ca(d->C);
   return 0;

@@ -59,7 +59,7 @@ def _blob(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
-# Algorithm for mode='dot' (glf_desc.reserved[1]): 0 = the library chooses (Gram form when N >= 5 C), 1 = token-space
+# Algorithm for mode='dot' (glf_desc.reserved[1]): 0 = the library chooses (Gram form when N >= 3 C at C = 256, 5 C below, 8 C above), 1 = token-space
 # form (theta/phi/g per token), 2 = Gram form (channel-space products only).  Tests pin it; users leave it alone.
 DOT_ALGO = int(os.environ.get("GLF_DOT_ALGO", "0"))
 

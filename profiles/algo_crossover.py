@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Token-space vs Gram form of mode='dot' across channel counts and sequence lengths (one TPAVIModule, fwd+bwd, bf16
-token-major input): where the library's N >= 4 C rule puts the crossover.  python profiles/algo_crossover.py"""
+token-major input): where the library's rule (N >= 3 C at C = 256, 5 C below, 8 C above) puts the crossover.  python profiles/algo_crossover.py"""
 import json
 import os
 import sys
@@ -54,7 +54,7 @@ for C, B, T, H, W in ((256, 128, 4, 28, 28), (256, 256, 4, 20, 20), (256, 512, 4
         torch.cuda.synchronize()
         row[name + "_ms"] = round(e0.elapsed_time(e1) / 10, 3)
     row["N_over_C"] = round(N / C, 2)
-    row["auto_picks"] = "gram" if N >= 4 * C else "token"
+    row["auto_picks"] = "gram" if N >= (3 if C == 256 else (8 if C > 256 else 5)) * C else "token"
     out[f"C={C} N={N} B={B}"] = row
     print(f"C={C} N={N} B={B}", row, flush=True)
 tpavi.DOT_ALGO = 0

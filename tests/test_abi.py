@@ -90,12 +90,12 @@ def test_invalid_descriptors_are_errors_with_messages(kw, frag):
 @pytest.mark.parametrize("C_,T,H,W", [(256, 4, 28, 28), (256, 4, 14, 14), (256, 4, 16, 20), (512, 4, 28, 28),
                                       (512, 8, 24, 24), (1024, 4, 40, 40), (128, 2, 16, 20), (2048, 3, 28, 28)])
 def test_automatic_dot_algorithm_follows_the_documented_rule(C_, T, H, W):
-    """reserved[1] = 0: Gram form iff N >= 5 C (8 C for 256 < C <= 768) — observable through the blob sizes; bench.py
-    mirrors the same rule for its FLOP / launch accounting."""
+    """reserved[1] = 0: Gram form iff N >= 3 C at C = 256 (the width with the per-sequence chain kernels), 5 C below,
+    8 C above — observable through the blob sizes; bench.py mirrors the same rule for its FLOP / launch accounting."""
     import bench
     lib = glfusion_b200.load_library()
     N = T * H * W
-    thr = 8 if 256 < C_ <= 768 else 5
+    thr = 3 if C_ == 256 else (8 if C_ > 256 else 5)
     expect = 2 if N >= thr * C_ else 1
     kw = dict(C=C_, Ci=C_ // 2, T=T, H=H, W=W)
     sa, se, so = L.GlfSizes(), L.GlfSizes(), L.GlfSizes()
