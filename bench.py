@@ -476,13 +476,13 @@ def count_launches(clips: int, C: int) -> int:
     """Kernels launched by libglf_sm100a per step (fwd+bwd, both modules + gate), counted from the orchestration in
     glfusion_b200/csrc/glf_api.cu (memset/memcpy nodes excluded); agrees with profiles/r01_v11_launches.csv (39,
     token-space form), profiles/r01_v17_launches.csv (55, Gram form as batched tile GEMMs) and
-    profiles/r02_v3_launches.csv / r02_v8_launches.csv (27, Gram form with the per-sequence chain kernels; 26 since the gate
-    backward finishes the chain to the logits in the same launch)."""
+    profiles/r02_v3_launches.csv / r02_v8_launches.csv (27, Gram form with the per-sequence chain kernels; 24 since the gate
+    backward finishes the chain to the logits itself and the weight preparation rides along in the S launch)."""
     if dot_algorithm(C) == "gram" and C == 256 and os.environ.get("GLF_GRAM_CHAIN", "1") != "0":
-        fwd_mod = 5      # prep_weights, S (gram_kernel), chain_fwd, U GEMM, bn_finalize
+        fwd_mod = 4      # S (gram_kernel; the weight preparation rides along as extra CTAs), chain_fwd, U GEMM, bn_finalize
         bwd_mod = 6      # finalize, R (gram_kernel), chain_bwd, wgrad, wgrad_reduce, dX GEMM
     elif dot_algorithm(C) == "gram":
-        fwd_mod = 9      # prep_weights, S (gram_kernel), T, M, W', Q~ GEMMs, cvec, U GEMM, bn_finalize
+        fwd_mod = 8 if C == 128 else 9   # (prep_weights,) S, T, M, W', Q~ GEMMs, cvec, U GEMM, bn_finalize
         bwd_mod = 16     # finalize, R (gram_kernel), kprep, dQ~, dW', dW~theta, dWz, dM, dW~g, dT, dW~phi, G0, H GEMMs,
         #                  assemble_F, dX GEMM, unpack_grads
     else:

@@ -344,7 +344,9 @@ int gram_big_tile() {
 // [[S, colsum(A)], [rowv^T, corner]] of width Ca.  Enough sequences: the GEMM writes bf16 straight into it and a border
 // kernel adds the homogeneous row / column; few long sequences: split-K into fp32, then one assembling pass.
 int gram_token_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* scratch, float* rowsum, const float* rowv,
-                           const float* rowscale, float corner, int B, int N, int C, int Ca, cudaStream_t stream) {
+                           const float* rowscale, float corner, int B, int N, int C, int Ca, cudaStream_t stream,
+                           const GramPrep* prep = nullptr, bool* prep_done = nullptr) {
+  if (prep_done != nullptr) *prep_done = false;
   const char* ek = getenv("GLF_GRAM_KERNEL");   // tuning aid: 0 = always the generic tile GEMM
   if (gram_contraction_supported(C) && !(ek && ek[0] == '0')) {
     // one CTA per sequence; few long sequences are split along the tokens to fill two rounds of the SMs
@@ -353,7 +355,8 @@ int gram_token_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* s
       ks = (2 * 148) / B;
       if (ks < 1) ks = 1;
     }
-    GLF_TRY(gram_contraction(A, X, out_aug, scratch, rowsum, rowscale, rowv, corner, 1, B, N, C, Ca, ks, stream));
+    GLF_TRY(gram_contraction(A, X, out_aug, scratch, rowsum, rowscale, rowv, corner, 1, B, N, C, Ca, ks, stream, prep));
+    if (prep != nullptr && prep_done != nullptr) *prep_done = true;
     const int kb = (N + 63) / 64;
     if ((ks > kb ? kb : ks) > 1)
       return gram_assemble_aug(scratch, rowsum, rowv ? rowv : rowsum, rowscale, out_aug, B, C, Ca, corner, stream);
@@ -415,7 +418,6 @@ int tpavi_fwd_gram(const glf_desc* d, const Dims& m, const void* x, const glf_we
   const long long CCa = static_cast<long long>(C) * Ca, CiCi = static_cast<long long>(Ci) * Ci;
   const long long CCi = static_cast<long long>(C) * Ci;
   const int wide = gram_wide_tile();
-  GLF_TRY(gram_prep_weights(w, C, Ci, Ca, s.waug, s.wz, stream));
   const bf16* X = reinterpret_cast<const bf16*>(x);
   if (m.pack_x) {
     if (d->x_layout == GLF_LAYOUT_NCTHW)
@@ -425,7 +427,14 @@ int tpavi_fwd_gram(const glf_desc* d, const Dims& m, const void* x, const glf_we
     X = s.xtok;
   }
   // S_b = X_b^T X_b, s_b = X_b^T 1   ->   S~_b
-  GLF_TRY(gram_token_contraction(X, X, s.Sa, wf.Sf, s.sfv, nullptr, nullptr, static_cast<float>(N), B, N, C, Ca, stream));
+  //   (the fp32 -> bf16 weight preparation for the chain that follows rides along as extra CTAs of the same launch)
+  GramPrep prep;
+  prep.tw = w->theta_w; prep.tb = w->theta_b; prep.pw = w->phi_w; prep.pb = w->phi_b; prep.gw = w->g_w; prep.gb = w->g_b;
+  prep.wz = w->wz_w; prep.waug = s.waug; prep.wzb = s.wz; prep.C = C; prep.Ci = Ci; prep.Ca = Ca;
+  bool prep_done = false;
+  GLF_TRY(gram_token_contraction(X, X, s.Sa, wf.Sf, s.sfv, nullptr, nullptr, static_cast<float>(N), B, N, C, Ca, stream,
+                                 &prep, &prep_done));
+  if (!prep_done) GLF_TRY(gram_prep_weights(w, C, Ci, Ca, s.waug, s.wz, stream));
   if (gram_chain_supported(C, Ci)) {
     // T~, M, W', Q~ and c of every sequence in one launch, one CTA per sequence (glf_chain.cu)
     GLF_TRY(gram_chain_fwd(s.Sa, s.sfv, s.waug, s.wz, w->phi_b, w->g_b, w->theta_b, s.T, s.Mb, s.Wp, s.Qb, s.cvec, s.tv, B,

@@ -42,6 +42,10 @@ struct GramKParams {
   const float* rowv;       // optional [B][C]
   float corner;
   int border;              // 1: write the border (needs Ca >= C + 1)
+  // CTAs >= nwork are not contraction work: they convert the fp32 weight masters to the bf16 operands of the chain
+  // that follows (W~{theta,phi,g} = [W | b | 0] as [3][Ci][Ca], Wz as [C][Ci]) — the launch the forward used to spend on it
+  int nwork, nprep;
+  GramPrep prep;
 };
 
 __global__ void __launch_bounds__(GK_THREADS, 1)
@@ -52,6 +56,22 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
   __shared__ uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_holder;
 
+  if (static_cast<int>(blockIdx.x) >= p.nwork) {            // weight preparation rides along (whole CTA, no barriers used)
+    const GramPrep& q = p.prep;
+    const int naug = 3 * q.Ci * q.Ca, nz = q.C * q.Ci;
+    for (int i = (blockIdx.x - p.nwork) * GK_THREADS + threadIdx.x; i < naug + nz; i += p.nprep * GK_THREADS) {
+      if (i < naug) {
+        const int m = i / (q.Ci * q.Ca), r = (i / q.Ca) % q.Ci, c = i % q.Ca;
+        const float* W = m == 0 ? q.tw : (m == 1 ? q.pw : q.gw);
+        const float* bb = m == 0 ? q.tb : (m == 1 ? q.pb : q.gb);
+        const float v = c < q.C ? W[static_cast<size_t>(r) * q.C + c] : (c == q.C ? bb[r] : 0.f);
+        q.waug[i] = __float2bfloat16(v);
+      } else {
+        q.wzb[i - naug] = __float2bfloat16(q.wz[i - naug]);
+      }
+    }
+    return;
+  }
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5;
@@ -300,7 +320,7 @@ bool gram_contraction_supported(int C) { return C == 128 || C == 256; }
 // rowsum = column sums of A (unscaled).
 int gram_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* scratch, float* rowsum, const float* rowscale,
                      const float* rowv, float corner, int border, int B, int N, int C, int Ca, int ksplit,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, const GramPrep* prep) {
   if (!gram_contraction_supported(C)) return set_error(GLF_ERR_UNSUPPORTED, "gram_contraction: C must be 128 or 256");
   CUtensorMap tmA, tmX;
   int rc = make_tmap_bf16(&tmA, A, C, N, B, C, static_cast<long long>(N) * C, 64);
@@ -332,7 +352,14 @@ int gram_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* scratch
   if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gram)");
   const long long grid = static_cast<long long>(B) * p.ksplit;
   if (grid > 0x7fffffffLL) return set_error(GLF_ERR_INVALID, "gram_contraction: too many work items");
-  gram_kernel<<<static_cast<int>(grid), GK_THREADS, GK_SMEM, stream>>>(tmA, tmX, p);
+  p.nwork = static_cast<int>(grid);
+  p.nprep = 0;
+  p.prep = GramPrep{};
+  if (prep != nullptr) {
+    p.prep = *prep;
+    p.nprep = 20;          // ~134 K elements at C = 256: 21 per thread
+  }
+  gram_kernel<<<static_cast<int>(grid) + p.nprep, GK_THREADS, GK_SMEM, stream>>>(tmA, tmX, p);
   return check_cuda(cudaGetLastError(), "gram_contraction launch");
 }
 

@@ -113,6 +113,12 @@ int cast_bf16(const float* in, bf16* out, long long n, cudaStream_t stream);
 // Augmented width of the per-sequence matrices: column C is the homogeneous coordinate, the rest zero padding.
 inline int gram_ca(int C) { return C + 8; }
 int gram_prep_weights(const glf_weights* w, int C, int Ci, int Ca, bf16* waug, bf16* wzb, cudaStream_t stream);
+// the same conversion as extra CTAs of the S contraction's launch (gram_kernel): no launch of its own
+struct GramPrep {
+  const float *tw, *tb, *pw, *pb, *gw, *gb, *wz;
+  bf16 *waug, *wzb;
+  int C, Ci, Ca;
+};
 // rowscale (optional, [C]): rows < C of the augmented matrix (column C included) are scaled per row
 int gram_assemble_aug(const float* Mf, const float* colv, const float* rowv, const float* rowscale, bf16* out, int B,
                       int C, int Ca, float corner, cudaStream_t stream);
@@ -127,7 +133,7 @@ int gram_assemble_F(const bf16* G0, const bf16* Hf, const bf16* dT, const bf16* 
 bool gram_contraction_supported(int C);
 int gram_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* scratch, float* rowsum, const float* rowscale,
                      const float* rowv, float corner, int border, int B, int N, int C, int Ca, int ksplit,
-                     cudaStream_t stream);
+                     cudaStream_t stream, const GramPrep* prep = nullptr);
 int gram_unpack_grads(const float* dwaug, const glf_grads* g, int C, int Ci, int Ca, cudaStream_t stream);
 // One CTA per sequence runs the whole [C x C] chain between the token-sized products (glf_chain.cu), C = 256, C' = 128
 bool gram_chain_supported(int C, int Ci);
