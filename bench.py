@@ -476,8 +476,8 @@ def count_launches(clips: int, C: int) -> int:
     """Kernels launched by libglf_sm100a per step (fwd+bwd, both modules + gate), counted from the orchestration in
     glfusion_b200/csrc/glf_api.cu (memset/memcpy nodes excluded); agrees with profiles/r01_v11_launches.csv (39,
     token-space form), profiles/r01_v17_launches.csv (55, Gram form as batched tile GEMMs) and
-    profiles/r02_v3_launches.csv / r02_v8_launches.csv (27, Gram form with the per-sequence chain kernels; 24 since the gate
-    backward finishes the chain to the logits itself and the weight preparation rides along in the S launch)."""
+    profiles/r02_v3_launches.csv / r02_v8_launches.csv (27, Gram form with the per-sequence chain kernels; 25 since the weight
+    preparation rides along in the S launch)."""
     if dot_algorithm(C) == "gram" and C == 256 and os.environ.get("GLF_GRAM_CHAIN", "1") != "0":
         fwd_mod = 4      # S (gram_kernel; the weight preparation rides along as extra CTAs), chain_fwd, U GEMM, bn_finalize
         bwd_mod = 6      # finalize, R (gram_kernel), chain_bwd, wgrad, wgrad_reduce, dX GEMM
@@ -489,9 +489,7 @@ def count_launches(clips: int, C: int) -> int:
         fwd_mod = 6      # prep_weights, proj GEMM, M GEMM, W' GEMM, U GEMM, bn_finalize
         bwd_mod = 11     # finalize, apply, dTheta, dW', dWz, dM, dPhi, dG, dWcat, dX, bias-gradient reduction
     pair = 2             # fused MGFM+MLFM LayerNorm forward / backward
-    # gate_concat fwd, gate_concat bwd (the TMA form finishes the chain to the logits itself: cfg2 / C <= 512 bf16 views);
-    # the SIMT and channels-last forms add gate_finish
-    gate = 2 if (C % 64 == 0 and C <= 512) else 3
+    gate = 3             # gate_concat fwd, gate_concat bwd, gate_finish
     return 2 * (fwd_mod + bwd_mod) + pair + gate
 
 

@@ -355,12 +355,11 @@ __global__ void __launch_bounds__(256)
 // da[p] = sum_c f4[c,p] * dXl[p,c] (the CTA sees every channel, so no partial table: da_part has one slice).
 __global__ void __launch_bounds__(256)
     gate_concat_bwd_tma_kernel(const __grid_constant__ ViewMaps maps, const ViewPtrs vp, const float* __restrict__ gate,
-                               const bf16* __restrict__ dxg, const bf16* __restrict__ dxl, int C, int V, int hw,
-                               int ncls, float weight) {
+                               const bf16* __restrict__ dxg, const bf16* __restrict__ dxl, float* __restrict__ da_part,
+                               int C, int V, int hw) {
   extern __shared__ uint8_t gsm_raw[];
   __shared__ uint64_t bar;
   __shared__ float a_sm[64];
-  __shared__ float da_sm[64];
   const uint32_t base = (smem_u32(gsm_raw) + 1023u) & ~1023u;
   uint8_t* gen = gsm_raw + (base - smem_u32(gsm_raw));
   const int bv = blockIdx.y, b = bv / V, v = bv % V;
@@ -440,7 +439,7 @@ __global__ void __launch_bounds__(256)
     float da = acc.x + acc.y;
     da += __shfl_xor_sync(0xffffffffu, da, 1);
     da += __shfl_xor_sync(0xffffffffu, da, 2);
-    if ((lane & 3) == 0) da_sm[pl] = da;
+    if ((lane & 3) == 0 && pl < valid) da_part[static_cast<long long>(bv) * hw + p0 + pl] = da;
   }
   __syncthreads();
   {
@@ -458,10 +457,6 @@ __global__ void __launch_bounds__(256)
       if (pp < hw) *reinterpret_cast<uint4*>(df4 + static_cast<long long>(c) * hw + pp) = make_uint4(r[0], r[1], r[2], r[3]);
     }
   }
-  // the CTA saw every channel, so the gate gradient of its 64 positions is complete: finish the chain to the logits here
-  // (coalesced along the positions) instead of in a second launch
-  if (threadIdx.x < valid)
-    gate_finish_one(vp, v, b, p0 + threadIdx.x, hw, ncls, weight, a_sm[threadIdx.x], da_sm[threadIdx.x]);
 }
 
 bool gate_tma_ok(int C, int hw, int io_dtype, int x_dtype, const void* const* f4, int V) {
@@ -826,8 +821,16 @@ int gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, i
     cudaError_t e = cudaFuncSetAttribute(gate_concat_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gate_bwd_tma)");
     gate_concat_bwd_tma_kernel<<<dim3((hw + 63) / 64, B * V), 256, smem, stream>>>(
-        maps, vp, gate, reinterpret_cast<const bf16*>(dxg), reinterpret_cast<const bf16*>(dxl), C, V, hw, ncls, weight);
-    return check_cuda(cudaGetLastError(), "gate_concat_bwd_tma launch");   // (the chain to the logits is finished inside)
+        maps, vp, gate, reinterpret_cast<const bf16*>(dxg), reinterpret_cast<const bf16*>(dxl), da_part, C, V, hw);
+    int rc = check_cuda(cudaGetLastError(), "gate_concat_bwd_tma launch");
+    if (rc) return rc;
+    // (finishing the chain to the logits inside this kernel was tried: the extra ~2 us at the end of every CTA, two CTAs
+    //  per SM and 22 waves, cost 50 us against the 11 us of the launch below)
+    nct = 1;   // the gate gradient is complete: one slice of the table
+    const long long n = static_cast<long long>(B) * V * hw;
+    gate_finish_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(vp, gate, da_part, nct, B * V, V, hw,
+                                                                                  ncls, weight);
+    return check_cuda(cudaGetLastError(), "gate_finish launch");
   }
   dim3 grid((hw + 63) / 64, nct, B * V);
   if (grid.y > 65535 || grid.z > 65535) return set_error(GLF_ERR_INVALID, "gate_concat: grid too large");
