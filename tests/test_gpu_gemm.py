@@ -127,7 +127,7 @@ def test_gemm_cta_pair_epilogues():
 
 
 @pytest.mark.parametrize("M,K,batch,shared_b", [(3136, 256, 16, False), (1000, 128, 40, False), (50176, 128, 1, True),
-                                                 (2049, 64, 20, False)])
+                                                 (2049, 64, 20, False), (1536, 192, 30, False)])
 def test_gemm_resident_b_operand(M, K, batch, shared_b):
     """N = 256, K <= 256, many row tiles per B operand: the kernel that keeps B in shared memory and streams only A
     (csrc/glf_gemm3.cu; U = X Q^T + c of the Gram form).  CTAs own contiguous tile ranges that straddle batch entries;
