@@ -12,6 +12,7 @@
 //   warp 1      MMA issuer: tcgen05.mma M=128, N=C, K=16, both operands MN-major, C/128 accumulators
 //   warps 2..9  during the main loop: column sums of A read from the staged blocks (thread = channel); afterwards the
 //               epilogue: tcgen05.ld -> bf16 rows of the augmented [Ca x Ca] matrix, or fp32 red.add for split-K
+#include <cstdio>
 #include <cstdlib>
 
 #include "glf_internal.h"
@@ -27,6 +28,13 @@ constexpr int GK_MAX_STAGES = 6;                   // A == X: the same ring hold
 constexpr uint32_t GK_BLK = 64 * 256 * 2;          // one operand block: 64 tokens x 256 channels (4 boxes of 64 x 64)
 constexpr uint32_t GK_STAGE = 2 * GK_BLK;          // A block + X block
 constexpr uint32_t GK_SMEM = GK_STAGES * GK_STAGE + 1024;
+
+// Debug aid (GLF_GRAM_TRACE=1): SM clock of CTA 0 at a few points, printed by the host after the launch.
+__device__ long long g_gram_trace[8];
+#define GK_TRACE(i)                                             \
+  do {                                                          \
+    if (p.trace && blockIdx.x == 0) g_gram_trace[i] = clock64(); \
+  } while (0)
 
 struct GramKParams {
   int B, N, C, Ca;
@@ -46,6 +54,7 @@ struct GramKParams {
   // that follows (W~{theta,phi,g} = [W | b | 0] as [3][Ci][Ca], Wz as [C][Ci]) — the launch the forward used to spend on it
   int nwork, nprep;
   GramPrep prep;
+  int trace;
 };
 
 __global__ void __launch_bounds__(GK_THREADS, 1)
@@ -88,6 +97,7 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
   const uint32_t stage_bytes = p.same ? GK_BLK : GK_STAGE;
 
   if (threadIdx.x == 0) {
+    GK_TRACE(0);
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmX);
 #pragma unroll
@@ -134,8 +144,11 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
       const uint32_t idesc_ones = make_idesc_bf16(128, 16, true, false);
       int stage = 0;
       uint32_t phase = 0;
+      GK_TRACE(1);
       for (int it = 0; it < nkb; ++it) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
+        if (it == 0) GK_TRACE(2);
+        if (it == nkb / 2) GK_TRACE(3);
         tc_fence_after();
         const uint32_t sa = smem_base + stage * stage_bytes;
         const uint32_t sb = p.same ? sa : sa + GK_BLK;
@@ -170,6 +183,7 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
         if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
       umma_commit(smem_u32(&tmem_full_bar));
+      GK_TRACE(4);
     }
   } else {
     // ---- column sums of A from the staged blocks: thread = (channel pair cp, half of the 64 rows); 32-bit loads (the
@@ -234,6 +248,7 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
     const int q = warp & 3;
     const int mt = (warp - 2) >> 2;
     mbar_wait(smem_u32(&tmem_full_bar), 0);
+    if (threadIdx.x == 64) GK_TRACE(5);
     tc_fence_after();
     if (mt < MT) {
       const int row = mt * 128 + q * 32 + lane;
@@ -307,6 +322,7 @@ __global__ void __launch_bounds__(GK_THREADS, 1)
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) GK_TRACE(6);
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -359,8 +375,21 @@ int gram_contraction(const bf16* A, const bf16* X, bf16* out_aug, float* scratch
     p.prep = *prep;
     p.nprep = 20;          // ~134 K elements at C = 256: 21 per thread
   }
+  {
+    const char* et = getenv("GLF_GRAM_TRACE");
+    p.trace = (et && et[0] == '1') ? 1 : 0;
+  }
   gram_kernel<<<static_cast<int>(grid) + p.nprep, GK_THREADS, GK_SMEM, stream>>>(tmA, tmX, p);
-  return check_cuda(cudaGetLastError(), "gram_contraction launch");
+  rc = check_cuda(cudaGetLastError(), "gram_contraction launch");
+  if (rc == 0 && p.trace) {      // debug only: synchronises the stream
+    long long t[8] = {0};
+    cudaStreamSynchronize(stream);
+    cudaMemcpyFromSymbol(t, g_gram_trace, sizeof(t));
+    fprintf(stderr, "[gram trace same=%d sym=%d] first block landed +%lld, half of the k-blocks +%lld, last MMA issued +%lld, "
+                    "accumulator complete +%lld, CTA done +%lld cycles (k loop entered +%lld)\n",
+            p.same, p.sym, t[2] - t[0], t[3] - t[0], t[4] - t[0], t[5] - t[0], t[6] - t[0], t[1] - t[0]);
+  }
+  return rc;
 }
 
 }  // namespace glf
