@@ -130,3 +130,25 @@ def test_cycle_pass_through_the_fusion_node():
     for a, b in zip(grads[0], grads[1]):
         scale = b.abs().max().item()
         assert (a - b).abs().max().item() <= 2e-2 * scale + 1e-12
+
+
+def test_install_trainer_replaces_the_two_methods_with_the_same_call_shape():
+    """glfusion_b200.install_trainer(main.Trainer): the call sites of R/main.py:231 and :234 work unchanged."""
+    import glfusion_b200
+
+    class Trainer:                       # stands in for main.Trainer (the script cannot be imported off the build box)
+        device = DEV
+
+    glfusion_b200.install_trainer(Trainer)
+    d = np.load(GOLDEN[0])               # dense fixture
+    assert int(d["dense"]) == 1
+    feat = torch.from_numpy(d["feat"]).to(DEV).requires_grad_(True)
+    t = Trainer()
+    loss = t.dense_seg_cycle(feat, target_region=int(d["target_region"]), cyc_off=int(d["cyc_off"]),
+                             chunk_size=int(d["chunk_size"]), temperature=float(d["temperature"]),
+                             soft_label=bool(d["soft_label"]), is_overlap=bool(d["is_overlap"]))
+    assert abs(loss.item() - float(d["loss"])) <= TOL * abs(float(d["loss"]))
+    s = np.load([g for g in GOLDEN if "single" in g][0])
+    np.random.seed(int(s["np_seed"]))
+    loss = t.seg_cycle(torch.from_numpy(s["feat"]).to(DEV), target_region=16, cyc_off=2, chunk_size=3, temperature=10)
+    assert abs(loss.item() - float(s["loss"])) <= TOL * abs(float(s["loss"]))
