@@ -256,6 +256,27 @@ def test_oracle_dot_channel_widths(C, B, T, H, W):
             assert_close("grad:" + k, pp.grad, go[k], grad_tol(k), zero_scale=scale)
 
 
+def test_network_width_at_the_network_sequence_length():
+    """in_channels = 2048 with the reference network's own sequence (3 views x 28 x 28 = 2 352 tokens, ours.py:1746-1747,
+    :1820): the token-space form with its big products on CTA pairs (projection, dTheta, dPhi / dG with alpha and column
+    statistics, dX with the residual addend, dWcat with K slices, W_z with several column tiles of statistics) and the
+    wide-row LayerNorm ring kernels, against the oracle."""
+    C, B, T, H, W = 2048, 2, 3, 28, 28
+    p = O.init_params(C, seed=81, randomize_affine=True)
+    gen = torch.Generator().manual_seed(82)
+    x = torch.randn(B, C, T, H, W, generator=gen)
+    dz = torch.randn(B, C, T, H, W, generator=gen)
+    zo, dxo, go = O.tpavi_fwd_bwd(x, dz, {k: v.clone() for k, v in p.items()}, mode="dot")
+    m = load_module_from_params(TPAVIModule, p, C, "dot", True).train()
+    z, dx = _run(m, x.to(DEV, torch.bfloat16), dz.to(DEV, torch.bfloat16))
+    assert_close("z", z, zo, BF16_TOL)
+    assert_close("dx", dx, dxo, BF16_TOL)
+    scale = grad_scale(go.values())
+    for k, pp in m.named_parameters():
+        if not k.startswith("align_channel"):
+            assert_close("grad:" + k, pp.grad, go[k], grad_tol(k), zero_scale=scale)
+
+
 @pytest.mark.parametrize("C,B,T,H,W", [(128, 3, 3, 5, 7), (256, 2, 1, 9, 15), (256, 1, 2, 13, 20), (64, 2, 2, 6, 6)])
 def test_oracle_embedded_ragged(C, B, T, H, W):
     """Softmax mode, token counts that are not multiples of the 128-wide query/key tiles (masking paths of the flash
