@@ -313,7 +313,8 @@ bool defer_ln(const glf_desc* d) { return d->reserved[0] == 1; }
 int check_pair(const glf_desc* d, const Dims& m) {
   if (d->precision != GLF_PRECISION_BF16 || d->io_dtype != GLF_DTYPE_BF16 || m.pack_x || d->dz_layout != GLF_LAYOUT_TOKEN)
     return set_error(GLF_ERR_UNSUPPORTED, "fused LayerNorm pair needs bf16 token-major activations");
-  if (!ln_tma_supported(m.C)) return set_error(GLF_ERR_UNSUPPORTED, "fused LayerNorm pair needs C <= 256");
+  if (!ln_tma_supported(m.C) && !ln_pair_wide_supported(m.C))
+    return set_error(GLF_ERR_UNSUPPORTED, "fused LayerNorm pair needs C %% 8 == 0 and C <= 2048");
   return 0;
 }
 
@@ -821,7 +822,8 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
   }
   int nb = 0;
   if (defer_ln(d)) {
-    nb = ln_bwd_tma_blocks(m.rows);   // dV and the partials were written by glf_fusion_ln_bwd
+    // dV and the partials were written by glf_fusion_ln_bwd
+    nb = ln_tma_supported(C) ? ln_bwd_tma_blocks(m.rows) : bn_res_ln_bwd_blocks(m.rows, C);
   } else {
     GLF_TRY(bn_res_ln_bwd(dZ, dz_dtype, s.U, X, GLF_DTYPE_BF16, s.bn_a, s.bn_b, s.bn_mean, s.bn_rstd, w->ln_w, s.ln_mu,
                           s.ln_r, wb.dV, wb.part_ln, m.rows, C, &nb, stream));
@@ -1025,6 +1027,9 @@ GLF_API int glf_fusion_ln_fwd_parts(const glf_desc* d, const void* xg, const voi
   const float* lb[2] = {wg->ln_b, wl->ln_b};
   float* mu[2] = {sg.ln_mu, sl.ln_mu};
   float* r[2] = {sg.ln_r, sl.ln_r};
+  if (!ln_tma_supported(m.C))     // wide rows (256 < C <= 2048): the sliced-row ring kernel, both blocks in one pass
+    return ln_pair_fwd_wide(U, X, a, b, lw, lb, mu, r, reinterpret_cast<bf16*>(z), m.rows, m.C, d->eps_ln, d->accumulate,
+                            stream, reinterpret_cast<bf16*>(z_global));
   return ln_fwd_tma(2, U, X, a, b, lw, lb, mu, r, reinterpret_cast<bf16*>(z), m.rows, m.C, d->eps_ln, d->accumulate,
                     stream, reinterpret_cast<bf16*>(z_global));
 }
@@ -1037,7 +1042,7 @@ GLF_API int glf_fusion_ln_bwd(const glf_desc* d, const void* dz, const void* xg,
 
 GLF_API int glf_fusion_ln_bwd_views_supported(const glf_desc* d) {
   Dims m;
-  if (d == nullptr || make_dims(d, &m) != 0 || check_pair(d, m) != 0) return 0;
+  if (d == nullptr || make_dims(d, &m) != 0 || check_pair(d, m) != 0 || !ln_tma_supported(m.C)) return 0;
   return (static_cast<long long>(d->H) * d->W) % ln_bwd_tma_tile_rows() == 0 && d->T <= 8 ? 1 : 0;
 }
 
@@ -1079,6 +1084,15 @@ GLF_API int glf_fusion_ln_bwd_views(const glf_desc* d, const void* dz, const voi
   float* part[2] = {bg.part_ln, bl.part_ln};
   int nb = 0;
   static_assert(sizeof(long long) == sizeof(int64_t), "stride tables are passed through unchanged");
+  if (!ln_tma_supported(m.C)) {
+    // wide rows: the backward is issue-bound, not bandwidth-bound, so sharing the dz read buys nothing;
+    // the two blocks run the sliced-row ring kernel one after the other
+    if (views) return set_error(GLF_ERR_UNSUPPORTED, "per-view dz needs C <= 256");
+    for (int k = 0; k < 2; ++k)
+      GLF_TRY(bn_res_ln_bwd(dz, GLF_DTYPE_BF16, U[k], X[k], GLF_DTYPE_BF16, a[k], b[k], mean[k], rstd[k], lw[k], mu[k], r[k],
+                            dV[k], part[k], m.rows, m.C, &nb, stream));
+    return 0;
+  }
   return ln_bwd_tma(2, reinterpret_cast<const bf16*>(dz), U, X, a, b, lw, mean, rstd, mu, r, dV, part, m.rows, m.C, &nb,
                     stream, views ? d->T : 0, dz_views, reinterpret_cast<const long long*>(dz_stride_b), d->H * d->W);
 }

@@ -608,6 +608,139 @@ __global__ void __launch_bounds__(ROW_THREADS)
   cp_async_wait<0>();
 }
 
+// The MGFM + MLFM pair of the fused call site for wide rows: Z = sum_m LayerNorm(a_m U_m + b_m + X_m) lw_m + lb_m in ONE pass
+// (the two single-block calls read and re-write Z in between: 7 row streams instead of 5), optionally storing module 0's
+// own output (f4_global_fusion) as well.  Same slicing and per-thread cp.async ring as bn_res_ln_fwd_ring_kernel.
+struct LnPairWide {
+  const bf16* U[2];
+  const bf16* X[2];
+  const float* a[2];
+  const float* b[2];
+  const float* lw[2];
+  const float* lb[2];
+  float* mu[2];
+  float* r[2];
+  bf16* Z;
+  bf16* Z0;
+  long long rows;
+  int C, S, accumulate;
+  float eps;
+};
+
+template <bool PARTS>
+__global__ void __launch_bounds__(ROW_THREADS, 2) ln_pair_fwd_ring_kernel(const LnPairWide p) {
+  extern __shared__ __align__(16) uint4 ln_ring[];
+  __shared__ float red[2 * ROW_WARPS * 2];
+  int buf = 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.S, C = p.C;
+  const int RPB = ROW_WARPS / S;
+  const int rslot = warp / S, slice = warp % S;
+  const int c0 = slice * 256 + lane * 8;
+  const bool cact = c0 < C;
+  float a0[8], b0[8], w0[8], a1[8], b1[8], w1[8], lbs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a0[i] = b0[i] = w0[i] = a1[i] = b1[i] = w1[i] = lbs[i] = 0.f;
+  if (cact) {
+    float t[8];
+    load8(p.a[0] + c0, a0); load8(p.b[0] + c0, b0); load8(p.lw[0] + c0, w0);
+    load8(p.a[1] + c0, a1); load8(p.b[1] + c0, b1); load8(p.lw[1] + c0, w1);
+    load8(p.lb[0] + c0, lbs); load8(p.lb[1] + c0, t);
+    if (!PARTS) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) lbs[i] += t[i];             // both biases at once
+    }
+  }
+  const float invC = 1.f / static_cast<float>(C);
+  const long long rows = p.rows;
+  const long long step = static_cast<long long>(gridDim.x) * RPB;
+  const long long first = static_cast<long long>(blockIdx.x) * RPB + rslot;
+  uint4* mine = ln_ring + threadIdx.x;
+  constexpr int NOPS = 5;
+  auto issue = [&](long long row, int slot) {
+    if (cact && row < rows) {
+      uint4* dst = mine + slot * NOPS * ROW_THREADS;
+      const long long off = row * C + c0;
+      cp_async16(dst, p.X[0] + off);
+      cp_async16(dst + ROW_THREADS, p.U[0] + off);
+      cp_async16(dst + 2 * ROW_THREADS, p.X[1] + off);
+      cp_async16(dst + 3 * ROW_THREADS, p.U[1] + off);
+      if (p.accumulate) cp_async16(dst + 4 * ROW_THREADS, p.Z + off);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int d = 0; d < LN_DEPTH - 1; ++d) issue(first + d * step, d);
+  int it = 0;
+  for (long long base = static_cast<long long>(blockIdx.x) * RPB; base < rows; base += step, ++it) {
+    const long long row = base + rslot;
+    const bool act = cact && row < rows;
+    issue(row + (LN_DEPTH - 1) * step, (it + LN_DEPTH - 1) % LN_DEPTH);
+    cp_async_wait<LN_DEPTH - 1>();
+    const uint4* src = mine + (it % LN_DEPTH) * NOPS * ROW_THREADS;
+    float v0[8], v1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v0[i] = v1[i] = 0.f;
+    if (act) {
+      Raw8<bf16> q;
+      float x[8], u[8];
+      q.v = src[0]; cvt8(q, x);
+      q.v = src[ROW_THREADS]; cvt8(q, u);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v0[i] = fmaf(a0[i], u[i], b0[i]) + x[i];
+      q.v = src[2 * ROW_THREADS]; cvt8(q, x);
+      q.v = src[3 * ROW_THREADS]; cvt8(q, u);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v1[i] = fmaf(a1[i], u[i], b1[i]) + x[i];
+    }
+    float sm2[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sm2[0] += v0[i]; sm2[1] += v1[i]; }
+    row_reduce<2>(sm2, S, rslot, slice, red, buf);
+    const float mu0 = sm2[0] * invC, mu1 = sm2[1] * invC;
+    float q2[2] = {0.f, 0.f};
+    if (act) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        q2[0] = fmaf(v0[i] - mu0, v0[i] - mu0, q2[0]);
+        q2[1] = fmaf(v1[i] - mu1, v1[i] - mu1, q2[1]);
+      }
+    }
+    row_reduce<2>(q2, S, rslot, slice, red, buf);
+    const float r0 = rsqrtf(q2[0] * invC + p.eps), r1 = rsqrtf(q2[1] * invC + p.eps);
+    if (act) {
+      float o[8];
+      if (PARTS) {
+        float o0[8], lb1[8];
+        load8(p.lb[1] + c0, lb1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          o0[i] = fmaf((v0[i] - mu0) * r0, w0[i], lbs[i]);
+          o[i] = o0[i] + fmaf((v1[i] - mu1) * r1, w1[i], lb1[i]);
+        }
+        store8(p.Z0 + row * C + c0, o0);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaf((v0[i] - mu0) * r0, w0[i], fmaf((v1[i] - mu1) * r1, w1[i], lbs[i]));
+      }
+      if (p.accumulate) {
+        Raw8<bf16> zc;
+        zc.v = src[4 * ROW_THREADS];
+        float z0[8];
+        cvt8(zc, z0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += z0[i];
+      }
+      store8(p.Z + row * C + c0, o);
+      if (slice == 0 && lane == 0) {
+        if (p.mu[0] != nullptr) { p.mu[0][row] = mu0; p.r[0][row] = r0; }
+        if (p.mu[1] != nullptr) { p.mu[1][row] = mu1; p.r[1][row] = r1; }
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
 __global__ void __launch_bounds__(ROW_THREADS, 2)
     bn_res_ln_bwd_ring_kernel(const bf16* __restrict__ dZ, const bf16* __restrict__ U, const bf16* __restrict__ X,
                               const float* __restrict__ bn_a, const float* __restrict__ bn_b,
@@ -1017,6 +1150,38 @@ int bn_res_ln_fwd(const void* U_, const void* X_, int act_dtype, const float* a,
       bn_res_ln_fwd_kernel<float, float><<<grid, ROW_THREADS, 0, stream>>>(U, X, a, b, lw, lb, (float*)Z, mu, r, rows, C, S, eps, accumulate);
   }
   return check_cuda(cudaGetLastError(), "bn_res_ln_fwd launch");
+}
+
+// fused pair forward for wide rows (256 < C <= 2048, bf16): see ln_pair_fwd_ring_kernel
+bool ln_pair_wide_supported(int C) { return C > 256 && C <= 2048 && C % 8 == 0; }
+
+int ln_pair_fwd_wide(const bf16* const* U, const bf16* const* X, const float* const* a, const float* const* b,
+                     const float* const* lw, const float* const* lb, float* const* mu, float* const* r, bf16* Z,
+                     long long rows, int C, float eps, int accumulate, cudaStream_t stream, bf16* Z0) {
+  if (!ln_pair_wide_supported(C)) return set_error(GLF_ERR_UNSUPPORTED, "ln_pair_fwd_wide: 256 < C <= 2048 expected");
+  if (Z0 != nullptr && accumulate) return set_error(GLF_ERR_INVALID, "ln_pair_fwd_wide: parts with accumulate");
+  int S = (C + 255) / 256;
+  while (ROW_WARPS % S != 0) ++S;
+  LnPairWide p;
+  for (int m = 0; m < 2; ++m) {
+    p.U[m] = U[m]; p.X[m] = X[m]; p.a[m] = a[m]; p.b[m] = b[m]; p.lw[m] = lw[m]; p.lb[m] = lb[m];
+    p.mu[m] = mu[m]; p.r[m] = r[m];
+    if (U[m] == nullptr || !aligned16(U[m], X[m])) return set_error(GLF_ERR_INVALID, "ln_pair_fwd_wide: operands must be 16-byte aligned");
+  }
+  if (!aligned16(Z, Z0 != nullptr ? Z0 : Z)) return set_error(GLF_ERR_INVALID, "ln_pair_fwd_wide: outputs must be 16-byte aligned");
+  p.Z = Z; p.Z0 = Z0; p.rows = rows; p.C = C; p.S = S; p.accumulate = accumulate; p.eps = eps;
+  const int grid = row_grid(rows, S);
+  const size_t ring = LN_DEPTH * 5 * ROW_THREADS * sizeof(uint4);       // 80 KB
+  if (Z0 != nullptr) {
+    cudaError_t e = cudaFuncSetAttribute(ln_pair_fwd_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ring));
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(ln pair wide)");
+    ln_pair_fwd_ring_kernel<true><<<grid, ROW_THREADS, ring, stream>>>(p);
+  } else {
+    cudaError_t e = cudaFuncSetAttribute(ln_pair_fwd_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ring));
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(ln pair wide)");
+    ln_pair_fwd_ring_kernel<false><<<grid, ROW_THREADS, ring, stream>>>(p);
+  }
+  return check_cuda(cudaGetLastError(), "ln_pair_fwd_wide launch");
 }
 
 int bn_res_ln_bwd_blocks(long long rows, int C) {

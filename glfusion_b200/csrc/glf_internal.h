@@ -91,6 +91,11 @@ int ln_bwd_tma(int nmod, const bf16* dZ, const bf16* const* U, const bf16* const
                float* const* part, long long rows, int C, int* nblocks, cudaStream_t stream, int dz_nv = 0,
                const void* const* dz_views = nullptr, const long long* dz_sb = nullptr, int dz_hw = 0);
 int ln_bwd_tma_tile_rows();
+// (glf_eltwise.cu) the fused MGFM + MLFM LayerNorm forward for wide rows, 256 < C <= 2048 (sliced rows, cp.async ring)
+bool ln_pair_wide_supported(int C);
+int ln_pair_fwd_wide(const bf16* const* U, const bf16* const* X, const float* const* a, const float* const* b,
+                     const float* const* lw, const float* const* lb, float* const* mu, float* const* r, bf16* Z,
+                     long long rows, int C, float eps, int accumulate, cudaStream_t stream, bf16* Z0);
 int bn_bwd_finalize(const float* part, int np, int C, double count, const glf_desc* d, const glf_weights* w,
                     const float* mean, const float* rstd, const glf_grads* g, float* k1, float* k2, float* k3,
                     cudaStream_t stream);

@@ -130,7 +130,8 @@ GLF_API int glf_tpavi_bwd(const glf_desc* d, const void* dz, const void* x, cons
  *   3. backward: glf_fusion_ln_bwd fills dV / the per-channel partials inside ws_g and ws_l (each sized
  *      ws_bwd_bytes), then glf_tpavi_bwd(d, dz, x_g, ..., ws_g) and glf_tpavi_bwd(d, dz, x_l, ..., ws_l) with
  *      d->reserved[0] = 1 continue from there.
- * Requirements (glf_fusion_ln_supported returns 1): bf16 token-major x / dz, GLF_PRECISION_BF16, C <= 256. */
+ * Requirements (glf_fusion_ln_supported returns 1): bf16 token-major x / dz, GLF_PRECISION_BF16, C <= 2048 (C <= 256: one
+ * bulk-copy pass each way; wider rows: one sliced-row pass forward, the two blocks' backward passes back to back). */
 GLF_API int glf_fusion_ln_supported(const glf_desc* d);
 GLF_API int glf_fusion_ln_fwd(const glf_desc* d, const void* xg, const void* xl, const glf_weights* wg,
                       const glf_weights* wl, void* z, void* saved_g, void* saved_l, glf_stream_t stream);

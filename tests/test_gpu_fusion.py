@@ -426,3 +426,37 @@ def test_dict_api_backward_reads_per_view_gradients_in_place(h, w):
     for other in res[1:]:
         for a, b in zip(res[0][0] + res[0][1], other[0] + other[1]):
             assert (a - b).abs().max().item() <= 2e-2 * max(a.abs().max().item(), 1e-6) + 1e-7
+
+
+@pytest.mark.parametrize("C,V,h,w", [(512, 2, 9, 8), (2048, 3, 6, 6), (768, 2, 5, 7)])
+def test_wide_channel_fused_node_against_oracle(C, V, h, w):
+    """Channel counts above 256: the fused node still runs both blocks' LayerNorms in one pass forward (sliced rows,
+    ln_pair_fwd_ring_kernel) and returns the MGFM part beside the sum; seeded oracle comparison of outputs, parts and
+    every gradient."""
+    B = 2
+    pg = O.init_params(C, seed=41, randomize_affine=True)
+    pl = O.init_params(C, seed=42, randomize_affine=True)
+    gen = torch.Generator().manual_seed(43)
+    f4 = [torch.randn(B, C, h, w, generator=gen) for _ in range(V)]
+    cl = [torch.randn(B, 5, h, w, generator=gen) for _ in range(V)]
+    ct = [torch.randn(B, 1, h, w, generator=gen) for _ in range(V)]
+    do = [torch.randn(B, C, h, w, generator=gen) for _ in range(V)]
+    outs, df4, dcls, dctr, gg, gl = O.fusion_fwd_bwd(f4, cl, ct, do, {k: v.clone() for k, v in pg.items()},
+                                                     {k: v.clone() for k, v in pl.items()})
+    f = _build(C, pg, pl)
+    keys = [str(i) for i in range(V)]
+    f4d = {k: t.to(DEV, torch.bfloat16).requires_grad_(True) for k, t in zip(keys, f4)}
+    cld = {k: t.to(DEV).requires_grad_(True) for k, t in zip(keys, cl)}
+    ctd = {k: t.to(DEV).requires_grad_(True) for k, t in zip(keys, ct)}
+    fus, glob, loc = f.forward_parts(f4d, cld, ctd)
+    torch.autograd.backward([fus[k] for k in keys], [t.to(DEV, torch.bfloat16) for t in do])
+    torch.cuda.synchronize()
+    for v, k in enumerate(keys):
+        assert_close(f"out:{v}", fus[k], outs[v], BF16_TOL)
+        assert_close(f"global + local:{v}", glob[k].float() + loc[k].float(), outs[v], BF16_TOL)
+        assert_close(f"df4:{v}", f4d[k].grad, df4[v], BF16_TOL)
+        assert_close(f"dctr:{v}", ctd[k].grad, dctr[v], 4e-2)
+    for mod, ref in ((f.local_attn, gl), (f.global_attn, gg)):
+        for k, p in mod.named_parameters():
+            if not k.startswith("align_channel"):
+                assert_close("grad:" + k, p.grad, ref[k], grad_tol(k), abs_floor=1e-3)
