@@ -286,15 +286,17 @@ __device__ __forceinline__ void bulk_g2s_gate(uint32_t dst, const void* src, uin
 // grid: (ceil(hw/64), B*V); block 256 (8 warps: warp w owns positions 8w..8w+7 of the block)
 __global__ void __launch_bounds__(256)
     gate_concat_fwd_tma_kernel(const __grid_constant__ ViewMaps maps, const ViewPtrs vp, bf16* __restrict__ xg,
-                               bf16* __restrict__ xl, float* __restrict__ gate, int C, int V, int hw, int ncls,
+                               bf16* __restrict__ xl, float* __restrict__ gate, int C, int Cs, int V, int hw, int ncls,
                                float weight) {
+  // Cs: channels per CTA (a slab of the C channels, blockIdx.z selects it; Cs == C for C <= 512)
   extern __shared__ uint8_t gsm_raw[];
   __shared__ uint64_t bar;
   __shared__ float a_sm[64];
   const uint32_t base = (smem_u32(gsm_raw) + 1023u) & ~1023u;
   const int bv = blockIdx.y, b = bv / V, v = bv % V;
   const int p0 = blockIdx.x * 64;
-  const int nbox = C / 64;
+  const int c_base = blockIdx.z * Cs;
+  const int nbox = Cs / 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bar), 1);
@@ -303,7 +305,8 @@ __global__ void __launch_bounds__(256)
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_expect_tx(smem_u32(&bar), static_cast<uint32_t>(nbox) * 8192u);
-    for (int cb = 0; cb < nbox; ++cb) tma_load_4d(&maps.tm[v], smem_u32(&bar), base + cb * 8192, p0, cb * 64, b, 0);
+    for (int cb = 0; cb < nbox; ++cb)
+      tma_load_4d(&maps.tm[v], smem_u32(&bar), base + cb * 8192, p0, c_base + cb * 64, b, 0);
   }
   if (threadIdx.x < 64) {
     const int p = p0 + threadIdx.x;
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(256)
       const float m = sigmoidf_(lmax);  // max_c sigmoid(l_c) == sigmoid(max_c l_c)
       const float c = sigmoidf_(vp.ctr[v][static_cast<long long>(b) * hw + p]);
       a = sigmoidf_(weight * m * c);
-      gate[static_cast<long long>(bv) * hw + p] = a;
+      if (blockIdx.z == 0) gate[static_cast<long long>(bv) * hw + p] = a;
     }
     a_sm[threadIdx.x] = a;
   }
@@ -329,11 +332,11 @@ __global__ void __launch_bounds__(256)
   const int p = p0 + pl;
   const float a = a_sm[pl];
   const float2 a2 = make_float2(a, a);
-  const long long tok = (static_cast<long long>(b) * V * hw + static_cast<long long>(v) * hw + p) * C + (lane & 3) * 8;
-  const int ngrp = C / 32;
+  const long long tok = (static_cast<long long>(b) * V * hw + static_cast<long long>(v) * hw + p) * C + c_base + (lane & 3) * 8;
+  const int ngrp = Cs / 32;
 #pragma unroll 2
   for (int cg = 0; cg < ngrp; ++cg) {
-    const int ch = cg * 32 + co;                  // channel whose 8-position chunk this lane addresses
+    const int ch = cg * 32 + co;                  // channel (inside the slab) whose 8-position chunk this lane addresses
     const int row = ch & 63;
     const uint32_t addr = base + (ch >> 6) * 8192 + row * 128 + ((warp ^ (row & 7)) << 4);
     uint32_t r[4];
@@ -356,7 +359,9 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     gate_concat_bwd_tma_kernel(const __grid_constant__ ViewMaps maps, const ViewPtrs vp, const float* __restrict__ gate,
                                const bf16* __restrict__ dxg, const bf16* __restrict__ dxl, float* __restrict__ da_part,
-                               int C, int V, int hw) {
+                               int Ctot, int C, int V, int hw) {
+  // C: channels per CTA (a slab of the Ctot channels, blockIdx.z selects it; C == Ctot for Ctot <= 512): every loop
+  // below runs over the slab, only the global addresses know about Ctot; the gate gradient then has one slice per slab
   extern __shared__ uint8_t gsm_raw[];
   __shared__ uint64_t bar;
   __shared__ float a_sm[64];
@@ -364,6 +369,7 @@ __global__ void __launch_bounds__(256)
   uint8_t* gen = gsm_raw + (base - smem_u32(gsm_raw));
   const int bv = blockIdx.y, b = bv / V, v = bv % V;
   const int p0 = blockIdx.x * 64;
+  const int c_base = blockIdx.z * C;
   const int nbox = C / 64;
   const int valid = min(64, hw - p0);
   const uint32_t tile_bytes = 64u * C * 2u;       // one [64 positions][C] bf16 tile
@@ -379,10 +385,18 @@ __global__ void __launch_bounds__(256)
   if (threadIdx.x == 0) {
     const uint32_t tok_bytes = static_cast<uint32_t>(valid) * C * 2u;
     mbar_expect_tx(smem_u32(&bar), static_cast<uint32_t>(nbox) * 8192u + 2u * tok_bytes);
-    for (int cb = 0; cb < nbox; ++cb) tma_load_4d(&maps.tm[v], smem_u32(&bar), sF + cb * 8192, p0, cb * 64, b, 0);
-    const long long off = (static_cast<long long>(b) * V * hw + static_cast<long long>(v) * hw + p0) * C;
-    bulk_g2s_gate(sG, dxg + off, tok_bytes, smem_u32(&bar));
-    bulk_g2s_gate(sL, dxl + off, tok_bytes, smem_u32(&bar));
+    for (int cb = 0; cb < nbox; ++cb)
+      tma_load_4d(&maps.tm[v], smem_u32(&bar), sF + cb * 8192, p0, c_base + cb * 64, b, 0);
+    if (C == Ctot) {               // whole rows: the 64 token rows are one contiguous block
+      const long long off = (static_cast<long long>(b) * V * hw + static_cast<long long>(v) * hw + p0) * C;
+      bulk_g2s_gate(sG, dxg + off, tok_bytes, smem_u32(&bar));
+      bulk_g2s_gate(sL, dxl + off, tok_bytes, smem_u32(&bar));
+    }
+  }
+  if (C != Ctot && static_cast<int>(threadIdx.x) < valid) {     // a slab: one copy per token row and tensor
+    const long long off = (static_cast<long long>(b) * V * hw + static_cast<long long>(v) * hw + p0 + threadIdx.x) * Ctot + c_base;
+    bulk_g2s_gate(sG + threadIdx.x * C * 2u, dxg + off, static_cast<uint32_t>(C) * 2u, smem_u32(&bar));
+    bulk_g2s_gate(sL + threadIdx.x * C * 2u, dxl + off, static_cast<uint32_t>(C) * 2u, smem_u32(&bar));
   }
   if (threadIdx.x < 64) {
     const int p = p0 + threadIdx.x;
@@ -439,13 +453,14 @@ __global__ void __launch_bounds__(256)
     float da = acc.x + acc.y;
     da += __shfl_xor_sync(0xffffffffu, da, 1);
     da += __shfl_xor_sync(0xffffffffu, da, 2);
-    if ((lane & 3) == 0 && pl < valid) da_part[static_cast<long long>(bv) * hw + p0 + pl] = da;
+    if ((lane & 3) == 0 && pl < valid)
+      da_part[(static_cast<long long>(blockIdx.z) * gridDim.y + bv) * hw + p0 + pl] = da;
   }
   __syncthreads();
   {
     // phase B: [position][channel] -> NCHW.  ldmatrix rows = positions; thread T receives positions 8 (T%4) .. +7 of
     // channel 8 c8 + T/4
-    bf16* df4 = reinterpret_cast<bf16*>(vp.df4[v]) + static_cast<long long>(b) * C * hw;
+    bf16* df4 = reinterpret_cast<bf16*>(vp.df4[v]) + (static_cast<long long>(b) * Ctot + c_base) * hw;
     const int nunits = 2 * (C / 8);               // (32-position group, 8-channel chunk)
     for (int u = warp; u < nunits; u += 8) {
       const int pg = u & 1, c8 = u >> 1;
@@ -461,7 +476,8 @@ __global__ void __launch_bounds__(256)
 
 bool gate_tma_ok(int C, int hw, int io_dtype, int x_dtype, const void* const* f4, int V) {
   if (io_dtype != GLF_DTYPE_BF16 || x_dtype != GLF_DTYPE_BF16) return false;
-  if (C % 64 != 0 || C > 512 || hw % 8 != 0) return false;
+  if (C % 64 != 0 || hw % 8 != 0) return false;
+  if (C > 512 && C % 512 != 0) return false;      // wider rows are cut into 512- (forward) / 256-channel (backward) slabs
   for (int v = 0; v < V; ++v)
     if ((reinterpret_cast<uintptr_t>(f4[v]) & 15) != 0) return false;
   if (const char* e = getenv("GLF_DEBUG_GATE_SIMT")) return e[0] != '1';
@@ -775,11 +791,12 @@ int gate_concat_fwd(int B, int C, int V, int h, int w, int ncls, float weight, i
       if (rc) return rc;
     }
     for (int v = V; v < MAXV; ++v) maps.tm[v] = maps.tm[0];
-    const uint32_t smem = static_cast<uint32_t>(C / 64) * 8192u + 1024u;
+    const int Cs = C <= 512 ? C : 512;
+    const uint32_t smem = static_cast<uint32_t>(Cs / 64) * 8192u + 1024u;
     cudaError_t e = cudaFuncSetAttribute(gate_concat_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gate_fwd_tma)");
-    gate_concat_fwd_tma_kernel<<<dim3((hw + 63) / 64, B * V), 256, smem, stream>>>(
-        maps, vp, reinterpret_cast<bf16*>(xg), reinterpret_cast<bf16*>(xl), gate, C, V, hw, ncls, weight);
+    gate_concat_fwd_tma_kernel<<<dim3((hw + 63) / 64, B * V, C / Cs), 256, smem, stream>>>(
+        maps, vp, reinterpret_cast<bf16*>(xg), reinterpret_cast<bf16*>(xl), gate, C, Cs, V, hw, ncls, weight);
     return check_cuda(cudaGetLastError(), "gate_concat_fwd_tma launch");
   }
   dim3 grid((hw + 63) / 64, (C + 63) / 64, B * V);
@@ -817,16 +834,17 @@ int gate_concat_bwd(int B, int C, int V, int h, int w, int ncls, float weight, i
       if (rc) return rc;
     }
     for (int v = V; v < MAXV; ++v) maps.tm[v] = maps.tm[0];
-    const uint32_t smem = 3u * 64u * C * 2u + 1024u;
+    const int Cs = C <= 512 ? C : 256;
+    const uint32_t smem = 3u * 64u * Cs * 2u + 1024u;
     cudaError_t e = cudaFuncSetAttribute(gate_concat_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gate_bwd_tma)");
-    gate_concat_bwd_tma_kernel<<<dim3((hw + 63) / 64, B * V), 256, smem, stream>>>(
-        maps, vp, gate, reinterpret_cast<const bf16*>(dxg), reinterpret_cast<const bf16*>(dxl), da_part, C, V, hw);
+    gate_concat_bwd_tma_kernel<<<dim3((hw + 63) / 64, B * V, C / Cs), 256, smem, stream>>>(
+        maps, vp, gate, reinterpret_cast<const bf16*>(dxg), reinterpret_cast<const bf16*>(dxl), da_part, C, Cs, V, hw);
     int rc = check_cuda(cudaGetLastError(), "gate_concat_bwd_tma launch");
     if (rc) return rc;
     // (finishing the chain to the logits inside this kernel was tried: the extra ~2 us at the end of every CTA, two CTAs
     //  per SM and 22 waves, cost 50 us against the 11 us of the launch below)
-    nct = 1;   // the gate gradient is complete: one slice of the table
+    nct = C / Cs;   // one slice of the gate-gradient table per channel slab (one for C <= 512)
     const long long n = static_cast<long long>(B) * V * hw;
     gate_finish_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(vp, gate, da_part, nct, B * V, V, hw,
                                                                                   ncls, weight);

@@ -428,11 +428,12 @@ def test_dict_api_backward_reads_per_view_gradients_in_place(h, w):
             assert (a - b).abs().max().item() <= 2e-2 * max(a.abs().max().item(), 1e-6) + 1e-7
 
 
-@pytest.mark.parametrize("C,V,h,w", [(512, 2, 9, 8), (2048, 3, 6, 6), (768, 2, 5, 7)])
+@pytest.mark.parametrize("C,V,h,w", [(512, 2, 9, 8), (2048, 3, 6, 6), (768, 2, 5, 7), (1024, 2, 10, 8), (2048, 3, 8, 8)])
 def test_wide_channel_fused_node_against_oracle(C, V, h, w):
     """Channel counts above 256: the fused node still runs both blocks' LayerNorms in one pass forward (sliced rows,
-    ln_pair_fwd_ring_kernel) and returns the MGFM part beside the sum; seeded oracle comparison of outputs, parts and
-    every gradient."""
+    ln_pair_fwd_ring_kernel) and returns the MGFM part beside the sum; the gate / concat kernels cut rows wider than 512
+    channels into slabs (h*w a multiple of 8: TMA transposition kernels; otherwise the SIMT ones); seeded oracle
+    comparison of outputs, parts and every gradient."""
     B = 2
     pg = O.init_params(C, seed=41, randomize_affine=True)
     pl = O.init_params(C, seed=42, randomize_affine=True)
