@@ -435,6 +435,10 @@ def run_ours(args):
         sec = gram_probe(dev, clips, C, pk)
         gr = gram_family_probe(dev, clips, C, pk, sec["ms_per_launch"])
         fam = {"roofline_dx_gemm": gm, "roofline_ln_bwd": ln, "roofline_gram": gr}
+        if C == 256:
+            ug = u_gemm_probe(dev, clips, C, pk)
+            ug["launches_per_step"] = 2
+            fam["roofline_u_gemm"] = ug
         for v in fam.values():
             v["share_of_step"] = round(v["launches_per_step"] * v["ms_per_launch"] / burst_ms, 3)
             v["share_note"] = "launches_per_step x ms_per_launch / burst ms_per_step (both timed at boost clocks)"
@@ -671,6 +675,49 @@ def dx_gemm_probe(dev, clips, C, pk):
             "achieved": round(ach, 1), "peak": pk["hbm_gbs"], "peak_source": pk["source"], "unit": "GB/s",
             "frac": round(ach / pk["hbm_gbs"], 4), "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
             "ms_per_launch": round(ms, 4), "inputs": "617 MB per launch, larger than the 126 MB L2"}
+
+
+def u_gemm_probe(dev, clips, C, pk):
+    """The forward's big product, timed alone: U_b = X_b Q_b^T + c_b (K = C, one [C x C] operand per sequence kept resident
+    in shared memory, per-sequence bias, BatchNorm column statistics in the epilogue; glf_gemm3.cu).  HBM-bound: reads X,
+    writes U = 2 bf16 passes over [rows, C]."""
+    import ctypes as Ct
+    from glfusion_b200 import _lib as L
+    lib = L.load()
+    B, N = clips * F, V * HH * WW
+    A = torch.randn(B, N, C, device=dev).to(torch.bfloat16)
+    Bm = (torch.randn(B, C, C, device=dev) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(C, device=dev)
+    D = torch.empty(B, N, C, device=dev, dtype=torch.bfloat16)
+    cs = torch.zeros(B * ((N + 127) // 128) * 4, 2, C, device=dev)
+    stream = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def launch():
+        L.check(lib.glf_gemm_bf16(L.ptr(A), L.ptr(Bm), L.ptr(D), N, C, C, B, 0, 0, C, C, C, N * C, C * C, N * C,
+                                  L.ptr(bias), 1.0, None, C, N * C, 0, 1, L.ptr(cs), stream))
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 10
+    e0.record()
+    for _ in range(n):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    alg_bytes = 2 * B * N * C * 2
+    ach = alg_bytes / (ms * 1e-3) / 1e9
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    traffic = None
+    if os.path.exists(tp):
+        t = json.load(open(tp)).get("gemm_u", {})
+        if t.get("rows") == B * N and t.get("C") == C:
+            traffic = int(t["traffic_bytes"])
+    return {"bound": "hbm", "kernel": "gemm_bres_kernel (U = X Q^T + c, K = C, per-sequence B operand resident in shared memory)",
+            "achieved": round(ach, 1), "peak": pk["hbm_gbs"], "peak_source": pk["source"], "unit": "GB/s",
+            "frac": round(ach / pk["hbm_gbs"], 4), "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
+            "ms_per_launch": round(ms, 4), "inputs": "206 MB per launch, larger than the 126 MB L2"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
