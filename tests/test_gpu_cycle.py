@@ -152,3 +152,24 @@ def test_install_trainer_replaces_the_two_methods_with_the_same_call_shape():
     np.random.seed(int(s["np_seed"]))
     loss = t.seg_cycle(torch.from_numpy(s["feat"]).to(DEV), target_region=16, cyc_off=2, chunk_size=3, temperature=10)
     assert abs(loss.item() - float(s["loss"])) <= TOL * abs(float(s["loss"]))
+
+
+def test_cycle_loss_odd_channel_count_and_bf16_features():
+    """C = 100 (not a multiple of the warp width) and bf16 features: the loss is computed in fp32 from the rounded values
+    and the gradient comes back in the features' dtype."""
+    T, Cn, R, off, ch = 30, 100, 12, 1, 2
+    g = torch.Generator().manual_seed(77)
+    feat = torch.cumsum(torch.randn(T, Cn, generator=g) * 0.4, 0)
+    x = feat.to(DEV).requires_grad_(True)
+    loss = cycle.dense_seg_cycle(x, R, off, ch, 5.0)
+    loss.backward()
+    lo, go = CO.dense_seg_cycle(feat.numpy(), R, off, ch, 5.0)
+    assert abs(loss.item() - lo) <= TOL * abs(lo)
+    assert np.abs(x.grad.cpu().numpy() - go).max() <= TOL * np.abs(go).max()
+    xb = feat.to(DEV).to(torch.bfloat16).requires_grad_(True)
+    lb = cycle.dense_seg_cycle(xb, R, off, ch, 5.0)
+    lb.backward()
+    lo2, go2 = CO.dense_seg_cycle(xb.detach().float().cpu().numpy(), R, off, ch, 5.0)
+    assert xb.grad.dtype == torch.bfloat16
+    assert abs(lb.item() - lo2) <= TOL * abs(lo2)
+    assert np.abs(xb.grad.float().cpu().numpy() - go2).max() <= 1e-2 * np.abs(go2).max()
